@@ -1,0 +1,147 @@
+/* kgan.h - C ABI of libkgan.so: the B200 (sm_100a) kernels behind the Kinetic-GAN ST-GCN hot path.
+ *
+ * The reference (DegardinBruno/Kinetic-GAN) has no FFI of its own: every arithmetic call site is a
+ * PyTorch operator.  Each entry point below names the reference call sites it replaces (paths are
+ * relative to the reference root).  Conventions for ALL entry points:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *     (torch's allocator); the library borrows it for the duration of the call and keeps nothing;
+ *   - tensors are float32, dense, NCHW-contiguous (N, C, T, V); a "plane" is the T*V block of one
+ *     (n, c) pair, P = T*V;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant per
+ *     stream (no global mutable state besides the per-thread last-error string);
+ *   - return value: 0 = ok, non-zero = error (message via kgan_last_error()); nothing throws
+ *     across the boundary; there is NO CPU fallback.
+ */
+#ifndef KGAN_H_
+#define KGAN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGAN_MAX_TAPS 16
+
+enum { KGAN_ACT_NONE = 0, KGAN_ACT_LRELU = 1 /* slope 0.2 */, KGAN_ACT_TANH = 2 };
+enum { KGAN_PREC_FP32 = 0 /* SIMT fp32 FMA */, KGAN_PREC_TF32 = 1 /* tcgen05 kind::tf32, fp32 accumulate */ };
+
+/* Geometry of one "tap convolution": the single GEMM-shaped primitive that the graph conv, the
+ * temporal conv, the residual 1x1 conv, the mapping MLP and the critic head all reduce to, in
+ * forward, data-gradient and weight-gradient form.
+ *
+ *   out[n, out_ch0 + oc, p] = act( bias[oc] + add[n, oc, p]
+ *        + sum_{tap < ntap} sum_{ic < ck}  W[w_base + tap_w_off[tap] + woff(oc) + ic*w_ic]
+ *                                        * in[n, in_ch0 + tap_in_ch[tap] + ic, pmap[tap_row[tap]*p_out + p]] )
+ *   woff(oc) = w_oc_blk ? (oc / w_oc_blk) * w_ocblk + (oc % w_oc_blk) * w_oc : oc * w_oc
+ *   pmap entries < 0 contribute zero (temporal zero padding, dropped joints / frames).
+ * `groups` > 1 repeats the whole operation with in_ch0 += g_in, out_ch0 += g_out, w_base += g_w.
+ */
+typedef struct kgan_tapconv_desc {
+    int32_t n;                 /* samples */
+    int32_t c_in_total;        /* channels of the `in` tensor  */
+    int32_t p_in;              /* plane size of `in`  (T_in * V_in)  */
+    int32_t c_out_total;       /* channels of the `out` tensor */
+    int32_t p_out;             /* plane size of `out` (T_out * V_out) */
+    int32_t ntap;              /* number of taps (<= KGAN_MAX_TAPS) */
+    int32_t ck;                /* contraction channels per tap */
+    int32_t co;                /* output channels computed per group */
+    int32_t groups;            /* >= 1 */
+    int32_t g_in, g_out;       /* per-group channel steps */
+    int64_t g_w;               /* per-group weight step (elements) */
+    int64_t w_oc, w_ic;        /* weight strides (elements) */
+    int32_t w_oc_blk;          /* 0 = single-level oc addressing */
+    int64_t w_ocblk;
+    int32_t tap_in_ch[KGAN_MAX_TAPS];
+    int64_t tap_w_off[KGAN_MAX_TAPS];
+    int32_t tap_row[KGAN_MAX_TAPS];  /* row of pmap used by the tap */
+    int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */
+    int32_t precision;         /* KGAN_PREC_* */
+} kgan_tapconv_desc;
+
+/* Version / diagnostics. */
+int kgan_version(void);
+const char* kgan_last_error(void);
+/* 1 if the device behind the current context is sm_100 (B200); kernels refuse to run otherwise. */
+int kgan_device_ok(void);
+
+/* ---- tap convolution ---------------------------------------------------------------------------
+ * Replaces: nn.Conv2d 1x1 of the graph conv (models/init_gan/tgcn.py:48,61) once the adjacency has been
+ * applied by kgan_adjmix_fwd; the temporal conv (models/generator.py:134-140, models/discriminator.py:99-105);
+ * the residual 1x1 conv (generator.py:155-159, discriminator.py:115-120); nn.Linear of the mapping network
+ * (generator.py:28, applied at :84-85) and of the critic head (discriminator.py:50,72); the fused epilogue
+ * replaces the bias add, `tcn(x) + res` (generator.py:176, discriminator.py:130), downsample_s
+ * (discriminator.py:139-142), F.interpolate nearest (discriminator.py:134) and LeakyReLU (discriminator.py:136).
+ * The data gradient (convolution_backward w.r.t. input) is the same entry point called with the transposed
+ * weight strides and the inverse position map; see kinetic-gan_b200/geometry.py.
+ * `bias` (co floats) and `add` (same shape as out) may be NULL. */
+int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, const float* w, const int32_t* pmap,
+                     const float* bias, const float* add, float* out, void* stream);
+
+/* dW[...same addressing as W...] = sum_{n,p} gout[n, out_ch0+oc, p] * in[n, in_ch0+tap_in_ch+ic, pmap[..]]
+ * Replaces convolution_backward w.r.t. weight for the same call sites, and (called with swapped roles)
+ * the weight terms of _convolution_double_backward used by the gradient penalty (kinetic-gan.py:104-113,154).
+ * `dw` must hold `dw_numel` floats and is overwritten (zeroed, then accumulated with fp32 atomics). */
+int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
+                       float* dw, int64_t dw_numel, void* stream);
+
+/* ---- adjacency product ---------------------------------------------------------------------------
+ * out[r, k, w] = sum_v x[r, v] * A[k, v, w]      rows r = (n, c, t); written as (N, K*C, T, W)
+ * Replaces torch.einsum('nkctv,kvw->nctw') at tgcn.py:66 (applied before the 1x1 conv, which commutes with it
+ * because gcn.conv has bias=False, tgcn.py:44,55).  A is (K, V, W) - rectangular so that upsample_s
+ * (generator.py:185-200) can be folded into it. */
+int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream);
+/* gx[r, v] = sum_k sum_w gout[r, k, w] * A[k, v, w] */
+int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream);
+/* gA[k, v, w] = sum_r x[r, v] * gout[r, k, w]  (gA overwritten) */
+int kgan_adjmix_bwd_a(const float* x, const float* gout, float* gA, int n, int c, int t, int v, int w, int k, void* stream);
+
+/* ---- pointwise epilogues -------------------------------------------------------------------------
+ * out[n,c,p] = act( a[n,c,p] + b[n,c,p] + bias[c] + nw[c] * noise[n,p] ); b, bias, (nw,noise) may be NULL.
+ * Replaces `tcn(x) + res`, NoiseInjection (generator.py:12-19,179-180) and LeakyReLU/Tanh (generator.py:182). */
+int kgan_epilogue_fwd(const float* a, const float* b, const float* bias, const float* nw, const float* noise,
+                      float* out, int n, int c, int p, int act, void* stream);
+/* gz = gout * act'(out)   (LeakyReLU: out > 0 ? 1 : 0.2;  tanh: 1 - out^2).  Replaces leaky_relu_backward /
+ * tanh_backward; also the second-order use of the same mask in the gradient penalty. */
+int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, void* stream);
+/* out[c] = sum_{n,p} g[n,c,p] * (mul ? mul[n,p] : 1).  Bias gradients and NoiseInjection.weight gradient. */
+int kgan_chan_reduce(const float* g, const float* mul, float* out, int n, int c, int p, void* stream);
+
+/* ---- plane gather / scatter ----------------------------------------------------------------------
+ * out[r, q] = sum_{j<J} wgt[q*J+j] * x[r, idx[q*J+j]]   (idx < 0 skipped); r over N*C planes.
+ * Replaces upsample_s + F.interpolate in G (generator.py:170-172,185-200), downsample_s + F.interpolate on the
+ * identity residual in D (discriminator.py:128-134), avg_pool2d (discriminator.py:68), and their backward passes
+ * (the transposed table). */
+int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out,
+                    int j, void* stream);
+
+/* ---- label planes (discriminator.py:57-60) -------------------------------------------------------
+ * out[n, c, p] = c < n_cls ? e[n, c] : x[n, c - n_cls, p] */
+int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, void* stream);
+/* ge[n, c] = sum_p g[n, c, p] (c < n_cls);  gx[n, c, p] = g[n, n_cls + c, p].  Either output may be NULL. */
+int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, void* stream);
+
+/* ---- BatchNorm2d, training mode (generator.py:142,160) ---------------------------------------------
+ * stats: mean[c], rstd[c] from biased variance over (n, p); running stats updated in place with `momentum`
+ * (unbiased variance), exactly nn.BatchNorm2d defaults.  running_* may be NULL. */
+int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean, float* running_var, int n, int c, int p,
+                  float eps, float momentum, void* stream);
+/* y = (x - mean[c]) * rstd[c] * gamma[c] + beta[c]  (also eval mode with running stats folded by the caller) */
+int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                  int n, int c, int p, void* stream);
+/* gx, ggamma[c], gbeta[c] of training-mode BN */
+int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx,
+                float* ggamma, float* gbeta, int n, int c, int p, void* stream);
+
+/* ---- fused Adam over a flat parameter buffer (torch.optim.Adam, kinetic-gan.py:77-78,155,174) ----
+ * g is multiplied by grad_scale first (1/world_size after the DDP sum all-reduce). `step` is 1-based. */
+int kgan_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float b1, float b2, float eps,
+                   int step, float grad_scale, void* stream);
+
+/* out = alpha * x + (1 - alpha) * y with alpha per sample (kinetic-gan.py:100); per_sample = C*T*V */
+int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGAN_H_ */

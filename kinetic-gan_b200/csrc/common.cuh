@@ -1,0 +1,50 @@
+// Shared helpers for libkgan.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/kgan.h"
+
+namespace kgan {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return 2;
+    }
+    return 0;
+}
+
+#define KGAN_REQUIRE(cond, ...)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            kgan::set_error(__VA_ARGS__); \
+            return 1;                    \
+        }                                \
+    } while (0)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == KGAN_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+    if (act == KGAN_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+__device__ __forceinline__ int64_t w_oc_offset(const kgan_tapconv_desc& d, int oc) {
+    return d.w_oc_blk ? (int64_t)(oc / d.w_oc_blk) * d.w_ocblk + (int64_t)(oc % d.w_oc_blk) * d.w_oc : (int64_t)oc * d.w_oc;
+}
+
+constexpr int kNumSMs = 148;   // B200
+
+// tcgen05 path (tapconv_umma.cu); returns -1 when the shape is not eligible (caller uses the SIMT path)
+int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* w, const int32_t* pmap, const float* bias,
+                     const float* add, float* out, cudaStream_t stream);
+
+}  // namespace kgan

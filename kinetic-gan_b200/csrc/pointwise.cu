@@ -1,0 +1,440 @@
+// Memory-bound kernels of the ST-GCN hot path: adjacency product, fused epilogues, plane gathers,
+// label planes, BatchNorm, Adam.  All are HBM-bound streaming kernels: lanes run along the contiguous
+// (t, v) plane axis, grids are sized in multiples of the SM count.  See include/kgan.h for semantics.
+#include "common.cuh"
+
+namespace kgan {
+
+constexpr int PT = 256;
+
+static inline int grid_for(int64_t work, int per_block = PT, int max_waves = 16) {
+    int64_t b = ceil_div64(work, per_block);
+    int64_t cap = (int64_t)kNumSMs * max_waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in every thread; `red` holds >= 32 floats
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjacency product
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) adjmix_fwd_k(const float* __restrict__ x, const float* __restrict__ A, float* __restrict__ out,
+                                                    int n, int c, int t, int v, int w, int k) {
+    extern __shared__ float As[];   // [k][v][w]
+    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[i] = A[i];
+    __syncthreads();
+    const int64_t total = (int64_t)n * k * c * t * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ww = (int)(i % w);
+        int64_t r = i / w;
+        const int tt = (int)(r % t);
+        r /= t;
+        const int kc = (int)(r % ((int64_t)k * c));
+        const int nn = (int)(r / ((int64_t)k * c));
+        const int kk = kc / c, cc = kc - kk * c;
+        const float* xr = x + (((int64_t)nn * c + cc) * t + tt) * v;
+        const float* a = As + (kk * v) * w + ww;
+        float acc = 0.f;
+        for (int j = 0; j < v; ++j) acc = fmaf(__ldg(xr + j), a[j * w], acc);
+        out[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(PT) adjmix_bwd_x_k(const float* __restrict__ g, const float* __restrict__ A, float* __restrict__ gx,
+                                                      int n, int c, int t, int v, int w, int k) {
+    extern __shared__ float As[];   // [k][v][wp], wp odd to spread banks across v
+    const int wp = w | 1;
+    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[(i / w) * wp + (i % w)] = A[i];
+    __syncthreads();
+    const int64_t total = (int64_t)n * c * t * v;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int vv = (int)(i % v);
+        int64_t r = i / v;
+        const int tt = (int)(r % t);
+        r /= t;
+        const int cc = (int)(r % c);
+        const int nn = (int)(r / c);
+        float acc = 0.f;
+        for (int kk = 0; kk < k; ++kk) {
+            const float* gr = g + (((int64_t)nn * k * c + (int64_t)kk * c + cc) * t + tt) * w;
+            const float* a = As + (kk * v + vv) * wp;
+            for (int j = 0; j < w; ++j) acc = fmaf(__ldg(gr + j), a[j], acc);
+        }
+        gx[i] = acc;
+    }
+}
+
+// gA[k,v,w] = sum over rows of x[row, v] * g[row(k), w].  Each CTA stages ROWS rows and every thread owns
+// a strided subset of the k*v*w outputs; partial sums merged with one atomic per output per CTA.
+constexpr int AROWS = 32;
+__global__ void __launch_bounds__(PT) adjmix_bwd_a_k(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gA,
+                                                      int n, int c, int t, int v, int w, int k, int64_t rows_per_cta) {
+    extern __shared__ float sm[];
+    float* xs = sm;                       // [AROWS][v]
+    float* gs = sm + AROWS * v;           // [k][AROWS][w]
+    const int64_t rows = (int64_t)n * c * t;
+    const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta, rend = min(rows, rbeg + rows_per_cta);
+    const int nout = k * v * w;
+    constexpr int MAXO = 8;               // outputs per thread (k*v*w <= 2048)
+    float acc[MAXO];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
+    for (int64_t r0 = rbeg; r0 < rend; r0 += AROWS) {
+        const int nr = (int)min((int64_t)AROWS, rend - r0);
+        for (int i = threadIdx.x; i < nr * v; i += blockDim.x) xs[i] = __ldg(x + r0 * v + i);
+        for (int i = threadIdx.x; i < k * nr * w; i += blockDim.x) {
+            const int ww = i % w, rr = (i / w) % nr, kk = i / (w * nr);
+            const int64_t row = r0 + rr;                       // (n, c, t)
+            const int tt = (int)(row % t);
+            const int64_t nc = row / t;
+            const int cc = (int)(nc % c), nn = (int)(nc / c);
+            gs[(kk * AROWS + rr) * w + ww] = __ldg(g + (((int64_t)nn * k * c + (int64_t)kk * c + cc) * t + tt) * w + ww);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) {
+            const int oi = threadIdx.x + o * PT;
+            if (oi < nout) {
+                const int ww = oi % w, vv = (oi / w) % v, kk = oi / (w * v);
+                float a = acc[o];
+                for (int rr = 0; rr < nr; ++rr) a = fmaf(xs[rr * v + vv], gs[(kk * AROWS + rr) * w + ww], a);
+                acc[o] = a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+        const int oi = threadIdx.x + o * PT;
+        if (oi < nout) atomicAdd(gA + oi, acc[o]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointwise epilogues
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
+                                                      const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
+                                                      int n, int c, int p, int act) {
+    const int64_t total = (int64_t)n * c * p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pp = (int)(i % p);
+        const int64_t nc = i / p;
+        const int cc = (int)(nc % c);
+        const int64_t nn = nc / c;
+        float v = a[i];
+        if (b) v += b[i];
+        if (bias) v += __ldg(bias + cc);
+        if (nw) v = fmaf(__ldg(nw + cc), __ldg(noise + nn * p + pp), v);
+        out[i] = apply_act(v, act);
+    }
+}
+
+__global__ void __launch_bounds__(PT) act_bwd_k(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ gz, int64_t numel,
+                                                 int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        const float y = o[i];
+        float m = 1.f;
+        if (act == KGAN_ACT_LRELU) m = y > 0.f ? 1.f : 0.2f;
+        else if (act == KGAN_ACT_TANH) m = 1.f - y * y;
+        gz[i] = go[i] * m;
+    }
+}
+
+// out[c] += sum over a slice of samples; grid (c, slices)
+__global__ void __launch_bounds__(PT) chan_reduce_k(const float* __restrict__ g, const float* __restrict__ mul, float* __restrict__ out, int n,
+                                                     int c, int p, int n_per_slice) {
+    __shared__ float red[32];
+    const int cc = blockIdx.x;
+    const int nbeg = blockIdx.y * n_per_slice, nend = min(n, nbeg + n_per_slice);
+    float acc = 0.f;
+    const int64_t cnt = (int64_t)(nend - nbeg) * p;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int nn = nbeg + (int)(i / p), pp = (int)(i % p);
+        float v = __ldg(g + ((int64_t)nn * c + cc) * p + pp);
+        if (mul) v *= __ldg(mul + (int64_t)nn * p + pp);
+        acc += v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out + cc, acc);
+}
+
+__global__ void __launch_bounds__(PT) plane_spmm_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                                                    float* __restrict__ out, int64_t rows, int p_in, int p_out, int jn) {
+    const int64_t total = rows * p_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % p_out);
+        const int64_t r = i / p_out;
+        const float* xr = x + r * p_in;
+        float acc = 0.f;
+        for (int j = 0; j < jn; ++j) {
+            const int s = __ldg(idx + q * jn + j);
+            if (s >= 0) acc = fmaf(__ldg(wgt + q * jn + j), __ldg(xr + s), acc);
+        }
+        out[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(PT) label_concat_k(const float* __restrict__ e, const float* __restrict__ x, float* __restrict__ out, int n,
+                                                      int ncls, int c, int p) {
+    const int ct = ncls + c;
+    const int64_t total = (int64_t)n * ct * p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pp = (int)(i % p);
+        const int64_t nc = i / p;
+        const int cc = (int)(nc % ct);
+        const int64_t nn = nc / ct;
+        out[i] = cc < ncls ? __ldg(e + nn * ncls + cc) : __ldg(x + (nn * c + (cc - ncls)) * p + pp);
+    }
+}
+
+// one warp per (n, channel) plane of the label part; remaining threads copy the data part
+__global__ void __launch_bounds__(PT) label_split_k(const float* __restrict__ g, float* __restrict__ ge, float* __restrict__ gx, int n, int ncls,
+                                                     int c, int p) {
+    const int ct = ncls + c;
+    if (ge) {
+        const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < (int64_t)n * ncls; r += warps) {
+            const int64_t nn = r / ncls;
+            const int cc = (int)(r % ncls);
+            const float* gp = g + (nn * ct + cc) * p;
+            float acc = 0.f;
+            for (int i = lane; i < p; i += 32) acc += __ldg(gp + i);
+            acc = warp_sum(acc);
+            if (lane == 0) ge[r] = acc;
+        }
+    }
+    if (gx) {
+        const int64_t total = (int64_t)n * c * p;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int pp = (int)(i % p);
+            const int64_t nc = i / p;
+            const int cc = (int)(nc % c);
+            const int64_t nn = nc / c;
+            gx[i] = __ldg(g + (nn * ct + ncls + cc) * p + pp);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm2d (training): one CTA per channel
+// ------------------------------------------------------------------------------------------------
+constexpr int BNT = 512;
+__global__ void __launch_bounds__(BNT) bn_stats_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
+                                                   float* __restrict__ rm, float* __restrict__ rv, int n, int c, int p, float eps, float mom) {
+    __shared__ float red[32];
+    const int cc = blockIdx.x;
+    const int64_t cnt = (int64_t)n * p;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) s += __ldg(x + ((i / p) * c + cc) * p + (i % p));
+    const float mu = block_sum(s, red) / (float)cnt;
+    float q = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const float dlt = __ldg(x + ((i / p) * c + cc) * p + (i % p)) - mu;
+        q = fmaf(dlt, dlt, q);
+    }
+    const float var = block_sum(q, red) / (float)cnt;
+    if (threadIdx.x == 0) {
+        mean[cc] = mu;
+        rstd[cc] = rsqrtf(var + eps);
+        if (rm) rm[cc] = (1.f - mom) * rm[cc] + mom * mu;
+        if (rv) rv[cc] = (1.f - mom) * rv[cc] + mom * var * ((float)cnt / (float)max((int64_t)1, cnt - 1));
+    }
+}
+
+__global__ void __launch_bounds__(PT) bn_apply_k(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int n, int c,
+                                                  int p) {
+    const int64_t total = (int64_t)n * c * p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)((i / p) % c);
+        const float sc = __ldg(rstd + cc) * __ldg(gamma + cc);
+        y[i] = fmaf(x[i] - __ldg(mean + cc), sc, __ldg(beta + cc));
+    }
+}
+
+__global__ void __launch_bounds__(BNT) bn_bwd_k(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
+                                                 const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ gx,
+                                                 float* __restrict__ ggamma, float* __restrict__ gbeta, int n, int c, int p) {
+    __shared__ float red[32];
+    const int cc = blockIdx.x;
+    const int64_t cnt = (int64_t)n * p;
+    const float mu = mean[cc], rs = rstd[cc];
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int64_t o = ((i / p) * c + cc) * p + (i % p);
+        const float g = __ldg(gy + o);
+        s1 += g;
+        s2 = fmaf(g, (__ldg(x + o) - mu) * rs, s2);
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        ggamma[cc] = s2;
+        gbeta[cc] = s1;
+    }
+    const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt, sc = gamma[cc] * rs;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int64_t o = ((i / p) * c + cc) * p + (i % p);
+        const float xh = (__ldg(x + o) - mu) * rs;
+        gx[o] = sc * (__ldg(gy + o) - m1 - xh * m2);
+    }
+}
+
+__global__ void __launch_bounds__(PT) adam_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                              int64_t numel, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2, float gs) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = g[i] * gs;
+        const float mi = b1 * m[i] + (1.f - b1) * gr;
+        const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+}
+
+__global__ void __launch_bounds__(PT) interpolate_k(const float* __restrict__ alpha, const float* __restrict__ x, const float* __restrict__ y,
+                                                     float* __restrict__ out, int n, int64_t per) {
+    const int64_t total = (int64_t)n * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = __ldg(alpha + i / per);
+        out[i] = a * x[i] + (1.f - a) * y[i];
+    }
+}
+
+}  // namespace kgan
+
+using namespace kgan;
+
+extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
+    KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 8192, "adjmix_fwd: bad shape");
+    const int64_t total = (int64_t)n * k * c * t * w;
+    adjmix_fwd_k<<<grid_for(total), PT, sizeof(float) * k * v * w, (cudaStream_t)stream>>>(x, A, out, n, c, t, v, w, k);
+    return check_launch("adjmix_fwd");
+}
+
+extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream) {
+    KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * (w | 1) <= 8192, "adjmix_bwd_x: bad shape");
+    const int64_t total = (int64_t)n * c * t * v;
+    adjmix_bwd_x_k<<<grid_for(total), PT, sizeof(float) * k * v * (w | 1), (cudaStream_t)stream>>>(g, A, gx, n, c, t, v, w, k);
+    return check_launch("adjmix_bwd_x");
+}
+
+extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
+    KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 8 * PT, "adjmix_bwd_a: k*v*w too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
+    const int64_t rows = (int64_t)n * c * t;
+    int64_t ctas = ceil_div64(rows, 4 * AROWS);
+    if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
+    const int64_t per = ceil_div64(ceil_div64(rows, ctas), AROWS) * AROWS;
+    ctas = ceil_div64(rows, per);
+    const size_t smem = sizeof(float) * (AROWS * v + k * AROWS * w);
+    adjmix_bwd_a_k<<<(unsigned)ctas, PT, smem, s>>>(x, g, gA, n, c, t, v, w, k, per);
+    return check_launch("adjmix_bwd_a");
+}
+
+extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bias, const float* nw, const float* noise, float* out,
+                                 int n, int c, int p, int act, void* stream) {
+    KGAN_REQUIRE(a && out && n > 0 && c > 0 && p > 0, "epilogue_fwd: bad argument");
+    KGAN_REQUIRE((nw == nullptr) == (noise == nullptr), "epilogue_fwd: nw and noise go together");
+    epilogue_fwd_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act);
+    return check_launch("epilogue_fwd");
+}
+
+extern "C" int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, void* stream) {
+    KGAN_REQUIRE(gout && out && gz && numel > 0, "act_bwd: bad argument");
+    act_bwd_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(gout, out, gz, numel, act);
+    return check_launch("act_bwd");
+}
+
+extern "C" int kgan_chan_reduce(const float* g, const float* mul, float* out, int n, int c, int p, void* stream) {
+    KGAN_REQUIRE(g && out && n > 0 && c > 0 && p > 0, "chan_reduce: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(out, 0, sizeof(float) * c, s) != cudaSuccess) return check_launch("chan_reduce memset");
+    int slices = ceil_div(4 * kNumSMs, c);
+    if (slices > n) slices = n;
+    if (slices > 65535) slices = 65535;
+    const int per = ceil_div(n, slices);
+    slices = ceil_div(n, per);
+    chan_reduce_k<<<dim3(c, slices), PT, 0, s>>>(g, mul, out, n, c, p, per);
+    return check_launch("chan_reduce");
+}
+
+extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out, int j,
+                               void* stream) {
+    KGAN_REQUIRE(x && idx && wgt && out && rows > 0 && p_in > 0 && p_out > 0 && j > 0, "plane_spmm: bad argument");
+    plane_spmm_k<<<grid_for(rows * p_out), PT, 0, (cudaStream_t)stream>>>(x, idx, wgt, out, rows, p_in, p_out, j);
+    return check_launch("plane_spmm");
+}
+
+extern "C" int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, void* stream) {
+    KGAN_REQUIRE(e && x && out && n > 0 && n_cls > 0 && c > 0 && p > 0, "label_concat: bad argument");
+    label_concat_k<<<grid_for((int64_t)n * (n_cls + c) * p), PT, 0, (cudaStream_t)stream>>>(e, x, out, n, n_cls, c, p);
+    return check_launch("label_concat");
+}
+
+extern "C" int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, void* stream) {
+    KGAN_REQUIRE(g && (ge || gx) && n > 0 && n_cls > 0 && c > 0 && p > 0, "label_split: bad argument");
+    const int64_t work = (int64_t)n * (n_cls * 32 > c * p ? n_cls * 32 : c * p);
+    label_split_k<<<grid_for(work), PT, 0, (cudaStream_t)stream>>>(g, ge, gx, n, n_cls, c, p);
+    return check_launch("label_split");
+}
+
+extern "C" int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean, float* running_var, int n, int c, int p, float eps,
+                             float momentum, void* stream) {
+    KGAN_REQUIRE(x && mean && rstd && n > 0 && c > 0 && p > 0, "bn_stats: bad argument");
+    bn_stats_k<<<c, BNT, 0, (cudaStream_t)stream>>>(x, mean, rstd, running_mean, running_var, n, c, p, eps, momentum);
+    return check_launch("bn_stats");
+}
+
+extern "C" int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int n, int c,
+                             int p, void* stream) {
+    KGAN_REQUIRE(x && mean && rstd && gamma && beta && y && n > 0 && c > 0 && p > 0, "bn_apply: bad argument");
+    bn_apply_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(x, mean, rstd, gamma, beta, y, n, c, p);
+    return check_launch("bn_apply");
+}
+
+extern "C" int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx, float* ggamma,
+                           float* gbeta, int n, int c, int p, void* stream) {
+    KGAN_REQUIRE(gy && x && mean && rstd && gamma && gx && ggamma && gbeta && n > 0 && c > 0 && p > 0, "bn_bwd: bad argument");
+    bn_bwd_k<<<c, BNT, 0, (cudaStream_t)stream>>>(gy, x, mean, rstd, gamma, gx, ggamma, gbeta, n, c, p);
+    return check_launch("bn_bwd");
+}
+
+extern "C" int kgan_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float b1, float b2, float eps, int step,
+                              float grad_scale, void* stream) {
+    KGAN_REQUIRE(p && g && m && v && numel > 0 && step >= 1, "adam_step: bad argument");
+    const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    adam_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(p, g, m, v, numel, (float)(lr / bc1), b1, b2, eps, (float)(1.0 / sqrt(bc2)),
+                                                           grad_scale);
+    return check_launch("adam_step");
+}
+
+extern "C" int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, void* stream) {
+    KGAN_REQUIRE(alpha && x && y && out && n > 0 && per_sample > 0, "interpolate: bad argument");
+    interpolate_k<<<grid_for((int64_t)n * per_sample), PT, 0, (cudaStream_t)stream>>>(alpha, x, y, out, n, per_sample);
+    return check_launch("interpolate");
+}

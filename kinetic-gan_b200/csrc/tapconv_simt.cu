@@ -1,0 +1,244 @@
+// Tap convolution, fp32 SIMT path (KGAN_PREC_FP32): exact-fp32 FMA GEMM used for the <=1e-5 parity
+// path, for the small / ragged layers (C <= 9 tail of G, D0's 3 input channels, critic head) and as the
+// on-device cross-check of the tcgen05 path.  See include/kgan.h for the operator definition.
+//
+// GEMM view: rows = flattened output positions (n, p), columns = output channels,
+// contraction = (tap, input channel).  Positions are contiguous in memory for a fixed channel (NCHW), so
+// lanes run along positions for every global load/store (coalesced 128 B segments).
+#include "common.cuh"
+
+namespace kgan {
+
+constexpr int BM = 128;   // positions per CTA
+constexpr int BK = 16;    // contraction slice
+constexpr int TM = 8;     // positions per thread
+constexpr int NT = 256;   // threads per CTA
+
+template <int TN>   // output channels per thread; BN = 16 * TN
+__global__ void __launch_bounds__(NT) tapconv_fwd_simt(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
+                                                       const float* __restrict__ w, const int32_t* __restrict__ pmap,
+                                                       const float* __restrict__ bias, const float* __restrict__ add,
+                                                       float* __restrict__ out) {
+    constexpr int BN = 16 * TN;
+    constexpr int WS = BN + 4;
+    __shared__ float Xs[BK][BM];
+    __shared__ __align__(16) float Ws[BK][WS];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int g = blockIdx.z;
+    const int in_ch0 = g * d.g_in, out_ch0 = g * d.g_out;
+    const float* wg = w + (int64_t)g * d.g_w;
+    const int64_t total_pos = (int64_t)d.n * d.p_out;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int oc0 = blockIdx.y * BN;
+
+    // X loader role: one position, 8 contraction rows
+    const int lm = tid & (BM - 1), lk0 = tid >> 7;             // rows lk0 + 2*j
+    const int64_t lpos = m0 + lm;
+    const bool lvalid = lpos < total_pos;
+    const int ln = lvalid ? (int)(lpos / d.p_out) : 0;
+    const int lp = lvalid ? (int)(lpos % d.p_out) : 0;
+    // W loader role
+    const bool ic_fast = d.w_ic <= d.w_oc;
+    const int wk = ic_fast ? (tid & 15) : (tid >> 4);          // contraction row
+    const int wo = ic_fast ? (tid >> 4) : (tid & 15);          // first column; columns wo + 16*j
+
+    const int nk = ceil_div(d.ck, BK);
+    const int iters = d.ntap * nk;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float xr[8], wr[TN];
+    auto load = [&](int it) {
+        const int tap = it / nk, ic0 = (it - tap * nk) * BK;
+        const int src = lvalid ? pmap[(int64_t)d.tap_row[tap] * d.p_out + lp] : -1;
+        const float* xb = in + ((int64_t)ln * d.c_in_total + in_ch0 + d.tap_in_ch[tap] + ic0) * d.p_in + src;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kk = lk0 + 2 * j;
+            xr[j] = (src >= 0 && ic0 + kk < d.ck) ? __ldg(xb + (int64_t)kk * d.p_in) : 0.f;
+        }
+        const float* wb = wg + d.tap_w_off[tap];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int oc = oc0 + wo + 16 * j;
+            wr[j] = (oc < d.co && ic0 + wk < d.ck) ? __ldg(wb + w_oc_offset(d, oc) + (int64_t)(ic0 + wk) * d.w_ic) : 0.f;
+        }
+    };
+
+    load(0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Xs[lk0 + 2 * j][lm] = xr[j];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) Ws[wk][wo + 16 * j] = wr[j];
+        __syncthreads();
+        if (it + 1 < iters) load(it + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float xv[TM], wv[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) xv[i] = Xs[kk][tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) wv[j] = Ws[kk][ty * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t pos = m0 + tx + 16 * i;
+        if (pos >= total_pos) continue;
+        const int nn = (int)(pos / d.p_out), p = (int)(pos % d.p_out);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int oc = oc0 + ty * TN + j;
+            if (oc >= d.co) continue;
+            const int64_t o = ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.p_out + p;
+            float v = acc[i][j];
+            if (bias) v += __ldg(bias + out_ch0 + oc);
+            if (add) v += __ldg(add + o);
+            out[o] = apply_act(v, d.act);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient: dW[tap, oc, ic] = sum_pos gout[oc, pos] * in[(tap, ic), pmap(pos)]
+// CTA tile 64 oc x 64 ic for one tap, contraction over a chunk of positions; fp32 atomics merge chunks.
+// ---------------------------------------------------------------------------------------------
+constexpr int WB = 64, WK = 32, WSTR = WB + 1;
+
+__global__ void __launch_bounds__(NT) tapconv_wgrad_simt(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
+                                                         const float* __restrict__ gout, const int32_t* __restrict__ pmap,
+                                                         float* __restrict__ dw, int nchunks, int64_t chunk) {
+    __shared__ float Gs[WK][WSTR];
+    __shared__ float Xs[WK][WSTR];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int ictiles = ceil_div(d.ck, WB);
+    const int tap = blockIdx.x / ictiles, ic0 = (blockIdx.x % ictiles) * WB;
+    const int oc0 = blockIdx.y * WB;
+    const int g = blockIdx.z / nchunks, ch = blockIdx.z % nchunks;
+    const int in_ch0 = g * d.g_in + d.tap_in_ch[tap], out_ch0 = g * d.g_out;
+    const int64_t total_pos = (int64_t)d.n * d.p_out;
+    const int64_t pbeg = (int64_t)ch * chunk, pend = min(total_pos, pbeg + chunk);
+    const int lane = tid & 31, r0 = tid >> 5;                    // channel rows r0 + 8*j
+    const int32_t* prow = pmap + (int64_t)d.tap_row[tap] * d.p_out;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t k0 = pbeg; k0 < pend; k0 += WK) {
+        const int64_t pos = k0 + lane;
+        const bool valid = pos < pend;
+        const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+        const int src = valid ? prow[p] : -1;
+        const float* gb = gout + ((int64_t)nn * d.c_out_total + out_ch0 + oc0) * d.p_out + p;
+        const float* xb = in + ((int64_t)nn * d.c_in_total + in_ch0 + ic0) * d.p_in + src;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = r0 + 8 * j;
+            Gs[lane][c] = (valid && oc0 + c < d.co) ? __ldg(gb + (int64_t)c * d.p_out) : 0.f;
+            Xs[lane][c] = (src >= 0 && ic0 + c < d.ck) ? __ldg(xb + (int64_t)c * d.p_in) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < WK; ++kk) {
+            float gv[4], xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gv[i] = Gs[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[j] = Xs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* wb = dw + (int64_t)g * d.g_w + d.tap_w_off[tap];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int oc = oc0 + ty * 4 + i;
+        if (oc >= d.co) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ic = ic0 + tx + 16 * j;
+            if (ic >= d.ck) continue;
+            atomicAdd(wb + w_oc_offset(d, oc) + (int64_t)ic * d.w_ic, acc[i][j]);
+        }
+    }
+}
+
+static int validate(const kgan_tapconv_desc* d) {
+    KGAN_REQUIRE(d != nullptr, "tapconv: null descriptor");
+    KGAN_REQUIRE(d->n > 0 && d->p_in > 0 && d->p_out > 0 && d->ck > 0 && d->co > 0, "tapconv: empty dimension");
+    KGAN_REQUIRE(d->ntap >= 1 && d->ntap <= KGAN_MAX_TAPS, "tapconv: ntap=%d out of range", d->ntap);
+    KGAN_REQUIRE(d->groups >= 1 && d->groups <= 65535, "tapconv: groups=%d out of range", d->groups);
+    KGAN_REQUIRE(d->act >= KGAN_ACT_NONE && d->act <= KGAN_ACT_TANH, "tapconv: bad act %d", d->act);
+    for (int t = 0; t < d->ntap; ++t)
+        KGAN_REQUIRE(d->tap_in_ch[t] >= 0 && d->tap_in_ch[t] + d->ck + (d->groups - 1) * d->g_in <= d->c_in_total,
+                     "tapconv: tap %d reads channels beyond c_in_total", t);
+    KGAN_REQUIRE(d->co + (d->groups - 1) * d->g_out <= d->c_out_total, "tapconv: writes channels beyond c_out_total");
+    return 0;
+}
+
+}  // namespace kgan
+
+using namespace kgan;
+
+extern "C" int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, const float* w, const int32_t* pmap,
+                                const float* bias, const float* add, float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && w && pmap && out, "tapconv_fwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->precision == KGAN_PREC_TF32) {
+        int r = tapconv_fwd_tf32(*d, in, w, pmap, bias, add, out, s);
+        if (r >= 0) return r;   // -1: shape not eligible for the tensor-core path -> exact path below
+    }
+    const int64_t total = (int64_t)d->n * d->p_out;
+    const int64_t gx = ceil_div64(total, BM);
+    KGAN_REQUIRE(gx < (1ll << 31), "tapconv_fwd: too many positions");
+    if (d->co <= 32) {
+        dim3 grid((unsigned)gx, ceil_div(d->co, 32), d->groups);
+        tapconv_fwd_simt<2><<<grid, NT, 0, s>>>(*d, in, w, pmap, bias, add, out);
+    } else if (d->co <= 64 || gx * ceil_div(d->co, 128) < 2 * kNumSMs) {
+        dim3 grid((unsigned)gx, ceil_div(d->co, 64), d->groups);
+        tapconv_fwd_simt<4><<<grid, NT, 0, s>>>(*d, in, w, pmap, bias, add, out);
+    } else {
+        dim3 grid((unsigned)gx, ceil_div(d->co, 128), d->groups);
+        tapconv_fwd_simt<8><<<grid, NT, 0, s>>>(*d, in, w, pmap, bias, add, out);
+    }
+    return check_launch("tapconv_fwd");
+}
+
+extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
+                                  float* dw, int64_t dw_numel, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
+    const int64_t total = (int64_t)d->n * d->p_out;
+    const int tiles = d->ntap * ceil_div(d->ck, WB) * ceil_div(d->co, WB) * d->groups;
+    int64_t nchunks = ceil_div64(4 * kNumSMs, tiles);
+    const int64_t max_chunks = ceil_div64(total, 8 * WK);
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    int64_t chunk = ceil_div64(ceil_div64(total, nchunks), WK) * WK;
+    nchunks = ceil_div64(total, chunk);
+    KGAN_REQUIRE((int64_t)d->groups * nchunks <= 65535, "tapconv_wgrad: grid too large");
+    dim3 grid(d->ntap * ceil_div(d->ck, WB), ceil_div(d->co, WB), (unsigned)(d->groups * nchunks));
+    tapconv_wgrad_simt<<<grid, NT, 0, s>>>(*d, in, gout, pmap, dw, (int)nchunks, chunk);
+    return check_launch("tapconv_wgrad");
+}

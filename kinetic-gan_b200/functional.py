@@ -1,0 +1,296 @@
+"""Differentiable operators over the libkgan kernels.
+
+Every operator family is closed under differentiation: the backward of each Function is itself
+written with Functions of the same family, so `autograd.grad(..., create_graph=True)` followed by
+`.backward()` - the WGAN-GP gradient penalty, kinetic-gan.py:104-113,154 - stays entirely on the
+device kernels (what torch does for the reference through convolution_backward /
+_convolution_double_backward / bmm backward).
+
+  tap convolution   F(x, w)   |  Dgrad(g, w) = dF/dx^T g  |  Wgrad(x, g) = dF/dw^T g     (bilinear)
+  adjacency product M(x, A)   |  Dx(g, A)                 |  DA(x, g)                    (bilinear)
+  activation mask   ActGrad(g, y) = g * act'(y)            (linear in g; the mask is piecewise constant)
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_TANH  # noqa: F401
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# tap convolution family
+# ------------------------------------------------------------------------------------------------
+class TapConv(Function):
+    @staticmethod
+    def forward(ctx, x, w, geom):
+        ctx.geom = geom
+        ctx.save_for_backward(x, w)
+        return ops.tapconv_fwd(_c(x), _c(w), geom.fwd)
+
+    @staticmethod
+    def backward(ctx, go):
+        x, w = ctx.saved_tensors
+        go = _c(go)
+        gx = TapConvDgrad.apply(go, w, ctx.geom) if ctx.needs_input_grad[0] else None
+        gw = TapConvWgrad.apply(x, go, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
+        return gx, gw, None
+
+
+class TapConvDgrad(Function):
+    @staticmethod
+    def forward(ctx, go, w, geom):
+        ctx.geom = geom
+        ctx.save_for_backward(go, w)
+        return ops.tapconv_fwd(_c(go), _c(w), geom.dgrad)
+
+    @staticmethod
+    def backward(ctx, h):
+        go, w = ctx.saved_tensors
+        h = _c(h)
+        ggo = TapConv.apply(h, w, ctx.geom) if ctx.needs_input_grad[0] else None
+        gw = TapConvWgrad.apply(h, go, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
+        return ggo, gw, None
+
+
+class TapConvWgrad(Function):
+    @staticmethod
+    def forward(ctx, x, go, geom, w_shape):
+        ctx.geom = geom
+        ctx.save_for_backward(x, go)
+        return ops.tapconv_wgrad(_c(x), _c(go), geom.fwd, tuple(w_shape))
+
+    @staticmethod
+    def backward(ctx, hw):
+        x, go = ctx.saved_tensors
+        hw = _c(hw)
+        gx = TapConvDgrad.apply(go, hw, ctx.geom) if ctx.needs_input_grad[0] else None
+        ggo = TapConv.apply(x, hw, ctx.geom) if ctx.needs_input_grad[1] else None
+        return gx, ggo, None, None
+
+
+class TapConvEp(Function):
+    """out = act(F(x, w) + bias[c] + add): the convolution with its fused epilogue (one kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, add, geom, act):
+        ctx.geom, ctx.act = geom, act
+        out = ops.tapconv_fwd(_c(x), _c(w), geom.fwd, bias, None if add is None else _c(add), act)
+        ctx.save_for_backward(x, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, w, out = ctx.saved_tensors
+        go = _c(go)
+        gz = ActGrad.apply(go, out, ctx.act) if ctx.act != ACT_NONE else go
+        gx = TapConvDgrad.apply(gz, w, ctx.geom) if ctx.needs_input_grad[0] else None
+        gw = TapConvWgrad.apply(x, gz, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
+        gb = ChanSum.apply(gz) if ctx.needs_input_grad[2] else None
+        ga = gz if ctx.needs_input_grad[3] else None
+        return gx, gw, gb, ga, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# adjacency product family
+# ------------------------------------------------------------------------------------------------
+class AdjMix(Function):
+    @staticmethod
+    def forward(ctx, x, A):
+        ctx.save_for_backward(x, A)
+        return ops.adjmix_fwd(_c(x), _c(A))
+
+    @staticmethod
+    def backward(ctx, go):
+        x, A = ctx.saved_tensors
+        go = _c(go)
+        gx = AdjMixDx.apply(go, A) if ctx.needs_input_grad[0] else None
+        gA = AdjMixDA.apply(x, go, A.shape[0]) if ctx.needs_input_grad[1] else None
+        return gx, gA
+
+
+class AdjMixDx(Function):
+    @staticmethod
+    def forward(ctx, g, A):
+        ctx.save_for_backward(g, A)
+        return ops.adjmix_bwd_x(_c(g), _c(A))
+
+    @staticmethod
+    def backward(ctx, h):
+        g, A = ctx.saved_tensors
+        h = _c(h)
+        gg = AdjMix.apply(h, A) if ctx.needs_input_grad[0] else None
+        gA = AdjMixDA.apply(h, g, A.shape[0]) if ctx.needs_input_grad[1] else None
+        return gg, gA
+
+
+class AdjMixDA(Function):
+    @staticmethod
+    def forward(ctx, x, g, k):
+        ctx.save_for_backward(x, g)
+        return ops.adjmix_bwd_a(_c(x), _c(g), k)
+
+    @staticmethod
+    def backward(ctx, hA):
+        x, g = ctx.saved_tensors
+        hA = _c(hA)
+        gx = AdjMixDx.apply(g, hA) if ctx.needs_input_grad[0] else None
+        gg = AdjMix.apply(x, hA) if ctx.needs_input_grad[1] else None
+        return gx, gg, None
+
+
+# ------------------------------------------------------------------------------------------------
+# activation mask, channel reductions
+# ------------------------------------------------------------------------------------------------
+class ActGrad(Function):
+    """gz = go * act'(y), y = the block OUTPUT (LeakyReLU keeps the sign, so sign(y) == sign(pre-activation))."""
+
+    @staticmethod
+    def forward(ctx, go, y, act):
+        ctx.act = act
+        ctx.save_for_backward(go, y)
+        return ops.act_bwd(_c(go), y, act)
+
+    @staticmethod
+    def backward(ctx, h):
+        go, y = ctx.saved_tensors
+        h = _c(h)
+        ggo = ActGrad.apply(h, y, ctx.act) if ctx.needs_input_grad[0] else None
+        gy = None
+        if ctx.needs_input_grad[1] and ctx.act == ACT_TANH:
+            gy = -2.0 * y * go * h            # d/dy [go (1 - y^2)]; never reached by the WGAN-GP step (G is first-order only)
+        return ggo, gy, None
+
+
+class ChanSum(Function):
+    """out[c] = sum_{n,t,v} g[n,c,t,v]  (bias gradients)."""
+
+    @staticmethod
+    def forward(ctx, g):
+        ctx.shape = g.shape
+        return ops.chan_reduce(_c(g))
+
+    @staticmethod
+    def backward(ctx, h):
+        return h.view(1, -1, 1, 1).expand(ctx.shape)
+
+
+class ChanSumMul(Function):
+    """out[c] = sum_{n,t,v} g[n,c,t,v] * m[n,0,t,v]  (NoiseInjection.weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, g, m):
+        ctx.save_for_backward(g, m)
+        return ops.chan_reduce(_c(g), _c(m))
+
+    @staticmethod
+    def backward(ctx, h):
+        g, m = ctx.saved_tensors
+        hv = h.view(1, -1, 1, 1)
+        gg = hv * m if ctx.needs_input_grad[0] else None
+        gm = (hv * g).sum(1, keepdim=True) if ctx.needs_input_grad[1] else None
+        return gg, gm
+
+
+class NoiseAct(Function):
+    """out = act(a + b + nw[c] * noise[n,0,t,v]): `tcn(x) + res`, NoiseInjection and the activation of a
+    generator block in one pass (generator.py:176-182)."""
+
+    @staticmethod
+    def forward(ctx, a, b, noise, nw, act):
+        ctx.act = act
+        out = ops.epilogue_fwd(_c(a), None if b is None else _c(b), None, _c(nw.reshape(-1)), _c(noise), act)
+        ctx.save_for_backward(out, noise)
+        ctx.nw_shape = nw.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        out, noise = ctx.saved_tensors
+        gz = ActGrad.apply(_c(go), out, ctx.act) if ctx.act != ACT_NONE else _c(go)
+        ga = gz if ctx.needs_input_grad[0] else None
+        gb = gz if ctx.needs_input_grad[1] else None
+        gnw = ChanSumMul.apply(gz, noise).view(ctx.nw_shape) if ctx.needs_input_grad[3] else None
+        return ga, gb, None, gnw, None
+
+
+# ------------------------------------------------------------------------------------------------
+# plane gather / scatter, label planes
+# ------------------------------------------------------------------------------------------------
+class PlaneSpmm(Function):
+    @staticmethod
+    def forward(ctx, x, table):
+        ctx.table = table
+        return ops.plane_spmm(_c(x), table)
+
+    @staticmethod
+    def backward(ctx, go):
+        return PlaneSpmm.apply(_c(go), ctx.table.T), None
+
+
+class LabelConcat(Function):
+    """cat(label planes, x) along channels (discriminator.py:57-60) without the (N,n_cls,T,V) repeat."""
+
+    @staticmethod
+    def forward(ctx, e, x):
+        ctx.ncls = e.shape[1]
+        return ops.label_concat(_c(e), _c(x))
+
+    @staticmethod
+    def backward(ctx, go):
+        ge, gx = LabelSplit.apply(_c(go), ctx.ncls)
+        return (ge if ctx.needs_input_grad[0] else None), (gx if ctx.needs_input_grad[1] else None)
+
+
+class LabelSplit(Function):
+    @staticmethod
+    def forward(ctx, g, ncls):
+        ge, gx = ops.label_split(_c(g), ncls)
+        return ge, gx
+
+    @staticmethod
+    def backward(ctx, he, hx):
+        return LabelConcat.apply(_c(he), _c(hx)), None
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm2d
+# ------------------------------------------------------------------------------------------------
+class BatchNormTrain(Function):
+    """nn.BatchNorm2d in training mode (generator.py:142,160); running stats are updated in place by the
+    statistics kernel.  First-order backward only (nothing in the WGAN-GP step differentiates G twice)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum):
+        x = _c(x)
+        mean, rstd = ops.bn_stats(x, running_mean, running_var, eps, momentum)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return ops.bn_apply(x, mean, rstd, gamma, beta)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        gx, gg, gb = ops.bn_bwd(_c(gy), x, mean, rstd, gamma)
+        return gx, gg, gb, None, None, None, None
+
+
+class BatchNormEval(Function):
+    """nn.BatchNorm2d in eval mode (generate.py:67): affine map with the running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps):
+        rstd = torch.rsqrt(running_var + eps)
+        ctx.save_for_backward(x, gamma, running_mean, rstd)
+        return ops.bn_apply(_c(x), running_mean, rstd, gamma, beta)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        sc = (gamma * rstd).view(1, -1, 1, 1)
+        xh = (x - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+        return gy * sc, (gy * xh).sum((0, 2, 3)), gy.sum((0, 2, 3)), None, None, None

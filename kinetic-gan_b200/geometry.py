@@ -1,0 +1,177 @@
+"""Host-side geometry tables for the tap-convolution and plane-gather kernels.
+
+Everything the reference does with shapes and indices around its convolutions - temporal zero
+padding (generator.py:129, discriminator.py:94), `downsample_s` joint selection
+(discriminator.py:139-142), nearest-neighbour `F.interpolate` along T (generator.py:172,
+discriminator.py:134), `upsample_s` joint insertion (generator.py:185-200), global average pooling
+(discriminator.py:68) - becomes a small int32/float32 table that the kernels consume, so that no
+resampled tensor is ever materialised on the discriminator side and the generator side needs one
+gather.  Tables are built once per module (ctor time) with numpy and cached per device.
+"""
+import numpy as np
+import torch
+
+from ._lib import MAX_TAPS
+
+
+def nearest_src(t_in, t_out):
+    """Index rule of F.interpolate(mode='nearest'): src = floor(dst * in / out)."""
+    return [min(int(np.floor(d * (t_in / t_out))), t_in - 1) for d in range(t_out)]
+
+
+class _DeviceCache:
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, key, device, make):
+        k = (key, str(device))
+        if k not in self._cache:
+            self._cache[k] = make().to(device)
+        return self._cache[k]
+
+
+class TapDesc:
+    """Static part of a `kgan_tapconv_desc` plus its position map (see include/kgan.h)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        assert self.ntap <= MAX_TAPS
+        assert self.pmap.dtype == np.int32 and self.pmap.shape[1] == self.p_out
+        self._dev = _DeviceCache()
+        self._structs = {}
+
+    def pmap_on(self, device):
+        return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
+
+    def cstruct(self, n, act, precision):
+        from ._lib import TapConvDesc
+
+        key = (n, act, precision)
+        s = self._structs.get(key)
+        if s is None:
+            s = TapConvDesc()
+            s.n, s.c_in_total, s.p_in, s.c_out_total, s.p_out = n, self.c_in_total, self.p_in, self.c_out_total, self.p_out
+            s.ntap, s.ck, s.co, s.groups = self.ntap, self.ck, self.co, self.groups
+            s.g_in, s.g_out, s.g_w = self.g_in, self.g_out, self.g_w
+            s.w_oc, s.w_ic, s.w_oc_blk, s.w_ocblk = self.w_oc, self.w_ic, 0, 0
+            for i in range(self.ntap):
+                s.tap_in_ch[i], s.tap_w_off[i], s.tap_row[i] = self.tap_in_ch[i], self.tap_w_off[i], self.tap_row[i]
+            s.act, s.precision = act, precision
+            self._structs[key] = s
+        return s
+
+
+class TapConvGeom:
+    """One convolution site: K channel blocks (graph partitions; 1 for ordinary convs) x kt temporal taps.
+
+    natural weight shape (K*c_out, c_in, kt, 1) - exactly nn.Conv2d's (tgcn.py:48, generator.py:134,155,
+    discriminator.py:99,115) - or (c_out, c_in) for nn.Linear (kt = 1).
+    input  (N, K*c_in, t_in, v_in)   [for K > 1 the input is the adjacency-mixed tensor, kgan_adjmix_fwd]
+    output (N, c_out, len(t_sel), len(v_keep)): only the frames / joints that survive the block's
+    down-sampling are computed (SURVEY.md §7 I2 - selection commutes with the linear map).
+    """
+
+    def __init__(self, c_in, c_out, t_in, v_in, K=1, kt=1, pad=0, stride=1, dil=1, t_sel=None, v_keep=None):
+        self.c_in, self.c_out, self.t_in, self.v_in, self.K, self.kt = c_in, c_out, t_in, v_in, K, kt
+        t_conv = (t_in + 2 * pad - dil * (kt - 1) - 1) // stride + 1
+        assert t_conv >= 1, "temporal kernel larger than the padded input"
+        self.t_sel = list(range(t_conv)) if t_sel is None else [int(t) for t in t_sel]
+        self.v_keep = list(range(v_in)) if v_keep is None else [int(v) for v in v_keep]
+        assert all(0 <= t < t_conv for t in self.t_sel) and all(0 <= v < v_in for v in self.v_keep)
+        self.t_out, self.v_out = len(self.t_sel), len(self.v_keep)
+        self.p_in, self.p_out = t_in * v_in, self.t_out * self.v_out
+        self.w_numel = K * c_out * c_in * kt
+
+        pmap = np.full((kt, self.p_out), -1, np.int32)
+        inv = np.full((kt, self.p_in), -1, np.int32)
+        for dt in range(kt):
+            for a, tau in enumerate(self.t_sel):
+                t = tau * stride + dt * dil - pad
+                if 0 <= t < t_in:
+                    for b, v in enumerate(self.v_keep):
+                        q, p = a * self.v_out + b, t * v_in + v
+                        pmap[dt, q] = p
+                        assert inv[dt, p] == -1, "position map must be injective per tap"
+                        inv[dt, p] = q
+        taps = [(k, dt) for k in range(K) for dt in range(kt)]
+        self.fwd = TapDesc(
+            c_in_total=K * c_in, p_in=self.p_in, c_out_total=c_out, p_out=self.p_out, ntap=len(taps), ck=c_in, co=c_out,
+            groups=1, g_in=0, g_out=0, g_w=0, w_oc=c_in * kt, w_ic=kt,
+            tap_in_ch=[k * c_in for k, dt in taps], tap_w_off=[k * c_out * c_in * kt + dt for k, dt in taps],
+            tap_row=[dt for k, dt in taps], pmap=pmap, t_out=self.t_out, v_out=self.v_out)
+        # data gradient: same kernel, roles of (oc, ic) swapped, inverse map, one group per channel block
+        self.dgrad = TapDesc(
+            c_in_total=c_out, p_in=self.p_out, c_out_total=K * c_in, p_out=self.p_in, ntap=kt, ck=c_out, co=c_in,
+            groups=K, g_in=0, g_out=c_in, g_w=c_out * c_in * kt, w_oc=kt, w_ic=c_in * kt,
+            tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=inv, t_out=t_in, v_out=v_in)
+
+
+class PlaneTable:
+    """Sparse (p_out x p_in) matrix applied to every (n, c) plane: out[q] = sum_j wgt[q,j] * x[idx[q,j]]."""
+
+    def __init__(self, dense, t_out, v_out, t_in, v_in):
+        dense = np.asarray(dense, np.float64)                # (p_out, p_in)
+        self.p_out, self.p_in = dense.shape
+        self.t_out, self.v_out, self.t_in, self.v_in = t_out, v_out, t_in, v_in
+        assert self.p_out == t_out * v_out and self.p_in == t_in * v_in
+        self.dense = dense
+        self.J = max(1, int((dense != 0).sum(1).max()))
+        self.idx = np.full((self.p_out, self.J), -1, np.int32)
+        self.wgt = np.zeros((self.p_out, self.J), np.float32)
+        for q in range(self.p_out):
+            nz = np.nonzero(dense[q])[0]
+            self.idx[q, :len(nz)] = nz
+            self.wgt[q, :len(nz)] = dense[q, nz]
+        self._dev = _DeviceCache()
+        self._T = None
+
+    @property
+    def T(self):
+        if self._T is None:
+            self._T = PlaneTable(self.dense.T, self.t_in, self.v_in, self.t_out, self.v_out)
+            self._T._T = self
+        return self._T
+
+    def on(self, device):
+        return (self._dev.get("idx", device, lambda: torch.from_numpy(self.idx)),
+                self._dev.get("wgt", device, lambda: torch.from_numpy(self.wgt)))
+
+
+def upsample_matrix(hoods, v_coarse, halve):
+    """U (v_coarse x v_fine) with  upsample_s(x) == x @ U  (generator.py:185-200): every hood
+    [fine_idx, coarse...] inserts, at fine_idx, the mean of the listed coarse joints (/2 iff lvl == 2)."""
+    cols = [np.eye(v_coarse)[:, j] for j in range(v_coarse)]
+    new = []
+    for hood in hoods:
+        col = np.zeros(v_coarse)
+        for j in hood[1:]:
+            col[int(j)] += 1.0 / (len(hood) - 1)
+        new.append(col / 2 if halve else col)
+    for hood, col in zip(hoods, new):
+        cols.insert(int(hood[0]), col)
+    return np.stack(cols, 1)
+
+
+def resample_table(t_in, v_in, t_out, U=None):
+    """Plane table of  F.interpolate(upsample_s(x), size=(t_out, V))  (generator.py:170-172)."""
+    U = np.eye(v_in) if U is None else np.asarray(U)
+    v_out = U.shape[1]
+    src = nearest_src(t_in, t_out)
+    dense = np.zeros((t_out * v_out, t_in * v_in))
+    for t in range(t_out):
+        dense[t * v_out:(t + 1) * v_out, src[t] * v_in:(src[t] + 1) * v_in] = U.T
+    return PlaneTable(dense, t_out, v_out, t_in, v_in)
+
+
+def select_table(t_in, v_in, t_sel, v_keep):
+    """Plane table of  F.interpolate(x[..., keep], size=(t_out, V'))  on the identity residual (discriminator.py:128-134)."""
+    dense = np.zeros((len(t_sel) * len(v_keep), t_in * v_in))
+    for a, t in enumerate(t_sel):
+        for b, v in enumerate(v_keep):
+            dense[a * len(v_keep) + b, t * v_in + v] = 1.0
+    return PlaneTable(dense, len(t_sel), len(v_keep), t_in, v_in)
+
+
+def mean_table(t_in, v_in):
+    """Plane table of F.avg_pool2d(x, (T, V)) (discriminator.py:68)."""
+    return PlaneTable(np.full((1, t_in * v_in), 1.0 / (t_in * v_in)), 1, 1, t_in, v_in)

@@ -1,0 +1,44 @@
+"""Graph-convolution operator with the reference's module surface (models/init_gan/tgcn.py:6-68).
+
+Same ctor / forward signature, same `conv.weight` parameter (shape, init, state_dict key); the
+arithmetic is refolded: because `conv` has no bias, "1x1 conv to K*C_out channels,
+then einsum('nkctv,kvw->nctw')" equals ONE contraction over (k, c_in) of the adjacency-mixed input
+XA[n,k,ci,t,w] = sum_v x[n,ci,t,v] A[k,v,w] - kgan_adjmix_fwd followed by kgan_tapconv_fwd with K
+channel-block taps - so the K-times larger intermediate of the reference is never written."""
+import torch
+import torch.nn as nn
+
+from ... import functional as KF
+from ...geometry import TapConvGeom
+
+
+class ConvTemporalGraphical(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, t_kernel_size=1, t_stride=1, t_padding=0, t_dilation=1,
+                 bias=False):
+        super().__init__()
+        self.kernel_size = kernel_size
+        # parameter container only (shape/init/keys of tgcn.py:48-55); the cuDNN conv is never called
+        self.conv = nn.Conv2d(in_channels, out_channels * kernel_size, kernel_size=(t_kernel_size, 1),
+                              padding=(t_padding, 0), stride=(t_stride, 1), dilation=(t_dilation, 1), bias=bias)
+        self._t = (t_kernel_size, t_stride, t_padding, t_dilation)
+        self._geoms = {}
+
+    def _geom(self, t, w):
+        g = self._geoms.get((t, w))
+        if g is None:
+            kt, st, pad, dil = self._t
+            g = TapConvGeom(self.conv.in_channels, self.conv.out_channels // self.kernel_size, t, w, K=self.kernel_size,
+                            kt=kt, pad=pad, stride=st, dil=dil)
+            self._geoms[(t, w)] = g
+        return g
+
+    def forward(self, x, A):
+        assert A.size(0) == self.kernel_size
+        xa = KF.AdjMix.apply(x, A)                                  # (N, K*C_in, T, W)
+        out = KF.TapConv.apply(xa, self.conv.weight, self._geom(x.size(2), A.size(2)))
+        if self.conv.bias is not None:
+            # never used by Kinetic-GAN (bias=False at generator.py:132 / discriminator.py:96): the K*C_out conv
+            # biases reach the output through the column sums of A; tiny host-side torch ops
+            b = torch.einsum("kc,kw->cw", self.conv.bias.view(self.kernel_size, -1), A.sum(1))
+            out = out + b.view(1, b.size(0), 1, b.size(1))
+        return out, A

@@ -1,0 +1,209 @@
+"""Tensor-level wrappers of the C ABI (include/kgan.h): allocate outputs with torch, pass raw device
+pointers and the current CUDA stream.  No arithmetic happens here, and there is no fallback - every
+function ends in a libkgan.so kernel launch."""
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, PREC_FP32, PREC_TF32  # noqa: F401
+
+_precision = PREC_FP32
+launches = 0       # number of libkgan kernels launched by this process (bench.py reports it)
+
+
+def set_precision(name):
+    """'fp32' = exact SIMT FMA path (rel-L2 <= 1e-5 vs the fp32 reference);
+    'tf32' = tcgen05 kind::tf32 tensor-core path with fp32 accumulation (<= 1e-3)."""
+    global _precision
+    _precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}[name]
+
+
+def get_precision():
+    return "tf32" if _precision == PREC_TF32 else "fp32"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "kgan ops need contiguous float32 CUDA tensors"
+
+
+def _count(n=1):
+    global launches
+    launches += n
+
+
+def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
+    _chk(x, w, bias, add)
+    n = x.shape[0]
+    assert x.shape[1] == desc.c_in_total and x.shape[2] * x.shape[3] == desc.p_in, (tuple(x.shape), desc.c_in_total, desc.p_in)
+    out = torch.empty((n, desc.c_out_total, desc.t_out, desc.v_out), device=x.device, dtype=torch.float32)
+    if add is not None:
+        assert add.shape == out.shape
+    l = _lib.lib()
+    _lib.check(l.kgan_tapconv_fwd(desc.cstruct(n, act, _precision), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
+                                  _ptr(bias), _ptr(add), out.data_ptr(), _stream()), "kgan_tapconv_fwd")
+    _count()
+    return out
+
+
+def tapconv_wgrad(x, gout, desc, w_shape):
+    _chk(x, gout)
+    n = x.shape[0]
+    dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+    l = _lib.lib()
+    _lib.check(l.kgan_tapconv_wgrad(desc.cstruct(n, ACT_NONE, _precision), x.data_ptr(), gout.data_ptr(),
+                                    desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream()), "kgan_tapconv_wgrad")
+    _count()
+    return dw
+
+
+def adjmix_fwd(x, A):
+    _chk(x, A)
+    n, c, t, v = x.shape
+    k, v2, w = A.shape
+    assert v2 == v
+    out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_adjmix_fwd(x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_fwd")
+    _count()
+    return out
+
+
+def adjmix_bwd_x(g, A):
+    _chk(g, A)
+    k, v, w = A.shape
+    n, kc, t, w2 = g.shape
+    assert w2 == w and kc % k == 0
+    c = kc // k
+    gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_adjmix_bwd_x(g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_bwd_x")
+    _count()
+    return gx
+
+
+def adjmix_bwd_a(x, g, k):
+    _chk(x, g)
+    n, c, t, v = x.shape
+    w = g.shape[3]
+    assert g.shape[0] == n and g.shape[1] == k * c and g.shape[2] == t
+    gA = torch.empty((k, v, w), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_adjmix_bwd_a(x.data_ptr(), g.data_ptr(), gA.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_bwd_a")
+    _count()
+    return gA
+
+
+def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=ACT_NONE):
+    _chk(a, b, bias, nw, noise)
+    n, c, t, v = a.shape
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().kgan_epilogue_fwd(a.data_ptr(), _ptr(b), _ptr(bias), _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act,
+                                            _stream()), "kgan_epilogue_fwd")
+    _count()
+    return out
+
+
+def act_bwd(gout, out, act):
+    _chk(gout, out)
+    gz = torch.empty_like(out)
+    _lib.check(_lib.lib().kgan_act_bwd(gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream()), "kgan_act_bwd")
+    _count()
+    return gz
+
+
+def chan_reduce(g, mul=None):
+    _chk(g, mul)
+    n, c, t, v = g.shape
+    out = torch.empty((c,), device=g.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_chan_reduce(g.data_ptr(), _ptr(mul), out.data_ptr(), n, c, t * v, _stream()), "kgan_chan_reduce")
+    _count()
+    return out
+
+
+def plane_spmm(x, table):
+    _chk(x)
+    n, c, t, v = x.shape
+    assert t * v == table.p_in, (tuple(x.shape), table.p_in)
+    idx, wgt = table.on(x.device)
+    out = torch.empty((n, c, table.t_out, table.v_out), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_plane_spmm(x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
+                                          table.J, _stream()), "kgan_plane_spmm")
+    _count()
+    return out
+
+
+def label_concat(e, x):
+    _chk(e, x)
+    n, c, t, v = x.shape
+    ncls = e.shape[1]
+    out = torch.empty((n, ncls + c, t, v), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_label_concat(e.data_ptr(), x.data_ptr(), out.data_ptr(), n, ncls, c, t * v, _stream()), "kgan_label_concat")
+    _count()
+    return out
+
+
+def label_split(g, ncls, need_e=True, need_x=True):
+    _chk(g)
+    n, ct, t, v = g.shape
+    c = ct - ncls
+    ge = torch.empty((n, ncls), device=g.device, dtype=torch.float32) if need_e else None
+    gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32) if need_x else None
+    _lib.check(_lib.lib().kgan_label_split(g.data_ptr(), _ptr(ge), _ptr(gx), n, ncls, c, t * v, _stream()), "kgan_label_split")
+    _count()
+    return ge, gx
+
+
+def bn_stats(x, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    _chk(x, running_mean, running_var)
+    n, c, t, v = x.shape
+    mean = torch.empty((c,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((c,), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_bn_stats(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), n, c, t * v,
+                                        eps, momentum, _stream()), "kgan_bn_stats")
+    _count()
+    return mean, rstd
+
+
+def bn_apply(x, mean, rstd, gamma, beta):
+    _chk(x, mean, rstd, gamma, beta)
+    n, c, t, v = x.shape
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().kgan_bn_apply(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c,
+                                        t * v, _stream()), "kgan_bn_apply")
+    _count()
+    return y
+
+
+def bn_bwd(gy, x, mean, rstd, gamma):
+    _chk(gy, x, mean, rstd, gamma)
+    n, c, t, v = x.shape
+    gx = torch.empty_like(x)
+    gg = torch.empty((c,), device=x.device, dtype=torch.float32)
+    gb = torch.empty((c,), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().kgan_bn_bwd(gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
+                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _stream()), "kgan_bn_bwd")
+    _count()
+    return gx, gg, gb
+
+
+def adam_step(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
+    _chk(p, g, m, v)
+    _lib.check(_lib.lib().kgan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, step,
+                                         grad_scale, _stream()), "kgan_adam_step")
+    _count()
+
+
+def interpolate(alpha, x, y):
+    _chk(alpha, x, y)
+    n = x.shape[0]
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().kgan_interpolate(alpha.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, _stream()),
+               "kgan_interpolate")
+    _count()
+    return out

@@ -21,3 +21,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    """Routes kinetic-gan_b200.ops through the torch-CPU emulation of the C ABI (tests/emu_backend.py)."""
+    import emu_backend
+
+    emu_backend.install(monkeypatch)
+    return emu_backend

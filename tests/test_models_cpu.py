@@ -1,0 +1,110 @@
+"""Product modules (host logic, CPU, C-ABI primitives emulated) against the oracle and the golden fixtures:
+same synthetic weights loaded through `load_state_dict`, same inputs, same noise."""
+import numpy as np
+import pytest
+import torch
+
+import kgan_b200 as kgan
+from oracle import networks as onet
+from oracle.graph import SkeletonTables
+from helpers import CASES, draw_noises, inputs, load_golden, rel_l2, sub, within_noise_floor
+
+
+def build(cfg, dtype=torch.float32):
+    G = kgan.Generator(cfg.latent_dim, cfg.channels, cfg.n_classes, cfg.t_size, cfg.mlp_dim, dataset=cfg.dataset)
+    D = kgan.Discriminator(cfg.channels, cfg.n_classes, cfg.t_size, cfg.latent_dim, dataset=cfg.dataset)
+    pg = onet.synth_params(onet.g_param_shapes(cfg), 1)
+    pd = onet.synth_params(onet.d_param_shapes(cfg), 2)
+    G.load_state_dict(pg)          # strict: key names and shapes must be the reference's
+    D.load_state_dict(pd)
+    if dtype == torch.float64:
+        G, D = G.double(), D.double()
+        for m in (G, D):
+            for i, a in enumerate(m.graph.As):
+                setattr(m, "_A%d" % i, torch.tensor(a, dtype=torch.float64))
+    return G, D
+
+
+def test_state_dict_surface():
+    cfg = onet.Config()
+    G = kgan.Generator(512, 3, 60, 64, 4)
+    D = kgan.Discriminator(3, 60, 64, 512)
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == onet.g_param_shapes(cfg)
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == onet.d_param_shapes(cfg)
+    # reference init rules: N(0,1) mapping weights, zero noise weights, unit edge importance
+    assert abs(G.mlp.mlp[0].weight.std().item() - 1.0) < 0.02 and G.mlp.mlp[0].bias.abs().max() == 0
+    assert all(b.noise.weight.abs().max() == 0 for b in G.st_gcn_networks)
+    assert all((e == 1).all() for e in G.edge_importance) and all((e == 1).all() for e in D.edge_importance)
+    assert not any(k.startswith("_A") for k in G.state_dict())
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_generator_vs_golden(emu, case, tag):
+    gold, cfg, n = load_golden(case), CASES[case]["cfg"], CASES[case]["n"]
+    dtype = torch.float64 if tag == "f64" else torch.float32
+    tol = 1e-10 if tag == "f64" else 2e-5
+    G, _ = build(cfg, dtype)
+    x = inputs(cfg, n, 0, dtype)
+    G.train()
+    blocks = []
+    hooks = [m.register_forward_hook(lambda m, i, o: blocks.append(o[0].detach())) for m in G.st_gcn_networks]
+    fake = G(x["z"], x["labels"], noises=draw_noises(cfg, n, 11, dtype))
+    for h in hooks:
+        h.remove()
+    for i, b in enumerate(blocks):
+        assert rel_l2(b, gold[tag + "/g_block%d" % i]) < tol, i
+    assert rel_l2(fake, gold[tag + "/g_out"]) < tol
+    (fake * x["cot_g"]).sum().backward()
+    for k, p in G.named_parameters():
+        assert within_noise_floor(sub(p.grad), gold, "/g_grad/" + k, tag, 50 * tol), k
+    for k, b in G.named_buffers():
+        if "running" in k:
+            assert rel_l2(b, gold[tag + "/g_bn_after/" + k]) < tol, k
+        if "num_batches_tracked" in k:
+            assert int(b) == 1
+    # default noise path: same CPU RNG stream as the reference (generator.py:179)
+    G2, _ = build(cfg, dtype)
+    G2.eval()
+    torch.manual_seed(12)
+    assert rel_l2(G2(x["z"], x["labels"]), gold[tag + "/g_out_eval"]) < tol
+    np.random.seed(5)
+    torch.manual_seed(13)
+    assert rel_l2(G2(x["z"], x["labels"], 0.95), gold[tag + "/g_out_trunc"]) < 5 * tol
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_discriminator_and_gp_vs_golden(emu, case, tag):
+    gold, cfg, n = load_golden(case), CASES[case]["cfg"], CASES[case]["n"]
+    dtype = torch.float64 if tag == "f64" else torch.float32
+    tol = 1e-10 if tag == "f64" else 2e-5
+    _, D = build(cfg, dtype)
+    x = inputs(cfg, n, 0, dtype)
+    xr = x["real"].clone().requires_grad_(True)
+    blocks = []
+    hooks = [m.register_forward_hook(lambda m, i, o: blocks.append(o[0].detach())) for m in D.st_gcn_networks]
+    dv = D(xr, x["labels"])
+    for h in hooks:
+        h.remove()
+    for i, b in enumerate(blocks):
+        assert rel_l2(b, gold[tag + "/d_block%d" % i]) < tol, i
+    assert rel_l2(dv, gold[tag + "/d_out"]) < tol
+    (dv * x["cot_d"]).sum().backward()
+    assert rel_l2(xr.grad, gold[tag + "/d_grad_x"]) < 10 * tol
+    for k, p in D.named_parameters():
+        assert within_noise_floor(sub(p.grad), gold, "/d_grad/" + k, tag, 50 * tol), k
+    # gradient penalty (kinetic-gan.py:94-114): value, d/dx and the double-backward parameter gradients
+    from importlib import import_module
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    D.zero_grad()
+    fake = torch.as_tensor(gold[tag + "/g_out"]).to(dtype)
+    gp, grads = wg.compute_gradient_penalty(D, x["real"], fake, x["labels"], alpha=x["alpha"], return_gradients=True)
+    assert abs(gp.item() - float(gold[tag + "/gp"])) < 20 * tol * max(1.0, abs(float(gold[tag + "/gp"])))
+    assert rel_l2(grads, gold[tag + "/gp_grads_x"]) < 10 * tol
+    gp.backward()
+    for k, p in D.named_parameters():
+        if k.endswith("bias") or k == "label_emb.weight":
+            assert p.grad is None or p.grad.abs().max().item() == 0, k      # the penalty cannot see them
+        else:
+            assert within_noise_floor(sub(p.grad), gold, "/gp_grad/" + k, tag, 100 * tol), k
