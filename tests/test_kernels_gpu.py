@@ -1,0 +1,144 @@
+"""Every C-ABI kernel (called through the real libkgan.so on the GPU) against the torch-CPU statement of the same
+descriptor semantics in float64 (tests/emu_backend.py).  fp32 path: rel-L2 <= 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import emu_backend as emu
+import kgan_b200 as kgan
+
+pytestmark = pytest.mark.gpu
+ops, G = kgan.ops, kgan.geometry
+TOL = 1e-5
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def cu(t):
+    return None if t is None else t.cuda().contiguous()
+
+
+def dbl(t):
+    return None if t is None else t.double()
+
+
+def rel(a, b):
+    b = b.double()
+    return ((a.detach().cpu().double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+GEOMS = {
+    "gcn_k3_small": (dict(c_in=3, c_out=4, t_in=5, v_in=4, K=3), 2),
+    "tcn_select": (dict(c_in=2, c_out=3, t_in=8, v_in=5, kt=3, pad=1, t_sel=[0, 2, 4, 6], v_keep=[1, 3, 4]), 3),
+    "gcn_temporal": (dict(c_in=2, c_out=2, t_in=7, v_in=3, K=2, kt=3, pad=1, stride=2), 2),
+    "linear_mlp": (dict(c_in=572, c_out=572, t_in=1, v_in=1), 37),
+    "d0_gcn": (dict(c_in=63, c_out=32, t_in=64, v_in=25, K=3), 3),
+    "d2_gcn": (dict(c_in=64, c_out=128, t_in=64, v_in=11, K=3), 2),
+    "d2_tcn": (dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=[2, 4, 6, 8, 10]), 2),
+    "d4_tcn": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 5),
+    "g6_tcn": (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 4),
+    "head": (dict(c_in=512, c_out=1, t_in=1, v_in=1), 9),
+}
+
+
+@pytest.mark.parametrize("name", list(GEOMS))
+def test_tapconv_fwd_dgrad_wgrad(name):
+    kw, n = GEOMS[name]
+    geom = G.TapConvGeom(**kw)
+    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    w = rnd(geom.K * geom.c_out, geom.c_in, geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
+    bias = rnd(geom.c_out, seed=3)
+    add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)
+    go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
+    assert rel(ops.tapconv_fwd(cu(x), cu(w), geom.fwd), emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd)) < TOL
+    for act in (ops.ACT_NONE, ops.ACT_LRELU, ops.ACT_TANH):
+        got = ops.tapconv_fwd(cu(x), cu(w), geom.fwd, cu(bias), cu(add), act)
+        assert rel(got, emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd, dbl(bias), dbl(add), act)) < TOL, act
+    assert rel(ops.tapconv_fwd(cu(go), cu(w), geom.dgrad), emu.tapconv_fwd(dbl(go), dbl(w), geom.dgrad)) < TOL
+    assert rel(ops.tapconv_wgrad(cu(x), cu(go), geom.fwd, tuple(w.shape)), emu.tapconv_wgrad(dbl(x), dbl(go), geom.fwd, tuple(w.shape))) < TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7, 25, 25, 3), (2, 4, 3, 11, 25, 3), (2, 3, 4, 16, 16, 3), (5, 7, 1, 1, 1, 3), (2, 2, 5, 5, 11, 2)])
+def test_adjmix(shape):
+    n, c, t, v, w, k = shape
+    x, A, g = rnd(n, c, t, v, seed=1), rnd(k, v, w, seed=2), rnd(n, k * c, t, w, seed=3)
+    assert rel(ops.adjmix_fwd(cu(x), cu(A)), emu.adjmix_fwd(dbl(x), dbl(A))) < TOL
+    assert rel(ops.adjmix_bwd_x(cu(g), cu(A)), emu.adjmix_bwd_x(dbl(g), dbl(A))) < TOL
+    assert rel(ops.adjmix_bwd_a(cu(x), cu(g), k), emu.adjmix_bwd_a(dbl(x), dbl(g), k)) < TOL
+
+
+def test_adjmix_large_rows():
+    n, c, t, v, k = 16, 64, 64, 11, 3
+    x, g = rnd(n, c, t, v, seed=1), rnd(n, k * c, t, v, seed=3)
+    assert rel(ops.adjmix_bwd_a(cu(x), cu(g), k), emu.adjmix_bwd_a(dbl(x), dbl(g), k)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 4, 7), (2, 512, 4, 1), (33, 3, 64, 25)])
+def test_pointwise(shape):
+    n, c, t, v = shape
+    a, b, o = rnd(*shape, seed=1), rnd(*shape, seed=2), rnd(*shape, seed=3)
+    bias, nw, noise = rnd(c, seed=4), rnd(c, seed=5), rnd(n, 1, t, v, seed=6)
+    for act in (0, 1, 2):
+        assert rel(ops.epilogue_fwd(cu(a), cu(b), cu(bias), cu(nw), cu(noise), act), emu.epilogue_fwd(dbl(a), dbl(b), dbl(bias), dbl(nw), dbl(noise), act)) < TOL
+        assert rel(ops.epilogue_fwd(cu(a), None, None, None, None, act), emu.epilogue_fwd(dbl(a), act=act)) < TOL
+        assert rel(ops.act_bwd(cu(a), cu(o), act), emu.act_bwd(dbl(a), dbl(o), act)) < TOL
+    assert rel(ops.chan_reduce(cu(a)), emu.chan_reduce(dbl(a))) < TOL
+    assert rel(ops.chan_reduce(cu(a), cu(noise)), emu.chan_reduce(dbl(a), dbl(noise))) < TOL
+    e = rnd(n, 6, seed=7)
+    cat = ops.label_concat(cu(e), cu(a))
+    assert torch.equal(cat.cpu(), emu.label_concat(e, a))
+    ge, gx = ops.label_split(cat, 6)
+    rge, rgx = emu.label_split(dbl(cat.cpu()), 6)
+    assert rel(ge, rge) < TOL and torch.equal(gx.cpu(), a)
+    alpha = torch.rand(n)
+    assert rel(ops.interpolate(cu(alpha), cu(a), cu(b)), emu.interpolate(dbl(alpha), dbl(a), dbl(b))) < TOL
+
+
+def test_plane_spmm_tables():
+    from oracle.graph import SkeletonTables
+    t = SkeletonTables("ntu")
+    x = rnd(3, 5, 4, 11, seed=1)
+    U = G.upsample_matrix(t.mapping[0], 11, halve=False)
+    tab = G.resample_table(4, 11, 8, U)
+    for tb, inp in ((tab, x), (tab.T, rnd(3, 5, 8, 25, seed=2)), (G.mean_table(4, 11), x),
+                    (G.select_table(4, 11, [0, 2], [1, 5, 7]), x)):
+        assert rel(ops.plane_spmm(cu(inp), tb), emu.plane_spmm(dbl(inp), tb)) < TOL
+
+
+@pytest.mark.parametrize("shape", [(4, 6, 5, 3), (32, 3, 32, 11), (2, 256, 4, 1)])
+def test_batchnorm(shape):
+    n, c, t, v = shape
+    x, gy = rnd(*shape, seed=1) * 2 + 0.5, rnd(*shape, seed=2)
+    gamma, beta = rnd(c, seed=3), rnd(c, seed=4)
+    rm, rv = rnd(c, seed=5), rnd(c, seed=6).abs() + 0.5
+    rm_c, rv_c = cu(rm), cu(rv)
+    mean, rstd = ops.bn_stats(cu(x), rm_c, rv_c, 1e-5, 0.1)
+    rm_r, rv_r = dbl(rm).clone(), dbl(rv).clone()
+    mean_r, rstd_r = emu.bn_stats(dbl(x), rm_r, rv_r, 1e-5, 0.1)
+    assert rel(mean, mean_r) < TOL and rel(rstd, rstd_r) < TOL and rel(rm_c, rm_r) < TOL and rel(rv_c, rv_r) < TOL
+    assert rel(ops.bn_apply(cu(x), mean, rstd, cu(gamma), cu(beta)), emu.bn_apply(dbl(x), mean_r, rstd_r, dbl(gamma), dbl(beta))) < TOL
+    got = ops.bn_bwd(cu(gy), cu(x), mean, rstd, cu(gamma))
+    ref = emu.bn_bwd(dbl(gy), dbl(x), mean_r, rstd_r, dbl(gamma))
+    for a, b in zip(got, ref):
+        assert rel(a, b) < 5 * TOL
+
+
+def test_adam():
+    p, g = rnd(100003, seed=1), rnd(100003, seed=2)
+    m, v = rnd(100003, seed=3) * 0.1, rnd(100003, seed=4).abs() * 0.01
+    pc, mc, vc = cu(p), cu(m), cu(v)
+    pr, mr, vr = dbl(p).clone(), dbl(m).clone(), dbl(v).clone()
+    for step in (1, 2, 7):
+        ops.adam_step(pc, cu(g), mc, vc, 2e-4, 0.5, 0.999, 1e-8, step, 0.5)
+        emu.adam_step(pr, dbl(g), mr, vr, 2e-4, 0.5, 0.999, 1e-8, step, 0.5)
+    assert rel(pc, pr) < 1e-6 and rel(mc, mr) < TOL and rel(vc, vr) < TOL
+
+
+def test_errors_are_reported_not_thrown():
+    _lib = __import__("importlib").import_module("kinetic-gan_b200._lib")
+    lib = _lib.lib()
+    assert lib.kgan_adjmix_fwd(0, 0, 0, 1, 1, 1, 1, 1, 1, 0) != 0
+    assert b"null" in lib.kgan_last_error()
