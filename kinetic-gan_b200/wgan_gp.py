@@ -29,3 +29,93 @@ def compute_gradient_penalty(D, real_samples, fake_samples, labels, alpha=None, 
     flat = gradients.reshape(n, -1)
     gradient_penalty = ((flat.norm(2, dim=1) - 1) ** 2).mean()
     return (gradient_penalty, gradients) if return_gradients else gradient_penalty
+
+
+class FlatParams:
+    """All parameters of a module re-seated as views of ONE flat fp32 buffer (plus flat grad / Adam moments).
+    Offsets are 128-byte aligned so that vectorised and bulk (TMA) loads of any weight are legal."""
+
+    ALIGN = 32
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters()]
+        dev = self.params[0].device
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.numel = sum(p.numel() for p in self.params)
+        for p, o in zip(self.params, offs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view_as(p)
+            p.grad = self.grad[o:o + n].view_as(p)
+        self.step = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p in self.params:               # autograd accumulates in place into these views
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr():
+                raise RuntimeError("parameter gradient was re-seated outside the flat buffer")
+
+    def adam(self, lr, b1, b2, eps=1e-8, grad_scale=1.0):
+        self.step += 1
+        ops.adam_step(self.flat, self.grad, self.m, self.v, lr, b1, b2, eps, self.step, grad_scale)
+
+
+class WGANGPTrainer:
+    """The loop body kinetic-gan.py:137-174 as two methods.  `iteration(i, ...)` = critic step every iteration,
+    generator step when i % n_critic == 0 (:160).  Optional `comm` (ddp.Comm) sums the flat gradients across ranks."""
+
+    def __init__(self, generator, discriminator, lr=0.0002, b1=0.5, b2=0.999, n_critic=5, lambda_gp=10, comm=None):
+        self.G, self.D = generator, discriminator
+        self.lr, self.b1, self.b2, self.n_critic, self.lambda_gp = lr, b1, b2, n_critic, lambda_gp
+        self.comm = comm
+        if comm is not None:
+            comm.broadcast_module(self.G)
+            comm.broadcast_module(self.D)
+        self.fg, self.fd = FlatParams(self.G), FlatParams(self.D)
+        self.world = 1 if comm is None else comm.world_size
+
+    def _reduce(self, flat):
+        if self.comm is not None and self.world > 1:
+            self.comm.all_reduce_sum_(flat.grad)
+
+    def d_step(self, real, labels, z, alpha=None, noises=None):
+        """kinetic-gan.py:137-155."""
+        self.fd.zero_grad()
+        with torch.no_grad():           # G's graph is never used by the critic update (its grads are zeroed at :157)
+            fake = self.G(z, labels, noises=noises)
+        real_validity = self.D(real, labels)
+        fake_validity = self.D(fake, labels)
+        gp = compute_gradient_penalty(self.D, real, fake, labels, alpha)
+        d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + self.lambda_gp * gp
+        d_loss.backward()
+        self._reduce(self.fd)
+        self.fd.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
+        return d_loss.detach(), gp.detach()
+
+    def g_step(self, labels, z, noises=None):
+        """kinetic-gan.py:167-174; the critic's weight gradients are not needed (zeroed at :137 before use)."""
+        self.fg.zero_grad()
+        for p in self.fd.params:
+            p.requires_grad_(False)
+        try:
+            fake = self.G(z, labels, noises=noises)
+            g_loss = -torch.mean(self.D(fake, labels))
+            g_loss.backward()
+        finally:
+            for p in self.fd.params:
+                p.requires_grad_(True)
+        self._reduce(self.fg)
+        self.fg.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
+        return g_loss.detach()
+
+    def iteration(self, i, real, labels, z, alpha=None, noises_d=None, noises_g=None):
+        d_loss, gp = self.d_step(real, labels, z, alpha, noises_d)
+        g_loss = self.g_step(labels, z, noises_g) if i % self.n_critic == 0 else None
+        return d_loss, g_loss, gp

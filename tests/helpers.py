@@ -68,3 +68,12 @@ def within_noise_floor(mine, gold, key, tag, tol, floor_mult=4.0):
         floor = np.linalg.norm(ref - r64)
         return np.linalg.norm(mine - r64) <= floor_mult * floor + tol * np.linalg.norm(r64)
     return False
+
+
+def parity_ok(mine, gold, key, tol, floor_mult=4.0):
+    """fp32 CUDA result vs the fp64 ground truth of the reference: within `tol` rel-L2, or - for ill-conditioned
+    quantities (BatchNorm over a handful of samples) - within floor_mult x the reference's OWN fp32-vs-fp64 distance."""
+    mine = np.asarray(mine.detach().cpu() if torch.is_tensor(mine) else mine, dtype=np.float64)
+    r64, r32 = gold["f64" + key], gold["f32" + key]
+    err = np.linalg.norm(mine - r64)
+    return err <= tol * np.linalg.norm(r64) or err <= floor_mult * np.linalg.norm(r32 - r64) + tol * np.linalg.norm(r64)

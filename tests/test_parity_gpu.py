@@ -12,7 +12,7 @@ import torch
 import kgan_b200 as kgan
 from oracle import networks as onet
 from oracle.graph import SkeletonTables
-from helpers import CASES, draw_noises, inputs, load_golden, rel_l2, sub, within_noise_floor
+from helpers import CASES, draw_noises, inputs, load_golden, parity_ok, rel_l2, sub, within_noise_floor
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -46,18 +46,18 @@ def test_generator_vs_golden(case):
     for h in hooks:
         h.remove()
     for i, b in enumerate(blocks):
-        assert rel_l2(b, gold["f64/g_block%d" % i]) < TOL, i
-    assert rel_l2(fake, gold["f64/g_out"]) < TOL
+        assert parity_ok(b, gold, "/g_block%d" % i, TOL), (i, rel_l2(b, gold["f64/g_block%d" % i]))
+    assert parity_ok(fake, gold, "/g_out", TOL), rel_l2(fake, gold["f64/g_out"])
     (fake * x["cot_g"]).sum().backward()
     for k, p in G.named_parameters():
         assert within_noise_floor(sub(p.grad), gold, "/g_grad/" + k, "f32", 5e-4), k
     for k, b in G.named_buffers():
         if "running" in k:
-            assert rel_l2(b, gold["f64/g_bn_after/" + k]) < TOL, k
+            assert parity_ok(b, gold, "/g_bn_after/" + k, TOL), k
     G.eval()
     G.load_state_dict(onet.synth_params(onet.g_param_shapes(cfg), 1))
     ev = G(x["z"], x["labels"], noises=[t.cuda() for t in draw_noises(cfg, n, 12)])
-    assert rel_l2(ev, gold["f64/g_out_eval"]) < TOL
+    assert parity_ok(ev, gold, "/g_out_eval", TOL), rel_l2(ev, gold["f64/g_out_eval"])
 
 
 @pytest.mark.parametrize("case", list(CASES))
