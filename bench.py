@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Headline benchmark: WGAN-GP training throughput (samples/s) of Kinetic-GAN at the NTU 25x64x3 shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kgan|reference] [--batch B] [--precision fp32|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one iteration of the training loop body kinetic-gan.py:137-174 on one synthetic batch per GPU: the critic
+update (G forward, 3 critic forwards, gradient penalty with double backward, Adam) and, every n_critic=5 iterations,
+the generator update.  Workload (BASELINE.json configs[2]/[3]): kinetic-gan-mlp8, NTU-120 shape (25 joints x 64 frames
+x 3, 120 classes), random-init weights, synthetic data; weak scaling (fixed per-GPU batch).
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs per train sample, NTU-120 mlp8: 1.6 F_G + 10.4 F_D (SURVEY.md §8d / BASELINE.md §3)
+F_G, F_D = 32.24e6, 550.62e6
+FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
+WORKLOAD = "kinetic-gan-mlp8 NTU-120 xsub shape (25x64x3, 120 classes), WGAN-GP training, n_critic=5"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"      # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7 and f[0] == str(self.index):
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def physical_index(local_rank):
+    """nvidia-smi index of the GPU this rank drives."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v for v in vis.split(",") if v.strip().isdigit()]
+    return int(ids[local_rank]) if local_rank < len(ids) else local_rank
+
+
+def oracle_trainer(batch, per_sample_loop=True):
+    """The CPU restatement of the reference step (oracle/networks.py) at NTU-120 mlp8 - `kind: port`."""
+    import torch
+
+    from oracle import networks as onet
+    from oracle.graph import SkeletonTables
+
+    cfg = onet.Config(dataset="ntu", n_classes=120, t_size=64, mlp_dim=8, channels=3)
+    tables = SkeletonTables("ntu")
+    pg = onet.synth_params(onet.g_param_shapes(cfg, tables), 1, reference_init=True)
+    pd = onet.synth_params(onet.d_param_shapes(cfg, tables), 2)
+    tr = onet.Trainer(cfg, pg, pd, tables, per_sample_loop=per_sample_loop)
+    g = torch.Generator().manual_seed(0)
+
+    def batch_fn():
+        real = torch.rand(batch, 3, 64, 25, generator=g) * 2 - 1
+        labels = torch.randint(0, 120, (batch,), generator=g)
+        z = torch.randn(batch, 512, generator=g)
+        alpha = torch.rand(batch, 1, 1, 1, generator=g)
+        nz = [torch.randn(*s, generator=g) for s in onet.noise_shapes(cfg, batch, tables)]
+        nz2 = [torch.randn(*s, generator=g) for s in onet.noise_shapes(cfg, batch, tables)]
+        return real, labels, z, alpha, nz, nz2
+
+    return tr, batch_fn
+
+
+def time_oracle(batch, steps, warmup, first_index):
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr, batch_fn = oracle_trainer(batch)
+    i = first_index
+    for _ in range(warmup):
+        tr.iteration(i, *batch_fn())
+        i += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.iteration(i, *batch_fn())
+        i += 1
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port: same torch CPU operators in the reference's order,
+    including its per-sample mapping loop) on the host cores; each step = one iteration on a bounded batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = args.cpu_batch
+    sps, ms, cores = time_oracle(b, args.steps, args.warmup, first_index=0)
+    line = {
+        "impl": "reference", "metric": "wgan_gp_train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": b, "note": "CPU port of the reference step (oracle/networks.py), host cores only"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d iterations of batch %d (NTU-120 mlp8) after %d warm-up" % (args.steps, b, args.warmup)},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_kgan(args):
+    import torch
+
+    import kgan_b200 as kgan
+    from importlib import import_module
+
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    ddp = import_module("kinetic-gan_b200.ddp")
+    ops = kgan.ops
+    comm = ddp.Comm()
+    dev = torch.device("cuda", comm.local_rank)
+    torch.cuda.set_device(dev)
+    kgan.set_precision(args.precision)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    torch.manual_seed(0)
+    G = kgan.Generator(512, 3, 120, 64, mlp_dim=8).to(dev)
+    D = kgan.Discriminator(3, 120, 64, 512).to(dev)
+    G.train()
+    tr = wg.WGANGPTrainer(G, D, comm=comm)
+
+    # synthetic inputs: a small pool of distinct batches, per-rank RNG streams
+    gcpu = torch.Generator().manual_seed(1234 + comm.rank)
+    POOL = 4
+    host = []
+    for _ in range(POOL):
+        host.append(dict(real=(torch.rand(B, 3, 64, 25, generator=gcpu) * 2 - 1).pin_memory(),
+                         labels=torch.randint(0, 120, (B,), generator=gcpu).pin_memory(),
+                         z=torch.randn(B, 512, generator=gcpu).pin_memory(),
+                         alpha=torch.rand(B, 1, 1, 1, generator=gcpu).pin_memory()))
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step_resident(i):
+        x = resident[i % POOL]
+        return tr.iteration(i, x["real"], x["labels"], x["z"], x["alpha"])
+
+    def step_e2e(i):
+        h = host[i % POOL]
+        x = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        d_loss, _, _ = tr.iteration(i, x["real"], x["labels"], x["z"], x["alpha"])
+        return d_loss.item()                      # device -> host read of the step's result
+
+    def timed(fn, first):
+        comm.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, first + K):
+            fn(i)
+        e1.record()
+        comm.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        comm.all_reduce_max_(ms)
+        return ms.item()
+
+    it = 0
+    for _ in range(max(W, 3)):
+        step_resident(it)
+        it += 1
+    torch.cuda.synchronize()
+    l0 = ops.launches
+    sampler = ClockSampler(physical_index(comm.local_rank))
+    sampler.start()
+    ms_total = timed(step_resident, it)
+    clocks = sampler.stop()
+    launches = ops.launches - l0
+    it += K
+    value = B * comm.world_size * K / (ms_total * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e(it)
+        it += 1
+        # keep the n_critic phase of the timed window identical to the resident run
+        while it % 5 != (max(W, 3)) % 5:
+            step_e2e(it)
+            it += 1
+        ms_e2e = timed(step_e2e, it)
+        it += K
+        e2e = {"value": B * comm.world_size * K / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    # roofline of the dominant kernel family, measured live with CUDA events around every launch of one more pass
+    prof = ops.profile_start()
+    for i in range(it, it + 5):
+        step_resident(i)
+    torch.cuda.synchronize()
+    fam = ops.profile_stop(prof)
+    it += 5
+    tensor_peak, hbm_peak, peak_kind = peaks()
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    name, st = top
+    achieved = st["flops"] / (st["ms"] * 1e-3) / 1e12
+    total_ms = sum(v["ms"] for v in fam.values())
+    roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": None, "peak_kind": peak_kind + " bf16 sustained",
+                "launches_per_step": st["n"] / 5, "avg_launch_ms": st["ms"] / st["n"],
+                "share_of_kgan_kernel_time": st["ms"] / total_ms,
+                "step_algorithmic_tflops": FLOP_PER_SAMPLE * value / 1e12 / comm.world_size,
+                "families": {k: {"ms_per_step": v["ms"] / 5, "launches_per_step": v["n"] / 5,
+                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()}}
+
+    cpu = None
+    if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
+        sps, ms, cores = time_oracle(args.cpu_batch, 5, 1, first_index=4)     # one n_critic cycle: i = 5..9 after i = 4
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "one n_critic cycle (5 iterations, 1 G step) of batch %d, NTU-120 mlp8, after 1 warm-up" % args.cpu_batch}
+
+    if comm.rank == 0:
+        line = {
+            "metric": "wgan_gp_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": comm.world_size, "steps": K,
+            "warmup": max(W, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size,
+                       "parallelism": "dp%d" % comm.world_size, "n_critic": 5, "flop_per_sample": FLOP_PER_SAMPLE,
+                       "l2_policy": "per-step working set (activations of 4 critic passes at batch %d, >1 GB) exceeds the 126 MB L2; "
+                                    "inputs rotate over a pool of %d batches" % (B, POOL)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    comm.close()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_kgan(a)

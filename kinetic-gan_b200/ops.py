@@ -40,6 +40,46 @@ def _count(n=1):
     launches += n
 
 
+# ---- optional per-launch timing (bench.py roofline pass): CUDA events on the launching stream around each call
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+    return _prof
+
+
+def profile_stop(prof):
+    """-> {family: {"ms": total, "n": launches, "flops": total algorithmic flops}} (synchronises)."""
+    global _prof
+    _prof = None
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, e0, e1 in prof:
+        d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+        d["flops"] += flops
+    return out
+
+
+def _run(family, flops, fn, *args):
+    """One kernel launch through the C ABI (+ CUDA events around it when profiling)."""
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(fn(*args), fn.__name__)
+    _count()
+    if _prof is not None:
+        e1.record()
+        _prof.append((family, flops, e0, e1))
+
+
+def _tap_flops(desc, n):
+    return 2.0 * n * desc.p_out * desc.co * desc.ck * desc.ntap * desc.groups
+
+
 def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     _chk(x, w, bias, add)
     n = x.shape[0]
@@ -48,9 +88,8 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     if add is not None:
         assert add.shape == out.shape
     l = _lib.lib()
-    _lib.check(l.kgan_tapconv_fwd(desc.cstruct(n, act, _precision), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
-                                  _ptr(bias), _ptr(add), out.data_ptr(), _stream()), "kgan_tapconv_fwd")
-    _count()
+    _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, desc.cstruct(n, act, _precision), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
+                                  _ptr(bias), _ptr(add), out.data_ptr(), _stream())
     return out
 
 
@@ -59,9 +98,8 @@ def tapconv_wgrad(x, gout, desc, w_shape):
     n = x.shape[0]
     dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
     l = _lib.lib()
-    _lib.check(l.kgan_tapconv_wgrad(desc.cstruct(n, ACT_NONE, _precision), x.data_ptr(), gout.data_ptr(),
-                                    desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream()), "kgan_tapconv_wgrad")
-    _count()
+    _run('tapconv_wgrad', _tap_flops(desc, n), l.kgan_tapconv_wgrad, desc.cstruct(n, ACT_NONE, _precision), x.data_ptr(), gout.data_ptr(),
+                                    desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
     return dw
 
 
@@ -71,8 +109,7 @@ def adjmix_fwd(x, A):
     k, v2, w = A.shape
     assert v2 == v
     out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_adjmix_fwd(x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_fwd")
-    _count()
+    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream())
     return out
 
 
@@ -83,8 +120,7 @@ def adjmix_bwd_x(g, A):
     assert w2 == w and kc % k == 0
     c = kc // k
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_adjmix_bwd_x(g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_bwd_x")
-    _count()
+    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream())
     return gx
 
 
@@ -94,8 +130,7 @@ def adjmix_bwd_a(x, g, k):
     w = g.shape[3]
     assert g.shape[0] == n and g.shape[1] == k * c and g.shape[2] == t
     gA = torch.empty((k, v, w), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_adjmix_bwd_a(x.data_ptr(), g.data_ptr(), gA.data_ptr(), n, c, t, v, w, k, _stream()), "kgan_adjmix_bwd_a")
-    _count()
+    _run('adjmix_bwd_a', 0.0, _lib.lib().kgan_adjmix_bwd_a, x.data_ptr(), g.data_ptr(), gA.data_ptr(), n, c, t, v, w, k, _stream())
     return gA
 
 
@@ -103,17 +138,15 @@ def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=ACT_NONE):
     _chk(a, b, bias, nw, noise)
     n, c, t, v = a.shape
     out = torch.empty_like(a)
-    _lib.check(_lib.lib().kgan_epilogue_fwd(a.data_ptr(), _ptr(b), _ptr(bias), _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act,
-                                            _stream()), "kgan_epilogue_fwd")
-    _count()
+    _run('pointwise', 0.0, _lib.lib().kgan_epilogue_fwd, a.data_ptr(), _ptr(b), _ptr(bias), _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act,
+                                            _stream())
     return out
 
 
 def act_bwd(gout, out, act):
     _chk(gout, out)
     gz = torch.empty_like(out)
-    _lib.check(_lib.lib().kgan_act_bwd(gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream()), "kgan_act_bwd")
-    _count()
+    _run('pointwise', 0.0, _lib.lib().kgan_act_bwd, gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream())
     return gz
 
 
@@ -121,8 +154,7 @@ def chan_reduce(g, mul=None):
     _chk(g, mul)
     n, c, t, v = g.shape
     out = torch.empty((c,), device=g.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_chan_reduce(g.data_ptr(), _ptr(mul), out.data_ptr(), n, c, t * v, _stream()), "kgan_chan_reduce")
-    _count()
+    _run('reduce', 0.0, _lib.lib().kgan_chan_reduce, g.data_ptr(), _ptr(mul), out.data_ptr(), n, c, t * v, _stream())
     return out
 
 
@@ -132,9 +164,8 @@ def plane_spmm(x, table):
     assert t * v == table.p_in, (tuple(x.shape), table.p_in)
     idx, wgt = table.on(x.device)
     out = torch.empty((n, c, table.t_out, table.v_out), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_plane_spmm(x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
-                                          table.J, _stream()), "kgan_plane_spmm")
-    _count()
+    _run('plane_spmm', 0.0, _lib.lib().kgan_plane_spmm, x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
+                                          table.J, _stream())
     return out
 
 
@@ -143,8 +174,7 @@ def label_concat(e, x):
     n, c, t, v = x.shape
     ncls = e.shape[1]
     out = torch.empty((n, ncls + c, t, v), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_label_concat(e.data_ptr(), x.data_ptr(), out.data_ptr(), n, ncls, c, t * v, _stream()), "kgan_label_concat")
-    _count()
+    _run('label', 0.0, _lib.lib().kgan_label_concat, e.data_ptr(), x.data_ptr(), out.data_ptr(), n, ncls, c, t * v, _stream())
     return out
 
 
@@ -154,8 +184,7 @@ def label_split(g, ncls, need_e=True, need_x=True):
     c = ct - ncls
     ge = torch.empty((n, ncls), device=g.device, dtype=torch.float32) if need_e else None
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32) if need_x else None
-    _lib.check(_lib.lib().kgan_label_split(g.data_ptr(), _ptr(ge), _ptr(gx), n, ncls, c, t * v, _stream()), "kgan_label_split")
-    _count()
+    _run('label', 0.0, _lib.lib().kgan_label_split, g.data_ptr(), _ptr(ge), _ptr(gx), n, ncls, c, t * v, _stream())
     return ge, gx
 
 
@@ -164,9 +193,8 @@ def bn_stats(x, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
     n, c, t, v = x.shape
     mean = torch.empty((c,), device=x.device, dtype=torch.float32)
     rstd = torch.empty((c,), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_bn_stats(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), n, c, t * v,
-                                        eps, momentum, _stream()), "kgan_bn_stats")
-    _count()
+    _run('batchnorm', 0.0, _lib.lib().kgan_bn_stats, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), n, c, t * v,
+                                        eps, momentum, _stream())
     return mean, rstd
 
 
@@ -174,9 +202,8 @@ def bn_apply(x, mean, rstd, gamma, beta):
     _chk(x, mean, rstd, gamma, beta)
     n, c, t, v = x.shape
     y = torch.empty_like(x)
-    _lib.check(_lib.lib().kgan_bn_apply(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c,
-                                        t * v, _stream()), "kgan_bn_apply")
-    _count()
+    _run('batchnorm', 0.0, _lib.lib().kgan_bn_apply, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c,
+                                        t * v, _stream())
     return y
 
 
@@ -186,24 +213,20 @@ def bn_bwd(gy, x, mean, rstd, gamma):
     gx = torch.empty_like(x)
     gg = torch.empty((c,), device=x.device, dtype=torch.float32)
     gb = torch.empty((c,), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().kgan_bn_bwd(gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
-                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _stream()), "kgan_bn_bwd")
-    _count()
+    _run('batchnorm', 0.0, _lib.lib().kgan_bn_bwd, gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
+                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _stream())
     return gx, gg, gb
 
 
 def adam_step(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
     _chk(p, g, m, v)
-    _lib.check(_lib.lib().kgan_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, step,
-                                         grad_scale, _stream()), "kgan_adam_step")
-    _count()
+    _run('adam', 0.0, _lib.lib().kgan_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, step,
+                                         grad_scale, _stream())
 
 
 def interpolate(alpha, x, y):
     _chk(alpha, x, y)
     n = x.shape[0]
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().kgan_interpolate(alpha.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, _stream()),
-               "kgan_interpolate")
-    _count()
+    _run('pointwise', 0.0, _lib.lib().kgan_interpolate, alpha.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, _stream())
     return out
