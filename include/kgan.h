@@ -30,7 +30,7 @@ enum { KGAN_PREC_FP32 = 0 /* SIMT fp32 FMA */, KGAN_PREC_TF32 = 1 /* tcgen05 kin
  * temporal conv, the residual 1x1 conv, the mapping MLP and the critic head all reduce to, in
  * forward, data-gradient and weight-gradient form.
  *
- *   out[n, out_ch0 + oc, p] = act( bias[oc] + add[n, oc, p]
+ *   out[n, out_ch0 + oc, p] = act( bias[oc] + add[n, oc, p (or p % add_period)]
  *        + sum_{tap < ntap} sum_{ic < ck}  W[w_base + tap_w_off[tap] + woff(oc) + ic*w_ic]
  *                                        * in[n, in_ch0 + tap_in_ch[tap] + ic, pmap[tap_row[tap]*p_out + p]] )
  *   woff(oc) = w_oc_blk ? (oc / w_oc_blk) * w_ocblk + (oc % w_oc_blk) * w_oc : oc * w_oc
@@ -55,6 +55,8 @@ typedef struct kgan_tapconv_desc {
     int32_t tap_in_ch[KGAN_MAX_TAPS];
     int64_t tap_w_off[KGAN_MAX_TAPS];
     int32_t tap_row[KGAN_MAX_TAPS];  /* row of pmap used by the tap */
+    int32_t add_period;        /* 0: `add` has the shape of out; else add is (N, c_out_total, add_period) and is read at
+                                  p % add_period (a term that is constant over frames, broadcast along T) */
     int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */
     int32_t precision;         /* KGAN_PREC_* */
 } kgan_tapconv_desc;

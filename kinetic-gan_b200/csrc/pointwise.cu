@@ -36,10 +36,24 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------------
 // adjacency product
 // ------------------------------------------------------------------------------------------------
+// A_eff = A (.) edge_importance keeps the sparsity of the skeleton partitions (73 of 1875 entries at 25 joints), so
+// both kernels first compact the non-zero entries of A in shared memory and then touch only those: exact (a zero
+// multiplicand contributes nothing) and ~V times fewer instructions than the dense loop.
 __global__ void __launch_bounds__(PT) adjmix_fwd_k(const float* __restrict__ x, const float* __restrict__ A, float* __restrict__ out,
                                                     int n, int c, int t, int v, int w, int k) {
-    extern __shared__ float As[];   // [k][v][w]
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;                                   // [k][v][w]
+    int* nzv = (int*)(sm + k * v * w);                // [k*w][v] source joints with A != 0
+    int* nzc = nzv + k * w * v;                       // [k*w]
     for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[i] = A[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * w; i += blockDim.x) {
+        const int kk = i / w, ww = i - kk * w;
+        int cnt = 0;
+        for (int j = 0; j < v; ++j)
+            if (As[(kk * v + j) * w + ww] != 0.f) nzv[i * v + cnt++] = j;
+        nzc[i] = cnt;
+    }
     __syncthreads();
     const int64_t total = (int64_t)n * k * c * t * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -51,20 +65,34 @@ __global__ void __launch_bounds__(PT) adjmix_fwd_k(const float* __restrict__ x, 
         const int nn = (int)(r / ((int64_t)k * c));
         const int kk = kc / c, cc = kc - kk * c;
         const float* xr = x + (((int64_t)nn * c + cc) * t + tt) * v;
-        const float* a = As + (kk * v) * w + ww;
+        const int kw = kk * w + ww, cnt = nzc[kw];
         float acc = 0.f;
-        for (int j = 0; j < v; ++j) acc = fmaf(__ldg(xr + j), a[j * w], acc);
+        for (int j = 0; j < cnt; ++j) {
+            const int vv = nzv[kw * v + j];
+            acc = fmaf(__ldg(xr + vv), As[(kk * v + vv) * w + ww], acc);
+        }
         out[i] = acc;
     }
 }
 
 __global__ void __launch_bounds__(PT) adjmix_bwd_x_k(const float* __restrict__ g, const float* __restrict__ A, float* __restrict__ gx,
                                                       int n, int c, int t, int v, int w, int k) {
-    extern __shared__ float As[];   // [k][v][wp], wp odd to spread banks across v
-    const int wp = w | 1;
-    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[(i / w) * wp + (i % w)] = A[i];
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;                                   // [k][v][w]
+    int* nzw = (int*)(sm + k * v * w);                // [v][k*w] (k*w + w index) with A != 0
+    int* nzc = nzw + v * k * w;                       // [v]
+    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[i] = A[i];
+    __syncthreads();
+    for (int vv = threadIdx.x; vv < v; vv += blockDim.x) {
+        int cnt = 0;
+        for (int kk = 0; kk < k; ++kk)
+            for (int ww = 0; ww < w; ++ww)
+                if (As[(kk * v + vv) * w + ww] != 0.f) nzw[vv * k * w + cnt++] = kk * w + ww;
+        nzc[vv] = cnt;
+    }
     __syncthreads();
     const int64_t total = (int64_t)n * c * t * v;
+    const int64_t kstride = (int64_t)c * t * w;       // distance between partitions k of the same (n, c, t) row in g
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int vv = (int)(i % v);
         int64_t r = i / v;
@@ -72,59 +100,74 @@ __global__ void __launch_bounds__(PT) adjmix_bwd_x_k(const float* __restrict__ g
         r /= t;
         const int cc = (int)(r % c);
         const int nn = (int)(r / c);
+        const float* gr = g + (((int64_t)nn * k * c + cc) * t + tt) * w;
+        const int cnt = nzc[vv];
         float acc = 0.f;
-        for (int kk = 0; kk < k; ++kk) {
-            const float* gr = g + (((int64_t)nn * k * c + (int64_t)kk * c + cc) * t + tt) * w;
-            const float* a = As + (kk * v + vv) * wp;
-            for (int j = 0; j < w; ++j) acc = fmaf(__ldg(gr + j), a[j], acc);
+        for (int j = 0; j < cnt; ++j) {
+            const int e = nzw[vv * k * w + j], kk = e / w, ww = e - kk * w;
+            acc = fmaf(__ldg(gr + kk * kstride + ww), As[(kk * v + vv) * w + ww], acc);
         }
         gx[i] = acc;
     }
 }
 
-// gA[k,v,w] = sum over rows of x[row, v] * g[row(k), w].  Each CTA stages ROWS rows and every thread owns
-// a strided subset of the k*v*w outputs; partial sums merged with one atomic per output per CTA.
-constexpr int AROWS = 32;
+// gA[k,v,w] = sum over rows of x[row, v] * g[row(k), w]: a (k*w) x v GEMM with a very long contraction (all rows).
+// Each CTA stages AROWS rows in shared memory (zero-padded to multiples of 4 joints); every thread owns one 4x4
+// (v, w) register tile of one partition k and a strided subset of the staged rows; partial tiles are merged with
+// fp32 atomics (k*v*w <= 1875 addresses).
+constexpr int AROWS = 64;
 __global__ void __launch_bounds__(PT) adjmix_bwd_a_k(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gA,
                                                       int n, int c, int t, int v, int w, int k, int64_t rows_per_cta) {
-    extern __shared__ float sm[];
-    float* xs = sm;                       // [AROWS][v]
-    float* gs = sm + AROWS * v;           // [k][AROWS][w]
+    extern __shared__ __align__(16) float sm[];
+    const int vp = (v + 3) & ~3, wp = (w + 3) & ~3;
+    float* xs = sm;                        // [AROWS][vp]
+    float* gs = sm + AROWS * vp;           // [k][AROWS][wp]
+    const int vt = vp >> 2, wt = wp >> 2, ntile = k * vt * wt;
+    const int rgroups = max(1, PT / ntile);                      // row groups sharing the CTA
+    const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
+    const bool active = grp < rgroups && (int)threadIdx.x < rgroups * ntile;
+    const int kk = tile / (vt * wt), v0 = ((tile / wt) % vt) * 4, w0 = (tile % wt) * 4;
     const int64_t rows = (int64_t)n * c * t;
     const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta, rend = min(rows, rbeg + rows_per_cta);
-    const int nout = k * v * w;
-    constexpr int MAXO = 8;               // outputs per thread (k*v*w <= 2048)
-    float acc[MAXO];
+    float acc[4][4];
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) acc[o] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int64_t r0 = rbeg; r0 < rend; r0 += AROWS) {
         const int nr = (int)min((int64_t)AROWS, rend - r0);
-        for (int i = threadIdx.x; i < nr * v; i += blockDim.x) xs[i] = __ldg(x + r0 * v + i);
-        for (int i = threadIdx.x; i < k * nr * w; i += blockDim.x) {
-            const int ww = i % w, rr = (i / w) % nr, kk = i / (w * nr);
+        for (int i = threadIdx.x; i < nr * vp; i += blockDim.x) {
+            const int rr = i / vp, vv = i - rr * vp;
+            xs[i] = vv < v ? __ldg(x + (r0 + rr) * v + vv) : 0.f;
+        }
+        for (int i = threadIdx.x; i < k * nr * wp; i += blockDim.x) {
+            const int ww = i % wp, rr = (i / wp) % nr, k2 = i / (wp * nr);
             const int64_t row = r0 + rr;                       // (n, c, t)
             const int tt = (int)(row % t);
             const int64_t nc = row / t;
             const int cc = (int)(nc % c), nn = (int)(nc / c);
-            gs[(kk * AROWS + rr) * w + ww] = __ldg(g + (((int64_t)nn * k * c + (int64_t)kk * c + cc) * t + tt) * w + ww);
+            gs[(k2 * AROWS + rr) * wp + ww] = ww < w ? __ldg(g + (((int64_t)nn * k * c + (int64_t)k2 * c + cc) * t + tt) * w + ww) : 0.f;
         }
         __syncthreads();
+        if (active) {
+            for (int rr = grp; rr < nr; rr += rgroups) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + rr * vp + v0);
+                const float4 gv = *reinterpret_cast<const float4*>(gs + (kk * AROWS + rr) * wp + w0);
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-        for (int o = 0; o < MAXO; ++o) {
-            const int oi = threadIdx.x + o * PT;
-            if (oi < nout) {
-                const int ww = oi % w, vv = (oi / w) % v, kk = oi / (w * v);
-                float a = acc[o];
-                for (int rr = 0; rr < nr; ++rr) a = fmaf(xs[rr * v + vv], gs[(kk * AROWS + rr) * w + ww], a);
-                acc[o] = a;
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
             }
         }
         __syncthreads();
     }
+    if (active) {
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) {
-        const int oi = threadIdx.x + o * PT;
-        if (oi < nout) atomicAdd(gA + oi, acc[o]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (v0 + i < v && w0 + j < w) atomicAdd(gA + (kk * v + v0 + i) * w + w0 + j, acc[i][j]);
     }
 }
 
@@ -327,23 +370,26 @@ using namespace kgan;
 
 extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 8192, "adjmix_fwd: bad shape");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 4096, "adjmix_fwd: bad shape");
     const int64_t total = (int64_t)n * k * c * t * w;
-    adjmix_fwd_k<<<grid_for(total), PT, sizeof(float) * k * v * w, (cudaStream_t)stream>>>(x, A, out, n, c, t, v, w, k);
+    const size_t smem = sizeof(float) * (2 * (size_t)k * v * w + k * w);
+    adjmix_fwd_k<<<grid_for(total), PT, smem, (cudaStream_t)stream>>>(x, A, out, n, c, t, v, w, k);
     return check_launch("adjmix_fwd");
 }
 
 extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * (w | 1) <= 8192, "adjmix_bwd_x: bad shape");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 4096, "adjmix_bwd_x: bad shape");
     const int64_t total = (int64_t)n * c * t * v;
-    adjmix_bwd_x_k<<<grid_for(total), PT, sizeof(float) * k * v * (w | 1), (cudaStream_t)stream>>>(g, A, gx, n, c, t, v, w, k);
+    const size_t smem = sizeof(float) * (2 * (size_t)k * v * w + v);
+    adjmix_bwd_x_k<<<grid_for(total), PT, smem, (cudaStream_t)stream>>>(g, A, gx, n, c, t, v, w, k);
     return check_launch("adjmix_bwd_x");
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 8 * PT, "adjmix_bwd_a: k*v*w too large");
+    const int vp = (v + 3) & ~3, wp = (w + 3) & ~3;
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * (vp / 4) * (wp / 4) <= PT, "adjmix_bwd_a: k*v*w too large");
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
     const int64_t rows = (int64_t)n * c * t;
@@ -351,7 +397,7 @@ extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int 
     if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
     const int64_t per = ceil_div64(ceil_div64(rows, ctas), AROWS) * AROWS;
     ctas = ceil_div64(rows, per);
-    const size_t smem = sizeof(float) * (AROWS * v + k * AROWS * w);
+    const size_t smem = sizeof(float) * ((size_t)AROWS * vp + (size_t)k * AROWS * wp);
     adjmix_bwd_a_k<<<(unsigned)ctas, PT, smem, s>>>(x, g, gA, n, c, t, v, w, k, per);
     return check_launch("adjmix_bwd_a");
 }

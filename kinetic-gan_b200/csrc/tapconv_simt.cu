@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_simt(const __grid_constant__ k
             const int64_t o = ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.p_out + p;
             float v = acc[i][j];
             if (bias) v += __ldg(bias + out_ch0 + oc);
-            if (add) v += __ldg(add + o);
+            if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.add_period + p % d.add_period : o));
             out[o] = apply_act(v, d.act);
         }
     }
@@ -187,6 +187,7 @@ static int validate(const kgan_tapconv_desc* d) {
     KGAN_REQUIRE(d->ntap >= 1 && d->ntap <= KGAN_MAX_TAPS, "tapconv: ntap=%d out of range", d->ntap);
     KGAN_REQUIRE(d->groups >= 1 && d->groups <= 65535, "tapconv: groups=%d out of range", d->groups);
     KGAN_REQUIRE(d->act >= KGAN_ACT_NONE && d->act <= KGAN_ACT_TANH, "tapconv: bad act %d", d->act);
+    KGAN_REQUIRE(d->add_period >= 0 && d->add_period <= d->p_out, "tapconv: bad add_period %d", d->add_period);
     for (int t = 0; t < d->ntap; ++t)
         KGAN_REQUIRE(d->tap_in_ch[t] >= 0 && d->tap_in_ch[t] + d->ck + (d->groups - 1) * d->g_in <= d->c_in_total,
                      "tapconv: tap %d reads channels beyond c_in_total", t);

@@ -14,11 +14,23 @@ import torch
 from torch.autograd import Function
 
 from . import ops
+from .geometry import PlaneTable, mean_table  # noqa: F401
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH  # noqa: F401
 
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+_SUM_T = {}
+
+
+def sum_t_table(t, v):
+    from .geometry import sum_t_table as make
+
+    if (t, v) not in _SUM_T:
+        _SUM_T[(t, v)] = make(t, v)
+    return _SUM_T[(t, v)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -78,6 +90,7 @@ class TapConvEp(Function):
     @staticmethod
     def forward(ctx, x, w, bias, add, geom, act):
         ctx.geom, ctx.act = geom, act
+        ctx.add_bcast = add is not None and add.shape[2] == 1 and geom.t_out > 1
         out = ops.tapconv_fwd(_c(x), _c(w), geom.fwd, bias, None if add is None else _c(add), act)
         ctx.save_for_backward(x, w, out)
         return out
@@ -90,7 +103,9 @@ class TapConvEp(Function):
         gx = TapConvDgrad.apply(gz, w, ctx.geom) if ctx.needs_input_grad[0] else None
         gw = TapConvWgrad.apply(x, gz, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
         gb = ChanSum.apply(gz) if ctx.needs_input_grad[2] else None
-        ga = gz if ctx.needs_input_grad[3] else None
+        ga = None
+        if ctx.needs_input_grad[3]:
+            ga = PlaneSpmm.apply(gz, sum_t_table(ctx.geom.t_out, ctx.geom.v_out)) if ctx.add_bcast else gz
         return gx, gw, gb, ga, None, None
 
 

@@ -43,10 +43,10 @@ class TapDesc:
     def pmap_on(self, device):
         return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
 
-    def cstruct(self, n, act, precision):
+    def cstruct(self, n, act, precision, add_period=0):
         from ._lib import TapConvDesc
 
-        key = (n, act, precision)
+        key = (n, act, precision, add_period)
         s = self._structs.get(key)
         if s is None:
             s = TapConvDesc()
@@ -56,7 +56,7 @@ class TapDesc:
             s.w_oc, s.w_ic, s.w_oc_blk, s.w_ocblk = self.w_oc, self.w_ic, 0, 0
             for i in range(self.ntap):
                 s.tap_in_ch[i], s.tap_w_off[i], s.tap_row[i] = self.tap_in_ch[i], self.tap_w_off[i], self.tap_row[i]
-            s.act, s.precision = act, precision
+            s.add_period, s.act, s.precision = add_period, act, precision
             self._structs[key] = s
         return s
 
@@ -71,8 +71,13 @@ class TapConvGeom:
     down-sampling are computed (SURVEY.md §7 I2 - selection commutes with the linear map).
     """
 
-    def __init__(self, c_in, c_out, t_in, v_in, K=1, kt=1, pad=0, stride=1, dil=1, t_sel=None, v_keep=None):
+    def __init__(self, c_in, c_out, t_in, v_in, K=1, kt=1, pad=0, stride=1, dil=1, t_sel=None, v_keep=None, w_cin=None,
+                 w_ic0=0):
+        """w_cin / w_ic0: the weight tensor has w_cin >= c_in input channels and this site contracts over the slice
+        [w_ic0, w_ic0 + c_in) only (used to split the critic's first layer into label and data channels)."""
         self.c_in, self.c_out, self.t_in, self.v_in, self.K, self.kt = c_in, c_out, t_in, v_in, K, kt
+        w_cin = c_in if w_cin is None else w_cin
+        assert w_ic0 + c_in <= w_cin
         t_conv = (t_in + 2 * pad - dil * (kt - 1) - 1) // stride + 1
         assert t_conv >= 1, "temporal kernel larger than the padded input"
         self.t_sel = list(range(t_conv)) if t_sel is None else [int(t) for t in t_sel]
@@ -80,7 +85,7 @@ class TapConvGeom:
         assert all(0 <= t < t_conv for t in self.t_sel) and all(0 <= v < v_in for v in self.v_keep)
         self.t_out, self.v_out = len(self.t_sel), len(self.v_keep)
         self.p_in, self.p_out = t_in * v_in, self.t_out * self.v_out
-        self.w_numel = K * c_out * c_in * kt
+        self.w_numel = K * c_out * w_cin * kt
 
         pmap = np.full((kt, self.p_out), -1, np.int32)
         inv = np.full((kt, self.p_in), -1, np.int32)
@@ -96,14 +101,15 @@ class TapConvGeom:
         taps = [(k, dt) for k in range(K) for dt in range(kt)]
         self.fwd = TapDesc(
             c_in_total=K * c_in, p_in=self.p_in, c_out_total=c_out, p_out=self.p_out, ntap=len(taps), ck=c_in, co=c_out,
-            groups=1, g_in=0, g_out=0, g_w=0, w_oc=c_in * kt, w_ic=kt,
-            tap_in_ch=[k * c_in for k, dt in taps], tap_w_off=[k * c_out * c_in * kt + dt for k, dt in taps],
+            groups=1, g_in=0, g_out=0, g_w=0, w_oc=w_cin * kt, w_ic=kt,
+            tap_in_ch=[k * c_in for k, dt in taps], tap_w_off=[(k * c_out * w_cin + w_ic0) * kt + dt for k, dt in taps],
             tap_row=[dt for k, dt in taps], pmap=pmap, t_out=self.t_out, v_out=self.v_out)
         # data gradient: same kernel, roles of (oc, ic) swapped, inverse map, one group per channel block
         self.dgrad = TapDesc(
             c_in_total=c_out, p_in=self.p_out, c_out_total=K * c_in, p_out=self.p_in, ntap=kt, ck=c_out, co=c_in,
-            groups=K, g_in=0, g_out=c_in, g_w=c_out * c_in * kt, w_oc=kt, w_ic=c_in * kt,
-            tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=inv, t_out=t_in, v_out=v_in)
+            groups=K, g_in=0, g_out=c_in, g_w=c_out * w_cin * kt, w_oc=kt, w_ic=w_cin * kt,
+            tap_in_ch=[0] * kt, tap_w_off=[w_ic0 * kt + dt for dt in range(kt)], tap_row=list(range(kt)), pmap=inv, t_out=t_in,
+            v_out=v_in)
 
 
 class PlaneTable:
@@ -170,6 +176,14 @@ def select_table(t_in, v_in, t_sel, v_keep):
         for b, v in enumerate(v_keep):
             dense[a * len(v_keep) + b, t * v_in + v] = 1.0
     return PlaneTable(dense, len(t_sel), len(v_keep), t_in, v_in)
+
+
+def sum_t_table(t_in, v_in):
+    """Plane table summing over frames: (T, V) -> (1, V); the adjoint of broadcasting a per-joint term along T."""
+    dense = np.zeros((v_in, t_in * v_in))
+    for t in range(t_in):
+        dense[np.arange(v_in), t * v_in + np.arange(v_in)] = 1.0
+    return PlaneTable(dense, 1, v_in, t_in, v_in)
 
 
 def mean_table(t_in, v_in):

@@ -52,11 +52,14 @@ class Discriminator(nn.Module):
 
     def forward(self, x, labels):
         N, C, T, V = x.size()
-        c = self.label_emb(labels)                       # (N, n_cls); the (N, n_cls, T, V) repeat is never built
-        x = KF.LabelConcat.apply(c, x)
+        c = self.label_emb(labels)                       # (N, n_cls); the (N, n_cls, T, V) planes are never built
         A = self.A
-        for gcn, importance in zip(self.st_gcn_networks, self.edge_importance):
-            x, _ = gcn(x, A[gcn.lvl] * importance)
+        for i, (gcn, importance) in enumerate(zip(self.st_gcn_networks, self.edge_importance)):
+            if i == 0 and gcn._res == "none":
+                x, _ = gcn(x, A[gcn.lvl] * importance, label_emb=c)      # label channels folded analytically (I3)
+            else:
+                x = KF.LabelConcat.apply(c, x) if i == 0 else x
+                x, _ = gcn(x, A[gcn.lvl] * importance)
         # global pooling + prediction (discriminator.py:68-72)
         key = (x.size(1), x.size(2), x.size(3))
         if key not in self._head:
@@ -104,8 +107,15 @@ class st_gcn(nn.Module):
             p = self._plans[(T, V)] = (tcn, res)
         return p
 
-    def forward(self, x, A):
+    def forward(self, x, A, label_emb=None):
+        """`label_emb` (optional, not in the reference): (N, n_cls) label embedding standing for the first n_cls input
+        channels, which the reference materialises as constant planes (discriminator.py:57-60); x then holds only the
+        data channels.  Only valid for a block without residual branch (the critic's first block)."""
         tcn, res = self._plan(x.size(2), A.size(2))
+        if label_emb is not None:
+            assert self._res == "none"
+            g, A = self.gcn.forward_with_labels(x, A, label_emb)
+            return KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, None, tcn, KF.ACT_LRELU), A
         if self._res == "none":
             r = None
         elif self._res == "identity":

@@ -32,6 +32,33 @@ class ConvTemporalGraphical(nn.Module):
             self._geoms[(t, w)] = g
         return g
 
+    def _label_geoms(self, n_lab, c, t, w):
+        key = ("lab", n_lab, c, t, w)
+        g = self._geoms.get(key)
+        if g is None:
+            K, kc, cin = self.kernel_size, self.conv.out_channels, self.conv.in_channels
+            assert self._t == (1, 1, 0, 1) and n_lab + c == cin
+            g = (TapConvGeom(n_lab, kc, 1, 1, w_cin=cin, w_ic0=0),                         # label channels -> (N, K*C_out)
+                 TapConvGeom(c, kc // K, t, w, K=K, w_cin=cin, w_ic0=n_lab))               # data channels
+            self._geoms[key] = g
+        return g
+
+    def forward_with_labels(self, x, A, label_emb):
+        """The critic's first layer (discriminator.py:57-64) without the label planes: the input of the reference is
+        cat(label_emb tiled over (T, V), x).  The tiled channels are constant over (t, v), so their share of the output is
+            L[n, c, w] = sum_k (W[kC+c, :n_cls] . e[n]) * sum_v A[k, v, w]
+        - a per-sample bias times the column sums of A - added (broadcast along T) in the epilogue of the GEMM over the
+        C data channels only.  Exact up to summation order."""
+        assert A.size(0) == self.kernel_size
+        K, n, n_lab = self.kernel_size, x.size(0), label_emb.size(1)
+        g_lab, g_dat = self._label_geoms(n_lab, x.size(1), x.size(2), A.size(2))
+        b = KF.TapConv.apply(label_emb.reshape(n, n_lab, 1, 1), self.conv.weight, g_lab)      # (N, K*C_out, 1, 1)
+        b = b.view(n, K, -1).transpose(1, 2).reshape(n, -1, 1, K)                             # (N, C_out, 1, K)
+        L = KF.AdjMix.apply(b, A.sum(1).unsqueeze(0))                                         # (N, C_out, 1, W)
+        xa = KF.AdjMix.apply(x, A)
+        out = KF.TapConvEp.apply(xa, self.conv.weight, None, L, g_dat, KF.ACT_NONE)
+        return out, A
+
     def forward(self, x, A):
         assert A.size(0) == self.kernel_size
         xa = KF.AdjMix.apply(x, A)                                  # (N, K*C_in, T, W)

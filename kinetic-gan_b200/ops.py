@@ -85,10 +85,12 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     n = x.shape[0]
     assert x.shape[1] == desc.c_in_total and x.shape[2] * x.shape[3] == desc.p_in, (tuple(x.shape), desc.c_in_total, desc.p_in)
     out = torch.empty((n, desc.c_out_total, desc.t_out, desc.v_out), device=x.device, dtype=torch.float32)
-    if add is not None:
-        assert add.shape == out.shape
+    add_period = 0
+    if add is not None and add.shape != out.shape:      # per-joint term broadcast along T: (N, C, 1, V)
+        assert add.shape == (n, desc.c_out_total, 1, desc.v_out), (tuple(add.shape), tuple(out.shape))
+        add_period = desc.v_out
     l = _lib.lib()
-    _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, desc.cstruct(n, act, _precision), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
+    _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, desc.cstruct(n, act, _precision, add_period), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
                                   _ptr(bias), _ptr(add), out.data_ptr(), _stream())
     return out
 

@@ -48,7 +48,10 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=0):
         if bias is not None:
             acc = acc + bias[o0:o0 + desc.co].view(1, -1, 1)
         if add is not None:
-            acc = acc + add.reshape(n, desc.c_out_total, desc.p_out)[:, o0:o0 + desc.co]
+            a = add
+            if a.shape[2] == 1 and desc.t_out > 1:       # broadcast along T (add_period = V)
+                a = a.expand(n, desc.c_out_total, desc.t_out, desc.v_out)
+            acc = acc + a.reshape(n, desc.c_out_total, desc.p_out)[:, o0:o0 + desc.co]
         out[:, o0:o0 + desc.co] = _act(acc, act)
     return out.view(n, desc.c_out_total, desc.t_out, desc.v_out)
 

@@ -108,3 +108,19 @@ def test_discriminator_and_gp_vs_golden(emu, case, tag):
             assert p.grad is None or p.grad.abs().max().item() == 0, k      # the penalty cannot see them
         else:
             assert within_noise_floor(sub(p.grad), gold, "/gp_grad/" + k, tag, 100 * tol), k
+
+
+def test_label_folding_equals_label_planes(emu):
+    """Critic block 0 with the label channels folded analytically == the same block on cat(label planes, x)."""
+    cfg = CASES["ntu_small"]["cfg"]
+    _, D = build(cfg, torch.float64)
+    x = inputs(cfg, 3, 0, torch.float64)
+    c = D.label_emb(x["labels"])
+    blk, A = D.st_gcn_networks[0], D.A[0] * D.edge_importance[0]
+    a, _ = blk(x["real"], A, label_emb=c)
+    b, _ = blk(kgan.functional.LabelConcat.apply(c, x["real"]), A)
+    assert torch.allclose(a, b, atol=1e-12)
+    ga = torch.autograd.grad(a.sum(), [blk.gcn.conv.weight, D.label_emb.weight, D.edge_importance[0]])
+    gb = torch.autograd.grad(b.sum(), [blk.gcn.conv.weight, D.label_emb.weight, D.edge_importance[0]])
+    for u, v in zip(ga, gb):
+        assert torch.allclose(u, v, atol=1e-10)
