@@ -58,7 +58,7 @@ typedef struct kgan_tapconv_desc {
     int32_t add_period;        /* 0: `add` has the shape of out; else add is (N, c_out_total, add_period) and is read at
                                   p % add_period (a term that is constant over frames, broadcast along T) */
     int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */
-    int32_t precision;         /* KGAN_PREC_* */
+    int32_t precision;         /* KGAN_PREC_*: informational (which entry point the caller intends to use) */
 } kgan_tapconv_desc;
 
 /* Version / diagnostics. */
@@ -79,6 +79,19 @@ int kgan_device_ok(void);
  * `bias` (co floats) and `add` (same shape as out) may be NULL. */
 int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, const float* w, const int32_t* pmap,
                      const float* bias, const float* add, float* out, void* stream);
+
+/* Tensor-core path of kgan_tapconv_fwd: tcgen05.mma kind::tf32 (inputs rounded to tf32 with round-to-nearest, fp32
+ * accumulation in TMEM; rel-L2 ~3e-4 per layer).  The weights are first packed into the shared-memory image the
+ * kernel streams with bulk copies:
+ *   kgan_tapconv_tf32_workspace(d)  -> number of floats of the packed image; 0 if the shape is not eligible
+ *                                      (ck < 16, co < 16 or fewer than 256 output positions: use kgan_tapconv_fwd)
+ *   kgan_tapconv_pack_tf32(d, w, wp) -> fills wp (caller-owned, 16-byte aligned) from the natural weights
+ *   kgan_tapconv_fwd_tf32(d, in, wp, ...) -> same semantics as kgan_tapconv_fwd
+ * A packed image depends on the descriptor's geometry but not on d->n / act / add_period. */
+int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d);
+int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream);
+int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
+                          const float* bias, const float* add, float* out, void* stream);
 
 /* dW[...same addressing as W...] = sum_{n,p} gout[n, out_ch0+oc, p] * in[n, in_ch0+tap_in_ch+ic, pmap[..]]
  * Replaces convolution_backward w.r.t. weight for the same call sites, and (called with swapped roles)

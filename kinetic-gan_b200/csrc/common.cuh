@@ -43,8 +43,10 @@ __device__ __forceinline__ int64_t w_oc_offset(const kgan_tapconv_desc& d, int o
 
 constexpr int kNumSMs = 148;   // B200
 
-// tcgen05 path (tapconv_umma.cu); returns -1 when the shape is not eligible (caller uses the SIMT path)
-int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* w, const int32_t* pmap, const float* bias,
-                     const float* add, float* out, cudaStream_t stream);
+// tcgen05 path (tapconv_umma.cu)
+int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d);      // 0: shape not eligible for the tensor-core path
+int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cudaStream_t stream);
+int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias,
+                     const float* add, float* out, cudaStream_t stream);   // -1: not eligible
 
 }  // namespace kgan

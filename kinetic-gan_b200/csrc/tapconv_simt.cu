@@ -204,10 +204,6 @@ extern "C" int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, con
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && w && pmap && out, "tapconv_fwd: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    if (d->precision == KGAN_PREC_TF32) {
-        int r = tapconv_fwd_tf32(*d, in, w, pmap, bias, add, out, s);
-        if (r >= 0) return r;   // -1: shape not eligible for the tensor-core path -> exact path below
-    }
     const int64_t total = (int64_t)d->n * d->p_out;
     const int64_t gx = ceil_div64(total, BM);
     KGAN_REQUIRE(gx < (1ll << 31), "tapconv_fwd: too many positions");
@@ -242,4 +238,27 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
     dim3 grid(d->ntap * ceil_div(d->ck, WB), ceil_div(d->co, WB), (unsigned)(d->groups * nchunks));
     tapconv_wgrad_simt<<<grid, NT, 0, s>>>(*d, in, gout, pmap, dw, (int)nchunks, chunk);
     return check_launch("tapconv_wgrad");
+}
+
+extern "C" int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d) {
+    if (validate(d)) return -1;
+    return tapconv_tf32_packed_numel(*d);
+}
+
+extern "C" int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(w && wp, "tapconv_pack_tf32: null pointer");
+    return tapconv_pack_tf32(*d, w, wp, (cudaStream_t)stream);
+}
+
+extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
+                                     const float* bias, const float* add, float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
+    int r = tapconv_fwd_tf32(*d, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("tapconv_fwd_tf32: shape not eligible for the tensor-core path (kgan_tapconv_tf32_workspace() == 0)");
+        return 1;
+    }
+    return r;
 }

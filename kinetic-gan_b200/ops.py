@@ -80,6 +80,36 @@ def _tap_flops(desc, n):
     return 2.0 * n * desc.p_out * desc.co * desc.ck * desc.ntap * desc.groups
 
 
+# ---- tf32 tensor-core path: packed weight images are cached per (weight storage, version, geometry) ----------
+weights_epoch = 0          # bumped by the fused Adam (it rewrites weights behind autograd's version counter)
+_packed = {}
+
+
+def invalidate_packed_weights():
+    global weights_epoch
+    weights_epoch += 1
+    _packed.clear()
+
+
+def _packed_weights(w, desc, cs, l):
+    numel = desc.__dict__.get("_tf32_numel")
+    if numel is None:
+        numel = desc._tf32_numel = int(l.kgan_tapconv_tf32_workspace(cs))
+    if numel <= 0:
+        return None
+    key = (w.data_ptr(), w._version, id(desc))
+    hit = _packed.get(key)
+    if hit is not None and hit[1] is desc:
+        return hit[0]
+    wp = torch.empty(numel, device=w.device, dtype=torch.float32)
+    _run('tapconv_pack', 0.0, l.kgan_tapconv_pack_tf32, cs, w.data_ptr(), wp.data_ptr(), _stream())
+    if w.is_leaf:                             # parameters: reuse until the next optimizer step; temporaries: no caching
+        if len(_packed) > 256:
+            _packed.clear()
+        _packed[key] = (wp, desc, w)          # keeps `w` alive so data_ptr cannot be recycled under the key
+    return wp
+
+
 def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     _chk(x, w, bias, add)
     n = x.shape[0]
@@ -90,8 +120,15 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
         assert add.shape == (n, desc.c_out_total, 1, desc.v_out), (tuple(add.shape), tuple(out.shape))
         add_period = desc.v_out
     l = _lib.lib()
-    _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, desc.cstruct(n, act, _precision, add_period), x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
-                                  _ptr(bias), _ptr(add), out.data_ptr(), _stream())
+    cs = desc.cstruct(n, act, _precision, add_period)
+    if _precision == PREC_TF32:
+        wp = _packed_weights(w, desc, cs, l)
+        if wp is not None:
+            _run('tapconv_fwd_tf32', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(),
+                 desc.pmap_on(x.device).data_ptr(), _ptr(bias), _ptr(add), out.data_ptr(), _stream())
+            return out
+    _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, cs, x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
+         _ptr(bias), _ptr(add), out.data_ptr(), _stream())
     return out
 
 

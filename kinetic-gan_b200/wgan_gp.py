@@ -65,6 +65,7 @@ class FlatParams:
     def adam(self, lr, b1, b2, eps=1e-8, grad_scale=1.0):
         self.step += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, lr, b1, b2, eps, self.step, grad_scale)
+        ops.invalidate_packed_weights()          # tf32 path: packed weight images are stale now
 
 
 class WGANGPTrainer:

@@ -1,0 +1,98 @@
+"""tcgen05 / TMEM tap convolution (precision 'tf32') against the float64 statement of the same descriptor semantics
+and against the exact fp32 SIMT kernel.  Inputs are rounded to tf32 (10-bit mantissa, round-to-nearest), products are
+exact and accumulated in fp32: rel-L2 ~3e-4 per layer; the stated tolerance for this path is 1e-3 (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+import emu_backend as emu
+import kgan_b200 as kgan
+
+pytestmark = pytest.mark.gpu
+ops, G = kgan.ops, kgan.geometry
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def tf32_path():
+    kgan.set_precision("tf32")
+    yield
+    kgan.set_precision("fp32")
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def rel(a, b):
+    b = b.double()
+    return ((a.detach().cpu().double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+GEOMS = {
+    "d1_gcn": (dict(c_in=32, c_out=64, t_in=64, v_in=11, K=3), 4),
+    "d2_gcn": (dict(c_in=64, c_out=128, t_in=64, v_in=11, K=3), 3),
+    "d2_tcn_select": (dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=[2, 4, 6, 8, 10]), 5),
+    "d3_tcn": (dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 6),
+    "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40),
+    "d4_res": (dict(c_in=256, c_out=512, t_in=16, v_in=5, kt=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40),
+    "ragged_k": (dict(c_in=50, c_out=24, t_in=9, v_in=7, kt=3, pad=1), 5),
+    "mlp_632": (dict(c_in=632, c_out=632, t_in=1, v_in=1), 300),
+    "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64),
+}
+
+
+@pytest.mark.parametrize("name", list(GEOMS))
+def test_tapconv_tf32(name):
+    kw, n = GEOMS[name]
+    geom = G.TapConvGeom(**kw)
+    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    w = rnd(geom.K * geom.c_out, geom.c_in, geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
+    bias = rnd(geom.c_out, seed=3)
+    add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)
+    go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
+    xc, wc = x.cuda(), w.cuda()
+    l0 = ops.launches
+    got = ops.tapconv_fwd(xc, wc, geom.fwd)
+    assert rel(got, emu.tapconv_fwd(x.double(), w.double(), geom.fwd)) < TOL
+    got = ops.tapconv_fwd(xc, wc, geom.fwd, bias.cuda(), add.cuda(), ops.ACT_LRELU)
+    assert rel(got, emu.tapconv_fwd(x.double(), w.double(), geom.fwd, bias.double(), add.double(), ops.ACT_LRELU)) < TOL
+    got = ops.tapconv_fwd(go.cuda(), wc, geom.dgrad)                       # data gradient = same kernel, transposed roles
+    assert rel(got, emu.tapconv_fwd(go.double(), w.double(), geom.dgrad)) < TOL
+    # the tensor-core entry point really ran (pack + fwd) and differs from the exact kernel only by tf32 rounding
+    kgan.set_precision("fp32")
+    exact = ops.tapconv_fwd(xc, wc, geom.fwd)
+    kgan.set_precision("tf32")
+    again = ops.tapconv_fwd(xc, wc, geom.fwd)
+    d = rel(again, exact.cpu())
+    assert 1e-6 < d < TOL, d
+
+
+def test_critic_tf32_vs_oracle():
+    from importlib import import_module
+    from oracle import networks as onet
+    from oracle.graph import SkeletonTables
+    from helpers import inputs
+    cfg = onet.Config()
+    n = 6
+    tables = SkeletonTables("ntu")
+    D = kgan.Discriminator(3, 60, 64, 512)
+    pd = onet.synth_params(onet.d_param_shapes(cfg), 2)
+    D.load_state_dict(pd)
+    D = D.cuda()
+    x = inputs(cfg, n, 3)
+    pd64 = {k: v.double().requires_grad_(True) for k, v in pd.items()}
+    dv = D(x["real"].cuda(), x["labels"].cuda())
+    dv_ref = onet.discriminator_forward(pd64, x["real"].double(), x["labels"], cfg, tables)
+    assert rel(dv, dv_ref.detach()) < 2e-3
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    fake = torch.tanh(torch.randn(n, 3, 64, 25, generator=torch.Generator().manual_seed(5)))
+    gp = wg.compute_gradient_penalty(D, x["real"].cuda(), fake.cuda(), x["labels"].cuda(), alpha=x["alpha"].cuda())
+    (-dv.mean() + 10 * gp).backward()
+    gp_ref = onet.gradient_penalty(pd64, x["real"].double(), fake.double(), x["labels"], x["alpha"].double(), cfg, tables)
+    assert abs(gp.item() - gp_ref.item()) < 2e-3 * max(1.0, abs(gp_ref.item()))
+    keys = list(pd64)
+    gref = dict(zip(keys, torch.autograd.grad(-dv_ref.mean() + 10 * gp_ref, [pd64[k] for k in keys], allow_unused=True)))
+    for k, p in D.named_parameters():
+        assert rel(p.grad, gref[k]) < 5e-3, k
