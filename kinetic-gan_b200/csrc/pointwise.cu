@@ -111,49 +111,49 @@ __global__ void __launch_bounds__(PT) adjmix_bwd_x_k(const float* __restrict__ g
     }
 }
 
-// gA[k,v,w] = sum over rows of x[row, v] * g[row(k), w]: a (k*w) x v GEMM with a very long contraction (all rows).
-// Each CTA stages AROWS rows in shared memory (zero-padded to multiples of 4 joints); every thread owns one 4x4
-// (v, w) register tile of one partition k and a strided subset of the staged rows; partial tiles are merged with
-// fp32 atomics (k*v*w <= 1875 addresses).
-constexpr int AROWS = 64;
+// gA[k,v,w] = sum_{n,c,t} x[n,c,t,v] * g[n,kC+c,t,w]: per (n,c) plane pair a (V x T).(T x W) product, summed over all
+// planes.  A CTA stages PL consecutive planes with linear, fully coalesced copies (x planes are contiguous in memory;
+// for each k so are the matching g planes of one sample), every thread owns one 4x4 (v,w) register tile of one
+// partition k and a strided subset of the staged (plane, t) rows; CTA partials are merged with fp32 atomics.
 __global__ void __launch_bounds__(PT) adjmix_bwd_a_k(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gA,
-                                                      int n, int c, int t, int v, int w, int k, int64_t rows_per_cta) {
+                                                      int n, int c, int t, int v, int w, int k, int pl, int64_t planes_per_cta) {
     extern __shared__ __align__(16) float sm[];
-    const int vp = (v + 3) & ~3, wp = (w + 3) & ~3;
-    float* xs = sm;                        // [AROWS][vp]
-    float* gs = sm + AROWS * vp;           // [k][AROWS][wp]
-    const int vt = vp >> 2, wt = wp >> 2, ntile = k * vt * wt;
-    const int rgroups = max(1, PT / ntile);                      // row groups sharing the CTA
+    float* xs = sm;                        // [pl][t][v]
+    float* gs = sm + pl * t * v;           // [k][pl][t][w]
+    const int vt = (v + 3) >> 2, wt = (w + 3) >> 2, ntile = k * vt * wt;
+    const int rgroups = max(1, PT / ntile);
     const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
-    const bool active = grp < rgroups && (int)threadIdx.x < rgroups * ntile;
+    const bool active = grp < rgroups;
     const int kk = tile / (vt * wt), v0 = ((tile / wt) % vt) * 4, w0 = (tile % wt) * 4;
-    const int64_t rows = (int64_t)n * c * t;
-    const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta, rend = min(rows, rbeg + rows_per_cta);
+    const int64_t planes = (int64_t)n * c;
+    const int64_t pbeg = (int64_t)blockIdx.x * planes_per_cta, pend = min(planes, pbeg + planes_per_cta);
+    const int tv = t * v, tw = t * w;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int64_t r0 = rbeg; r0 < rend; r0 += AROWS) {
-        const int nr = (int)min((int64_t)AROWS, rend - r0);
-        for (int i = threadIdx.x; i < nr * vp; i += blockDim.x) {
-            const int rr = i / vp, vv = i - rr * vp;
-            xs[i] = vv < v ? __ldg(x + (r0 + rr) * v + vv) : 0.f;
-        }
-        for (int i = threadIdx.x; i < k * nr * wp; i += blockDim.x) {
-            const int ww = i % wp, rr = (i / wp) % nr, k2 = i / (wp * nr);
-            const int64_t row = r0 + rr;                       // (n, c, t)
-            const int tt = (int)(row % t);
-            const int64_t nc = row / t;
-            const int cc = (int)(nc % c), nn = (int)(nc / c);
-            gs[(k2 * AROWS + rr) * wp + ww] = ww < w ? __ldg(g + (((int64_t)nn * k * c + (int64_t)k2 * c + cc) * t + tt) * w + ww) : 0.f;
+    for (int64_t p0 = pbeg; p0 < pend; p0 += pl) {
+        const int np = (int)min((int64_t)pl, pend - p0);
+        for (int i = threadIdx.x; i < np * tv; i += blockDim.x) xs[i] = __ldg(x + p0 * tv + i);
+        for (int q = 0; q < k * np; ++q) {                        // (k2, plane) pairs: one contiguous T*W block each
+            const int k2 = q / np, pp = q - k2 * np;
+            const int64_t plane = p0 + pp;
+            const int64_t nn = plane / c, cc = plane - nn * c;
+            const float* src = g + ((nn * k + k2) * c + cc) * tw;
+            float* dst = gs + ((int64_t)k2 * pl + pp) * tw;
+            for (int i = threadIdx.x; i < tw; i += blockDim.x) dst[i] = __ldg(src + i);
         }
         __syncthreads();
         if (active) {
-            for (int rr = grp; rr < nr; rr += rgroups) {
-                const float4 xv = *reinterpret_cast<const float4*>(xs + rr * vp + v0);
-                const float4 gv = *reinterpret_cast<const float4*>(gs + (kk * AROWS + rr) * wp + w0);
-                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+            const int rows = np * t;
+            const float* gk = gs + (int64_t)kk * pl * tw;
+            for (int rr = grp; rr < rows; rr += rgroups) {
+                float xa[4], ga[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xa[i] = (v0 + i < v) ? xs[rr * v + v0 + i] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ga[j] = (w0 + j < w) ? gk[rr * w + w0 + j] : 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -388,17 +388,28 @@ extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int 
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
-    const int vp = (v + 3) & ~3, wp = (w + 3) & ~3;
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * (vp / 4) * (wp / 4) <= PT, "adjmix_bwd_a: k*v*w too large");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * ((v + 3) / 4) * ((w + 3) / 4) <= PT, "adjmix_bwd_a: k*v*w too large");
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
-    const int64_t rows = (int64_t)n * c * t;
-    int64_t ctas = ceil_div64(rows, 4 * AROWS);
-    if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
-    const int64_t per = ceil_div64(ceil_div64(rows, ctas), AROWS) * AROWS;
-    ctas = ceil_div64(rows, per);
-    const size_t smem = sizeof(float) * ((size_t)AROWS * vp + (size_t)k * AROWS * wp);
-    adjmix_bwd_a_k<<<(unsigned)ctas, PT, smem, s>>>(x, g, gA, n, c, t, v, w, k, per);
+    const int64_t plane_floats = (int64_t)t * (v + (int64_t)k * w);
+    KGAN_REQUIRE(plane_floats * 4 <= 160 * 1024, "adjmix_bwd_a: one (T, V) plane does not fit in shared memory");
+    int64_t pl = (40 * 1024 / 4) / plane_floats;                 // planes per stage: <= 40 KB so several CTAs share an SM
+    if (pl < 1) pl = 1;
+    if (pl * t > 2048) pl = (2048 + t - 1) / t;
+    const int64_t planes = (int64_t)n * c;
+    if (pl > planes) pl = planes;
+    int64_t ctas = ceil_div64(planes, pl);
+    if (ctas > 4 * kNumSMs) ctas = 4 * kNumSMs;
+    const int64_t per = ceil_div64(ceil_div64(planes, ctas), pl) * pl;
+    ctas = ceil_div64(planes, per);
+    const size_t smem = sizeof(float) * (size_t)(pl * plane_floats);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(adjmix_bwd_a_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+            return check_launch("adjmix_bwd_a attribute");
+        attr_set = true;
+    }
+    adjmix_bwd_a_k<<<(unsigned)ctas, PT, smem, s>>>(x, g, gA, n, c, t, v, w, k, (int)pl, per);
     return check_launch("adjmix_bwd_a");
 }
 
