@@ -93,6 +93,12 @@ int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp
 int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
                           const float* bias, const float* add, float* out, void* stream);
 
+/* Tensor-core path of kgan_tapconv_wgrad (tcgen05.mma kind::tf32, split-K over CTAs, fp32 atomics into dw).
+ * kgan_tapconv_wgrad_tf32_ok(d) -> 1 if the shape is eligible (else use kgan_tapconv_wgrad). */
+int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d);
+int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
+                            float* dw, int64_t dw_numel, void* stream);
+
 /* dW[...same addressing as W...] = sum_{n,p} gout[n, out_ch0+oc, p] * in[n, in_ch0+tap_in_ch+ic, pmap[..]]
  * Replaces convolution_backward w.r.t. weight for the same call sites, and (called with swapped roles)
  * the weight terms of _convolution_double_backward used by the gradient penalty (kinetic-gan.py:104-113,154).

@@ -33,6 +33,8 @@ _SIGS = {
     "kgan_tapconv_tf32_workspace": ([C.POINTER(TapConvDesc)], C.c_int64),
     "kgan_tapconv_pack_tf32": ([C.POINTER(TapConvDesc), _F, _F, _V], C.c_int),
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
+    "kgan_tapconv_wgrad_tf32_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
     "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
     "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),

@@ -262,3 +262,20 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     }
     return r;
 }
+
+extern "C" int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d) {
+    if (validate(d)) return 0;
+    return tapconv_wgrad_tf32_eligible(*d);
+}
+
+extern "C" int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
+                                       float* dw, int64_t dw_numel, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad_tf32: null pointer");
+    int r = tapconv_wgrad_tf32(*d, in, gout, pmap, dw, dw_numel, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("tapconv_wgrad_tf32: shape not eligible for the tensor-core path (kgan_tapconv_wgrad_tf32_ok() == 0)");
+        return 1;
+    }
+    return r;
+}

@@ -92,12 +92,13 @@ def invalidate_packed_weights():
 
 
 def _packed_weights(w, desc, cs, l):
-    numel = desc.__dict__.get("_tf32_numel")
+    cache = desc.__dict__.setdefault("_tf32_numel", {})       # eligibility / image size depend on the batch size too
+    numel = cache.get(cs.n)
     if numel is None:
-        numel = desc._tf32_numel = int(l.kgan_tapconv_tf32_workspace(cs))
+        numel = cache[cs.n] = int(l.kgan_tapconv_tf32_workspace(cs))
     if numel <= 0:
         return None
-    key = (w.data_ptr(), w._version, id(desc))
+    key = (w.data_ptr(), w._version, id(desc), numel)
     hit = _packed.get(key)
     if hit is not None and hit[1] is desc:
         return hit[0]
@@ -137,8 +138,17 @@ def tapconv_wgrad(x, gout, desc, w_shape):
     n = x.shape[0]
     dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
     l = _lib.lib()
-    _run('tapconv_wgrad', _tap_flops(desc, n), l.kgan_tapconv_wgrad, desc.cstruct(n, ACT_NONE, _precision), x.data_ptr(), gout.data_ptr(),
-                                    desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
+    cs = desc.cstruct(n, ACT_NONE, _precision)
+    if _precision == PREC_TF32:
+        ok = desc.__dict__.setdefault("_tf32_wgrad_ok", {})
+        if n not in ok:
+            ok[n] = bool(l.kgan_tapconv_wgrad_tf32_ok(cs))
+        if ok[n]:
+            _run('tapconv_wgrad_tf32', _tap_flops(desc, n), l.kgan_tapconv_wgrad_tf32, cs, x.data_ptr(), gout.data_ptr(),
+                 desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
+            return dw
+    _run('tapconv_wgrad', _tap_flops(desc, n), l.kgan_tapconv_wgrad, cs, x.data_ptr(), gout.data_ptr(),
+         desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
     return dw
 
 

@@ -118,7 +118,8 @@ def test_label_folding_equals_label_planes(emu):
     c = D.label_emb(x["labels"])
     blk, A = D.st_gcn_networks[0], D.A[0] * D.edge_importance[0]
     a, _ = blk(x["real"], A, label_emb=c)
-    b, _ = blk(kgan.functional.LabelConcat.apply(c, x["real"]), A)
+    A = D.A[0] * D.edge_importance[0]
+    b, _ = blk(kgan.functional.LabelConcat.apply(D.label_emb(x["labels"]), x["real"]), A)
     assert torch.allclose(a, b, atol=1e-12)
     ga = torch.autograd.grad(a.sum(), [blk.gcn.conv.weight, D.label_emb.weight, D.edge_importance[0]])
     gb = torch.autograd.grad(b.sum(), [blk.gcn.conv.weight, D.label_emb.weight, D.edge_importance[0]])

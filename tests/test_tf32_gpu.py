@@ -35,9 +35,9 @@ GEOMS = {
     "d2_gcn": (dict(c_in=64, c_out=128, t_in=64, v_in=11, K=3), 3),
     "d2_tcn_select": (dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=[2, 4, 6, 8, 10]), 5),
     "d3_tcn": (dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 6),
-    "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40),
+    "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 160),
     "d4_res": (dict(c_in=256, c_out=512, t_in=16, v_in=5, kt=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40),
-    "ragged_k": (dict(c_in=50, c_out=24, t_in=9, v_in=7, kt=3, pad=1), 5),
+    "ragged_k": (dict(c_in=50, c_out=24, t_in=9, v_in=7, kt=3, pad=1), 21),
     "mlp_632": (dict(c_in=632, c_out=632, t_in=1, v_in=1), 300),
     "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64),
 }
@@ -60,6 +60,8 @@ def test_tapconv_tf32(name):
     assert rel(got, emu.tapconv_fwd(x.double(), w.double(), geom.fwd, bias.double(), add.double(), ops.ACT_LRELU)) < TOL
     got = ops.tapconv_fwd(go.cuda(), wc, geom.dgrad)                       # data gradient = same kernel, transposed roles
     assert rel(got, emu.tapconv_fwd(go.double(), w.double(), geom.dgrad)) < TOL
+    got = ops.tapconv_wgrad(xc, go.cuda(), geom.fwd, tuple(w.shape))         # weight gradient (tensor cores when eligible)
+    assert rel(got, emu.tapconv_wgrad(x.double(), go.double(), geom.fwd, tuple(w.shape))) < TOL
     # the tensor-core entry point really ran (pack + fwd) and differs from the exact kernel only by tf32 rounding
     kgan.set_precision("fp32")
     exact = ops.tapconv_fwd(xc, wc, geom.fwd)
