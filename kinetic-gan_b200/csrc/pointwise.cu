@@ -162,13 +162,20 @@ __global__ void __launch_bounds__(PT) adjmix_bwd_a_k(const float* __restrict__ x
         }
         __syncthreads();
     }
+    // merge the row groups of this CTA in shared memory first: one global atomic per output per CTA (k*v*w can be as
+    // small as 3 addresses, which thousands of same-address L2 atomics would serialise)
+    const int nout = k * v * w;
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
     if (active) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (v0 + i < v && w0 + j < w) atomicAdd(gA + (kk * v + v0 + i) * w + w0 + j, acc[i][j]);
+                if (v0 + i < v && w0 + j < w) atomicAdd(sm + (kk * v + v0 + i) * w + w0 + j, acc[i][j]);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) atomicAdd(gA + i, sm[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -399,10 +406,11 @@ extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int 
     const int64_t planes = (int64_t)n * c;
     if (pl > planes) pl = planes;
     int64_t ctas = ceil_div64(planes, pl);
-    if (ctas > 4 * kNumSMs) ctas = 4 * kNumSMs;
+    if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
     const int64_t per = ceil_div64(ceil_div64(planes, ctas), pl) * pl;
     ctas = ceil_div64(planes, per);
-    const size_t smem = sizeof(float) * (size_t)(pl * plane_floats);
+    size_t smem = sizeof(float) * (size_t)(pl * plane_floats);
+    if (smem < sizeof(float) * (size_t)k * v * w) smem = sizeof(float) * (size_t)k * v * w;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(adjmix_bwd_a_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)

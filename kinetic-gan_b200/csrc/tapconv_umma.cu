@@ -13,16 +13,9 @@
 //
 // The layer is HBM/L2-bound at tensor-core rates (AI ~ 0.75*C_out flop/B unfused), so each CTA computes ALL of its
 // output channels for a 128-position tile and reads the activation tile exactly once.
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace kgan {
-
-constexpr int UM = 128;                        // UMMA M = positions per CTA
-constexpr int UK = 32;                         // contraction elements per pipeline stage (4 MMAs of K = 8)
-constexpr int A_STAGE_BYTES = UM * UK * 4;     // 16 KB
-constexpr int A_LBO = UM * 16;                 // bytes between the two 16-byte k-chunks of one row group
-constexpr int CORE_SBO = 128;                  // bytes between 8-row groups (core matrices are contiguous)
-constexpr int UMMA_THREADS = 192;              // warps 0-3: A producers + epilogue, warp 4: MMA, warp 5: weight loader
 
 struct UmmaPlan {
     int n_cta;        // output channels per CTA (multiple of 16; of 32 when > 256)
@@ -35,8 +28,6 @@ struct UmmaPlan {
     int nkt;          // input-channel tiles of UK
     int smem_bytes;
 };
-
-static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
     if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0) return false;
@@ -63,71 +54,6 @@ static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
     if (p.stages < 2) p.stages = 2;
     p.smem_bytes = p.stages * stage + 256;
     return true;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
-}
-// K-major, no swizzle (LayoutType::SWIZZLE_NONE = 0), descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -203,15 +129,29 @@ __global__ void __launch_bounds__(UMMA_THREADS) tapconv_fwd_umma(const __grid_co
         const bool valid = pos < total_pos;
         const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
         const float* in_n = in + ((int64_t)nn * d.c_in_total + g * d.g_in) * d.p_in;
-        for (int it = 0; it < iters; ++it) {
+        // position map of this row for every tap (constant over the input-channel tiles)
+        constexpr int SRC_CACHE = 4;
+        int srcs[SRC_CACHE];
+#pragma unroll
+        for (int i = 0; i < SRC_CACHE; ++i) srcs[i] = (valid && i < d.ntap) ? __ldg(pmap + (int64_t)d.tap_row[i] * d.p_out + p) : -1;
+        // all UK loads of a stage are issued back to back (volatile asm keeps them ahead of the barrier wait), and the loads
+        // of stage it+1 are in flight while stage it is converted and stored: two stages of gathers outstanding per thread
+        auto issue = [&](int it, float (&v)[UK]) {
             const int ict = it / d.ntap, tap = it - ict * d.ntap, ic0 = ict * UK;
+            int src = -1;
+            if (tap < SRC_CACHE) {
+#pragma unroll
+                for (int i = 0; i < SRC_CACHE; ++i) src = (i == tap) ? srcs[i] : src;
+            } else if (valid) {
+                src = __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p);
+            }
+            const float* xb = in_n + (int64_t)(d.tap_in_ch[tap] + ic0) * d.p_in + src;
+#pragma unroll
+            for (int kk = 0; kk < UK; ++kk) v[kk] = ldg_pred(xb + (int64_t)kk * d.p_in, src >= 0 && ic0 + kk < d.ck);
+        };
+        auto stage_out = [&](int it, float (&v)[UK]) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)(it / S) & 1u;
-            const int src = valid ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p) : -1;
-            const float* xb = in_n + (int64_t)(d.tap_in_ch[tap] + ic0) * d.p_in + src;
-            float v[UK];
-#pragma unroll
-            for (int kk = 0; kk < UK; ++kk) v[kk] = (src >= 0 && ic0 + kk < d.ck) ? __ldg(xb + (int64_t)kk * d.p_in) : 0.f;
             mbar_wait(empty0 + 8 * s, ph ^ 1u);                      // slot free (first lap passes immediately)
             const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + t * 16;
 #pragma unroll
@@ -221,6 +161,16 @@ __global__ void __launch_bounds__(UMMA_THREADS) tapconv_fwd_umma(const __grid_co
                              : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
             mbar_arrive(full0 + 8 * s);
+        };
+        float va[UK], vb[UK];
+        issue(0, va);
+        for (int it = 0; it < iters; it += 2) {
+            if (it + 1 < iters) issue(it + 1, vb);
+            stage_out(it, va);
+            if (it + 1 < iters) {
+                if (it + 2 < iters) issue(it + 2, va);
+                stage_out(it + 1, vb);
+            }
         }
         // ===== epilogue: TMEM lane t -> out[n, oc, p] =====
         mbar_wait(accfull, 0);
@@ -292,214 +242,6 @@ __global__ void __launch_bounds__(UMMA_THREADS) tapconv_fwd_umma(const __grid_co
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// weight gradient on the tensor cores:  dW[tap][oc][ic] = sum_pos gout[oc, pos] * in[(tap, ic), pmap_tap(pos)]
-//   D[M = 128 output channels][N = n_ic input channels] per tap (ntap accumulators side by side in TMEM),
-//   K = output positions: both operands are K-major in global memory already (positions are contiguous per channel),
-//   so producer lanes run along positions (coalesced loads) and scatter into the K-major core-matrix layout with a
-//   one-row pad per k-chunk (LBO = (rows+1)*16 B) that makes the transposing 4-byte stores bank-conflict free.
-//   gout (A operand) is staged once per K tile and reused by all taps.  Split-K over CTAs, fp32 atomics into dW.
-// ---------------------------------------------------------------------------------------------------------------
-struct WgradPlan {
-    int n_ic;         // input channels (UMMA N) per CTA
-    int ic_tiles, oc_tiles;
-    int tmem_cols;
-    int stages;
-    int a_bytes, b_bytes;   // per stage: A image, one tap's B image
-    int nchunks;
-    int64_t chunk;    // positions per split-K chunk (multiple of UK)
-    int smem_bytes;
-};
-
-static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
-    if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0 || d.ntap > 8) return false;
-    const int64_t total = (int64_t)d.n * d.p_out;
-    if (total < 1024) return false;
-    int n_max = (512 / d.ntap) / 16 * 16;
-    if (n_max > 256) n_max = 256;
-    if (d.ntap == 3 && n_max > 128) n_max = 128;
-    p.n_ic = round_up(d.ck, 16) < n_max ? round_up(d.ck, 16) : n_max;
-    p.ic_tiles = ceil_div(d.ck, p.n_ic);
-    p.oc_tiles = ceil_div(d.co, UM);
-    p.tmem_cols = 32;
-    while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
-    p.a_bytes = 8 * (UM + 1) * 16;
-    p.b_bytes = 8 * (p.n_ic + 1) * 16;
-    const int stage = p.a_bytes + d.ntap * p.b_bytes;
-    p.stages = (200 * 1024) / stage;
-    if (p.stages > 4) p.stages = 4;
-    if (p.stages < 2) return false;
-    const int64_t ktiles = ceil_div64(total, UK);
-    const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
-    int64_t nchunks = ceil_div64(2 * kNumSMs, tiles);
-    if (nchunks > ktiles / 4) nchunks = ktiles / 4;
-    if (nchunks < 1) nchunks = 1;
-    p.chunk = ceil_div64(ktiles, nchunks) * UK;
-    p.nchunks = (int)ceil_div64(total, p.chunk);
-    if ((int64_t)p.nchunks * d.groups > 65535) return false;
-    p.smem_bytes = p.stages * stage + 256;
-    return true;
-}
-
-__global__ void __launch_bounds__(UMMA_THREADS) tapconv_wgrad_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradPlan pl,
-                                                                   const float* __restrict__ in, const float* __restrict__ gout,
-                                                                   const int32_t* __restrict__ pmap, float* __restrict__ dw) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = pl.stages;
-    const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);           // full[S], empty[S], accfull
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
-    const uint32_t a_lbo = (UM + 1) * 16, b_lbo = (pl.n_ic + 1) * 16;
-
-    const int ic0 = blockIdx.x * pl.n_ic, oc0 = blockIdx.y * UM;
-    const int g = blockIdx.z / pl.nchunks, ch = blockIdx.z % pl.nchunks;
-    const int64_t total_pos = (int64_t)d.n * d.p_out;
-    const int64_t pbeg = (int64_t)ch * pl.chunk, pend = min(total_pos, pbeg + pl.chunk);
-    const int iters = (int)ceil_div64(pend - pbeg, UK);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, 128);
-            mbar_init(empty0 + 8 * s, 1);
-        }
-        mbar_init(accfull, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < 4) {
-        // ===== producers: lane = position inside the K tile, warp w stages rows w, w+4, ... =====
-        const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
-        const uint32_t koff = (uint32_t)(lane >> 2) * 0 + (uint32_t)(lane & 3) * 4;      // element offset inside a 16-byte chunk
-        for (int it = 0; it < iters; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            const int64_t pos = pbeg + (int64_t)it * UK + lane;
-            const bool valid = pos < pend;
-            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            const uint32_t st_a = smem_u32(smem + (size_t)s * stage_bytes);
-            // A: gout rows (output channels)
-            {
-                const float* gb = gout + ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
-                const uint32_t dst = st_a + (uint32_t)(lane >> 2) * a_lbo + koff;
-#pragma unroll
-                for (int b = 0; b < UM / 4; b += 16) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int r = warp + 4 * (b + j);
-                        v[j] = (valid && oc0 + r < d.co) ? __ldg(gb + (int64_t)r * d.p_out) : 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int r = warp + 4 * (b + j);
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[j])) : "memory");
-                    }
-                }
-            }
-            // B: input rows (input channels), one image per tap through the tap's position map
-            for (int tap = 0; tap < d.ntap; ++tap) {
-                const int src = valid ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p) : -1;
-                const float* xb = in + ((int64_t)nn * d.c_in_total + in_ch0 + d.tap_in_ch[tap]) * d.p_in + src;
-                const uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + (uint32_t)(lane >> 2) * b_lbo + koff;
-                for (int b = 0; b < (pl.n_ic + 3) / 4; b += 16) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int r = warp + 4 * (b + j);
-                        v[j] = (src >= 0 && r < pl.n_ic && ic0 + r < d.ck) ? __ldg(xb + (int64_t)r * d.p_in) : 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int r = warp + 4 * (b + j);
-                        if (r < pl.n_ic) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[j])) : "memory");
-                    }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(full0 + 8 * s);
-        }
-        // ===== epilogue: TMEM lane = output channel row; atomics into the natural weight layout =====
-        mbar_wait(accfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int oc = oc0 + threadIdx.x;
-        float* wb = dw + (int64_t)g * d.g_w + (int64_t)oc * d.w_oc;
-        for (int tap = 0; tap < d.ntap; ++tap) {
-            for (int col0 = 0; col0 < pl.n_ic; col0 += 16) {
-                if (ic0 + col0 >= d.ck) break;                       // warp-uniform
-                uint32_t r[16];
-                tmem_ld16(taddr + tap * pl.n_ic + col0, r);
-                if (oc < d.co) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int ic = ic0 + col0 + j;
-                        if (ic < d.ck) atomicAdd(wb + d.tap_w_off[tap] + (int64_t)ic * d.w_ic, __uint_as_float(r[j]));
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else if (warp == 4) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_tf32(pl.n_ic);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                for (int tap = 0; tap < d.ntap; ++tap) {
-                    const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
-#pragma unroll
-                    for (int j = 0; j < UK / 8; ++j)
-                        umma_tf32(tmem_base + tap * pl.n_ic, smem_desc(a_addr + j * 2 * a_lbo, a_lbo, CORE_SBO),
-                                  smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
-                }
-                umma_commit(empty0 + 8 * s);
-            }
-            umma_commit(accfull);
-        }
-    }
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
-    }
-}
-
-int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
-    WgradPlan p;
-    return make_wgrad_plan(d, p) ? 1 : 0;
-}
-
-int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
-                       cudaStream_t stream) {
-    WgradPlan p;
-    if (!make_wgrad_plan(d, p)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tapconv_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return check_launch("tapconv_wgrad_tf32 attribute");
-        attr_set = true;
-    }
-    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tf32 memset");
-    dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
-    tapconv_wgrad_umma<<<grid, UMMA_THREADS, p.smem_bytes, stream>>>(d, p, in, gout, pmap, dw);
-    return check_launch("tapconv_wgrad_tf32");
 }
 
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d) {

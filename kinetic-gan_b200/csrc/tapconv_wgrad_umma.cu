@@ -1,0 +1,237 @@
+// Weight gradient of the tap convolution on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM):
+//     dW[tap][oc][ic] = sum_pos gout[oc, pos] * in[(tap, ic), pmap_tap(pos)]
+//   D[M = 128 output channels][N = n_ic input channels] per tap - the ntap accumulators sit side by side in TMEM;
+//   K = output positions.  Both operands are K-major in global memory already (positions are contiguous per channel),
+//   so producer lanes run along positions (coalesced 128-byte loads) and scatter 4-byte stores into the K-major
+//   core-matrix layout; a one-row pad per k-chunk (LBO = (rows+1)*16 B) makes those transposing stores bank-conflict
+//   free.  gout (A operand) is staged once per K tile and reused by all taps.  Split-K over CTAs, fp32 atomics into dW.
+// Warp roles: warps 0-7 producers (64 gathers in flight per thread) and epilogue, warp 8 MMA issuer / TMEM owner.
+#include "umma.cuh"
+
+namespace kgan {
+
+constexpr int WG_PRODUCER_WARPS = 8;
+constexpr int WG_THREADS = 32 * (WG_PRODUCER_WARPS + 1);
+constexpr int WG_UNIT = 16;                      // rows a warp loads per unit (= 128 rows of a 128-row image)
+
+struct WgradPlan {
+    int n_ic;         // input channels (UMMA N) per CTA, multiple of 16, <= 256
+    int ic_tiles, oc_tiles;
+    int tmem_cols;
+    int stages;
+    int a_bytes, b_bytes;   // per stage: A image, one tap's B image
+    int b_units;      // 16-row units per warp per tap: ceil(n_ic / 128)
+    int nchunks;
+    int64_t chunk;    // positions per split-K chunk (multiple of UK)
+    int smem_bytes;
+};
+
+static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
+    if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0 || d.ntap > 8) return false;
+    const int64_t total = (int64_t)d.n * d.p_out;
+    if (total < 1024) return false;
+    int n_max = (512 / d.ntap) / 16 * 16;
+    if (n_max > 256) n_max = 256;
+    if (d.ntap >= 3 && n_max > 128) n_max = 128;
+    p.n_ic = round_up(d.ck, 16) < n_max ? round_up(d.ck, 16) : n_max;
+    p.ic_tiles = ceil_div(d.ck, p.n_ic);
+    p.oc_tiles = ceil_div(d.co, UM);
+    p.tmem_cols = 32;
+    while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
+    p.a_bytes = 8 * (UM + 1) * 16;
+    p.b_bytes = 8 * (p.n_ic + 1) * 16;
+    p.b_units = ceil_div(p.n_ic, WG_PRODUCER_WARPS * WG_UNIT);
+    const int stage = p.a_bytes + d.ntap * p.b_bytes;
+    p.stages = (200 * 1024) / stage;
+    if (p.stages > 4) p.stages = 4;
+    if (p.stages < 2) return false;
+    const int64_t ktiles = ceil_div64(total, UK);
+    const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
+    int64_t nchunks = ceil_div64(2 * kNumSMs, tiles);
+    if (nchunks > ktiles / 4) nchunks = ktiles / 4;
+    if (nchunks < 1) nchunks = 1;
+    p.chunk = ceil_div64(ktiles, nchunks) * UK;
+    p.nchunks = (int)ceil_div64(total, p.chunk);
+    if ((int64_t)p.nchunks * d.groups > 65535) return false;
+    p.smem_bytes = p.stages * stage + 256;
+    return true;
+}
+
+__global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradPlan pl,
+                                                                 const float* __restrict__ in, const float* __restrict__ gout,
+                                                                 const int32_t* __restrict__ pmap, float* __restrict__ dw) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = pl.stages;
+    const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);           // full[S], empty[S], accfull
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+    const uint32_t a_lbo = (UM + 1) * 16, b_lbo = (pl.n_ic + 1) * 16;
+
+    const int ic0 = blockIdx.x * pl.n_ic, oc0 = blockIdx.y * UM;
+    const int g = blockIdx.z / pl.nchunks, ch = blockIdx.z % pl.nchunks;
+    const int64_t total_pos = (int64_t)d.n * d.p_out;
+    const int64_t pbeg = (int64_t)ch * pl.chunk, pend = min(total_pos, pbeg + pl.chunk);
+    const int iters = (int)ceil_div64(pend - pbeg, UK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 32 * WG_PRODUCER_WARPS);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WG_PRODUCER_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < WG_PRODUCER_WARPS) {
+        // ===== producers: lane = position inside the K tile; warp w stages rows w, w+8, ... of every image =====
+        const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
+        const uint32_t koff = (uint32_t)(lane >> 2), kel = (uint32_t)(lane & 3) * 4;      // k-chunk and byte offset inside it
+        const int units = 1 + d.ntap * pl.b_units;                                       // unit 0 = gout, then taps
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            const int64_t pos = pbeg + (int64_t)it * UK + lane;
+            const bool valid = pos < pend;
+            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+            const uint32_t st_a = smem_u32(smem + (size_t)s * stage_bytes);
+            const float* gb = gout + ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
+            const float* xn = in + ((int64_t)nn * d.c_in_total + in_ch0) * d.p_in;
+            bool waited = false;
+            for (int u0 = 0; u0 < units; u0 += 4) {
+                float v[4][WG_UNIT];
+                // issue every gather of up to 4 units back to back (64 loads in flight per thread) ...
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int u = u0 + q;
+                    if (u >= units) break;
+                    if (u == 0) {
+#pragma unroll
+                        for (int j = 0; j < WG_UNIT; ++j) {
+                            const int r = warp + WG_PRODUCER_WARPS * j;
+                            v[q][j] = ldg_pred(gb + (int64_t)r * d.p_out, valid && oc0 + r < d.co);
+                        }
+                    } else {
+                        const int tap = (u - 1) / pl.b_units, half = (u - 1) % pl.b_units;
+                        const int src = valid ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p) : -1;
+                        const float* xb = xn + (int64_t)d.tap_in_ch[tap] * d.p_in + src;
+#pragma unroll
+                        for (int j = 0; j < WG_UNIT; ++j) {
+                            const int r = warp + WG_PRODUCER_WARPS * (j + WG_UNIT * half);
+                            v[q][j] = ldg_pred(xb + (int64_t)r * d.p_in, src >= 0 && r < pl.n_ic && ic0 + r < d.ck);
+                        }
+                    }
+                }
+                if (!waited) {
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    waited = true;
+                }
+                // ... then round to tf32 and scatter into the K-major images
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int u = u0 + q;
+                    if (u >= units) break;
+                    if (u == 0) {
+                        const uint32_t dst = st_a + koff * a_lbo + kel;
+#pragma unroll
+                        for (int j = 0; j < WG_UNIT; ++j) {
+                            const int r = warp + WG_PRODUCER_WARPS * j;
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[q][j])) : "memory");
+                        }
+                    } else {
+                        const int tap = (u - 1) / pl.b_units, half = (u - 1) % pl.b_units;
+                        const uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + koff * b_lbo + kel;
+#pragma unroll
+                        for (int j = 0; j < WG_UNIT; ++j) {
+                            const int r = warp + WG_PRODUCER_WARPS * (j + WG_UNIT * half);
+                            if (r < pl.n_ic) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[q][j])) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full0 + 8 * s);
+        }
+        // ===== epilogue: TMEM lane = output channel row (warp % 4 selects the lane quarter, warp / 4 the column half) =====
+        mbar_wait(accfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3, colhalf = warp >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int oc = oc0 + quarter * 32 + lane;
+        float* wb = dw + (int64_t)g * d.g_w + (int64_t)oc * d.w_oc;
+        for (int tap = 0; tap < d.ntap; ++tap) {
+            for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
+                if (ic0 + col0 >= d.ck) break;                       // warp-uniform
+                uint32_t r[16];
+                tmem_ld16(taddr + tap * pl.n_ic + col0, r);
+                if (oc < d.co) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int ic = ic0 + col0 + j;
+                        if (ic < d.ck) atomicAdd(wb + d.tap_w_off[tap] + (int64_t)ic * d.w_ic, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_tf32(pl.n_ic);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                for (int tap = 0; tap < d.ntap; ++tap) {
+                    const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
+#pragma unroll
+                    for (int j = 0; j < UK / 8; ++j)
+                        umma_tf32(tmem_base + tap * pl.n_ic, smem_desc(a_addr + j * 2 * a_lbo, a_lbo, CORE_SBO),
+                                  smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(accfull);
+        }
+    }
+    __syncthreads();
+    if (warp == WG_PRODUCER_WARPS) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
+    }
+}
+
+int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
+    WgradPlan p;
+    return make_wgrad_plan(d, p) ? 1 : 0;
+}
+
+int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
+                       cudaStream_t stream) {
+    WgradPlan p;
+    if (!make_wgrad_plan(d, p)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tapconv_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return check_launch("tapconv_wgrad_tf32 attribute");
+        attr_set = true;
+    }
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tf32 memset");
+    dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
+    tapconv_wgrad_umma<<<grid, WG_THREADS, p.smem_bytes, stream>>>(d, p, in, gout, pmap, dw);
+    return check_launch("tapconv_wgrad_tf32");
+}
+
+}  // namespace kgan
