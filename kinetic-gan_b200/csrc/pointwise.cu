@@ -1,4 +1,4 @@
-// Memory-bound kernels of the ST-GCN hot path: adjacency product, fused epilogues, plane gathers,
+// Memory-bound kernels of the ST-GCN hot path (the adjacency product lives in adjmix.cu): fused epilogues, plane gathers,
 // label planes, BatchNorm, Adam.  All are HBM-bound streaming kernels: lanes run along the contiguous
 // (t, v) plane axis, grids are sized in multiples of the SM count.  See include/kgan.h for semantics.
 #include "common.cuh"
@@ -31,151 +31,6 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     float r = (lane < nw) ? red[lane] : 0.f;
     r = warp_sum(r);
     return r;
-}
-
-// ------------------------------------------------------------------------------------------------
-// adjacency product
-// ------------------------------------------------------------------------------------------------
-// A_eff = A (.) edge_importance keeps the sparsity of the skeleton partitions (73 of 1875 entries at 25 joints), so
-// both kernels first compact the non-zero entries of A in shared memory and then touch only those: exact (a zero
-// multiplicand contributes nothing) and ~V times fewer instructions than the dense loop.
-__global__ void __launch_bounds__(PT) adjmix_fwd_k(const float* __restrict__ x, const float* __restrict__ A, float* __restrict__ out,
-                                                    int n, int c, int t, int v, int w, int k) {
-    extern __shared__ __align__(16) float sm[];
-    float* As = sm;                                   // [k][v][w]
-    int* nzv = (int*)(sm + k * v * w);                // [k*w][v] source joints with A != 0
-    int* nzc = nzv + k * w * v;                       // [k*w]
-    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[i] = A[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < k * w; i += blockDim.x) {
-        const int kk = i / w, ww = i - kk * w;
-        int cnt = 0;
-        for (int j = 0; j < v; ++j)
-            if (As[(kk * v + j) * w + ww] != 0.f) nzv[i * v + cnt++] = j;
-        nzc[i] = cnt;
-    }
-    __syncthreads();
-    const int64_t total = (int64_t)n * k * c * t * w;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int ww = (int)(i % w);
-        int64_t r = i / w;
-        const int tt = (int)(r % t);
-        r /= t;
-        const int kc = (int)(r % ((int64_t)k * c));
-        const int nn = (int)(r / ((int64_t)k * c));
-        const int kk = kc / c, cc = kc - kk * c;
-        const float* xr = x + (((int64_t)nn * c + cc) * t + tt) * v;
-        const int kw = kk * w + ww, cnt = nzc[kw];
-        float acc = 0.f;
-        for (int j = 0; j < cnt; ++j) {
-            const int vv = nzv[kw * v + j];
-            acc = fmaf(__ldg(xr + vv), As[(kk * v + vv) * w + ww], acc);
-        }
-        out[i] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(PT) adjmix_bwd_x_k(const float* __restrict__ g, const float* __restrict__ A, float* __restrict__ gx,
-                                                      int n, int c, int t, int v, int w, int k) {
-    extern __shared__ __align__(16) float sm[];
-    float* As = sm;                                   // [k][v][w]
-    int* nzw = (int*)(sm + k * v * w);                // [v][k*w] (k*w + w index) with A != 0
-    int* nzc = nzw + v * k * w;                       // [v]
-    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) As[i] = A[i];
-    __syncthreads();
-    for (int vv = threadIdx.x; vv < v; vv += blockDim.x) {
-        int cnt = 0;
-        for (int kk = 0; kk < k; ++kk)
-            for (int ww = 0; ww < w; ++ww)
-                if (As[(kk * v + vv) * w + ww] != 0.f) nzw[vv * k * w + cnt++] = kk * w + ww;
-        nzc[vv] = cnt;
-    }
-    __syncthreads();
-    const int64_t total = (int64_t)n * c * t * v;
-    const int64_t kstride = (int64_t)c * t * w;       // distance between partitions k of the same (n, c, t) row in g
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int vv = (int)(i % v);
-        int64_t r = i / v;
-        const int tt = (int)(r % t);
-        r /= t;
-        const int cc = (int)(r % c);
-        const int nn = (int)(r / c);
-        const float* gr = g + (((int64_t)nn * k * c + cc) * t + tt) * w;
-        const int cnt = nzc[vv];
-        float acc = 0.f;
-        for (int j = 0; j < cnt; ++j) {
-            const int e = nzw[vv * k * w + j], kk = e / w, ww = e - kk * w;
-            acc = fmaf(__ldg(gr + kk * kstride + ww), As[(kk * v + vv) * w + ww], acc);
-        }
-        gx[i] = acc;
-    }
-}
-
-// gA[k,v,w] = sum_{n,c,t} x[n,c,t,v] * g[n,kC+c,t,w]: per (n,c) plane pair a (V x T).(T x W) product, summed over all
-// planes.  A CTA stages PL consecutive planes with linear, fully coalesced copies (x planes are contiguous in memory;
-// for each k so are the matching g planes of one sample), every thread owns one 4x4 (v,w) register tile of one
-// partition k and a strided subset of the staged (plane, t) rows; CTA partials are merged with fp32 atomics.
-__global__ void __launch_bounds__(PT) adjmix_bwd_a_k(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gA,
-                                                      int n, int c, int t, int v, int w, int k, int pl, int64_t planes_per_cta) {
-    extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                        // [pl][t][v]
-    float* gs = sm + pl * t * v;           // [k][pl][t][w]
-    const int vt = (v + 3) >> 2, wt = (w + 3) >> 2, ntile = k * vt * wt;
-    const int rgroups = max(1, PT / ntile);
-    const int tile = threadIdx.x % ntile, grp = threadIdx.x / ntile;
-    const bool active = grp < rgroups;
-    const int kk = tile / (vt * wt), v0 = ((tile / wt) % vt) * 4, w0 = (tile % wt) * 4;
-    const int64_t planes = (int64_t)n * c;
-    const int64_t pbeg = (int64_t)blockIdx.x * planes_per_cta, pend = min(planes, pbeg + planes_per_cta);
-    const int tv = t * v, tw = t * w;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int64_t p0 = pbeg; p0 < pend; p0 += pl) {
-        const int np = (int)min((int64_t)pl, pend - p0);
-        for (int i = threadIdx.x; i < np * tv; i += blockDim.x) xs[i] = __ldg(x + p0 * tv + i);
-        for (int q = 0; q < k * np; ++q) {                        // (k2, plane) pairs: one contiguous T*W block each
-            const int k2 = q / np, pp = q - k2 * np;
-            const int64_t plane = p0 + pp;
-            const int64_t nn = plane / c, cc = plane - nn * c;
-            const float* src = g + ((nn * k + k2) * c + cc) * tw;
-            float* dst = gs + ((int64_t)k2 * pl + pp) * tw;
-            for (int i = threadIdx.x; i < tw; i += blockDim.x) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();
-        if (active) {
-            const int rows = np * t;
-            const float* gk = gs + (int64_t)kk * pl * tw;
-            for (int rr = grp; rr < rows; rr += rgroups) {
-                float xa[4], ga[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xa[i] = (v0 + i < v) ? xs[rr * v + v0 + i] : 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ga[j] = (w0 + j < w) ? gk[rr * w + w0 + j] : 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
-            }
-        }
-        __syncthreads();
-    }
-    // merge the row groups of this CTA in shared memory first: one global atomic per output per CTA (k*v*w can be as
-    // small as 3 addresses, which thousands of same-address L2 atomics would serialise)
-    const int nout = k * v * w;
-    for (int i = threadIdx.x; i < nout; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (v0 + i < v && w0 + j < w) atomicAdd(sm + (kk * v + v0 + i) * w + w0 + j, acc[i][j]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nout; i += blockDim.x) atomicAdd(gA + i, sm[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,52 +229,6 @@ __global__ void __launch_bounds__(PT) interpolate_k(const float* __restrict__ al
 }  // namespace kgan
 
 using namespace kgan;
-
-extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
-    KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 4096, "adjmix_fwd: bad shape");
-    const int64_t total = (int64_t)n * k * c * t * w;
-    const size_t smem = sizeof(float) * (2 * (size_t)k * v * w + k * w);
-    adjmix_fwd_k<<<grid_for(total), PT, smem, (cudaStream_t)stream>>>(x, A, out, n, c, t, v, w, k);
-    return check_launch("adjmix_fwd");
-}
-
-extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream) {
-    KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * v * w <= 4096, "adjmix_bwd_x: bad shape");
-    const int64_t total = (int64_t)n * c * t * v;
-    const size_t smem = sizeof(float) * (2 * (size_t)k * v * w + v);
-    adjmix_bwd_x_k<<<grid_for(total), PT, smem, (cudaStream_t)stream>>>(g, A, gx, n, c, t, v, w, k);
-    return check_launch("adjmix_bwd_x");
-}
-
-extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
-    KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
-    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0 && k * ((v + 3) / 4) * ((w + 3) / 4) <= PT, "adjmix_bwd_a: k*v*w too large");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
-    const int64_t plane_floats = (int64_t)t * (v + (int64_t)k * w);
-    KGAN_REQUIRE(plane_floats * 4 <= 160 * 1024, "adjmix_bwd_a: one (T, V) plane does not fit in shared memory");
-    int64_t pl = (40 * 1024 / 4) / plane_floats;                 // planes per stage: <= 40 KB so several CTAs share an SM
-    if (pl < 1) pl = 1;
-    if (pl * t > 2048) pl = (2048 + t - 1) / t;
-    const int64_t planes = (int64_t)n * c;
-    if (pl > planes) pl = planes;
-    int64_t ctas = ceil_div64(planes, pl);
-    if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
-    const int64_t per = ceil_div64(ceil_div64(planes, ctas), pl) * pl;
-    ctas = ceil_div64(planes, per);
-    size_t smem = sizeof(float) * (size_t)(pl * plane_floats);
-    if (smem < sizeof(float) * (size_t)k * v * w) smem = sizeof(float) * (size_t)k * v * w;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(adjmix_bwd_a_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-            return check_launch("adjmix_bwd_a attribute");
-        attr_set = true;
-    }
-    adjmix_bwd_a_k<<<(unsigned)ctas, PT, smem, s>>>(x, g, gA, n, c, t, v, w, k, (int)pl, per);
-    return check_launch("adjmix_bwd_a");
-}
 
 extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bias, const float* nw, const float* noise, float* out,
                                  int n, int c, int p, int act, void* stream) {

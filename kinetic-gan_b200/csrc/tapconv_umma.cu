@@ -1,31 +1,41 @@
 // Tap convolution on the 5th-generation tensor cores (KGAN_PREC_TF32): tcgen05.mma kind::tf32, fp32 accumulators
 // in TMEM, weights staged by the bulk-copy engine (cp.async.bulk -> UBLKCP) from a pre-packed tf32 image,
-// activations gathered by SIMT producer warps (position map = zero padding / joint & frame selection / tap shift),
-// mbarrier full/empty ring between producers and the single MMA-issuing thread.
+// activations gathered by SIMT producer warps (position map = zero padding / joint & frame selection / tap shift).
 //
 // GEMM orientation (see DESIGN.md "tcgen05 tap convolution"):
 //   D[M = 128 positions][N = output channels]  +=  A[M][K] * B[N][K]^T,   K = (input-channel tile, tap)
-//   A (activations): gathered from NCHW global memory, one thread per position row, written K-major into shared
-//       memory in the canonical no-swizzle core-matrix layout (8 rows x 16 B), rounded to tf32 (cvt.rna).
+//   A (activations): gathered from NCHW global memory, written K-major into shared memory in the canonical no-swizzle
+//       core-matrix layout (8 rows x 16 B), rounded to tf32 (cvt.rna).
 //   B (weights):     pre-packed by tapconv_pack_k in exactly the shared-memory image, so a stage is 8 bulk copies.
 //   D: TMEM lane = position, TMEM column = output channel -> the epilogue thread that owns lane l stores
 //       out[n, oc, p(l)]: for a fixed oc consecutive lanes are consecutive addresses (coalesced NCHW stores).
 //
-// The layer is HBM/L2-bound at tensor-core rates (AI ~ 0.75*C_out flop/B unfused), so each CTA computes ALL of its
-// output channels for a 128-position tile and reads the activation tile exactly once.
+// Persistent, warp-specialised CTA (one per SM), three pipelines:
+//   warps 0-7   activation producers: thread = (row, k-half); PF stages of gathers in flight per thread
+//   warp  8     MMA issuer (one thread) + TMEM owner; accumulators are double-buffered in TMEM (2 x n_cta columns)
+//   warp  9     weight loader (one thread, bulk copies)
+//   warps 10-13 epilogue: drain accumulator b of tile i (TMEM -> bias/add/act -> global) while tile i+1 is computed
+//   smem ring full[S]/empty[S] (producers+loader <-> MMA), tmem_full[2]/tmem_empty[2] (MMA <-> epilogue).
+// The layer is HBM/L2-bound at tensor-core rates (AI ~ 0.75*C_out flop/B unfused): what matters is bytes in flight.
 #include "umma.cuh"
 
 namespace kgan {
 
+constexpr int FW_PRODUCER_WARPS = 8;
+constexpr int FW_MMA_WARP = 8, FW_LOAD_WARP = 9, FW_EPI_WARP0 = 10;
+constexpr int FW_THREADS = 32 * 14;
+constexpr int FW_KH = UK / 2;                  // channels per producer thread per stage
+constexpr int FW_PF = 3;                       // stages of gathers in flight per producer thread
+
 struct UmmaPlan {
-    int n_cta;        // output channels per CTA (multiple of 16; of 32 when > 256)
-    int n_split;      // CTAs along output channels
+    int n_cta;        // output channels per tile (UMMA N, multiple of 16, <= 256)
+    int n_split;      // tiles along output channels
     int n_rows;       // n_cta * n_split: rows of the packed weight image (zero padded)
-    int n_acc;        // accumulators per CTA (1 or 2)
-    int n_per_acc;    // UMMA N
-    int tmem_cols;    // power of two >= n_cta, >= 32
+    int tmem_cols;    // power of two >= 2 * n_cta
     int stages;
     int nkt;          // input-channel tiles of UK
+    int m_tiles;      // position tiles of 128
+    int num_tiles;    // m_tiles * n_split * groups
     int smem_bytes;
 };
 
@@ -33,26 +43,23 @@ static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
     if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0) return false;
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 256) return false;
-    const int64_t tiles = ceil_div64(total, UM) * d.groups;
+    const int64_t m_tiles = ceil_div64(total, UM);
+    if (m_tiles * d.groups > (1 << 24)) return false;
     const int n16 = round_up(d.co, 16);
-    int split = ceil_div(n16, 512);
-    while (tiles * split < kNumSMs && ceil_div(n16, split * 2) >= 64) split *= 2;
-    int n_cta = round_up(ceil_div(n16, split), 16);
-    if (n_cta > 256) n_cta = round_up(n_cta, 32);
-    p.n_cta = n_cta;
-    p.n_split = ceil_div(n16, n_cta);
+    int split = ceil_div(n16, 256);
+    while (m_tiles * d.groups * split < kNumSMs && ceil_div(n16, split * 2) >= 64) split *= 2;
+    p.n_cta = round_up(ceil_div(n16, split), 16);
+    p.n_split = ceil_div(n16, p.n_cta);
     p.n_rows = p.n_cta * p.n_split;
-    p.n_acc = n_cta > 256 ? 2 : 1;
-    p.n_per_acc = n_cta / p.n_acc;
     p.tmem_cols = 32;
-    while (p.tmem_cols < n_cta) p.tmem_cols *= 2;
+    while (p.tmem_cols < 2 * p.n_cta) p.tmem_cols *= 2;
     p.nkt = ceil_div(d.ck, UK);
-    const int stage = A_STAGE_BYTES + n_cta * UK * 4;
-    const int budget = (p.tmem_cols <= 256 ? 100 : 200) * 1024;      // <= 256 columns: two CTAs per SM
-    p.stages = budget / stage;
-    if (p.stages > 6) p.stages = 6;
-    if (p.stages < 2) p.stages = 2;
-    p.smem_bytes = p.stages * stage + 256;
+    p.m_tiles = (int)m_tiles;
+    p.num_tiles = (int)m_tiles * p.n_split * d.groups;
+    const int stage = A_STAGE_BYTES + p.n_cta * UK * 4;
+    p.stages = (200 * 1024) / stage;
+    if (p.stages > 8) p.stages = 8;
+    p.smem_bytes = p.stages * stage + 512;
     return true;
 }
 
@@ -81,38 +88,51 @@ __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kg
     }
 }
 
+// tile id -> (group, position tile, channel split); consecutive ids share the activation tile (L2 reuse)
+struct TileCoord {
+    int g, mt, ns;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, const UmmaPlan& pl) {
+    TileCoord c;
+    c.ns = tile % pl.n_split;
+    const int r = tile / pl.n_split;
+    c.mt = r % pl.m_tiles;
+    c.g = r / pl.m_tiles;
+    return c;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UMMA_THREADS) tapconv_fwd_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ UmmaPlan pl,
-                                                                 const float* __restrict__ in, const float* __restrict__ wp,
-                                                                 const int32_t* __restrict__ pmap, const float* __restrict__ bias,
-                                                                 const float* __restrict__ add, float* __restrict__ out) {
+__global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ UmmaPlan pl,
+                                                                  const float* __restrict__ in, const float* __restrict__ wp,
+                                                                  const int32_t* __restrict__ pmap, const float* __restrict__ bias,
+                                                                  const float* __restrict__ add, float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int b_stage_bytes = pl.n_cta * UK * 4;
     uint8_t* a_base = smem;
     uint8_t* b_base = smem + (size_t)S * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * b_stage_bytes);     // full[S], empty[S], accfull
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
-
-    const int g = blockIdx.z;
-    const int oc_base = blockIdx.y * pl.n_cta;
-    const int64_t m0 = (int64_t)blockIdx.x * UM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * b_stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+    const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
     const int64_t total_pos = (int64_t)d.n * d.p_out;
-    const int iters = pl.nkt * d.ntap;
+    const int kiters = pl.nkt * d.ntap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, UM + 1);       // 128 producer threads + the weight loader's expect_tx arrive
-            mbar_init(empty0 + 8 * s, 1);           // tcgen05.commit
+            mbar_init(full0 + 8 * s, 32 * FW_PRODUCER_WARPS + 1);    // producer threads + the weight loader's expect_tx arrive
+            mbar_init(empty0 + 8 * s, 1);                            // tcgen05.commit
         }
-        mbar_init(accfull, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull0 + 8 * b, 1);                            // tcgen05.commit after the last MMA of a tile
+            mbar_init(tempty0 + 8 * b, 128);                         // epilogue threads
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == FW_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -122,123 +142,166 @@ __global__ void __launch_bounds__(UMMA_THREADS) tapconv_fwd_umma(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ===== activation producers: thread t owns tile row t (one output position) =====
-        const int t = threadIdx.x;
-        const int64_t pos = m0 + t;
-        const bool valid = pos < total_pos;
-        const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
-        const float* in_n = in + ((int64_t)nn * d.c_in_total + g * d.g_in) * d.p_in;
-        // position map of this row for every tap (constant over the input-channel tiles)
-        constexpr int SRC_CACHE = 4;
-        int srcs[SRC_CACHE];
+    if (warp < FW_PRODUCER_WARPS) {
+        // ===== activation producers: thread = (tile row, k half): FW_KH channels of one position per stage =====
+        const int row = threadIdx.x & (UM - 1), kh = threadIdx.x >> 7;
+        int kit = 0;                                                  // ring position, continues across tiles
+        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord(tile, pl);
+            const int64_t pos = (int64_t)tc.mt * UM + row;
+            const bool valid = pos < total_pos;
+            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+            const float* in_n = in + ((int64_t)nn * d.c_in_total + tc.g * d.g_in) * d.p_in;
+            constexpr int SRC_CACHE = 4;                              // position map of this row for the first taps
+            int srcs[SRC_CACHE];
 #pragma unroll
-        for (int i = 0; i < SRC_CACHE; ++i) srcs[i] = (valid && i < d.ntap) ? __ldg(pmap + (int64_t)d.tap_row[i] * d.p_out + p) : -1;
-        // all UK loads of a stage are issued back to back (volatile asm keeps them ahead of the barrier wait), and the loads
-        // of stage it+1 are in flight while stage it is converted and stored: two stages of gathers outstanding per thread
-        auto issue = [&](int it, float (&v)[UK]) {
-            const int ict = it / d.ntap, tap = it - ict * d.ntap, ic0 = ict * UK;
-            int src = -1;
-            if (tap < SRC_CACHE) {
+            for (int i = 0; i < SRC_CACHE; ++i) srcs[i] = (valid && i < d.ntap) ? __ldg(pmap + (int64_t)d.tap_row[i] * d.p_out + p) : -1;
+
+            auto issue = [&](int it, float (&v)[FW_KH]) {
+                const int ict = it / d.ntap, tap = it - ict * d.ntap, ic0 = ict * UK + kh * FW_KH;
+                int src = -1;
+                if (tap < SRC_CACHE) {
 #pragma unroll
-                for (int i = 0; i < SRC_CACHE; ++i) src = (i == tap) ? srcs[i] : src;
-            } else if (valid) {
-                src = __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p);
-            }
-            const float* xb = in_n + (int64_t)(d.tap_in_ch[tap] + ic0) * d.p_in + src;
+                    for (int i = 0; i < SRC_CACHE; ++i) src = (i == tap) ? srcs[i] : src;
+                } else if (valid) {
+                    src = __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p);
+                }
+                const float* xb = in_n + (int64_t)(d.tap_in_ch[tap] + ic0) * d.p_in + src;
 #pragma unroll
-            for (int kk = 0; kk < UK; ++kk) v[kk] = ldg_pred(xb + (int64_t)kk * d.p_in, src >= 0 && ic0 + kk < d.ck);
-        };
-        auto stage_out = [&](int it, float (&v)[UK]) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);                      // slot free (first lap passes immediately)
-            const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + t * 16;
+                for (int kk = 0; kk < FW_KH; ++kk) v[kk] = ldg_pred(xb + (int64_t)kk * d.p_in, src >= 0 && ic0 + kk < d.ck);
+            };
+            auto stage_out = [&](int it, float (&v)[FW_KH]) {
+                const int k = kit + it, s = k % S;
+                const uint32_t ph = (uint32_t)(k / S) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);                   // slot free (first lap passes immediately)
+                const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + kh * (FW_KH / 4) * A_LBO + row * 16;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * A_LBO), "r"(to_tf32(v[4 * c])),
-                             "r"(to_tf32(v[4 * c + 1])), "r"(to_tf32(v[4 * c + 2])), "r"(to_tf32(v[4 * c + 3]))
-                             : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(full0 + 8 * s);
-        };
-        float va[UK], vb[UK];
-        issue(0, va);
-        for (int it = 0; it < iters; it += 2) {
-            if (it + 1 < iters) issue(it + 1, vb);
-            stage_out(it, va);
-            if (it + 1 < iters) {
-                if (it + 2 < iters) issue(it + 2, va);
-                stage_out(it + 1, vb);
-            }
-        }
-        // ===== epilogue: TMEM lane t -> out[n, oc, p] =====
-        mbar_wait(accfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int out_ch0 = g * d.g_out;
-        for (int col0 = 0; col0 < pl.n_cta; col0 += 16) {
-            if (oc_base + col0 >= d.co) break;                       // warp-uniform
-            uint32_t r[16];
-            tmem_ld16(taddr + col0, r);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int oc = oc_base + col0 + j;
-                    if (oc < d.co) {
-                        const int64_t o = ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.p_out + p;
-                        float val = __uint_as_float(r[j]);
-                        if (bias) val += __ldg(bias + out_ch0 + oc);
-                        if (add) val += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.add_period + p % d.add_period : o));
-                        out[o] = apply_act(val, d.act);
-                    }
+                for (int c = 0; c < FW_KH / 4; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * A_LBO), "r"(to_tf32(v[4 * c])),
+                                 "r"(to_tf32(v[4 * c + 1])), "r"(to_tf32(v[4 * c + 2])), "r"(to_tf32(v[4 * c + 3]))
+                                 : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(full0 + 8 * s);
+            };
+            // FW_PF stages of gathers are always in flight: issue(it + PF) follows stage_out(it) on the same registers
+            float v0[FW_KH], v1[FW_KH], v2[FW_KH];
+            static_assert(FW_PF == 3, "register ring below is written for PF = 3");
+            if (0 < kiters) issue(0, v0);
+            if (1 < kiters) issue(1, v1);
+            if (2 < kiters) issue(2, v2);
+            for (int it = 0; it < kiters; it += 3) {
+                stage_out(it, v0);
+                if (it + 3 < kiters) issue(it + 3, v0);
+                if (it + 1 < kiters) {
+                    stage_out(it + 1, v1);
+                    if (it + 4 < kiters) issue(it + 4, v1);
+                }
+                if (it + 2 < kiters) {
+                    stage_out(it + 2, v2);
+                    if (it + 5 < kiters) issue(it + 5, v2);
                 }
             }
+            kit += kiters;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else if (warp == 4) {
+    } else if (warp == FW_MMA_WARP) {
         // ===== MMA issuer: one thread drives the tensor core =====
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_tf32(pl.n_per_acc);
+            const uint32_t idesc = instr_desc_tf32(pl.n_cta);
             const uint32_t b_lbo = pl.n_cta * 16;
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+            int kit = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                const uint32_t acc = tmem_base + buf * pl.n_cta;
+                for (int it = 0; it < kiters; ++it) {
+                    const int k = kit + it, s = k % S;
+                    const uint32_t ph = (uint32_t)(k / S) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
-                for (int j = 0; j < UK / 8; ++j) {
-                    const uint64_t adesc = smem_desc(a_addr + j * 2 * A_LBO, A_LBO, CORE_SBO);
-                    for (int a = 0; a < pl.n_acc; ++a) {
-                        const uint64_t bdesc = smem_desc(b_addr + a * pl.n_per_acc * 16 + j * 2 * b_lbo, b_lbo, CORE_SBO);
-                        umma_tf32(tmem_base + a * pl.n_per_acc, adesc, bdesc, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    }
+                    for (int j = 0; j < UK / 8; ++j)
+                        umma_tf32(acc, smem_desc(a_addr + j * 2 * A_LBO, A_LBO, CORE_SBO), smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO),
+                                  idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);                      // frees the stage when these MMAs retire
                 }
-                umma_commit(empty0 + 8 * s);                          // frees the stage when these MMAs retire
+                umma_commit(tfull0 + 8 * buf);                        // accumulator complete -> epilogue
+                kit += kiters;
             }
-            umma_commit(accfull);
         }
-    } else {
+    } else if (warp == FW_LOAD_WARP) {
         // ===== weight loader: bulk copies of the packed tf32 image =====
         if (lane == 0) {
-            const float* wg = wp + (int64_t)g * pl.nkt * d.ntap * pl.n_rows * UK;
             const uint32_t chunk_bytes = pl.n_cta * 16;
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                mbar_arrive_expect_tx(full0 + 8 * s, chunk_bytes * 8);
-                const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
-                const uint32_t dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
+            int kit = 0;
+            for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, pl);
+                const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
+                const int oc_base = tc.ns * pl.n_cta;
+                for (int it = 0; it < kiters; ++it) {
+                    const int k = kit + it, s = k % S;
+                    const uint32_t ph = (uint32_t)(k / S) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full0 + 8 * s, chunk_bytes * 8);
+                    const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
+                    const uint32_t dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                    for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                }
+                kit += kiters;
             }
         }
+    } else {
+        // ===== epilogue warps: TMEM lane = position row; 32 columns per step, residual loads issued before the TMEM wait =====
+        const int quarter = warp & 3;                                 // warps 10..13 -> TMEM lane quarters 2,3,0,1
+        const int row = quarter * 32 + lane;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
+            const TileCoord tc = tile_coord(tile, pl);
+            const int buf = ti & 1;
+            const int64_t pos = (int64_t)tc.mt * UM + row;
+            const bool valid = pos < total_pos;
+            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+            const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
+            const int64_t obase = ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
+            const int64_t abase = d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0) * d.add_period + p % d.add_period : obase;
+            const int64_t astride = d.add_period ? d.add_period : d.p_out;
+            mbar_wait(tfull0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
+            for (int col0 = 0; col0 < pl.n_cta; col0 += 32) {
+                if (oc_base + col0 >= d.co) break;                    // warp-uniform
+                float av[32];
+                if (add) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) av[j] = ldg_pred(add + abase + (int64_t)(oc_base + col0 + j) * astride, valid && oc_base + col0 + j < d.co);
+                }
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(taddr + col0, r0);
+                if (col0 + 16 < pl.n_cta) tmem_ld16_nowait(taddr + col0 + 16, r1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int oc = oc_base + col0 + j;
+                        if (oc < d.co && col0 + j < pl.n_cta) {
+                            float val = __uint_as_float(j < 16 ? r0[j & 15] : r1[j & 15]);
+                            if (bias) val += __ldg(bias + out_ch0 + oc);
+                            if (add) val += av[j];
+                            out[obase + (int64_t)oc * d.p_out] = apply_act(val, d.act);
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty0 + 8 * buf);                           // accumulator may be overwritten
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == FW_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
     }
@@ -273,9 +336,8 @@ int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* w
             return check_launch("tapconv_fwd_tf32 attribute");
         attr_set = true;
     }
-    const int64_t tiles = ceil_div64((int64_t)d.n * d.p_out, UM);
-    dim3 grid((unsigned)tiles, p.n_split, d.groups);
-    tapconv_fwd_umma<<<grid, UMMA_THREADS, p.smem_bytes, stream>>>(d, p, in, wp, pmap, bias, add, out);
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;         // persistent: one CTA per SM
+    tapconv_fwd_umma<<<grid, FW_THREADS, p.smem_bytes, stream>>>(d, p, in, wp, pmap, bias, add, out);
     return check_launch("tapconv_fwd_tf32");
 }
 
