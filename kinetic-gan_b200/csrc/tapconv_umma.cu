@@ -42,7 +42,7 @@ struct UmmaPlan {
 static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
     if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0) return false;
     const int64_t total = (int64_t)d.n * d.p_out;
-    if (total < 256) return false;
+    if (total < 256 || total >= (1ll << 31) - UM) return false;
     const int64_t m_tiles = ceil_div64(total, UM);
     if (m_tiles * d.groups > (1 << 24)) return false;
     const int n16 = round_up(d.co, 16);
@@ -101,6 +101,35 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const UmmaPlan& pl) {
     return c;
 }
 
+// Drain one accumulator (this thread's TMEM lane = one output position) to global memory, 16 channels per step:
+// residual values are requested before the TMEM wait, the bias chunk is loaded once per step (lane j holds channel j)
+// and broadcast by shuffle, the activation is a template parameter, addresses advance by one plane per channel.
+template <int ACT>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int ncols, int n_cta, bool valid, float* __restrict__ op, int p_out,
+                                              const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane) {
+    for (int col0 = 0; col0 < ncols; col0 += 16) {
+        const int nc = min(16, ncols - col0);                         // warp-uniform
+        float av[16];
+        if (ap) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) av[j] = ldg_pred(ap + (int64_t)(col0 + j) * astride, valid && j < nc);
+        }
+        const float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        uint32_t r[16];
+        tmem_ld16(taddr + col0, r);
+        float* o = op + (int64_t)col0 * p_out;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float val = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+            if (ap) val += av[j];
+            if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
+            if (ACT == KGAN_ACT_TANH) val = tanhf(val);
+            if (valid && j < nc) *o = val;
+            o += p_out;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------------------------
@@ -143,49 +172,82 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < FW_PRODUCER_WARPS) {
-        // ===== activation producers: thread = (tile row, k half): FW_KH channels of one position per stage =====
-        const int row = threadIdx.x & (UM - 1), kh = threadIdx.x >> 7;
+        // ===== activation producers: warp = 16-byte k-chunk (4 channels), lane q = tile rows q, q+32, q+64, q+96 =====
+        // 16 elements per thread per stage: loads are coalesced along positions (lanes = consecutive rows), the four
+        // 16-byte shared stores of a thread go to consecutive rows across lanes (conflict-free), and addressing is one
+        // 64-bit row pointer per (tap, row) plus a 32-bit channel offset.
+        const int q = lane, chunk = warp;
         int kit = 0;                                                  // ring position, continues across tiles
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
             const TileCoord tc = tile_coord(tile, pl);
-            const int64_t pos = (int64_t)tc.mt * UM + row;
-            const bool valid = pos < total_pos;
-            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
-            const float* in_n = in + ((int64_t)nn * d.c_in_total + tc.g * d.g_in) * d.p_in;
-            constexpr int SRC_CACHE = 4;                              // position map of this row for the first taps
-            int srcs[SRC_CACHE];
+            constexpr int SRC_CACHE = 3;                              // taps whose position map is kept in registers
+            const float* rowp[SRC_CACHE][4];                          // in + sample/tap offset + source position (or null)
+            int pp[4];
+            const float* in_n[4];
 #pragma unroll
-            for (int i = 0; i < SRC_CACHE; ++i) srcs[i] = (valid && i < d.ntap) ? __ldg(pmap + (int64_t)d.tap_row[i] * d.p_out + p) : -1;
-
-            auto issue = [&](int it, float (&v)[FW_KH]) {
-                const int ict = it / d.ntap, tap = it - ict * d.ntap, ic0 = ict * UK + kh * FW_KH;
-                int src = -1;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t pos = (uint32_t)tc.mt * UM + q + 32 * i;     // make_plan guarantees total_pos < 2^31
+                const bool valid = pos < (uint32_t)total_pos;
+                const uint32_t nn = valid ? pos / (uint32_t)d.p_out : 0u;
+                pp[i] = valid ? (int)(pos - nn * (uint32_t)d.p_out) : -1;
+                in_n[i] = in + ((int64_t)nn * d.c_in_total + tc.g * d.g_in) * d.p_in;
+#pragma unroll
+                for (int tp = 0; tp < SRC_CACHE; ++tp) {
+                    int src = -1;
+                    if (tp < d.ntap && valid) src = __ldg(pmap + (int64_t)d.tap_row[tp] * d.p_out + pp[i]);
+                    rowp[tp][i] = src >= 0 ? in_n[i] + (int64_t)d.tap_in_ch[tp < d.ntap ? tp : 0] * d.p_in + src : nullptr;
+                }
+            }
+            auto issue = [&](int it, float (&v)[16]) {
+                const int ict = it / d.ntap, tap = it - ict * d.ntap;
+                const int ch0 = ict * UK + chunk * 4;                 // first of this thread's 4 channels
+                const float* rp[4];
                 if (tap < SRC_CACHE) {
 #pragma unroll
-                    for (int i = 0; i < SRC_CACHE; ++i) src = (i == tap) ? srcs[i] : src;
-                } else if (valid) {
-                    src = __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p);
-                }
-                const float* xb = in_n + (int64_t)(d.tap_in_ch[tap] + ic0) * d.p_in + src;
+                    for (int i = 0; i < 4; ++i) {
+                        rp[i] = rowp[0][i];
 #pragma unroll
-                for (int kk = 0; kk < FW_KH; ++kk) v[kk] = ldg_pred(xb + (int64_t)kk * d.p_in, src >= 0 && ic0 + kk < d.ck);
+                        for (int tp = 1; tp < SRC_CACHE; ++tp) rp[i] = (tp == tap) ? rowp[tp][i] : rp[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int src = pp[i] >= 0 ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + pp[i]) : -1;
+                        rp[i] = src >= 0 ? in_n[i] + (int64_t)d.tap_in_ch[tap] * d.p_in + src : nullptr;
+                    }
+                }
+                const bool all = rp[0] && rp[1] && rp[2] && rp[3] && ch0 + 3 < d.ck;
+                if (all) {                                            // common case: no predication at all
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned off = (unsigned)(ch0 + j) * (unsigned)d.p_in;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[4 * i + j] = ldg_nc(rp[i] + off);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned off = (unsigned)(ch0 + j) * (unsigned)d.p_in;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[4 * i + j] = ldg_pred(rp[i] + off, rp[i] != nullptr && ch0 + j < d.ck);
+                    }
+                }
             };
-            auto stage_out = [&](int it, float (&v)[FW_KH]) {
+            auto stage_out = [&](int it, float (&v)[16]) {
                 const int k = kit + it, s = k % S;
                 const uint32_t ph = (uint32_t)(k / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);                   // slot free (first lap passes immediately)
-                const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + kh * (FW_KH / 4) * A_LBO + row * 16;
+                const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + chunk * A_LBO + q * 16;
 #pragma unroll
-                for (int c = 0; c < FW_KH / 4; ++c)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * A_LBO), "r"(to_tf32(v[4 * c])),
-                                 "r"(to_tf32(v[4 * c + 1])), "r"(to_tf32(v[4 * c + 2])), "r"(to_tf32(v[4 * c + 3]))
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + i * 32 * 16), "r"(to_tf32_fast(v[4 * i])),
+                                 "r"(to_tf32_fast(v[4 * i + 1])), "r"(to_tf32_fast(v[4 * i + 2])), "r"(to_tf32_fast(v[4 * i + 3]))
                                  : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-                mbar_arrive(full0 + 8 * s);
+                mbar_arrive(full0 + 8 * s);                           // release; the MMA thread runs the proxy fence (see there)
             };
             // FW_PF stages of gathers are always in flight: issue(it + PF) follows stage_out(it) on the same registers
-            float v0[FW_KH], v1[FW_KH], v2[FW_KH];
-            static_assert(FW_PF == 3, "register ring below is written for PF = 3");
+            float v0[16], v1[16], v2[16];
+            static_assert(FW_PF == 3 && UK == 32 && FW_PRODUCER_WARPS == 8, "producer mapping below assumes 8 chunk-warps, PF = 3");
             if (0 < kiters) issue(0, v0);
             if (1 < kiters) issue(1, v1);
             if (2 < kiters) issue(2, v2);
@@ -217,7 +279,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
                 for (int it = 0; it < kiters; ++it) {
                     const int k = kit + it, s = k % S;
                     const uint32_t ph = (uint32_t)(k / S) & 1u;
-                    mbar_wait(full0 + 8 * s, ph);
+                    mbar_wait(full0 + 8 * s, ph);                     // acquire: the producers' st.shared are visible to this thread
+                    // generic-proxy writes (observed through the barrier) -> async proxy (tcgen05.mma operand reads).  The fence
+                    // sits on the consumer side: a producer-side fence would also wait for that thread's in-flight gathers of
+                    // the following stages and serialise the pipeline.
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
@@ -254,47 +320,29 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane = position row; 32 columns per step, residual loads issued before the TMEM wait =====
+        // ===== epilogue warps: TMEM lane = position row; 32 columns per step =====
         const int quarter = warp & 3;                                 // warps 10..13 -> TMEM lane quarters 2,3,0,1
         const int row = quarter * 32 + lane;
         int ti = 0;
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
             const TileCoord tc = tile_coord(tile, pl);
             const int buf = ti & 1;
-            const int64_t pos = (int64_t)tc.mt * UM + row;
-            const bool valid = pos < total_pos;
-            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+            const uint32_t pos = (uint32_t)tc.mt * UM + row;          // make_plan guarantees total_pos < 2^31
+            const bool valid = pos < (uint32_t)total_pos;
+            const uint32_t nn = valid ? pos / (uint32_t)d.p_out : 0u, p = valid ? pos - nn * (uint32_t)d.p_out : 0u;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
-            const int64_t obase = ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
-            const int64_t abase = d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0) * d.add_period + p % d.add_period : obase;
+            float* op = out + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * d.p_out + p;
             const int64_t astride = d.add_period ? d.add_period : d.p_out;
+            const float* ap = add ? add + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? p % (uint32_t)d.add_period : p)
+                                  : nullptr;
+            const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
             mbar_wait(tfull0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
-            for (int col0 = 0; col0 < pl.n_cta; col0 += 32) {
-                if (oc_base + col0 >= d.co) break;                    // warp-uniform
-                float av[32];
-                if (add) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) av[j] = ldg_pred(add + abase + (int64_t)(oc_base + col0 + j) * astride, valid && oc_base + col0 + j < d.co);
-                }
-                uint32_t r0[16], r1[16];
-                tmem_ld16_nowait(taddr + col0, r0);
-                if (col0 + 16 < pl.n_cta) tmem_ld16_nowait(taddr + col0 + 16, r1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int oc = oc_base + col0 + j;
-                        if (oc < d.co && col0 + j < pl.n_cta) {
-                            float val = __uint_as_float(j < 16 ? r0[j & 15] : r1[j & 15]);
-                            if (bias) val += __ldg(bias + out_ch0 + oc);
-                            if (add) val += av[j];
-                            out[obase + (int64_t)oc * d.p_out] = apply_act(val, d.act);
-                        }
-                    }
-                }
-            }
+            const int ncols = min(pl.n_cta, d.co - oc_base);          // columns of this tile that exist
+            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
+            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
+            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);                           // accumulator may be overwritten
         }

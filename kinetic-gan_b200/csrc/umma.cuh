@@ -59,6 +59,15 @@ __device__ __forceinline__ float ldg_pred(const float* ptr, bool pred) {
         : "l"(ptr), "r"((int)pred));
     return v;
 }
+// unpredicated read-only load as volatile asm (same ordering guarantee as ldg_pred)
+__device__ __forceinline__ float ldg_nc(const float* ptr) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+    return v;
+}
+// fp32 -> tf32 with round-to-nearest, ties away from zero (== cvt.rna.tf32.f32 for finite inputs) in two integer ops:
+// add half an ulp of the 10-bit mantissa to the magnitude bits, clear the 13 dropped bits
+__device__ __forceinline__ uint32_t to_tf32_fast(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
