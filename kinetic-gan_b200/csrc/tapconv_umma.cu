@@ -14,7 +14,7 @@
 //   warps 0-7   activation producers: thread = (row, k-half); PF stages of gathers in flight per thread
 //   warp  8     MMA issuer (one thread) + TMEM owner; accumulators are double-buffered in TMEM (2 x n_cta columns)
 //   warp  9     weight loader (one thread, bulk copies)
-//   warps 10-13 epilogue: drain accumulator b of tile i (TMEM -> bias/add/act -> global) while tile i+1 is computed
+//   warps 10-17 epilogue: drain accumulator b of tile i (TMEM -> bias/add/act -> global) while tile i+1 is computed
 //   smem ring full[S]/empty[S] (producers+loader <-> MMA), tmem_full[2]/tmem_empty[2] (MMA <-> epilogue).
 // The layer is HBM/L2-bound at tensor-core rates (AI ~ 0.75*C_out flop/B unfused): what matters is bytes in flight.
 #include "umma.cuh"
@@ -23,9 +23,10 @@ namespace kgan {
 
 constexpr int FW_PRODUCER_WARPS = 8;
 constexpr int FW_MMA_WARP = 8, FW_LOAD_WARP = 9, FW_EPI_WARP0 = 10;
-constexpr int FW_THREADS = 32 * 14;
+constexpr int FW_EPI_WARPS = 8;                // two warps per TMEM lane quarter, alternating 16-column steps
+constexpr int FW_THREADS = 32 * (10 + FW_EPI_WARPS);
 constexpr int FW_KH = UK / 2;                  // channels per producer thread per stage
-constexpr int FW_PF = 3;                       // stages of gathers in flight per producer thread
+constexpr int FW_PF = 2;                       // stages of gathers in flight per producer thread
 
 struct UmmaPlan {
     int n_cta;        // output channels per tile (UMMA N, multiple of 16, <= 256)
@@ -105,9 +106,9 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const UmmaPlan& pl) {
 // residual values are requested before the TMEM wait, the bias chunk is loaded once per step (lane j holds channel j)
 // and broadcast by shuffle, the activation is a template parameter, addresses advance by one plane per channel.
 template <int ACT>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int ncols, int n_cta, bool valid, float* __restrict__ op, int p_out,
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                               const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane) {
-    for (int col0 = 0; col0 < ncols; col0 += 16) {
+    for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (FW_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
         float av[16];
         if (ap) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8 * b, 1);                            // tcgen05.commit after the last MMA of a tile
-            mbar_init(tempty0 + 8 * b, 128);                         // epilogue threads
+            mbar_init(tempty0 + 8 * b, 32 * FW_EPI_WARPS);           // epilogue threads
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -246,21 +247,16 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
                 mbar_arrive(full0 + 8 * s);                           // release; the MMA thread runs the proxy fence (see there)
             };
             // FW_PF stages of gathers are always in flight: issue(it + PF) follows stage_out(it) on the same registers
-            float v0[16], v1[16], v2[16];
-            static_assert(FW_PF == 3 && UK == 32 && FW_PRODUCER_WARPS == 8, "producer mapping below assumes 8 chunk-warps, PF = 3");
+            float v0[16], v1[16];
+            static_assert(FW_PF == 2 && UK == 32 && FW_PRODUCER_WARPS == 8, "producer mapping below assumes 8 chunk-warps, PF = 2");
             if (0 < kiters) issue(0, v0);
             if (1 < kiters) issue(1, v1);
-            if (2 < kiters) issue(2, v2);
-            for (int it = 0; it < kiters; it += 3) {
+            for (int it = 0; it < kiters; it += 2) {
                 stage_out(it, v0);
-                if (it + 3 < kiters) issue(it + 3, v0);
+                if (it + 2 < kiters) issue(it + 2, v0);
                 if (it + 1 < kiters) {
                     stage_out(it + 1, v1);
-                    if (it + 4 < kiters) issue(it + 4, v1);
-                }
-                if (it + 2 < kiters) {
-                    stage_out(it + 2, v2);
-                    if (it + 5 < kiters) issue(it + 5, v2);
+                    if (it + 3 < kiters) issue(it + 3, v1);
                 }
             }
             kit += kiters;
@@ -321,7 +317,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
         }
     } else {
         // ===== epilogue warps: TMEM lane = position row; 32 columns per step =====
-        const int quarter = warp & 3;                                 // warps 10..13 -> TMEM lane quarters 2,3,0,1
+        const int quarter = warp & 3;                                 // warps 10..17 -> TMEM lane quarters 2,3,0,1,2,3,0,1
+        const int colpar = (warp - FW_EPI_WARP0) >> 2;                // which of the alternating 16-column steps
         const int row = quarter * 32 + lane;
         int ti = 0;
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
@@ -340,9 +337,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);          // columns of this tile that exist
-            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
-            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
-            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, pl.n_cta, valid, op, d.p_out, ap, astride, bp, lane);
+            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);                           // accumulator may be overwritten
         }

@@ -29,7 +29,7 @@ struct WgradPlan {
 static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
     if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0 || d.ntap > 8) return false;
     const int64_t total = (int64_t)d.n * d.p_out;
-    if (total < 1024) return false;
+    if (total < 1024 || total >= (1ll << 31) - UK) return false;
     int n_max = (512 / d.ntap) / 16 * 16;
     if (n_max > 256) n_max = 256;
     if (d.ntap >= 3 && n_max > 128) n_max = 128;
@@ -95,40 +95,53 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
 
     if (warp < WG_PRODUCER_WARPS) {
         // ===== producers: lane = position inside the K tile; warp w stages rows w, w+8, ... of every image =====
+        // lean inner loops: one row pointer advanced by 8 planes per load, immediate shared-memory offsets, predicates only
+        // on ragged tiles; every gather of a batch is issued before the first conversion
         const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
-        const uint32_t koff = (uint32_t)(lane >> 2), kel = (uint32_t)(lane & 3) * 4;      // k-chunk and byte offset inside it
-        const int units = 1 + d.ntap * pl.b_units;                                       // unit 0 = gout, then taps
+        const uint32_t kbyte = (uint32_t)(lane >> 2) * 0u + (uint32_t)(lane & 3) * 4;     // byte offset inside the 16-byte k-chunk
+        const uint32_t kchunk = (uint32_t)(lane >> 2);
+        const bool a_full = oc0 + UM <= d.co, b_full = ic0 + pl.n_ic <= d.ck && (pl.n_ic & 127) == 0;
+        const int64_t a_step = (int64_t)WG_PRODUCER_WARPS * d.p_out, b_step = (int64_t)WG_PRODUCER_WARPS * d.p_in;
         for (int it = 0; it < iters; ++it) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)(it / S) & 1u;
-            const int64_t pos = pbeg + (int64_t)it * UK + lane;
-            const bool valid = pos < pend;
-            const int nn = valid ? (int)(pos / d.p_out) : 0, p = valid ? (int)(pos % d.p_out) : 0;
+            const uint32_t pos = (uint32_t)(pbeg + (int64_t)it * UK) + lane;             // total_pos < 2^31 (plan)
+            const bool valid = pos < (uint32_t)pend;
+            const uint32_t nn = valid ? pos / (uint32_t)d.p_out : 0u, p = valid ? pos - nn * (uint32_t)d.p_out : 0u;
             const uint32_t st_a = smem_u32(smem + (size_t)s * stage_bytes);
-            const float* gb = gout + ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
-            const float* xn = in + ((int64_t)nn * d.c_in_total + in_ch0) * d.p_in;
+            // batches of 16 rows per warp: batch 0 = gout (A), then (tap, half) input batches (B); the gathers of up to four
+            // batches (64 per thread) are issued back to back before anything is converted or stored
+            const int nbatch = 1 + d.ntap * pl.b_units;
             bool waited = false;
-            for (int u0 = 0; u0 < units; u0 += 4) {
+            for (int b0 = 0; b0 < nbatch; b0 += 4) {
                 float v[4][WG_UNIT];
-                // issue every gather of up to 4 units back to back (64 loads in flight per thread) ...
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int u = u0 + q;
-                    if (u >= units) break;
-                    if (u == 0) {
+                for (int qb = 0; qb < 4; ++qb) {
+                    const int bi = b0 + qb;
+                    if (bi >= nbatch) break;
+                    if (bi == 0) {
+                        const float* gp = gout + ((int64_t)nn * d.c_out_total + out_ch0 + warp) * d.p_out + p;
+                        if (valid && a_full) {
 #pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j) {
-                            const int r = warp + WG_PRODUCER_WARPS * j;
-                            v[q][j] = ldg_pred(gb + (int64_t)r * d.p_out, valid && oc0 + r < d.co);
+                            for (int j = 0; j < WG_UNIT; ++j, gp += a_step) v[qb][j] = ldg_nc(gp);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < WG_UNIT; ++j, gp += a_step) v[qb][j] = ldg_pred(gp, valid && oc0 + warp + WG_PRODUCER_WARPS * j < d.co);
                         }
                     } else {
-                        const int tap = (u - 1) / pl.b_units, half = (u - 1) % pl.b_units;
+                        const int tap = (bi - 1) / pl.b_units, half = (bi - 1) - tap * pl.b_units;
                         const int src = valid ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p) : -1;
-                        const float* xb = xn + (int64_t)d.tap_in_ch[tap] * d.p_in + src;
+                        const int r0 = warp + WG_PRODUCER_WARPS * WG_UNIT * half;
+                        const float* xp = in + ((int64_t)nn * d.c_in_total + in_ch0 + d.tap_in_ch[tap] + r0) * d.p_in + src;
+                        if (src >= 0 && b_full) {
 #pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j) {
-                            const int r = warp + WG_PRODUCER_WARPS * (j + WG_UNIT * half);
-                            v[q][j] = ldg_pred(xb + (int64_t)r * d.p_in, src >= 0 && r < pl.n_ic && ic0 + r < d.ck);
+                            for (int j = 0; j < WG_UNIT; ++j, xp += b_step) v[qb][j] = ldg_nc(xp);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < WG_UNIT; ++j, xp += b_step) {
+                                const int r = r0 + WG_PRODUCER_WARPS * j;
+                                v[qb][j] = ldg_pred(xp, src >= 0 && r < pl.n_ic && ic0 + r < d.ck);
+                            }
                         }
                     }
                 }
@@ -136,26 +149,23 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     waited = true;
                 }
-                // ... then round to tf32 and scatter into the K-major images
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int u = u0 + q;
-                    if (u >= units) break;
-                    if (u == 0) {
-                        const uint32_t dst = st_a + koff * a_lbo + kel;
+                for (int qb = 0; qb < 4; ++qb) {
+                    const int bi = b0 + qb;
+                    if (bi >= nbatch) break;
+                    if (bi == 0) {
+                        const uint32_t dst = st_a + kchunk * a_lbo + kbyte + warp * 16;
 #pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j) {
-                            const int r = warp + WG_PRODUCER_WARPS * j;
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[q][j])) : "memory");
-                        }
+                        for (int j = 0; j < WG_UNIT; ++j)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + j * (WG_PRODUCER_WARPS * 16)), "r"(to_tf32_fast(v[qb][j])) : "memory");
                     } else {
-                        const int tap = (u - 1) / pl.b_units, half = (u - 1) % pl.b_units;
-                        const uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + koff * b_lbo + kel;
+                        const int tap = (bi - 1) / pl.b_units, half = (bi - 1) - tap * pl.b_units;
+                        const int r0 = warp + WG_PRODUCER_WARPS * WG_UNIT * half;
+                        const uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + kchunk * b_lbo + kbyte + r0 * 16;
 #pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j) {
-                            const int r = warp + WG_PRODUCER_WARPS * (j + WG_UNIT * half);
-                            if (r < pl.n_ic) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + r * 16), "r"(to_tf32(v[q][j])) : "memory");
-                        }
+                        for (int j = 0; j < WG_UNIT; ++j)
+                            if (b_full || r0 + WG_PRODUCER_WARPS * j < pl.n_ic)
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + j * (WG_PRODUCER_WARPS * 16)), "r"(to_tf32_fast(v[qb][j])) : "memory");
                     }
                 }
             }
