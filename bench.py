@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
-    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -41,7 +41,7 @@ struct UmmaPlan {
 };
 
 static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
-    if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0) return false;
+    if (d.w_oc_blk != 0) return false;                      // any channel count: ragged K and N are zero padded
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 256 || total >= (1ll << 31) - UM) return false;
     const int64_t m_tiles = ceil_div64(total, UM);

@@ -27,7 +27,7 @@ struct WgradPlan {
 };
 
 static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
-    if (d.ck < 16 || d.co < 16 || d.w_oc_blk != 0 || d.ntap > 8) return false;
+    if (d.w_oc_blk != 0 || d.ntap > 8) return false;        // any channel count: ragged M and N are zero padded
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 1024 || total >= (1ll << 31) - UK) return false;
     int n_max = (512 / d.ntap) / 16 * 16;

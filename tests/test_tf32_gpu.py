@@ -40,6 +40,8 @@ GEOMS = {
     "ragged_k": (dict(c_in=50, c_out=24, t_in=9, v_in=7, kt=3, pad=1), 21),
     "mlp_632": (dict(c_in=632, c_out=632, t_in=1, v_in=1), 300),
     "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64),
+    "d0_gcn_3ch": (dict(c_in=3, c_out=32, t_in=64, v_in=25, K=3, w_cin=123, w_ic0=120), 4),
+    "g6_tcn_3ch": (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 4),
 }
 
 
@@ -48,7 +50,7 @@ def test_tapconv_tf32(name):
     kw, n = GEOMS[name]
     geom = G.TapConvGeom(**kw)
     x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
-    w = rnd(geom.K * geom.c_out, geom.c_in, geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
+    w = rnd(geom.K * geom.c_out, kw.get("w_cin", geom.c_in), geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
     bias = rnd(geom.c_out, seed=3)
     add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)
     go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
