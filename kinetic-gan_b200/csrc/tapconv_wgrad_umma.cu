@@ -42,12 +42,14 @@ static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
     p.b_bytes = 8 * (p.n_ic + 1) * 16;
     p.b_units = ceil_div(p.n_ic, WG_PRODUCER_WARPS * WG_UNIT);
     const int stage = p.a_bytes + d.ntap * p.b_bytes;
-    p.stages = (200 * 1024) / stage;
+    // thin layers (<= 256 TMEM columns, small stages) run two CTAs per SM: the kernel is gather-latency bound there
+    const int per_sm = (p.tmem_cols <= 256 && 2 * stage <= 100 * 1024) ? 2 : 1;
+    p.stages = ((per_sm == 2 ? 100 : 200) * 1024) / stage;
     if (p.stages > 4) p.stages = 4;
     if (p.stages < 2) return false;
     const int64_t ktiles = ceil_div64(total, UK);
     const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
-    int64_t nchunks = ceil_div64(2 * kNumSMs, tiles);
+    int64_t nchunks = ((int64_t)per_sm * kNumSMs) / tiles;        // floor: the grid must fit in ONE wave (no tail CTAs)
     if (nchunks > ktiles / 4) nchunks = ktiles / 4;
     if (nchunks < 1) nchunks = 1;
     p.chunk = ceil_div64(ktiles, nchunks) * UK;
@@ -179,16 +181,60 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int oc = oc0 + quarter * 32 + lane;
         float* wb = dw + (int64_t)g * d.g_w + (int64_t)oc * d.w_oc;
-        for (int tap = 0; tap < d.ntap; ++tap) {
+        // 16-byte vector reductions (REDG.ADD.F32x4) wherever 4 consecutive results are contiguous in dW:
+        //   w_ic == 1          (graph conv / 1x1 / linear weights): 16 input channels of one tap are contiguous
+        //   taps innermost     (temporal conv weights (C_out, C_in, 3, 1)): the 3 taps x 16 channels interleave to 48 floats
+        bool taps_inner = d.ntap == 3 && d.w_ic == 3;
+        for (int tp = 0; tp < d.ntap; ++tp) taps_inner = taps_inner && d.tap_w_off[tp] == d.tap_w_off[0] + tp;
+        if (taps_inner) {
             for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
                 if (ic0 + col0 >= d.ck) break;                       // warp-uniform
-                uint32_t r[16];
-                tmem_ld16(taddr + tap * pl.n_ic + col0, r);
+                uint32_t r[3][16];
+                tmem_ld16_nowait(taddr + col0, r[0]);
+                tmem_ld16_nowait(taddr + pl.n_ic + col0, r[1]);
+                tmem_ld16_nowait(taddr + 2 * pl.n_ic + col0, r[2]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (oc < d.co) {
+                    float* dst = wb + d.tap_w_off[0] + (int64_t)(ic0 + col0) * 3;
+                    if (ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int ic = ic0 + col0 + j;
-                        if (ic < d.ck) atomicAdd(wb + d.tap_w_off[tap] + (int64_t)ic * d.w_ic, __uint_as_float(r[j]));
+                        for (int v4 = 0; v4 < 12; ++v4) {
+                            float4 q;
+                            q.x = __uint_as_float(r[(4 * v4 + 0) % 3][(4 * v4 + 0) / 3]);
+                            q.y = __uint_as_float(r[(4 * v4 + 1) % 3][(4 * v4 + 1) / 3]);
+                            q.z = __uint_as_float(r[(4 * v4 + 2) % 3][(4 * v4 + 2) / 3]);
+                            q.w = __uint_as_float(r[(4 * v4 + 3) % 3][(4 * v4 + 3) / 3]);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + v4, q);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ic0 + col0 + j < d.ck) {
+#pragma unroll
+                                for (int tp = 0; tp < 3; ++tp) atomicAdd(dst + j * 3 + tp, __uint_as_float(r[tp][j]));
+                            }
+                    }
+                }
+            }
+        } else {
+            for (int tap = 0; tap < d.ntap; ++tap) {
+                for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
+                    if (ic0 + col0 >= d.ck) break;                   // warp-uniform
+                    uint32_t r[16];
+                    tmem_ld16(taddr + tap * pl.n_ic + col0, r);
+                    if (oc < d.co) {
+                        float* dst = wb + d.tap_w_off[tap] + (int64_t)(ic0 + col0) * d.w_ic;
+                        if (d.w_ic == 1 && ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                            for (int v4 = 0; v4 < 4; ++v4)
+                                atomicAdd(reinterpret_cast<float4*>(dst) + v4,
+                                          make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]), __uint_as_float(r[4 * v4 + 2]),
+                                                      __uint_as_float(r[4 * v4 + 3])));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ic0 + col0 + j < d.ck) atomicAdd(dst + (int64_t)j * d.w_ic, __uint_as_float(r[j]));
+                        }
                     }
                 }
             }
