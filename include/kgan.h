@@ -55,6 +55,9 @@ typedef struct kgan_tapconv_desc {
     int32_t tap_in_ch[KGAN_MAX_TAPS];
     int64_t tap_w_off[KGAN_MAX_TAPS];
     int32_t tap_row[KGAN_MAX_TAPS];  /* row of pmap used by the tap */
+    int32_t pmap_vec_mask;     /* bit r set: pmap row r sends every aligned group of 4 output positions either to 4 consecutive,
+                                  16-byte aligned input positions or entirely to -1, and p_in, p_out are multiples of 4 (the
+                                  tensor-core weight-gradient kernel then stages 16 bytes per cp.async); 0 is always valid */
     int32_t add_period;        /* 0: `add` has the shape of out; else add is (N, c_out_total, add_period) and is read at
                                   p % add_period (a term that is constant over frames, broadcast along T) */
     int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */

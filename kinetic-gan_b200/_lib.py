@@ -20,7 +20,7 @@ class TapConvDesc(C.Structure):
         ("g_in", C.c_int32), ("g_out", C.c_int32), ("g_w", C.c_int64), ("w_oc", C.c_int64), ("w_ic", C.c_int64),
         ("w_oc_blk", C.c_int32), ("w_ocblk", C.c_int64),
         ("tap_in_ch", C.c_int32 * MAX_TAPS), ("tap_w_off", C.c_int64 * MAX_TAPS), ("tap_row", C.c_int32 * MAX_TAPS),
-        ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
+        ("pmap_vec_mask", C.c_int32), ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
     ]
 
 

@@ -1,18 +1,27 @@
 // Weight gradient of the tap convolution on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM):
 //     dW[tap][oc][ic] = sum_pos gout[oc, pos] * in[(tap, ic), pmap_tap(pos)]
 //   D[M = 128 output channels][N = n_ic input channels] per tap - the ntap accumulators sit side by side in TMEM;
-//   K = output positions.  Both operands are K-major in global memory already (positions are contiguous per channel),
-//   so producer lanes run along positions (coalesced 128-byte loads) and scatter 4-byte stores into the K-major
-//   core-matrix layout; a one-row pad per k-chunk (LBO = (rows+1)*16 B) makes those transposing stores bank-conflict
-//   free.  gout (A operand) is staged once per K tile and reused by all taps.  Split-K over CTAs, fp32 atomics into dW.
-// Warp roles: warps 0-7 producers (64 gathers in flight per thread) and epilogue, warp 8 MMA issuer / TMEM owner.
+//   K = output positions.  Both operands are K-major in global memory already (positions are contiguous per channel):
+//   a 16-byte chunk of 4 consecutive positions of one channel is exactly one k-chunk of one row of the canonical
+//   no-swizzle K-major core-matrix layout.  The producers therefore issue cp.async (LDGSTS) copies straight from global
+//   to shared memory - no registers, no waiting: up to S stages (the whole shared memory) of loads are in flight per
+//   SM, which is what this HBM/latency-bound kernel needs.  A one-row pad per k-chunk (LBO = (rows+1)*16 B) spreads
+//   the scattered 16-byte writes over the banks.  Taps whose position map is not 4-contiguous (joint / frame
+//   selection, odd temporal shifts) fall back to four 4-byte copies per chunk.  gout (A operand) is staged once per K
+//   tile and reused by all taps.  Split-K over one wave of CTAs; the epilogue adds into dW with 16-byte vector
+//   reductions (REDG.ADD.F32x4) where the weight layout allows.
+//   Operands reach the tensor core as raw fp32: kind::tf32 reads the upper 19 bits (truncation).  Truncating both
+//   operands biases every product by -7.06e-4 (measured; 2 x the mean truncation error of a 10-bit mantissa); the
+//   epilogue removes that bias, leaving the zero-mean part (~3e-4 rel-L2, same as round-to-nearest operands).
+// Warp roles: warps 0-7 cp.async producers, then epilogue; warp 8 MMA issuer / TMEM owner.
 #include "umma.cuh"
 
 namespace kgan {
 
 constexpr int WG_PRODUCER_WARPS = 8;
-constexpr int WG_THREADS = 32 * (WG_PRODUCER_WARPS + 1);
-constexpr int WG_UNIT = 16;                      // rows a warp loads per unit (= 128 rows of a 128-row image)
+constexpr int WG_PRODUCERS = 32 * WG_PRODUCER_WARPS;
+constexpr int WG_THREADS = WG_PRODUCERS + 32;
+constexpr float WG_TRUNC_FIX = 1.000706f;        // 1 / (1 - 7.06e-4): undoes the truncation bias of the two operands
 
 struct WgradPlan {
     int n_ic;         // input channels (UMMA N) per CTA, multiple of 16, <= 256
@@ -20,14 +29,14 @@ struct WgradPlan {
     int tmem_cols;
     int stages;
     int a_bytes, b_bytes;   // per stage: A image, one tap's B image
-    int b_units;      // 16-row units per warp per tap: ceil(n_ic / 128)
     int nchunks;
     int64_t chunk;    // positions per split-K chunk (multiple of UK)
     int smem_bytes;
 };
 
 static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
-    if (d.w_oc_blk != 0 || d.ntap > 8) return false;        // any channel count: ragged M and N are zero padded
+    if (d.w_oc_blk != 0 || d.ntap > 8) return false;         // any channel count: ragged M and N are zero filled
+    if ((d.p_out & 3) || (d.p_in & 3)) return false;           // 16-byte chunks must not straddle samples
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 1024 || total >= (1ll << 31) - UK) return false;
     int n_max = (512 / d.ntap) / 16 * 16;
@@ -40,16 +49,13 @@ static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
     while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
     p.a_bytes = 8 * (UM + 1) * 16;
     p.b_bytes = 8 * (p.n_ic + 1) * 16;
-    p.b_units = ceil_div(p.n_ic, WG_PRODUCER_WARPS * WG_UNIT);
     const int stage = p.a_bytes + d.ntap * p.b_bytes;
-    // thin layers (<= 256 TMEM columns, small stages) run two CTAs per SM: the kernel is gather-latency bound there
-    const int per_sm = (p.tmem_cols <= 256 && 2 * stage <= 100 * 1024) ? 2 : 1;
-    p.stages = ((per_sm == 2 ? 100 : 200) * 1024) / stage;
-    if (p.stages > 4) p.stages = 4;
+    p.stages = (200 * 1024) / stage;
+    if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return false;
     const int64_t ktiles = ceil_div64(total, UK);
     const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
-    int64_t nchunks = ((int64_t)per_sm * kNumSMs) / tiles;        // floor: the grid must fit in ONE wave (no tail CTAs)
+    int64_t nchunks = kNumSMs / tiles;                         // floor: the grid must fit in ONE wave (no tail CTAs)
     if (nchunks > ktiles / 4) nchunks = ktiles / 4;
     if (nchunks < 1) nchunks = 1;
     p.chunk = ceil_div64(ktiles, nchunks) * UK;
@@ -59,9 +65,17 @@ static bool make_wgrad_plan(const kgan_tapconv_desc& d, WgradPlan& p) {
     return true;
 }
 
-__global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradPlan pl,
-                                                                 const float* __restrict__ in, const float* __restrict__ gout,
-                                                                 const int32_t* __restrict__ pmap, float* __restrict__ dw) {
+// 16-byte (or 4-byte) asynchronous global -> shared copy; src_bytes = 0 zero-fills the destination without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradPlan pl,
+                                                                    const float* __restrict__ in, const float* __restrict__ gout,
+                                                                    const int32_t* __restrict__ pmap, float* __restrict__ dw) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = pl.stages;
@@ -79,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, 32 * WG_PRODUCER_WARPS);
+            mbar_init(full0 + 8 * s, WG_PRODUCERS);            // one (asynchronous) arrival per producer thread
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accfull, 1);
@@ -96,83 +110,52 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < WG_PRODUCER_WARPS) {
-        // ===== producers: lane = position inside the K tile; warp w stages rows w, w+8, ... of every image =====
-        // lean inner loops: one row pointer advanced by 8 planes per load, immediate shared-memory offsets, predicates only
-        // on ragged tiles; every gather of a batch is issued before the first conversion
+        // ===== producers: thread = (k-chunk of 4 positions, row slot); 8 consecutive lanes copy 128 contiguous bytes of a row =====
+        const int chunk = threadIdx.x & 7, rslot = threadIdx.x >> 3;      // rows rslot, rslot + 32, ...
         const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
-        const uint32_t kbyte = (uint32_t)(lane >> 2) * 0u + (uint32_t)(lane & 3) * 4;     // byte offset inside the 16-byte k-chunk
-        const uint32_t kchunk = (uint32_t)(lane >> 2);
-        const bool a_full = oc0 + UM <= d.co, b_full = ic0 + pl.n_ic <= d.ck && (pl.n_ic & 127) == 0;
-        const int64_t a_step = (int64_t)WG_PRODUCER_WARPS * d.p_out, b_step = (int64_t)WG_PRODUCER_WARPS * d.p_in;
+        const int a_rows = min(UM, d.co - oc0), b_rows = min(pl.n_ic, d.ck - ic0);   // rows that exist; the rest is zero filled
         for (int it = 0; it < iters; ++it) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)(it / S) & 1u;
-            const uint32_t pos = (uint32_t)(pbeg + (int64_t)it * UK) + lane;             // total_pos < 2^31 (plan)
+            const uint32_t pos = (uint32_t)(pbeg + (int64_t)it * UK) + chunk * 4;        // total_pos < 2^31 (plan); p_out % 4 == 0
             const bool valid = pos < (uint32_t)pend;
             const uint32_t nn = valid ? pos / (uint32_t)d.p_out : 0u, p = valid ? pos - nn * (uint32_t)d.p_out : 0u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
             const uint32_t st_a = smem_u32(smem + (size_t)s * stage_bytes);
-            // batches of 16 rows per warp: batch 0 = gout (A), then (tap, half) input batches (B); the gathers of up to four
-            // batches (64 per thread) are issued back to back before anything is converted or stored
-            const int nbatch = 1 + d.ntap * pl.b_units;
-            bool waited = false;
-            for (int b0 = 0; b0 < nbatch; b0 += 4) {
-                float v[4][WG_UNIT];
+            {   // A: gout rows
+                const float* gp = gout + ((int64_t)nn * d.c_out_total + out_ch0 + rslot) * d.p_out + p;
+                uint32_t dst = st_a + chunk * a_lbo + rslot * 16;
 #pragma unroll
-                for (int qb = 0; qb < 4; ++qb) {
-                    const int bi = b0 + qb;
-                    if (bi >= nbatch) break;
-                    if (bi == 0) {
-                        const float* gp = gout + ((int64_t)nn * d.c_out_total + out_ch0 + warp) * d.p_out + p;
-                        if (valid && a_full) {
-#pragma unroll
-                            for (int j = 0; j < WG_UNIT; ++j, gp += a_step) v[qb][j] = ldg_nc(gp);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < WG_UNIT; ++j, gp += a_step) v[qb][j] = ldg_pred(gp, valid && oc0 + warp + WG_PRODUCER_WARPS * j < d.co);
-                        }
-                    } else {
-                        const int tap = (bi - 1) / pl.b_units, half = (bi - 1) - tap * pl.b_units;
-                        const int src = valid ? __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p) : -1;
-                        const int r0 = warp + WG_PRODUCER_WARPS * WG_UNIT * half;
-                        const float* xp = in + ((int64_t)nn * d.c_in_total + in_ch0 + d.tap_in_ch[tap] + r0) * d.p_in + src;
-                        if (src >= 0 && b_full) {
-#pragma unroll
-                            for (int j = 0; j < WG_UNIT; ++j, xp += b_step) v[qb][j] = ldg_nc(xp);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < WG_UNIT; ++j, xp += b_step) {
-                                const int r = r0 + WG_PRODUCER_WARPS * j;
-                                v[qb][j] = ldg_pred(xp, src >= 0 && r < pl.n_ic && ic0 + r < d.ck);
-                            }
-                        }
+                for (int i = 0; i < UM / 32; ++i, gp += (int64_t)32 * d.p_out, dst += 32 * 16) {
+                    const bool ok = valid && rslot + 32 * i < a_rows;
+                    cp_async16(dst, ok ? gp : gout, ok ? 16u : 0u);
+                }
+            }
+            for (int tap = 0; tap < d.ntap; ++tap) {     // B: input rows through the tap's position map
+                const int32_t* pm = pmap + (int64_t)d.tap_row[tap] * d.p_out + p;
+                const float* xb = in + ((int64_t)nn * d.c_in_total + in_ch0 + d.tap_in_ch[tap] + rslot) * d.p_in;
+                uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + chunk * b_lbo + rslot * 16;
+                if ((d.pmap_vec_mask >> d.tap_row[tap]) & 1) {
+                    const int src = valid ? __ldg(pm) : -1;
+                    for (int r = rslot; r < pl.n_ic; r += 32, xb += (int64_t)32 * d.p_in, dst += 32 * 16) {
+                        const bool ok = src >= 0 && r < b_rows;
+                        cp_async16(dst, ok ? xb + src : in, ok ? 16u : 0u);
                     }
-                }
-                if (!waited) {
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    waited = true;
-                }
+                } else {
+                    int src[4];
 #pragma unroll
-                for (int qb = 0; qb < 4; ++qb) {
-                    const int bi = b0 + qb;
-                    if (bi >= nbatch) break;
-                    if (bi == 0) {
-                        const uint32_t dst = st_a + kchunk * a_lbo + kbyte + warp * 16;
+                    for (int e = 0; e < 4; ++e) src[e] = valid ? __ldg(pm + e) : -1;
+                    for (int r = rslot; r < pl.n_ic; r += 32, xb += (int64_t)32 * d.p_in, dst += 32 * 16) {
 #pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j)
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + j * (WG_PRODUCER_WARPS * 16)), "r"(to_tf32_fast(v[qb][j])) : "memory");
-                    } else {
-                        const int tap = (bi - 1) / pl.b_units, half = (bi - 1) - tap * pl.b_units;
-                        const int r0 = warp + WG_PRODUCER_WARPS * WG_UNIT * half;
-                        const uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + kchunk * b_lbo + kbyte + r0 * 16;
-#pragma unroll
-                        for (int j = 0; j < WG_UNIT; ++j)
-                            if (b_full || r0 + WG_PRODUCER_WARPS * j < pl.n_ic)
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + j * (WG_PRODUCER_WARPS * 16)), "r"(to_tf32_fast(v[qb][j])) : "memory");
+                        for (int e = 0; e < 4; ++e) {
+                            const bool ok = src[e] >= 0 && r < b_rows;
+                            cp_async4(dst + 4 * e, ok ? xb + src[e] : in, ok ? 4u : 0u);
+                        }
                     }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(full0 + 8 * s);
+            // arrives on full[s] when every copy issued by this thread so far has landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8 * s) : "memory");
         }
         // ===== epilogue: TMEM lane = output channel row (warp % 4 selects the lane quarter, warp / 4 the column half) =====
         mbar_wait(accfull, 0);
@@ -186,6 +169,7 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
         //   taps innermost     (temporal conv weights (C_out, C_in, 3, 1)): the 3 taps x 16 channels interleave to 48 floats
         bool taps_inner = d.ntap == 3 && d.w_ic == 3;
         for (int tp = 0; tp < d.ntap; ++tp) taps_inner = taps_inner && d.tap_w_off[tp] == d.tap_w_off[0] + tp;
+        auto fix = [](uint32_t bits) { return __uint_as_float(bits) * WG_TRUNC_FIX; };
         if (taps_inner) {
             for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
                 if (ic0 + col0 >= d.ck) break;                       // warp-uniform
@@ -200,10 +184,10 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
 #pragma unroll
                         for (int v4 = 0; v4 < 12; ++v4) {
                             float4 q;
-                            q.x = __uint_as_float(r[(4 * v4 + 0) % 3][(4 * v4 + 0) / 3]);
-                            q.y = __uint_as_float(r[(4 * v4 + 1) % 3][(4 * v4 + 1) / 3]);
-                            q.z = __uint_as_float(r[(4 * v4 + 2) % 3][(4 * v4 + 2) / 3]);
-                            q.w = __uint_as_float(r[(4 * v4 + 3) % 3][(4 * v4 + 3) / 3]);
+                            q.x = fix(r[(4 * v4 + 0) % 3][(4 * v4 + 0) / 3]);
+                            q.y = fix(r[(4 * v4 + 1) % 3][(4 * v4 + 1) / 3]);
+                            q.z = fix(r[(4 * v4 + 2) % 3][(4 * v4 + 2) / 3]);
+                            q.w = fix(r[(4 * v4 + 3) % 3][(4 * v4 + 3) / 3]);
                             atomicAdd(reinterpret_cast<float4*>(dst) + v4, q);
                         }
                     } else {
@@ -211,7 +195,7 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
                         for (int j = 0; j < 16; ++j)
                             if (ic0 + col0 + j < d.ck) {
 #pragma unroll
-                                for (int tp = 0; tp < 3; ++tp) atomicAdd(dst + j * 3 + tp, __uint_as_float(r[tp][j]));
+                                for (int tp = 0; tp < 3; ++tp) atomicAdd(dst + j * 3 + tp, fix(r[tp][j]));
                             }
                     }
                 }
@@ -228,12 +212,11 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
 #pragma unroll
                             for (int v4 = 0; v4 < 4; ++v4)
                                 atomicAdd(reinterpret_cast<float4*>(dst) + v4,
-                                          make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]), __uint_as_float(r[4 * v4 + 2]),
-                                                      __uint_as_float(r[4 * v4 + 3])));
+                                          make_float4(fix(r[4 * v4]), fix(r[4 * v4 + 1]), fix(r[4 * v4 + 2]), fix(r[4 * v4 + 3])));
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (ic0 + col0 + j < d.ck) atomicAdd(dst + (int64_t)j * d.w_ic, __uint_as_float(r[j]));
+                                if (ic0 + col0 + j < d.ck) atomicAdd(dst + (int64_t)j * d.w_ic, fix(r[j]));
                         }
                     }
                 }
@@ -247,7 +230,9 @@ __global__ void __launch_bounds__(WG_THREADS) tapconv_wgrad_umma(const __grid_co
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+                mbar_wait(full0 + 8 * s, ph);                  // acquire: every producer's copies for this stage have landed
+                // cp.async wrote through the generic proxy; tcgen05.mma reads operands through the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 for (int tap = 0; tap < d.ntap; ++tap) {
@@ -278,6 +263,10 @@ int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float*
                        cudaStream_t stream) {
     WgradPlan p;
     if (!make_wgrad_plan(d, p)) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(gout)) & 15) {
+        set_error("tapconv_wgrad_tf32: in / gout must be 16-byte aligned");
+        return 1;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(tapconv_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)

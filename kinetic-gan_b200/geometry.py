@@ -39,6 +39,20 @@ class TapDesc:
         assert self.pmap.dtype == np.int32 and self.pmap.shape[1] == self.p_out
         self._dev = _DeviceCache()
         self._structs = {}
+        self.pmap_vec_mask = self._vec_mask()
+
+    def _vec_mask(self):
+        """Rows of pmap whose aligned groups of 4 output positions map to 4 consecutive, aligned inputs (or all to -1)."""
+        if self.p_in % 4 or self.p_out % 4:
+            return 0
+        mask = 0
+        for r in range(min(self.pmap.shape[0], 31)):
+            q = self.pmap[r].reshape(-1, 4).astype(np.int64)
+            hole = (q < 0).all(1)
+            run = (q[:, 0] >= 0) & (q[:, 0] % 4 == 0) & (q == q[:, :1] + np.arange(4)).all(1)
+            if (hole | run).all():
+                mask |= 1 << r
+        return mask
 
     def pmap_on(self, device):
         return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
@@ -56,7 +70,7 @@ class TapDesc:
             s.w_oc, s.w_ic, s.w_oc_blk, s.w_ocblk = self.w_oc, self.w_ic, 0, 0
             for i in range(self.ntap):
                 s.tap_in_ch[i], s.tap_w_off[i], s.tap_row[i] = self.tap_in_ch[i], self.tap_w_off[i], self.tap_row[i]
-            s.add_period, s.act, s.precision = add_period, act, precision
+            s.pmap_vec_mask, s.add_period, s.act, s.precision = self.pmap_vec_mask, add_period, act, precision
             self._structs[key] = s
         return s
 
