@@ -89,16 +89,18 @@ __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kg
     }
 }
 
-// tile id -> (group, position tile, channel split); consecutive ids share the activation tile (L2 reuse)
+// tile id -> (position tile, group, channel split); consecutive ids share the activation tile, so the channel splits and
+// the groups of one position tile (data gradient of the graph conv: 3 groups re-read the same gout) hit in L2
 struct TileCoord {
     int g, mt, ns;
 };
 __device__ __forceinline__ TileCoord tile_coord(int tile, const UmmaPlan& pl) {
     TileCoord c;
-    c.ns = tile % pl.n_split;
-    const int r = tile / pl.n_split;
-    c.mt = r % pl.m_tiles;
-    c.g = r / pl.m_tiles;
+    const int per_mt = pl.num_tiles / pl.m_tiles;      // groups * n_split
+    c.mt = tile / per_mt;
+    const int r = tile - c.mt * per_mt;
+    c.g = r / pl.n_split;
+    c.ns = r - c.g * pl.n_split;
     return c;
 }
 

@@ -91,8 +91,11 @@ class WGANGPTrainer:
         self.fd.zero_grad()
         with torch.no_grad():           # G's graph is never used by the critic update (its grads are zeroed at :157)
             fake = self.G(z, labels, noises=noises)
-        real_validity = self.D(real, labels)
-        fake_validity = self.D(fake, labels)
+        # the critic has no BatchNorm: every sample is processed independently, so the real and the fake pass
+        # (kinetic-gan.py:146,148) run as ONE pass over the concatenated batch - same values, half the launches
+        n = real.size(0)
+        validity = self.D(torch.cat((real, fake), 0), torch.cat((labels, labels), 0))
+        real_validity, fake_validity = validity[:n], validity[n:]
         gp = compute_gradient_penalty(self.D, real, fake, labels, alpha)
         d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + self.lambda_gp * gp
         d_loss.backward()
