@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -197,7 +198,10 @@ def run_kgan(args):
 
     def step_e2e(i):
         h = host[i % POOL]
-        x = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        if graphs:                                # pinned host buffers are copied straight into the graphs' static inputs
+            x = h
+        else:
+            x = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
         d_loss, _, _ = tr.iteration(i, x["real"], x["labels"], x["z"], x["alpha"])
         return d_loss.item()                      # device -> host read of the step's result
 
@@ -215,6 +219,10 @@ def run_kgan(args):
         comm.all_reduce_max_(ms)
         return ms.item()
 
+    graphs = not args.no_graphs
+    if graphs:
+        r0 = resident[0]
+        tr.capture_graphs(r0["real"], r0["labels"], r0["z"], r0["alpha"])
     it = 0
     for _ in range(max(W, 3)):
         step_resident(it)
@@ -242,11 +250,13 @@ def run_kgan(args):
         e2e = {"value": B * comm.world_size * K / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     # roofline of the dominant kernel family, measured live with CUDA events around every launch of one more pass
+    tr.use_graphs = False                       # eager launches: CUDA events around every libkgan kernel
     prof = ops.profile_start()
     for i in range(it, it + 5):
         step_resident(i)
     torch.cuda.synchronize()
     fam = ops.profile_stop(prof)
+    tr.use_graphs = graphs
     it += 5
     tensor_peak, hbm_peak, peak_kind = peaks()
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
@@ -274,6 +284,7 @@ def run_kgan(args):
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size,
                        "parallelism": "dp%d" % comm.world_size, "n_critic": 5, "flop_per_sample": FLOP_PER_SAMPLE,
+                       "cuda_graphs": graphs,
                        "l2_policy": "per-step working set (activations of 4 critic passes at batch %d, >1 GB) exceeds the 126 MB L2; "
                                     "inputs rotate over a pool of %d batches" % (B, POOL)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

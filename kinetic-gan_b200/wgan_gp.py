@@ -81,13 +81,16 @@ class WGANGPTrainer:
             comm.broadcast_module(self.D)
         self.fg, self.fd = FlatParams(self.G), FlatParams(self.D)
         self.world = 1 if comm is None else comm.world_size
+        self._graphs = None
+        self.use_graphs = True      # set False to run eagerly even after capture_graphs() (per-kernel profiling)
 
     def _reduce(self, flat):
         if self.comm is not None and self.world > 1:
             self.comm.all_reduce_sum_(flat.grad)
 
-    def d_step(self, real, labels, z, alpha=None, noises=None):
-        """kinetic-gan.py:137-155."""
+    # ---- forward + backward halves (everything that can be captured into a CUDA graph) ----------------------------
+    def _d_grads(self, real, labels, z, alpha=None, noises=None):
+        """kinetic-gan.py:137-154: fills the critic's flat gradient buffer, returns (d_loss, gp)."""
         self.fd.zero_grad()
         with torch.no_grad():           # G's graph is never used by the critic update (its grads are zeroed at :157)
             fake = self.G(z, labels, noises=noises)
@@ -99,12 +102,10 @@ class WGANGPTrainer:
         gp = compute_gradient_penalty(self.D, real, fake, labels, alpha)
         d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + self.lambda_gp * gp
         d_loss.backward()
-        self._reduce(self.fd)
-        self.fd.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
         return d_loss.detach(), gp.detach()
 
-    def g_step(self, labels, z, noises=None):
-        """kinetic-gan.py:167-174; the critic's weight gradients are not needed (zeroed at :137 before use)."""
+    def _g_grads(self, labels, z, noises=None):
+        """kinetic-gan.py:167-173; the critic's weight gradients are not needed (zeroed at :137 before use)."""
         self.fg.zero_grad()
         for p in self.fd.params:
             p.requires_grad_(False)
@@ -115,9 +116,74 @@ class WGANGPTrainer:
         finally:
             for p in self.fd.params:
                 p.requires_grad_(True)
+        return g_loss.detach()
+
+    # ---- CUDA graphs: at the reference batch size the step is launch-bound ------------------
+    def capture_graphs(self, real, labels, z, alpha):
+        """Captures forward+backward of the critic step and of the generator step into two CUDA graphs fed from static
+        input buffers (shapes taken from the arguments).  The optimizer update and the DDP all-reduce stay outside the
+        graphs.  Afterwards `iteration()` copies its inputs into the static buffers and replays."""
+        if self._graphs is not None:
+            return
+        st = {k: torch.empty_like(v) for k, v in dict(real=real, labels=labels, z=z, alpha=alpha).items()}
+        for k, v in dict(real=real, labels=labels, z=z, alpha=alpha).items():
+            st[k].copy_(v)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # warm-up on a side stream: builds every cached table / descriptor / workspace
+            for _ in range(2):
+                self._d_grads(st["real"], st["labels"], st["z"], st["alpha"])
+                self._g_grads(st["labels"], st["z"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ops.invalidate_packed_weights()     # packing kernels must be part of the graphs: replays re-pack the current weights
+        gd, gg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        l0 = ops.launches
+        with torch.cuda.graph(gd):
+            d_out = self._d_grads(st["real"], st["labels"], st["z"], st["alpha"])
+        l1 = ops.launches
+        ops.invalidate_packed_weights()
+        with torch.cuda.graph(gg, pool=gd.pool()):
+            g_out = self._g_grads(st["labels"], st["z"])
+        l2 = ops.launches
+        ops.invalidate_packed_weights()
+        self._graphs = dict(static=st, d=gd, g=gg, d_out=d_out, g_out=g_out, d_launches=l1 - l0, g_launches=l2 - l1)
+
+    def d_step(self, real, labels, z, alpha=None, noises=None):
+        """kinetic-gan.py:137-155."""
+        g = self._graphs
+        if g is not None and self.use_graphs and noises is None:
+            st = g["static"]
+            if alpha is None:
+                alpha = torch.as_tensor(np.random.random(tuple(st["alpha"].shape)), dtype=torch.float32)
+            for k, v in (("real", real), ("labels", labels), ("z", z), ("alpha", alpha)):
+                if v is not st[k]:
+                    st[k].copy_(v, non_blocking=True)
+            g["d"].replay()
+            ops.launches += g["d_launches"]
+            d_loss, gp = g["d_out"]
+        else:
+            d_loss, gp = self._d_grads(real, labels, z, alpha, noises)
+        self._reduce(self.fd)
+        self.fd.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
+        return d_loss, gp
+
+    def g_step(self, labels, z, noises=None):
+        """kinetic-gan.py:167-174.  With CUDA graphs the (labels, z) of the preceding d_step are reused, as in the reference loop."""
+        g = self._graphs
+        if g is not None and self.use_graphs and noises is None:
+            st = g["static"]
+            for k, v in (("labels", labels), ("z", z)):
+                if v is not st[k]:
+                    st[k].copy_(v, non_blocking=True)
+            g["g"].replay()
+            ops.launches += g["g_launches"]
+            g_loss = g["g_out"]
+        else:
+            g_loss = self._g_grads(labels, z, noises)
         self._reduce(self.fg)
         self.fg.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
-        return g_loss.detach()
+        return g_loss
 
     def iteration(self, i, real, labels, z, alpha=None, noises_d=None, noises_g=None):
         d_loss, gp = self.d_step(real, labels, z, alpha, noises_d)
