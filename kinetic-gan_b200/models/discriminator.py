@@ -3,7 +3,7 @@ forward signatures and state_dict keys; the arithmetic runs on the libkgan sm_10
 
 Per block (discriminator.py:125-136)   lrelu( interp_T( downsample_s( tcn(gcn(x, A)) + res(x) ) ) )
 is evaluated as two fused launches plus the adjacency product:
-    xa  = adjmix(x, A)                                  kgan_adjmix_fwd
+    xa  = adjmix(x, A[:, :, keep])                      kgan_adjmix_fwd   (kept joints only: selection folded into A)
     g   = tapconv(xa, gcn.conv.weight)                  kgan_tapconv_fwd  (K channel-block taps)
     r   = tapconv(x, residual.weight) + residual.bias   kgan_tapconv_fwd  (only at kept frames / joints)
     out = lrelu(tapconv(g, tcn.weight) + tcn.bias + r)  kgan_tapconv_fwd  (3 temporal taps, only kept outputs)
@@ -98,33 +98,43 @@ class st_gcn(nn.Module):
             t_conv = (T + 2 * self._pad - (self._kt - 1) - 1) // self._stride + 1
             t_sel = nearest_src(t_conv, self.dw_t)
             v_keep = [int(v) for v in self.graph.map[self.lvl + 1][:, 1]] if self.dw_s else list(range(V))
-            tcn = TapConvGeom(co, co, T, V, kt=self._kt, pad=self._pad, stride=self._stride, t_sel=t_sel, v_keep=v_keep)
+            # joint selection commutes with everything between the graph conv's adjacency product and the block output
+            # (the temporal conv, bias, residual add and activation act per joint), so it is folded into the adjacency:
+            # the graph conv runs with A[:, :, keep] and only ever produces the kept joints
+            tcn = TapConvGeom(co, co, T, len(v_keep), kt=self._kt, pad=self._pad, stride=self._stride, t_sel=t_sel)
             res = None
             if self._res == "conv":
                 res = TapConvGeom(ci, co, T, V, kt=1, stride=self._stride, t_sel=t_sel, v_keep=v_keep)
             elif self._res == "identity" and (t_sel != list(range(T)) or len(v_keep) != V):
                 res = select_table(T, V, t_sel, v_keep)
-            p = self._plans[(T, V)] = (tcn, res)
+            keep = torch.tensor(v_keep, dtype=torch.long) if len(v_keep) != V else None
+            p = self._plans[(T, V)] = (tcn, res, keep)
         return p
 
     def forward(self, x, A, label_emb=None):
         """`label_emb` (optional, not in the reference): (N, n_cls) label embedding standing for the first n_cls input
         channels, which the reference materialises as constant planes (discriminator.py:57-60); x then holds only the
         data channels.  Only valid for a block without residual branch (the critic's first block)."""
-        tcn, res = self._plan(x.size(2), A.size(2))
+        tcn, res, keep = self._plan(x.size(2), A.size(2))
+        A_in = A
+        if keep is not None:
+            if keep.device != A.device:
+                keep = keep.to(A.device)
+                self._plans[(x.size(2), A.size(2))] = (tcn, res, keep)
+            A = A.index_select(2, keep)                    # (K, V, V_keep): dropped joints are never computed
         if label_emb is not None:
             assert self._res == "none"
-            g, A = self.gcn.forward_with_labels(x, A, label_emb)
-            return KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, None, tcn, KF.ACT_LRELU), A
+            g, _ = self.gcn.forward_with_labels(x, A, label_emb)
+            return KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, None, tcn, KF.ACT_LRELU), A_in
         if self._res == "none":
             r = None
         elif self._res == "identity":
             r = x if res is None else KF.PlaneSpmm.apply(x, res)
         else:
             r = KF.TapConvEp.apply(x, self.residual.weight, self.residual.bias, None, res, KF.ACT_NONE)
-        g, A = self.gcn(x, A)
+        g, _ = self.gcn(x, A)
         x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU)
-        return x, A
+        return x, A_in
 
     def downsample_s(self, tensor):
         """Kept for API parity (discriminator.py:139-142); the forward pass folds it into the conv's position map."""

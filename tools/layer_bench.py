@@ -44,17 +44,17 @@ def timeit(fn):
 
 
 LAYERS = [
-    ("D0.tcn", dict(c_in=32, c_out=32, t_in=64, v_in=25, kt=3, pad=1, v_keep=keep1)),
+    ("D0.tcn", dict(c_in=32, c_out=32, t_in=64, v_in=11, kt=3, pad=1)),          # joint selection folded into the adjacency
     ("D1.gcn", dict(c_in=32, c_out=64, t_in=64, v_in=11, K=3)),
     ("D1.tcn", dict(c_in=64, c_out=64, t_in=64, v_in=11, kt=3, pad=1)),
     ("D1.res", dict(c_in=32, c_out=64, t_in=64, v_in=11)),
-    ("D2.gcn", dict(c_in=64, c_out=128, t_in=64, v_in=11, K=3)),
-    ("D2.tcn", dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=keep2)),
+    ("D2.gcn", dict(c_in=64, c_out=128, t_in=64, v_in=5, K=3)),
+    ("D2.tcn", dict(c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, t_sel=list(range(0, 64, 2)))),
     ("D2.res", dict(c_in=64, c_out=128, t_in=64, v_in=11, t_sel=list(range(0, 64, 2)), v_keep=keep2)),
     ("D3.gcn", dict(c_in=128, c_out=256, t_in=32, v_in=5, K=3)),
     ("D3.tcn", dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2)))),
-    ("D4.gcn", dict(c_in=256, c_out=512, t_in=16, v_in=5, K=3)),
-    ("D4.tcn", dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4])),
+    ("D4.gcn", dict(c_in=256, c_out=512, t_in=16, v_in=1, K=3)),
+    ("D4.tcn", dict(c_in=512, c_out=512, t_in=16, v_in=1, kt=3, pad=1, t_sel=list(range(0, 16, 2)))),
     ("D5.gcn", dict(c_in=512, c_out=512, t_in=8, v_in=1, K=3)),
     ("D5.tcn", dict(c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, t_sel=[0, 2, 4, 6])),
 ]
@@ -72,12 +72,13 @@ for name, kw in LAYERS:
                    ("wgrad", lambda: ops.tapconv_wgrad(x, go, g.fwd, tuple(w.shape)))):
         us = timeit(fn)
         print("%-8s %-6s %9.1f %9.0f %9.1f" % (name, op, us, bytes_io / us / 1e3, flops / us / 1e6))
-for name, (c, t, v) in (("D0", (3, 64, 25)), ("D1", (32, 64, 11)), ("D2", (64, 64, 11)), ("D3", (128, 32, 5)), ("D4", (256, 16, 5)), ("D5", (512, 8, 1))):
+for name, (c, t, v, vo) in (("D0", (3, 64, 25, 11)), ("D1", (32, 64, 11, 11)), ("D2", (64, 64, 11, 5)), ("D3", (128, 32, 5, 5)),
+                            ("D4", (256, 16, 5, 1)), ("D5", (512, 8, 1, 1))):
     if a.only and a.only not in name:
         continue
     x = torch.randn(N, c, t, v, device=dev)
-    A = (torch.rand(3, v, v, device=dev) < 0.15).float() * torch.rand(3, v, v, device=dev) + torch.eye(v, device=dev)
-    gx = torch.randn(N, 3 * c, t, v, device=dev)
+    A = ((torch.rand(3, v, v, device=dev) < 0.15).float() * torch.rand(3, v, v, device=dev) + torch.eye(v, device=dev))[:, :, :vo].contiguous()
+    gx = torch.randn(N, 3 * c, t, vo, device=dev)
     bytes_io = 4.0 * (x.numel() + gx.numel())
     for op, fn in (("mix", lambda: ops.adjmix_fwd(x, A)), ("mix_dx", lambda: ops.adjmix_bwd_x(gx, A)), ("mix_dA", lambda: ops.adjmix_bwd_a(x, gx, 3))):
         us = timeit(fn)
