@@ -62,6 +62,13 @@ typedef struct kgan_tapconv_desc {
                                   p % add_period (a term that is constant over frames, broadcast along T) */
     int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */
     int32_t precision;         /* KGAN_PREC_*: informational (which entry point the caller intends to use) */
+    /* Shift form of the position maps, used by the TMA-fed tensor-core kernel (kgan_tapconv_fwd_tf32); the gather form
+     * above stays authoritative for every other entry point.
+     *   tma_mode 0: no shift form.
+     *   tma_mode 1: pmap[tap_row[t]][p] == p + tap_shift[t] when that lies in [0, p_in), else -1 (p_in may differ from p_out).
+     * The TMA kernel additionally needs p_in, p_out and every shift to be multiples of 4 (16-byte box origins). */
+    int32_t tma_mode;
+    int32_t tap_shift[KGAN_MAX_TAPS];
 } kgan_tapconv_desc;
 
 /* Version / diagnostics. */
@@ -95,6 +102,10 @@ int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d);
 int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream);
 int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
                           const float* bias, const float* add, float* out, void* stream);
+
+/* 1 if kgan_tapconv_fwd_tf32 will run the TMA-fed kernel for this descriptor (tma_mode != 0, plane size a multiple of 4,
+ * tensor-core eligible): activations then reach shared memory by cp.async.bulk.tensor instead of per-thread gathers. */
+int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d);
 
 /* Tensor-core path of kgan_tapconv_wgrad (tcgen05.mma kind::tf32, split-K over CTAs, fp32 atomics into dw).
  * kgan_tapconv_wgrad_tf32_ok(d) -> 1 if the shape is eligible (else use kgan_tapconv_wgrad). */

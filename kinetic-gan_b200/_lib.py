@@ -21,6 +21,7 @@ class TapConvDesc(C.Structure):
         ("w_oc_blk", C.c_int32), ("w_ocblk", C.c_int64),
         ("tap_in_ch", C.c_int32 * MAX_TAPS), ("tap_w_off", C.c_int64 * MAX_TAPS), ("tap_row", C.c_int32 * MAX_TAPS),
         ("pmap_vec_mask", C.c_int32), ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
+        ("tma_mode", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
     ]
 
 
@@ -33,6 +34,7 @@ _SIGS = {
     "kgan_tapconv_tf32_workspace": ([C.POINTER(TapConvDesc)], C.c_int64),
     "kgan_tapconv_pack_tf32": ([C.POINTER(TapConvDesc), _F, _F, _V], C.c_int),
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
+    "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
     "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),

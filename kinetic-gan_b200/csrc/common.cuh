@@ -49,6 +49,11 @@ int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cud
 int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias,
                      const float* add, float* out, cudaStream_t stream);   // -1: not eligible
 
+// TMA-fed variant (tapconv_tma.cu) for descriptors whose taps are pure position shifts (tma_mode != 0); -1: not eligible
+int tapconv_tma_eligible(const kgan_tapconv_desc& d);
+int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                    float* out, cudaStream_t stream);
+
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d);
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
                        cudaStream_t stream);   // -1: not eligible

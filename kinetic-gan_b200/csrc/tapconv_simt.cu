@@ -5,6 +5,8 @@
 // GEMM view: rows = flattened output positions (n, p), columns = output channels,
 // contraction = (tap, input channel).  Positions are contiguous in memory for a fixed channel (NCHW), so
 // lanes run along positions for every global load/store (coalesced 128 B segments).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kgan {
@@ -255,12 +257,22 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
                                      const float* bias, const float* add, float* out, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
+    static const bool no_tma = getenv("KGAN_NO_TMA") != nullptr;      // A/B switch for benchmarks: force the gather kernel
+    if (d->tma_mode != 0 && !no_tma) {
+        const int rt = tapconv_fwd_tma(*d, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+        if (rt != -1) return rt;
+    }
     int r = tapconv_fwd_tf32(*d, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_fwd_tf32: shape not eligible for the tensor-core path (kgan_tapconv_tf32_workspace() == 0)");
         return 1;
     }
     return r;
+}
+
+extern "C" int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d) {
+    if (validate(d)) return 0;
+    return tapconv_tf32_packed_numel(*d) > 0 && tapconv_tma_eligible(*d);
 }
 
 extern "C" int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d) {

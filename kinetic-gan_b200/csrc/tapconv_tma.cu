@@ -1,0 +1,334 @@
+// Tap convolution fed by the Tensor Memory Accelerator (KGAN_PREC_TF32, descriptors with tma_mode != 0).
+//
+// Same GEMM as tapconv_umma.cu -  D[M = 128 positions][N = output channels] += A[M][K] * B[N][K]^T,  K = (channel tile, tap) -
+// but the activation operand never touches a register: activations are NCHW, i.e. for a fixed channel the positions of a
+// plane are contiguous, which is exactly an "MN-major" UMMA operand.  A 3-D tensor map over (position, sample, channel)
+// lets one elected thread fetch a [32 channels] x [32 positions] box (4 KB, 128-byte rows, 32-byte swizzle atoms) per M group with a single
+// cp.async.bulk.tensor; four boxes make the 128 x 32 A tile of a pipeline stage.  A temporal tap is a shift of the
+// position coordinate by (tap - pad) * dilation * V; positions shifted outside the plane are zero-filled by the TMA unit,
+// which is the convolution's zero padding.  Small planes (P = 16, 8, 4) use boxes of p_box positions x n_box samples.
+// With 4-6 stages of 16 KB in flight per SM the kernel is bandwidth- instead of latency-bound (the SIMT-gather kernel
+// holds at most 32 KB of loads in registers, and measured 8-20 % of HBM peak with long-scoreboard stalls dominating).
+//
+// Raw fp32 activations reach the tensor core, which reads the upper 19 bits (truncation); the weights are pre-rounded
+// (round-to-nearest) by tapconv_pack_k.  Truncating one operand biases every product by -3.53e-4 (half of the two-operand
+// figure measured for the weight-gradient kernel); the epilogue removes that bias, leaving the zero-mean rounding noise
+// (~3e-4 rel-L2, same as round-to-nearest operands).
+//
+// The TMA unit requires the innermost (position) coordinate of a box to be a multiple of 16 bytes - an unaligned shift
+// raises an illegal-instruction fault - so only descriptors whose shifts are multiples of 4 positions are eligible.  The host
+// side arranges that: joints are padded to a multiple of 4 where that is cheap (11 -> 12), and temporally strided
+// convolutions read a time-unfolded copy of their input whose taps sit at block offsets (see geometry.py).
+//
+// Warp roles: warp 0 = producer (one thread: tensor loads + bulk copies of the packed weights), warp 1 = MMA issuer and
+// TMEM owner (accumulators double-buffered), warps 2-9 = epilogue (TMEM -> bias/add/act -> coalesced NCHW stores).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "umma.cuh"
+
+namespace kgan {
+
+constexpr int TM_EPI_WARPS = 8;
+constexpr int TM_EPI_WARP0 = 2;
+constexpr int TM_THREADS = 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);
+constexpr float TM_TRUNC_FIX = 1.000353f;      // 1 / (1 - 3.53e-4)
+constexpr int TM_GROUP_BYTES = 32 * 32 * 4;    // one box: 32 channel rows of 128 bytes
+
+struct TmaPlan {
+    int n_cta, n_split, n_rows, tmem_cols, nkt;   // identical to UmmaPlan (the packed weight image is shared)
+    int p_box, n_box, p_shift;                    // box = p_box positions x n_box samples; p_box = 1 << p_shift
+    int cps;                                      // position chunks per output plane: p_out / p_box
+    int64_t groups32;                             // 32-row M groups: ceil(n / n_box) * cps
+    int m_tiles, num_tiles, stages, smem_bytes;
+    int a_lbo, a_sbo;                             // A descriptor strides (bytes): between 32-position M groups / between 8-channel K groups
+};
+
+bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, int* n_rows, int* tmem_cols, int* nkt);
+
+static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
+    if (d.tma_mode != 1) return false;
+    if ((d.p_in & 3) || (d.p_out & 3)) return false;               // global strides / box origins must be multiples of 16 bytes
+    for (int t = 0; t < d.ntap; ++t)
+        if (d.tap_shift[t] & 3) return false;                      // unaligned box origin: the TMA unit faults
+    if (!tapconv_umma_nsplit(d, &p.n_cta, &p.n_split, &p.n_rows, &p.tmem_cols, &p.nkt)) return false;
+    p.p_shift = 5;
+    while (p.p_shift > 2 && (d.p_out & ((1 << p.p_shift) - 1))) --p.p_shift;
+    p.p_box = 1 << p.p_shift;
+    p.n_box = 32 / p.p_box;
+    p.cps = d.p_out / p.p_box;
+    p.groups32 = ceil_div64(d.n, p.n_box) * p.cps;
+    if (p.groups32 < 8 || p.groups32 >= (1ll << 28)) return false;
+    p.m_tiles = (int)ceil_div64(p.groups32, 4);
+    if ((int64_t)p.m_tiles * d.groups * p.n_split > (1 << 28)) return false;
+    p.num_tiles = p.m_tiles * p.n_split * d.groups;
+    const int stage = A_STAGE_BYTES + p.n_cta * UK * 4;
+    p.stages = (200 * 1024) / stage;
+    if (p.stages > 8) p.stages = 8;
+    p.smem_bytes = p.stages * stage + 1024 + 512;                  // + alignment slack + barriers
+    p.a_lbo = TM_GROUP_BYTES;
+    p.a_sbo = 512;
+    return true;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+// MN-major 32-bit operand: the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1) - 128-byte rows of
+// 32 consecutive M elements, 32-byte chunks XOR-swizzled with (row & 3), atoms of 4 K rows (512 bytes).  The TMA unit writes
+// exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = bytes between 32-element M groups, SBO = bytes between
+// 4-row K groups.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+
+struct TmaTile {
+    int g, mt, ns;
+};
+__device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
+    TmaTile c;
+    const int per_mt = pl.num_tiles / pl.m_tiles;      // groups * n_split: consecutive tiles re-use the activation tile in L2
+    c.mt = tile / per_mt;
+    const int r = tile - c.mt * per_mt;
+    c.g = r / pl.n_split;
+    c.ns = r - c.g * pl.n_split;
+    return c;
+}
+
+template <int ACT>
+__device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
+                                                  const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane) {
+    for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
+        const int nc = min(16, ncols - col0);                         // warp-uniform
+        float av[16];
+        if (ap) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) av[j] = ldg_pred(ap + (int64_t)(col0 + j) * astride, valid && j < nc);
+        }
+        const float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        uint32_t r[16];
+        tmem_ld16(taddr + col0, r);
+        float* o = op + (int64_t)col0 * p_out;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float val = fmaf(__uint_as_float(r[j]), TM_TRUNC_FIX, __shfl_sync(0xffffffffu, bl, j));
+            if (ap) val += av[j];
+            if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
+            if (ACT == KGAN_ACT_TANH) val = tanhf(val);
+            if (valid && j < nc) *o = val;
+            o += p_out;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
+                                                                    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
+                                                                    const float* __restrict__ bias,
+                                                                    const float* __restrict__ add, float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = pl.stages;
+    const int b_stage_bytes = pl.n_cta * UK * 4;
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + (size_t)S * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * b_stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+    const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
+    const int kiters = pl.nkt * d.ntap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);                             // the producer's arrive.expect_tx; the copies complete the bytes
+            mbar_init(empty0 + 8 * s, 1);                            // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull0 + 8 * b, 1);
+            mbar_init(tempty0 + 8 * b, 32 * TM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: tensor loads of the activation boxes + bulk copies of the packed weights =====
+        if (lane == 0) {
+            const uint32_t chunk_bytes = pl.n_cta * 16;
+            const uint32_t stage_tx = A_STAGE_BYTES + chunk_bytes * 8;
+            int kit = 0;
+            for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+                const TmaTile tc = tma_tile(tile, pl);
+                int cp[4], cn[4];                                     // box origin (position, sample) of the 4 M groups
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t G = (int64_t)tc.mt * 4 + i;
+                    const int nb = (int)(G / pl.cps);
+                    cp[i] = (int)(G - (int64_t)nb * pl.cps) << pl.p_shift;
+                    cn[i] = nb * pl.n_box;                            // >= n for the groups past the end: zero-filled
+                }
+                const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
+                const int oc_base = tc.ns * pl.n_cta;
+                const int ch_g = tc.g * d.g_in;
+                for (int it = 0; it < kiters; ++it) {
+                    const int k = kit + it, s = k % S;
+                    const uint32_t ph = (uint32_t)(k / S) & 1u;
+                    const int ict = it / d.ntap, tap = it - ict * d.ntap;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
+                    const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                    const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                    const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
+                    const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                    if (pl.n_split == 1) {
+                        bulk_g2s(b_dst, src, chunk_bytes * 8, full0 + 8 * s);       // the whole stage is contiguous in the image
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            bulk_g2s(b_dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                    }
+                }
+                kit += kiters;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (1u << 15);          // A operand MN-major
+            const uint32_t b_lbo = pl.n_cta * 16;
+            int kit = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * pl.n_cta;
+                for (int it = 0; it < kiters; ++it) {
+                    const int k = kit + it, s = k % S;
+                    const uint32_t ph = (uint32_t)(k / S) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);                     // both operands were written by the async proxy: no proxy fence
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
+#pragma unroll
+                    for (int j = 0; j < UK / 8; ++j)
+                        umma_tf32(acc, smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
+                                  smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);
+                }
+                umma_commit(tfull0 + 8 * buf);
+                kit += kiters;
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane = row of the tile = (M group, element of the box) =====
+        const int quarter = warp & 3;                                 // TMEM lane quarter this warp may read == M group of the tile
+        const int colpar = (warp - TM_EPI_WARP0) >> 2;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
+            const TmaTile tc = tma_tile(tile, pl);
+            const int buf = ti & 1;
+            const int64_t G = (int64_t)tc.mt * 4 + quarter;
+            const int nb = (int)(G / pl.cps);
+            const int nn = nb * pl.n_box + (lane >> pl.p_shift);
+            const int pv = ((int)(G - (int64_t)nb * pl.cps) << pl.p_shift) + (lane & (pl.p_box - 1));
+            const bool valid = G < pl.groups32 && nn < d.n;
+            const int po = valid ? pv : 0, nv = valid ? nn : 0;
+            const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
+            float* op = out + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * d.p_out + po;
+            const int64_t astride = d.add_period ? d.add_period : d.p_out;
+            const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? po % d.add_period : po)
+                                  : nullptr;
+            const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
+            mbar_wait(tfull0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
+            const int ncols = min(pl.n_cta, d.co - oc_base);
+            if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty0 + 8 * buf);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libkgan.so does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int tapconv_tma_eligible(const kgan_tapconv_desc& d) {
+    TmaPlan p;
+    return make_tma_plan(d, p) ? 1 : 0;
+}
+
+// -1: not eligible (caller falls back to the gather kernel)
+int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                    float* out, cudaStream_t stream) {
+    TmaPlan p;
+    if (!make_tma_plan(d, p)) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled not available");
+        return 1;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.p_in, (cuuint64_t)d.n, (cuuint64_t)d.c_in_total};
+    const cuuint64_t gstr[2] = {(cuuint64_t)d.c_in_total * d.p_in * 4, (cuuint64_t)d.p_in * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)p.p_box, (cuuint32_t)p.n_box, 32u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tapconv_fwd_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return check_launch("tapconv_fwd_tma attribute");
+        attr_set = true;
+    }
+    if (const char* v = getenv("KGAN_TMA_DESC_SWAP")) {            // bring-up switch: exchange the two descriptor strides
+        if (v[0] == '1') {
+            p.a_lbo = 512;
+            p.a_sbo = TM_GROUP_BYTES;
+        }
+    }
+    (void)pmap;                                                    // the shift form replaces the position map
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    tapconv_fwd_tma_k<<<grid, TM_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, bias, add, out);
+    return check_launch("tapconv_fwd_tma");
+}
+
+}  // namespace kgan

@@ -40,7 +40,9 @@ struct UmmaPlan {
     int smem_bytes;
 };
 
-static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
+// Channel tiling shared by every tensor-core forward kernel (this file and tapconv_tma.cu): it fixes the layout of the
+// packed weight image, so it depends on the descriptor only.
+bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, int* n_rows, int* tmem_cols, int* nkt) {
     if (d.w_oc_blk != 0) return false;                      // any channel count: ragged K and N are zero padded
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 256 || total >= (1ll << 31) - UM) return false;
@@ -49,12 +51,18 @@ static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
     const int n16 = round_up(d.co, 16);
     int split = ceil_div(n16, 256);
     while (m_tiles * d.groups * split < kNumSMs && ceil_div(n16, split * 2) >= 64) split *= 2;
-    p.n_cta = round_up(ceil_div(n16, split), 16);
-    p.n_split = ceil_div(n16, p.n_cta);
-    p.n_rows = p.n_cta * p.n_split;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * p.n_cta) p.tmem_cols *= 2;
-    p.nkt = ceil_div(d.ck, UK);
+    *n_cta = round_up(ceil_div(n16, split), 16);
+    *n_split = ceil_div(n16, *n_cta);
+    *n_rows = *n_cta * *n_split;
+    *tmem_cols = 32;
+    while (*tmem_cols < 2 * *n_cta) *tmem_cols *= 2;
+    *nkt = ceil_div(d.ck, UK);
+    return true;
+}
+
+static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
+    if (!tapconv_umma_nsplit(d, &p.n_cta, &p.n_split, &p.n_rows, &p.tmem_cols, &p.nkt)) return false;
+    const int64_t m_tiles = ceil_div64((int64_t)d.n * d.p_out, UM);
     p.m_tiles = (int)m_tiles;
     p.num_tiles = (int)m_tiles * p.n_split * d.groups;
     const int stage = A_STAGE_BYTES + p.n_cta * UK * 4;

@@ -40,6 +40,7 @@ class TapDesc:
         self._dev = _DeviceCache()
         self._structs = {}
         self.pmap_vec_mask = self._vec_mask()
+        self.tma_mode, self.tap_shift = self._shift_form()
 
     def _vec_mask(self):
         """Rows of pmap whose aligned groups of 4 output positions map to 4 consecutive, aligned inputs (or all to -1)."""
@@ -53,6 +54,23 @@ class TapDesc:
             if (hole | run).all():
                 mask |= 1 << r
         return mask
+
+    def _shift_form(self):
+        """tma_mode 1 (include/kgan.h): every tap reads input position p + shift (zero outside the input plane)."""
+        none = (0, [0] * self.ntap)
+        p = np.arange(self.p_out, dtype=np.int64)
+        shifts = []
+        for t in range(self.ntap):
+            row = self.pmap[self.tap_row[t]].astype(np.int64)
+            hit = np.nonzero(row >= 0)[0]
+            if len(hit) == 0:
+                return none
+            sh = int(row[hit[0]] - hit[0])
+            want = np.where((p + sh >= 0) & (p + sh < self.p_in), p + sh, -1)
+            if not (row == want).all():
+                return none
+            shifts.append(sh)
+        return 1, shifts
 
     def pmap_on(self, device):
         return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
@@ -71,6 +89,9 @@ class TapDesc:
             for i in range(self.ntap):
                 s.tap_in_ch[i], s.tap_w_off[i], s.tap_row[i] = self.tap_in_ch[i], self.tap_w_off[i], self.tap_row[i]
             s.pmap_vec_mask, s.add_period, s.act, s.precision = self.pmap_vec_mask, add_period, act, precision
+            s.tma_mode = self.tma_mode
+            for i in range(self.ntap):
+                s.tap_shift[i] = self.tap_shift[i]
             self._structs[key] = s
         return s
 
@@ -96,7 +117,7 @@ class TapConvGeom:
         assert t_conv >= 1, "temporal kernel larger than the padded input"
         self.t_sel = list(range(t_conv)) if t_sel is None else [int(t) for t in t_sel]
         self.v_keep = list(range(v_in)) if v_keep is None else [int(v) for v in v_keep]
-        assert all(0 <= t < t_conv for t in self.t_sel) and all(0 <= v < v_in for v in self.v_keep)
+        assert all(0 <= t < t_conv for t in self.t_sel) and all(-1 <= v < v_in for v in self.v_keep)   # -1: padded (dummy) joint, reads zero
         self.t_out, self.v_out = len(self.t_sel), len(self.v_keep)
         self.p_in, self.p_out = t_in * v_in, self.t_out * self.v_out
         self.w_numel = K * c_out * w_cin * kt
@@ -108,6 +129,8 @@ class TapConvGeom:
                 t = tau * stride + dt * dil - pad
                 if 0 <= t < t_in:
                     for b, v in enumerate(self.v_keep):
+                        if v < 0:
+                            continue
                         q, p = a * self.v_out + b, t * v_in + v
                         pmap[dt, q] = p
                         assert inv[dt, p] == -1, "position map must be injective per tap"
@@ -124,6 +147,47 @@ class TapConvGeom:
             groups=K, g_in=0, g_out=c_in, g_w=c_out * w_cin * kt, w_oc=kt, w_ic=w_cin * kt,
             tap_in_ch=[0] * kt, tap_w_off=[w_ic0 * kt + dt for dt in range(kt)], tap_row=list(range(kt)), pmap=inv, t_out=t_in,
             v_out=v_in)
+
+
+class UnfoldedTcnGeom:
+    """Temporal convolution with frame selection (stride / nearest-T resampling) over a TIME-UNFOLDED copy of its input.
+
+    The temporal conv of a down-sampling critic block (discriminator.py:99-105 followed by F.interpolate at :134) reads,
+    for output frame a and tap d, input frame t_sel[a]*stride + d*dil - pad.  `unfold` (a PlaneTable, applied with
+    kgan_plane_spmm) gathers exactly those frames into kt consecutive blocks of H = len(t_sel)*V positions - block d holds
+    the operand of tap d (zero rows where the tap falls into the temporal padding) - so that the convolution itself becomes
+    out[q] = sum_d W_d . u[d*H + q]: every tap is a pure position shift by a multiple of H.  With H a multiple of 4 this is
+    the form the TMA-fed tensor-core kernel accepts (tapconv_tma.cu); the unaligned shifts by V = 5 or 1 positions of the
+    direct formulation are not.  For stride 2 the unfolded copy is 1.5x the input.
+    Exposes the same attributes as TapConvGeom (.fwd / .dgrad descriptors) so the TapConv* Functions apply unchanged."""
+
+    def __init__(self, c_in, c_out, t_in, v_in, kt, pad, stride, dil, t_sel):
+        self.c_in, self.c_out, self.t_in, self.v_in, self.K, self.kt = c_in, c_out, t_in, v_in, 1, kt
+        self.t_sel = [int(t) for t in t_sel]
+        self.t_out, self.v_out = len(self.t_sel), v_in
+        H = self.t_out * v_in
+        self.p_in, self.p_out = kt * H, H
+        self.w_numel = c_out * c_in * kt
+        dense = np.zeros((kt * H, t_in * v_in))
+        for d in range(kt):
+            for a, tau in enumerate(self.t_sel):
+                t = tau * stride + d * dil - pad
+                if 0 <= t < t_in:
+                    dense[d * H + a * v_in + np.arange(v_in), t * v_in + np.arange(v_in)] = 1.0
+        self.unfold = PlaneTable(dense, kt * self.t_out, v_in, t_in, v_in)
+        q = np.arange(H, dtype=np.int32)
+        pmap = np.stack([q + d * H for d in range(kt)]).astype(np.int32)
+        inv = np.full((kt, kt * H), -1, np.int32)
+        for d in range(kt):
+            inv[d, d * H:(d + 1) * H] = q
+        self.fwd = TapDesc(
+            c_in_total=c_in, p_in=kt * H, c_out_total=c_out, p_out=H, ntap=kt, ck=c_in, co=c_out, groups=1, g_in=0, g_out=0, g_w=0,
+            w_oc=c_in * kt, w_ic=kt, tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=pmap,
+            t_out=self.t_out, v_out=v_in)
+        self.dgrad = TapDesc(
+            c_in_total=c_out, p_in=H, c_out_total=c_in, p_out=kt * H, ntap=kt, ck=c_out, co=c_in, groups=1, g_in=0, g_out=0, g_w=0,
+            w_oc=kt, w_ic=c_in * kt, tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=inv,
+            t_out=kt * self.t_out, v_out=v_in)
 
 
 class PlaneTable:
@@ -188,7 +252,8 @@ def select_table(t_in, v_in, t_sel, v_keep):
     dense = np.zeros((len(t_sel) * len(v_keep), t_in * v_in))
     for a, t in enumerate(t_sel):
         for b, v in enumerate(v_keep):
-            dense[a * len(v_keep) + b, t * v_in + v] = 1.0
+            if v >= 0:                                       # -1: padded (dummy) joint, stays zero
+                dense[a * len(v_keep) + b, t * v_in + v] = 1.0
     return PlaneTable(dense, len(t_sel), len(v_keep), t_in, v_in)
 
 

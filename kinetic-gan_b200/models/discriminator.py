@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as KF
-from ..geometry import TapConvGeom, mean_table, nearest_src, select_table
+from ..geometry import TapConvGeom, UnfoldedTcnGeom, mean_table, nearest_src, select_table
 from .init_gan.graph_h36m import Graph_h36m
 from .init_gan.graph_ntu import graph_ntu
 from .init_gan.tgcn import ConvTemporalGraphical
@@ -54,12 +54,13 @@ class Discriminator(nn.Module):
         N, C, T, V = x.size()
         c = self.label_emb(labels)                       # (N, n_cls); the (N, n_cls, T, V) planes are never built
         A = self.A
+        last = len(self.st_gcn_networks) - 1
         for i, (gcn, importance) in enumerate(zip(self.st_gcn_networks, self.edge_importance)):
             if i == 0 and gcn._res == "none":
-                x, _ = gcn(x, A[gcn.lvl] * importance, label_emb=c)      # label channels folded analytically (I3)
+                x, _ = gcn(x, A[gcn.lvl] * importance, label_emb=c, pad_joints=i < last)      # label channels folded analytically (I3)
             else:
                 x = KF.LabelConcat.apply(c, x) if i == 0 else x
-                x, _ = gcn(x, A[gcn.lvl] * importance)
+                x, _ = gcn(x, A[gcn.lvl] * importance, pad_joints=i < last)
         # global pooling + prediction (discriminator.py:68-72)
         key = (x.size(1), x.size(2), x.size(3))
         if key not in self._head:
@@ -68,6 +69,19 @@ class Discriminator(nn.Module):
         x = KF.PlaneSpmm.apply(x, pool)
         validity = KF.TapConvEp.apply(x, self.fcn.weight, self.fcn.bias, None, geom, KF.ACT_NONE)
         return validity.view(N, -1)
+
+
+# Layout policy of the tensor-core path (module-level switches so that benchmarks can A/B them).  The TMA-fed tap
+# convolution (csrc/tapconv_tma.cu) needs every tap to be a position shift by a multiple of 4:
+PAD_JOINTS = True          # inside the critic, carry round_up(V, 4) joints where that costs <= 15 % (11 -> 12): the dummy joint has
+                           # zero adjacency rows / columns, never reaches a real joint and is dropped by the next joint selection
+SELECT_THEN_CONV = True    # residual 1x1 conv of a down-sampling block: gather the kept frames / joints first, then a plain 1x1 conv
+UNFOLD_STRIDED_TCN = True  # temporal conv of a down-sampling block: time-unfold the kept frames' operands (geometry.UnfoldedTcnGeom)
+
+
+def _pad4(v):
+    vp = (v + 3) // 4 * 4
+    return vp if PAD_JOINTS and vp != v and vp <= 1.15 * v else v
 
 
 class st_gcn(nn.Module):
@@ -91,52 +105,76 @@ class st_gcn(nn.Module):
         self.l_relu = nn.LeakyReLU(0.2, inplace=True)
         self._plans = {}
 
-    def _plan(self, T, V):
-        p = self._plans.get((T, V))
+    def _plan(self, T, V, Vx, pad_out, device):
+        """Geometry of one call: T frames, V graph joints, Vx >= V joints carried by the input tensor (the extra ones are
+        dummies), output joints padded to a multiple of 4 when `pad_out` and cheap."""
+        key = (T, V, Vx, pad_out, str(device))
+        p = self._plans.get(key)
         if p is None:
             co, ci = self.tcn.out_channels, self.gcn.conv.in_channels
             t_conv = (T + 2 * self._pad - (self._kt - 1) - 1) // self._stride + 1
             t_sel = nearest_src(t_conv, self.dw_t)
-            v_keep = [int(v) for v in self.graph.map[self.lvl + 1][:, 1]] if self.dw_s else list(range(V))
             # joint selection commutes with everything between the graph conv's adjacency product and the block output
             # (the temporal conv, bias, residual add and activation act per joint), so it is folded into the adjacency:
             # the graph conv runs with A[:, :, keep] and only ever produces the kept joints
-            tcn = TapConvGeom(co, co, T, len(v_keep), kt=self._kt, pad=self._pad, stride=self._stride, t_sel=t_sel)
-            res = None
+            v_keep = [int(v) for v in self.graph.map[self.lvl + 1][:, 1]] if self.dw_s else list(range(V))
+            W = len(v_keep)
+            Wp = _pad4(W) if pad_out else W
+            # source joint of every output joint; a dummy output joint takes the input's dummy joint when there is one (its
+            # value is irrelevant but finite), else nothing (-1: zero)
+            v_src = v_keep + [V if Vx > V else -1] * (Wp - W)
+            plain_t = t_sel == list(range(T)) and self._stride == 1
+            if plain_t or not UNFOLD_STRIDED_TCN or (len(t_sel) * Wp) % 4:
+                tcn = TapConvGeom(co, co, T, Wp, kt=self._kt, pad=self._pad, stride=self._stride, t_sel=t_sel)
+            else:
+                tcn = UnfoldedTcnGeom(co, co, T, Wp, self._kt, self._pad, self._stride, 1, t_sel)
+            res = sel = None
+            ident = plain_t and v_src == list(range(Vx))
             if self._res == "conv":
-                res = TapConvGeom(ci, co, T, V, kt=1, stride=self._stride, t_sel=t_sel, v_keep=v_keep)
-            elif self._res == "identity" and (t_sel != list(range(T)) or len(v_keep) != V):
-                res = select_table(T, V, t_sel, v_keep)
-            keep = torch.tensor(v_keep, dtype=torch.long) if len(v_keep) != V else None
-            p = self._plans[(T, V)] = (tcn, res, keep)
+                if ident or not SELECT_THEN_CONV:
+                    res = TapConvGeom(ci, co, T, Vx, kt=1, stride=self._stride, t_sel=t_sel, v_keep=v_src)
+                else:
+                    sel = select_table(T, Vx, [t * self._stride for t in t_sel], v_src)
+                    res = TapConvGeom(ci, co, len(t_sel), Wp, kt=1)
+            elif self._res == "identity" and not ident:
+                sel = select_table(T, Vx, t_sel, v_src)
+            # A (K, V, V) -> (K, Vx, Wp): kept columns, zero rows for the input's dummy joints, zero columns for the output's
+            cols = torch.tensor(v_keep + [V] * (Wp - W), dtype=torch.long, device=device)
+            rows = torch.tensor(list(range(V)) + [V] * (Vx - V), dtype=torch.long, device=device)
+            amap = None if (W == V and Wp == V and Vx == V) else (rows, cols)
+            p = self._plans[key] = (tcn, res, sel, amap)
         return p
 
-    def forward(self, x, A, label_emb=None):
+    def forward(self, x, A, label_emb=None, pad_joints=False):
         """`label_emb` (optional, not in the reference): (N, n_cls) label embedding standing for the first n_cls input
         channels, which the reference materialises as constant planes (discriminator.py:57-60); x then holds only the
-        data channels.  Only valid for a block without residual branch (the critic's first block)."""
-        tcn, res, keep = self._plan(x.size(2), A.size(2))
+        data channels.  Only valid for a block without residual branch (the critic's first block).
+        `pad_joints` (optional, not in the reference; used by Discriminator.forward): x may carry dummy joints beyond the
+        graph's V and the output may be padded likewise - see PAD_JOINTS above."""
+        V = A.size(1)
+        assert x.size(3) >= V and (pad_joints or x.size(3) == V)
+        tcn, res, sel, amap = self._plan(x.size(2), V, x.size(3), pad_joints, x.device)
         A_in = A
-        if keep is not None:
-            if keep.device != A.device:
-                keep = keep.to(A.device)
-                self._plans[(x.size(2), A.size(2))] = (tcn, res, keep)
-            A = A.index_select(2, keep)                    # (K, V, V_keep): dropped joints are never computed
+        if amap is not None:
+            A = torch.nn.functional.pad(A, (0, 1, 0, 1)).index_select(1, amap[0]).index_select(2, amap[1])
         if label_emb is not None:
             assert self._res == "none"
             g, _ = self.gcn.forward_with_labels(x, A, label_emb)
-            return KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, None, tcn, KF.ACT_LRELU), A_in
+        else:
+            g, _ = self.gcn(x, A)
         if self._res == "none":
             r = None
         elif self._res == "identity":
-            r = x if res is None else KF.PlaneSpmm.apply(x, res)
+            r = x if sel is None else KF.PlaneSpmm.apply(x, sel)
         else:
-            r = KF.TapConvEp.apply(x, self.residual.weight, self.residual.bias, None, res, KF.ACT_NONE)
-        g, _ = self.gcn(x, A)
+            xs = x if sel is None else KF.PlaneSpmm.apply(x, sel)
+            r = KF.TapConvEp.apply(xs, self.residual.weight, self.residual.bias, None, res, KF.ACT_NONE)
+        if isinstance(tcn, UnfoldedTcnGeom):
+            g = KF.PlaneSpmm.apply(g, tcn.unfold)
         x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU)
         return x, A_in
 
     def downsample_s(self, tensor):
-        """Kept for API parity (discriminator.py:139-142); the forward pass folds it into the conv's position map."""
+        """Kept for API parity (discriminator.py:139-142); the forward pass folds it into the adjacency."""
         keep = [int(v) for v in self.graph.map[self.lvl + 1][:, 1]]
         return KF.PlaneSpmm.apply(tensor, select_table(tensor.size(2), tensor.size(3), list(range(tensor.size(2))), keep))

@@ -88,7 +88,9 @@ def test_discriminator_and_gp_vs_golden(emu, case, tag):
     for h in hooks:
         h.remove()
     for i, b in enumerate(blocks):
-        assert rel_l2(b, gold[tag + "/d_block%d" % i]) < tol, i
+        ref = gold[tag + "/d_block%d" % i]
+        # inside Discriminator.forward a block may carry dummy joints beyond the graph's V (joint axis padded to a multiple of 4)
+        assert rel_l2(b[..., :ref.shape[-1]], ref) < tol, i
     assert rel_l2(dv, gold[tag + "/d_out"]) < tol
     (dv * x["cot_d"]).sum().backward()
     assert rel_l2(xr.grad, gold[tag + "/d_grad_x"]) < 10 * tol

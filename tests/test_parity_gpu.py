@@ -72,7 +72,8 @@ def test_discriminator_and_gp_vs_golden(case):
     for h in hooks:
         h.remove()
     for i, b in enumerate(blocks):
-        assert rel_l2(b, gold["f64/d_block%d" % i]) < TOL, i
+        ref = gold["f64/d_block%d" % i]
+        assert rel_l2(b[..., :ref.shape[-1]], ref) < TOL, i       # dummy joints (axis padded to a multiple of 4) are dropped
     assert rel_l2(dv, gold["f64/d_out"]) < TOL
     (dv * x["cot_d"]).sum().backward()
     assert rel_l2(xr.grad, gold["f64/d_grad_x"]) < 10 * TOL

@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from importlib import import_module
+
 import emu_backend as emu
 import kgan_b200 as kgan
 
@@ -33,6 +35,12 @@ def rel(a, b):
 GEOMS = {
     "d1_gcn": (dict(c_in=32, c_out=64, t_in=64, v_in=11, K=3), 4),
     "d2_gcn": (dict(c_in=64, c_out=128, t_in=64, v_in=11, K=3), 3),
+    "d1_tcn_v12": (dict(c_in=64, c_out=64, t_in=64, v_in=12, kt=3, pad=1), 4),                     # aligned shifts: TMA-fed kernel
+    "d1_tcn_v11": (dict(c_in=64, c_out=64, t_in=64, v_in=11, kt=3, pad=1), 4),                     # unaligned shifts: gather kernel
+    "d4_gcn_p80": (dict(c_in=256, c_out=512, t_in=16, v_in=5, K=3), 7),                            # boxes of 16 positions x 2 samples
+    "d5_gcn_p8": (dict(c_in=512, c_out=512, t_in=8, v_in=1, K=3), 70),                             # boxes of 8 positions x 4 samples
+    "d2_tcn_unfolded": (dict(unfold=True, c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 64, 2))), 5),
+    "d5_tcn_unfolded": (dict(unfold=True, c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, stride=1, dil=1, t_sel=[0, 2, 4, 6]), 130),
     "d2_tcn_select": (dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=[2, 4, 6, 8, 10]), 5),
     "d3_tcn": (dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 6),
     "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 160),
@@ -45,11 +53,24 @@ GEOMS = {
 }
 
 
+TMA_EXPECTED = {"d1_gcn": (1, 1), "d2_gcn": (1, 1), "d1_tcn_v12": (1, 1), "d1_tcn_v11": (0, 0), "d4_gcn_p80": (1, 1), "d5_gcn_p8": (1, 1),
+                "d2_tcn_unfolded": (1, 1), "d5_tcn_unfolded": (1, 1), "d2_tcn_select": (0, 0), "ragged_k": (0, 0)}
+
+
 @pytest.mark.parametrize("name", list(GEOMS))
 def test_tapconv_tf32(name):
     kw, n = GEOMS[name]
-    geom = G.TapConvGeom(**kw)
-    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    kw = dict(kw)
+    if kw.pop("unfold", False):
+        geom = G.UnfoldedTcnGeom(**kw)                # operates on the time-unfolded input (kt blocks of t_out frames)
+        x = rnd(n, geom.c_in, geom.kt * geom.t_out, geom.v_in, seed=1)
+    else:
+        geom = G.TapConvGeom(**kw)
+        x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    if name in TMA_EXPECTED:                          # the TMA-fed kernel is the one that runs (no silent gather fallback)
+        lib = import_module("kinetic-gan_b200._lib").lib()
+        assert lib.kgan_tapconv_tma_ok(geom.fwd.cstruct(n, 0, 1)) == TMA_EXPECTED[name][0]
+        assert lib.kgan_tapconv_tma_ok(geom.dgrad.cstruct(n, 0, 1)) == TMA_EXPECTED[name][1]
     w = rnd(geom.K * geom.c_out, kw.get("w_cin", geom.c_in), geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
     bias = rnd(geom.c_out, seed=3)
     add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)

@@ -43,27 +43,37 @@ def timeit(fn):
     return _span(fn)
 
 
-LAYERS = [
-    ("D0.tcn", dict(c_in=32, c_out=32, t_in=64, v_in=11, kt=3, pad=1)),          # joint selection folded into the adjacency
-    ("D1.gcn", dict(c_in=32, c_out=64, t_in=64, v_in=11, K=3)),
-    ("D1.tcn", dict(c_in=64, c_out=64, t_in=64, v_in=11, kt=3, pad=1)),
-    ("D1.res", dict(c_in=32, c_out=64, t_in=64, v_in=11)),
+LAYERS = [   # the critic's tap convolutions as Discriminator.forward runs them (joints 11 -> 12 padded, strided tcn unfolded)
+    ("D0.tcn", dict(c_in=32, c_out=32, t_in=64, v_in=12, kt=3, pad=1)),
+    ("D1.gcn", dict(c_in=32, c_out=64, t_in=64, v_in=12, K=3)),
+    ("D1.tcn", dict(c_in=64, c_out=64, t_in=64, v_in=12, kt=3, pad=1)),
+    ("D1.res", dict(c_in=32, c_out=64, t_in=64, v_in=12)),
     ("D2.gcn", dict(c_in=64, c_out=128, t_in=64, v_in=5, K=3)),
-    ("D2.tcn", dict(c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, t_sel=list(range(0, 64, 2)))),
-    ("D2.res", dict(c_in=64, c_out=128, t_in=64, v_in=11, t_sel=list(range(0, 64, 2)), v_keep=keep2)),
+    ("D2.tcn", dict(unfold=True, c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 64, 2)))),
+    ("D2.res", dict(c_in=64, c_out=128, t_in=32, v_in=5)),
     ("D3.gcn", dict(c_in=128, c_out=256, t_in=32, v_in=5, K=3)),
-    ("D3.tcn", dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2)))),
+    ("D3.tcn", dict(unfold=True, c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 32, 2)))),
+    ("D3.res", dict(c_in=128, c_out=256, t_in=16, v_in=5)),
     ("D4.gcn", dict(c_in=256, c_out=512, t_in=16, v_in=1, K=3)),
-    ("D4.tcn", dict(c_in=512, c_out=512, t_in=16, v_in=1, kt=3, pad=1, t_sel=list(range(0, 16, 2)))),
+    ("D4.tcn", dict(unfold=True, c_in=512, c_out=512, t_in=16, v_in=1, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 16, 2)))),
+    ("D4.res", dict(c_in=256, c_out=512, t_in=8, v_in=1)),
     ("D5.gcn", dict(c_in=512, c_out=512, t_in=8, v_in=1, K=3)),
-    ("D5.tcn", dict(c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, t_sel=[0, 2, 4, 6])),
+    ("D5.tcn", dict(unfold=True, c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, stride=1, dil=1, t_sel=[0, 2, 4, 6])),
 ]
 print("%-8s %-6s %9s %9s %9s   (batch %d, %s)" % ("layer", "op", "us", "GB/s", "TFLOP/s", N, a.precision))
 for name, kw in LAYERS:
     if a.only and a.only not in name:
         continue
-    g = G.TapConvGeom(**kw)
-    x = torch.randn(N, g.K * g.c_in, g.t_in, g.v_in, device=dev)
+    kw = dict(kw)
+    if kw.pop("unfold", False):
+        g = G.UnfoldedTcnGeom(**kw)
+        xr = torch.randn(N, g.c_in, g.t_in, g.v_in, device=dev)
+        us = timeit(lambda: ops.plane_spmm(xr, g.unfold))
+        print("%-8s %-6s %9.1f %9.0f" % (name, "unfold", us, 4.0 * xr.numel() * (1 + g.kt * g.t_out / g.t_in) / us / 1e3))
+        x = torch.randn(N, g.c_in, g.kt * g.t_out, g.v_in, device=dev)
+    else:
+        g = G.TapConvGeom(**kw)
+        x = torch.randn(N, g.K * g.c_in, g.t_in, g.v_in, device=dev)
     w = torch.randn(g.K * g.c_out, g.c_in, g.kt, 1, device=dev) * 0.05
     go = torch.randn(N, g.c_out, g.t_out, g.v_out, device=dev)
     bytes_io = 4.0 * (x.numel() + go.numel())
@@ -72,7 +82,7 @@ for name, kw in LAYERS:
                    ("wgrad", lambda: ops.tapconv_wgrad(x, go, g.fwd, tuple(w.shape)))):
         us = timeit(fn)
         print("%-8s %-6s %9.1f %9.0f %9.1f" % (name, op, us, bytes_io / us / 1e3, flops / us / 1e6))
-for name, (c, t, v, vo) in (("D0", (3, 64, 25, 11)), ("D1", (32, 64, 11, 11)), ("D2", (64, 64, 11, 5)), ("D3", (128, 32, 5, 5)),
+for name, (c, t, v, vo) in (("D0", (3, 64, 25, 12)), ("D1", (32, 64, 12, 12)), ("D2", (64, 64, 12, 5)), ("D3", (128, 32, 5, 5)),
                             ("D4", (256, 16, 5, 1)), ("D5", (512, 8, 1, 1))):
     if a.only and a.only not in name:
         continue
