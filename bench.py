@@ -256,6 +256,7 @@ def run_kgan(args):
         step_resident(i)
     torch.cuda.synchronize()
     fam = ops.profile_stop(prof)
+    sites = fam.pop("_sites")
     tr.use_graphs = graphs
     it += 5
     tensor_peak, hbm_peak, peak_kind = peaks()
@@ -269,7 +270,10 @@ def run_kgan(args):
                 "share_of_kgan_kernel_time": st["ms"] / total_ms,
                 "step_algorithmic_tflops": FLOP_PER_SAMPLE * value / 1e12 / comm.world_size,
                 "families": {k: {"ms_per_step": v["ms"] / 5, "launches_per_step": v["n"] / 5,
-                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()}}
+                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()},
+                "top_sites": [{"site": k, "ms_per_step": round(v["ms"] / 5, 3), "launches_per_step": v["n"] / 5,
+                               "us_per_launch": round(v["ms"] / v["n"] * 1e3, 1)}
+                              for k, v in sorted(sites.items(), key=lambda kv: -kv[1]["ms"])[:40]]}
 
     cpu = None
     if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:

@@ -6,7 +6,10 @@
 // lets one elected thread fetch a [32 channels] x [32 positions] box (4 KB, 128-byte rows, 32-byte swizzle atoms) per M group with a single
 // cp.async.bulk.tensor; four boxes make the 128 x 32 A tile of a pipeline stage.  A temporal tap is a shift of the
 // position coordinate by (tap - pad) * dilation * V; positions shifted outside the plane are zero-filled by the TMA unit,
-// which is the convolution's zero padding.  Small planes (P = 16, 8, 4) use boxes of p_box positions x n_box samples.
+// which is the convolution's zero padding.  Planes that are not a multiple of 32 positions (P = 80, 16, 8, 4) cannot be boxed
+// that way (the 32-byte-atom swizzle needs 128-byte box rows); for them four extra warps write the same shared-memory
+// image with 16-byte cp.async copies (p_box positions x n_box samples per 128-byte row, swizzle applied by hand) - still
+// register-free, so the whole ring of stages is in flight.
 // With 4-6 stages of 16 KB in flight per SM the kernel is bandwidth- instead of latency-bound (the SIMT-gather kernel
 // holds at most 32 KB of loads in registers, and measured 8-20 % of HBM peak with long-scoreboard stalls dominating).
 //
@@ -21,9 +24,11 @@
 // convolutions read a time-unfolded copy of their input whose taps sit at block offsets (see geometry.py).
 //
 // Warp roles: warp 0 = producer (one thread: tensor loads + bulk copies of the packed weights), warp 1 = MMA issuer and
-// TMEM owner (accumulators double-buffered), warps 2-9 = epilogue (TMEM -> bias/add/act -> coalesced NCHW stores).
+// TMEM owner (accumulators double-buffered), warps 2-9 = epilogue (TMEM -> bias/add/act -> coalesced NCHW stores),
+// warps 10-13 = cp.async activation producers (only launched when p_box < 32).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "umma.cuh"
 
@@ -31,7 +36,9 @@ namespace kgan {
 
 constexpr int TM_EPI_WARPS = 8;
 constexpr int TM_EPI_WARP0 = 2;
-constexpr int TM_THREADS = 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);
+constexpr int TM_THREADS = 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);       // TMA mode
+constexpr int TM_CP_WARPS = 4;
+constexpr int TM_THREADS_CP = TM_THREADS + 32 * TM_CP_WARPS;          // cp.async mode
 constexpr float TM_TRUNC_FIX = 1.000353f;      // 1 / (1 - 3.53e-4)
 constexpr int TM_GROUP_BYTES = 32 * 32 * 4;    // one box: 32 channel rows of 128 bytes
 
@@ -124,9 +131,13 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
     }
 }
 
-__global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
+__device__ __forceinline__ void tm_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
                                                                     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
-                                                                    const float* __restrict__ bias,
+                                                                    const float* __restrict__ in, const float* __restrict__ bias,
                                                                     const float* __restrict__ add, float* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
@@ -140,10 +151,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
     const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
     const int kiters = pl.nkt * d.ntap;
+    const bool use_tma = pl.p_box == 32;                             // else: cp.async producers (warps 10-13)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, 1);                             // the producer's arrive.expect_tx; the copies complete the bytes
+            // the producer's arrive.expect_tx (the bulk / tensor copies complete the bytes) + in cp.async mode one deferred
+            // arrival per producer thread
+            mbar_init(full0 + 8 * s, use_tma ? 1 : 1 + 32 * TM_CP_WARPS);
             mbar_init(empty0 + 8 * s, 1);                            // tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
             mbar_init(tempty0 + 8 * b, 32 * TM_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        if (use_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
@@ -167,7 +181,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
         // ===== producer: tensor loads of the activation boxes + bulk copies of the packed weights =====
         if (lane == 0) {
             const uint32_t chunk_bytes = pl.n_cta * 16;
-            const uint32_t stage_tx = A_STAGE_BYTES + chunk_bytes * 8;
+            const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + chunk_bytes * 8;
             int kit = 0;
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
                 const TmaTile tc = tma_tile(tile, pl);
@@ -190,8 +204,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
                     mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
                     const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
                     const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+                    if (use_tma) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                        for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                    }
                     const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
                     const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
                     if (pl.n_split == 1) {
@@ -219,7 +235,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
                 for (int it = 0; it < kiters; ++it) {
                     const int k = kit + it, s = k % S;
                     const uint32_t ph = (uint32_t)(k / S) & 1u;
-                    mbar_wait(full0 + 8 * s, ph);                     // both operands were written by the async proxy: no proxy fence
+                    mbar_wait(full0 + 8 * s, ph);
+                    // TMA mode: both operands were written by the async proxy.  cp.async mode: the activations went through the
+                    // generic proxy and must be made visible to the tensor core's async-proxy reads
+                    if (!use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
@@ -232,6 +251,50 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tapconv_fwd_tma_k(const __grid_
                 umma_commit(tfull0 + 8 * buf);
                 kit += kiters;
             }
+        }
+    } else if (warp >= TM_EPI_WARP0 + TM_EPI_WARPS) {
+        // ===== cp.async activation producers (p_box < 32): thread = (16-byte chunk of the 128-byte row, channel rows rr, rr + 16) =====
+        const int t = threadIdx.x - 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);
+        const int chunk = t & 7, rr = t >> 3;
+        const int m0 = chunk * 4;                                     // first of this chunk's 4 M elements within the group
+        const int nl = m0 >> pl.p_shift, pl0 = m0 & (pl.p_box - 1);   // sample within the box, position within the chunk row
+        int kit = 0;
+        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+            const TmaTile tc = tma_tile(tile, pl);
+            const float* base[4];
+            int pq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t G = (int64_t)tc.mt * 4 + i;
+                const int nb = (int)(G / pl.cps);
+                const int nn = nb * pl.n_box + nl;
+                const bool ok = G < pl.groups32 && nn < d.n;
+                pq[i] = ok ? ((int)(G - (int64_t)nb * pl.cps) << pl.p_shift) + pl0 : -(1 << 30);
+                base[i] = in + (int64_t)(ok ? nn : 0) * d.c_in_total * d.p_in;
+            }
+            const int ch_g = tc.g * d.g_in;
+            for (int it = 0; it < kiters; ++it) {
+                const int k = kit + it, s = k % S;
+                const uint32_t ph = (uint32_t)(k / S) & 1u;
+                const int ict = it / d.ntap, tap = it - ict * d.ntap;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pos = pq[i] + sh;                       // 4-aligned: the chunk lies entirely inside or outside the plane
+                    const bool pok = pos >= 0 && pos < d.p_in;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = rr + 16 * h;
+                        const bool ok = pok && ch0 + c < d.c_in_total;
+                        const uint32_t dst = a_dst + i * TM_GROUP_BYTES + c * 128 + ((chunk * 16) ^ ((c & 3) << 5));
+                        tm_cp_async16(dst, ok ? base[i] + (int64_t)(ch0 + c) * d.p_in + pos : in, ok ? 16u : 0u);
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8 * s) : "memory");
+            }
+            kit += kiters;
         }
     } else {
         // ===== epilogue warps: TMEM lane = row of the tile = (M group, element of the box) =====
@@ -303,11 +366,12 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
         return 1;
     }
     CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
     const cuuint64_t gdim[3] = {(cuuint64_t)d.p_in, (cuuint64_t)d.n, (cuuint64_t)d.c_in_total};
     const cuuint64_t gstr[2] = {(cuuint64_t)d.c_in_total * d.p_in * 4, (cuuint64_t)d.p_in * 4};
     const cuuint32_t box[3] = {(cuuint32_t)p.p_box, (cuuint32_t)p.n_box, 32u};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = p.p_box != 32 ? CUDA_SUCCESS : enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -327,7 +391,7 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     }
     (void)pmap;                                                    // the shift form replaces the position map
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_tma_k<<<grid, TM_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, bias, add, out);
+    tapconv_fwd_tma_k<<<grid, p.p_box == 32 ? TM_THREADS : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
     return check_launch("tapconv_fwd_tma");
 }
 

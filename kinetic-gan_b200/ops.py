@@ -55,17 +55,24 @@ def profile_stop(prof):
     global _prof
     _prof = None
     torch.cuda.synchronize()
-    out = {}
-    for name, flops, e0, e1 in prof:
-        d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
-        d["ms"] += e0.elapsed_time(e1)
-        d["n"] += 1
-        d["flops"] += flops
+    out, sites = {}, {}
+    for name, flops, e0, e1, sig in prof:
+        ms = e0.elapsed_time(e1)
+        for table, key in ((out, name), (sites, name + " " + sig)):
+            d = table.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
+            d["ms"] += ms
+            d["n"] += 1
+            d["flops"] += flops
+    out["_sites"] = sites
     return out
+
+
+_sig = ""          # shape signature of the launch being issued (profiling only)
 
 
 def _run(family, flops, fn, *args):
     """One kernel launch through the C ABI (+ CUDA events around it when profiling)."""
+    global _sig
     if _prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -73,11 +80,21 @@ def _run(family, flops, fn, *args):
     _count()
     if _prof is not None:
         e1.record()
-        _prof.append((family, flops, e0, e1))
+        _prof.append((family, flops, e0, e1, _sig))
+        _sig = ""
 
 
 def _tap_flops(desc, n):
+    global _sig
+    if _prof is not None:
+        _sig = "n%d ck%d co%d tap%d g%d pin%d pout%d tma%d" % (n, desc.ck, desc.co, desc.ntap, desc.groups, desc.p_in, desc.p_out, desc.tma_mode)
     return 2.0 * n * desc.p_out * desc.co * desc.ck * desc.ntap * desc.groups
+
+
+def _shape_sig(*ts):
+    global _sig
+    if _prof is not None:
+        _sig = " ".join("x".join(str(d) for d in t.shape) for t in ts)
 
 
 # ---- tf32 tensor-core path: packed weight images are cached per (weight storage, version, geometry) ----------
@@ -158,6 +175,7 @@ def adjmix_fwd(x, A):
     k, v2, w = A.shape
     assert v2 == v
     out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
+    _shape_sig(x, A)
     _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream())
     return out
 
@@ -169,6 +187,7 @@ def adjmix_bwd_x(g, A):
     assert w2 == w and kc % k == 0
     c = kc // k
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
+    _shape_sig(g, A)
     _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream())
     return gx
 
@@ -179,6 +198,7 @@ def adjmix_bwd_a(x, g, k):
     w = g.shape[3]
     assert g.shape[0] == n and g.shape[1] == k * c and g.shape[2] == t
     gA = torch.empty((k, v, w), device=x.device, dtype=torch.float32)
+    _shape_sig(x, g)
     _run('adjmix_bwd_a', 0.0, _lib.lib().kgan_adjmix_bwd_a, x.data_ptr(), g.data_ptr(), gA.data_ptr(), n, c, t, v, w, k, _stream())
     return gA
 
@@ -195,6 +215,7 @@ def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=ACT_NONE):
 def act_bwd(gout, out, act):
     _chk(gout, out)
     gz = torch.empty_like(out)
+    _shape_sig(out)
     _run('pointwise', 0.0, _lib.lib().kgan_act_bwd, gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream())
     return gz
 
@@ -203,6 +224,7 @@ def chan_reduce(g, mul=None):
     _chk(g, mul)
     n, c, t, v = g.shape
     out = torch.empty((c,), device=g.device, dtype=torch.float32)
+    _shape_sig(g)
     _run('reduce', 0.0, _lib.lib().kgan_chan_reduce, g.data_ptr(), _ptr(mul), out.data_ptr(), n, c, t * v, _stream())
     return out
 
@@ -213,6 +235,7 @@ def plane_spmm(x, table):
     assert t * v == table.p_in, (tuple(x.shape), table.p_in)
     idx, wgt = table.on(x.device)
     out = torch.empty((n, c, table.t_out, table.v_out), device=x.device, dtype=torch.float32)
+    _shape_sig(x, out)
     _run('plane_spmm', 0.0, _lib.lib().kgan_plane_spmm, x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
                                           table.J, _stream())
     return out
