@@ -102,6 +102,13 @@ int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d);
 int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream);
 int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
                           const float* bias, const float* add, float* out, void* stream);
+/* One launch that (re)packs `count` weights - what a trainer calls after its optimizer step instead of `count` launches of
+ * kgan_tapconv_pack_tf32.  descs / w / wp are HOST arrays (w[i], wp[i] device pointers as above); `items` is a caller-owned
+ * device workspace of count * kgan_tapconv_pack_item_bytes() bytes that holds the item table: pass upload = 1 whenever the
+ * set of items changed since the last call with this workspace (the table is rebuilt and copied), 0 to reuse it. */
+int64_t kgan_tapconv_pack_item_bytes(void);
+int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
+                                   int upload, void* stream);
 
 /* 1 if kgan_tapconv_fwd_tf32 will run the TMA-fed kernel for this descriptor (tma_mode != 0, plane size a multiple of 4,
  * tensor-core eligible): activations then reach shared memory by cp.async.bulk.tensor instead of per-thread gathers. */

@@ -58,74 +58,85 @@ __device__ __forceinline__ Carve carve(float* sm, int k, int v, int w, int lists
     return c;
 }
 
-__global__ void __launch_bounds__(AT) adjmix_fwd_k(const float* __restrict__ x, const float* __restrict__ A, float* __restrict__ out,
-                                                    int ct, int v, int w, int k, int blocks_per_sample) {
-    extern __shared__ __align__(16) float sm[];
-    const Carve s = carve(sm, k, v, w, k * w, v);
-    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) s.As[i] = A[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < k * w; i += blockDim.x) {          // per output (k, w): source joints with A != 0
-        const int kk = i / w, ww = i - kk * w;
-        int cnt = 0;
-        for (int j = 0; j < v; ++j)
-            if (s.As[(kk * v + j) * w + ww] != 0.f) s.nz[i * v + cnt++] = j;
-        s.nzc[i] = cnt;
-    }
-    const int nn = blockIdx.x / blocks_per_sample, q0 = (blockIdx.x % blocks_per_sample) * RB;
-    const int rows = min(RB, ct - q0);
-    copy_in(s.xs, x + ((int64_t)nn * ct + q0) * v, rows * v);
-    __syncthreads();
-    const int gstride = align4(RB * w);
-    // thread = (row, half of the k*w outputs)
-    const int row = threadIdx.x & (RB - 1), half = threadIdx.x >> 7;
-    if (row < rows) {
-        const float* xr = s.xs + row * v;
-        for (int o = half; o < k * w; o += 2) {
-            const int kk = o / w, ww = o - kk * w, cnt = s.nzc[o];
-            float acc = 0.f;
-            for (int j = 0; j < cnt; ++j) {
-                const int vv = s.nz[o * v + j];
-                acc = fmaf(xr[vv], s.As[(kk * v + vv) * w + ww], acc);
-            }
-            s.gs[kk * gstride + row * w + ww] = acc;
-        }
-    }
-    __syncthreads();
-    for (int kk = 0; kk < k; ++kk) copy_out(out + (((int64_t)nn * k + kk) * ct + q0) * w, s.gs + kk * gstride, rows * w);
-}
+// Forward and dx share one kernel.  Both are a small sparse mix along the joint axis of every row q = (c, t):
+//     out[n, ko, q, wo] = sum_j coef_j * in[n, kin_j, q, vi_j]
+//   fwd (MODE 0): in = x (one block per sample), out blocks ko = k:   entries of (k, w) = { (0, v, A[k,v,w]) : A[k,v,w] != 0 }
+//   dx  (MODE 1): in = g (K blocks per sample), one out block:        entries of v      = { (k, w, A[k,v,w]) : A[k,v,w] != 0 }
+// Every CTA first compacts A into per-output entry lists in shared memory (exact: zero entries contribute nothing), then a
+// thread produces 4 CONSECUTIVE outputs of one (n, ko) block - one 16-byte store, one integer division per 4 outputs - and
+// reads its inputs straight from global memory (a row of V <= 32 floats is shared by the W threads next to it: L1 hits).
+// Compared with the previous staged version (one thread per row looping over shared memory: 78 % SM-busy at 6 % of HBM
+// peak) this removes the per-element index arithmetic and the three block-wide barriers per 128 rows.
+struct MixEntry {
+    int off;       // element offset of the input relative to the sample's first block at row q = 0
+    float coef;
+};
 
-__global__ void __launch_bounds__(AT) adjmix_bwd_x_k(const float* __restrict__ g, const float* __restrict__ A, float* __restrict__ gx,
-                                                      int ct, int v, int w, int k, int blocks_per_sample) {
+template <int MODE>
+__global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int n,
+                                                       int ct, int v, int w, int k, int chunks_per_block, int64_t total_items) {
     extern __shared__ __align__(16) float sm[];
-    const Carve s = carve(sm, k, v, w, v, k * w);
-    for (int i = threadIdx.x; i < k * v * w; i += blockDim.x) s.As[i] = A[i];
-    __syncthreads();
-    for (int vv = threadIdx.x; vv < v; vv += blockDim.x) {           // per output joint v: (k, w) pairs with A != 0
-        int cnt = 0;
-        for (int kk = 0; kk < k; ++kk)
-            for (int ww = 0; ww < w; ++ww)
-                if (s.As[(kk * v + vv) * w + ww] != 0.f) s.nz[vv * k * w + cnt++] = kk * w + ww;
-        s.nzc[vv] = cnt;
-    }
-    const int nn = blockIdx.x / blocks_per_sample, q0 = (blockIdx.x % blocks_per_sample) * RB;
-    const int rows = min(RB, ct - q0);
-    const int gstride = align4(RB * w);
-    for (int kk = 0; kk < k; ++kk) copy_in(s.gs + kk * gstride, g + (((int64_t)nn * k + kk) * ct + q0) * w, rows * w);
-    __syncthreads();
-    const int row = threadIdx.x & (RB - 1), half = threadIdx.x >> 7;
-    if (row < rows) {
-        for (int vv = half; vv < v; vv += 2) {
-            const int cnt = s.nzc[vv];
-            float acc = 0.f;
-            for (int j = 0; j < cnt; ++j) {
-                const int e = s.nz[vv * k * w + j], kk = e / w, ww = e - kk * w;
-                acc = fmaf(s.gs[kk * gstride + row * w + ww], s.As[(kk * v + vv) * w + ww], acc);
+    const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;           // output blocks per sample / outputs per row
+    const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;           // inputs per row / input blocks per sample
+    const int maxj = MODE == 0 ? v : k * w;
+    const int nlists = ko * wo;
+    int* cnt = reinterpret_cast<int*>(sm);
+    MixEntry* ent = reinterpret_cast<MixEntry*>(sm + ((nlists + 3) & ~3));
+    for (int o = threadIdx.x; o < nlists; o += blockDim.x) {
+        int c = 0;
+        if (MODE == 0) {
+            const int kk = o / w, ww = o - kk * w;
+            for (int vv = 0; vv < v; ++vv) {
+                const float a = __ldg(A + (kk * v + vv) * w + ww);
+                if (a != 0.f) ent[o * maxj + c++] = MixEntry{vv, a};
             }
-            s.xs[row * v + vv] = acc;
+        } else {
+            for (int kk = 0; kk < k; ++kk)
+                for (int ww = 0; ww < w; ++ww) {
+                    const float a = __ldg(A + (kk * v + o) * w + ww);
+                    if (a != 0.f) ent[o * maxj + c++] = MixEntry{kk * ct * w + ww, a};
+                }
+        }
+        cnt[o] = c;
+    }
+    __syncthreads();
+    const unsigned plane = (unsigned)ct * (unsigned)wo;                  // outputs of one (n, ko) block, contiguous
+    const bool vec = (plane & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int chunk = (int)(item % chunks_per_block);
+        const int64_t nb = item / chunks_per_block;                      // n * ko + kb
+        const int kb = (int)(nb % ko);
+        const int64_t nn = nb / ko;
+        const unsigned e0 = ((unsigned)chunk * AT + threadIdx.x) * 4u;
+        if (e0 >= plane) continue;
+        const float* in_n = in + nn * (int64_t)ki * ct * vi;
+        unsigned q = e0 / (unsigned)wo, ww = e0 - q * (unsigned)wo;
+        float r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float acc = 0.f;
+            if (e0 + u < plane) {
+                const int o = kb * wo + (int)ww;
+                const MixEntry* el = ent + o * maxj;
+                const float* xq = in_n + (int64_t)q * vi;
+                const int c = cnt[o];
+                for (int j = 0; j < c; ++j) acc = fmaf(el[j].coef, __ldg(xq + el[j].off), acc);
+            }
+            r[u] = acc;
+            if (++ww == (unsigned)wo) {
+                ww = 0;
+                ++q;
+            }
+        }
+        float* op = out + nb * (int64_t)plane + e0;
+        if (vec) {
+            *reinterpret_cast<float4*>(op) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u < plane) op[u] = r[u];
         }
     }
-    __syncthreads();
-    copy_out(gx + ((int64_t)nn * ct + q0) * v, s.xs, rows * v);
 }
 
 // gA: a (k*w) x v GEMM with a very long contraction (all rows).  Each CTA walks over many row blocks; every thread owns
@@ -203,26 +214,36 @@ static int set_smem(Kern kern, size_t bytes, bool& done) {
 
 using namespace kgan;
 
+template <int MODE>
+static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "%s: empty dimension", what);
+    const int64_t ct64 = (int64_t)c * t;
+    KGAN_REQUIRE(ct64 * (MODE == 0 ? w : v) < (1ll << 31) && ct64 * k * w < (1ll << 31), "%s: plane too large", what);
+    const int ct = (int)ct64, ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;
+    const int nlists = ko * wo;
+    const size_t smem = (size_t)((nlists + 3) & ~3) * 4 + (size_t)k * v * w * sizeof(MixEntry);
+    KGAN_REQUIRE(smem <= 200 * 1024, "%s: V=%d, W=%d, K=%d do not fit in shared memory", what, v, w, k);
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(adjmix_rowmix_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return check_launch("adjmix attribute");
+        attr = true;
+    }
+    const int chunks = (int)ceil_div64((int64_t)ct * wo, AT * 4);
+    const int64_t items = (int64_t)n * ko * chunks;
+    const int64_t grid = items < 8 * kNumSMs ? items : 8 * kNumSMs;
+    adjmix_rowmix_k<MODE><<<(unsigned)grid, AT, smem, (cudaStream_t)stream>>>(in, A, out, n, ct, v, w, k, chunks, items);
+    return check_launch(what);
+}
+
 extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
-    const size_t fl = carve_floats(k, v, w, k * w, v);
-    if (int e = check_shape("adjmix_fwd", n, c, t, v, w, k, fl)) return e;
-    static bool attr = false;
-    if (int e = set_smem(adjmix_fwd_k, fl * 4, attr)) return e;
-    const int ct = c * t, bps = ceil_div(ct, RB);
-    adjmix_fwd_k<<<(unsigned)(n * bps), AT, fl * 4, (cudaStream_t)stream>>>(x, A, out, ct, v, w, k, bps);
-    return check_launch("adjmix_fwd");
+    return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream) {
     KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
-    const size_t fl = carve_floats(k, v, w, v, k * w);
-    if (int e = check_shape("adjmix_bwd_x", n, c, t, v, w, k, fl)) return e;
-    static bool attr = false;
-    if (int e = set_smem(adjmix_bwd_x_k, fl * 4, attr)) return e;
-    const int ct = c * t, bps = ceil_div(ct, RB);
-    adjmix_bwd_x_k<<<(unsigned)(n * bps), AT, fl * 4, (cudaStream_t)stream>>>(g, A, gx, ct, v, w, k, bps);
-    return check_launch("adjmix_bwd_x");
+    return launch_rowmix<1>("adjmix_bwd_x", g, A, gx, n, c, t, v, w, k, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {

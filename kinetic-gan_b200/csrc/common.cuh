@@ -46,6 +46,9 @@ constexpr int kNumSMs = 148;   // B200
 // tcgen05 path (tapconv_umma.cu)
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d);      // 0: shape not eligible for the tensor-core path
 int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cudaStream_t stream);
+int64_t tapconv_pack_item_bytes();
+int tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items_dev, int upload,
+                              cudaStream_t stream);
 int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias,
                      const float* add, float* out, cudaStream_t stream);   // -1: not eligible
 

@@ -53,6 +53,29 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
     }
 }
 
+// 16-byte vector variant (numel % 4 == 0, 16-byte aligned pointers)
+__global__ void __launch_bounds__(PT) act_bwd4_k(const float4* __restrict__ go, const float4* __restrict__ o, float4* __restrict__ gz, int64_t n4,
+                                                  int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 y = o[i], g = go[i];
+        float4 r;
+        if (act == KGAN_ACT_LRELU) {
+            r.x = g.x * (y.x > 0.f ? 1.f : 0.2f);
+            r.y = g.y * (y.y > 0.f ? 1.f : 0.2f);
+            r.z = g.z * (y.z > 0.f ? 1.f : 0.2f);
+            r.w = g.w * (y.w > 0.f ? 1.f : 0.2f);
+        } else if (act == KGAN_ACT_TANH) {
+            r.x = g.x * (1.f - y.x * y.x);
+            r.y = g.y * (1.f - y.y * y.y);
+            r.z = g.z * (1.f - y.z * y.z);
+            r.w = g.w * (1.f - y.w * y.w);
+        } else {
+            r = g;
+        }
+        gz[i] = r;
+    }
+}
+
 __global__ void __launch_bounds__(PT) act_bwd_k(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ gz, int64_t numel,
                                                  int act) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
@@ -80,6 +103,62 @@ __global__ void __launch_bounds__(PT) chan_reduce_k(const float* __restrict__ g,
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(out + cc, acc);
+}
+
+// 16-byte vector variant without multiplier (bias gradients): p % 4 == 0, 16-byte aligned g
+__global__ void __launch_bounds__(PT) chan_reduce4_k(const float* __restrict__ g, float* __restrict__ out, int n, int c, int p4, int n_per_slice) {
+    __shared__ float red[32];
+    const int cc = blockIdx.x;
+    const int nbeg = blockIdx.y * n_per_slice, nend = min(n, nbeg + n_per_slice);
+    const unsigned cnt = (unsigned)(nend - nbeg) * (unsigned)p4;          // < 2^31 by the launcher's check
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const unsigned nn = i / (unsigned)p4, q = i - nn * (unsigned)p4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + ((int64_t)(nbeg + nn) * c + cc) * (int64_t)(4 * p4)) + q);
+        a0 += v.x;
+        a1 += v.y;
+        a2 += v.z;
+        a3 += v.w;
+    }
+    const float acc = block_sum((a0 + a1) + (a2 + a3), red);
+    if (threadIdx.x == 0) atomicAdd(out + cc, acc);
+}
+
+// Row-blocked variant for small tables (J <= 4) and planes of at least 64 positions: a thread owns ONE output position, keeps
+// its table entries in registers and walks over the (n, c) planes - no index arithmetic and no table loads per element.
+template <int J>
+__global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                                                         float* __restrict__ out, int64_t rows, int p_in, int p_out) {
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
+    if (q >= p_out) return;
+    int id[J];
+    float w[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int s = __ldg(idx + q * J + j);
+        id[j] = s >= 0 ? s : 0;
+        w[j] = s >= 0 ? __ldg(wgt + q * J + j) : 0.f;
+    }
+    int64_t r = blockIdx.x;
+    for (; r + 3 * (int64_t)gridDim.x < rows; r += 4 * (int64_t)gridDim.x) {      // 4 planes in flight per thread
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* xr = x + (r + u * (int64_t)gridDim.x) * p_in;
+            acc[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[u] = fmaf(w[j], __ldg(xr + id[j]), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) out[(r + u * (int64_t)gridDim.x) * p_out + q] = acc[u];
+    }
+    for (; r < rows; r += gridDim.x) {
+        const float* xr = x + r * p_in;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc = fmaf(w[j], __ldg(xr + id[j]), acc);
+        out[r * p_out + q] = acc;
+    }
 }
 
 __global__ void __launch_bounds__(PT) plane_spmm_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
@@ -240,7 +319,11 @@ extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bi
 
 extern "C" int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, void* stream) {
     KGAN_REQUIRE(gout && out && gz && numel > 0, "act_bwd: bad argument");
-    act_bwd_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(gout, out, gz, numel, act);
+    if ((numel & 3) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gz)) & 15) == 0)
+        act_bwd4_k<<<grid_for(numel / 4), PT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(gout), reinterpret_cast<const float4*>(out),
+                                                                        reinterpret_cast<float4*>(gz), numel / 4, act);
+    else
+        act_bwd_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(gout, out, gz, numel, act);
     return check_launch("act_bwd");
 }
 
@@ -253,13 +336,29 @@ extern "C" int kgan_chan_reduce(const float* g, const float* mul, float* out, in
     if (slices > 65535) slices = 65535;
     const int per = ceil_div(n, slices);
     slices = ceil_div(n, per);
-    chan_reduce_k<<<dim3(c, slices), PT, 0, s>>>(g, mul, out, n, c, p, per);
+    if (!mul && (p & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (int64_t)per * (p / 4) < (1ll << 31))
+        chan_reduce4_k<<<dim3(c, slices), PT, 0, s>>>(g, out, n, c, p / 4, per);
+    else
+        chan_reduce_k<<<dim3(c, slices), PT, 0, s>>>(g, mul, out, n, c, p, per);
     return check_launch("chan_reduce");
 }
 
 extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out, int j,
                                void* stream) {
     KGAN_REQUIRE(x && idx && wgt && out && rows > 0 && p_in > 0 && p_out > 0 && j > 0, "plane_spmm: bad argument");
+    if (j <= 4 && p_out >= 64 && rows >= 64) {
+        const int chunks = ceil_div(p_out, PT);
+        int64_t gx = (int64_t)kNumSMs * 8 / chunks;
+        if (gx > rows) gx = rows;
+        if (gx < 1) gx = 1;
+        const dim3 grid((unsigned)gx, (unsigned)chunks);
+        cudaStream_t s = (cudaStream_t)stream;
+        if (j == 1) plane_spmm_rows_k<1><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        else if (j == 2) plane_spmm_rows_k<2><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        else if (j == 3) plane_spmm_rows_k<3><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        else plane_spmm_rows_k<4><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        return check_launch("plane_spmm");
+    }
     plane_spmm_k<<<grid_for(rows * p_out), PT, 0, (cudaStream_t)stream>>>(x, idx, wgt, out, rows, p_in, p_out, j);
     return check_launch("plane_spmm");
 }

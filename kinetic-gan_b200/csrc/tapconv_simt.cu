@@ -253,6 +253,14 @@ extern "C" int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w
     return tapconv_pack_tf32(*d, w, wp, (cudaStream_t)stream);
 }
 
+extern "C" int64_t kgan_tapconv_pack_item_bytes(void) { return tapconv_pack_item_bytes(); }
+
+extern "C" int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
+                                              int upload, void* stream) {
+    KGAN_REQUIRE(count > 0 && count <= 65535 && descs && w && wp && items, "tapconv_pack_tf32_batched: bad argument");
+    return tapconv_pack_tf32_batched(count, descs, w, wp, items, upload, (cudaStream_t)stream);
+}
+
 extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
                                      const float* bias, const float* add, float* out, void* stream) {
     if (int e = validate(d)) return e;

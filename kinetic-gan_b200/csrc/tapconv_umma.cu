@@ -97,6 +97,36 @@ __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kg
     }
 }
 
+// Batched variant: one launch re-packs every cached weight of a network after the optimizer step (blockIdx.y = item).
+struct PackItem {
+    kgan_tapconv_desc d;
+    const float* w;
+    float* wp;
+    int32_t n_rows, nkt;
+    int64_t total;
+};
+__global__ void __launch_bounds__(256) tapconv_pack_batched_k(const PackItem* __restrict__ items) {
+    const PackItem& it = items[blockIdx.y];
+    const kgan_tapconv_desc& d = it.d;
+    const int n_rows = it.n_rows, nkt = it.nkt;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i & 3);
+        int64_t r = i >> 2;
+        const int row = (int)(r % n_rows);
+        r /= n_rows;
+        const int c = (int)(r & 7);
+        r >>= 3;
+        const int tap = (int)(r % d.ntap);
+        r /= d.ntap;
+        const int ict = (int)(r % nkt);
+        const int g = (int)(r / nkt);
+        const int ic = ict * UK + c * 4 + e;
+        float v = 0.f;
+        if (row < d.co && ic < d.ck) v = __ldg(it.w + (int64_t)g * d.g_w + d.tap_w_off[tap] + (int64_t)row * d.w_oc + (int64_t)ic * d.w_ic);
+        it.wp[i] = __uint_as_float(to_tf32(v));
+    }
+}
+
 // tile id -> (position tile, group, channel split); consecutive ids share the activation tile, so the channel splits and
 // the groups of one position tile (data gradient of the graph conv: 3 groups re-read the same gout) hit in L2
 struct TileCoord {
@@ -379,6 +409,35 @@ int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cud
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     tapconv_pack_k<<<(unsigned)blocks, 256, 0, stream>>>(d, w, wp, p.n_rows, p.nkt);
     return check_launch("tapconv_pack");
+}
+
+int64_t tapconv_pack_item_bytes() { return (int64_t)sizeof(PackItem); }
+
+int tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items_dev, int upload,
+                              cudaStream_t stream) {
+    if (upload) {
+        PackItem* host = new PackItem[count];
+        for (int i = 0; i < count; ++i) {
+            UmmaPlan p;
+            if (!make_plan(descs[i], p)) {
+                delete[] host;
+                set_error("tapconv_pack_batched: item %d not eligible for the tf32 path", i);
+                return 1;
+            }
+            host[i].d = descs[i];
+            host[i].w = w[i];
+            host[i].wp = wp[i];
+            host[i].n_rows = p.n_rows;
+            host[i].nkt = p.nkt;
+            host[i].total = (int64_t)descs[i].groups * p.nkt * descs[i].ntap * p.n_rows * UK;
+        }
+        // pageable source: the copy is staged by the runtime before the call returns, so `host` may be freed right away
+        const cudaError_t e = cudaMemcpyAsync(items_dev, host, sizeof(PackItem) * count, cudaMemcpyHostToDevice, stream);
+        delete[] host;
+        if (e != cudaSuccess) return check_launch("tapconv_pack_batched upload");
+    }
+    tapconv_pack_batched_k<<<dim3(32, (unsigned)count), 256, 0, stream>>>(static_cast<const PackItem*>(items_dev));
+    return check_launch("tapconv_pack_batched");
 }
 
 int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias,

@@ -135,8 +135,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
                 const int32_t* pm = pmap + (int64_t)d.tap_row[tap] * d.p_out + p;
                 const float* xb = in + ((int64_t)nn * d.c_in_total + in_ch0 + d.tap_in_ch[tap] + rslot) * d.p_in;
                 uint32_t dst = st_a + pl.a_bytes + tap * pl.b_bytes + chunk * b_lbo + rslot * 16;
+                // shift form (tma_mode 1): the source position is arithmetic - no dependent position-map load in front of the copies
+                const bool shift_form = d.tma_mode == 1;
+                const int q0 = (int)p + d.tap_shift[tap];
                 if ((d.pmap_vec_mask >> d.tap_row[tap]) & 1) {
-                    const int src = valid ? __ldg(pm) : -1;
+                    const int src = !valid ? -1 : shift_form ? ((q0 >= 0 && q0 < d.p_in) ? q0 : -1) : __ldg(pm);
                     for (int r = rslot; r < pl.n_ic; r += 32, xb += (int64_t)32 * d.p_in, dst += 32 * 16) {
                         const bool ok = src >= 0 && r < b_rows;
                         cp_async16(dst, ok ? xb + src : in, ok ? 16u : 0u);
@@ -144,7 +147,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
                 } else {
                     int src[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) src[e] = valid ? __ldg(pm + e) : -1;
+                    for (int e = 0; e < 4; ++e)
+                        src[e] = !valid ? -1 : shift_form ? ((q0 + e >= 0 && q0 + e < d.p_in) ? q0 + e : -1) : __ldg(pm + e);
                     for (int r = rslot; r < pl.n_ic; r += 32, xb += (int64_t)32 * d.p_in, dst += 32 * 16) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

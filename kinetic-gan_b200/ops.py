@@ -97,15 +97,61 @@ def _shape_sig(*ts):
         _sig = " ".join("x".join(str(d) for d in t.shape) for t in ts)
 
 
-# ---- tf32 tensor-core path: packed weight images are cached per (weight storage, version, geometry) ----------
+# ---- tf32 tensor-core path: packed weight images ----------------------------------------------------------------------
+# Parameters keep a persistent packed image per (storage, geometry): it is refreshed by ONE batched launch after the
+# optimizer step (repack_weights) - inside a captured CUDA graph the tap convolutions then simply read it.  Any other tensor
+# used as a "weight" (the second-order terms of the gradient penalty) is packed on the spot, cached only until the next
+# optimizer step.
 weights_epoch = 0          # bumped by the fused Adam (it rewrites weights behind autograd's version counter)
-_packed = {}
+_packed = {}               # temporaries: key -> (wp, desc, w)
+_persist = {}              # parameters:  key -> _PackedParam
+_batches = {}              # flat-buffer id -> _PackBatch
+
+
+class _PackedParam:
+    __slots__ = ("w", "desc", "cs", "wp", "epoch", "version")
+
+
+class _PackBatch:
+    __slots__ = ("entries", "table", "uploaded", "arrays")
 
 
 def invalidate_packed_weights():
     global weights_epoch
     weights_epoch += 1
     _packed.clear()
+
+
+def clear_temporary_packs():
+    _packed.clear()
+
+
+def repack_weights(flat):
+    """Refresh, with one launch, every persistent packed image whose weight lives in the flat parameter buffer `flat`
+    (called by FlatParams.adam right after the optimizer kernel)."""
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+    ents = [e for e in _persist.values() if lo <= e.w.data_ptr() < hi]
+    if not ents:
+        return
+    b = _batches.get(lo)
+    if b is None:
+        b = _batches[lo] = _PackBatch()
+        b.entries, b.table, b.uploaded, b.arrays = [], None, False, None
+    if len(b.entries) != len(ents) or any(x is not y for x, y in zip(b.entries, ents)):
+        import ctypes as C
+
+        n = len(ents)
+        descs = (_lib.TapConvDesc * n)(*[e.cs for e in ents])
+        wv = (C.c_void_p * n)(*[e.w.data_ptr() for e in ents])
+        wpv = (C.c_void_p * n)(*[e.wp.data_ptr() for e in ents])
+        b.entries, b.arrays, b.uploaded = ents, (descs, wv, wpv), False
+        b.table = torch.empty(n * int(_lib.lib().kgan_tapconv_pack_item_bytes()), device=flat.device, dtype=torch.uint8)
+    descs, wv, wpv = b.arrays
+    _run('tapconv_pack', 0.0, _lib.lib().kgan_tapconv_pack_tf32_batched, len(ents), descs, wv, wpv, b.table.data_ptr(), 0 if b.uploaded else 1,
+         _stream())
+    b.uploaded = True
+    for e in ents:
+        e.epoch, e.version = weights_epoch, e.w._version
 
 
 def _packed_weights(w, desc, cs, l):
@@ -115,13 +161,25 @@ def _packed_weights(w, desc, cs, l):
         numel = cache[cs.n] = int(l.kgan_tapconv_tf32_workspace(cs))
     if numel <= 0:
         return None
+    if isinstance(w, torch.nn.Parameter):
+        key = (w.data_ptr(), id(desc), numel)
+        e = _persist.get(key)
+        if e is None or e.desc is not desc or e.w is not w:
+            e = _PackedParam()
+            e.w, e.desc, e.cs, e.epoch, e.version = w, desc, cs, -1, -1
+            e.wp = torch.empty(numel, device=w.device, dtype=torch.float32)
+            _persist[key] = e
+        if e.epoch != weights_epoch or e.version != w._version:
+            _run('tapconv_pack', 0.0, l.kgan_tapconv_pack_tf32, cs, w.data_ptr(), e.wp.data_ptr(), _stream())
+            e.epoch, e.version = weights_epoch, w._version
+        return e.wp
     key = (w.data_ptr(), w._version, id(desc), numel)
     hit = _packed.get(key)
     if hit is not None and hit[1] is desc:
         return hit[0]
     wp = torch.empty(numel, device=w.device, dtype=torch.float32)
     _run('tapconv_pack', 0.0, l.kgan_tapconv_pack_tf32, cs, w.data_ptr(), wp.data_ptr(), _stream())
-    if w.is_leaf:                             # parameters: reuse until the next optimizer step; temporaries: no caching
+    if w.is_leaf:                             # reuse until the next optimizer step
         if len(_packed) > 256:
             _packed.clear()
         _packed[key] = (wp, desc, w)          # keeps `w` alive so data_ptr cannot be recycled under the key

@@ -65,7 +65,8 @@ class FlatParams:
     def adam(self, lr, b1, b2, eps=1e-8, grad_scale=1.0):
         self.step += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, lr, b1, b2, eps, self.step, grad_scale)
-        ops.invalidate_packed_weights()          # tf32 path: packed weight images are stale now
+        ops.invalidate_packed_weights()          # tf32 path: packed weight images are stale now ...
+        ops.repack_weights(self.flat)            # ... and refreshed for this network's parameters by one batched launch
 
 
 class WGANGPTrainer:
@@ -136,17 +137,20 @@ class WGANGPTrainer:
                 self._g_grads(st["labels"], st["z"])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        ops.invalidate_packed_weights()     # packing kernels must be part of the graphs: replays re-pack the current weights
+        # parameters: their packed tf32 images are persistent buffers refreshed after every optimizer step (ops.repack_weights),
+        # so the graphs only read them.  Images of temporaries (second-order terms) must be packed INSIDE the graphs: drop
+        # whatever the eager warm-up cached so that no capture-time lookup hits a buffer no replay would refresh.
+        ops.clear_temporary_packs()
         gd, gg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         l0 = ops.launches
         with torch.cuda.graph(gd):
             d_out = self._d_grads(st["real"], st["labels"], st["z"], st["alpha"])
         l1 = ops.launches
-        ops.invalidate_packed_weights()
+        ops.clear_temporary_packs()
         with torch.cuda.graph(gg, pool=gd.pool()):
             g_out = self._g_grads(st["labels"], st["z"])
         l2 = ops.launches
-        ops.invalidate_packed_weights()
+        ops.clear_temporary_packs()
         self._graphs = dict(static=st, d=gd, g=gg, d_out=d_out, g_out=g_out, d_launches=l1 - l0, g_launches=l2 - l1)
 
     def d_step(self, real, labels, z, alpha=None, noises=None):

@@ -1,0 +1,90 @@
+"""WGAN-GP trainer on the GPU: two iterations of kinetic-gan.py:137-174 through the CUDA kernels against the golden fixtures
+of the unmodified reference (fp32 path), CUDA-graph replay against eager launches, and the batched refresh of the packed
+tf32 weight images after the fused Adam step."""
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+
+import kgan_b200 as kgan
+from oracle import networks as onet
+from helpers import CASES, draw_noises, inputs, load_golden, sub
+
+pytestmark = pytest.mark.gpu
+ops = kgan.ops
+
+
+def build(cfg):
+    G = kgan.Generator(cfg.latent_dim, cfg.channels, cfg.n_classes, cfg.t_size, cfg.mlp_dim, dataset=cfg.dataset)
+    D = kgan.Discriminator(cfg.channels, cfg.n_classes, cfg.t_size, cfg.latent_dim, dataset=cfg.dataset)
+    G.load_state_dict(onet.synth_params(onet.g_param_shapes(cfg), 1))
+    D.load_state_dict(onet.synth_params(onet.d_param_shapes(cfg), 2))
+    return G.cuda().train(), D.cuda()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_two_iterations_vs_golden_fp32(case):
+    """Same check as tests/test_trainer_cpu.py, but every operator is a libkgan.so kernel (fp32 SIMT path): losses and
+    the parameters after a critic+generator update and a second critic update."""
+    gold, cfg, n = load_golden(case), CASES[case]["cfg"], CASES[case]["n"]
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    kgan.set_precision("fp32")
+    G, D = build(cfg)
+    tr = wg.WGANGPTrainer(G, D, cfg.lr, cfg.b1, cfg.b2, cfg.n_critic, cfg.lambda_gp)
+    dev = lambda ts: [t.cuda() for t in ts]
+    for i in range(2):
+        xi = {k: v.cuda() for k, v in inputs(cfg, n, 10 + i, torch.float32).items()}
+        d_loss, g_loss, _ = tr.iteration(i, xi["real"], xi["labels"], xi["z"], xi["alpha"],
+                                         dev(draw_noises(cfg, n, 100 + 2 * i)), dev(draw_noises(cfg, n, 101 + 2 * i)))
+        ref = float(gold["f64/train/d_loss%d" % i])
+        assert abs(d_loss.item() - ref) < 2e-4 * max(1.0, abs(ref))
+        if i == 0:
+            ref = float(gold["f64/train/g_loss0"])
+            assert abs(g_loss.item() - ref) < 2e-4 * max(1.0, abs(ref))
+    # Adam normalises every gradient to a step of ~lr: compare the parameter DELTAS' bulk, not single elements
+    for net, m in (("g", G), ("d", D)):
+        for k, v in m.state_dict().items():
+            ref = gold["f64/train/%s_after/%s" % (net, k)]
+            mine = sub(v) if v.numel() > 4096 else v.detach().double().cpu().numpy()
+            assert np.abs(mine - ref).max() < 3 * cfg.lr + 1e-6, k          # never further than a few optimizer steps
+            assert np.abs(mine - ref).mean() < 0.25 * cfg.lr + 1e-7, k      # and on average much closer
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_graph_replay_matches_eager(precision):
+    """capture_graphs() + replay == eager launches for the critic update (iterations 1..3: no generator update, and the
+    generator's noise weights are zero at init, so the step is deterministic up to the order of fp32 atomics)."""
+    cfg, n = CASES["ntu_small"]["cfg"], 8
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    kgan.set_precision(precision)
+    try:
+        flats = []
+        for graphs in (False, True):
+            G, D = build(cfg)
+            tr = wg.WGANGPTrainer(G, D, cfg.lr, cfg.b1, cfg.b2, cfg.n_critic, cfg.lambda_gp)
+            x0 = {k: v.cuda() for k, v in inputs(cfg, n, 20, torch.float32).items()}
+            if graphs:
+                tr.capture_graphs(x0["real"], x0["labels"], x0["z"], x0["alpha"])
+            for i in range(1, 4):
+                xi = {k: v.cuda() for k, v in inputs(cfg, n, 20 + i, torch.float32).items()}
+                tr.iteration(i, xi["real"], xi["labels"], xi["z"], xi["alpha"])
+            torch.cuda.synchronize()
+            flats.append(tr.fd.flat.clone())
+            if precision == "tf32":
+                # every persistent packed image equals a fresh pack of the CURRENT weights
+                lib = import_module("kinetic-gan_b200._lib").lib()
+                assert len(ops._persist) > 0
+                for e in ops._persist.values():
+                    fresh = torch.empty_like(e.wp)
+                    assert lib.kgan_tapconv_pack_tf32(e.cs, e.w.data_ptr(), fresh.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+                    torch.cuda.synchronize()
+                    assert torch.equal(fresh, e.wp)
+        a, b = flats
+        # three Adam steps of size lr each: identical up to atomics-order noise amplified by Adam's normalisation
+        assert (a - b).abs().max().item() < 3 * cfg.lr
+        assert (a - b).abs().mean().item() < (2e-2 if precision == "fp32" else 1e-1) * cfg.lr
+    finally:
+        kgan.set_precision("fp32")
+        ops._persist.clear()
+        ops._batches.clear()
