@@ -137,6 +137,12 @@ int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, in
 int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream);
 /* gA[k, v, w] = sum_r x[r, v] * gout[r, k, w]  (gA overwritten) */
 int kgan_adjmix_bwd_a(const float* x, const float* gout, float* gA, int n, int c, int t, int v, int w, int k, void* stream);
+/* Same, restricted to the support of `mask` (K, V, W): gA[k, v, w] = 0 where mask[k, v, w] == 0.  The callers pass the
+ * adjacency A (.) edge_importance itself (generator.py:93, discriminator.py:64): its gradient only flows on into
+ * edge_importance through the product with A, so entries outside the skeleton's support are never used; mask == NULL
+ * computes every entry. */
+int kgan_adjmix_bwd_a_masked(const float* x, const float* gout, const float* mask, float* gA, int n, int c, int t, int v, int w, int k,
+                             void* stream);
 
 /* ---- pointwise epilogues -------------------------------------------------------------------------
  * out[n,c,p] = act( a[n,c,p] + b[n,c,p] + bias[c] + nw[c] * noise[n,p] ); b, bias, (nw,noise) may be NULL.

@@ -43,6 +43,7 @@ _SIGS = {
     "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_adjmix_bwd_a_masked": ([_F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_epilogue_fwd": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
     "kgan_act_bwd": ([_F, _F, _F, C.c_int64, _I, _V], C.c_int),
     "kgan_chan_reduce": ([_F, _F, _F, _I, _I, _I, _V], C.c_int),

@@ -9,6 +9,8 @@
 // All index arithmetic is per block, not per element.
 // A_eff = A (.) edge_importance keeps the skeleton's sparsity (73 of 1875 entries at 25 joints): the forward and dx
 // kernels compact the non-zeros of A in shared memory and touch only those (exact).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kgan {
@@ -193,6 +195,300 @@ __global__ void __launch_bounds__(AT) adjmix_bwd_a_k(const float* __restrict__ x
     for (int i = threadIdx.x; i < nout; i += blockDim.x) atomicAdd(gA + i, s.As[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk-copy pipelined versions (the default whenever a row block is 16-byte addressable).
+//
+// Rows q = (c, t) of one sample are contiguous, so a block of R rows is ONE contiguous range per input partition:
+// an elected thread fetches it with cp.async.bulk (no registers, no per-element instructions) into a double-buffered
+// shared-memory tile while the other buffer is being consumed; an mbarrier carries the completion.
+//
+// rowmix2: consecutive lanes produce CONSECUTIVE outputs (coalesced 4-byte stores, conflict-free shared-memory reads for
+// the self-loop partition, near conflict-free for the neighbour partitions).  The compacted non-zero lists of A are padded
+// with zero coefficients to one length per output partition, so the inner loop has a warp-uniform trip count: no
+// divergence, and the four independent outputs of a thread give the loads instruction-level parallelism.  (The previous
+// kernel ran variable-length dependent load chains per lane: 18-25 % of HBM peak, issue-bound.)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void am_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void am_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void am_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "AM_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra AM_WAIT_DONE;\n\t"
+        "bra AM_WAIT_LOOP;\n\t"
+        "AM_WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void am_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+struct Mix2Plan {
+    int R;              // rows per tile
+    int tiles_per_n;    // ceil(ct / R)
+    int64_t tiles;      // n * tiles_per_n
+    int in_floats;      // floats of one staged tile: ki * R * vi
+    int lc_max;         // upper bound of the padded list length (stride of the final entry table)
+    uint32_t magic;     // ceil(2^32 / wo): e / wo == umulhi(e, magic) for e < 2^20
+    int smem_bytes;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(AT) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
+                                                        int w, int k, const __grid_constant__ Mix2Plan pl) {
+    extern __shared__ __align__(128) float sm[];
+    const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;
+    const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
+    const int maxj = MODE == 0 ? v : k * w;
+    const int nlists = ko * wo;
+    const int R = pl.R;
+    // carve: [2 x in tile][bars 16 B][Lk ko ints (padded to 4)][cnt nlists][ent nlists * lc_max]
+    float* tile0 = sm;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * pl.in_floats);
+    int* Lk = reinterpret_cast<int*>(bars + 2);
+    int* cnt = Lk + 4;
+    MixEntry* ent = reinterpret_cast<MixEntry*>(cnt + ((nlists + 3) & ~3));
+    const uint32_t bar0 = am_smem_u32(bars);
+
+    if (threadIdx.x == 0) {
+        am_mbar_init(bar0, 1);
+        am_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 4) Lk[threadIdx.x] = 0;
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int buf) {      // one thread: ki contiguous ranges of this tile -> shared memory
+        const int64_t nn = tile / pl.tiles_per_n;
+        const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
+        const int rows = min(R, ct - q0);
+        const uint32_t bytes = (uint32_t)rows * vi * 4u;
+        const uint32_t bar = bar0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of this buffer vs the async writes
+        am_mbar_expect_tx(bar, bytes * ki);
+        for (int kin = 0; kin < ki; ++kin)
+            am_bulk_g2s(am_smem_u32(tile0 + buf * pl.in_floats + kin * R * vi), in + ((nn * ki + kin) * (int64_t)ct + q0) * vi, bytes, bar);
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < pl.tiles) issue(blockIdx.x, 0);       // overlaps the list construction below
+
+    // ---- compacted, padded non-zero lists: entry (offset of the input inside the staged tile relative to its row, coefficient)
+    const int lc = pl.lc_max;
+    for (int o = threadIdx.x; o < nlists; o += blockDim.x) {
+        int c = 0;
+        if (MODE == 0) {
+            const int kk = o / w, ww = o - kk * w;
+            for (int vv = 0; vv < v; ++vv) {
+                const float a = __ldg(A + (kk * v + vv) * w + ww);
+                if (a != 0.f) ent[o * lc + c++] = MixEntry{vv, a};
+            }
+            atomicMax(Lk + kk, c);
+        } else {
+            for (int kk = 0; kk < k; ++kk)
+                for (int ww = 0; ww < w; ++ww) {
+                    const float a = __ldg(A + (kk * v + o) * w + ww);
+                    if (a != 0.f) ent[o * lc + c++] = MixEntry{kk * R * w + ww, a};
+                }
+            atomicMax(Lk, c);
+        }
+        cnt[o] = c;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nlists; o += blockDim.x) {
+        const int L = Lk[MODE == 0 ? o / w : 0];
+        for (int j = cnt[o]; j < L; ++j) ent[o * lc + j] = MixEntry{0, 0.f};          // padding: 0 * x[row][0]
+    }
+    __syncthreads();
+    (void)maxj;
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < pl.tiles) issue(next, buf ^ 1);                  // buffer buf^1 was released by the barrier below
+        const int64_t nn = tile / pl.tiles_per_n;
+        const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
+        const int rows = min(R, ct - q0);
+        const unsigned outs = (unsigned)rows * (unsigned)wo;
+        am_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const float* xs = tile0 + buf * pl.in_floats;
+        for (int kb = 0; kb < ko; ++kb) {
+            const int L = Lk[kb];
+            const MixEntry* ek = ent + (size_t)kb * wo * lc;
+            float* ob = out + ((nn * ko + kb) * (int64_t)ct + q0) * wo;
+            for (unsigned e0 = threadIdx.x; e0 < outs; e0 += 4 * AT) {
+                unsigned xb[4], eb[4];
+                float acc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    unsigned e = e0 + u * AT;
+                    e = e < outs ? e : 0u;
+                    const unsigned q = pl.magic ? __umulhi(e, pl.magic) : e;
+                    xb[u] = q * (unsigned)vi;
+                    eb[u] = (e - q * (unsigned)wo) * (unsigned)lc;
+                    acc[u] = 0.f;
+                }
+                for (int j = 0; j < L; ++j) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const MixEntry en = ek[eb[u] + j];
+                        acc[u] = fmaf(en.coef, xs[xb[u] + en.off], acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + u * AT < outs) ob[e0 + u * AT] = acc[u];
+            }
+        }
+        __syncthreads();                                                                // every read of xs[buf] is done
+    }
+}
+
+// gA restricted to the non-zeros of a mask (the adjacency itself: d loss / d edge_importance = gA (.) A, so entries where
+// A == 0 are never used).  lane = (non-zero entry, row group): for every staged row one shared-memory read of x, one of g and
+// one FMA - a few dozen dot products instead of the dense (k*w) x v product, which made the dense kernel FMA/LDS-bound at
+// ~20 % of HBM peak.  Tiles are fetched with cp.async.bulk like above.
+struct DA2Plan {
+    int R, tiles_per_n;
+    int64_t tiles;
+    int x_floats, g_floats;     // staged floats per tile: R * v, k * g_stride
+    int g_stride;               // floats between the partitions of g in shared memory: R * w + pad (12 banks apart)
+    int cap;                    // entry capacity: k * v * w
+    int smem_bytes;
+};
+struct DAEntry {
+    int xoff, goff, oidx;
+};
+constexpr int DA_EPT = 8;       // entries per thread at most: k * v * w <= DA_EPT * AT
+
+__global__ void __launch_bounds__(AT) adjmix_bwd_a2_k(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mask,
+                                                       float* __restrict__ gA, int ct, int v, int w, int k, const __grid_constant__ DA2Plan pl) {
+    extern __shared__ __align__(128) float sm[];
+    const int R = pl.R, stage = pl.x_floats + pl.g_floats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * stage);
+    int* nnz_s = reinterpret_cast<int*>(bars + 2);
+    DAEntry* ent = reinterpret_cast<DAEntry*>(nnz_s + 4);
+    float* red = reinterpret_cast<float*>(ent + pl.cap);
+    const uint32_t bar0 = am_smem_u32(bars);
+    if (threadIdx.x == 0) {
+        am_mbar_init(bar0, 1);
+        am_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *nnz_s = 0;
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile, int buf) {
+        const int64_t nn = tile / pl.tiles_per_n;
+        const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
+        const int rows = min(R, ct - q0);
+        const uint32_t bar = bar0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        am_mbar_expect_tx(bar, (uint32_t)rows * (v + k * w) * 4u);
+        float* xs = sm + buf * stage;
+        am_bulk_g2s(am_smem_u32(xs), x + (nn * (int64_t)ct + q0) * v, (uint32_t)rows * v * 4u, bar);
+        for (int kk = 0; kk < k; ++kk)
+            am_bulk_g2s(am_smem_u32(xs + pl.x_floats + kk * pl.g_stride), g + ((nn * k + kk) * (int64_t)ct + q0) * w, (uint32_t)rows * w * 4u, bar);
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < pl.tiles) issue(blockIdx.x, 0);
+    // entry list in (k, v, w) order: warp 1 compacts the mask with ballots (k*v*w <= a few thousand)
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {
+        const int lane = threadIdx.x - 32, total = k * v * w;
+        int c = 0;
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            const bool nzp = i < total && __ldg(mask + i) != 0.f;
+            const unsigned bal = __ballot_sync(0xffffffffu, nzp);
+            if (nzp) {
+                const int kk = i / (v * w), r = i - kk * v * w, vv = r / w, ww = r - vv * w;
+                ent[c + __popc(bal & ((1u << lane) - 1u))] = DAEntry{vv, kk * pl.g_stride + ww, i};
+            }
+            c += __popc(bal);
+        }
+        if (lane == 0) *nnz_s = c;
+    }
+    __syncthreads();
+    const int nnz = *nnz_s;
+    // nnz <= AT: lane = (entry, row group), the rows of a tile are split over AT / nnz groups.  Otherwise (dense masks): one
+    // row group, up to DA_EPT entries per thread.
+    const bool multi = nnz > AT;
+    const int rg_count = multi ? 1 : (nnz > 0 ? AT / nnz : 1);
+    const int my_e = multi ? threadIdx.x : threadIdx.x % max(nnz, 1), my_rg = multi ? 0 : threadIdx.x / max(nnz, 1);
+    const bool active = nnz > 0 && my_rg < rg_count;
+    float acc[DA_EPT];
+#pragma unroll
+    for (int s = 0; s < DA_EPT; ++s) acc[s] = 0.f;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < pl.tiles) issue(next, buf ^ 1);
+        const int64_t nn = tile / pl.tiles_per_n;
+        const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
+        const int rows = min(R, ct - q0);
+        am_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const float* xs = sm + buf * stage;
+        const float* gs = xs + pl.x_floats;
+        if (!multi) {
+            if (active) {
+                const DAEntry me = ent[my_e];
+                const float* xp = xs + me.xoff;
+                const float* gp = gs + me.goff;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int r = my_rg;
+                for (; r + 3 * rg_count < rows; r += 4 * rg_count) {
+                    a0 = fmaf(xp[r * v], gp[r * w], a0);
+                    a1 = fmaf(xp[(r + rg_count) * v], gp[(r + rg_count) * w], a1);
+                    a2 = fmaf(xp[(r + 2 * rg_count) * v], gp[(r + 2 * rg_count) * w], a2);
+                    a3 = fmaf(xp[(r + 3 * rg_count) * v], gp[(r + 3 * rg_count) * w], a3);
+                }
+                for (; r < rows; r += rg_count) a0 = fmaf(xp[r * v], gp[r * w], a0);
+                acc[0] += (a0 + a1) + (a2 + a3);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < DA_EPT; ++s) {
+                const int e = s * AT + threadIdx.x;
+                if (e < nnz) {
+                    const DAEntry me = ent[e];
+                    const float* xp = xs + me.xoff;
+                    const float* gp = gs + me.goff;
+                    float a0 = 0.f;
+                    for (int r = 0; r < rows; ++r) a0 = fmaf(xp[r * v], gp[r * w], a0);
+                    acc[s] += a0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // CTA-level merge of the row groups, then one atomic per non-zero
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    if (!multi) {
+        if (active) atomicAdd(red + my_e, acc[0]);
+    } else {
+#pragma unroll
+        for (int s = 0; s < DA_EPT; ++s)
+            if (s * AT + threadIdx.x < nnz) red[s * AT + threadIdx.x] = acc[s];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) atomicAdd(gA + ent[i].oidx, red[i]);
+}
+
+__global__ void mask_zero_k(float* __restrict__ gA, const float* __restrict__ mask, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && mask[i] == 0.f) gA[i] = 0.f;
+}
+
 static int check_shape(const char* what, int n, int c, int t, int v, int w, int k, size_t smem_floats) {
     KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "%s: empty dimension", what);
     KGAN_REQUIRE((int64_t)c * t < (1ll << 31) && (int64_t)n * ceil_div64((int64_t)c * t, RB) < (1ll << 31), "%s: too many rows", what);
@@ -229,6 +525,44 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
             return check_launch("adjmix attribute");
         attr = true;
     }
+    // bulk-copy pipelined kernel whenever every row block is 16-byte addressable
+    {
+        const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
+        const int maxj = MODE == 0 ? v : k * w;
+        static const bool force_old = getenv("KGAN_ADJMIX_V1") != nullptr;
+        if (!force_old && k <= 4 && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            Mix2Plan pl;
+            int R = (24 * 1024) / (ki * vi * 4);                 // <= 24 KB per stage: 4 CTAs (2 stages each) per SM
+            R = R / 8 * 8;
+            if (R > 1024) R = 1024;
+            if (R >= ct) R = (ct + 3) / 4 * 4;
+            else R = (ceil_div(ct, ceil_div(ct, R)) + 7) / 8 * 8;   // equal tiles: no sliver at the end of a sample
+            if (R >= 8 && (int64_t)R * wo < (1 << 20) && (int64_t)R * vi * ki < (1 << 20)) {
+                pl.R = R;
+                pl.tiles_per_n = ceil_div(ct, R);
+                pl.tiles = (int64_t)n * pl.tiles_per_n;
+                pl.in_floats = ki * R * vi;
+                pl.lc_max = maxj | 1;
+                pl.magic = wo == 1 ? 0u : (uint32_t)(((1ull << 32) + wo - 1) / wo);      // wo == 1: q = e (2^32 does not fit)
+                const size_t smem2 = (size_t)2 * pl.in_floats * 4 + 16 + 16 + (size_t)((nlists + 3) & ~3) * 4 + (size_t)nlists * pl.lc_max * sizeof(MixEntry);
+                pl.smem_bytes = (int)smem2;
+                if (smem2 <= 100 * 1024) {
+                    static bool attr2 = false;
+                    if (!attr2) {
+                        if (cudaFuncSetAttribute(adjmix_rowmix2_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                            return check_launch("adjmix attribute");
+                        attr2 = true;
+                    }
+                    const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
+                    const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
+                    const int64_t waves = ceil_div64(pl.tiles, cap);
+                    const int64_t grid2 = ceil_div64(pl.tiles, waves);   // every CTA gets `waves` tiles (+-1), all CTAs co-resident
+                    adjmix_rowmix2_k<MODE><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl);
+                    return check_launch(what);
+                }
+            }
+        }
+    }
     const int chunks = (int)ceil_div64((int64_t)ct * wo, AT * 4);
     const int64_t items = (int64_t)n * ko * chunks;
     const int64_t grid = items < 8 * kNumSMs ? items : 8 * kNumSMs;
@@ -247,7 +581,49 @@ extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int 
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
+    return kgan_adjmix_bwd_a_masked(x, g, nullptr, gA, n, c, t, v, w, k, stream);
+}
+
+extern "C" int kgan_adjmix_bwd_a_masked(const float* x, const float* g, const float* mask, float* gA, int n, int c, int t, int v, int w, int k,
+                                        void* stream) {
     KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
+    KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "adjmix_bwd_a: empty dimension");
+    static const bool force_old = getenv("KGAN_ADJMIX_V1") != nullptr;
+    const int64_t ct64 = (int64_t)c * t;
+    if (mask && !force_old && (ct64 * v) % 4 == 0 && (ct64 * w) % 4 == 0 && ct64 < (1ll << 30) &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g)) & 15) == 0) {
+        // sparse path: lane = non-zero of the mask (any number of non-zeros up to k*v*w <= DA_EPT * AT)
+        const int per_row = (v + k * w) * 4;
+        int R = (48 * 1024) / per_row;
+        R = R / 8 * 8;
+        if (R > 1024) R = 1024;
+        if (R >= ct64) R = (int)((ct64 + 3) / 4 * 4);
+        else R = (int)((ceil_div64(ct64, ceil_div64(ct64, R)) + 7) / 8 * 8);
+        if (R >= 8 && k * v * w <= DA_EPT * AT) {
+            DA2Plan pl;
+            pl.R = R;
+            pl.tiles_per_n = (int)ceil_div64(ct64, R);
+            pl.tiles = (int64_t)n * pl.tiles_per_n;
+            pl.x_floats = R * v;
+            pl.g_stride = R * w + ((12 - (R * w) % 32 + 32) % 32);
+            pl.g_floats = k * pl.g_stride;
+            pl.cap = k * v * w;
+            const size_t smem2 = (size_t)2 * (pl.x_floats + pl.g_floats) * 4 + 16 + 16 + (sizeof(DAEntry) + 4) * (size_t)pl.cap;
+            pl.smem_bytes = (int)smem2;
+            static bool attr2 = false;
+            if (!attr2) {
+                if (cudaFuncSetAttribute(adjmix_bwd_a2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+                    return check_launch("adjmix attribute");
+                attr2 = true;
+            }
+            cudaStream_t s2 = (cudaStream_t)stream;
+            if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s2) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
+            const int64_t cap = 2 * kNumSMs;
+            const int64_t grid2 = ceil_div64(pl.tiles, ceil_div64(pl.tiles, cap));
+            adjmix_bwd_a2_k<<<(unsigned)grid2, AT, smem2, s2>>>(x, g, mask, gA, (int)ct64, v, w, k, pl);
+            return check_launch("adjmix_bwd_a");
+        }
+    }
     KGAN_REQUIRE(k * ((v + 3) / 4) * ((w + 3) / 4) <= AT, "adjmix_bwd_a: k*v*w too large");
     const size_t fl = carve_floats(k, v, w, 0, 0);
     if (int e = check_shape("adjmix_bwd_a", n, c, t, v, w, k, fl)) return e;
@@ -259,5 +635,6 @@ extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int 
     const int64_t total = (int64_t)n * bps;
     const int64_t grid = total < 4 * kNumSMs ? total : 4 * kNumSMs;
     adjmix_bwd_a_k<<<(unsigned)grid, AT, fl * 4, s>>>(x, g, gA, ct, v, w, k, bps, (int)total);
+    if (mask) mask_zero_k<<<ceil_div(k * v * w, 256), 256, 0, s>>>(gA, mask, k * v * w);      // same contract as the sparse kernel
     return check_launch("adjmix_bwd_a");
 }

@@ -123,7 +123,7 @@ class AdjMix(Function):
         x, A = ctx.saved_tensors
         go = _c(go)
         gx = AdjMixDx.apply(go, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(x, go, A.shape[0]) if ctx.needs_input_grad[1] else None
+        gA = AdjMixDA.apply(x, go, A.shape[0], A) if ctx.needs_input_grad[1] else None
         return gx, gA
 
 
@@ -138,15 +138,20 @@ class AdjMixDx(Function):
         g, A = ctx.saved_tensors
         h = _c(h)
         gg = AdjMix.apply(h, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(h, g, A.shape[0]) if ctx.needs_input_grad[1] else None
+        gA = AdjMixDA.apply(h, g, A.shape[0], A) if ctx.needs_input_grad[1] else None
         return gg, gA
 
 
 class AdjMixDA(Function):
+    """gA = dM/dA^T g, evaluated on the support of `support` only (the adjacency the product was taken with: its gradient
+    reaches edge_importance through `A * importance`, i.e. multiplied by A, so entries where A == 0 are never used - and a
+    cotangent hA of this output is zero there for the same reason).  `support` is used as a mask, not differentiated."""
+
     @staticmethod
-    def forward(ctx, x, g, k):
+    def forward(ctx, x, g, k, support=None):
+        mask = None if support is None else _c(support.detach())
         ctx.save_for_backward(x, g)
-        return ops.adjmix_bwd_a(_c(x), _c(g), k)
+        return ops.adjmix_bwd_a(_c(x), _c(g), k, mask)
 
     @staticmethod
     def backward(ctx, hA):
@@ -154,7 +159,7 @@ class AdjMixDA(Function):
         hA = _c(hA)
         gx = AdjMixDx.apply(g, hA) if ctx.needs_input_grad[0] else None
         gg = AdjMix.apply(x, hA) if ctx.needs_input_grad[1] else None
-        return gx, gg, None
+        return gx, gg, None, None
 
 
 # ------------------------------------------------------------------------------------------------

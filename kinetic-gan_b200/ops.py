@@ -250,14 +250,16 @@ def adjmix_bwd_x(g, A):
     return gx
 
 
-def adjmix_bwd_a(x, g, k):
-    _chk(x, g)
+def adjmix_bwd_a(x, g, k, mask=None):
+    """gA (k, v, w); with `mask` (k, v, w) only the entries where mask != 0 are computed, the others are 0."""
+    _chk(x, g, mask)
     n, c, t, v = x.shape
     w = g.shape[3]
     assert g.shape[0] == n and g.shape[1] == k * c and g.shape[2] == t
+    assert mask is None or tuple(mask.shape) == (k, v, w)
     gA = torch.empty((k, v, w), device=x.device, dtype=torch.float32)
     _shape_sig(x, g)
-    _run('adjmix_bwd_a', 0.0, _lib.lib().kgan_adjmix_bwd_a, x.data_ptr(), g.data_ptr(), gA.data_ptr(), n, c, t, v, w, k, _stream())
+    _run('adjmix_bwd_a', 0.0, _lib.lib().kgan_adjmix_bwd_a_masked, x.data_ptr(), g.data_ptr(), _ptr(mask), gA.data_ptr(), n, c, t, v, w, k, _stream())
     return gA
 
 

@@ -82,9 +82,10 @@ def adjmix_bwd_x(g, A):
     return torch.einsum("nkctw,kvw->nctv", g.reshape(n, k, kc // k, t, w), A)
 
 
-def adjmix_bwd_a(x, g, k):
+def adjmix_bwd_a(x, g, k, mask=None):
     n, c, t, v = x.shape
-    return torch.einsum("nctv,nkctw->kvw", x, g.reshape(n, k, c, t, g.shape[3]))
+    gA = torch.einsum("nctv,nkctw->kvw", x, g.reshape(n, k, c, t, g.shape[3]))
+    return gA if mask is None else gA * (mask != 0).to(gA.dtype)
 
 
 def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=0):

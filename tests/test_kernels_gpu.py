@@ -61,13 +61,34 @@ def test_tapconv_fwd_dgrad_wgrad(name):
     assert rel(ops.tapconv_wgrad(cu(x), cu(go), geom.fwd, tuple(w.shape)), emu.tapconv_wgrad(dbl(x), dbl(go), geom.fwd, tuple(w.shape))) < TOL
 
 
-@pytest.mark.parametrize("shape", [(3, 5, 7, 25, 25, 3), (2, 4, 3, 11, 25, 3), (2, 3, 4, 16, 16, 3), (5, 7, 1, 1, 1, 3), (2, 2, 5, 5, 11, 2)])
-def test_adjmix(shape):
+ADJ_SHAPES = [(3, 5, 7, 25, 25, 3), (2, 4, 3, 11, 25, 3), (2, 3, 4, 16, 16, 3), (5, 7, 1, 1, 1, 3), (2, 2, 5, 5, 11, 2),
+              # 16-byte addressable row blocks -> the bulk-copy pipelined kernels: several tiles per sample with a ragged tail,
+              # the padded 12-joint level, joint selection 12 -> 5, 25 -> 12, single-joint level, H36M 16 joints
+              (3, 32, 64, 12, 12, 3), (2, 64, 64, 12, 5, 3), (2, 8, 16, 25, 12, 3), (4, 16, 8, 5, 1, 3), (3, 64, 4, 1, 1, 3),
+              (2, 12, 32, 16, 16, 3), (70, 4, 4, 5, 5, 3), (2, 200, 64, 12, 12, 3)]
+
+
+def sparse_adjacency(k, v, w, seed, density=0.15):
+    g = torch.Generator().manual_seed(seed)
+    A = (torch.rand(k, v, w, generator=g) < density).float() * (torch.rand(k, v, w, generator=g) + 0.5)
+    A[0, :min(v, w), :min(v, w)] += torch.eye(min(v, w))
+    return A
+
+
+@pytest.mark.parametrize("shape", ADJ_SHAPES)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_adjmix(shape, sparse):
     n, c, t, v, w, k = shape
-    x, A, g = rnd(n, c, t, v, seed=1), rnd(k, v, w, seed=2), rnd(n, k * c, t, w, seed=3)
+    x, g = rnd(n, c, t, v, seed=1), rnd(n, k * c, t, w, seed=3)
+    A = sparse_adjacency(k, v, w, 2) if sparse else rnd(k, v, w, seed=2)
     assert rel(ops.adjmix_fwd(cu(x), cu(A)), emu.adjmix_fwd(dbl(x), dbl(A))) < TOL
     assert rel(ops.adjmix_bwd_x(cu(g), cu(A)), emu.adjmix_bwd_x(dbl(g), dbl(A))) < TOL
     assert rel(ops.adjmix_bwd_a(cu(x), cu(g), k), emu.adjmix_bwd_a(dbl(x), dbl(g), k)) < TOL
+    # masked form: exactly zero outside the support of the mask, the dense values inside
+    got = ops.adjmix_bwd_a(cu(x), cu(g), k, cu(A))
+    ref = emu.adjmix_bwd_a(dbl(x), dbl(g), k, dbl(A))
+    assert rel(got, ref) < TOL
+    assert (got.cpu()[A == 0] == 0).all()
 
 
 def test_adjmix_large_rows():

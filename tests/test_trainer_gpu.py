@@ -23,6 +23,14 @@ def build(cfg):
     return G.cuda().train(), D.cuda()
 
 
+def loss_ok(mine, gold, key):
+    """Within 2e-4 of the reference's fp64 value, or - after an optimizer step, where Adam turns fp32 rounding noise of
+    near-zero gradients (BatchNorm over 2-3 samples) into steps of size lr - within twice the reference's OWN fp32-vs-fp64
+    distance (ntu_small d_loss1: reference fp32 2.7211 vs fp64 2.6866)."""
+    r64, r32 = float(gold["f64/" + key]), float(gold["f32/" + key])
+    return abs(mine - r64) < max(2e-4 * max(1.0, abs(r64)), 2.0 * abs(r32 - r64))
+
+
 @pytest.mark.parametrize("case", list(CASES))
 def test_two_iterations_vs_golden_fp32(case):
     """Same check as tests/test_trainer_cpu.py, but every operator is a libkgan.so kernel (fp32 SIMT path): losses and
@@ -37,24 +45,25 @@ def test_two_iterations_vs_golden_fp32(case):
         xi = {k: v.cuda() for k, v in inputs(cfg, n, 10 + i, torch.float32).items()}
         d_loss, g_loss, _ = tr.iteration(i, xi["real"], xi["labels"], xi["z"], xi["alpha"],
                                          dev(draw_noises(cfg, n, 100 + 2 * i)), dev(draw_noises(cfg, n, 101 + 2 * i)))
-        ref = float(gold["f64/train/d_loss%d" % i])
-        assert abs(d_loss.item() - ref) < 2e-4 * max(1.0, abs(ref))
+        assert loss_ok(d_loss.item(), gold, "train/d_loss%d" % i), (i, d_loss.item())
         if i == 0:
-            ref = float(gold["f64/train/g_loss0"])
-            assert abs(g_loss.item() - ref) < 2e-4 * max(1.0, abs(ref))
+            assert loss_ok(g_loss.item(), gold, "train/g_loss0"), g_loss.item()
     # Adam normalises every gradient to a step of ~lr: compare the parameter DELTAS' bulk, not single elements
     for net, m in (("g", G), ("d", D)):
         for k, v in m.state_dict().items():
             ref = gold["f64/train/%s_after/%s" % (net, k)]
+            floor = np.abs(gold["f32/train/%s_after/%s" % (net, k)] - ref).mean()     # the reference's own fp32-vs-fp64 distance
             mine = sub(v) if v.numel() > 4096 else v.detach().double().cpu().numpy()
             assert np.abs(mine - ref).max() < 3 * cfg.lr + 1e-6, k          # never further than a few optimizer steps
-            assert np.abs(mine - ref).mean() < 0.25 * cfg.lr + 1e-7, k      # and on average much closer
+            # and on average much closer - except where the gradient is pure rounding noise (a conv bias in front of a
+            # BatchNorm: analytically zero), which Adam turns into +-lr steps in the reference's fp32 run as well
+            assert np.abs(mine - ref).mean() < 0.25 * cfg.lr + 1e-7 + 2.0 * floor, k
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_graph_replay_matches_eager(precision):
     """capture_graphs() + replay == eager launches for the critic update (iterations 1..3: no generator update, and the
-    generator's noise weights are zero at init, so the step is deterministic up to the order of fp32 atomics)."""
+    generator's noise weights are zeroed, so the step is deterministic up to the order of fp32 atomics)."""
     cfg, n = CASES["ntu_small"]["cfg"], 8
     wg = import_module("kinetic-gan_b200.wgan_gp")
     kgan.set_precision(precision)
@@ -62,6 +71,9 @@ def test_graph_replay_matches_eager(precision):
         flats = []
         for graphs in (False, True):
             G, D = build(cfg)
+            with torch.no_grad():               # synth_params draws non-zero noise weights: zero them so that the device-drawn
+                for blk in G.st_gcn_networks:   # noise (different random numbers eagerly and under graph capture) has no effect
+                    blk.noise.weight.zero_()
             tr = wg.WGANGPTrainer(G, D, cfg.lr, cfg.b1, cfg.b2, cfg.n_critic, cfg.lambda_gp)
             x0 = {k: v.cuda() for k, v in inputs(cfg, n, 20, torch.float32).items()}
             if graphs:

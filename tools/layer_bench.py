@@ -90,6 +90,6 @@ for name, (c, t, v, vo) in (("D0", (3, 64, 25, 12)), ("D1", (32, 64, 12, 12)), (
     A = ((torch.rand(3, v, v, device=dev) < 0.15).float() * torch.rand(3, v, v, device=dev) + torch.eye(v, device=dev))[:, :, :vo].contiguous()
     gx = torch.randn(N, 3 * c, t, vo, device=dev)
     bytes_io = 4.0 * (x.numel() + gx.numel())
-    for op, fn in (("mix", lambda: ops.adjmix_fwd(x, A)), ("mix_dx", lambda: ops.adjmix_bwd_x(gx, A)), ("mix_dA", lambda: ops.adjmix_bwd_a(x, gx, 3))):
+    for op, fn in (("mix", lambda: ops.adjmix_fwd(x, A)), ("mix_dx", lambda: ops.adjmix_bwd_x(gx, A)), ("mix_dA", lambda: ops.adjmix_bwd_a(x, gx, 3, A))):
         us = timeit(fn)
         print("%-8s %-6s %9.1f %9.0f" % (name, op, us, bytes_io / us / 1e3))
