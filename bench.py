@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--workload", default="train", choices=["train", "generate"],
+                    help="train: WGAN-GP training samples/s (headline); generate: inference-only generated sequences/s (BASELINE.json configs[4])")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 256 for train, 4096 for generate)")
+    ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,9 +300,170 @@ def run_kgan(args):
     comm.close()
 
 
+GEN_WORKLOAD = "generate.py generator pass, kinetic-gan-mlp8 NTU-120 shape (25x64x3, 120 classes), eval mode, no_grad"
+
+
+def time_oracle_generate(batch, steps, warmup, trunc=None):
+    """The reference's generate.py:93 call on the host cores: eval-mode generator with its per-sample mapping loop
+    (generator.py:84-85), restated in oracle/networks.py."""
+    import numpy as np
+    import torch
+
+    from oracle import networks as onet
+    from oracle.graph import SkeletonTables
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = onet.Config(dataset="ntu", n_classes=120, t_size=64, mlp_dim=8, channels=3)
+    tables = SkeletonTables("ntu")
+    pg = onet.synth_params(onet.g_param_shapes(cfg, tables), 1, reference_init=True)
+    g = torch.Generator().manual_seed(0)
+
+    def once():
+        z = torch.randn(batch, 512, generator=g)
+        labels = torch.randint(0, 120, (batch,), generator=g)
+        nz = [torch.randn(*s, generator=g) for s in onet.noise_shapes(cfg, batch, tables)]
+        tl = torch.as_tensor(np.random.normal(0, 1, (1000, cfg.latent_dim + cfg.n_classes)), dtype=torch.float32) if trunc is not None else None
+        with torch.no_grad():
+            return onet.generator_forward(pg, z, labels, cfg, tables, nz, training=False, trunc=trunc, trunc_latents=tl, per_sample_loop=True)
+
+    for _ in range(warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference_generate(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    b = args.cpu_batch * 8
+    sps, ms, cores = time_oracle_generate(b, args.steps, args.warmup, args.trunc)
+    print(json.dumps({
+        "impl": "reference", "metric": "generated_sequences_per_s", "value": sps, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+        "data": "synthetic", "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": b, "trunc": args.trunc,
+                                        "note": "CPU port of the reference generator call (oracle/networks.py), host cores only"},
+        "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
+                         "sample": "%d generator calls of batch %d after %d warm-up" % (args.steps, b, args.warmup)},
+        "e2e": {"value": sps, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_generate(args):
+    """BASELINE.json configs[4]: inference-only generator throughput, NTU 25x64x3, batch 4096 per GPU; independent replicas
+    (no collective)."""
+    import torch
+
+    import kgan_b200 as kgan
+    from importlib import import_module
+
+    gen = import_module("kinetic-gan_b200.generate")
+    ddp = import_module("kinetic-gan_b200.ddp")
+    ops = kgan.ops
+    comm = ddp.Comm()
+    dev = torch.device("cuda", comm.local_rank)
+    torch.cuda.set_device(dev)
+    kgan.set_precision(args.precision)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    torch.manual_seed(0)
+    G = kgan.Generator(512, 3, 120, 64, mlp_dim=8).to(dev)
+    with torch.no_grad():                       # a trained generator has non-zero noise weights; exercise that path
+        for blk in G.st_gcn_networks:
+            blk.noise.weight.normal_(0, 0.1)
+    runner = gen.GeneratorRunner(G, B, 512, trunc=args.trunc, graphs=not args.no_graphs, device=dev)
+    gcpu = torch.Generator().manual_seed(4321 + comm.rank)
+    POOL = 4
+    host = [dict(z=torch.randn(B, 512, generator=gcpu).pin_memory(), labels=torch.randint(0, 120, (B,), generator=gcpu).pin_memory())
+            for _ in range(POOL)]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step_resident(i):
+        x = resident[i % POOL]
+        return runner(x["z"], x["labels"])
+
+    def step_e2e(i):
+        h = host[i % POOL]
+        runner(h["z"], h["labels"])
+        return runner.to_host()
+
+    def timed(fn, first):
+        comm.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, first + K):
+            fn(i)
+        e1.record()
+        comm.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        comm.all_reduce_max_(ms)
+        return ms.item()
+
+    it = 0
+    for _ in range(W):
+        step_resident(it)
+        it += 1
+    torch.cuda.synchronize()
+    l0 = ops.launches
+    sampler = ClockSampler(physical_index(comm.local_rank))
+    sampler.start()
+    ms_total = timed(step_resident, it)
+    clocks = sampler.stop()
+    launches = ops.launches - l0
+    it += K
+    value = B * comm.world_size * K / (ms_total * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        out = step_e2e(it)
+        it += 1
+        ms_e2e = timed(step_e2e, it)
+        it += K
+        e2e = {"value": B * comm.world_size * K / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": out.numel() * out.element_size()}
+    runner.graphs = False
+    prof = ops.profile_start()
+    for i in range(it, it + 3):
+        step_resident(i)
+    torch.cuda.synchronize()
+    fam = ops.profile_stop(prof)
+    fam.pop("_sites")
+    runner.graphs = not args.no_graphs
+    tensor_peak, hbm_peak, peak_kind = peaks()
+    name, st = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    total_ms = sum(v["ms"] for v in fam.values())
+    achieved = st["flops"] / (st["ms"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": None, "peak_kind": peak_kind + " bf16 sustained", "launches_per_step": st["n"] / 3, "avg_launch_ms": st["ms"] / st["n"],
+                "share_of_kgan_kernel_time": st["ms"] / total_ms, "step_algorithmic_tflops": F_G * value / 1e12 / comm.world_size,
+                "hbm_floor_frac": (value / comm.world_size) * 21.2e3 / (hbm_peak * 1e9),
+                "families": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["n"] / 3,
+                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()}}
+    cpu = None
+    if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
+        sps, ms, cores = time_oracle_generate(args.cpu_batch * 8, 2, 1, args.trunc)
+        cpu = {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
+               "sample": "2 generator calls of batch %d (NTU-120 mlp8, per-sample mapping loop as generator.py:84-85) after 1 warm-up" % (args.cpu_batch * 8)}
+    if comm.rank == 0:
+        print(json.dumps({
+            "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size, "parallelism": "replicas%d" % comm.world_size,
+                       "trunc": args.trunc, "flop_per_sequence": F_G, "cuda_graphs": not args.no_graphs,
+                       "l2_policy": "inputs rotate over a pool of %d batches; the activations of one pass at batch %d exceed the 126 MB L2" % (POOL, B)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+    comm.close()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.batch is None:
+        a.batch = 256 if a.workload == "train" else 4096
+    if a.workload == "generate":
+        run_reference_generate(a) if a.impl == "reference" else run_generate(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_kgan(a)

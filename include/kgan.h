@@ -117,6 +117,9 @@ int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d);
 /* Tensor-core path of kgan_tapconv_wgrad (tcgen05.mma kind::tf32, split-K over CTAs, fp32 atomics into dw).
  * kgan_tapconv_wgrad_tf32_ok(d) -> 1 if the shape is eligible (else use kgan_tapconv_wgrad). */
 int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d);
+/* 1 if kgan_tapconv_wgrad_tf32 will feed both operands with cp.async.bulk.tensor (shift form, output plane a multiple of 32
+ * positions, shifts multiples of 4) instead of per-thread cp.async copies. */
+int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d);
 int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
                             float* dw, int64_t dw_numel, void* stream);
 

@@ -38,6 +38,7 @@ _SIGS = {
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_wgrad_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
     "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
     "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),

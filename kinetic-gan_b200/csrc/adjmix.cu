@@ -244,8 +244,53 @@ struct Mix2Plan {
     int smem_bytes;
 };
 
+// rows q, q + rs, ... of one output column: LT = (padded) length of the column's non-zero list, held in registers
+template <int LT>
+__device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const MixEntry* __restrict__ el, float* __restrict__ ob, int q, int rs, int rows,
+                                         int vi, int wo) {
+    float cf[LT > 0 ? LT : 1];
+    int of[LT > 0 ? LT : 1];
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+        const MixEntry en = el[j];
+        cf[j] = en.coef;
+        of[j] = en.off;
+    }
+    const float* xp = xs + q * vi;
+    float* op = ob + (size_t)q * wo;
+    const int xstep = rs * vi, ostep = rs * wo;
+    for (; q + 3 * rs < rows; q += 4 * rs, xp += 4 * xstep, op += 4 * ostep) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < LT; ++j) {
+            a0 = fmaf(cf[j], xp[of[j]], a0);
+            a1 = fmaf(cf[j], xp[xstep + of[j]], a1);
+            a2 = fmaf(cf[j], xp[2 * xstep + of[j]], a2);
+            a3 = fmaf(cf[j], xp[3 * xstep + of[j]], a3);
+        }
+        op[0] = a0;
+        op[ostep] = a1;
+        op[2 * ostep] = a2;
+        op[3 * ostep] = a3;
+    }
+    for (; q < rows; q += rs, xp += xstep, op += ostep) {
+        float a0 = 0.f;
+#pragma unroll
+        for (int j = 0; j < LT; ++j) a0 = fmaf(cf[j], xp[of[j]], a0);
+        op[0] = a0;
+    }
+}
+__device__ __noinline__ void mix_rows_any(const float* __restrict__ xs, const MixEntry* __restrict__ el, int L, float* __restrict__ ob, int q, int rs,
+                                          int rows, int vi, int wo) {
+    for (; q < rows; q += rs) {
+        float a0 = 0.f;
+        for (int j = 0; j < L; ++j) a0 = fmaf(el[j].coef, xs[q * vi + el[j].off], a0);
+        ob[(size_t)q * wo] = a0;
+    }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(AT) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
+__global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
                                                         int w, int k, const __grid_constant__ Mix2Plan pl) {
     extern __shared__ __align__(128) float sm[];
     const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;
@@ -310,6 +355,12 @@ __global__ void __launch_bounds__(AT) adjmix_rowmix2_k(const float* __restrict__
     }
     __syncthreads();
     (void)maxj;
+    // thread -> (row slot, output column): the first (AT / wo) * wo threads each own ONE output column, so a thread's non-zero
+    // list is loop-invariant (held in registers) and its outputs are rows my_q, my_q + rs, ...; consecutive lanes still write
+    // consecutive addresses
+    const int rs = wo <= AT ? AT / wo : 0;
+    const bool t_active = (int)threadIdx.x < rs * wo;
+    const int my_q = t_active ? (int)threadIdx.x / wo : 0, my_w = t_active ? (int)threadIdx.x - my_q * wo : 0;
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x, ++it) {
@@ -319,35 +370,25 @@ __global__ void __launch_bounds__(AT) adjmix_rowmix2_k(const float* __restrict__
         const int64_t nn = tile / pl.tiles_per_n;
         const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
         const int rows = min(R, ct - q0);
-        const unsigned outs = (unsigned)rows * (unsigned)wo;
         am_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
         const float* xs = tile0 + buf * pl.in_floats;
-        for (int kb = 0; kb < ko; ++kb) {
-            const int L = Lk[kb];
-            const MixEntry* ek = ent + (size_t)kb * wo * lc;
-            float* ob = out + ((nn * ko + kb) * (int64_t)ct + q0) * wo;
-            for (unsigned e0 = threadIdx.x; e0 < outs; e0 += 4 * AT) {
-                unsigned xb[4], eb[4];
-                float acc[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    unsigned e = e0 + u * AT;
-                    e = e < outs ? e : 0u;
-                    const unsigned q = pl.magic ? __umulhi(e, pl.magic) : e;
-                    xb[u] = q * (unsigned)vi;
-                    eb[u] = (e - q * (unsigned)wo) * (unsigned)lc;
-                    acc[u] = 0.f;
+        if (t_active) {
+            for (int kb = 0; kb < ko; ++kb) {
+                const int L = Lk[kb];
+                const MixEntry* el = ent + ((size_t)kb * wo + my_w) * lc;          // this thread's list: same output column for every row
+                float* ob = out + ((nn * ko + kb) * (int64_t)ct + q0) * wo + my_w;
+                switch (L) {
+                    case 0: mix_rows<0>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 1: mix_rows<1>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 2: mix_rows<2>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 3: mix_rows<3>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 4: mix_rows<4>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 5: mix_rows<5>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 6: mix_rows<6>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 7: mix_rows<7>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    case 8: mix_rows<8>(xs, el, ob, my_q, rs, rows, vi, wo); break;
+                    default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo); break;
                 }
-                for (int j = 0; j < L; ++j) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const MixEntry en = ek[eb[u] + j];
-                        acc[u] = fmaf(en.coef, xs[xb[u] + en.off], acc[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (e0 + u * AT < outs) ob[e0 + u * AT] = acc[u];
             }
         }
         __syncthreads();                                                                // every read of xs[buf] is done
@@ -530,7 +571,7 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
         const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
         const int maxj = MODE == 0 ? v : k * w;
         static const bool force_old = getenv("KGAN_ADJMIX_V1") != nullptr;
-        if (!force_old && k <= 4 && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        if (!force_old && k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             Mix2Plan pl;
             int R = (24 * 1024) / (ki * vi * 4);                 // <= 24 KB per stage: 4 CTAs (2 stages each) per SM
             R = R / 8 * 8;

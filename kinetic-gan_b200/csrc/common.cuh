@@ -58,6 +58,7 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
                     float* out, cudaStream_t stream);
 
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d);
+int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);   // TMA-fed variant (tapconv_wgrad_tma.cu)
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
                        cudaStream_t stream);   // -1: not eligible
 

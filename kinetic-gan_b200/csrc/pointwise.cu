@@ -36,20 +36,44 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------------
 // pointwise epilogues
 // ------------------------------------------------------------------------------------------------
+// one warp per (n, c) plane: per-plane constants, 16-byte accesses when the plane allows, no per-element index arithmetic
 __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                                                       const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
-                                                      int n, int c, int p, int act) {
-    const int64_t total = (int64_t)n * c * p;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int pp = (int)(i % p);
-        const int64_t nc = i / p;
-        const int cc = (int)(nc % c);
-        const int64_t nn = nc / c;
-        float v = a[i];
-        if (b) v += b[i];
-        if (bias) v += __ldg(bias + cc);
-        if (nw) v = fmaf(__ldg(nw + cc), __ldg(noise + nn * p + pp), v);
-        out[i] = apply_act(v, act);
+                                                      int n, int c, int p, int act, int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t planes = (int64_t)n * c, tw = (int64_t)gridDim.x * (PT / 32);
+    for (int64_t pl = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5); pl < planes; pl += tw) {
+        const int64_t nn = pl / c;
+        const int cc = (int)(pl - nn * c);
+        const float bs = bias ? __ldg(bias + cc) : 0.f, wn = nw ? __ldg(nw + cc) : 0.f;
+        const int64_t o = pl * p, on = nn * p;
+        if (vec) {
+            const float4* ap = reinterpret_cast<const float4*>(a + o);
+            const float4* bp = reinterpret_cast<const float4*>(b + o);
+            const float4* zp = reinterpret_cast<const float4*>(noise + on);
+            float4* op = reinterpret_cast<float4*>(out + o);
+            for (int i = lane; i < (p >> 2); i += 32) {
+                float4 v = ap[i];
+                if (b) {
+                    const float4 t = bp[i];
+                    v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+                }
+                v.x += bs, v.y += bs, v.z += bs, v.w += bs;
+                if (nw) {
+                    const float4 z = __ldg(zp + i);
+                    v.x = fmaf(wn, z.x, v.x), v.y = fmaf(wn, z.y, v.y), v.z = fmaf(wn, z.z, v.z), v.w = fmaf(wn, z.w, v.w);
+                }
+                op[i] = make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
+            }
+        } else {
+            for (int i = lane; i < p; i += 32) {
+                float v = a[o + i];
+                if (b) v += b[o + i];
+                v += bs;
+                if (nw) v = fmaf(wn, __ldg(noise + on + i), v);
+                out[o + i] = apply_act(v, act);
+            }
+        }
     }
 }
 
@@ -220,68 +244,128 @@ __global__ void __launch_bounds__(PT) label_split_k(const float* __restrict__ g,
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm2d (training): one CTA per channel
+// BatchNorm2d (training).  Statistics: grid (sample chunks, channels) - every warp walks whole (n, c) planes of its channel with
+// 16-byte loads, the CTA's partial sums go to the per-channel accumulators with one atomic each, a one-CTA kernel finalises.
+// Sums are taken around a per-channel shift (the channel's first element), so E[d^2] - E[d]^2 does not cancel.  (The first
+// version used ONE CTA per channel with a 64-bit division per element: 3 CTAs for the generator's 3-channel layers.)
+// Elementwise passes: one warp per (n, c) plane, per-plane constants, no per-element index arithmetic.
 // ------------------------------------------------------------------------------------------------
-constexpr int BNT = 512;
-__global__ void __launch_bounds__(BNT) bn_stats_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
-                                                   float* __restrict__ rm, float* __restrict__ rv, int n, int c, int p, float eps, float mom) {
-    __shared__ float red[32];
-    const int cc = blockIdx.x;
-    const int64_t cnt = (int64_t)n * p;
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) s += __ldg(x + ((i / p) * c + cc) * p + (i % p));
-    const float mu = block_sum(s, red) / (float)cnt;
-    float q = 0.f;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const float dlt = __ldg(x + ((i / p) * c + cc) * p + (i % p)) - mu;
-        q = fmaf(dlt, dlt, q);
-    }
-    const float var = block_sum(q, red) / (float)cnt;
-    if (threadIdx.x == 0) {
-        mean[cc] = mu;
-        rstd[cc] = rsqrtf(var + eps);
-        if (rm) rm[cc] = (1.f - mom) * rm[cc] + mom * mu;
-        if (rv) rv[cc] = (1.f - mom) * rv[cc] + mom * var * ((float)cnt / (float)max((int64_t)1, cnt - 1));
-    }
-}
+constexpr int BNW = PT / 32;      // warps per CTA
 
-__global__ void __launch_bounds__(PT) bn_apply_k(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int n, int c,
-                                                  int p) {
-    const int64_t total = (int64_t)n * c * p;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cc = (int)((i / p) % c);
-        const float sc = __ldg(rstd + cc) * __ldg(gamma + cc);
-        y[i] = fmaf(x[i] - __ldg(mean + cc), sc, __ldg(beta + cc));
-    }
-}
-
-__global__ void __launch_bounds__(BNT) bn_bwd_k(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
-                                                 const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ gx,
-                                                 float* __restrict__ ggamma, float* __restrict__ gbeta, int n, int c, int p) {
+template <bool BWD>
+__global__ void __launch_bounds__(PT) bn_partial_k(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ mean,
+                                                    const float* __restrict__ rstd, float* __restrict__ acc1, float* __restrict__ acc2, int n, int c,
+                                                    int p, int vec) {
     __shared__ float red[32];
-    const int cc = blockIdx.x;
-    const int64_t cnt = (int64_t)n * p;
-    const float mu = mean[cc], rs = rstd[cc];
+    const int cc = blockIdx.y, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * BNW + (threadIdx.x >> 5), tw = gridDim.x * BNW;
+    const float sh = BWD ? __ldg(mean + cc) : __ldg(x + (int64_t)cc * p);
+    const float rs = BWD ? __ldg(rstd + cc) : 1.f;
     float s1 = 0.f, s2 = 0.f;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const int64_t o = ((i / p) * c + cc) * p + (i % p);
-        const float g = __ldg(gy + o);
-        s1 += g;
-        s2 = fmaf(g, (__ldg(x + o) - mu) * rs, s2);
+    for (int nn = gw; nn < n; nn += tw) {
+        const int64_t o = ((int64_t)nn * c + cc) * p;
+        if (vec) {
+            const float4* xp = reinterpret_cast<const float4*>(x + o);
+            const float4* gp = reinterpret_cast<const float4*>(gy + o);
+            for (int i = lane; i < (p >> 2); i += 32) {
+                const float4 v = __ldg(xp + i);
+                if (BWD) {
+                    const float4 g = __ldg(gp + i);
+                    s1 += (g.x + g.y) + (g.z + g.w);
+                    s2 = fmaf(g.x, (v.x - sh) * rs, s2);
+                    s2 = fmaf(g.y, (v.y - sh) * rs, s2);
+                    s2 = fmaf(g.z, (v.z - sh) * rs, s2);
+                    s2 = fmaf(g.w, (v.w - sh) * rs, s2);
+                } else {
+                    const float d0 = v.x - sh, d1 = v.y - sh, d2 = v.z - sh, d3 = v.w - sh;
+                    s1 += (d0 + d1) + (d2 + d3);
+                    s2 = fmaf(d0, d0, s2);
+                    s2 = fmaf(d1, d1, s2);
+                    s2 = fmaf(d2, d2, s2);
+                    s2 = fmaf(d3, d3, s2);
+                }
+            }
+        } else {
+            for (int i = lane; i < p; i += 32) {
+                const float v = __ldg(x + o + i);
+                if (BWD) {
+                    const float g = __ldg(gy + o + i);
+                    s1 += g;
+                    s2 = fmaf(g, (v - sh) * rs, s2);
+                } else {
+                    const float d0 = v - sh;
+                    s1 += d0;
+                    s2 = fmaf(d0, d0, s2);
+                }
+            }
+        }
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
     if (threadIdx.x == 0) {
-        ggamma[cc] = s2;
-        gbeta[cc] = s1;
+        atomicAdd(acc1 + cc, s1);
+        atomicAdd(acc2 + cc, s2);
     }
-    const float m1 = s1 / (float)cnt, m2 = s2 / (float)cnt, sc = gamma[cc] * rs;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const int64_t o = ((i / p) * c + cc) * p + (i % p);
-        const float xh = (__ldg(x + o) - mu) * rs;
-        gx[o] = sc * (__ldg(gy + o) - m1 - xh * m2);
+}
+
+// mean / rstd hold sum(d), sum(d^2) on entry (d = x - first element of the channel)
+__global__ void bn_finalize_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rm,
+                              float* __restrict__ rv, int n, int c, int p, float eps, float mom) {
+    const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= c) return;
+    const float cnt = (float)((int64_t)n * p);
+    const float sh = __ldg(x + (int64_t)cc * p);
+    const float m = mean[cc] / cnt;
+    const float var = fmaxf(rstd[cc] / cnt - m * m, 0.f);
+    const float mu = sh + m;
+    mean[cc] = mu;
+    rstd[cc] = rsqrtf(var + eps);
+    if (rm) rm[cc] = (1.f - mom) * rm[cc] + mom * mu;
+    if (rv) rv[cc] = (1.f - mom) * rv[cc] + mom * var * (cnt / fmaxf(1.f, cnt - 1.f));
+}
+
+// MODE 0: y = (x - mean) * rstd * gamma + beta.   MODE 1: gx = gamma * rstd * (gy - mean(gy) - xhat * mean(gy * xhat)), with the two
+// sums in s1 (= gbeta) and s2 (= ggamma).
+template <int MODE>
+__global__ void __launch_bounds__(PT) bn_elem_k(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ mean,
+                                                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 const float* __restrict__ s1, const float* __restrict__ s2, float* __restrict__ out, int n, int c, int p,
+                                                 int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t planes = (int64_t)n * c, tw = (int64_t)gridDim.x * BNW;
+    const float inv_cnt = 1.f / (float)((int64_t)n * p);
+    for (int64_t pl = (int64_t)blockIdx.x * BNW + (threadIdx.x >> 5); pl < planes; pl += tw) {
+        const int cc = (int)(pl % c);
+        const float mu = __ldg(mean + cc), rs = __ldg(rstd + cc), sc = rs * __ldg(gamma + cc);
+        const float b0 = MODE == 0 ? __ldg(beta + cc) : 0.f;
+        const float m1 = MODE == 1 ? __ldg(s1 + cc) * inv_cnt : 0.f, m2 = MODE == 1 ? __ldg(s2 + cc) * inv_cnt : 0.f;
+        const int64_t o = pl * p;
+        auto f = [&](float xv, float gv) { return MODE == 0 ? fmaf(xv - mu, sc, b0) : sc * (gv - m1 - (xv - mu) * rs * m2); };
+        if (vec) {
+            const float4* xp = reinterpret_cast<const float4*>(x + o);
+            const float4* gp = reinterpret_cast<const float4*>(gy + o);
+            float4* op = reinterpret_cast<float4*>(out + o);
+            for (int i = lane; i < (p >> 2); i += 32) {
+                const float4 v = __ldg(xp + i);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == 1) g = __ldg(gp + i);
+                op[i] = make_float4(f(v.x, g.x), f(v.y, g.y), f(v.z, g.z), f(v.w, g.w));
+            }
+        } else {
+            for (int i = lane; i < p; i += 32) out[o + i] = f(__ldg(x + o + i), MODE == 1 ? __ldg(gy + o + i) : 0.f);
+        }
     }
+}
+
+static inline int bn_vec_ok(int p, const void* a, const void* b, const void* c2) {
+    return (p & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c2)) & 15) == 0;
+}
+static inline dim3 bn_partial_grid(int n, int c) {
+    int s = ceil_div(4 * kNumSMs, c);
+    const int smax = ceil_div(n, BNW);
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    return dim3((unsigned)s, (unsigned)c);
 }
 
 __global__ void __launch_bounds__(PT) adam_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -313,7 +397,9 @@ extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bi
                                  int n, int c, int p, int act, void* stream) {
     KGAN_REQUIRE(a && out && n > 0 && c > 0 && p > 0, "epilogue_fwd: bad argument");
     KGAN_REQUIRE((nw == nullptr) == (noise == nullptr), "epilogue_fwd: nw and noise go together");
-    epilogue_fwd_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act);
+    const int vec = (p & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(noise) |
+                                      reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec);
     return check_launch("epilogue_fwd");
 }
 
@@ -379,21 +465,33 @@ extern "C" int kgan_label_split(const float* g, float* ge, float* gx, int n, int
 extern "C" int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean, float* running_var, int n, int c, int p, float eps,
                              float momentum, void* stream) {
     KGAN_REQUIRE(x && mean && rstd && n > 0 && c > 0 && p > 0, "bn_stats: bad argument");
-    bn_stats_k<<<c, BNT, 0, (cudaStream_t)stream>>>(x, mean, rstd, running_mean, running_var, n, c, p, eps, momentum);
+    KGAN_REQUIRE(c <= 65535, "bn_stats: too many channels");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(mean, 0, sizeof(float) * c, s) != cudaSuccess || cudaMemsetAsync(rstd, 0, sizeof(float) * c, s) != cudaSuccess)
+        return check_launch("bn_stats memset");
+    bn_partial_k<false><<<bn_partial_grid(n, c), PT, 0, s>>>(x, nullptr, nullptr, nullptr, mean, rstd, n, c, p, bn_vec_ok(p, x, nullptr, nullptr));
+    bn_finalize_k<<<ceil_div(c, 128), 128, 0, s>>>(x, mean, rstd, running_mean, running_var, n, c, p, eps, momentum);
     return check_launch("bn_stats");
 }
 
 extern "C" int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int n, int c,
                              int p, void* stream) {
     KGAN_REQUIRE(x && mean && rstd && gamma && beta && y && n > 0 && c > 0 && p > 0, "bn_apply: bad argument");
-    bn_apply_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(x, mean, rstd, gamma, beta, y, n, c, p);
+    bn_elem_k<0><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, (cudaStream_t)stream>>>(x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, y, n, c, p,
+                                                                                  bn_vec_ok(p, x, y, nullptr));
     return check_launch("bn_apply");
 }
 
 extern "C" int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx, float* ggamma,
                            float* gbeta, int n, int c, int p, void* stream) {
     KGAN_REQUIRE(gy && x && mean && rstd && gamma && gx && ggamma && gbeta && n > 0 && c > 0 && p > 0, "bn_bwd: bad argument");
-    bn_bwd_k<<<c, BNT, 0, (cudaStream_t)stream>>>(gy, x, mean, rstd, gamma, gx, ggamma, gbeta, n, c, p);
+    KGAN_REQUIRE(c <= 65535, "bn_bwd: too many channels");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(ggamma, 0, sizeof(float) * c, s) != cudaSuccess || cudaMemsetAsync(gbeta, 0, sizeof(float) * c, s) != cudaSuccess)
+        return check_launch("bn_bwd memset");
+    const int vec = bn_vec_ok(p, x, gy, gx);
+    bn_partial_k<true><<<bn_partial_grid(n, c), PT, 0, s>>>(x, gy, mean, rstd, gbeta, ggamma, n, c, p, vec);
+    bn_elem_k<1><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, s>>>(x, gy, mean, rstd, gamma, nullptr, gbeta, ggamma, gx, n, c, p, vec);
     return check_launch("bn_bwd");
 }
 

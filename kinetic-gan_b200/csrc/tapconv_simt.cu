@@ -283,6 +283,11 @@ extern "C" int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d) {
     return tapconv_tf32_packed_numel(*d) > 0 && tapconv_tma_eligible(*d);
 }
 
+extern "C" int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d) {
+    if (validate(d)) return 0;
+    return tapconv_wgrad_tma_eligible(*d);
+}
+
 extern "C" int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d) {
     if (validate(d)) return 0;
     return tapconv_wgrad_tf32_eligible(*d);

@@ -1,0 +1,280 @@
+// Weight gradient of the tap convolution with TMA-fed operands (tcgen05.mma kind::tf32, fp32 accumulators in TMEM).
+//
+//     dW[tap][oc][ic] = sum_{n, p} gout[n, oc, p] * in[n, (tap, ic), p + shift_tap]          (zero outside the input plane)
+//
+// Same GEMM as tapconv_wgrad_umma.cu - D[M = 128 output channels][N = n_ic input channels] per tap, K = positions, split-K over
+// one wave of CTAs - but for descriptors in shift form (tma_mode 1) whose output plane is a multiple of 32 positions the
+// operands never pass through a register or a per-thread copy instruction: positions are contiguous per channel (NCHW), so a
+// [channels] x [32 positions] box of a 3-D tensor map over (position, sample, channel) IS a K-major operand tile with
+// 128-byte rows, which the TMA unit writes in the canonical SWIZZLE_128B layout (8-row atoms of 1024 bytes).  One elected
+// thread issues 1 + ntap tensor loads per pipeline stage; a temporal tap is a shift of the position coordinate and the TMA
+// unit zero-fills what falls outside the plane.  (The cp.async producers of tapconv_wgrad_umma.cu issue ~1000 16-byte copies
+// per stage and reached 25-35 % of HBM peak.)
+//
+// Both operands reach the tensor core as raw fp32 (truncation to tf32); the epilogue removes the truncation bias exactly as
+// tapconv_wgrad_umma.cu does.  Rows of a box beyond the channel tile read neighbouring channels (or zeros beyond the tensor);
+// they only feed accumulator rows / columns the epilogue never stores.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-9 = epilogue.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "umma.cuh"
+
+namespace kgan {
+
+constexpr int WT_EPI_WARPS = 8;
+constexpr int WT_THREADS = 32 * (2 + WT_EPI_WARPS);
+constexpr float WT_TRUNC_FIX = 1.000706f;        // 1 / (1 - 7.06e-4), see tapconv_wgrad_umma.cu
+constexpr int WT_KT = 32;                        // positions per K tile: one 128-byte swizzled row per channel
+
+struct WgradTmaPlan {
+    int n_ic, ic_tiles, oc_tiles, tmem_cols, stages;
+    int a_rows;              // rows of the gout box (multiple of 8, <= 128)
+    int a_bytes, b_bytes;    // per stage: A tile (always 16 KB: the MMA reads 128 rows), one tap's B tile
+    int kt_per_plane;        // p_out / 32
+    int64_t ktiles;          // n * kt_per_plane
+    int nchunks;
+    int64_t chunk;           // K tiles per split-K chunk
+    int smem_bytes;
+};
+
+int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle128);
+
+static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
+    if (d.tma_mode != 1 || d.w_oc_blk != 0 || d.ntap > 8) return false;
+    if ((d.p_out % WT_KT) || (d.p_in & 3)) return false;
+    for (int t = 0; t < d.ntap; ++t)
+        if (d.tap_shift[t] & 3) return false;                    // box origins must be 16-byte aligned
+    const int64_t total = (int64_t)d.n * d.p_out;
+    if (total < 1024 || total >= (1ll << 31) - WT_KT) return false;
+    int n_max = (512 / d.ntap) / 16 * 16;
+    if (n_max > 256) n_max = 256;
+    if (d.ntap >= 3 && n_max > 128) n_max = 128;
+    p.n_ic = round_up(d.ck, 16) < n_max ? round_up(d.ck, 16) : n_max;
+    p.ic_tiles = ceil_div(d.ck, p.n_ic);
+    p.oc_tiles = ceil_div(d.co, UM);
+    p.tmem_cols = 32;
+    while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
+    if (p.tmem_cols > 512) return false;
+    p.a_rows = d.co >= UM ? UM : round_up(d.co, 8);
+    p.a_bytes = UM * 128;
+    p.b_bytes = p.n_ic * 128;
+    const int stage = p.a_bytes + d.ntap * p.b_bytes;
+    p.stages = (196 * 1024) / stage;
+    if (p.stages > 10) p.stages = 10;
+    if (p.stages < 2) return false;
+    p.kt_per_plane = d.p_out / WT_KT;
+    p.ktiles = (int64_t)d.n * p.kt_per_plane;
+    const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
+    int64_t nchunks = kNumSMs / tiles;                           // one wave
+    if (nchunks > p.ktiles / 4) nchunks = p.ktiles / 4;
+    if (nchunks < 1) nchunks = 1;
+    p.chunk = ceil_div64(p.ktiles, nchunks);
+    p.nchunks = (int)ceil_div64(p.ktiles, p.chunk);
+    if ((int64_t)p.nchunks * d.groups > 65535) return false;
+    p.smem_bytes = p.stages * stage + 1024 + 256;               // + alignment slack + barriers
+    return true;
+}
+
+__device__ __forceinline__ void wt_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+// K-major operand, SWIZZLE_128B (layout type 2): rows of 128 bytes (32 tf32 elements of K), 8-row atoms of 1024 bytes (SBO); LBO unused
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradTmaPlan pl,
+                                                                     const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
+                                                                     float* __restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = pl.stages;
+    const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);           // full[S], empty[S], accfull
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+
+    const int ic0 = blockIdx.x * pl.n_ic, oc0 = blockIdx.y * UM;
+    const int g = blockIdx.z / pl.nchunks, ch = blockIdx.z % pl.nchunks;
+    const int64_t kbeg = (int64_t)ch * pl.chunk, kend = min(pl.ktiles, kbeg + pl.chunk);
+    const int iters = (int)(kend - kbeg);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: one gout box + ntap input boxes per K tile =====
+        if (lane == 0) {
+            const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
+            const uint32_t stage_tx = (uint32_t)pl.a_rows * 128u + (uint32_t)d.ntap * pl.b_bytes;
+            int64_t kt = kbeg;
+            int nn = (int)(kt / pl.kt_per_plane), pt = (int)(kt - (int64_t)nn * pl.kt_per_plane);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
+                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                const int p0 = pt * WT_KT;
+                wt_tma_load_3d(st, &map_g, p0, nn, out_ch0, full0 + 8 * s);
+                for (int tap = 0; tap < d.ntap; ++tap)
+                    wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], nn, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                if (++pt == pl.kt_per_plane) {
+                    pt = 0;
+                    ++nn;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_tf32(pl.n_ic);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                for (int tap = 0; tap < d.ntap; ++tap) {
+                    const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
+#pragma unroll
+                    for (int j = 0; j < WT_KT / 8; ++j)                 // 32 bytes of K per MMA inside the 128-byte swizzled row
+                        umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw128(a_addr + j * 32), smem_desc_k_sw128(b_addr + j * 32), idesc,
+                                  (it > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(accfull);
+        }
+    } else {
+        // ===== epilogue: TMEM lane = output channel row (warp % 4 selects the lane quarter, the other bit the column half) =====
+        mbar_wait(accfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3, colhalf = (warp - 2) >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int oc = oc0 + quarter * 32 + lane;
+        float* wb = dw + (int64_t)g * d.g_w + (int64_t)oc * d.w_oc;
+        bool taps_inner = d.ntap == 3 && d.w_ic == 3;
+        for (int tp = 0; tp < d.ntap; ++tp) taps_inner = taps_inner && d.tap_w_off[tp] == d.tap_w_off[0] + tp;
+        auto fix = [](uint32_t bits) { return __uint_as_float(bits) * WT_TRUNC_FIX; };
+        if (iters > 0) {
+            if (taps_inner) {
+                for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
+                    if (ic0 + col0 >= d.ck) break;                       // warp-uniform
+                    uint32_t r[3][16];
+                    tmem_ld16_nowait(taddr + col0, r[0]);
+                    tmem_ld16_nowait(taddr + pl.n_ic + col0, r[1]);
+                    tmem_ld16_nowait(taddr + 2 * pl.n_ic + col0, r[2]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (oc < d.co) {
+                        float* dst = wb + d.tap_w_off[0] + (int64_t)(ic0 + col0) * 3;
+                        if (ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                            for (int v4 = 0; v4 < 12; ++v4) {
+                                float4 q;
+                                q.x = fix(r[(4 * v4 + 0) % 3][(4 * v4 + 0) / 3]);
+                                q.y = fix(r[(4 * v4 + 1) % 3][(4 * v4 + 1) / 3]);
+                                q.z = fix(r[(4 * v4 + 2) % 3][(4 * v4 + 2) / 3]);
+                                q.w = fix(r[(4 * v4 + 3) % 3][(4 * v4 + 3) / 3]);
+                                atomicAdd(reinterpret_cast<float4*>(dst) + v4, q);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (ic0 + col0 + j < d.ck) {
+#pragma unroll
+                                    for (int tp = 0; tp < 3; ++tp) atomicAdd(dst + j * 3 + tp, fix(r[tp][j]));
+                                }
+                        }
+                    }
+                }
+            } else {
+                for (int tap = 0; tap < d.ntap; ++tap) {
+                    for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
+                        if (ic0 + col0 >= d.ck) break;                   // warp-uniform
+                        uint32_t r[16];
+                        tmem_ld16(taddr + tap * pl.n_ic + col0, r);
+                        if (oc < d.co) {
+                            float* dst = wb + d.tap_w_off[tap] + (int64_t)(ic0 + col0) * d.w_ic;
+                            if (d.w_ic == 1 && ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                                for (int v4 = 0; v4 < 4; ++v4)
+                                    atomicAdd(reinterpret_cast<float4*>(dst) + v4,
+                                              make_float4(fix(r[4 * v4]), fix(r[4 * v4 + 1]), fix(r[4 * v4 + 2]), fix(r[4 * v4 + 3])));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (ic0 + col0 + j < d.ck) atomicAdd(dst + (int64_t)j * d.w_ic, fix(r[j]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols) : "memory");
+    }
+}
+
+int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d) {
+    WgradTmaPlan p;
+    return make_wgrad_tma_plan(d, p) ? 1 : 0;
+}
+
+// -1: not eligible (the caller falls back to the cp.async kernel)
+int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, cudaStream_t stream) {
+    WgradTmaPlan p;
+    if (!make_wgrad_tma_plan(d, p)) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(gout)) & 15) return -1;
+    CUtensorMap map_g, map_x;
+    {
+        const uint64_t gdim[3] = {(uint64_t)d.p_out, (uint64_t)d.n, (uint64_t)d.c_out_total};
+        const uint64_t gstr[2] = {(uint64_t)d.c_out_total * d.p_out * 4, (uint64_t)d.p_out * 4};
+        const uint32_t box[3] = {(uint32_t)WT_KT, 1u, (uint32_t)p.a_rows};
+        if (int e = tma_encode_3d_f32(&map_g, gout, gdim, gstr, box, 1)) return e;
+    }
+    {
+        const uint64_t gdim[3] = {(uint64_t)d.p_in, (uint64_t)d.n, (uint64_t)d.c_in_total};
+        const uint64_t gstr[2] = {(uint64_t)d.c_in_total * d.p_in * 4, (uint64_t)d.p_in * 4};
+        const uint32_t box[3] = {(uint32_t)WT_KT, 1u, (uint32_t)p.n_ic};
+        if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, 1)) return e;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tapconv_wgrad_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return check_launch("tapconv_wgrad_tma attribute");
+        attr_set = true;
+    }
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tma memset");
+    dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
+    tapconv_wgrad_tma_k<<<grid, WT_THREADS, p.smem_bytes, stream>>>(d, p, map_g, map_x, dw);
+    return check_launch("tapconv_wgrad_tma");
+}
+
+}  // namespace kgan

@@ -14,6 +14,8 @@
 //   operands biases every product by -7.06e-4 (measured; 2 x the mean truncation error of a 10-bit mantissa); the
 //   epilogue removes that bias, leaving the zero-mean part (~3e-4 rel-L2, same as round-to-nearest operands).
 // Warp roles: warps 0-7 cp.async producers, then epilogue; warp 8 MMA issuer / TMEM owner.
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace kgan {
@@ -258,13 +260,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
     }
 }
 
+int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);
+int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, cudaStream_t stream);
+
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
     WgradPlan p;
-    return make_wgrad_plan(d, p) ? 1 : 0;
+    return (make_wgrad_plan(d, p) || tapconv_wgrad_tma_eligible(d)) ? 1 : 0;
 }
 
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
                        cudaStream_t stream) {
+    static const bool no_tma = getenv("KGAN_NO_WGRAD_TMA") != nullptr;     // A/B switch: force the cp.async producers
+    if (!no_tma) {
+        const int rt = tapconv_wgrad_tma(d, in, gout, dw, dw_numel, stream);
+        if (rt != -1) return rt;
+    }
     WgradPlan p;
     if (!make_wgrad_plan(d, p)) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(gout)) & 15) {

@@ -50,11 +50,17 @@ GEOMS = {
     "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64),
     "d0_gcn_3ch": (dict(c_in=3, c_out=32, t_in=64, v_in=25, K=3, w_cin=123, w_ic0=120), 4),
     "g6_tcn_3ch": (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 4),
+    "d3_tcn_p160": (dict(c_in=128, c_out=256, t_in=32, v_in=5, K=3), 70),                          # several N / M tiles, split-K over 2+ samples
+    "d1_res_v12": (dict(c_in=32, c_out=64, t_in=64, v_in=12, kt=1), 9),
 }
 
 
 TMA_EXPECTED = {"d1_gcn": (1, 1), "d2_gcn": (1, 1), "d1_tcn_v12": (1, 1), "d1_tcn_v11": (0, 0), "d4_gcn_p80": (1, 1), "d5_gcn_p8": (1, 1),
                 "d2_tcn_unfolded": (1, 1), "d5_tcn_unfolded": (1, 1), "d2_tcn_select": (0, 0), "ragged_k": (0, 0)}
+
+
+WGRAD_TMA_EXPECTED = {"d1_gcn": 1, "d2_gcn": 1, "d1_tcn_v12": 1, "d1_tcn_v11": 0, "d0_gcn_3ch": 1, "d3_tcn_p160": 1, "d1_res_v12": 1,
+                      "d4_gcn_p80": 0, "g6_tcn_3ch": 0}
 
 
 @pytest.mark.parametrize("name", list(GEOMS))
@@ -71,6 +77,9 @@ def test_tapconv_tf32(name):
         lib = import_module("kinetic-gan_b200._lib").lib()
         assert lib.kgan_tapconv_tma_ok(geom.fwd.cstruct(n, 0, 1)) == TMA_EXPECTED[name][0]
         assert lib.kgan_tapconv_tma_ok(geom.dgrad.cstruct(n, 0, 1)) == TMA_EXPECTED[name][1]
+    if name in WGRAD_TMA_EXPECTED:                    # ... and likewise the TMA-fed weight-gradient kernel
+        lib = import_module("kinetic-gan_b200._lib").lib()
+        assert lib.kgan_tapconv_wgrad_tma_ok(geom.fwd.cstruct(n, 0, 1)) == WGRAD_TMA_EXPECTED[name]
     w = rnd(geom.K * geom.c_out, kw.get("w_cin", geom.c_in), geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
     bias = rnd(geom.c_out, seed=3)
     add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)

