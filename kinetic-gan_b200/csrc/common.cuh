@@ -43,6 +43,8 @@ __device__ __forceinline__ int64_t w_oc_offset(const kgan_tapconv_desc& d, int o
 
 constexpr int kNumSMs = 148;   // B200
 
+bool tapconv_is_thin(const kgan_tapconv_desc& d);   // small contraction: streaming SIMT kernel in both precision modes (tapconv_simt.cu)
+
 // tcgen05 path (tapconv_umma.cu)
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d);      // 0: shape not eligible for the tensor-core path
 int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cudaStream_t stream);

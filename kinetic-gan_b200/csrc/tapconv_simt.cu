@@ -183,6 +183,85 @@ __global__ void __launch_bounds__(NT) tapconv_wgrad_simt(const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Thin" layers: ck * ntap * co <= 1024 and co <= 32 (the 3-channel tail of the generator, the critic's first layer on the 3
+// data channels, their data gradients).  As GEMMs they would pad a contraction of 3..32 to a 128 x 16 x 32 tile per tap and
+// spend 20-50x the memory time; here a thread owns one output position, streams the ck * ntap inputs it needs once (lanes run
+// along positions: coalesced), keeps CO accumulators in registers and reads the weights as shared-memory broadcasts.
+// Exact fp32 FMA arithmetic: used in both precision modes.
+// ---------------------------------------------------------------------------------------------
+constexpr int THIN_MAX_W = 1024;
+
+template <int CO>   // accumulators per thread (co <= CO), CO in {4, 8, 16, 32}
+__global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
+                                                       const float* __restrict__ w, const int32_t* __restrict__ pmap,
+                                                       const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ out) {
+    __shared__ __align__(16) float ws[4096];     // ntap * ck * CO <= 4096 (tapconv_is_thin)
+    const int g = blockIdx.y;
+    const float* wg = w + (int64_t)g * d.g_w;
+    // weights -> ws[(tap * ck + ic) * CO + oc], zero for oc >= co
+    for (int i = threadIdx.x; i < d.ntap * d.ck * CO; i += NT) {
+        const int oc = i % CO, r = i / CO, ic = r % d.ck, tap = r / d.ck;
+        ws[i] = oc < d.co ? __ldg(wg + d.tap_w_off[tap] + w_oc_offset(d, oc) + (int64_t)ic * d.w_ic) : 0.f;
+    }
+    __syncthreads();
+    const int in_ch0 = g * d.g_in, out_ch0 = g * d.g_out;
+    const int64_t total = (int64_t)d.n * d.p_out;
+    for (int64_t pos = (int64_t)blockIdx.x * NT + threadIdx.x; pos < total; pos += (int64_t)gridDim.x * NT) {
+        const int nn = (int)(pos / d.p_out), p = (int)(pos - (int64_t)nn * d.p_out);
+        float acc[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[j] = 0.f;
+        const float* xn = in + ((int64_t)nn * d.c_in_total + in_ch0) * d.p_in;
+        for (int tap = 0; tap < d.ntap; ++tap) {
+            const int src = __ldg(pmap + (int64_t)d.tap_row[tap] * d.p_out + p);
+            if (src < 0) continue;
+            const float* xb = xn + (int64_t)d.tap_in_ch[tap] * d.p_in + src;
+            const float* wt = ws + tap * d.ck * CO;
+            for (int ic = 0; ic < d.ck; ++ic) {
+                const float v = __ldg(xb + (int64_t)ic * d.p_in);
+#pragma unroll
+                for (int j4 = 0; j4 < CO / 4; ++j4) {
+                    const float4 q = *reinterpret_cast<const float4*>(wt + ic * CO + 4 * j4);
+                    acc[4 * j4 + 0] = fmaf(v, q.x, acc[4 * j4 + 0]);
+                    acc[4 * j4 + 1] = fmaf(v, q.y, acc[4 * j4 + 1]);
+                    acc[4 * j4 + 2] = fmaf(v, q.z, acc[4 * j4 + 2]);
+                    acc[4 * j4 + 3] = fmaf(v, q.w, acc[4 * j4 + 3]);
+                }
+            }
+        }
+        const int64_t ob = ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+            if (j < d.co) {
+                float v = acc[j];
+                if (bias) v += __ldg(bias + out_ch0 + j);
+                if (add)
+                    v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + j) * d.add_period + p % d.add_period
+                                                   : ob + (int64_t)j * d.p_out));
+                out[ob + (int64_t)j * d.p_out] = apply_act(v, d.act);
+            }
+        }
+    }
+}
+
+bool tapconv_is_thin(const kgan_tapconv_desc& d) {
+    static const bool off = getenv("KGAN_NO_THIN") != nullptr;
+    if (off || d.co > 32 || d.w_oc_blk != 0 || (int64_t)d.n * d.p_out < 4096) return false;
+    const int CO = d.co <= 4 ? 4 : d.co <= 8 ? 8 : d.co <= 16 ? 16 : 32;
+    return (int64_t)d.ck * d.ntap * d.co <= THIN_MAX_W && (int64_t)d.ck * d.ntap * CO <= 4096;
+}
+
+template <int CO>
+static void launch_thin(const kgan_tapconv_desc& d, const float* in, const float* w, const int32_t* pmap, const float* bias, const float* add,
+                        float* out, cudaStream_t s) {
+    const int64_t total = (int64_t)d.n * d.p_out;
+    int64_t gx = ceil_div64(total, NT);
+    const int64_t cap = ceil_div64(8 * kNumSMs, d.groups);
+    if (gx > cap) gx = cap;
+    tapconv_fwd_thin<CO><<<dim3((unsigned)gx, d.groups), NT, 0, s>>>(d, in, w, pmap, bias, add, out);
+}
+
 static int validate(const kgan_tapconv_desc* d) {
     KGAN_REQUIRE(d != nullptr, "tapconv: null descriptor");
     KGAN_REQUIRE(d->n > 0 && d->p_in > 0 && d->p_out > 0 && d->ck > 0 && d->co > 0, "tapconv: empty dimension");
@@ -209,6 +288,13 @@ extern "C" int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, con
     const int64_t total = (int64_t)d->n * d->p_out;
     const int64_t gx = ceil_div64(total, BM);
     KGAN_REQUIRE(gx < (1ll << 31), "tapconv_fwd: too many positions");
+    if (tapconv_is_thin(*d)) {
+        if (d->co <= 4) launch_thin<4>(*d, in, w, pmap, bias, add, out, s);
+        else if (d->co <= 8) launch_thin<8>(*d, in, w, pmap, bias, add, out, s);
+        else if (d->co <= 16) launch_thin<16>(*d, in, w, pmap, bias, add, out, s);
+        else launch_thin<32>(*d, in, w, pmap, bias, add, out, s);
+        return check_launch("tapconv_fwd");
+    }
     if (d->co <= 32) {
         dim3 grid((unsigned)gx, ceil_div(d->co, 32), d->groups);
         tapconv_fwd_simt<2><<<grid, NT, 0, s>>>(*d, in, w, pmap, bias, add, out);

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
 }
 
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d) {
+    if (tapconv_is_thin(d)) return 0;          // small contractions run on the exact streaming kernel (tapconv_simt.cu) in both modes
     UmmaPlan p;
     if (!make_plan(d, p)) return 0;
     return (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;

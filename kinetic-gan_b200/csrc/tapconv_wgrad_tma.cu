@@ -33,8 +33,9 @@ struct WgradTmaPlan {
     int n_ic, ic_tiles, oc_tiles, tmem_cols, stages;
     int a_rows;              // rows of the gout box (multiple of 8, <= 128)
     int a_bytes, b_bytes;    // per stage: A tile (always 16 KB: the MMA reads 128 rows), one tap's B tile
-    int kt_per_plane;        // p_out / 32
-    int64_t ktiles;          // n * kt_per_plane
+    int p_box, n_box;        // a K tile = p_box positions x n_box samples = 32 contraction elements (p_box = 32: one sample)
+    int kt_per_plane;        // p_out / p_box
+    int64_t ktiles;          // ceil(n / n_box) * kt_per_plane
     int nchunks;
     int64_t chunk;           // K tiles per split-K chunk
     int smem_bytes;
@@ -44,11 +45,15 @@ int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3
 
 static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     if (d.tma_mode != 1 || d.w_oc_blk != 0 || d.ntap > 8) return false;
-    if ((d.p_out % WT_KT) || (d.p_in & 3)) return false;
+    if ((d.p_out & 3) || (d.p_in & 3)) return false;
+    p.p_box = WT_KT;
+    while (p.p_box > 4 && (d.p_out % p.p_box)) p.p_box >>= 1;     // planes of 80, 16, 8 ... positions: boxes span several samples
+    p.n_box = WT_KT / p.p_box;
     for (int t = 0; t < d.ntap; ++t)
         if (d.tap_shift[t] & 3) return false;                    // box origins must be 16-byte aligned
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 1024 || total >= (1ll << 31) - WT_KT) return false;
+    if (getenv("KGAN_WGRAD_TMA_BOX32") && p.p_box != WT_KT) return false;      // A/B switch: only whole-sample boxes
     int n_max = (512 / d.ntap) / 16 * 16;
     if (n_max > 256) n_max = 256;
     if (d.ntap >= 3 && n_max > 128) n_max = 128;
@@ -65,8 +70,8 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     p.stages = (196 * 1024) / stage;
     if (p.stages > 10) p.stages = 10;
     if (p.stages < 2) return false;
-    p.kt_per_plane = d.p_out / WT_KT;
-    p.ktiles = (int64_t)d.n * p.kt_per_plane;
+    p.kt_per_plane = d.p_out / p.p_box;
+    p.ktiles = ceil_div64(d.n, p.n_box) * p.kt_per_plane;
     const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
     int64_t nchunks = kNumSMs / tiles;                           // one wave
     if (nchunks > p.ktiles / 4) nchunks = p.ktiles / 4;
@@ -137,10 +142,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                const int p0 = pt * WT_KT;
-                wt_tma_load_3d(st, &map_g, p0, nn, out_ch0, full0 + 8 * s);
+                const int p0 = pt * pl.p_box, n0 = nn * pl.n_box;       // samples beyond n are zero-filled by the TMA unit
+                wt_tma_load_3d(st, &map_g, p0, n0, out_ch0, full0 + 8 * s);
                 for (int tap = 0; tap < d.ntap; ++tap)
-                    wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], nn, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                    wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], n0, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
                 if (++pt == pl.kt_per_plane) {
                     pt = 0;
                     ++nn;
@@ -256,13 +261,13 @@ int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* 
     {
         const uint64_t gdim[3] = {(uint64_t)d.p_out, (uint64_t)d.n, (uint64_t)d.c_out_total};
         const uint64_t gstr[2] = {(uint64_t)d.c_out_total * d.p_out * 4, (uint64_t)d.p_out * 4};
-        const uint32_t box[3] = {(uint32_t)WT_KT, 1u, (uint32_t)p.a_rows};
+        const uint32_t box[3] = {(uint32_t)p.p_box, (uint32_t)p.n_box, (uint32_t)p.a_rows};
         if (int e = tma_encode_3d_f32(&map_g, gout, gdim, gstr, box, 1)) return e;
     }
     {
         const uint64_t gdim[3] = {(uint64_t)d.p_in, (uint64_t)d.n, (uint64_t)d.c_in_total};
         const uint64_t gstr[2] = {(uint64_t)d.c_in_total * d.p_in * 4, (uint64_t)d.p_in * 4};
-        const uint32_t box[3] = {(uint32_t)WT_KT, 1u, (uint32_t)p.n_ic};
+        const uint32_t box[3] = {(uint32_t)p.p_box, (uint32_t)p.n_box, (uint32_t)p.n_ic};
         if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, 1)) return e;
     }
     static bool attr_set = false;

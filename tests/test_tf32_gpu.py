@@ -59,8 +59,9 @@ TMA_EXPECTED = {"d1_gcn": (1, 1), "d2_gcn": (1, 1), "d1_tcn_v12": (1, 1), "d1_tc
                 "d2_tcn_unfolded": (1, 1), "d5_tcn_unfolded": (1, 1), "d2_tcn_select": (0, 0), "ragged_k": (0, 0)}
 
 
+THIN = {"d0_gcn_3ch", "g6_tcn_3ch"}
 WGRAD_TMA_EXPECTED = {"d1_gcn": 1, "d2_gcn": 1, "d1_tcn_v12": 1, "d1_tcn_v11": 0, "d0_gcn_3ch": 1, "d3_tcn_p160": 1, "d1_res_v12": 1,
-                      "d4_gcn_p80": 0, "g6_tcn_3ch": 0}
+                      "d4_gcn_p80": 1, "d5_gcn_p8": 1, "d2_tcn_unfolded": 1, "d5_tcn_unfolded": 1, "g6_tcn_3ch": 0}
 
 
 @pytest.mark.parametrize("name", list(GEOMS))
@@ -100,7 +101,10 @@ def test_tapconv_tf32(name):
     kgan.set_precision("tf32")
     again = ops.tapconv_fwd(xc, wc, geom.fwd)
     d = rel(again, exact.cpu())
-    assert 1e-6 < d < TOL, d
+    if name in THIN:            # small contractions run on the exact streaming kernel in both modes (csrc/tapconv_simt.cu)
+        assert d == 0.0, d
+    else:
+        assert 1e-6 < d < TOL, d
 
 
 def test_critic_tf32_vs_oracle():
