@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "generate"],
                     help="train: WGAN-GP training samples/s (headline); generate: inference-only generated sequences/s (BASELINE.json configs[4])")
-    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 256 for train, 4096 for generate)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 1024 for train, 4096 for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
@@ -162,6 +162,46 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def make_roofline(fam, sites, passes, step_tflops):
+    """Roofline of the dominant kernel family of the step (CUDA events around every launch of `passes` eager steps).
+    achieved = algorithmic bytes (every operand tensor once: inputs + outputs, ops.py `_io`) / summed launch durations for an
+    HBM-bound family, algorithmic FLOPs / durations for a tensor-bound one; the family's arithmetic intensity against the
+    measured ridge point decides which.  `traffic` = measured DRAM bytes per launch of the family's kernel from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json), when present."""
+    tensor_peak, hbm_peak, peak_kind = peaks()
+    name, st = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    sec = st["ms"] * 1e-3
+    tf = st["flops"] / sec / 1e12
+    gbs = st["bytes"] / sec / 1e9
+    ai = st["flops"] / max(st["bytes"], 1.0)
+    ridge = tensor_peak * 1e12 / (hbm_peak * 1e9)
+    total_ms = sum(v["ms"] for v in fam.values())
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f).get(name)
+    except Exception:
+        pass
+    r = {"kernel": name, "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+         "algorithmic_bytes_per_launch": st["bytes"] / st["n"], "traffic": traffic, "peak_kind": peak_kind,
+         "tensor": {"achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "peak_kind": peak_kind + " bf16 sustained"},
+         "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_kind": peak_kind + " copy bandwidth"},
+         "launches_per_step": st["n"] / passes, "avg_launch_ms": st["ms"] / st["n"], "share_of_kgan_kernel_time": st["ms"] / total_ms,
+         "step_algorithmic_tflops": step_tflops,
+         "families": {k: {"ms_per_step": v["ms"] / passes, "launches_per_step": v["n"] / passes,
+                          "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None,
+                          "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] else None} for k, v in fam.items()},
+         "top_sites": [{"site": k, "ms_per_step": round(v["ms"] / passes, 3), "launches_per_step": v["n"] / passes,
+                        "us_per_launch": round(v["ms"] / v["n"] * 1e3, 1),
+                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] else None}
+                       for k, v in sorted(sites.items(), key=lambda kv: -kv[1]["ms"])[:40]]}
+    if ai < ridge:
+        r.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak)
+    else:
+        r.update(bound="tensor", achieved=tf, peak=tensor_peak, unit="TFLOP/s", frac=tf / tensor_peak)
+    return r
+
+
 def run_kgan(args):
     import torch
 
@@ -262,21 +302,7 @@ def run_kgan(args):
     sites = fam.pop("_sites")
     tr.use_graphs = graphs
     it += 5
-    tensor_peak, hbm_peak, peak_kind = peaks()
-    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    name, st = top
-    achieved = st["flops"] / (st["ms"] * 1e-3) / 1e12
-    total_ms = sum(v["ms"] for v in fam.values())
-    roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None, "peak_kind": peak_kind + " bf16 sustained",
-                "launches_per_step": st["n"] / 5, "avg_launch_ms": st["ms"] / st["n"],
-                "share_of_kgan_kernel_time": st["ms"] / total_ms,
-                "step_algorithmic_tflops": FLOP_PER_SAMPLE * value / 1e12 / comm.world_size,
-                "families": {k: {"ms_per_step": v["ms"] / 5, "launches_per_step": v["n"] / 5,
-                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()},
-                "top_sites": [{"site": k, "ms_per_step": round(v["ms"] / 5, 3), "launches_per_step": v["n"] / 5,
-                               "us_per_launch": round(v["ms"] / v["n"] * 1e3, 1)}
-                              for k, v in sorted(sites.items(), key=lambda kv: -kv[1]["ms"])[:40]]}
+    roofline = make_roofline(fam, sites, 5, FLOP_PER_SAMPLE * value / 1e12 / comm.world_size)
 
     cpu = None
     if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
@@ -429,18 +455,12 @@ def run_generate(args):
         step_resident(i)
     torch.cuda.synchronize()
     fam = ops.profile_stop(prof)
-    fam.pop("_sites")
+    sites = fam.pop("_sites")
     runner.graphs = not args.no_graphs
-    tensor_peak, hbm_peak, peak_kind = peaks()
-    name, st = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    total_ms = sum(v["ms"] for v in fam.values())
-    achieved = st["flops"] / (st["ms"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": None, "peak_kind": peak_kind + " bf16 sustained", "launches_per_step": st["n"] / 3, "avg_launch_ms": st["ms"] / st["n"],
-                "share_of_kgan_kernel_time": st["ms"] / total_ms, "step_algorithmic_tflops": F_G * value / 1e12 / comm.world_size,
-                "hbm_floor_frac": (value / comm.world_size) * 21.2e3 / (hbm_peak * 1e9),
-                "families": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["n"] / 3,
-                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None} for k, v in fam.items()}}
+    roofline = make_roofline(fam, sites, 3, F_G * value / 1e12 / comm.world_size)
+    # lower bound of the whole pass: z + output (+ noise) = ~21 KB of compulsory HBM traffic per sequence
+    roofline["pass_hbm_floor_frac"] = (value / comm.world_size) * 21.2e3 / (peaks()[1] * 1e9)
+
     cpu = None
     if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
         sps, ms, cores = time_oracle_generate(args.cpu_batch * 8, 2, 1, args.trunc)
@@ -460,7 +480,7 @@ def run_generate(args):
 if __name__ == "__main__":
     a = parse()
     if a.batch is None:
-        a.batch = 256 if a.workload == "train" else 4096
+        a.batch = 1024 if a.workload == "train" else 4096
     if a.workload == "generate":
         run_reference_generate(a) if a.impl == "reference" else run_generate(a)
     elif a.impl == "reference":

@@ -192,20 +192,27 @@ __global__ void __launch_bounds__(NT) tapconv_wgrad_simt(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 constexpr int THIN_MAX_W = 1024;
 
-template <int CO>   // accumulators per thread (co <= CO), CO in {4, 8, 16, 32}
+// groups that read the same input channels (g_in == 0: the K partitions of a graph conv's data gradient) are merged into one pass:
+// accumulator a = (group, oc), so the input is streamed once instead of once per group
+static inline int thin_merge(const kgan_tapconv_desc& d) { return (d.groups > 1 && d.g_in == 0 && d.groups * d.co <= 16) ? d.groups : 1; }
+
+template <int CO>   // accumulators per thread (ng * co <= CO), CO in {4, 8, 16}
 __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
                                                        const float* __restrict__ w, const int32_t* __restrict__ pmap,
-                                                       const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ out) {
+                                                       const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ out,
+                                                       int ng) {
     __shared__ __align__(16) float ws[4096];     // ntap * ck * CO <= 4096 (tapconv_is_thin)
-    const int g = blockIdx.y;
-    const float* wg = w + (int64_t)g * d.g_w;
-    // weights -> ws[(tap * ck + ic) * CO + oc], zero for oc >= co
+    __shared__ int och[CO];                      // output channel of accumulator a, -1: unused
+    const int g0 = blockIdx.y * ng, na = ng * d.co;
+    // weights -> ws[(tap * ck + ic) * CO + a], zero for a >= na
     for (int i = threadIdx.x; i < d.ntap * d.ck * CO; i += NT) {
-        const int oc = i % CO, r = i / CO, ic = r % d.ck, tap = r / d.ck;
-        ws[i] = oc < d.co ? __ldg(wg + d.tap_w_off[tap] + w_oc_offset(d, oc) + (int64_t)ic * d.w_ic) : 0.f;
+        const int a = i % CO, r = i / CO, ic = r % d.ck, tap = r / d.ck;
+        const int gg = a / d.co, oc = a - gg * d.co;
+        ws[i] = a < na ? __ldg(w + (int64_t)(g0 + gg) * d.g_w + d.tap_w_off[tap] + w_oc_offset(d, oc) + (int64_t)ic * d.w_ic) : 0.f;
     }
+    if (threadIdx.x < CO) och[threadIdx.x] = (int)threadIdx.x < na ? (g0 + threadIdx.x / d.co) * d.g_out + threadIdx.x % d.co : -1;
     __syncthreads();
-    const int in_ch0 = g * d.g_in, out_ch0 = g * d.g_out;
+    const int in_ch0 = g0 * d.g_in;
     const int64_t total = (int64_t)d.n * d.p_out;
     for (int64_t pos = (int64_t)blockIdx.x * NT + threadIdx.x; pos < total; pos += (int64_t)gridDim.x * NT) {
         const int nn = (int)(pos / d.p_out), p = (int)(pos - (int64_t)nn * d.p_out);
@@ -218,6 +225,7 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
             if (src < 0) continue;
             const float* xb = xn + (int64_t)d.tap_in_ch[tap] * d.p_in + src;
             const float* wt = ws + tap * d.ck * CO;
+#pragma unroll 4
             for (int ic = 0; ic < d.ck; ++ic) {
                 const float v = __ldg(xb + (int64_t)ic * d.p_in);
 #pragma unroll
@@ -230,16 +238,16 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
                 }
             }
         }
-        const int64_t ob = ((int64_t)nn * d.c_out_total + out_ch0) * d.p_out + p;
+        const int pa = d.add_period ? p % d.add_period : 0;
 #pragma unroll
         for (int j = 0; j < CO; ++j) {
-            if (j < d.co) {
+            const int c = och[j];
+            if (c >= 0) {
+                const int64_t o = ((int64_t)nn * d.c_out_total + c) * d.p_out + p;
                 float v = acc[j];
-                if (bias) v += __ldg(bias + out_ch0 + j);
-                if (add)
-                    v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + j) * d.add_period + p % d.add_period
-                                                   : ob + (int64_t)j * d.p_out));
-                out[ob + (int64_t)j * d.p_out] = apply_act(v, d.act);
+                if (bias) v += __ldg(bias + c);
+                if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + c) * d.add_period + pa : o));
+                out[o] = apply_act(v, d.act);
             }
         }
     }
@@ -247,19 +255,21 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
 
 bool tapconv_is_thin(const kgan_tapconv_desc& d) {
     static const bool off = getenv("KGAN_NO_THIN") != nullptr;
-    if (off || d.co > 32 || d.w_oc_blk != 0 || (int64_t)d.n * d.p_out < 4096) return false;
-    const int CO = d.co <= 4 ? 4 : d.co <= 8 ? 8 : d.co <= 16 ? 16 : 32;
-    return (int64_t)d.ck * d.ntap * d.co <= THIN_MAX_W && (int64_t)d.ck * d.ntap * CO <= 4096;
+    const int na = thin_merge(d) * d.co;
+    if (off || na > 16 || d.w_oc_blk != 0 || (int64_t)d.n * d.p_out < 4096) return false;
+    const int CO = na <= 4 ? 4 : na <= 8 ? 8 : 16;
+    return (int64_t)d.ck * d.ntap * na <= THIN_MAX_W && (int64_t)d.ck * d.ntap * CO <= 4096;
 }
 
 template <int CO>
 static void launch_thin(const kgan_tapconv_desc& d, const float* in, const float* w, const int32_t* pmap, const float* bias, const float* add,
                         float* out, cudaStream_t s) {
+    const int ng = thin_merge(d), gy = d.groups / ng;
     const int64_t total = (int64_t)d.n * d.p_out;
     int64_t gx = ceil_div64(total, NT);
-    const int64_t cap = ceil_div64(8 * kNumSMs, d.groups);
+    const int64_t cap = ceil_div64(8 * kNumSMs, gy);
     if (gx > cap) gx = cap;
-    tapconv_fwd_thin<CO><<<dim3((unsigned)gx, d.groups), NT, 0, s>>>(d, in, w, pmap, bias, add, out);
+    tapconv_fwd_thin<CO><<<dim3((unsigned)gx, gy), NT, 0, s>>>(d, in, w, pmap, bias, add, out, ng);
 }
 
 static int validate(const kgan_tapconv_desc* d) {
@@ -289,10 +299,10 @@ extern "C" int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, con
     const int64_t gx = ceil_div64(total, BM);
     KGAN_REQUIRE(gx < (1ll << 31), "tapconv_fwd: too many positions");
     if (tapconv_is_thin(*d)) {
-        if (d->co <= 4) launch_thin<4>(*d, in, w, pmap, bias, add, out, s);
-        else if (d->co <= 8) launch_thin<8>(*d, in, w, pmap, bias, add, out, s);
-        else if (d->co <= 16) launch_thin<16>(*d, in, w, pmap, bias, add, out, s);
-        else launch_thin<32>(*d, in, w, pmap, bias, add, out, s);
+        const int na = thin_merge(*d) * d->co;
+        if (na <= 4) launch_thin<4>(*d, in, w, pmap, bias, add, out, s);
+        else if (na <= 8) launch_thin<8>(*d, in, w, pmap, bias, add, out, s);
+        else launch_thin<16>(*d, in, w, pmap, bias, add, out, s);
         return check_launch("tapconv_fwd");
     }
     if (d->co <= 32) {
@@ -328,15 +338,33 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
     return check_launch("tapconv_wgrad");
 }
 
+// Groups that read the same input channels and write adjacent output channel blocks (the K partitions of a graph conv's data
+// gradient: g_in == 0, g_out == co) are ONE GEMM over groups * co output channels whose weight rows are addressed block-wise
+// (w_oc_blk): the activation tile is fetched once instead of once per group.  Applied to every descriptor entering the tensor-core
+// forward path (workspace size, packing, launch), so the packed image and the kernel always agree.
+static kgan_tapconv_desc merge_groups(const kgan_tapconv_desc& d) {
+    static const bool off = getenv("KGAN_NO_GROUP_MERGE") != nullptr;
+    if (off || d.groups <= 1 || d.g_in != 0 || d.g_out != d.co || d.w_oc_blk != 0) return d;
+    kgan_tapconv_desc m = d;
+    m.w_oc_blk = d.co;
+    m.w_ocblk = d.g_w;
+    m.co = d.groups * d.co;
+    m.groups = 1;
+    m.g_out = 0;
+    m.g_w = 0;
+    return m;
+}
+
 extern "C" int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d) {
     if (validate(d)) return -1;
-    return tapconv_tf32_packed_numel(*d);
+    if (tapconv_is_thin(*d)) return 0;         // small contractions run on the exact streaming kernel in both precision modes
+    return tapconv_tf32_packed_numel(merge_groups(*d));
 }
 
 extern "C" int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(w && wp, "tapconv_pack_tf32: null pointer");
-    return tapconv_pack_tf32(*d, w, wp, (cudaStream_t)stream);
+    return tapconv_pack_tf32(merge_groups(*d), w, wp, (cudaStream_t)stream);
 }
 
 extern "C" int64_t kgan_tapconv_pack_item_bytes(void) { return tapconv_pack_item_bytes(); }
@@ -344,7 +372,12 @@ extern "C" int64_t kgan_tapconv_pack_item_bytes(void) { return tapconv_pack_item
 extern "C" int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
                                               int upload, void* stream) {
     KGAN_REQUIRE(count > 0 && count <= 65535 && descs && w && wp && items, "tapconv_pack_tf32_batched: bad argument");
-    return tapconv_pack_tf32_batched(count, descs, w, wp, items, upload, (cudaStream_t)stream);
+    if (!upload) return tapconv_pack_tf32_batched(count, descs, w, wp, items, 0, (cudaStream_t)stream);
+    kgan_tapconv_desc* merged = new kgan_tapconv_desc[count];
+    for (int i = 0; i < count; ++i) merged[i] = merge_groups(descs[i]);
+    const int rc = tapconv_pack_tf32_batched(count, merged, w, wp, items, 1, (cudaStream_t)stream);
+    delete[] merged;
+    return rc;
 }
 
 extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap,
@@ -352,11 +385,12 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
     static const bool no_tma = getenv("KGAN_NO_TMA") != nullptr;      // A/B switch for benchmarks: force the gather kernel
-    if (d->tma_mode != 0 && !no_tma) {
-        const int rt = tapconv_fwd_tma(*d, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+    const kgan_tapconv_desc m = merge_groups(*d);
+    if (m.tma_mode != 0 && !no_tma) {
+        const int rt = tapconv_fwd_tma(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
         if (rt != -1) return rt;
     }
-    int r = tapconv_fwd_tf32(*d, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+    int r = tapconv_fwd_tf32(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_fwd_tf32: shape not eligible for the tensor-core path (kgan_tapconv_tf32_workspace() == 0)");
         return 1;
@@ -365,8 +399,9 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
 }
 
 extern "C" int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d) {
-    if (validate(d)) return 0;
-    return tapconv_tf32_packed_numel(*d) > 0 && tapconv_tma_eligible(*d);
+    if (validate(d) || tapconv_is_thin(*d)) return 0;
+    const kgan_tapconv_desc m = merge_groups(*d);
+    return tapconv_tf32_packed_numel(m) > 0 && tapconv_tma_eligible(m);
 }
 
 extern "C" int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d) {

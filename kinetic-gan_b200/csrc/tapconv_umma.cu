@@ -43,8 +43,7 @@ struct UmmaPlan {
 // Channel tiling shared by every tensor-core forward kernel (this file and tapconv_tma.cu): it fixes the layout of the
 // packed weight image, so it depends on the descriptor only.
 bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, int* n_rows, int* tmem_cols, int* nkt) {
-    if (d.w_oc_blk != 0) return false;                      // any channel count: ragged K and N are zero padded
-    const int64_t total = (int64_t)d.n * d.p_out;
+    const int64_t total = (int64_t)d.n * d.p_out;                // any channel count: ragged K and N are zero padded
     if (total < 256 || total >= (1ll << 31) - UM) return false;
     const int64_t m_tiles = ceil_div64(total, UM);
     if (m_tiles * d.groups > (1 << 24)) return false;
@@ -92,7 +91,7 @@ __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kg
         const int g = (int)(r / nkt);
         const int ic = ict * UK + c * 4 + e;
         float v = 0.f;
-        if (row < d.co && ic < d.ck) v = __ldg(w + (int64_t)g * d.g_w + d.tap_w_off[tap] + (int64_t)row * d.w_oc + (int64_t)ic * d.w_ic);
+        if (row < d.co && ic < d.ck) v = __ldg(w + (int64_t)g * d.g_w + d.tap_w_off[tap] + w_oc_offset(d, row) + (int64_t)ic * d.w_ic);
         wp[i] = __uint_as_float(to_tf32(v));
     }
 }
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(256) tapconv_pack_batched_k(const PackItem* __
         const int g = (int)(r / nkt);
         const int ic = ict * UK + c * 4 + e;
         float v = 0.f;
-        if (row < d.co && ic < d.ck) v = __ldg(it.w + (int64_t)g * d.g_w + d.tap_w_off[tap] + (int64_t)row * d.w_oc + (int64_t)ic * d.w_ic);
+        if (row < d.co && ic < d.ck) v = __ldg(it.w + (int64_t)g * d.g_w + d.tap_w_off[tap] + w_oc_offset(d, row) + (int64_t)ic * d.w_ic);
         it.wp[i] = __uint_as_float(to_tf32(v));
     }
 }
@@ -393,7 +392,6 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
 }
 
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d) {
-    if (tapconv_is_thin(d)) return 0;          // small contractions run on the exact streaming kernel (tapconv_simt.cu) in both modes
     UmmaPlan p;
     if (!make_plan(d, p)) return 0;
     return (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;

@@ -45,15 +45,16 @@ int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3
 
 static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     if (d.tma_mode != 1 || d.w_oc_blk != 0 || d.ntap > 8) return false;
-    if ((d.p_out & 3) || (d.p_in & 3)) return false;
+    // Planes below 32 positions would need boxes of p_box positions x n_box samples per 128-byte row.  Measured on B200 (tools/
+    // probe_wgrad_tma.py): with a 128-byte swizzle mode the TMA unit faults ("illegal memory access") for every box whose innermost
+    // extent is below 128 bytes (16 x 2, 8 x 4 and 4 x 8 all fail, 32 x 1 works) - those layers stay on the cp.async producers.
+    if ((d.p_out % WT_KT) || (d.p_in & 3)) return false;
     p.p_box = WT_KT;
-    while (p.p_box > 4 && (d.p_out % p.p_box)) p.p_box >>= 1;     // planes of 80, 16, 8 ... positions: boxes span several samples
-    p.n_box = WT_KT / p.p_box;
+    p.n_box = 1;
     for (int t = 0; t < d.ntap; ++t)
         if (d.tap_shift[t] & 3) return false;                    // box origins must be 16-byte aligned
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 1024 || total >= (1ll << 31) - WT_KT) return false;
-    if (getenv("KGAN_WGRAD_TMA_BOX32") && p.p_box != WT_KT) return false;      // A/B switch: only whole-sample boxes
     int n_max = (512 / d.ntap) / 16 * 16;
     if (n_max > 256) n_max = 256;
     if (d.ntap >= 3 && n_max > 128) n_max = 128;

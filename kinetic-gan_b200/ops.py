@@ -56,23 +56,31 @@ def profile_stop(prof):
     _prof = None
     torch.cuda.synchronize()
     out, sites = {}, {}
-    for name, flops, e0, e1, sig in prof:
+    for name, flops, e0, e1, sig, nbytes in prof:
         ms = e0.elapsed_time(e1)
         for table, key in ((out, name), (sites, name + " " + sig)):
-            d = table.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
+            d = table.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += ms
             d["n"] += 1
             d["flops"] += flops
+            d["bytes"] += nbytes
     out["_sites"] = sites
     return out
 
 
 _sig = ""          # shape signature of the launch being issued (profiling only)
+_nbytes = 0.0      # algorithmic bytes of the launch being issued: every operand tensor read or written once (profiling only)
+
+
+def _io(*ts):
+    global _nbytes
+    if _prof is not None:
+        _nbytes = float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
 def _run(family, flops, fn, *args):
     """One kernel launch through the C ABI (+ CUDA events around it when profiling)."""
-    global _sig
+    global _sig, _nbytes
     if _prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -80,8 +88,8 @@ def _run(family, flops, fn, *args):
     _count()
     if _prof is not None:
         e1.record()
-        _prof.append((family, flops, e0, e1, _sig))
-        _sig = ""
+        _prof.append((family, flops, e0, e1, _sig, _nbytes))
+        _sig, _nbytes = "", 0.0
 
 
 def _tap_flops(desc, n):
@@ -199,10 +207,12 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     cs = desc.cstruct(n, act, _precision, add_period)
     if _precision == PREC_TF32:
         wp = _packed_weights(w, desc, cs, l)
+        _io(x, w, bias, add, out)
         if wp is not None:
             _run('tapconv_fwd_tf32', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(),
                  desc.pmap_on(x.device).data_ptr(), _ptr(bias), _ptr(add), out.data_ptr(), _stream())
             return out
+    _io(x, w, bias, add, out)
     _run('tapconv_fwd', _tap_flops(desc, n), l.kgan_tapconv_fwd, cs, x.data_ptr(), w.data_ptr(), desc.pmap_on(x.device).data_ptr(),
          _ptr(bias), _ptr(add), out.data_ptr(), _stream())
     return out
@@ -214,11 +224,13 @@ def tapconv_wgrad(x, gout, desc, w_shape):
     dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
     l = _lib.lib()
     cs = desc.cstruct(n, ACT_NONE, _precision)
+    _io(x, gout, dw)
     if _precision == PREC_TF32:
         ok = desc.__dict__.setdefault("_tf32_wgrad_ok", {})
         if n not in ok:
             ok[n] = bool(l.kgan_tapconv_wgrad_tf32_ok(cs))
         if ok[n]:
+            _io(x, gout, dw)
             _run('tapconv_wgrad_tf32', _tap_flops(desc, n), l.kgan_tapconv_wgrad_tf32, cs, x.data_ptr(), gout.data_ptr(),
                  desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
             return dw
@@ -234,6 +246,7 @@ def adjmix_fwd(x, A):
     assert v2 == v
     out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
     _shape_sig(x, A)
+    _io(x, A, out)
     _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream())
     return out
 
@@ -246,6 +259,7 @@ def adjmix_bwd_x(g, A):
     c = kc // k
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
     _shape_sig(g, A)
+    _io(g, A, gx)
     _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream())
     return gx
 
@@ -259,6 +273,7 @@ def adjmix_bwd_a(x, g, k, mask=None):
     assert mask is None or tuple(mask.shape) == (k, v, w)
     gA = torch.empty((k, v, w), device=x.device, dtype=torch.float32)
     _shape_sig(x, g)
+    _io(x, g, gA)
     _run('adjmix_bwd_a', 0.0, _lib.lib().kgan_adjmix_bwd_a_masked, x.data_ptr(), g.data_ptr(), _ptr(mask), gA.data_ptr(), n, c, t, v, w, k, _stream())
     return gA
 
@@ -267,6 +282,7 @@ def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=ACT_NONE):
     _chk(a, b, bias, nw, noise)
     n, c, t, v = a.shape
     out = torch.empty_like(a)
+    _io(a, b, noise, out)
     _run('pointwise', 0.0, _lib.lib().kgan_epilogue_fwd, a.data_ptr(), _ptr(b), _ptr(bias), _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act,
                                             _stream())
     return out
@@ -276,6 +292,7 @@ def act_bwd(gout, out, act):
     _chk(gout, out)
     gz = torch.empty_like(out)
     _shape_sig(out)
+    _io(gout, out, gz)
     _run('pointwise', 0.0, _lib.lib().kgan_act_bwd, gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream())
     return gz
 
@@ -285,6 +302,7 @@ def chan_reduce(g, mul=None):
     n, c, t, v = g.shape
     out = torch.empty((c,), device=g.device, dtype=torch.float32)
     _shape_sig(g)
+    _io(g, mul)
     _run('reduce', 0.0, _lib.lib().kgan_chan_reduce, g.data_ptr(), _ptr(mul), out.data_ptr(), n, c, t * v, _stream())
     return out
 
@@ -296,6 +314,7 @@ def plane_spmm(x, table):
     idx, wgt = table.on(x.device)
     out = torch.empty((n, c, table.t_out, table.v_out), device=x.device, dtype=torch.float32)
     _shape_sig(x, out)
+    _io(x, out)
     _run('plane_spmm', 0.0, _lib.lib().kgan_plane_spmm, x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
                                           table.J, _stream())
     return out
@@ -325,6 +344,7 @@ def bn_stats(x, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
     n, c, t, v = x.shape
     mean = torch.empty((c,), device=x.device, dtype=torch.float32)
     rstd = torch.empty((c,), device=x.device, dtype=torch.float32)
+    _io(x)
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_stats, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), n, c, t * v,
                                         eps, momentum, _stream())
     return mean, rstd
@@ -334,6 +354,7 @@ def bn_apply(x, mean, rstd, gamma, beta):
     _chk(x, mean, rstd, gamma, beta)
     n, c, t, v = x.shape
     y = torch.empty_like(x)
+    _io(x, y)
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_apply, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c,
                                         t * v, _stream())
     return y
@@ -345,6 +366,7 @@ def bn_bwd(gy, x, mean, rstd, gamma):
     gx = torch.empty_like(x)
     gg = torch.empty((c,), device=x.device, dtype=torch.float32)
     gb = torch.empty((c,), device=x.device, dtype=torch.float32)
+    _io(gy, x, gy, x, gx)          # two passes over (gy, x): sums, then the elementwise pass
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_bwd, gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
                                       gg.data_ptr(), gb.data_ptr(), n, c, t * v, _stream())
     return gx, gg, gb
@@ -352,6 +374,7 @@ def bn_bwd(gy, x, mean, rstd, gamma):
 
 def adam_step(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
     _chk(p, g, m, v)
+    _io(p, g, m, v, p, m, v)
     _run('adam', 0.0, _lib.lib().kgan_adam_step, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, step,
                                          grad_scale, _stream())
 
