@@ -49,6 +49,8 @@ struct TmaPlan {
     int64_t groups32;                             // 32-row M groups: ceil(n / n_box) * cps
     int m_tiles, num_tiles, stages, smem_bytes;
     int a_lbo, a_sbo;                             // A descriptor strides (bytes): between 32-position M groups / between 8-channel K groups
+    int pf_tiles;                                 // L2 prefetch distance in tiles of this CTA (0: off)
+    uint32_t pf_taps;                             // taps whose boxes are prefetched (temporal shifts of the same channels are near-duplicates)
 };
 
 bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, int* n_rows, int* tmem_cols, int* nkt);
@@ -75,6 +77,25 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     p.smem_bytes = p.stages * stage + 1024 + 512;                  // + alignment slack + barriers
     p.a_lbo = TM_GROUP_BYTES;
     p.a_sbo = 512;
+    // L2 prefetch (TMA mode only): ~256 KB of unique activation bytes ahead of the shared-memory ring
+    static const int pf_env = getenv("KGAN_TMA_PREFETCH") ? atoi(getenv("KGAN_TMA_PREFETCH")) : -1;
+    p.pf_taps = 0;
+    int uniq = 0;
+    for (int t = 0; t < d.ntap; ++t) {
+        bool dup = false;
+        for (int u = 0; u < t; ++u)
+            if (((p.pf_taps >> u) & 1) && d.tap_in_ch[u] == d.tap_in_ch[t] && abs(d.tap_shift[u] - d.tap_shift[t]) < 32) dup = true;
+        if (!dup) {
+            p.pf_taps |= 1u << t;
+            ++uniq;
+        }
+    }
+    p.pf_tiles = (256 * 1024) / (p.nkt * uniq * A_STAGE_BYTES);
+    if (p.pf_tiles < 1) p.pf_tiles = 1;
+    if (p.pf_tiles > 16) p.pf_tiles = 16;
+    // measured on B200 (profiles/r1_layer_bench_tma_prefetch_ab.txt): the prefetch makes every layer 10-50 % SLOWER - off unless asked for
+    p.pf_tiles = pf_env > 0 ? (pf_env > 16 ? 16 : pf_env) : 0;
+    if (p.p_box != 32) p.pf_tiles = 0;
     return true;
 }
 
@@ -105,9 +126,13 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
     return c;
 }
 
+// The residual / label term `add` and the bias do not depend on the accumulator: their loads for the first column chunk are issued
+// BEFORE the wait on the accumulator barrier, so their latency hides behind the tile's main loop instead of following it.
 template <int ACT>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
-                                                  const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane) {
+                                                  const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
+                                                  uint32_t tfull_bar, uint32_t tfull_parity) {
+    bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
         float av[16];
@@ -116,6 +141,11 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
             for (int j = 0; j < 16; ++j) av[j] = ldg_pred(ap + (int64_t)(col0 + j) * astride, valid && j < nc);
         }
         const float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        if (!waited) {
+            mbar_wait(tfull_bar, tfull_parity);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            waited = true;
+        }
         uint32_t r[16];
         tmem_ld16(taddr + col0, r);
         float* o = op + (int64_t)col0 * p_out;
@@ -141,7 +171,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                                                                     const float* __restrict__ add, float* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int b_stage_bytes = pl.n_cta * UK * 4;
     uint8_t* a_base = smem;
@@ -179,11 +209,34 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
 
     if (warp == 0) {
         // ===== producer: tensor loads of the activation boxes + bulk copies of the packed weights =====
-        if (lane == 0) {
+        // (whole warp in uniform control flow, one elected lane issues: operands stay in uniform registers, see umma.cuh elect_one)
+        {
+            const bool leader = elect_one();
             const uint32_t chunk_bytes = pl.n_cta * 16;
             const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + chunk_bytes * 8;
-            int kit = 0;
+            // activation boxes of a later tile of this CTA -> L2 (off by default: measured slower); tiles that share an activation tile
+            // (other n splits / groups reading the same channels) leave the prefetch to the first of them
+            auto prefetch_tile = [&](int t2) {
+                if (t2 >= pl.num_tiles) return;
+                const TmaTile pc = tma_tile(t2, pl);
+                if (pc.ns != 0 || (pc.g != 0 && d.g_in == 0)) return;
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t G = (int64_t)pc.mt * 4 + i;
+                    if (G >= pl.groups32) break;
+                    const int nb = (int)(G / pl.cps);
+                    const int pp = (int)(G - (int64_t)nb * pl.cps) << pl.p_shift;
+                    for (int ict = 0; ict < pl.nkt; ++ict)
+                        for (int tap = 0; tap < d.ntap; ++tap)
+                            if ((pl.pf_taps >> tap) & 1)
+                                tma_prefetch_3d(&tmap, pp + d.tap_shift[tap], nb * pl.n_box, pc.g * d.g_in + d.tap_in_ch[tap] + ict * UK);
+                }
+            };
+            if (use_tma && pl.pf_tiles > 0 && leader)
+                for (int j = 1; j < pl.pf_tiles; ++j) prefetch_tile(blockIdx.x + j * gridDim.x);
+            int s = 0;
+            uint32_t ph = 1;                                          // parity to wait for on empty[s]
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+                if (use_tma && pl.pf_tiles > 0 && leader) prefetch_tile(tile + pl.pf_tiles * gridDim.x);
                 const TmaTile tc = tma_tile(tile, pl);
                 int cp[4], cn[4];                                     // box origin (position, sample) of the 4 M groups
 #pragma unroll
@@ -196,60 +249,75 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                 const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
                 const int oc_base = tc.ns * pl.n_cta;
                 const int ch_g = tc.g * d.g_in;
+                int ict = 0, tap = 0;
                 for (int it = 0; it < kiters; ++it) {
-                    const int k = kit + it, s = k % S;
-                    const uint32_t ph = (uint32_t)(k / S) & 1u;
-                    const int ict = it / d.ntap, tap = it - ict * d.ntap;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
-                    const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                    const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
-                    if (use_tma) {
+                    mbar_wait(empty0 + 8 * s, ph);
+                    if (leader) {
+                        mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
+                        const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                        const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+                        if (use_tma) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                            for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                        }
+                        const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
+                        const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                        if (pl.n_split == 1) {
+                            bulk_g2s(b_dst, src, chunk_bytes * 8, full0 + 8 * s);       // the whole stage is contiguous in the image
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                bulk_g2s(b_dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                        }
                     }
-                    const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
-                    const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
-                    if (pl.n_split == 1) {
-                        bulk_g2s(b_dst, src, chunk_bytes * 8, full0 + 8 * s);       // the whole stage is contiguous in the image
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            bulk_g2s(b_dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                    __syncwarp();
+                    if (++tap == d.ntap) {
+                        tap = 0;
+                        ++ict;
+                    }
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
                     }
                 }
-                kit += kiters;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (whole warp waits, one elected lane issues) =====
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (1u << 15);          // A operand MN-major
             const uint32_t b_lbo = pl.n_cta * 16;
-            int kit = 0, ti = 0;
+            int s = 0, ti = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
                 const int buf = ti & 1;
                 mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + buf * pl.n_cta;
                 for (int it = 0; it < kiters; ++it) {
-                    const int k = kit + it, s = k % S;
-                    const uint32_t ph = (uint32_t)(k / S) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     // TMA mode: both operands were written by the async proxy.  cp.async mode: the activations went through the
                     // generic proxy and must be made visible to the tensor core's async-proxy reads
                     if (!use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                    if (leader) {
+                        const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
-                    for (int j = 0; j < UK / 8; ++j)
-                        umma_tf32(acc, smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
-                                  smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    umma_commit(empty0 + 8 * s);
+                        for (int j = 0; j < UK / 8; ++j)
+                            umma_tf32(acc, smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
+                                      smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        umma_commit(empty0 + 8 * s);
+                    }
+                    __syncwarp();
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                umma_commit(tfull0 + 8 * buf);
-                kit += kiters;
+                if (leader) umma_commit(tfull0 + 8 * buf);
+                __syncwarp();
             }
         }
     } else if (warp >= TM_EPI_WARP0 + TM_EPI_WARPS) {
@@ -316,13 +384,15 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? po % d.add_period : po)
                                   : nullptr;
             const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
-            mbar_wait(tfull0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tbar = tfull0 + 8 * buf, tpar = (uint32_t)(ti >> 1) & 1u;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);
-            if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
-            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
-            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
+                mbar_wait(tbar, tpar);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
+            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
+            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);
         }

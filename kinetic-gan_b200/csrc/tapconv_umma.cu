@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
                                                                   const int32_t* __restrict__ pmap, const float* __restrict__ bias,
                                                                   const float* __restrict__ add, float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int b_stage_bytes = pl.n_cta * UK * 4;
     uint8_t* a_base = smem;
@@ -301,57 +301,71 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
             kit += kiters;
         }
     } else if (warp == FW_MMA_WARP) {
-        // ===== MMA issuer: one thread drives the tensor core =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp waits in uniform control flow, one elected lane drives the tensor core (umma.cuh elect_one) =====
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = instr_desc_tf32(pl.n_cta);
             const uint32_t b_lbo = pl.n_cta * 16;
-            int kit = 0, ti = 0;
+            int s = 0, ti = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
                 const int buf = ti & 1;
                 mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + buf * pl.n_cta;
                 for (int it = 0; it < kiters; ++it) {
-                    const int k = kit + it, s = k % S;
-                    const uint32_t ph = (uint32_t)(k / S) & 1u;
-                    mbar_wait(full0 + 8 * s, ph);                     // acquire: the producers' st.shared are visible to this thread
+                    mbar_wait(full0 + 8 * s, ph);                     // acquire: the producers' st.shared are visible
                     // generic-proxy writes (observed through the barrier) -> async proxy (tcgen05.mma operand reads).  The fence
                     // sits on the consumer side: a producer-side fence would also wait for that thread's in-flight gathers of
                     // the following stages and serialise the pipeline.
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                    if (leader) {
+                        const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
-                    for (int j = 0; j < UK / 8; ++j)
-                        umma_tf32(acc, smem_desc(a_addr + j * 2 * A_LBO, A_LBO, CORE_SBO), smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO),
-                                  idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    umma_commit(empty0 + 8 * s);                      // frees the stage when these MMAs retire
+                        for (int j = 0; j < UK / 8; ++j)
+                            umma_tf32(acc, smem_desc(a_addr + j * 2 * A_LBO, A_LBO, CORE_SBO), smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO),
+                                      idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        umma_commit(empty0 + 8 * s);                  // frees the stage when these MMAs retire
+                    }
+                    __syncwarp();
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                umma_commit(tfull0 + 8 * buf);                        // accumulator complete -> epilogue
-                kit += kiters;
+                if (leader) umma_commit(tfull0 + 8 * buf);            // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else if (warp == FW_LOAD_WARP) {
-        // ===== weight loader: bulk copies of the packed tf32 image =====
-        if (lane == 0) {
+        // ===== weight loader: bulk copies of the packed tf32 image (one elected lane issues) =====
+        {
+            const bool leader = elect_one();
             const uint32_t chunk_bytes = pl.n_cta * 16;
-            int kit = 0;
+            int s = 0;
+            uint32_t ph = 1;
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = tile_coord(tile, pl);
                 const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
                 const int oc_base = tc.ns * pl.n_cta;
                 for (int it = 0; it < kiters; ++it) {
-                    const int k = kit + it, s = k % S;
-                    const uint32_t ph = (uint32_t)(k / S) & 1u;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    mbar_arrive_expect_tx(full0 + 8 * s, chunk_bytes * 8);
-                    const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
-                    const uint32_t dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                    mbar_wait(empty0 + 8 * s, ph);
+                    if (leader) {
+                        mbar_arrive_expect_tx(full0 + 8 * s, chunk_bytes * 8);
+                        const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
+                        const uint32_t dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) bulk_g2s(dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                        for (int c = 0; c < 8; ++c)
+                            bulk_g2s(dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                    }
+                    __syncwarp();
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                kit += kiters;
             }
         }
     } else {

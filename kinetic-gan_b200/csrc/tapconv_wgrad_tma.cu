@@ -32,7 +32,10 @@ constexpr int WT_KT = 32;                        // positions per K tile: one 12
 struct WgradTmaPlan {
     int n_ic, ic_tiles, oc_tiles, tmem_cols, stages;
     int a_rows;              // rows of the gout box (multiple of 8, <= 128)
-    int a_bytes, b_bytes;    // per stage: A tile (always 16 KB: the MMA reads 128 rows), one tap's B tile
+    int a_bytes, b_bytes;    // per stage: A tile (a_rows rows of 128 bytes), one tap's B tile
+    int pf_dist;             // L2 prefetch distance in K tiles (0: off)
+    uint32_t pf_taps;        // taps whose box is prefetched (near-duplicates - temporal shifts of the same channels - are skipped)
+    int tail_pad;            // bytes after the last stage that the last A tile's 16 KB read window may touch
     int p_box, n_box;        // a K tile = p_box positions x n_box samples = 32 contraction elements (p_box = 32: one sample)
     int kt_per_plane;        // p_out / p_box
     int64_t ktiles;          // ceil(n / n_box) * kt_per_plane
@@ -65,11 +68,16 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
     if (p.tmem_cols > 512) return false;
     p.a_rows = d.co >= UM ? UM : round_up(d.co, 8);
-    p.a_bytes = UM * 128;
+    // The A tile only holds the a_rows rows the box writes; the M = 128 MMA reads on into the B tiles behind it (rows that feed
+    // accumulator lanes nobody stores).  The kernel is bound by the bytes in flight per SM (loaded HBM latency ~3 us), so a smaller
+    // stage means a deeper ring.  `tail_pad` keeps the last stage's 16 KB read window inside the allocation.
+    p.a_bytes = p.a_rows * 128;
     p.b_bytes = p.n_ic * 128;
     const int stage = p.a_bytes + d.ntap * p.b_bytes;
-    p.stages = (196 * 1024) / stage;
-    if (p.stages > 10) p.stages = 10;
+    const int tail_pad = stage < UM * 128 ? UM * 128 - stage : 0;
+    p.tail_pad = tail_pad;
+    p.stages = (212 * 1024 - tail_pad) / stage;
+    if (p.stages > 16) p.stages = 16;
     if (p.stages < 2) return false;
     p.kt_per_plane = d.p_out / p.p_box;
     p.ktiles = ceil_div64(d.n, p.n_box) * p.kt_per_plane;
@@ -80,7 +88,25 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     p.chunk = ceil_div64(p.ktiles, nchunks);
     p.nchunks = (int)ceil_div64(p.ktiles, p.chunk);
     if ((int64_t)p.nchunks * d.groups > 65535) return false;
-    p.smem_bytes = p.stages * stage + 1024 + 256;               // + alignment slack + barriers
+    p.smem_bytes = p.stages * stage + tail_pad + 1024 + 512;    // + alignment slack + barriers
+    // L2 prefetch: ~256 KB of unique operand bytes ahead of the ring
+    static const int pf_env = getenv("KGAN_TMA_PREFETCH") ? atoi(getenv("KGAN_TMA_PREFETCH")) : -1;
+    p.pf_taps = 0;
+    int uniq = 0;
+    for (int t = 0; t < d.ntap; ++t) {
+        bool dup = false;
+        for (int u = 0; u < t; ++u)
+            if (((p.pf_taps >> u) & 1) && d.tap_in_ch[u] == d.tap_in_ch[t] && abs(d.tap_shift[u] - d.tap_shift[t]) < WT_KT) dup = true;
+        if (!dup) {
+            p.pf_taps |= 1u << t;
+            ++uniq;
+        }
+    }
+    const int per_tile = (p.a_rows + uniq * p.n_ic) * 128;
+    p.pf_dist = p.stages + (256 * 1024) / per_tile;
+    if (p.pf_dist > 64) p.pf_dist = 64;
+    // measured on B200 (profiles/r1_layer_bench_tma_prefetch_ab.txt): the prefetch makes every layer 10-50 % SLOWER - off unless asked for
+    p.pf_dist = pf_env > 0 ? p.stages + pf_env : 0;
     return true;
 }
 
@@ -99,10 +125,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                                                                      float* __restrict__ dw) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);           // full[S], empty[S], accfull
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + pl.tail_pad);   // full[S], empty[S], accfull
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
 
@@ -131,48 +157,74 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: one gout box + ntap input boxes per K tile =====
-        if (lane == 0) {
+        // ===== producer: one gout box + ntap input boxes per K tile (whole warp in uniform control flow, one lane issues) =====
+        {
+            const bool leader = elect_one();
             const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
             const uint32_t stage_tx = (uint32_t)pl.a_rows * 128u + (uint32_t)d.ntap * pl.b_bytes;
             int64_t kt = kbeg;
             int nn = (int)(kt / pl.kt_per_plane), pt = (int)(kt - (int64_t)nn * pl.kt_per_plane);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
-                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                const int p0 = pt * pl.p_box, n0 = nn * pl.n_box;       // samples beyond n are zero-filled by the TMA unit
-                wt_tma_load_3d(st, &map_g, p0, n0, out_ch0, full0 + 8 * s);
+            auto prefetch = [&](int64_t k) {                            // operands of K tile k -> L2
+                const int pn = (int)(k / pl.kt_per_plane), pp = (int)(k - (int64_t)pn * pl.kt_per_plane) * pl.p_box;
+                tma_prefetch_3d(&map_g, pp, pn * pl.n_box, out_ch0);
                 for (int tap = 0; tap < d.ntap; ++tap)
-                    wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], n0, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                    if ((pl.pf_taps >> tap) & 1) tma_prefetch_3d(&map_x, pp + d.tap_shift[tap], pn * pl.n_box, in_ch0 + d.tap_in_ch[tap]);
+            };
+            if (pl.pf_dist > 0 && leader)
+                for (int64_t k = kbeg + S; k < kbeg + pl.pf_dist && k < kend; ++k) prefetch(k);
+            int s = 0;
+            uint32_t ph = 1;                                            // parity to wait for on empty[s]
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(empty0 + 8 * s, ph);
+                if (leader) {
+                    if (pl.pf_dist > 0 && kbeg + it + pl.pf_dist < kend) prefetch(kbeg + it + pl.pf_dist);
+                    mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const int p0 = pt * pl.p_box, n0 = nn * pl.n_box;
+                    wt_tma_load_3d(st, &map_g, p0, n0, out_ch0, full0 + 8 * s);
+                    for (int tap = 0; tap < d.ntap; ++tap)
+                        wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], n0, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                }
+                __syncwarp();
                 if (++pt == pl.kt_per_plane) {
                     pt = 0;
                     ++nn;
                 }
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (whole warp waits, one lane issues) =====
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = instr_desc_tf32(pl.n_ic);
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                for (int tap = 0; tap < d.ntap; ++tap) {
-                    const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
+                if (leader) {
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                    for (int tap = 0; tap < d.ntap; ++tap) {
+                        const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
 #pragma unroll
-                    for (int j = 0; j < WT_KT / 8; ++j)                 // 32 bytes of K per MMA inside the 128-byte swizzled row
-                        umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw128(a_addr + j * 32), smem_desc_k_sw128(b_addr + j * 32), idesc,
-                                  (it > 0 || j > 0) ? 1u : 0u);
+                        for (int j = 0; j < WT_KT / 8; ++j)             // 32 bytes of K per MMA inside the 128-byte swizzled row
+                            umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw128(a_addr + j * 32), smem_desc_k_sw128(b_addr + j * 32), idesc,
+                                      (it > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);
                 }
-                umma_commit(empty0 + 8 * s);
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
-            umma_commit(accfull);
+            if (leader) umma_commit(accfull);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM lane = output channel row (warp % 4 selects the lane quarter, the other bit the column half) =====

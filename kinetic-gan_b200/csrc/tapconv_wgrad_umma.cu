@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
                                                                     const float* __restrict__ in, const float* __restrict__ gout,
                                                                     const int32_t* __restrict__ pmap, float* __restrict__ dw) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);           // full[S], empty[S], accfull
@@ -230,16 +230,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_tf32(pl.n_ic);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);                  // acquire: every producer's copies for this stage have landed
-                // cp.async wrote through the generic proxy; tcgen05.mma reads operands through the async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== MMA issuer (whole warp waits in uniform control flow, one elected lane issues: umma.cuh elect_one) =====
+        const bool leader = elect_one();
+        const uint32_t idesc = instr_desc_tf32(pl.n_ic);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(full0 + 8 * s, ph);                      // acquire: every producer's copies for this stage have landed
+            // cp.async wrote through the generic proxy; tcgen05.mma reads operands through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (leader) {
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 for (int tap = 0; tap < d.ntap; ++tap) {
                     const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
@@ -250,8 +251,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
                 }
                 umma_commit(empty0 + 8 * s);
             }
-            umma_commit(accfull);
+            __syncwarp();
+            if (++s == S) {
+                s = 0;
+                ph ^= 1u;
+            }
         }
+        if (leader) umma_commit(accfull);
+        __syncwarp();
     }
     __syncthreads();
     if (warp == WG_PRODUCER_WARPS) {

@@ -44,6 +44,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// One lane of a fully active warp.  The producer / MMA-issuer loops run on ALL lanes of their warp in uniform control flow and
+// only the asynchronous-issue instructions sit behind this predicate: their operands (addresses, coordinates, descriptors) then
+// live in uniform registers.  Written as `if (lane == 0) { loop }` the compiler has to treat every operand as per-thread data and
+// wraps each UTMALDG / UTCHMMA / UBLKCP in a uniformisation loop (R2UR + ELECT + BRA.U.ANY, ~13 instructions per issue): measured
+// on the weight-gradient kernel, the single issuing thread - not memory, not the tensor pipe - bounded the pipeline.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// TMA prefetch of a 3-D box into L2 (no shared-memory destination, no barrier): widens the window of bytes in flight beyond what the
+// shared-memory ring can hold - the TMA-fed kernels are bound by (bytes in flight per SM) / (loaded HBM latency, ~3 us)
+__device__ __forceinline__ void tma_prefetch_3d(const void* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+}
 // predicated read-only global load as a volatile asm: keeps program order relative to the barrier waits, so a whole
 // stage of gathers is in flight before the thread blocks
 __device__ __forceinline__ float ldg_pred(const float* ptr, bool pred) {
