@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
         // ===== MMA issuer (whole warp waits, one lane issues) =====
         {
             const bool leader = elect_one();
-            const uint32_t idesc = instr_desc_tf32(pl.n_ic);
+            // the taps' B tiles are adjacent in shared memory and their accumulators adjacent in TMEM: when ntap * n_ic <= 256 all taps
+            // are ONE MMA of N = ntap * n_ic per K step (3x fewer instructions for the single issuing thread)
+            const int nmma = d.ntap * pl.n_ic <= 256 ? 1 : d.ntap;
+            const uint32_t idesc = instr_desc_tf32(nmma == 1 ? d.ntap * pl.n_ic : pl.n_ic);
             int s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
                     const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                    for (int tap = 0; tap < d.ntap; ++tap) {
+                    for (int tap = 0; tap < nmma; ++tap) {
                         const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
 #pragma unroll
                         for (int j = 0; j < WT_KT / 8; ++j)             // 32 bytes of K per MMA inside the 128-byte swizzled row
