@@ -456,7 +456,7 @@ def run_generate(args):
     torch.cuda.synchronize()
     fam = ops.profile_stop(prof)
     sites = fam.pop("_sites")
-    runner.graphs = not args.no_graphs
+    runner.graphs = not args.no_graphs and args.trunc is None
     roofline = make_roofline(fam, sites, 3, F_G * value / 1e12 / comm.world_size)
     # lower bound of the whole pass: z + output (+ noise) = ~21 KB of compulsory HBM traffic per sequence
     roofline["pass_hbm_floor_frac"] = (value / comm.world_size) * 21.2e3 / (peaks()[1] * 1e9)

@@ -69,6 +69,11 @@ typedef struct kgan_tapconv_desc {
      * The TMA kernel additionally needs p_in, p_out and every shift to be multiples of 4 (16-byte box origins). */
     int32_t tma_mode;
     int32_t tap_shift[KGAN_MAX_TAPS];
+    /* Position-block groups (kgan_tapconv_fwd / _fwd_tf32 only; 0, 0 = off): the output planes hold p_out_plane >= p_out positions
+     * and group g writes its p_out results at plane offset g * g_pout.  The data gradient of a time-unfolded temporal conv
+     * (geometry.UnfoldedTcnGeom) is kt such groups with ONE tap each instead of kt taps of which kt - 1 read nothing. */
+    int32_t p_out_plane;
+    int32_t g_pout;
 } kgan_tapconv_desc;
 
 /* Version / diagnostics. */

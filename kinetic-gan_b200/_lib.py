@@ -22,6 +22,7 @@ class TapConvDesc(C.Structure):
         ("tap_in_ch", C.c_int32 * MAX_TAPS), ("tap_w_off", C.c_int64 * MAX_TAPS), ("tap_row", C.c_int32 * MAX_TAPS),
         ("pmap_vec_mask", C.c_int32), ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
         ("tma_mode", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
+        ("p_out_plane", C.c_int32), ("g_pout", C.c_int32),
     ]
 
 

@@ -41,6 +41,9 @@ __device__ __forceinline__ int64_t w_oc_offset(const kgan_tapconv_desc& d, int o
     return d.w_oc_blk ? (int64_t)(oc / d.w_oc_blk) * d.w_ocblk + (int64_t)(oc % d.w_oc_blk) * d.w_oc : (int64_t)oc * d.w_oc;
 }
 
+// output plane stride / per-group plane offset (position-block groups, include/kgan.h)
+__host__ __device__ inline int out_plane(const kgan_tapconv_desc& d) { return d.p_out_plane ? d.p_out_plane : d.p_out; }
+
 constexpr int kNumSMs = 148;   // B200
 
 bool tapconv_is_thin(const kgan_tapconv_desc& d);   // small contraction: streaming SIMT kernel in both precision modes (tapconv_simt.cu)

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_simt(const __grid_constant__ k
         for (int j = 0; j < TN; ++j) {
             const int oc = oc0 + ty * TN + j;
             if (oc >= d.co) continue;
-            const int64_t o = ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.p_out + p;
+            const int pg = p + g * d.g_pout;                      // position inside the output plane (position-block groups)
+            const int64_t o = ((int64_t)nn * d.c_out_total + out_ch0 + oc) * out_plane(d) + pg;
             float v = acc[i][j];
             if (bias) v += __ldg(bias + out_ch0 + oc);
-            if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.add_period + p % d.add_period : o));
+            if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.add_period + pg % d.add_period : o));
             out[o] = apply_act(v, d.act);
         }
     }
@@ -194,7 +195,7 @@ constexpr int THIN_MAX_W = 1024;
 
 // groups that read the same input channels (g_in == 0: the K partitions of a graph conv's data gradient) are merged into one pass:
 // accumulator a = (group, oc), so the input is streamed once instead of once per group
-static inline int thin_merge(const kgan_tapconv_desc& d) { return (d.groups > 1 && d.g_in == 0 && d.groups * d.co <= 16) ? d.groups : 1; }
+static inline int thin_merge(const kgan_tapconv_desc& d) { return (d.groups > 1 && d.g_in == 0 && d.g_pout == 0 && d.groups * d.co <= 16) ? d.groups : 1; }
 
 template <int CO>   // accumulators per thread (ng * co <= CO), CO in {4, 8, 16}
 __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
@@ -238,12 +239,13 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
                 }
             }
         }
-        const int pa = d.add_period ? p % d.add_period : 0;
+        const int pg = p + (ng == 1 ? g0 * d.g_pout : 0);           // position-block groups are never merged (thin_merge)
+        const int pa = d.add_period ? pg % d.add_period : 0;
 #pragma unroll
         for (int j = 0; j < CO; ++j) {
             const int c = och[j];
             if (c >= 0) {
-                const int64_t o = ((int64_t)nn * d.c_out_total + c) * d.p_out + p;
+                const int64_t o = ((int64_t)nn * d.c_out_total + c) * out_plane(d) + pg;
                 float v = acc[j];
                 if (bias) v += __ldg(bias + c);
                 if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + c) * d.add_period + pa : o));
@@ -283,6 +285,9 @@ static int validate(const kgan_tapconv_desc* d) {
         KGAN_REQUIRE(d->tap_in_ch[t] >= 0 && d->tap_in_ch[t] + d->ck + (d->groups - 1) * d->g_in <= d->c_in_total,
                      "tapconv: tap %d reads channels beyond c_in_total", t);
     KGAN_REQUIRE(d->co + (d->groups - 1) * d->g_out <= d->c_out_total, "tapconv: writes channels beyond c_out_total");
+    KGAN_REQUIRE(d->p_out_plane >= 0 && d->g_pout >= 0 && (d->p_out_plane == 0 ? d->g_pout == 0 : d->p_out + (d->groups - 1) * d->g_pout <= d->p_out_plane),
+                 "tapconv: position-block groups write beyond the output plane");
+    KGAN_REQUIRE(d->p_out_plane == 0 || d->add_period == 0 || d->g_pout % d->add_period == 0, "tapconv: add_period does not divide g_pout");
     return 0;
 }
 
@@ -322,6 +327,7 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
                                   float* dw, int64_t dw_numel, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad: null pointer");
+    KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad: position-block groups are a forward / data-gradient feature");
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
     const int64_t total = (int64_t)d->n * d->p_out;
@@ -344,7 +350,7 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
 // forward path (workspace size, packing, launch), so the packed image and the kernel always agree.
 static kgan_tapconv_desc merge_groups(const kgan_tapconv_desc& d) {
     static const bool off = getenv("KGAN_NO_GROUP_MERGE") != nullptr;
-    if (off || d.groups <= 1 || d.g_in != 0 || d.g_out != d.co || d.w_oc_blk != 0) return d;
+    if (off || d.groups <= 1 || d.g_in != 0 || d.g_out != d.co || d.w_oc_blk != 0 || d.g_pout != 0) return d;
     kgan_tapconv_desc m = d;
     m.w_oc_blk = d.co;
     m.w_ocblk = d.g_w;
@@ -418,6 +424,7 @@ extern "C" int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* 
                                        float* dw, int64_t dw_numel, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad_tf32: null pointer");
+    KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad_tf32: position-block groups are a forward / data-gradient feature");
     int r = tapconv_wgrad_tf32(*d, in, gout, pmap, dw, dw_numel, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_wgrad_tf32: shape not eligible for the tensor-core path (kgan_tapconv_wgrad_tf32_ok() == 0)");

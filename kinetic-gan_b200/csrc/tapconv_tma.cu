@@ -379,9 +379,10 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const bool valid = G < pl.groups32 && nn < d.n;
             const int po = valid ? pv : 0, nv = valid ? nn : 0;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
-            float* op = out + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * d.p_out + po;
-            const int64_t astride = d.add_period ? d.add_period : d.p_out;
-            const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? po % d.add_period : po)
+            const int pst = out_plane(d), pg = po + tc.g * d.g_pout;      // plane stride, position inside the output plane
+            float* op = out + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * pst + pg;
+            const int64_t astride = d.add_period ? d.add_period : pst;
+            const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? pg % d.add_period : pg)
                                   : nullptr;
             const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
             const uint32_t tbar = tfull0 + 8 * buf, tpar = (uint32_t)(ti >> 1) & 1u;
@@ -390,9 +391,9 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
-            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
-            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane, tbar, tpar);
+            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
+            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
+            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);
         }

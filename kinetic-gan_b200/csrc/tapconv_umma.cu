@@ -381,18 +381,20 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
             const bool valid = pos < (uint32_t)total_pos;
             const uint32_t nn = valid ? pos / (uint32_t)d.p_out : 0u, p = valid ? pos - nn * (uint32_t)d.p_out : 0u;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
-            float* op = out + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * d.p_out + p;
-            const int64_t astride = d.add_period ? d.add_period : d.p_out;
-            const float* ap = add ? add + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? p % (uint32_t)d.add_period : p)
+            const int pst = out_plane(d);
+            const uint32_t pg = p + (uint32_t)(tc.g * d.g_pout);      // position inside the output plane (position-block groups)
+            float* op = out + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * pst + pg;
+            const int64_t astride = d.add_period ? d.add_period : pst;
+            const float* ap = add ? add + ((int64_t)nn * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? pg % (uint32_t)d.add_period : pg)
                                   : nullptr;
             const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
             mbar_wait(tfull0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);          // columns of this tile that exist
-            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
-            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
-            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, d.p_out, ap, astride, bp, lane);
+            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
+            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
+            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);                           // accumulator may be overwritten
         }

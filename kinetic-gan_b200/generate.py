@@ -21,7 +21,9 @@ class GeneratorRunner:
     def __init__(self, generator, batch, latent_dim=512, trunc=None, graphs=True, device=None):
         self.G = generator.eval()
         self.device = device or next(generator.parameters()).device
-        self.batch, self.trunc, self.graphs = batch, trunc, graphs
+        # W-space truncation draws its 1000 latents from the HOST RNG on every call (generator.py:98): a captured graph would freeze
+        # them (and a pageable H2D copy cannot be captured), so that mode launches eagerly
+        self.batch, self.trunc, self.graphs = batch, trunc, graphs and trunc is None
         self.z = torch.zeros(batch, latent_dim, device=self.device)
         self.labels = torch.zeros(batch, dtype=torch.long, device=self.device)
         self.out = None

@@ -92,6 +92,7 @@ class TapDesc:
             s.tma_mode = self.tma_mode
             for i in range(self.ntap):
                 s.tap_shift[i] = self.tap_shift[i]
+            s.p_out_plane, s.g_pout = getattr(self, "p_out_plane", 0), getattr(self, "g_pout", 0)
             self._structs[key] = s
         return s
 
@@ -177,17 +178,16 @@ class UnfoldedTcnGeom:
         self.unfold = PlaneTable(dense, kt * self.t_out, v_in, t_in, v_in)
         q = np.arange(H, dtype=np.int32)
         pmap = np.stack([q + d * H for d in range(kt)]).astype(np.int32)
-        inv = np.full((kt, kt * H), -1, np.int32)
-        for d in range(kt):
-            inv[d, d * H:(d + 1) * H] = q
         self.fwd = TapDesc(
             c_in_total=c_in, p_in=kt * H, c_out_total=c_out, p_out=H, ntap=kt, ck=c_in, co=c_out, groups=1, g_in=0, g_out=0, g_w=0,
             w_oc=c_in * kt, w_ic=kt, tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=pmap,
             t_out=self.t_out, v_out=v_in)
+        # data gradient: block d of the unfolded gradient is W_d^T g - kt position-block groups with ONE tap each (include/kgan.h
+        # p_out_plane / g_pout) instead of kt taps over the whole 3H plane of which kt - 1 would read nothing
         self.dgrad = TapDesc(
-            c_in_total=c_out, p_in=H, c_out_total=c_in, p_out=kt * H, ntap=kt, ck=c_out, co=c_in, groups=1, g_in=0, g_out=0, g_w=0,
-            w_oc=kt, w_ic=c_in * kt, tap_in_ch=[0] * kt, tap_w_off=list(range(kt)), tap_row=list(range(kt)), pmap=inv,
-            t_out=kt * self.t_out, v_out=v_in)
+            c_in_total=c_out, p_in=H, c_out_total=c_in, p_out=H, ntap=1, ck=c_out, co=c_in, groups=kt, g_in=0, g_out=0, g_w=1,
+            w_oc=kt, w_ic=c_in * kt, tap_in_ch=[0], tap_w_off=[0], tap_row=[0], pmap=q.reshape(1, H).astype(np.int32),
+            t_out=kt * self.t_out, v_out=v_in, p_out_plane=kt * H, g_pout=H)
 
 
 class PlaneTable:

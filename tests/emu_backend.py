@@ -39,20 +39,22 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=0):
     xin = x.reshape(n, desc.c_in_total, desc.p_in)
     wf = w.reshape(-1)
     pmap = torch.from_numpy(desc.pmap).long()
-    out = torch.zeros(n, desc.c_out_total, desc.p_out, dtype=x.dtype)
+    plane = getattr(desc, "p_out_plane", 0) or desc.p_out          # position-block groups (include/kgan.h p_out_plane / g_pout)
+    g_pout = getattr(desc, "g_pout", 0)
+    out = torch.zeros(n, desc.c_out_total, plane, dtype=x.dtype)
     for g in range(desc.groups):
         acc = torch.zeros(n, desc.co, desc.p_out, dtype=x.dtype)
         for tap in range(desc.ntap):
             acc = acc + torch.einsum("oi,nip->nop", wf[_w_index(desc, g, tap)], _gathered(xin, desc, g, tap, pmap))
-        o0 = g * desc.g_out
+        o0, q0 = g * desc.g_out, g * g_pout
         if bias is not None:
             acc = acc + bias[o0:o0 + desc.co].view(1, -1, 1)
         if add is not None:
             a = add
             if a.shape[2] == 1 and desc.t_out > 1:       # broadcast along T (add_period = V)
                 a = a.expand(n, desc.c_out_total, desc.t_out, desc.v_out)
-            acc = acc + a.reshape(n, desc.c_out_total, desc.p_out)[:, o0:o0 + desc.co]
-        out[:, o0:o0 + desc.co] = _act(acc, act)
+            acc = acc + a.reshape(n, desc.c_out_total, plane)[:, o0:o0 + desc.co, q0:q0 + desc.p_out]
+        out[:, o0:o0 + desc.co, q0:q0 + desc.p_out] = _act(acc, act)
     return out.view(n, desc.c_out_total, desc.t_out, desc.v_out)
 
 
