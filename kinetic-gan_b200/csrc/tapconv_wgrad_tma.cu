@@ -36,24 +36,31 @@ struct WgradTmaPlan {
     int pf_dist;             // L2 prefetch distance in K tiles (0: off)
     uint32_t pf_taps;        // taps whose box is prefetched (near-duplicates - temporal shifts of the same channels - are skipped)
     int tail_pad;            // bytes after the last stage that the last A tile's 16 KB read window may touch
-    int p_box, n_box;        // a K tile = p_box positions x n_box samples = 32 contraction elements (p_box = 32: one sample)
+    int p_box, nsub;         // a stage = nsub sub-tiles of p_box positions of ONE sample each (p_box = 32 / 16 / 8, nsub = 32 / p_box)
+    int row_bytes;           // 4 * p_box = swizzle span of the sub-tiles (SWIZZLE_128B / _64B / _32B)
+    int sub_bytes;           // (a_rows + ntap * n_ic) * row_bytes
+    uint32_t desc_hi;        // upper descriptor word: SBO = 8 rows, version, layout type of the swizzle mode
     int kt_per_plane;        // p_out / p_box
-    int64_t ktiles;          // ceil(n / n_box) * kt_per_plane
+    int64_t ktiles;          // stages in total: ceil(n * kt_per_plane / nsub)
     int nchunks;
     int64_t chunk;           // K tiles per split-K chunk
     int smem_bytes;
 };
 
-int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle128);
+int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle);
 
 static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     if (d.tma_mode != 1 || d.w_oc_blk != 0 || d.ntap > 8) return false;
-    // Planes below 32 positions would need boxes of p_box positions x n_box samples per 128-byte row.  Measured on B200 (tools/
-    // probe_wgrad_tma.py): with a 128-byte swizzle mode the TMA unit faults ("illegal memory access") for every box whose innermost
-    // extent is below 128 bytes (16 x 2, 8 x 4 and 4 x 8 all fail, 32 x 1 works) - those layers stay on the cp.async producers.
-    if ((d.p_out % WT_KT) || (d.p_in & 3)) return false;
-    p.p_box = WT_KT;
-    p.n_box = 1;
+    // A K tile is p_box positions of one sample, p_box = the largest of 32 / 16 / 8 that divides the plane, in the swizzle mode whose
+    // span equals the box row (128 / 64 / 32 bytes); a stage holds 32 / p_box such sub-tiles.  (Boxes spanning several samples to fill
+    // a 128-byte row do not work: with a swizzle span wider than the box's innermost extent the TMA unit faults on B200 - measured
+    // with tools/probe_wgrad_tma.py for 16 x 2, 8 x 4 and 4 x 8.)
+    if ((d.p_out & 7) || (d.p_in & 3)) return false;
+    p.p_box = (d.p_out % 32) == 0 ? 32 : (d.p_out % 16) == 0 ? 16 : 8;
+    if (getenv("KGAN_WGRAD_TMA_BOX32") && p.p_box != 32) return false;            // A/B switch: whole 128-byte rows only
+    p.nsub = WT_KT / p.p_box;
+    p.row_bytes = 4 * p.p_box;
+    p.desc_hi = (uint32_t)((8 * p.row_bytes) >> 4) | (1u << 14) | ((p.p_box == 32 ? 2u : p.p_box == 16 ? 4u : 6u) << 29);
     for (int t = 0; t < d.ntap; ++t)
         if (d.tap_shift[t] & 3) return false;                    // box origins must be 16-byte aligned
     const int64_t total = (int64_t)d.n * d.p_out;
@@ -71,16 +78,17 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     // The A tile only holds the a_rows rows the box writes; the M = 128 MMA reads on into the B tiles behind it (rows that feed
     // accumulator lanes nobody stores).  The kernel is bound by the bytes in flight per SM (loaded HBM latency ~3 us), so a smaller
     // stage means a deeper ring.  `tail_pad` keeps the last stage's 16 KB read window inside the allocation.
-    p.a_bytes = p.a_rows * 128;
-    p.b_bytes = p.n_ic * 128;
-    const int stage = p.a_bytes + d.ntap * p.b_bytes;
-    const int tail_pad = stage < UM * 128 ? UM * 128 - stage : 0;
+    p.a_bytes = p.a_rows * p.row_bytes;
+    p.b_bytes = p.n_ic * p.row_bytes;
+    p.sub_bytes = p.a_bytes + d.ntap * p.b_bytes;
+    const int stage = p.nsub * p.sub_bytes;
+    const int tail_pad = p.sub_bytes < UM * p.row_bytes ? UM * p.row_bytes - p.sub_bytes : 0;
     p.tail_pad = tail_pad;
     p.stages = (212 * 1024 - tail_pad) / stage;
     if (p.stages > 16) p.stages = 16;
     if (p.stages < 2) return false;
     p.kt_per_plane = d.p_out / p.p_box;
-    p.ktiles = ceil_div64(d.n, p.n_box) * p.kt_per_plane;
+    p.ktiles = ceil_div64((int64_t)d.n * p.kt_per_plane, p.nsub);
     const int tiles = p.ic_tiles * p.oc_tiles * d.groups;
     int64_t nchunks = kNumSMs / tiles;                           // one wave
     if (nchunks > p.ktiles / 4) nchunks = p.ktiles / 4;
@@ -103,10 +111,11 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
         }
     }
     const int per_tile = (p.a_rows + uniq * p.n_ic) * 128;
+    if (p.p_box != 32) p.pf_taps = 0, uniq = 0;                 // (the prefetch path only knows whole-row tiles; it is off anyway)
     p.pf_dist = p.stages + (256 * 1024) / per_tile;
     if (p.pf_dist > 64) p.pf_dist = 64;
     // measured on B200 (profiles/r1_layer_bench_tma_prefetch_ab.txt): the prefetch makes every layer 10-50 % SLOWER - off unless asked for
-    p.pf_dist = pf_env > 0 ? p.stages + pf_env : 0;
+    p.pf_dist = (pf_env > 0 && p.p_box == 32) ? p.stages + pf_env : 0;
     return true;
 }
 
@@ -115,9 +124,10 @@ __device__ __forceinline__ void wt_tma_load_3d(uint32_t dst, const CUtensorMap* 
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
-// K-major operand, SWIZZLE_128B (layout type 2): rows of 128 bytes (32 tf32 elements of K), 8-row atoms of 1024 bytes (SBO); LBO unused
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// K-major operand in a swizzled layout whose span equals the row (128 / 64 / 32 bytes): 8-row atoms (SBO = 8 rows), LBO unused.
+// `hi` = upper word from the plan: SBO >> 4 | version 1 (bit 46) | layout type (2 / 4 / 6 at bits 61-63).
+__device__ __forceinline__ uint64_t smem_desc_k_sw(uint32_t addr, uint32_t hi) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)hi << 32);
 }
 
 __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradTmaPlan pl,
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
-    const int stage_bytes = pl.a_bytes + d.ntap * pl.b_bytes;
+    const int stage_bytes = pl.nsub * pl.sub_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + pl.tail_pad);   // full[S], empty[S], accfull
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
@@ -161,14 +171,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
         {
             const bool leader = elect_one();
             const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
-            const uint32_t stage_tx = (uint32_t)pl.a_rows * 128u + (uint32_t)d.ntap * pl.b_bytes;
-            int64_t kt = kbeg;
-            int nn = (int)(kt / pl.kt_per_plane), pt = (int)(kt - (int64_t)nn * pl.kt_per_plane);
-            auto prefetch = [&](int64_t k) {                            // operands of K tile k -> L2
+            const uint32_t stage_tx = (uint32_t)stage_bytes;
+            // first K tile of this CTA's chunk: stage k covers K tiles k * nsub ... + nsub - 1, K tile t = (sample t / kt_per_plane, box t % ...)
+            const int64_t t0 = kbeg * pl.nsub;
+            int nn = (int)(t0 / pl.kt_per_plane), pt = (int)(t0 - (int64_t)nn * pl.kt_per_plane);
+            auto prefetch = [&](int64_t k) {                            // operands of stage k -> L2 (whole-row tiles only)
                 const int pn = (int)(k / pl.kt_per_plane), pp = (int)(k - (int64_t)pn * pl.kt_per_plane) * pl.p_box;
-                tma_prefetch_3d(&map_g, pp, pn * pl.n_box, out_ch0);
+                tma_prefetch_3d(&map_g, pp, pn, out_ch0);
                 for (int tap = 0; tap < d.ntap; ++tap)
-                    if ((pl.pf_taps >> tap) & 1) tma_prefetch_3d(&map_x, pp + d.tap_shift[tap], pn * pl.n_box, in_ch0 + d.tap_in_ch[tap]);
+                    if ((pl.pf_taps >> tap) & 1) tma_prefetch_3d(&map_x, pp + d.tap_shift[tap], pn, in_ch0 + d.tap_in_ch[tap]);
             };
             if (pl.pf_dist > 0 && leader)
                 for (int64_t k = kbeg + S; k < kbeg + pl.pf_dist && k < kend; ++k) prefetch(k);
@@ -180,14 +191,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                     if (pl.pf_dist > 0 && kbeg + it + pl.pf_dist < kend) prefetch(kbeg + it + pl.pf_dist);
                     mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                    const int p0 = pt * pl.p_box, n0 = nn * pl.n_box;
-                    wt_tma_load_3d(st, &map_g, p0, n0, out_ch0, full0 + 8 * s);
-                    for (int tap = 0; tap < d.ntap; ++tap)
-                        wt_tma_load_3d(st + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], n0, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                    int sn = nn, sp = pt;
+                    for (int sub = 0; sub < pl.nsub; ++sub) {           // samples past the end (sn >= n) are zero-filled by the TMA unit
+                        const uint32_t sb = st + sub * pl.sub_bytes;
+                        const int p0 = sp * pl.p_box;
+                        wt_tma_load_3d(sb, &map_g, p0, sn, out_ch0, full0 + 8 * s);
+                        for (int tap = 0; tap < d.ntap; ++tap)
+                            wt_tma_load_3d(sb + pl.a_bytes + tap * pl.b_bytes, &map_x, p0 + d.tap_shift[tap], sn, in_ch0 + d.tap_in_ch[tap], full0 + 8 * s);
+                        if (++sp == pl.kt_per_plane) {
+                            sp = 0;
+                            ++sn;
+                        }
+                    }
                 }
                 __syncwarp();
-                if (++pt == pl.kt_per_plane) {
-                    pt = 0;
+                pt += pl.nsub;
+                while (pt >= pl.kt_per_plane) {
+                    pt -= pl.kt_per_plane;
                     ++nn;
                 }
                 if (++s == S) {
@@ -210,13 +230,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                    for (int tap = 0; tap < nmma; ++tap) {
-                        const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
-#pragma unroll
-                        for (int j = 0; j < WT_KT / 8; ++j)             // 32 bytes of K per MMA inside the 128-byte swizzled row
-                            umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw128(a_addr + j * 32), smem_desc_k_sw128(b_addr + j * 32), idesc,
-                                      (it > 0 || j > 0) ? 1u : 0u);
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    for (int sub = 0; sub < pl.nsub; ++sub) {
+                        const uint32_t a_addr = st + sub * pl.sub_bytes;
+                        for (int tap = 0; tap < nmma; ++tap) {
+                            const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
+                            for (int j = 0; j < pl.p_box / 8; ++j)          // 32 bytes of K per MMA inside the swizzled row
+                                umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw(a_addr + j * 32, pl.desc_hi), smem_desc_k_sw(b_addr + j * 32, pl.desc_hi),
+                                          idesc, (it > 0 || sub > 0 || j > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty0 + 8 * s);
                 }
@@ -317,14 +339,14 @@ int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* 
     {
         const uint64_t gdim[3] = {(uint64_t)d.p_out, (uint64_t)d.n, (uint64_t)d.c_out_total};
         const uint64_t gstr[2] = {(uint64_t)d.c_out_total * d.p_out * 4, (uint64_t)d.p_out * 4};
-        const uint32_t box[3] = {(uint32_t)p.p_box, (uint32_t)p.n_box, (uint32_t)p.a_rows};
-        if (int e = tma_encode_3d_f32(&map_g, gout, gdim, gstr, box, 1)) return e;
+        const uint32_t box[3] = {(uint32_t)p.p_box, 1u, (uint32_t)p.a_rows};
+        if (int e = tma_encode_3d_f32(&map_g, gout, gdim, gstr, box, p.p_box == 32 ? 1 : p.p_box == 16 ? 2 : 3)) return e;
     }
     {
         const uint64_t gdim[3] = {(uint64_t)d.p_in, (uint64_t)d.n, (uint64_t)d.c_in_total};
         const uint64_t gstr[2] = {(uint64_t)d.c_in_total * d.p_in * 4, (uint64_t)d.p_in * 4};
-        const uint32_t box[3] = {(uint32_t)p.p_box, (uint32_t)p.n_box, (uint32_t)p.n_ic};
-        if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, 1)) return e;
+        const uint32_t box[3] = {(uint32_t)p.p_box, 1u, (uint32_t)p.n_ic};
+        if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, p.p_box == 32 ? 1 : p.p_box == 16 ? 2 : 3)) return e;
     }
     static bool attr_set = false;
     if (!attr_set) {

@@ -52,8 +52,9 @@ GEOMS = {
     "g6_tcn_3ch": (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 4),
     "d3_tcn_p160": (dict(c_in=128, c_out=256, t_in=32, v_in=5, K=3), 70),                          # several N / M tiles, split-K over 2+ samples
     "d1_res_v12": (dict(c_in=32, c_out=64, t_in=64, v_in=12, kt=1), 9),
-    # planes below 32 positions with >= 1024 positions in total: TMA boxes of 16 positions x 2 samples / 4 x 8 (ragged sample tail)
-    "d4_gcn_p80_big": (dict(c_in=256, c_out=512, t_in=16, v_in=5, K=3), 15),
+    # planes below 32 positions with >= 1024 positions in total
+    "d4_gcn_p80_big": (dict(c_in=256, c_out=512, t_in=16, v_in=5, K=3), 15),                       # 64-byte swizzled sub-tiles (16 positions)
+    "d5_gcn_p8_big": (dict(c_in=512, c_out=512, t_in=8, v_in=1, K=3), 141),                        # 32-byte swizzled sub-tiles, ragged last stage
     "d5_tcn_unfolded_big": (dict(unfold=True, c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, stride=1, dil=1, t_sel=[0, 2, 4, 6]), 301),
 }
 
@@ -64,7 +65,7 @@ TMA_EXPECTED = {"d1_gcn": (1, 1), "d2_gcn": (1, 1), "d1_tcn_v12": (1, 1), "d1_tc
 
 THIN = {"g6_tcn_3ch"}
 WGRAD_TMA_EXPECTED = {"d1_gcn": 1, "d2_gcn": 1, "d1_tcn_v12": 1, "d1_tcn_v11": 0, "d0_gcn_3ch": 1, "d3_tcn_p160": 1, "d1_res_v12": 1,
-                      "d2_tcn_unfolded": 0, "g2_gcn": 0, "d4_gcn_p80_big": 0, "d5_tcn_unfolded_big": 0, "g6_tcn_3ch": 0}
+                      "d2_tcn_unfolded": 0, "g2_gcn": 0, "d4_gcn_p80_big": 1, "d5_gcn_p8_big": 1, "d5_tcn_unfolded_big": 0, "g6_tcn_3ch": 0}
 
 
 @pytest.mark.parametrize("name", list(GEOMS))
