@@ -24,9 +24,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic FLOPs per train sample, NTU-120 mlp8: 1.6 F_G + 10.4 F_D (SURVEY.md §8d / BASELINE.md §3)
-F_G, F_D = 32.24e6, 550.62e6
+# BASELINE.json configs: forward FLOPs per sample of G and D from SURVEY.md §6/§8d
+SHAPES = {
+    "ntu120": dict(dataset="ntu", n_classes=120, t_size=64, mlp_dim=8, channels=3, joints=25, f_g=32.24e6, f_d=550.62e6,
+                   name="kinetic-gan-mlp8 NTU-120 xsub shape (25x64x3, 120 classes)"),
+    "ntu60": dict(dataset="ntu", n_classes=60, t_size=64, mlp_dim=4, channels=3, joints=25, f_g=28.28e6, f_d=532.19e6,
+                  name="kinetic-gan-mlp4 NTU-60 xsub shape (25x64x3, 60 classes)"),
+    "h36m": dict(dataset="h36m", n_classes=10, t_size=32, mlp_dim=4, channels=2, joints=16, f_g=11.95e6, f_d=129.29e6,
+                 name="kinetic-gan-mlp4 Human3.6M shape (16x32x2, 10 classes)"),
+}
+SHAPE = SHAPES["ntu120"]          # the headline configuration; --shape selects another (set_shape)
+F_G, F_D = SHAPE["f_g"], SHAPE["f_d"]
 FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
-WORKLOAD = "kinetic-gan-mlp8 NTU-120 xsub shape (25x64x3, 120 classes), WGAN-GP training, n_critic=5"
+WORKLOAD = SHAPE["name"] + ", WGAN-GP training, n_critic=5"
+GEN_WORKLOAD = "generate.py generator pass, " + SHAPE["name"] + ", eval mode, no_grad"
+
+
+def set_shape(key):
+    global SHAPE, F_G, F_D, FLOP_PER_SAMPLE, WORKLOAD, GEN_WORKLOAD
+    SHAPE = SHAPES[key]
+    F_G, F_D = SHAPE["f_g"], SHAPE["f_d"]
+    FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
+    WORKLOAD = SHAPE["name"] + ", WGAN-GP training, n_critic=5"
+    GEN_WORKLOAD = "generate.py generator pass, " + SHAPE["name"] + ", eval mode, no_grad"
+
+
+def oracle_cfg():
+    from oracle import networks as onet
+
+    return onet.Config(dataset=SHAPE["dataset"], n_classes=SHAPE["n_classes"], t_size=SHAPE["t_size"], mlp_dim=SHAPE["mlp_dim"],
+                       channels=SHAPE["channels"])
 
 
 def parse():
@@ -37,6 +64,7 @@ def parse():
     ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "generate"],
                     help="train: WGAN-GP training samples/s (headline); generate: inference-only generated sequences/s (BASELINE.json configs[4])")
+    ap.add_argument("--shape", default="ntu120", choices=list(SHAPES), help="network / data shape (BASELINE.json configs); headline: ntu120")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 1024 for train, 4096 for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
@@ -106,16 +134,16 @@ def oracle_trainer(batch, per_sample_loop=True):
     from oracle import networks as onet
     from oracle.graph import SkeletonTables
 
-    cfg = onet.Config(dataset="ntu", n_classes=120, t_size=64, mlp_dim=8, channels=3)
-    tables = SkeletonTables("ntu")
+    cfg = oracle_cfg()
+    tables = SkeletonTables(SHAPE["dataset"])
     pg = onet.synth_params(onet.g_param_shapes(cfg, tables), 1, reference_init=True)
     pd = onet.synth_params(onet.d_param_shapes(cfg, tables), 2)
     tr = onet.Trainer(cfg, pg, pd, tables, per_sample_loop=per_sample_loop)
     g = torch.Generator().manual_seed(0)
 
     def batch_fn():
-        real = torch.rand(batch, 3, 64, 25, generator=g) * 2 - 1
-        labels = torch.randint(0, 120, (batch,), generator=g)
+        real = torch.rand(batch, SHAPE["channels"], SHAPE["t_size"], SHAPE["joints"], generator=g) * 2 - 1
+        labels = torch.randint(0, SHAPE["n_classes"], (batch,), generator=g)
         z = torch.randn(batch, 512, generator=g)
         alpha = torch.rand(batch, 1, 1, 1, generator=g)
         nz = [torch.randn(*s, generator=g) for s in onet.noise_shapes(cfg, batch, tables)]
@@ -156,7 +184,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": b, "note": "CPU port of the reference step (oracle/networks.py), host cores only"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d iterations of batch %d (NTU-120 mlp8) after %d warm-up" % (args.steps, b, args.warmup)},
+                         "sample": "%d iterations of batch %d (%s) after %d warm-up" % (args.steps, b, SHAPE["name"], args.warmup)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -218,8 +246,8 @@ def run_kgan(args):
     B, K, W = args.batch, args.steps, args.warmup
 
     torch.manual_seed(0)
-    G = kgan.Generator(512, 3, 120, 64, mlp_dim=8).to(dev)
-    D = kgan.Discriminator(3, 120, 64, 512).to(dev)
+    G = kgan.Generator(512, SHAPE["channels"], SHAPE["n_classes"], SHAPE["t_size"], mlp_dim=SHAPE["mlp_dim"], dataset=SHAPE["dataset"]).to(dev)
+    D = kgan.Discriminator(SHAPE["channels"], SHAPE["n_classes"], SHAPE["t_size"], 512, dataset=SHAPE["dataset"]).to(dev)
     G.train()
     tr = wg.WGANGPTrainer(G, D, comm=comm)
 
@@ -228,8 +256,8 @@ def run_kgan(args):
     POOL = 4
     host = []
     for _ in range(POOL):
-        host.append(dict(real=(torch.rand(B, 3, 64, 25, generator=gcpu) * 2 - 1).pin_memory(),
-                         labels=torch.randint(0, 120, (B,), generator=gcpu).pin_memory(),
+        host.append(dict(real=(torch.rand(B, SHAPE["channels"], SHAPE["t_size"], SHAPE["joints"], generator=gcpu) * 2 - 1).pin_memory(),
+                         labels=torch.randint(0, SHAPE["n_classes"], (B,), generator=gcpu).pin_memory(),
                          z=torch.randn(B, 512, generator=gcpu).pin_memory(),
                          alpha=torch.rand(B, 1, 1, 1, generator=gcpu).pin_memory()))
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
@@ -308,7 +336,7 @@ def run_kgan(args):
     if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
         sps, ms, cores = time_oracle(args.cpu_batch, 5, 1, first_index=4)     # one n_critic cycle: i = 5..9 after i = 4
         cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "one n_critic cycle (5 iterations, 1 G step) of batch %d, NTU-120 mlp8, after 1 warm-up" % args.cpu_batch}
+               "sample": "one n_critic cycle (5 iterations, 1 G step) of batch %d, %s, after 1 warm-up" % (args.cpu_batch, SHAPE["name"])}
 
     if comm.rank == 0:
         line = {
@@ -326,7 +354,6 @@ def run_kgan(args):
     comm.close()
 
 
-GEN_WORKLOAD = "generate.py generator pass, kinetic-gan-mlp8 NTU-120 shape (25x64x3, 120 classes), eval mode, no_grad"
 
 
 def time_oracle_generate(batch, steps, warmup, trunc=None):
@@ -339,14 +366,14 @@ def time_oracle_generate(batch, steps, warmup, trunc=None):
     from oracle.graph import SkeletonTables
 
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = onet.Config(dataset="ntu", n_classes=120, t_size=64, mlp_dim=8, channels=3)
-    tables = SkeletonTables("ntu")
+    cfg = oracle_cfg()
+    tables = SkeletonTables(SHAPE["dataset"])
     pg = onet.synth_params(onet.g_param_shapes(cfg, tables), 1, reference_init=True)
     g = torch.Generator().manual_seed(0)
 
     def once():
         z = torch.randn(batch, 512, generator=g)
-        labels = torch.randint(0, 120, (batch,), generator=g)
+        labels = torch.randint(0, SHAPE["n_classes"], (batch,), generator=g)
         nz = [torch.randn(*s, generator=g) for s in onet.noise_shapes(cfg, batch, tables)]
         tl = torch.as_tensor(np.random.normal(0, 1, (1000, cfg.latent_dim + cfg.n_classes)), dtype=torch.float32) if trunc is not None else None
         with torch.no_grad():
@@ -393,14 +420,14 @@ def run_generate(args):
     kgan.set_precision(args.precision)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
-    G = kgan.Generator(512, 3, 120, 64, mlp_dim=8).to(dev)
+    G = kgan.Generator(512, SHAPE["channels"], SHAPE["n_classes"], SHAPE["t_size"], mlp_dim=SHAPE["mlp_dim"], dataset=SHAPE["dataset"]).to(dev)
     with torch.no_grad():                       # a trained generator has non-zero noise weights; exercise that path
         for blk in G.st_gcn_networks:
             blk.noise.weight.normal_(0, 0.1)
     runner = gen.GeneratorRunner(G, B, 512, trunc=args.trunc, graphs=not args.no_graphs, device=dev)
     gcpu = torch.Generator().manual_seed(4321 + comm.rank)
     POOL = 4
-    host = [dict(z=torch.randn(B, 512, generator=gcpu).pin_memory(), labels=torch.randint(0, 120, (B,), generator=gcpu).pin_memory())
+    host = [dict(z=torch.randn(B, 512, generator=gcpu).pin_memory(), labels=torch.randint(0, SHAPE["n_classes"], (B,), generator=gcpu).pin_memory())
             for _ in range(POOL)]
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -465,7 +492,7 @@ def run_generate(args):
     if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
         sps, ms, cores = time_oracle_generate(args.cpu_batch * 8, 2, 1, args.trunc)
         cpu = {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
-               "sample": "2 generator calls of batch %d (NTU-120 mlp8, per-sample mapping loop as generator.py:84-85) after 1 warm-up" % (args.cpu_batch * 8)}
+               "sample": "2 generator calls of batch %d (%s, per-sample mapping loop as generator.py:84-85) after 1 warm-up" % (args.cpu_batch * 8, SHAPE["name"])}
     if comm.rank == 0:
         print(json.dumps({
             "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
@@ -479,6 +506,7 @@ def run_generate(args):
 
 if __name__ == "__main__":
     a = parse()
+    set_shape(a.shape)
     if a.batch is None:
         a.batch = 1024 if a.workload == "train" else 4096
     if a.workload == "generate":
