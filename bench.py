@@ -38,6 +38,8 @@ F_G, F_D = SHAPE["f_g"], SHAPE["f_d"]
 FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
 WORKLOAD = SHAPE["name"] + ", WGAN-GP training, n_critic=5"
 GEN_WORKLOAD = "generate.py generator pass, " + SHAPE["name"] + ", eval mode, no_grad"
+TRAFFIC_FILE = "r1_traffic_b1024.json"        # ncu DRAM-traffic capture of the training step (generate: r1_traffic_generate.json)
+NCU_RANGE = os.environ.get("KGAN_NCU_RANGE") == "1"   # bracket the eager roofline pass with cudaProfilerStart/Stop (ncu --profile-from-start off)
 
 
 def set_shape(key):
@@ -204,14 +206,16 @@ def make_roofline(fam, sites, passes, step_tflops):
     ai = st["flops"] / max(st["bytes"], 1.0)
     ridge = tensor_peak * 1e12 / (hbm_peak * 1e9)
     total_ms = sum(v["ms"] for v in fam.values())
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f).get(name)
+    traffic = traffic_src = None
+    try:                                        # per-family DRAM bytes per launch, tools/ncu_traffic_summary.py over the same eager pass
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
+            t = json.load(f)
+        traffic = t["families"][name]["dram_bytes_per_launch"]
+        traffic_src = "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch, per-GPU batch %s)" % (TRAFFIC_FILE, t.get("per_gpu_batch"))
     except Exception:
         pass
     r = {"kernel": name, "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
-         "algorithmic_bytes_per_launch": st["bytes"] / st["n"], "traffic": traffic, "peak_kind": peak_kind,
+         "algorithmic_bytes_per_launch": st["bytes"] / st["n"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
          "tensor": {"achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "peak_kind": peak_kind + " bf16 sustained"},
          "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_kind": peak_kind + " copy bandwidth"},
          "launches_per_step": st["n"] / passes, "avg_launch_ms": st["ms"] / st["n"], "share_of_kgan_kernel_time": st["ms"] / total_ms,
@@ -322,10 +326,15 @@ def run_kgan(args):
 
     # roofline of the dominant kernel family, measured live with CUDA events around every launch of one more pass
     tr.use_graphs = False                       # eager launches: CUDA events around every libkgan kernel
+    if NCU_RANGE:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     prof = ops.profile_start()
     for i in range(it, it + 5):
         step_resident(i)
     torch.cuda.synchronize()
+    if NCU_RANGE:
+        torch.cuda.profiler.stop()
     fam = ops.profile_stop(prof)
     sites = fam.pop("_sites")
     tr.use_graphs = graphs
@@ -476,11 +485,18 @@ def run_generate(args):
         it += K
         e2e = {"value": B * comm.world_size * K / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": out.numel() * out.element_size()}
+    global TRAFFIC_FILE
+    TRAFFIC_FILE = "r1_traffic_generate.json"
     runner.graphs = False
+    if NCU_RANGE:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     prof = ops.profile_start()
     for i in range(it, it + 3):
         step_resident(i)
     torch.cuda.synchronize()
+    if NCU_RANGE:
+        torch.cuda.profiler.stop()
     fam = ops.profile_stop(prof)
     sites = fam.pop("_sites")
     runner.graphs = not args.no_graphs and args.trunc is None

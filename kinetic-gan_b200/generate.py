@@ -7,7 +7,17 @@ mode, :85-93 latent / label construction and `generator(z, labels, trunc)`), res
   * W-space truncation (generate.py default `--trunc_mode w`) runs the 1000 mapping passes of generator.py:97-108 as one
     batched pass (models/generator.py: Generator.truncate).
 
-File outputs (.npy / labels .pkl, generate.py:105-123) are host I/O and out of scope."""
+`generate_dataset` / `main` are the reference script itself on top of that runner: same options
+(generate.py:27-47), same sampling loop (:70-103), same output files in the same formats (:105-123), with the generated
+batches accumulated in one preallocated host array instead of an O(n^2) `np.concatenate` per iteration.
+
+    python -m kgan_b200.generate --model runs/kinetic-gan/exp1/models/generator_10000.pth --n_classes 60 --gen_qtd 1000
+"""
+import argparse
+import os
+import pickle
+from collections import Counter
+
 import numpy as np
 import torch
 
@@ -82,3 +92,124 @@ def class_conditioned_batch(n_classes, per_class, latent_dim=512, seed=None):
     z = torch.as_tensor(rng.normal(0, 1, (n_classes * per_class, latent_dim)), dtype=torch.float32)
     labels = torch.as_tensor(np.array([c for _ in range(per_class) for c in range(n_classes)]), dtype=torch.long)
     return z, labels
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generate.py as a function + CLI
+# ------------------------------------------------------------------------------------------------------------------
+def trunc_z(latent, mean_size, truncation):
+    """generate.py:14-21, truncation trick on Z: pull every latent towards the mean of `mean_size` fresh N(0,1) draws
+    (host RNG, as the reference); one vector expression instead of the per-row loop."""
+    t = torch.as_tensor(np.random.normal(0, 1, (mean_size, *latent.shape[1:])), dtype=latent.dtype, device=latent.device)
+    m = t.mean(0, keepdim=True)
+    return m + truncation * (latent - m)
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--batch_size", type=int, default=10, help="How many samples PER CLASS (each iteration of course)")
+    p.add_argument("--latent_dim", type=int, default=512, help="dimensionality of the latent space")
+    p.add_argument("--mlp_dim", type=int, default=4, help="mapping network depth")
+    p.add_argument("--n_classes", type=int, default=60, help="number of classes for dataset")
+    p.add_argument("--label", type=int, default=-1, help="Sepecific label to generate, -1 for all classes")
+    p.add_argument("--t_size", type=int, default=64, help="size of each temporal dimension")
+    p.add_argument("--v_size", type=int, default=25, help="size of each spatial dimension (vertices)")
+    p.add_argument("--channels", type=int, default=3, help="number of channels (coordinates)")
+    p.add_argument("--dataset", type=str, default="ntu", help="dataset")
+    p.add_argument("--model", type=str, default="runs/kinetic-gan/exp1/models/generator_ntu_xsub_mlp4_1370000.pth", help="path to gen model")
+    p.add_argument("--stochastic", action='store_true', help="Generate/Get one sample and verify stochasticity")
+    p.add_argument("--stochastic_file", type=str, default="-", help="Read one sample and verify stochasticity")
+    p.add_argument("--stochastic_index", type=int, default=0, help="Sample index to get your latent point")
+    p.add_argument("--gen_qtd", type=int, default=1000, help="How many samples to generate per class")
+    p.add_argument("--trunc", type=float, default=0.95, help="Truncation sigma")
+    p.add_argument("--trunc_mode", type=str, default='w', choices=['z', 'w', '-'], help="Truncation mode (check paper for details)")
+    p.add_argument("--mean_size", type=int, default=1000, help="Samples to estimate mean")
+    # not in the reference
+    p.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4)")
+    p.add_argument("--out", type=str, default=None, help="output directory (default: actions/ of the latest run, generate.py:24-26)")
+    return p
+
+
+def output_stem(opt):
+    """File-name stem of generate.py:113-123."""
+    return (str(opt.n_classes if opt.label == -1 else opt.label) + '_' + str(opt.gen_qtd)
+            + ('_trunc' + str(opt.trunc) if opt.trunc_mode != '-' else '') + ('_stochastic' if opt.stochastic else ''))
+
+
+def generate_dataset(generator, opt, device=None):
+    """The sampling loop generate.py:70-103.  Returns (data, z, labels) exactly as the reference writes them:
+    data (n, C, T, V[, 1 for ntu]) float32, z (n, latent) float32 (after Z truncation, as the reference stores it),
+    labels (2, n) int (the label row duplicated, generate.py:110)."""
+    device = device or next(generator.parameters()).device
+    generator.eval()
+    classes = list(np.arange(opt.n_classes)) if opt.label == -1 else [opt.label]
+    qtd = opt.batch_size
+    rounds = -(-opt.gen_qtd // qtd)                         # every class gains `qtd` samples per round: all finish together
+    batch = qtd * len(classes)
+    total = rounds * batch
+    runner = GeneratorRunner(generator, batch, opt.latent_dim, trunc=opt.trunc if opt.trunc_mode == 'w' else None,
+                             graphs=device.type == "cuda", device=device)
+    imgs = z_all = None
+    labels_all = np.empty(total, dtype=np.int64)
+    if opt.stochastic:                                      # one latent point repeated (generate.py:81-83)
+        if opt.stochastic_file != '-':
+            z0 = np.expand_dims(np.load(opt.stochastic_file)[opt.stochastic_index], 0)
+        else:
+            z0 = np.random.normal(0, 1, (1, opt.latent_dim))
+        z = torch.as_tensor(z0, dtype=torch.float32).repeat(batch, 1)
+    for r in range(rounds):
+        if not opt.stochastic:
+            z = torch.as_tensor(np.random.normal(0, 1, (batch, opt.latent_dim)), dtype=torch.float32)
+        if opt.trunc_mode == 'z':
+            z = trunc_z(z, opt.mean_size, opt.trunc)
+        labels_np = np.array([num for _ in range(qtd) for num in classes])
+        runner(z, torch.as_tensor(labels_np, dtype=torch.long))
+        gen = runner.to_host() if device.type == "cuda" else runner.out
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        if imgs is None:
+            imgs = np.empty((total,) + tuple(gen.shape[1:]), np.float32)
+            z_all = np.empty((total, opt.latent_dim), np.float32)
+        sl = slice(r * batch, (r + 1) * batch)
+        imgs[sl], z_all[sl], labels_all[sl] = gen.numpy(), z.numpy(), labels_np
+    counts = Counter(labels_all.tolist())
+    assert all(counts[c] >= opt.gen_qtd for c in classes)
+    if opt.dataset == 'ntu':
+        imgs = np.expand_dims(imgs, axis=-1)
+    labels2 = np.concatenate((np.expand_dims(labels_all, 0), np.expand_dims(labels_all, 0)), axis=0)
+    return imgs, z_all, labels2
+
+
+def write_outputs(actions_out, opt, imgs, z_all, labels2):
+    stem = os.path.join(actions_out, output_stem(opt))
+    with open(stem + '_gen_data.npy', 'wb') as f:
+        np.save(f, imgs)
+    with open(stem + '_gen_z.npy', 'wb') as f:
+        np.save(f, z_all)
+    with open(stem + '_gen_label.pkl', 'wb') as f:
+        pickle.dump(labels2, f)
+    return stem
+
+
+def main(argv=None):
+    from .models.generator import Generator
+    from .train import check_runs
+
+    opt = build_parser().parse_args(argv)
+    print(opt)
+    actions_out = opt.out
+    if actions_out is None:
+        actions_out = os.path.join(check_runs('kinetic-gan', id=-1), 'actions')
+    os.makedirs(actions_out, exist_ok=True)
+    with open(os.path.join(os.path.dirname(actions_out.rstrip('/')) or '.', "gen_config.txt"), "w") as f:
+        f.write(os.path.basename(__file__) + '|' + str(opt))
+    device = torch.device("cuda", 0)
+    ops.set_precision(opt.precision)
+    generator = Generator(opt.latent_dim, opt.channels, opt.n_classes, opt.t_size, mlp_dim=opt.mlp_dim, dataset=opt.dataset).to(device)
+    generator.load_state_dict(torch.load(opt.model, map_location=device), strict=False)          # generate.py:66
+    imgs, z_all, labels2 = generate_dataset(generator, opt, device)
+    print(write_outputs(actions_out, opt, imgs, z_all, labels2))
+
+
+if __name__ == "__main__":
+    main()

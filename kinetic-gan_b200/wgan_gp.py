@@ -129,6 +129,8 @@ class WGANGPTrainer:
         st = {k: torch.empty_like(v) for k, v in dict(real=real, labels=labels, z=z, alpha=alpha).items()}
         for k, v in dict(real=real, labels=labels, z=z, alpha=alpha).items():
             st[k].copy_(v)
+        # the warm-up and capture passes run G in training mode: keep its BatchNorm running statistics as they were
+        buffers = [(b, b.detach().clone()) for m in (self.G, self.D) for b in m.buffers()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):       # warm-up on a side stream: builds every cached table / descriptor / workspace
@@ -151,6 +153,9 @@ class WGANGPTrainer:
             g_out = self._g_grads(st["labels"], st["z"])
         l2 = ops.launches
         ops.clear_temporary_packs()
+        with torch.no_grad():
+            for b, saved in buffers:
+                b.copy_(saved)
         self._graphs = dict(static=st, d=gd, g=gg, d_out=d_out, g_out=g_out, d_launches=l1 - l0, g_launches=l2 - l1)
 
     def d_step(self, real, labels, z, alpha=None, noises=None):
