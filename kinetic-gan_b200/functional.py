@@ -22,6 +22,38 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# Two rules keep a backward sweep from doing work nobody reads (torch's built-in convolution / bmm nodes follow both, custom
+# Functions have to do it themselves):
+#   * undefined incoming gradients are NOT materialised as zeros (`set_materialize_grads(False)`): in the gradient penalty
+#     the forward nodes of D(x_hat) hang off the second-order graph only through LeakyReLU masks, whose derivative is zero -
+#     with materialisation on, autograd would run their whole backward (data, weight and adjacency gradients) on zeros;
+#   * inside `data_grads_only()` a backward computes the gradient of its data input only.  `ctx.needs_input_grad` says
+#     whether an input REQUIRES grad, not whether this particular `autograd.grad(..., inputs=x)` call asked for it: the
+#     first-order pass of the penalty (kinetic-gan.py:104) wants d/dx_hat alone, yet every node would also produce its
+#     weight / bias / adjacency gradients only for the engine to drop them.
+_data_only = False
+
+
+class data_grads_only:
+    """Context manager: Function backwards executed inside skip parameter-side gradients (weights, biases, adjacency,
+    label embedding).  Used around the `autograd.grad(outputs, inputs=x_hat, create_graph=True)` call of the gradient
+    penalty; the graph built there still carries every parameter dependence (TapConvDgrad / AdjMixDx nodes are created
+    with the live weights), so the following `backward()` is unchanged."""
+
+    def __enter__(self):
+        global _data_only
+        self.prev, _data_only = _data_only, True
+
+    def __exit__(self, *exc):
+        global _data_only
+        _data_only = self.prev
+
+
+def _want(ctx, i):
+    """Parameter-side gradient i of this node wanted?"""
+    return ctx.needs_input_grad[i] and not _data_only
+
+
 _SUM_T = {}
 
 
@@ -40,15 +72,18 @@ class TapConv(Function):
     @staticmethod
     def forward(ctx, x, w, geom):
         ctx.geom = geom
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, w)
         return ops.tapconv_fwd(_c(x), _c(w), geom.fwd)
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None, None
         x, w = ctx.saved_tensors
         go = _c(go)
         gx = TapConvDgrad.apply(go, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(x, go, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
+        gw = TapConvWgrad.apply(x, go, ctx.geom, w.shape) if _want(ctx, 1) else None
         return gx, gw, None
 
 
@@ -56,15 +91,18 @@ class TapConvDgrad(Function):
     @staticmethod
     def forward(ctx, go, w, geom):
         ctx.geom = geom
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(go, w)
         return ops.tapconv_fwd(_c(go), _c(w), geom.dgrad)
 
     @staticmethod
     def backward(ctx, h):
+        if h is None:
+            return None, None, None
         go, w = ctx.saved_tensors
         h = _c(h)
         ggo = TapConv.apply(h, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(h, go, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
+        gw = TapConvWgrad.apply(h, go, ctx.geom, w.shape) if _want(ctx, 1) else None
         return ggo, gw, None
 
 
@@ -72,11 +110,14 @@ class TapConvWgrad(Function):
     @staticmethod
     def forward(ctx, x, go, geom, w_shape):
         ctx.geom = geom
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, go)
         return ops.tapconv_wgrad(_c(x), _c(go), geom.fwd, tuple(w_shape))
 
     @staticmethod
     def backward(ctx, hw):
+        if hw is None:
+            return None, None, None, None
         x, go = ctx.saved_tensors
         hw = _c(hw)
         gx = TapConvDgrad.apply(go, hw, ctx.geom) if ctx.needs_input_grad[0] else None
@@ -91,18 +132,21 @@ class TapConvEp(Function):
     def forward(ctx, x, w, bias, add, geom, act):
         ctx.geom, ctx.act = geom, act
         ctx.add_bcast = add is not None and add.shape[2] == 1 and geom.t_out > 1
+        ctx.set_materialize_grads(False)
         out = ops.tapconv_fwd(_c(x), _c(w), geom.fwd, bias, None if add is None else _c(add), act)
         ctx.save_for_backward(x, w, out)
         return out
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None, None, None, None, None
         x, w, out = ctx.saved_tensors
         go = _c(go)
         gz = ActGrad.apply(go, out, ctx.act) if ctx.act != ACT_NONE else go
         gx = TapConvDgrad.apply(gz, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(x, gz, ctx.geom, w.shape) if ctx.needs_input_grad[1] else None
-        gb = ChanSum.apply(gz) if ctx.needs_input_grad[2] else None
+        gw = TapConvWgrad.apply(x, gz, ctx.geom, w.shape) if _want(ctx, 1) else None
+        gb = ChanSum.apply(gz) if _want(ctx, 2) else None
         ga = None
         if ctx.needs_input_grad[3]:
             ga = PlaneSpmm.apply(gz, sum_t_table(ctx.geom.t_out, ctx.geom.v_out)) if ctx.add_bcast else gz
@@ -115,30 +159,36 @@ class TapConvEp(Function):
 class AdjMix(Function):
     @staticmethod
     def forward(ctx, x, A):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, A)
         return ops.adjmix_fwd(_c(x), _c(A))
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None
         x, A = ctx.saved_tensors
         go = _c(go)
         gx = AdjMixDx.apply(go, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(x, go, A.shape[0], A) if ctx.needs_input_grad[1] else None
+        gA = AdjMixDA.apply(x, go, A.shape[0], A) if _want(ctx, 1) else None
         return gx, gA
 
 
 class AdjMixDx(Function):
     @staticmethod
     def forward(ctx, g, A):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, A)
         return ops.adjmix_bwd_x(_c(g), _c(A))
 
     @staticmethod
     def backward(ctx, h):
+        if h is None:
+            return None, None
         g, A = ctx.saved_tensors
         h = _c(h)
         gg = AdjMix.apply(h, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(h, g, A.shape[0], A) if ctx.needs_input_grad[1] else None
+        gA = AdjMixDA.apply(h, g, A.shape[0], A) if _want(ctx, 1) else None
         return gg, gA
 
 
@@ -150,11 +200,14 @@ class AdjMixDA(Function):
     @staticmethod
     def forward(ctx, x, g, k, support=None):
         mask = None if support is None else _c(support.detach())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, g)
         return ops.adjmix_bwd_a(_c(x), _c(g), k, mask)
 
     @staticmethod
     def backward(ctx, hA):
+        if hA is None:
+            return None, None, None, None
         x, g = ctx.saved_tensors
         hA = _c(hA)
         gx = AdjMixDx.apply(g, hA) if ctx.needs_input_grad[0] else None
@@ -171,11 +224,14 @@ class ActGrad(Function):
     @staticmethod
     def forward(ctx, go, y, act):
         ctx.act = act
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(go, y)
         return ops.act_bwd(_c(go), y, act)
 
     @staticmethod
     def backward(ctx, h):
+        if h is None:
+            return None, None, None
         go, y = ctx.saved_tensors
         h = _c(h)
         ggo = ActGrad.apply(h, y, ctx.act) if ctx.needs_input_grad[0] else None
@@ -191,11 +247,12 @@ class ChanSum(Function):
     @staticmethod
     def forward(ctx, g):
         ctx.shape = g.shape
+        ctx.set_materialize_grads(False)
         return ops.chan_reduce(_c(g))
 
     @staticmethod
     def backward(ctx, h):
-        return h.view(1, -1, 1, 1).expand(ctx.shape)
+        return None if h is None else h.view(1, -1, 1, 1).expand(ctx.shape)
 
 
 class ChanSumMul(Function):
@@ -203,11 +260,14 @@ class ChanSumMul(Function):
 
     @staticmethod
     def forward(ctx, g, m):
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, m)
         return ops.chan_reduce(_c(g), _c(m))
 
     @staticmethod
     def backward(ctx, h):
+        if h is None:
+            return None, None
         g, m = ctx.saved_tensors
         hv = h.view(1, -1, 1, 1)
         gg = hv * m if ctx.needs_input_grad[0] else None
@@ -223,17 +283,20 @@ class NoiseAct(Function):
     def forward(ctx, a, b, noise, nw, act):
         ctx.act = act
         out = ops.epilogue_fwd(_c(a), None if b is None else _c(b), None, _c(nw.reshape(-1)), _c(noise), act)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(out, noise)
         ctx.nw_shape = nw.shape
         return out
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None, None, None, None
         out, noise = ctx.saved_tensors
         gz = ActGrad.apply(_c(go), out, ctx.act) if ctx.act != ACT_NONE else _c(go)
         ga = gz if ctx.needs_input_grad[0] else None
         gb = gz if ctx.needs_input_grad[1] else None
-        gnw = ChanSumMul.apply(gz, noise).view(ctx.nw_shape) if ctx.needs_input_grad[3] else None
+        gnw = ChanSumMul.apply(gz, noise).view(ctx.nw_shape) if _want(ctx, 3) else None
         return ga, gb, None, gnw, None
 
 
@@ -244,10 +307,13 @@ class PlaneSpmm(Function):
     @staticmethod
     def forward(ctx, x, table):
         ctx.table = table
+        ctx.set_materialize_grads(False)
         return ops.plane_spmm(_c(x), table)
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None
         return PlaneSpmm.apply(_c(go), ctx.table.T), None
 
 
@@ -257,12 +323,15 @@ class LabelConcat(Function):
     @staticmethod
     def forward(ctx, e, x):
         ctx.ncls = e.shape[1]
+        ctx.set_materialize_grads(False)
         return ops.label_concat(_c(e), _c(x))
 
     @staticmethod
     def backward(ctx, go):
+        if go is None:
+            return None, None
         ge, gx = LabelSplit.apply(_c(go), ctx.ncls)
-        return (ge if ctx.needs_input_grad[0] else None), (gx if ctx.needs_input_grad[1] else None)
+        return (ge if _want(ctx, 0) else None), (gx if ctx.needs_input_grad[1] else None)
 
 
 class LabelSplit(Function):

@@ -11,7 +11,7 @@
 import numpy as np
 import torch
 
-from . import ops
+from . import functional, ops
 
 
 def compute_gradient_penalty(D, real_samples, fake_samples, labels, alpha=None, return_gradients=False):
@@ -24,8 +24,11 @@ def compute_gradient_penalty(D, real_samples, fake_samples, labels, alpha=None, 
                                    fake_samples.contiguous()).requires_grad_(True)
     d_interpolates = D(interpolates, labels)
     fake = torch.ones(n, 1, dtype=real_samples.dtype, device=real_samples.device)
-    gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=fake, create_graph=True,
-                                    retain_graph=True, only_inputs=True)[0]
+    # only d/d(interpolates) is asked for: skip the weight / bias / adjacency gradients every node would otherwise compute
+    # for the engine to drop (functional.data_grads_only); the graph built here still depends on all parameters
+    with functional.data_grads_only():
+        gradients = torch.autograd.grad(outputs=d_interpolates, inputs=interpolates, grad_outputs=fake, create_graph=True,
+                                        retain_graph=True, only_inputs=True)[0]
     flat = gradients.reshape(n, -1)
     gradient_penalty = ((flat.norm(2, dim=1) - 1) ** 2).mean()
     return (gradient_penalty, gradients) if return_gradients else gradient_penalty

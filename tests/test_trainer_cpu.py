@@ -71,3 +71,36 @@ def test_ddp_two_ranks_gloo(tmp_path):
     c = torch.load(os.path.join(str(tmp_path), "d_flat_w1_r0.pt"))
     assert torch.equal(a, b)                                   # replicas stay identical
     assert (a - c).abs().max().item() < 1e-9                   # == global-batch update
+
+
+def test_critic_step_runs_no_unread_backward_work(emu):
+    """Launch census of one critic step (kinetic-gan.py:137-154).  The gradient penalty's first-order pass asks for d/dx_hat
+    only, and the forward nodes of D(x_hat) receive no gradient from the second-order graph (LeakyReLU masks are piecewise
+    constant): no weight gradient, bias reduction or adjacency gradient may run for them, and no backward sweep on
+    materialised zeros (functional.py: set_materialize_grads(False) / data_grads_only)."""
+    import collections
+
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    ops = kgan.ops
+    cfg, n = CASES["ntu_small"]["cfg"], 3
+    G, D = build(cfg, torch.float32)
+    tr = wg.WGANGPTrainer(G, D)
+    cnt = collections.Counter()
+    for name in ("tapconv_fwd", "tapconv_wgrad", "adjmix_bwd_a", "adjmix_bwd_x", "chan_reduce", "act_bwd"):
+        f = getattr(ops, name)
+
+        def wrap(*a, _f=f, _n=name, **k):
+            cnt[(_n, a[0].shape[0])] += 1
+            return _f(*a, **k)
+
+        setattr(ops, name, wrap)
+    xi = inputs(cfg, n, 3)
+    tr._d_grads(xi["real"], xi["labels"], xi["z"], xi["alpha"])
+    convs = 6 + 6 + 4 + 1                 # graph convs, temporal convs, residual convs, head (discriminator.py:29-34,47-50)
+    # concatenated real+fake pass (batch 2n): one weight gradient per conv (+ the label-fold GEMM of the first layer)
+    assert cnt[("tapconv_wgrad", 2 * n)] == convs + 1
+    # x_hat path (batch n): one weight gradient per conv, from the second-order graph only
+    assert cnt[("tapconv_wgrad", n)] == convs
+    assert cnt[("adjmix_bwd_a", n)] == 6 and cnt[("adjmix_bwd_x", n)] == 6
+    assert cnt[("chan_reduce", n)] == 0   # d(penalty)/d(bias) == 0 exactly: never computed
+    assert cnt[("act_bwd", n)] == 2 * 6   # mask applied once in the first-order pass, once in the second-order pass
