@@ -77,6 +77,22 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
     }
 }
 
+// planes below one warp's worth of positions (the generator's first blocks: 1, 4 or 20 positions per plane): one thread per
+// element, consecutive threads on consecutive addresses; the warp-per-plane kernel above would leave 31 / 28 / 12 lanes idle
+__global__ void __launch_bounds__(PT) epilogue_fwd_small_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
+                                                            const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
+                                                            unsigned total, unsigned c, unsigned p, int act) {
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned pl = e / p, pp = e - pl * p;
+        const unsigned nn = pl / c, cc = pl - nn * c;
+        float v = a[e];
+        if (b) v += b[e];
+        if (bias) v += __ldg(bias + cc);
+        if (nw) v = fmaf(__ldg(nw + cc), __ldg(noise + nn * p + pp), v);
+        out[e] = apply_act(v, act);
+    }
+}
+
 // 16-byte vector variant (numel % 4 == 0, 16-byte aligned pointers)
 __global__ void __launch_bounds__(PT) act_bwd4_k(const float4* __restrict__ go, const float4* __restrict__ o, float4* __restrict__ gz, int64_t n4,
                                                   int act) {
@@ -399,7 +415,11 @@ extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bi
     KGAN_REQUIRE((nw == nullptr) == (noise == nullptr), "epilogue_fwd: nw and noise go together");
     const int vec = (p & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(noise) |
                                       reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec);
+    if (p < 32 && (int64_t)n * c * p < (1ll << 31))
+        epilogue_fwd_small_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, (unsigned)((int64_t)n * c * p),
+                                                                                          (unsigned)c, (unsigned)p, act);
+    else
+        epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec);
     return check_launch("epilogue_fwd");
 }
 

@@ -49,6 +49,7 @@ struct TmaPlan {
     int64_t groups32;                             // 32-row M groups: ceil(n / n_box) * cps
     int m_tiles, num_tiles, stages, smem_bytes;
     int a_lbo, a_sbo;                             // A descriptor strides (bytes): between 32-position M groups / between 8-channel K groups
+    int kmajor;                                   // 1: one-position planes (Linear layers): A is a K-major [128 samples] x [32 channels] box
     int pf_tiles;                                 // L2 prefetch distance in tiles of this CTA (0: off)
     uint32_t pf_taps;                             // taps whose boxes are prefetched (temporal shifts of the same channels are near-duplicates)
 };
@@ -57,12 +58,24 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
 
 static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     if (d.tma_mode != 1) return false;
-    if ((d.p_in & 3) || (d.p_out & 3)) return false;               // global strides / box origins must be multiples of 16 bytes
-    for (int t = 0; t < d.ntap; ++t)
-        if (d.tap_shift[t] & 3) return false;                      // unaligned box origin: the TMA unit faults
+    // One-position planes (nn.Linear: the mapping network, the generator's first block at T = V = 1): the activations are an
+    // (N, C) row-major matrix, i.e. a plain K-major operand - one [128 samples] x [32 channels] box per stage in the standard
+    // SWIZZLE_128B layout.  (As an "MN-major" operand they would need a box along the sample axis, which is strided.)
+    static const bool no_kmajor = getenv("KGAN_TMA_NO_KMAJOR") != nullptr;
+    p.kmajor = (d.p_in == 1 && d.p_out == 1 && out_plane(d) == 1 && !no_kmajor) ? 1 : 0;
+    if (p.kmajor) {
+        if (d.c_in_total & 3) return false;                        // row stride of the (N, C) matrix must be a multiple of 16 bytes
+        for (int t = 0; t < d.ntap; ++t)
+            if (d.tap_shift[t] != 0) return false;
+    } else {
+        if ((d.p_in & 3) || (d.p_out & 3)) return false;           // global strides / box origins must be multiples of 16 bytes
+        for (int t = 0; t < d.ntap; ++t)
+            if (d.tap_shift[t] & 3) return false;                  // unaligned box origin: the TMA unit faults
+    }
     if (!tapconv_umma_nsplit(d, &p.n_cta, &p.n_split, &p.n_rows, &p.tmem_cols, &p.nkt)) return false;
     p.p_shift = 5;
     while (p.p_shift > 2 && (d.p_out & ((1 << p.p_shift) - 1))) --p.p_shift;
+    if (p.kmajor) p.p_shift = 0;                                   // M group = 32 samples x 1 position (the epilogue's row -> (sample, position) rule)
     p.p_box = 1 << p.p_shift;
     p.n_box = 32 / p.p_box;
     p.cps = d.p_out / p.p_box;
@@ -111,6 +124,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
            (1ull << 61);
+}
+
+// K-major 32-bit operand, SWIZZLE_128B (layout type 2): 128-byte rows (32 K elements), 8-row atoms of 1024 bytes (SBO), LBO unused;
+// a K step of 8 elements advances the start address by 32 bytes inside the atom.
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 struct TmaTile {
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
     const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
     const int kiters = pl.nkt * d.ntap;
-    const bool use_tma = pl.p_box == 32;                             // else: cp.async producers (warps 10-13)
+    const bool use_tma = pl.p_box == 32 || pl.kmajor;                // else: cp.async producers (warps 10-13)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -256,7 +275,9 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                         mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
                         const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
                         const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
-                        if (use_tma) {
+                        if (pl.kmajor) {
+                            tma_load_3d(a_dst, &tmap, ch0, tc.mt * UM, 0, full0 + 8 * s);      // (channel, sample, -): rows past n / channels past C read zero
+                        } else if (use_tma) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
                         }
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
         // ===== MMA issuer (whole warp waits, one elected lane issues) =====
         {
             const bool leader = elect_one();
-            const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (1u << 15);          // A operand MN-major
+            const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (pl.kmajor ? 0u : (1u << 15));      // A operand MN-major unless kmajor
             const uint32_t b_lbo = pl.n_cta * 16;
             int s = 0, ti = 0;
             uint32_t ph = 0;
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                         const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
                         for (int j = 0; j < UK / 8; ++j)
-                            umma_tf32(acc, smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
+                            umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
                                       smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
                         umma_commit(empty0 + 8 * s);
                     }
@@ -465,8 +486,17 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     const cuuint64_t gstr[2] = {(cuuint64_t)d.c_in_total * d.p_in * 4, (cuuint64_t)d.p_in * 4};
     const cuuint32_t box[3] = {(cuuint32_t)p.p_box, (cuuint32_t)p.n_box, 32u};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = p.p_box != 32 ? CUDA_SUCCESS : enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = CUDA_SUCCESS;
+    if (p.kmajor) {                                                // (channel, sample, 1): 128 sample rows of 32 channels, SWIZZLE_128B
+        const cuuint64_t kdim[3] = {(cuuint64_t)d.c_in_total, (cuuint64_t)d.n, 1};
+        const cuuint64_t kstr[2] = {(cuuint64_t)d.c_in_total * 4, (cuuint64_t)d.c_in_total * 4 * (cuuint64_t)d.n};
+        const cuuint32_t kbox[3] = {32u, (cuuint32_t)UM, 1u};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), kdim, kstr, kbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (p.p_box == 32) {
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return 1;
@@ -485,7 +515,7 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     }
     (void)pmap;                                                    // the shift form replaces the position map
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_tma_k<<<grid, p.p_box == 32 ? TM_THREADS : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
+    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
     return check_launch("tapconv_fwd_tma");
 }
 

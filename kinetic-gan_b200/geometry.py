@@ -136,7 +136,10 @@ class TapConvGeom:
                         pmap[dt, q] = p
                         assert inv[dt, p] == -1, "position map must be injective per tap"
                         inv[dt, p] = q
-        taps = [(k, dt) for k in range(K) for dt in range(kt)]
+        # temporal taps that only ever read zero padding (a 3-tap kernel on a 1-frame plane: the generator's first block) are
+        # dropped from the contraction; their weight gradients are exactly zero (the weight-gradient kernels clear dw first)
+        live = [dt for dt in range(kt) if (pmap[dt] >= 0).any()]
+        taps = [(k, dt) for k in range(K) for dt in live]
         self.fwd = TapDesc(
             c_in_total=K * c_in, p_in=self.p_in, c_out_total=c_out, p_out=self.p_out, ntap=len(taps), ck=c_in, co=c_out,
             groups=1, g_in=0, g_out=0, g_w=0, w_oc=w_cin * kt, w_ic=kt,
@@ -144,9 +147,9 @@ class TapConvGeom:
             tap_row=[dt for k, dt in taps], pmap=pmap, t_out=self.t_out, v_out=self.v_out)
         # data gradient: same kernel, roles of (oc, ic) swapped, inverse map, one group per channel block
         self.dgrad = TapDesc(
-            c_in_total=c_out, p_in=self.p_out, c_out_total=K * c_in, p_out=self.p_in, ntap=kt, ck=c_out, co=c_in,
+            c_in_total=c_out, p_in=self.p_out, c_out_total=K * c_in, p_out=self.p_in, ntap=len(live), ck=c_out, co=c_in,
             groups=K, g_in=0, g_out=c_in, g_w=c_out * w_cin * kt, w_oc=kt, w_ic=w_cin * kt,
-            tap_in_ch=[0] * kt, tap_w_off=[w_ic0 * kt + dt for dt in range(kt)], tap_row=list(range(kt)), pmap=inv, t_out=t_in,
+            tap_in_ch=[0] * len(live), tap_w_off=[w_ic0 * kt + dt for dt in live], tap_row=list(live), pmap=inv, t_out=t_in,
             v_out=v_in)
 
 

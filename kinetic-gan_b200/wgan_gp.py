@@ -190,7 +190,9 @@ class WGANGPTrainer:
                     st[k].copy_(v, non_blocking=True)
             g["g"].replay()
             ops.launches += g["g_launches"]
-            g_loss = g["g_out"]
+            # the two graphs share one memory pool: the critic graph's temporaries may occupy the bytes of this output, so
+            # hand out a copy that survives the next d_step replay
+            g_loss = g["g_out"].clone()
         else:
             g_loss = self._g_grads(labels, z, noises)
         self._reduce(self.fg)

@@ -97,7 +97,7 @@ def test_adjmix_large_rows():
     assert rel(ops.adjmix_bwd_a(cu(x), cu(g), k), emu.adjmix_bwd_a(dbl(x), dbl(g), k)) < TOL
 
 
-@pytest.mark.parametrize("shape", [(3, 5, 4, 7), (2, 512, 4, 1), (33, 3, 64, 25)])
+@pytest.mark.parametrize("shape", [(3, 5, 4, 7), (2, 512, 4, 1), (33, 3, 64, 25), (9, 7, 1, 1), (4, 8, 4, 5)])
 def test_pointwise(shape):
     n, c, t, v = shape
     a, b, o = rnd(*shape, seed=1), rnd(*shape, seed=2), rnd(*shape, seed=3)

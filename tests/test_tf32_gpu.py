@@ -46,7 +46,10 @@ GEOMS = {
     "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 160),
     "d4_res": (dict(c_in=256, c_out=512, t_in=16, v_in=5, kt=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40),
     "ragged_k": (dict(c_in=50, c_out=24, t_in=9, v_in=7, kt=3, pad=1), 21),
-    "mlp_632": (dict(c_in=632, c_out=632, t_in=1, v_in=1), 300),
+    "mlp_632": (dict(c_in=632, c_out=632, t_in=1, v_in=1), 300),                                   # one-position planes: K-major TMA boxes
+    "mlp_522": (dict(c_in=522, c_out=522, t_in=1, v_in=1), 300),                                   # row stride not a multiple of 16 bytes: gather kernel
+    "g0_gcn_p1": (dict(c_in=632, c_out=512, t_in=1, v_in=1, K=3), 260),                            # channel-block taps of a K-major operand, ragged K tail
+    "g0_tcn_p1": (dict(c_in=512, c_out=512, t_in=1, v_in=1, kt=3, pad=1), 520),                    # 2 of 3 taps only read padding: pruned
     "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64),
     "d0_gcn_3ch": (dict(c_in=3, c_out=32, t_in=64, v_in=25, K=3, w_cin=123, w_ic0=120), 4),
     "g6_tcn_3ch": (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 4),
@@ -60,7 +63,8 @@ GEOMS = {
 
 
 TMA_EXPECTED = {"d1_gcn": (1, 1), "d2_gcn": (1, 1), "d1_tcn_v12": (1, 1), "d1_tcn_v11": (0, 0), "d4_gcn_p80": (1, 1), "d5_gcn_p8": (1, 1),
-                "d2_tcn_unfolded": (1, 1), "d5_tcn_unfolded": (1, 1), "d2_tcn_select": (0, 0), "ragged_k": (0, 0)}
+                "d2_tcn_unfolded": (1, 1), "d5_tcn_unfolded": (1, 1), "d2_tcn_select": (0, 0), "ragged_k": (0, 0),
+                "mlp_632": (1, 1), "mlp_522": (0, 0), "g0_gcn_p1": (1, 1), "g0_tcn_p1": (1, 1)}
 
 
 THIN = {"g6_tcn_3ch"}
