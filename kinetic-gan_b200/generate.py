@@ -5,7 +5,9 @@ mode, :85-93 latent / label construction and `generator(z, labels, trunc)`), res
   * the whole forward pass - mapping network, 7 blocks, per-block noise draws - is captured ONCE into a CUDA graph
     fed from static (z, labels) buffers, so a call is two small copies and one graph launch;
   * W-space truncation (generate.py default `--trunc_mode w`) runs the 1000 mapping passes of generator.py:97-108 as one
-    batched pass (models/generator.py: Generator.truncate).
+    batched pass (models/generator.py: Generator.truncate);
+  * eval-mode BatchNorm is folded into the convolution in front of it (Generator.fold_batchnorm), so no BatchNorm kernel
+    runs.  Re-create the runner (or call `generator.fold_batchnorm()` again) after loading other weights.
 
 `generate_dataset` / `main` are the reference script itself on top of that runner: same options
 (generate.py:27-47), same sampling loop (:70-103), same output files in the same formats (:105-123), with the generated
@@ -30,6 +32,7 @@ class GeneratorRunner:
 
     def __init__(self, generator, batch, latent_dim=512, trunc=None, graphs=True, device=None):
         self.G = generator.eval()
+        self.G.fold_batchnorm()             # eval-mode BatchNorm becomes part of the convolution weights: no BN launches
         self.device = device or next(generator.parameters()).device
         # W-space truncation draws its 1000 latents from the HOST RNG on every call (generator.py:98): a captured graph would freeze
         # them (and a pageable H2D copy cannot be captured), so that mode launches eagerly

@@ -92,6 +92,20 @@ class Generator(nn.Module):
             x, _ = gcn(x, A[gcn.lvl] * importance, noise=None if noises is None else noises[i])
         return x
 
+    def fold_batchnorm(self):
+        """Inference only: fold every eval-mode BatchNorm (generator.py:142,160 with running
+        statistics) into the convolution in front of it - w' = w * gamma * rstd, b' = (b - mean) * gamma * rstd + beta - so
+        that the eval-mode pass launches no BatchNorm kernel at all.  Used by generate.GeneratorRunner; the folds are
+        dropped by `.train()`, `.to()` and `load_state_dict()`, and must be redone after the parameters change."""
+        for blk in self.st_gcn_networks:
+            blk.fold_batchnorm()
+        return self
+
+    def load_state_dict(self, *args, **kwargs):
+        for blk in self.st_gcn_networks:
+            blk._fold = None
+        return super().load_state_dict(*args, **kwargs)
+
     def truncate(self, w, mean, truncation):
         """generator.py:97-108: W-space truncation towards the mean of `mean` mapped N(0,1) latents (host RNG, as the
         reference); the 1000 per-sample MLP passes of the reference become one batched pass."""
@@ -126,6 +140,30 @@ class st_gcn(nn.Module):
         self.l_relu = nn.LeakyReLU(0.2, inplace=True)
         self.tanh = nn.Tanh()
         self._plans = {}
+        self._fold = None               # eval-mode (weight, bias) pairs with the BatchNorm folded in, see Generator.fold_batchnorm
+
+    @staticmethod
+    def _folded(conv, bn):
+        sc = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        return (conv.weight * sc.view(-1, 1, 1, 1)).contiguous(), ((conv.bias - bn.running_mean) * sc + bn.bias).contiguous()
+
+    def fold_batchnorm(self):
+        with torch.no_grad():
+            fold = {}
+            if self._bn:
+                fold["tcn"] = self._folded(self.tcn[0], self.tcn[1])
+            if self._res == "conv":
+                fold["res"] = self._folded(self.residual[0], self.residual[1])
+        self._fold = fold
+
+    def train(self, mode=True):
+        if mode:
+            self._fold = None
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fold = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _plan(self, T, V):
         p = self._plans.get((T, V))
@@ -148,18 +186,24 @@ class st_gcn(nn.Module):
 
     def forward(self, x, A, noise=None):
         up, tcn, res = self._plan(x.size(2), x.size(3))
+        fold = (self._fold or {}) if not self.training else {}
         x = x if up is None else KF.PlaneSpmm.apply(x, up)          # upsample_s + F.interpolate, one gather
         if self._res == "none":
             r = None
         elif self._res == "identity":
             r = x
+        elif "res" in fold:
+            r = KF.TapConvEp.apply(x, fold["res"][0], fold["res"][1], None, res, KF.ACT_NONE)
         else:
             r = KF.TapConvEp.apply(x, self.residual[0].weight, self.residual[0].bias, None, res, KF.ACT_NONE)
             r = self._batch_norm(self.residual[1], r)
         g, A = self.gcn(x, A)
-        z = KF.TapConvEp.apply(g, self.tcn[0].weight, self.tcn[0].bias, None, tcn, KF.ACT_NONE)
-        if self._bn:
-            z = self._batch_norm(self.tcn[1], z)
+        if "tcn" in fold:
+            z = KF.TapConvEp.apply(g, fold["tcn"][0], fold["tcn"][1], None, tcn, KF.ACT_NONE)
+        else:
+            z = KF.TapConvEp.apply(g, self.tcn[0].weight, self.tcn[0].bias, None, tcn, KF.ACT_NONE)
+            if self._bn:
+                z = self._batch_norm(self.tcn[1], z)
         if noise is None:
             noise = torch.randn(z.size(0), 1, z.size(2), z.size(3), device=z.device)
         out = KF.NoiseAct.apply(z, r, noise, self.noise.weight, KF.ACT_TANH if self.tan else KF.ACT_LRELU)

@@ -59,13 +59,33 @@ class ConvTemporalGraphical(nn.Module):
         out = KF.TapConvEp.apply(xa, self.conv.weight, None, L, g_dat, KF.ACT_NONE)
         return out, A
 
+    def _conv_first_geom(self, t, v):
+        key = ("cf", t, v)
+        g = self._geoms.get(key)
+        if g is None:
+            kt, st, pad, dil = self._t
+            g = self._geoms[key] = TapConvGeom(self.conv.in_channels, self.conv.out_channels, t, v, kt=kt, pad=pad, stride=st, dil=dil)
+        return g
+
     def forward(self, x, A):
         assert A.size(0) == self.kernel_size
+        c_in, c_out = self.conv.in_channels, self.conv.out_channels // self.kernel_size
+        # Both evaluation orders of tgcn.py:61-66 are the same bilinear map; they differ in the intermediate that crosses HBM:
+        # K*C_in channels on W joints (adjacency first) or K*C_out channels on V joints (convolution first, the reference's
+        # order).  The generator halves its channels in every block, the critic doubles them: pick the smaller one.
+        if c_out * A.size(1) < c_in * A.size(2) and self._t == (1, 1, 0, 1):
+            y = KF.TapConv.apply(x, self.conv.weight, self._conv_first_geom(x.size(2), x.size(3)))      # (N, K*C_out, T, V)
+            # out[c, t, w] = sum_k sum_v y[k*C + c, t, v] A[k, v, w]: the adjoint-product member of the adjacency family
+            out = KF.AdjMixDx.apply(y, A.transpose(1, 2))
+            return self._with_bias(out, A), A
         xa = KF.AdjMix.apply(x, A)                                  # (N, K*C_in, T, W)
         out = KF.TapConv.apply(xa, self.conv.weight, self._geom(x.size(2), A.size(2)))
+        return self._with_bias(out, A), A
+
+    def _with_bias(self, out, A):
         if self.conv.bias is not None:
             # never used by Kinetic-GAN (bias=False at generator.py:132 / discriminator.py:96): the K*C_out conv
             # biases reach the output through the column sums of A; tiny host-side torch ops
             b = torch.einsum("kc,kw->cw", self.conv.bias.view(self.kernel_size, -1), A.sum(1))
             out = out + b.view(1, b.size(0), 1, b.size(1))
-        return out, A
+        return out

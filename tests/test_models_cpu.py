@@ -127,3 +127,34 @@ def test_label_folding_equals_label_planes(emu):
     gb = torch.autograd.grad(b.sum(), [blk.gcn.conv.weight, D.label_emb.weight, D.edge_importance[0]])
     for u, v in zip(ga, gb):
         assert torch.allclose(u, v, atol=1e-10)
+
+
+def test_generator_eval_batchnorm_folding(emu):
+    """Generator.fold_batchnorm (inference only): same eval-mode output with the BatchNorms folded into the convolutions;
+    `.train()` and `load_state_dict()` drop the folds."""
+    cfg, n = CASES["ntu_small"]["cfg"], 3
+    G = kgan.Generator(cfg.latent_dim, cfg.channels, cfg.n_classes, cfg.t_size, cfg.mlp_dim, dataset=cfg.dataset).double()
+    G.load_state_dict(onet.synth_params(onet.g_param_shapes(cfg), 1))
+    for i, a in enumerate(G.graph.As):
+        setattr(G, "_A%d" % i, torch.tensor(a, dtype=torch.float64))
+    G.eval()
+    xi = inputs(cfg, n, 4, torch.float64)
+    nz = draw_noises(cfg, n, 7, torch.float64)
+    with torch.no_grad():
+        ref = G(xi["z"], xi["labels"], noises=nz)
+        G.fold_batchnorm()
+        assert all((blk._fold is not None) for blk in G.st_gcn_networks)
+        calls = []
+        orig = kgan.ops.bn_apply
+        kgan.ops.bn_apply = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        try:
+            out = G(xi["z"], xi["labels"], noises=nz)
+        finally:
+            kgan.ops.bn_apply = orig
+    assert not calls                                               # no BatchNorm launch left in the eval pass
+    assert (out - ref).abs().max().item() < 1e-10
+    G.train()
+    assert all(blk._fold is None for blk in G.st_gcn_networks)
+    G.eval().fold_batchnorm()
+    G.load_state_dict(G.state_dict())
+    assert all(blk._fold is None for blk in G.st_gcn_networks)

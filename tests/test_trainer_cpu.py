@@ -95,7 +95,12 @@ def test_critic_step_runs_no_unread_backward_work(emu):
 
         setattr(ops, name, wrap)
     xi = inputs(cfg, n, 3)
+    with torch.no_grad():                 # the generator's own launches (batch n as well): counted alone, then subtracted
+        G(xi["z"], xi["labels"])
+    gen_only = collections.Counter(cnt)
+    cnt.clear()
     tr._d_grads(xi["real"], xi["labels"], xi["z"], xi["alpha"])
+    cnt.subtract(gen_only)
     convs = 6 + 6 + 4 + 1                 # graph convs, temporal convs, residual convs, head (discriminator.py:29-34,47-50)
     # concatenated real+fake pass (batch 2n): one weight gradient per conv (+ the label-fold GEMM of the first layer)
     assert cnt[("tapconv_wgrad", 2 * n)] == convs + 1
