@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--shape", default="ntu120", choices=list(SHAPES), help="network / data shape (BASELINE.json configs); headline: ntu120")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 1024 for train, 4096 for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
+    ap.add_argument("--trunc-cached", action="store_true", help="generate: estimate the W-space mean once (GeneratorRunner cache_mean) instead of per call")
     ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -433,7 +434,7 @@ def run_generate(args):
     with torch.no_grad():                       # a trained generator has non-zero noise weights; exercise that path
         for blk in G.st_gcn_networks:
             blk.noise.weight.normal_(0, 0.1)
-    runner = gen.GeneratorRunner(G, B, 512, trunc=args.trunc, graphs=not args.no_graphs, device=dev)
+    runner = gen.GeneratorRunner(G, B, 512, trunc=args.trunc, graphs=not args.no_graphs, device=dev, cache_mean=args.trunc_cached)
     gcpu = torch.Generator().manual_seed(4321 + comm.rank)
     POOL = 4
     host = [dict(z=torch.randn(B, 512, generator=gcpu).pin_memory(), labels=torch.randint(0, SHAPE["n_classes"], (B,), generator=gcpu).pin_memory())
@@ -499,7 +500,7 @@ def run_generate(args):
         torch.cuda.profiler.stop()
     fam = ops.profile_stop(prof)
     sites = fam.pop("_sites")
-    runner.graphs = not args.no_graphs and args.trunc is None
+    runner.graphs = not args.no_graphs and (args.trunc is None or args.trunc_cached)
     roofline = make_roofline(fam, sites, 3, F_G * value / 1e12 / comm.world_size)
     # lower bound of the whole pass: z + output (+ noise) = ~21 KB of compulsory HBM traffic per sequence
     roofline["pass_hbm_floor_frac"] = (value / comm.world_size) * 21.2e3 / (peaks()[1] * 1e9)
@@ -514,7 +515,7 @@ def run_generate(args):
             "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size, "parallelism": "replicas%d" % comm.world_size,
-                       "trunc": args.trunc, "flop_per_sequence": F_G, "cuda_graphs": not args.no_graphs,
+                       "trunc": args.trunc, "trunc_mean_cached": bool(args.trunc_cached), "flop_per_sequence": F_G, "cuda_graphs": not args.no_graphs,
                        "l2_policy": "inputs rotate over a pool of %d batches; the activations of one pass at batch %d exceed the 126 MB L2" % (POOL, B)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
     comm.close()

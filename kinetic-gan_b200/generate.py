@@ -30,19 +30,25 @@ class GeneratorRunner:
     """`runner(z, labels) -> (N, C, T, V)` in eval mode.  `z`: (N, latent) float32, `labels`: (N,) int64; host (pinned)
     or device tensors.  The returned tensor is the graph's static output buffer: copy it (or `to_host`) before the next call."""
 
-    def __init__(self, generator, batch, latent_dim=512, trunc=None, graphs=True, device=None):
+    def __init__(self, generator, batch, latent_dim=512, trunc=None, graphs=True, device=None, cache_mean=False):
+        """`cache_mean` (W-space truncation only): estimate the mean latent ONCE here instead of from 1000 fresh host draws in
+        every call as generator.py:97-108 does (statistically the same estimator; the per-call draw costs ~10 ms of host RNG
+        and forces eager launches) - the truncated pass then replays as a CUDA graph like the plain one."""
         self.G = generator.eval()
         self.G.fold_batchnorm()             # eval-mode BatchNorm becomes part of the convolution weights: no BN launches
         self.device = device or next(generator.parameters()).device
         # W-space truncation draws its 1000 latents from the HOST RNG on every call (generator.py:98): a captured graph would freeze
         # them (and a pageable H2D copy cannot be captured), so that mode launches eagerly
-        self.batch, self.trunc, self.graphs = batch, trunc, graphs and trunc is None
+        self.batch, self.trunc, self.graphs = batch, trunc, graphs and (trunc is None or cache_mean)
+        self.G._w_mean = self.G.estimate_w_mean() if (trunc is not None and cache_mean) else None
         self.z = torch.zeros(batch, latent_dim, device=self.device)
         self.labels = torch.zeros(batch, dtype=torch.long, device=self.device)
         self.out = None
         self._graph = None
         self.launches_per_call = 0
-        self._host_out = None
+        self._ring = None               # to_host(): two (device staging, pinned host, D2H-done event) slots + the copy stream
+        self._ring_k = 0
+        self.host_ready = None          # event of the last to_host() copy
 
     def _forward(self):
         with torch.no_grad():
@@ -82,11 +88,29 @@ class GeneratorRunner:
         return self.out
 
     def to_host(self):
-        """Asynchronous copy of the last result into a pinned host buffer (what generate.py's `.cpu()` at :95 does)."""
-        if self._host_out is None:
-            self._host_out = torch.empty(self.out.shape, dtype=self.out.dtype).pin_memory()
-        self._host_out.copy_(self.out, non_blocking=True)
-        return self._host_out
+        """Asynchronous copy of the last result into a pinned host buffer (what generate.py's `.cpu()` at :95 does), overlapped
+        with the NEXT call: the result is first duplicated on the device (the graph's output buffer is overwritten by the next
+        replay), then a side stream moves the duplicate over PCIe.  Returns the pinned tensor; it is valid once
+        `runner.host_ready.synchronize()` (or any later device synchronisation) returns, and until the second next to_host()."""
+        if self._ring is None:
+            mk = lambda: [torch.empty_like(self.out), torch.empty(self.out.shape, dtype=self.out.dtype).pin_memory(), None]
+            self._ring = ([mk(), mk()], torch.cuda.Stream(device=self.device))
+        slots, copy_stream = self._ring
+        slot = slots[self._ring_k]
+        self._ring_k ^= 1
+        cur = torch.cuda.current_stream(self.device)
+        if slot[2] is not None:
+            cur.wait_event(slot[2])                  # the staging buffer's previous D2H copy has drained
+        slot[0].copy_(self.out)
+        staged = torch.cuda.Event()
+        staged.record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(staged)
+            slot[1].copy_(slot[0], non_blocking=True)
+            slot[2] = torch.cuda.Event()
+            slot[2].record(copy_stream)
+        self.host_ready = slot[2]
+        return slot[1]
 
 
 def class_conditioned_batch(n_classes, per_class, latent_dim=512, seed=None):
@@ -152,7 +176,7 @@ def generate_dataset(generator, opt, device=None):
     total = rounds * batch
     runner = GeneratorRunner(generator, batch, opt.latent_dim, trunc=opt.trunc if opt.trunc_mode == 'w' else None,
                              graphs=device.type == "cuda", device=device)
-    imgs = z_all = None
+    imgs = None
     labels_all = np.empty(total, dtype=np.int64)
     if opt.stochastic:                                      # one latent point repeated (generate.py:81-83)
         if opt.stochastic_file != '-':
@@ -160,21 +184,36 @@ def generate_dataset(generator, opt, device=None):
         else:
             z0 = np.random.normal(0, 1, (1, opt.latent_dim))
         z = torch.as_tensor(z0, dtype=torch.float32).repeat(batch, 1)
+    pending = None                                          # (round, pinned result, its D2H event): drained one round later
+
+    def drain(p):
+        nonlocal imgs
+        rr, gen, ev = p
+        if ev is not None:
+            ev.synchronize()
+        if imgs is None:
+            imgs = np.empty((total,) + tuple(gen.shape[1:]), np.float32)
+        imgs[rr * batch:(rr + 1) * batch] = gen.numpy()
+
+    z_all = np.empty((total, opt.latent_dim), np.float32)
     for r in range(rounds):
         if not opt.stochastic:
             z = torch.as_tensor(np.random.normal(0, 1, (batch, opt.latent_dim)), dtype=torch.float32)
         if opt.trunc_mode == 'z':
             z = trunc_z(z, opt.mean_size, opt.trunc)
         labels_np = np.array([num for _ in range(qtd) for num in classes])
-        runner(z, torch.as_tensor(labels_np, dtype=torch.long))
-        gen = runner.to_host() if device.type == "cuda" else runner.out
-        if device.type == "cuda":
-            torch.cuda.current_stream().synchronize()
-        if imgs is None:
-            imgs = np.empty((total,) + tuple(gen.shape[1:]), np.float32)
-            z_all = np.empty((total, opt.latent_dim), np.float32)
         sl = slice(r * batch, (r + 1) * batch)
-        imgs[sl], z_all[sl], labels_all[sl] = gen.numpy(), z.numpy(), labels_np
+        z_all[sl], labels_all[sl] = z.numpy(), labels_np
+        runner(z, torch.as_tensor(labels_np, dtype=torch.long))
+        if device.type == "cuda":
+            cur = (r, runner.to_host(), runner.host_ready)  # this round's copy overlaps the next round's generator pass
+            if pending is not None:
+                drain(pending)
+            pending = cur
+        else:
+            drain((r, runner.out.clone(), None))
+    if pending is not None:
+        drain(pending)
     counts = Counter(labels_all.tolist())
     assert all(counts[c] >= opt.gen_qtd for c in classes)
     if opt.dataset == 'ntu':

@@ -109,9 +109,18 @@ class Generator(nn.Module):
     def truncate(self, w, mean, truncation):
         """generator.py:97-108: W-space truncation towards the mean of `mean` mapped N(0,1) latents (host RNG, as the
         reference); the 1000 per-sample MLP passes of the reference become one batched pass."""
-        t = torch.as_tensor(np.random.normal(0, 1, (mean, *w.shape[1:])), dtype=w.dtype, device=w.device)
-        m = self.mlp(t).mean(0, keepdim=True)
+        m = getattr(self, "_w_mean", None)          # generate.GeneratorRunner(cache_mean=True): one estimate for all calls
+        if m is None:
+            t = torch.as_tensor(np.random.normal(0, 1, (mean, *w.shape[1:])), dtype=w.dtype, device=w.device)
+            m = self.mlp(t).mean(0, keepdim=True)
         return m + truncation * (w - m)
+
+    def estimate_w_mean(self, mean=1000):
+        """The W-space mean of generator.py:98-104 (host RNG draw of `mean` latents, batched mapping pass) as a tensor."""
+        dev, dt = self.label_emb.weight.device, self.label_emb.weight.dtype
+        with torch.no_grad():
+            t = torch.as_tensor(np.random.normal(0, 1, (mean, self.mlp.mlp[0].in_features)), dtype=dt, device=dev)
+            return self.mlp(t).mean(0, keepdim=True)
 
 
 class st_gcn(nn.Module):

@@ -71,3 +71,27 @@ def test_runner_w_truncation():
     with torch.no_grad():
         c = G(z.cuda(), labels.cuda())
     assert (a - c).abs().max().item() > 1e-4                           # the truncation really moved the latents
+
+
+def test_runner_cached_w_mean_replays_as_graph():
+    """cache_mean=True: the W-space mean is estimated once, the truncated pass is a CUDA-graph replay and equals the module's
+    own truncated forward with that mean; the default keeps the reference's per-call estimate (test above)."""
+    gen = import_module("kinetic-gan_b200.generate")
+    cfg = CASES["h36m_small"]["cfg"]
+    G, _ = build(cfg)
+    z, labels = gen.class_conditioned_batch(cfg.n_classes, 4, cfg.latent_dim, seed=6)
+    np.random.seed(12)
+    runner = gen.GeneratorRunner(G, z.shape[0], cfg.latent_dim, trunc=0.7, cache_mean=True)
+    try:
+        a = runner(z.cuda(), labels.cuda()).clone()
+        a2 = runner(z.cuda(), labels.cuda()).clone()
+        assert runner.graphs and runner.launches_per_call > 0 and torch.equal(a, a2)
+        with torch.no_grad():
+            b = G(z.cuda(), labels.cuda(), 0.7)
+            c = G(z.cuda(), labels.cuda())
+        assert (a - b).abs().max().item() < 1e-6
+        assert (a - c).abs().max().item() > 1e-4
+        np.random.seed(12)
+        assert torch.allclose(G._w_mean, G.estimate_w_mean(), atol=1e-6)
+    finally:
+        G._w_mean = None
