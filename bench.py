@@ -42,6 +42,24 @@ TRAFFIC_FILE = "r1_traffic_b1024.json"        # ncu DRAM-traffic capture of the 
 NCU_RANGE = os.environ.get("KGAN_NCU_RANGE") == "1"   # bracket the eager roofline pass with cudaProfilerStart/Stop (ncu --profile-from-start off)
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version banner
+    under NCCL_DEBUG=VERSION, warnings) is routed to stderr for the duration of the run."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (line + "\n").encode())
+
+
 def set_shape(key):
     global SHAPE, F_G, F_D, FLOP_PER_SAMPLE, WORKLOAD, GEN_WORKLOAD
     SHAPE = SHAPES[key]
@@ -190,7 +208,7 @@ def run_reference(args):
                          "sample": "%d iterations of batch %d (%s) after %d warm-up" % (args.steps, b, SHAPE["name"], args.warmup)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def make_roofline(fam, sites, passes, step_tflops):
@@ -360,7 +378,7 @@ def run_kgan(args):
                                     "inputs rotate over a pool of %d batches" % (B, POOL)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     comm.close()
 
 
@@ -403,7 +421,7 @@ def run_reference_generate(args):
         return
     b = args.cpu_batch * 8
     sps, ms, cores = time_oracle_generate(b, args.steps, args.warmup, args.trunc)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "generated_sequences_per_s", "value": sps, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
         "data": "synthetic", "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": b, "trunc": args.trunc,
@@ -511,7 +529,7 @@ def run_generate(args):
         cpu = {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
                "sample": "2 generator calls of batch %d (%s, per-sample mapping loop as generator.py:84-85) after 1 warm-up" % (args.cpu_batch * 8, SHAPE["name"])}
     if comm.rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size, "parallelism": "replicas%d" % comm.world_size,
@@ -523,6 +541,7 @@ def run_generate(args):
 
 if __name__ == "__main__":
     a = parse()
+    quiet_stdout()
     set_shape(a.shape)
     if a.batch is None:
         a.batch = 1024 if a.workload == "train" else 4096
