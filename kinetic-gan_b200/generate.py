@@ -13,7 +13,7 @@ mode, :85-93 latent / label construction and `generator(z, labels, trunc)`), res
 (generate.py:27-47), same sampling loop (:70-103), same output files in the same formats (:105-123), with the generated
 batches accumulated in one preallocated host array instead of an O(n^2) `np.concatenate` per iteration.
 
-    python -m kgan_b200.generate --model runs/kinetic-gan/exp1/models/generator_10000.pth --n_classes 60 --gen_qtd 1000
+    python generate.py --model runs/kinetic-gan/exp1/models/generator_10000.pth --n_classes 60 --gen_qtd 1000
 """
 import argparse
 import os

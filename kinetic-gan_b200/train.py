@@ -1,7 +1,7 @@
 """The caller of the hot path: `kinetic-gan.py` re-hosted on the B200 trainer.
 
-    python -m kgan_b200.train --data_path train_data.npy --label_path train_label.pkl [reference options ...]
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 -m kgan_b200.train ...       # batch-sharded DDP
+    python kinetic-gan.py --data_path train_data.npy --label_path train_label.pkl [reference options ...]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 kinetic-gan.py ...            # batch-sharded DDP
 
 Every option of the reference script (kinetic-gan.py:23-44) exists with the same name, meaning and default; the run
 directory (`runs/kinetic-gan/expN/{models,actions}`, `config.txt`), the checkpoints (`generator_%d.pth`,
