@@ -211,3 +211,31 @@ def test_trunc_z_matches_reference_loop():
     for i, _ in enumerate(want):
         want[i] = m + 0.9 * (want[i] - m)
     assert torch.allclose(got, want, atol=1e-6)
+
+
+def test_train_cli_two_ranks_gloo(tmp_path):
+    """The CLI loop under torch.distributed (world_size 2, gloo): both ranks walk rank 0's permutation and take disjoint
+    halves of every global batch; replicas stay identical (flat-gradient all-reduce) so the critic losses they log differ only
+    through their different samples; only rank 0 writes a run directory."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dp, lp, _, _ = make_dataset(str(tmp_path))
+    script = os.path.join(root, "tests", "ddp_train_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, script, dp, lp, str(tmp_path)], env=dict(env, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r)))
+             for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    a = torch.load(os.path.join(str(tmp_path), "train_w2_r0.pt"), weights_only=False)
+    b = torch.load(os.path.join(str(tmp_path), "train_w2_r1.pt"), weights_only=False)
+    assert a["run"] is not None and b["run"] is None
+    assert a["seen"].shape == b["seen"].shape == (3, 2)
+    # rank 0's permutation (train.py re-seeds torch with seed + 7919 * (rank + 1) after the shared model init; rank 1's own
+    # seed is different and must not matter): global batches of 4, rank r takes [2r, 2r + 2)
+    torch.manual_seed(11 + 7919)
+    perm = feeder_mod.epoch_permutation(23)
+    for i in range(3):
+        assert np.array_equal(a["seen"][i], perm[4 * i:4 * i + 2]) and np.array_equal(b["seen"][i], perm[4 * i + 2:4 * i + 4])
+    assert len(a["loss_d"]) == len(b["loss_d"]) == 3 and np.isfinite(a["loss_d"]).all() and np.isfinite(b["loss_d"]).all()
