@@ -152,9 +152,20 @@ __global__ void __launch_bounds__(PT) chan_reduce4_k(const float* __restrict__ g
     const int nbeg = blockIdx.y * n_per_slice, nend = min(n, nbeg + n_per_slice);
     const unsigned cnt = (unsigned)(nend - nbeg) * (unsigned)p4;          // < 2^31 by the launcher's check
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+    auto ld = [&](unsigned i) {
         const unsigned nn = i / (unsigned)p4, q = i - nn * (unsigned)p4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(g + ((int64_t)(nbeg + nn) * c + cc) * (int64_t)(4 * p4)) + q);
+        return __ldg(reinterpret_cast<const float4*>(g + ((int64_t)(nbeg + nn) * c + cc) * (int64_t)(4 * p4)) + q);
+    };
+    unsigned i = threadIdx.x;
+    for (; i + 3 * blockDim.x < cnt; i += 4 * blockDim.x) {               // 4 independent 16-byte loads in flight per thread
+        const float4 v0 = ld(i), v1 = ld(i + blockDim.x), v2 = ld(i + 2 * blockDim.x), v3 = ld(i + 3 * blockDim.x);
+        a0 += (v0.x + v1.x) + (v2.x + v3.x);
+        a1 += (v0.y + v1.y) + (v2.y + v3.y);
+        a2 += (v0.z + v1.z) + (v2.z + v3.z);
+        a3 += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; i < cnt; i += blockDim.x) {
+        const float4 v = ld(i);
         a0 += v.x;
         a1 += v.y;
         a2 += v.z;
@@ -179,18 +190,21 @@ __global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict_
         id[j] = s >= 0 ? s : 0;
         w[j] = s >= 0 ? __ldg(wgt + q * J + j) : 0.f;
     }
+    // U planes in flight per thread: with 4-byte accesses the kernel is bound by bytes in flight / loaded DRAM latency
+    // (2048 threads x 4 loads x 4 B = 32 KB per SM gave ~3.3 TB/s), so single-entry tables keep 8 loads outstanding
+    constexpr int U = J <= 2 ? 8 : 4;
     int64_t r = blockIdx.x;
-    for (; r + 3 * (int64_t)gridDim.x < rows; r += 4 * (int64_t)gridDim.x) {      // 4 planes in flight per thread
-        float acc[4];
+    for (; r + (U - 1) * (int64_t)gridDim.x < rows; r += U * (int64_t)gridDim.x) {
+        float acc[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const float* xr = x + (r + u * (int64_t)gridDim.x) * p_in;
             acc[u] = 0.f;
 #pragma unroll
             for (int j = 0; j < J; ++j) acc[u] = fmaf(w[j], __ldg(xr + id[j]), acc[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) out[(r + u * (int64_t)gridDim.x) * p_out + q] = acc[u];
+        for (int u = 0; u < U; ++u) out[(r + u * (int64_t)gridDim.x) * p_out + q] = acc[u];
     }
     for (; r < rows; r += gridDim.x) {
         const float* xr = x + r * p_in;
