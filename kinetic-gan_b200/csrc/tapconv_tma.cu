@@ -37,6 +37,8 @@ namespace kgan {
 constexpr int TM_EPI_WARPS = 8;
 constexpr int TM_EPI_WARP0 = 2;
 constexpr int TM_THREADS = 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);       // TMA mode
+constexpr int TM_PROD_WARPS = 3;                                       // TMA mode: warp 0 + warps 10, 11 issue the loads of every 3rd stage each
+constexpr int TM_THREADS_TMA = TM_THREADS + 32 * (TM_PROD_WARPS - 1);
 constexpr int TM_CP_WARPS = 4;
 constexpr int TM_THREADS_CP = TM_THREADS + 32 * TM_CP_WARPS;          // cp.async mode
 constexpr float TM_TRUNC_FIX = 1.000353f;      // 1 / (1 - 3.53e-4)
@@ -49,6 +51,8 @@ struct TmaPlan {
     int64_t groups32;                             // 32-row M groups: ceil(n / n_box) * cps
     int m_tiles, num_tiles, stages, smem_bytes;
     int a_lbo, a_sbo;                             // A descriptor strides (bytes): between 32-position M groups / between 8-channel K groups
+    int w_res;                                    // 1: the whole packed weight image stays resident in shared memory (loaded once per CTA)
+    int w_res_bytes;
     int kmajor;                                   // 1: one-position planes (Linear layers): A is a K-major [128 samples] x [32 channels] box
     int pf_tiles;                                 // L2 prefetch distance in tiles of this CTA (0: off)
     uint32_t pf_taps;                             // taps whose boxes are prefetched (temporal shifts of the same channels are near-duplicates)
@@ -88,6 +92,26 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     p.stages = (200 * 1024) / stage;
     if (p.stages > 8) p.stages = 8;
     p.smem_bytes = p.stages * stage + 1024 + 512;                  // + alignment slack + barriers
+    // Resident weights: a CTA re-fetches the same packed weight stages for every one of its tiles - a third of the bytes an SM
+    // ingests at N = 64 (the marginal cost of a K stage measured ~700 cycles for 16 KB of activations + 8 KB of weights).  When
+    // the whole image (all groups, all K stages) fits beside a ring of >= 5 activation stages it is loaded once per CTA.
+    static const bool no_wres = getenv("KGAN_TMA_NO_WRES") != nullptr;
+    p.w_res = 0;
+    p.w_res_bytes = 0;
+    {
+        const int64_t img = (int64_t)d.groups * p.nkt * d.ntap * p.n_cta * UK * 4;
+        const int64_t tiles_per_cta = ceil_div64(p.num_tiles, kNumSMs);
+        if (!no_wres && p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
+            int st = (int)((200 * 1024 - img) / A_STAGE_BYTES);
+            if (st > 8) st = 8;
+            if (st >= 5) {
+                p.w_res = 1;
+                p.w_res_bytes = (int)img;
+                p.stages = st;
+                p.smem_bytes = st * A_STAGE_BYTES + (int)img + 1024 + 512;
+            }
+        }
+    }
     p.a_lbo = TM_GROUP_BYTES;
     p.a_sbo = 512;
     // L2 prefetch (TMA mode only): ~256 KB of unique activation bytes ahead of the shared-memory ring
@@ -194,11 +218,13 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     const int S = pl.stages;
     const int b_stage_bytes = pl.n_cta * UK * 4;
     uint8_t* a_base = smem;
-    uint8_t* b_base = smem + (size_t)S * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)S * b_stage_bytes);   // full[S], empty[S], tfull[2], tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    uint8_t* b_base = smem + (size_t)S * A_STAGE_BYTES;             // ring of S weight stages, or the resident image (pl.w_res)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (pl.w_res ? (size_t)pl.w_res_bytes : (size_t)S * b_stage_bytes));
+    // full[S], empty[S], tfull[2], tempty[2], wfull
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
     const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
+    const uint32_t wfull = smem_u32(bars + 2 * S + 4);
     const int kiters = pl.nkt * d.ntap;
     const bool use_tma = pl.p_box == 32 || pl.kmajor;                // else: cp.async producers (warps 10-13)
 
@@ -213,6 +239,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             mbar_init(tfull0 + 8 * b, 1);
             mbar_init(tempty0 + 8 * b, 32 * TM_EPI_WARPS);
         }
+        mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (use_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     }
@@ -226,13 +253,28 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // Producer warps.  ncu (profiles/r1_ncu_d1_stalls.txt) showed ONE producer warp to be the bottleneck of the 3-tap temporal conv:
+    // it never waited on an empty stage, the MMA warp waited on full ones a third of its time, and a stage cost ~780 cycles of
+    // mostly dependent uniform-datapath instructions (coordinates, descriptors, 4 UTMALDG).  In TMA mode the stages are
+    // therefore dealt round-robin to TM_PROD_WARPS warps (each stage still has exactly one producer and its own barrier pair).
+    const int n_prod = use_tma ? TM_PROD_WARPS : 1;
+    const int prod_idx = warp == 0 ? 0 : (use_tma && warp >= TM_EPI_WARP0 + TM_EPI_WARPS && warp < TM_EPI_WARP0 + TM_EPI_WARPS + TM_PROD_WARPS - 1)
+                                             ? warp - (TM_EPI_WARP0 + TM_EPI_WARPS) + 1
+                                             : -1;
+    if (prod_idx >= 0) {
         // ===== producer: tensor loads of the activation boxes + bulk copies of the packed weights =====
         // (whole warp in uniform control flow, one elected lane issues: operands stay in uniform registers, see umma.cuh elect_one)
         {
             const bool leader = elect_one();
             const uint32_t chunk_bytes = pl.n_cta * 16;
-            const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + chunk_bytes * 8;
+            const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + (pl.w_res ? 0u : chunk_bytes * 8);
+            if (pl.w_res && leader && prod_idx == 0) {               // the whole packed image (contiguous for n_split == 1), once
+                mbar_arrive_expect_tx(wfull, (uint32_t)pl.w_res_bytes);
+                for (int off = 0; off < pl.w_res_bytes; off += 16384) {
+                    const int nb = min(16384, pl.w_res_bytes - off);
+                    bulk_g2s(smem_u32(b_base + off), reinterpret_cast<const uint8_t*>(wp) + off, (uint32_t)nb, wfull);
+                }
+            }
             // activation boxes of a later tile of this CTA -> L2 (off by default: measured slower); tiles that share an activation tile
             // (other n splits / groups reading the same channels) leave the prefetch to the first of them
             auto prefetch_tile = [&](int t2) {
@@ -250,12 +292,13 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                                 tma_prefetch_3d(&tmap, pp + d.tap_shift[tap], nb * pl.n_box, pc.g * d.g_in + d.tap_in_ch[tap] + ict * UK);
                 }
             };
-            if (use_tma && pl.pf_tiles > 0 && leader)
+            if (use_tma && pl.pf_tiles > 0 && leader && prod_idx == 0)
                 for (int j = 1; j < pl.pf_tiles; ++j) prefetch_tile(blockIdx.x + j * gridDim.x);
-            int s = 0;
+            int s = prod_idx;                                         // this warp's next stage slot (n_prod <= 5 <= S)
             uint32_t ph = 1;                                          // parity to wait for on empty[s]
+            int it = prod_idx;                                        // ... and its index within the current tile's K loop
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
-                if (use_tma && pl.pf_tiles > 0 && leader) prefetch_tile(tile + pl.pf_tiles * gridDim.x);
+                if (use_tma && pl.pf_tiles > 0 && leader && prod_idx == 0) prefetch_tile(tile + pl.pf_tiles * gridDim.x);
                 const TmaTile tc = tma_tile(tile, pl);
                 int cp[4], cn[4];                                     // box origin (position, sample) of the 4 M groups
 #pragma unroll
@@ -268,8 +311,8 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                 const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
                 const int oc_base = tc.ns * pl.n_cta;
                 const int ch_g = tc.g * d.g_in;
-                int ict = 0, tap = 0;
-                for (int it = 0; it < kiters; ++it) {
+                int ict = it / d.ntap, tap = it - ict * d.ntap;
+                for (; it < kiters; it += n_prod) {
                     mbar_wait(empty0 + 8 * s, ph);
                     if (leader) {
                         mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
@@ -283,7 +326,9 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                         }
                         const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
                         const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
-                        if (pl.n_split == 1) {
+                        if (pl.w_res) {
+                            // nothing: the weights are resident
+                        } else if (pl.n_split == 1) {
                             bulk_g2s(b_dst, src, chunk_bytes * 8, full0 + 8 * s);       // the whole stage is contiguous in the image
                         } else {
 #pragma unroll
@@ -292,15 +337,18 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                         }
                     }
                     __syncwarp();
-                    if (++tap == d.ntap) {
-                        tap = 0;
+                    tap += n_prod;
+                    while (tap >= d.ntap) {
+                        tap -= d.ntap;
                         ++ict;
                     }
-                    if (++s == S) {
-                        s = 0;
+                    s += n_prod;
+                    if (s >= S) {
+                        s -= S;
                         ph ^= 1u;
                     }
                 }
+                it -= kiters;
             }
         }
     } else if (warp == 1) {
@@ -311,8 +359,10 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const uint32_t b_lbo = pl.n_cta * 16;
             int s = 0, ti = 0;
             uint32_t ph = 0;
+            if (pl.w_res) mbar_wait(wfull, 0);
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
                 const int buf = ti & 1;
+                const uint32_t b_res = smem_u32(b_base) + (uint32_t)(tma_tile(tile, pl).g * kiters) * (uint32_t)b_stage_bytes;
                 mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + buf * pl.n_cta;
@@ -324,7 +374,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (leader) {
                         const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                        const uint32_t b_addr = smem_u32(b_base + (size_t)s * b_stage_bytes);
+                        const uint32_t b_addr = pl.w_res ? b_res + (uint32_t)it * (uint32_t)b_stage_bytes : smem_u32(b_base + (size_t)s * b_stage_bytes);
 #pragma unroll
                         for (int j = 0; j < UK / 8; ++j)
                             umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
@@ -515,7 +565,7 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     }
     (void)pmap;                                                    // the shift form replaces the position map
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
+    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
     return check_launch("tapconv_fwd_tma");
 }
 
