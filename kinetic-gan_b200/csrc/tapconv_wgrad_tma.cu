@@ -166,14 +166,19 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // Producers: warp 0 and - until the accumulators are complete they have nothing else to do - the first two epilogue warps deal
+    // the stages round-robin (a single producer warp was the bottleneck of the TMA-fed forward kernel: ~780 cycles of dependent
+    // uniform-datapath instructions per stage, see tapconv_tma.cu); each stage still has exactly one producer.
+    const int n_prod = S >= 3 ? 3 : 1;
+    const int prod_idx = warp == 0 ? 0 : (n_prod == 3 && (warp == 2 || warp == 3)) ? warp - 1 : -1;
+    if (prod_idx >= 0) {
         // ===== producer: one gout box + ntap input boxes per K tile (whole warp in uniform control flow, one lane issues) =====
         {
             const bool leader = elect_one();
             const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
             const uint32_t stage_tx = (uint32_t)stage_bytes;
-            // first K tile of this CTA's chunk: stage k covers K tiles k * nsub ... + nsub - 1, K tile t = (sample t / kt_per_plane, box t % ...)
-            const int64_t t0 = kbeg * pl.nsub;
+            // first K tile of this producer: stage k covers K tiles k * nsub ... + nsub - 1, K tile t = (sample t / kt_per_plane, box t % ...)
+            const int64_t t0 = (kbeg + prod_idx) * pl.nsub;
             int nn = (int)(t0 / pl.kt_per_plane), pt = (int)(t0 - (int64_t)nn * pl.kt_per_plane);
             auto prefetch = [&](int64_t k) {                            // operands of stage k -> L2 (whole-row tiles only)
                 const int pn = (int)(k / pl.kt_per_plane), pp = (int)(k - (int64_t)pn * pl.kt_per_plane) * pl.p_box;
@@ -181,11 +186,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                 for (int tap = 0; tap < d.ntap; ++tap)
                     if ((pl.pf_taps >> tap) & 1) tma_prefetch_3d(&map_x, pp + d.tap_shift[tap], pn, in_ch0 + d.tap_in_ch[tap]);
             };
-            if (pl.pf_dist > 0 && leader)
+            if (pl.pf_dist > 0 && leader && prod_idx == 0)
                 for (int64_t k = kbeg + S; k < kbeg + pl.pf_dist && k < kend; ++k) prefetch(k);
-            int s = 0;
+            int s = prod_idx;
             uint32_t ph = 1;                                            // parity to wait for on empty[s]
-            for (int it = 0; it < iters; ++it) {
+            for (int it = prod_idx; it < iters; it += n_prod) {
                 mbar_wait(empty0 + 8 * s, ph);
                 if (leader) {
                     if (pl.pf_dist > 0 && kbeg + it + pl.pf_dist < kend) prefetch(kbeg + it + pl.pf_dist);
@@ -205,17 +210,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                     }
                 }
                 __syncwarp();
-                pt += pl.nsub;
+                pt += n_prod * pl.nsub;
                 while (pt >= pl.kt_per_plane) {
                     pt -= pl.kt_per_plane;
                     ++nn;
                 }
-                if (++s == S) {
-                    s = 0;
+                s += n_prod;
+                if (s >= S) {
+                    s -= S;
                     ph ^= 1u;
                 }
             }
         }
+    }
+    if (warp == 0) {
+        // producer only
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp waits, one lane issues) =====
         {
