@@ -38,6 +38,7 @@ F_G, F_D = SHAPE["f_g"], SHAPE["f_d"]
 FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
 WORKLOAD = SHAPE["name"] + ", WGAN-GP training, n_critic=5"
 GEN_WORKLOAD = "generate.py generator pass, " + SHAPE["name"] + ", eval mode, no_grad"
+TRAFFIC_BATCH, TRAFFIC_SHAPE = None, None      # configuration of THIS run (set in __main__): a capture of another one is not attached
 TRAFFIC_FILE = "r1_traffic_b1024.json"        # ncu DRAM-traffic capture of the training step (generate: r1_traffic_generate.json)
 NCU_RANGE = os.environ.get("KGAN_NCU_RANGE") == "1"   # bracket the eager roofline pass with cudaProfilerStart/Stop (ncu --profile-from-start off)
 
@@ -229,6 +230,8 @@ def make_roofline(fam, sites, passes, step_tflops):
     try:                                        # per-family DRAM bytes per launch, tools/ncu_traffic_summary.py over the same eager pass
         with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             t = json.load(f)
+        if t.get("per_gpu_batch") != TRAFFIC_BATCH or t.get("shape", "ntu120") != TRAFFIC_SHAPE:
+            raise KeyError("capture is for another configuration")
         traffic = t["families"][name]["dram_bytes_per_launch"]
         traffic_src = "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch, per-GPU batch %s)" % (TRAFFIC_FILE, t.get("per_gpu_batch"))
     except Exception:
@@ -345,15 +348,17 @@ def run_kgan(args):
 
     # roofline of the dominant kernel family, measured live with CUDA events around every launch of one more pass
     tr.use_graphs = False                       # eager launches: CUDA events around every libkgan kernel
+    ncu_steps = int(os.environ.get("KGAN_NCU_STEPS", "5"))      # steps of the pass inside the cudaProfilerStart/Stop range
     if NCU_RANGE:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
     prof = ops.profile_start()
     for i in range(it, it + 5):
         step_resident(i)
+        if NCU_RANGE and i - it + 1 == ncu_steps:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
     torch.cuda.synchronize()
-    if NCU_RANGE:
-        torch.cuda.profiler.stop()
     fam = ops.profile_stop(prof)
     sites = fam.pop("_sites")
     tr.use_graphs = graphs
@@ -545,6 +550,7 @@ if __name__ == "__main__":
     set_shape(a.shape)
     if a.batch is None:
         a.batch = 1024 if a.workload == "train" else 4096
+    TRAFFIC_BATCH, TRAFFIC_SHAPE = a.batch, a.shape
     if a.workload == "generate":
         run_reference_generate(a) if a.impl == "reference" else run_generate(a)
     elif a.impl == "reference":

@@ -70,7 +70,7 @@ def main():
     total_us = sum(a["us"] for a in fam.values())
     out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over the eager "
                      "roofline pass of bench.py (one n_critic cycle, 5 iterations); per-launch times are cold-cache and serialised",
-           "per_gpu_batch": int(sys.argv[2]) if len(sys.argv) > 2 else None, "launches": len(per_id), "total_us": total_us, "families": {}}
+           "per_gpu_batch": int(sys.argv[2]) if len(sys.argv) > 2 else None, "shape": sys.argv[3] if len(sys.argv) > 3 else "ntu120", "launches": len(per_id), "total_us": total_us, "families": {}}
     for k, a in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
         n = a["launches"]
         out["families"][k] = {"launches": n, "dram_bytes_per_launch": (a["rd"] + a["wr"]) / n, "dram_read_bytes_per_launch": a["rd"] / n,
