@@ -140,3 +140,64 @@ def test_properties_at_baseline_batch():
     with torch.no_grad():
         out = G(x["z"], x["labels"])
     assert out.shape == (32, 3, 64, 25) and torch.isfinite(out).all() and out.abs().max() <= 1
+
+
+def test_properties_at_bench_size_tf32():
+    """Size-independent properties at the bench's own size (BASELINE configs[2]: NTU-120 mlp8, per-GPU batch 1024, tf32 path):
+    (1) adjoint identities <F(x, w), g> = <x, Dgrad(g, w)> = <w, Wgrad(x, g)> on the largest layers (the three kernels must be
+    transposes of one another whatever the tiling); (2) the critic treats samples independently (a batch equals its slices);
+    (3) one full WGAN-GP iteration through the CUDA-graph trainer leaves finite losses, finite parameters and a tanh-bounded
+    generator."""
+    geo = import_module("kinetic-gan_b200.geometry")
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    n = 1024
+    kgan.set_precision("tf32")
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        sites = {"d1_gcn": dict(c_in=32, c_out=64, t_in=64, v_in=12, K=3), "d1_tcn": dict(c_in=64, c_out=64, t_in=64, v_in=12, kt=3, pad=1),
+                 "d3_gcn": dict(c_in=128, c_out=256, t_in=32, v_in=5, K=3), "map": dict(c_in=632, c_out=632, t_in=1, v_in=1)}
+        for name, kw in sites.items():
+            g = geo.TapConvGeom(**kw)
+            x = torch.randn(n, g.K * g.c_in, g.t_in, g.v_in, device="cuda", generator=gen)
+            w = torch.randn(g.K * g.c_out, g.c_in, g.kt, 1, device="cuda", generator=gen) / (g.c_in * g.kt * g.K) ** 0.5
+            go = torch.randn(n, g.c_out, g.t_out, g.v_out, device="cuda", generator=gen)
+            y = kgan.ops.tapconv_fwd(x, w, g.fwd)
+            a = (y.double() * go.double()).sum().item()
+            b = (x.double() * kgan.ops.tapconv_fwd(go, w, g.dgrad).double()).sum().item()
+            c = (w.double() * kgan.ops.tapconv_wgrad(x, go, g.fwd, tuple(w.shape)).double()).sum().item()
+            # the inner product sums M = y.numel() terms of random sign: |a| ~ ||y|| ||g|| / sqrt(M), and so does the rounding noise
+            # (~3e-4 per term); a wrong tap, tile or tail would show up at the scale of |a| itself
+            tol = 3e-3 * (y.double().norm() * go.double().norm()).item() / y.numel() ** 0.5
+            assert abs(a - b) < tol and abs(a - c) < tol, (name, a, b, c, tol)
+            del x, w, go, y
+        torch.manual_seed(0)
+        G = kgan.Generator(512, 3, 120, 64, mlp_dim=8).cuda()
+        D = kgan.Discriminator(3, 120, 64, 512).cuda()
+        gc = torch.Generator().manual_seed(11)
+        real = (torch.rand(n, 3, 64, 25, generator=gc) * 2 - 1).cuda()
+        labels = torch.randint(0, 120, (n,), generator=gc).cuda()
+        z = torch.randn(n, 512, generator=gc).cuda()
+        alpha = torch.rand(n, 1, 1, 1, generator=gc).cuda()
+        with torch.no_grad():
+            dv = D(real, labels)
+            part = torch.cat([D(real[:96], labels[:96]), D(real[-160:], labels[-160:])])
+        # slices of 96 / 160 samples take other kernel plans (exact SIMT kernels below 256 GEMM rows): tf32-level agreement
+        assert rel_l2(torch.cat([dv[:96], dv[-160:]]), part) < 5e-3
+        tr = wg.WGANGPTrainer(G, D)
+        tr.capture_graphs(real, labels, z, alpha)
+        d_loss, g_loss, gp = tr.iteration(0, real, labels, z, alpha)
+        d2, g2, _ = tr.iteration(1, real, labels, z, alpha)
+        assert g_loss is not None and g2 is None
+        vals = torch.stack([d_loss, g_loss, gp, d2]).cpu()
+        assert torch.isfinite(vals).all() and gp.item() >= 0
+        assert torch.isfinite(tr.fd.flat).all() and torch.isfinite(tr.fg.flat).all()
+        assert tr.fd.step == 2 and tr.fg.step == 1
+        G.eval()
+        with torch.no_grad():
+            out = G(z, labels)
+        assert out.shape == (n, 3, 64, 25) and torch.isfinite(out).all() and out.abs().max() <= 1
+    finally:
+        kgan.set_precision("fp32")
+        kgan.ops._persist.clear()
+        kgan.ops._batches.clear()
+        kgan.ops.clear_temporary_packs()
