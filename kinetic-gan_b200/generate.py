@@ -134,23 +134,23 @@ def trunc_z(latent, mean_size, truncation):
 
 def build_parser():
     p = argparse.ArgumentParser()
-    p.add_argument("--batch_size", type=int, default=10, help="How many samples PER CLASS (each iteration of course)")
-    p.add_argument("--latent_dim", type=int, default=512, help="dimensionality of the latent space")
-    p.add_argument("--mlp_dim", type=int, default=4, help="mapping network depth")
-    p.add_argument("--n_classes", type=int, default=60, help="number of classes for dataset")
-    p.add_argument("--label", type=int, default=-1, help="Sepecific label to generate, -1 for all classes")
-    p.add_argument("--t_size", type=int, default=64, help="size of each temporal dimension")
-    p.add_argument("--v_size", type=int, default=25, help="size of each spatial dimension (vertices)")
-    p.add_argument("--channels", type=int, default=3, help="number of channels (coordinates)")
-    p.add_argument("--dataset", type=str, default="ntu", help="dataset")
-    p.add_argument("--model", type=str, default="runs/kinetic-gan/exp1/models/generator_ntu_xsub_mlp4_1370000.pth", help="path to gen model")
-    p.add_argument("--stochastic", action='store_true', help="Generate/Get one sample and verify stochasticity")
-    p.add_argument("--stochastic_file", type=str, default="-", help="Read one sample and verify stochasticity")
-    p.add_argument("--stochastic_index", type=int, default=0, help="Sample index to get your latent point")
-    p.add_argument("--gen_qtd", type=int, default=1000, help="How many samples to generate per class")
-    p.add_argument("--trunc", type=float, default=0.95, help="Truncation sigma")
-    p.add_argument("--trunc_mode", type=str, default='w', choices=['z', 'w', '-'], help="Truncation mode (check paper for details)")
-    p.add_argument("--mean_size", type=int, default=1000, help="Samples to estimate mean")
+    p.add_argument("--batch_size", type=int, default=10, help="samples per class generated in one round")
+    p.add_argument("--latent_dim", type=int, default=512, help="length of the latent vector z")
+    p.add_argument("--mlp_dim", type=int, default=4, help="number of Linear layers in the mapping network")
+    p.add_argument("--n_classes", type=int, default=60, help="number of action classes")
+    p.add_argument("--label", type=int, default=-1, help="generate this class only (-1: every class)")
+    p.add_argument("--t_size", type=int, default=64, help="frames per sequence (T)")
+    p.add_argument("--v_size", type=int, default=25, help="joints per frame (V); fixed by --dataset, kept for compatibility")
+    p.add_argument("--channels", type=int, default=3, help="coordinates per joint (C)")
+    p.add_argument("--dataset", type=str, default="ntu", help="skeleton layout: ntu or h36m")
+    p.add_argument("--model", type=str, default="runs/kinetic-gan/exp1/models/generator_ntu_xsub_mlp4_1370000.pth", help="generator checkpoint (state_dict)")
+    p.add_argument("--stochastic", action='store_true', help="repeat ONE latent point for the whole batch (only the per-block noise varies)")
+    p.add_argument("--stochastic_file", type=str, default="-", help=".npy of latents to take that point from (- : draw a fresh one)")
+    p.add_argument("--stochastic_index", type=int, default=0, help="row of --stochastic_file to use")
+    p.add_argument("--gen_qtd", type=int, default=1000, help="samples wanted per class")
+    p.add_argument("--trunc", type=float, default=0.95, help="truncation factor")
+    p.add_argument("--trunc_mode", type=str, default='w', choices=['z', 'w', '-'], help="truncate in Z space, in W space, or not at all")
+    p.add_argument("--mean_size", type=int, default=1000, help="latents used to estimate the truncation mean")
     # not in the reference
     p.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4)")
     p.add_argument("--out", type=str, default=None, help="output directory (default: actions/ of the latest run, generate.py:24-26)")

@@ -45,25 +45,25 @@ def check_runs(method, id=None, root="runs"):
 
 def build_parser():
     p = argparse.ArgumentParser()
-    p.add_argument("--n_epochs", type=int, default=1200, help="number of epochs of training")
-    p.add_argument("--batch_size", type=int, default=32, help="size of the batches (per GPU)")
-    p.add_argument("--lr", type=float, default=0.0002, help="adam: learning rate")
-    p.add_argument("--b1", type=float, default=0.5, help="adam: decay of first order momentum of gradient")
-    p.add_argument("--b2", type=float, default=0.999, help="adam: decay of first order momentum of gradient")
+    p.add_argument("--n_epochs", type=int, default=1200, help="passes over the dataset")
+    p.add_argument("--batch_size", type=int, default=32, help="samples per batch and per GPU")
+    p.add_argument("--lr", type=float, default=0.0002, help="Adam step size")
+    p.add_argument("--b1", type=float, default=0.5, help="Adam beta1")
+    p.add_argument("--b2", type=float, default=0.999, help="Adam beta2")
     p.add_argument("--n_cpu", type=int, default=8, help="kept for compatibility (batches are assembled by one gather thread)")
-    p.add_argument("--latent_dim", type=int, default=512, help="dimensionality of the latent space")
-    p.add_argument("--mlp_dim", type=int, default=4, help="mapping network depth")
-    p.add_argument("--n_classes", type=int, default=60, help="number of classes for dataset")
-    p.add_argument("--t_size", type=int, default=64, help="size of each temporal dimension")
-    p.add_argument("--v_size", type=int, default=25, help="size of each spatial dimension (vertices)")
-    p.add_argument("--channels", type=int, default=3, help="number of channels (coordinates)")
-    p.add_argument("--n_critic", type=int, default=5, help="number of training steps for discriminator per generator's iteration")
-    p.add_argument("--lambda_gp", type=int, default=10, help="Loss weight for gradient penalty in WGAN-GP Loss")
-    p.add_argument("--sample_interval", type=int, default=5000, help="interval between action sampling")
-    p.add_argument("--checkpoint_interval", type=int, default=10000, help="interval between model saving")
-    p.add_argument("--dataset", type=str, default="ntu", help="dataset")
-    p.add_argument("--data_path", type=str, required=True, help="path to data")
-    p.add_argument("--label_path", type=str, required=True, help="path to label")
+    p.add_argument("--latent_dim", type=int, default=512, help="length of the latent vector z")
+    p.add_argument("--mlp_dim", type=int, default=4, help="number of Linear layers in the mapping network")
+    p.add_argument("--n_classes", type=int, default=60, help="number of action classes")
+    p.add_argument("--t_size", type=int, default=64, help="frames per sequence (T)")
+    p.add_argument("--v_size", type=int, default=25, help="joints per frame (V); fixed by --dataset, kept for compatibility")
+    p.add_argument("--channels", type=int, default=3, help="coordinates per joint (C)")
+    p.add_argument("--n_critic", type=int, default=5, help="critic updates per generator update")
+    p.add_argument("--lambda_gp", type=int, default=10, help="weight of the gradient penalty in the critic loss")
+    p.add_argument("--sample_interval", type=int, default=5000, help="iterations between saved action samples")
+    p.add_argument("--checkpoint_interval", type=int, default=10000, help="iterations between checkpoints (-1: never)")
+    p.add_argument("--dataset", type=str, default="ntu", help="skeleton layout: ntu or h36m")
+    p.add_argument("--data_path", type=str, required=True, help=".npy with the training sequences")
+    p.add_argument("--label_path", type=str, required=True, help=".pkl with (names, labels)")
     # not in the reference
     p.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4)")
     p.add_argument("--log_interval", type=int, default=100, help="iterations between loss read-backs / prints")
