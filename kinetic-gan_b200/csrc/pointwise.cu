@@ -215,19 +215,73 @@ __global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict_
     }
 }
 
+// Small planes (p_out <= 64) with small tables (J <= 4) - the one-joint / five-joint ends of both networks: a CTA works on
+// PT / tpp planes at once (tpp = threads per plane, a power of two >= p_out), every thread owns one output position of one plane
+// lane with its table entries in registers, 4 planes in flight.  Consecutive planes are contiguous, so a warp still touches
+// consecutive addresses.  (The generic kernel below pays a 64-bit division and J table loads per element.)
+template <int J>
+__global__ void __launch_bounds__(PT) plane_spmm_small_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
+                                                          float* __restrict__ out, int64_t rows, int p_in, int p_out, int tpp) {
+    const int q = threadIdx.x & (tpp - 1);
+    if (q >= p_out) return;
+    const int ppb = PT / tpp;
+    int id[J];
+    float w[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int s = __ldg(idx + q * J + j);
+        id[j] = s >= 0 ? s : 0;
+        w[j] = s >= 0 ? __ldg(wgt + q * J + j) : 0.f;
+    }
+    const int64_t stride = (int64_t)gridDim.x * ppb;
+    int64_t r = (int64_t)blockIdx.x * ppb + threadIdx.x / tpp;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* xr = x + (r + u * stride) * p_in;
+            acc[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[u] = fmaf(w[j], __ldg(xr + id[j]), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) out[(r + u * stride) * p_out + q] = acc[u];
+    }
+    for (; r < rows; r += stride) {
+        const float* xr = x + r * p_in;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc = fmaf(w[j], __ldg(xr + id[j]), acc);
+        out[r * p_out + q] = acc;
+    }
+}
+
+// generic tables (long lists: frame sums, pooling): one thread per output element, four independent partial sums
 __global__ void __launch_bounds__(PT) plane_spmm_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
                                                     float* __restrict__ out, int64_t rows, int p_in, int p_out, int jn) {
     const int64_t total = rows * p_out;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int q = (int)(i % p_out);
         const int64_t r = i / p_out;
+        const int q = (int)(i - r * p_out);
         const float* xr = x + r * p_in;
-        float acc = 0.f;
-        for (int j = 0; j < jn; ++j) {
-            const int s = __ldg(idx + q * jn + j);
-            if (s >= 0) acc = fmaf(__ldg(wgt + q * jn + j), __ldg(xr + s), acc);
+        const int32_t* iq = idx + q * jn;
+        const float* wq = wgt + q * jn;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int j = 0;
+        for (; j + 3 < jn; j += 4) {
+            const int s0 = __ldg(iq + j), s1 = __ldg(iq + j + 1), s2 = __ldg(iq + j + 2), s3 = __ldg(iq + j + 3);
+            const float v0 = s0 >= 0 ? __ldg(xr + s0) : 0.f, v1 = s1 >= 0 ? __ldg(xr + s1) : 0.f;
+            const float v2 = s2 >= 0 ? __ldg(xr + s2) : 0.f, v3 = s3 >= 0 ? __ldg(xr + s3) : 0.f;
+            a0 = fmaf(__ldg(wq + j), v0, a0);
+            a1 = fmaf(__ldg(wq + j + 1), v1, a1);
+            a2 = fmaf(__ldg(wq + j + 2), v2, a2);
+            a3 = fmaf(__ldg(wq + j + 3), v3, a3);
         }
-        out[i] = acc;
+        for (; j < jn; ++j) {
+            const int s0 = __ldg(iq + j);
+            if (s0 >= 0) a0 = fmaf(__ldg(wq + j), __ldg(xr + s0), a0);
+        }
+        out[i] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -477,6 +531,19 @@ extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* 
         else if (j == 2) plane_spmm_rows_k<2><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
         else if (j == 3) plane_spmm_rows_k<3><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
         else plane_spmm_rows_k<4><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        return check_launch("plane_spmm");
+    }
+    if (j <= 4 && p_out <= 64) {
+        int tpp = 1;
+        while (tpp < p_out) tpp *= 2;
+        const int ppb = PT / tpp;
+        int64_t gx = ceil_div64(rows, ppb);
+        if (gx > (int64_t)kNumSMs * 8) gx = (int64_t)kNumSMs * 8;
+        cudaStream_t s = (cudaStream_t)stream;
+        if (j == 1) plane_spmm_small_k<1><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
+        else if (j == 2) plane_spmm_small_k<2><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
+        else if (j == 3) plane_spmm_small_k<3><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
+        else plane_spmm_small_k<4><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
         return check_launch("plane_spmm");
     }
     plane_spmm_k<<<grid_for(rows * p_out), PT, 0, (cudaStream_t)stream>>>(x, idx, wgt, out, rows, p_in, p_out, j);

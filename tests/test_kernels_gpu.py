@@ -163,3 +163,19 @@ def test_errors_are_reported_not_thrown():
     lib = _lib.lib()
     assert lib.kgan_adjmix_fwd(0, 0, 0, 1, 1, 1, 1, 1, 1, 0) != 0
     assert b"null" in lib.kgan_last_error()
+
+
+def test_plane_spmm_small_planes_and_long_lists():
+    """The one-/five-joint ends of the critic: planes below 64 positions (several planes per CTA, table entries in registers),
+    their adjoints (two-entry lists), and long lists (frame sums, pooling) on the generic kernel."""
+    unf = G.UnfoldedTcnGeom(7, 7, 16, 1, 3, 1, 1, 1, list(range(0, 16, 2))).unfold          # (16, 1) -> (24, 1)
+    unf5 = G.UnfoldedTcnGeom(7, 7, 8, 5, 3, 1, 1, 1, list(range(0, 8, 2))).unfold            # (8, 5) -> (12, 5): 60 positions
+    cases = [(unf, rnd(301, 7, 16, 1, seed=1)), (unf.T, rnd(301, 7, 24, 1, seed=2)),
+             (unf5, rnd(130, 9, 8, 5, seed=3)), (unf5.T, rnd(130, 9, 12, 5, seed=4)),
+             (G.select_table(16, 5, list(range(0, 16, 2)), [4]), rnd(77, 33, 16, 5, seed=5)),          # (16, 5) -> (8, 1)
+             (G.select_table(16, 5, list(range(0, 16, 2)), [4]).T, rnd(77, 33, 8, 1, seed=6)),
+             (G.select_table(8, 1, [0, 2, 4, 6], [0]), rnd(2, 3, 8, 1, seed=7)),                        # fewer planes than one CTA holds
+             (G.sum_t_table(64, 12), rnd(40, 32, 64, 12, seed=8)), (G.sum_t_table(64, 12).T, rnd(40, 32, 1, 12, seed=9)),
+             (G.mean_table(4, 1), rnd(50, 512, 4, 1, seed=10)), (G.mean_table(4, 1).T, rnd(50, 512, 1, 1, seed=11))]
+    for tb, inp in cases:
+        assert rel(ops.plane_spmm(cu(inp), tb), emu.plane_spmm(dbl(inp), tb)) < TOL, (tb.p_in, tb.p_out, tb.J)
