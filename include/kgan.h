@@ -66,7 +66,8 @@ typedef struct kgan_tapconv_desc {
      * above stays authoritative for every other entry point.
      *   tma_mode 0: no shift form.
      *   tma_mode 1: pmap[tap_row[t]][p] == p + tap_shift[t] when that lies in [0, p_in), else -1 (p_in may differ from p_out).
-     * The TMA kernel additionally needs p_in, p_out and every shift to be multiples of 4 (16-byte box origins). */
+     * The TMA kernel additionally needs p_in, p_out and every shift to be multiples of 4 (16-byte box origins), or one-position
+     * planes with a channel count that is a multiple of 4 (see kgan_tapconv_tma_ok). */
     int32_t tma_mode;
     int32_t tap_shift[KGAN_MAX_TAPS];
     /* Position-block groups (kgan_tapconv_fwd / _fwd_tf32 only; 0, 0 = off): the output planes hold p_out_plane >= p_out positions
@@ -115,8 +116,12 @@ int64_t kgan_tapconv_pack_item_bytes(void);
 int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
                                    int upload, void* stream);
 
-/* 1 if kgan_tapconv_fwd_tf32 will run the TMA-fed kernel for this descriptor (tma_mode != 0, plane size a multiple of 4,
- * tensor-core eligible): activations then reach shared memory by cp.async.bulk.tensor instead of per-thread gathers. */
+/* 1 if kgan_tapconv_fwd_tf32 will run the TMA-fed kernel for this descriptor: activations then reach shared memory by
+ * cp.async.bulk.tensor instead of per-thread gathers.  Eligible: tma_mode != 0, tensor-core eligible, and either
+ *   - planes of a multiple of 4 positions with every tap shift a multiple of 4 positions (activations as an MN-major operand:
+ *     boxes of 32 positions x 32 channels, a temporal tap is a coordinate shift), or
+ *   - one-position planes (p_in == p_out == 1: nn.Linear) with all shifts 0 and c_in_total a multiple of 4 (the (N, C)
+ *     activation matrix as a K-major operand: boxes of 128 samples x 32 channels). */
 int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d);
 
 /* Tensor-core path of kgan_tapconv_wgrad (tcgen05.mma kind::tf32, split-K over CTAs, fp32 atomics into dw).
