@@ -9,7 +9,7 @@ if _root not in sys.path:
     sys.path.insert(0, _root)
 _REAL = "kinetic-gan_b200"
 _pkg = importlib.import_module(_REAL)
-for _sub in ("wgan_gp", "ddp", "generate", "feeder", "train"):
+for _sub in ("wgan_gp", "ddp", "generate", "feeder", "train", "evaluation"):
     importlib.import_module(_REAL + "." + _sub)
 for _name, _mod in list(sys.modules.items()):
     if _name == _REAL or _name.startswith(_REAL + "."):
