@@ -239,3 +239,22 @@ def test_train_cli_two_ranks_gloo(tmp_path):
     for i in range(3):
         assert np.array_equal(a["seen"][i], perm[4 * i:4 * i + 2]) and np.array_equal(b["seen"][i], perm[4 * i + 2:4 * i + 4])
     assert len(a["loss_d"]) == len(b["loss_d"]) == 3 and np.isfinite(a["loss_d"]).all() and np.isfinite(b["loss_d"]).all()
+
+
+def test_train_rejects_dataset_smaller_than_a_global_batch(emu, tmp_path):
+    """drop_last semantics leave zero batches: the reference would silently run zero iterations per epoch; here it is an error."""
+    dp, lp, _, _ = make_dataset(str(tmp_path), n=3)
+    with pytest.raises(ValueError, match="smaller than one global batch"):
+        train_mod.train(_train_opts(dp, lp, os.path.join(str(tmp_path), "runs")))
+
+
+def test_feeder_without_normalisation_and_h36m_layout(tmp_path):
+    """norm=False returns the stored values (how mmd-actions.py reads generated data); h36m files have no person axis."""
+    dp, lp, data, labels = make_dataset(str(tmp_path), "h36m", n=9, c=2, t=12, v=16, n_classes=3)
+    f = feeder_mod.Feeder(dp, lp, norm=False, dataset="h36m", mmap=False)
+    a, la = f[4]
+    assert np.array_equal(a, data[4]) and la == labels[4] and (f.N, f.C, f.T, f.V) == (9, 2, 12, 16)
+    x, y = f.batch([8, 0], t_size=50)                      # t_size beyond the stored length: whole sequence
+    assert x.shape == (2, 2, 12, 16) and np.array_equal(x, data[[8, 0]]) and y.tolist() == [labels[8], labels[0]]
+    got = list(feeder_mod.BatchStream(f, 4, None, "cpu", shuffle=False))
+    assert len(got) == 2 and torch.equal(got[1][0], torch.from_numpy(data[4:8]))
