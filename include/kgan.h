@@ -8,7 +8,15 @@
  *   - tensors are float32, dense, NCHW-contiguous (N, C, T, V); a "plane" is the T*V block of one
  *     (n, c) pair, P = T*V;
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant per
- *     stream (no global mutable state besides the per-thread last-error string);
+ *     stream.  The library reads no environment variables and keeps no mutable state besides the
+ *     per-thread last-error string and a per-(kernel, device) "shared-memory attribute set" bit;
+ *   - `out_tf32` (and kgan_tapconv_desc.precision == KGAN_PREC_TF32 for the tap convolution): the
+ *     activations a kernel PRODUCES are stored rounded to tf32 (round to nearest, ties away; fp32
+ *     container).  The tensor-core kernels feed raw fp32 words to tcgen05.mma kind::tf32, which
+ *     reads the upper 19 bits: on tf32-rounded tensors that read is exact, so the tf32 mode
+ *     computes RN(x) * RN(w) with fp32 accumulation - unbiased, and exact on tf32-representable
+ *     data.  A tensor that did not come from a libkgan kernel is truncated instead (one-sided,
+ *     < 2^-10 relative); pass it through kgan_round_tf32 first if that matters;
  *   - return value: 0 = ok, non-zero = error (message via kgan_last_error()); nothing throws
  *     across the boundary; there is NO CPU fallback.
  */
@@ -61,7 +69,7 @@ typedef struct kgan_tapconv_desc {
     int32_t add_period;        /* 0: `add` has the shape of out; else add is (N, c_out_total, add_period) and is read at
                                   p % add_period (a term that is constant over frames, broadcast along T) */
     int32_t act;               /* KGAN_ACT_* applied by kgan_tapconv_fwd only */
-    int32_t precision;         /* KGAN_PREC_*: informational (which entry point the caller intends to use) */
+    int32_t precision;         /* KGAN_PREC_TF32: the output is stored tf32-rounded (see `out_tf32` above), by every tapconv entry point */
     /* Shift form of the position maps, used by the TMA-fed tensor-core kernel (kgan_tapconv_fwd_tf32); the gather form
      * above stays authoritative for every other entry point.
      *   tma_mode 0: no shift form.
@@ -96,8 +104,8 @@ int kgan_device_ok(void);
 int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, const float* w, const int32_t* pmap,
                      const float* bias, const float* add, float* out, void* stream);
 
-/* Tensor-core path of kgan_tapconv_fwd: tcgen05.mma kind::tf32 (inputs rounded to tf32 with round-to-nearest, fp32
- * accumulation in TMEM; rel-L2 ~3e-4 per layer).  The weights are first packed into the shared-memory image the
+/* Tensor-core path of kgan_tapconv_fwd: tcgen05.mma kind::tf32 (weights rounded to tf32 by the packing kernel, activations
+ * expected tf32-rounded - see `out_tf32` in the conventions; fp32 accumulation in TMEM; rel-L2 ~3e-4 per layer).  The weights are first packed into the shared-memory image the
  * kernel streams with bulk copies:
  *   kgan_tapconv_tf32_workspace(d)  -> number of floats of the packed image; 0 if the shape is not eligible
  *                                      (ck < 16, co < 16 or fewer than 256 output positions: use kgan_tapconv_fwd)
@@ -131,23 +139,25 @@ int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d);
  * positions, shifts multiples of 4) instead of per-thread cp.async copies. */
 int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d);
 int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
-                            float* dw, int64_t dw_numel, void* stream);
+                            float* dw, int64_t dw_numel, int accumulate, void* stream);
 
 /* dW[...same addressing as W...] = sum_{n,p} gout[n, out_ch0+oc, p] * in[n, in_ch0+tap_in_ch+ic, pmap[..]]
  * Replaces convolution_backward w.r.t. weight for the same call sites, and (called with swapped roles)
  * the weight terms of _convolution_double_backward used by the gradient penalty (kinetic-gan.py:104-113,154).
- * `dw` must hold `dw_numel` floats and is overwritten (zeroed, then accumulated with fp32 atomics). */
+ * `dw` must hold `dw_numel` floats.  accumulate == 0: dw is overwritten (zeroed, then accumulated with fp32 atomics);
+ * accumulate != 0: the result is ADDED to what dw holds - what autograd's AccumulateGrad does with a second launch
+ * (p.grad += dw) when dw is a view of the flat gradient buffer (kinetic-gan.py:154,173 `backward()`). */
 int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
-                       float* dw, int64_t dw_numel, void* stream);
+                       float* dw, int64_t dw_numel, int accumulate, void* stream);
 
 /* ---- adjacency product ---------------------------------------------------------------------------
  * out[r, k, w] = sum_v x[r, v] * A[k, v, w]      rows r = (n, c, t); written as (N, K*C, T, W)
  * Replaces torch.einsum('nkctv,kvw->nctw') at tgcn.py:66 (applied before the 1x1 conv, which commutes with it
  * because gcn.conv has bias=False, tgcn.py:44,55).  A is (K, V, W) - rectangular so that upsample_s
  * (generator.py:185-200) can be folded into it. */
-int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream);
+int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
 /* gx[r, v] = sum_k sum_w gout[r, k, w] * A[k, v, w] */
-int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream);
+int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
 /* gA[k, v, w] = sum_r x[r, v] * gout[r, k, w]  (gA overwritten) */
 int kgan_adjmix_bwd_a(const float* x, const float* gout, float* gA, int n, int c, int t, int v, int w, int k, void* stream);
 /* Same, restricted to the support of `mask` (K, V, W): gA[k, v, w] = 0 where mask[k, v, w] == 0.  The callers pass the
@@ -161,10 +171,10 @@ int kgan_adjmix_bwd_a_masked(const float* x, const float* gout, const float* mas
  * out[n,c,p] = act( a[n,c,p] + b[n,c,p] + bias[c] + nw[c] * noise[n,p] ); b, bias, (nw,noise) may be NULL.
  * Replaces `tcn(x) + res`, NoiseInjection (generator.py:12-19,179-180) and LeakyReLU/Tanh (generator.py:182). */
 int kgan_epilogue_fwd(const float* a, const float* b, const float* bias, const float* nw, const float* noise,
-                      float* out, int n, int c, int p, int act, void* stream);
+                      float* out, int n, int c, int p, int act, int out_tf32, void* stream);
 /* gz = gout * act'(out)   (LeakyReLU: out > 0 ? 1 : 0.2;  tanh: 1 - out^2).  Replaces leaky_relu_backward /
  * tanh_backward; also the second-order use of the same mask in the gradient penalty. */
-int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, void* stream);
+int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, int out_tf32, void* stream);
 /* out[c] = sum_{n,p} g[n,c,p] * (mul ? mul[n,p] : 1).  Bias gradients and NoiseInjection.weight gradient. */
 int kgan_chan_reduce(const float* g, const float* mul, float* out, int n, int c, int p, void* stream);
 
@@ -174,13 +184,13 @@ int kgan_chan_reduce(const float* g, const float* mul, float* out, int n, int c,
  * identity residual in D (discriminator.py:128-134), avg_pool2d (discriminator.py:68), and their backward passes
  * (the transposed table). */
 int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out,
-                    int j, void* stream);
+                    int j, int out_tf32, void* stream);
 
 /* ---- label planes (discriminator.py:57-60) -------------------------------------------------------
  * out[n, c, p] = c < n_cls ? e[n, c] : x[n, c - n_cls, p] */
-int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, void* stream);
+int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, int out_tf32, void* stream);
 /* ge[n, c] = sum_p g[n, c, p] (c < n_cls);  gx[n, c, p] = g[n, n_cls + c, p].  Either output may be NULL. */
-int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, void* stream);
+int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, int out_tf32, void* stream);
 
 /* ---- BatchNorm2d, training mode (generator.py:142,160) ---------------------------------------------
  * stats: mean[c], rstd[c] from biased variance over (n, p); running stats updated in place with `momentum`
@@ -189,10 +199,10 @@ int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean,
                   float eps, float momentum, void* stream);
 /* y = (x - mean[c]) * rstd[c] * gamma[c] + beta[c]  (also eval mode with running stats folded by the caller) */
 int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
-                  int n, int c, int p, void* stream);
+                  int n, int c, int p, int out_tf32, void* stream);
 /* gx, ggamma[c], gbeta[c] of training-mode BN */
 int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx,
-                float* ggamma, float* gbeta, int n, int c, int p, void* stream);
+                float* ggamma, float* gbeta, int n, int c, int p, int out_tf32, void* stream);
 
 /* ---- fused Adam over a flat parameter buffer (torch.optim.Adam, kinetic-gan.py:77-78,155,174) ----
  * g is multiplied by grad_scale first (1/world_size after the DDP sum all-reduce). `step` is 1-based. */
@@ -200,7 +210,11 @@ int kgan_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, 
                    int step, float grad_scale, void* stream);
 
 /* out = alpha * x + (1 - alpha) * y with alpha per sample (kinetic-gan.py:100); per_sample = C*T*V */
-int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, void* stream);
+int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, int out_tf32, void* stream);
+
+/* out = x rounded to tf32 (round to nearest, ties away; in place when out == x): for tensors that enter the tf32 path from
+ * outside the library (the latent / label-embedding rows fed to the mapping network, generator.py:80-85). */
+int kgan_round_tf32(const float* x, float* out, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,23 +40,24 @@ _SIGS = {
     "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
-    "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
-    "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _V], C.c_int),
-    "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
-    "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _I, _V], C.c_int),
+    "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _I, _V], C.c_int),
+    "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a_masked": ([_F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
-    "kgan_epilogue_fwd": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
-    "kgan_act_bwd": ([_F, _F, _F, C.c_int64, _I, _V], C.c_int),
+    "kgan_epilogue_fwd": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_act_bwd": ([_F, _F, _F, C.c_int64, _I, _I, _V], C.c_int),
     "kgan_chan_reduce": ([_F, _F, _F, _I, _I, _I, _V], C.c_int),
-    "kgan_plane_spmm": ([_F, _F, _F, _F, C.c_int64, _I, _I, _I, _V], C.c_int),
-    "kgan_label_concat": ([_F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
-    "kgan_label_split": ([_F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_plane_spmm": ([_F, _F, _F, _F, C.c_int64, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_label_concat": ([_F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_label_split": ([_F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_bn_stats": ([_F, _F, _F, _F, _F, _I, _I, _I, C.c_float, C.c_float, _V], C.c_int),
-    "kgan_bn_apply": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _V], C.c_int),
-    "kgan_bn_bwd": ([_F, _F, _F, _F, _F, _F, _F, _F, _I, _I, _I, _V], C.c_int),
+    "kgan_bn_apply": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_bn_bwd": ([_F, _F, _F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adam_step": ([_F, _F, _F, _F, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _V], C.c_int),
-    "kgan_interpolate": ([_F, _F, _F, _F, _I, C.c_int64, _V], C.c_int),
+    "kgan_interpolate": ([_F, _F, _F, _F, _I, C.c_int64, _I, _V], C.c_int),
+    "kgan_round_tf32": ([_F, _F, C.c_int64, _V], C.c_int),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -9,8 +9,6 @@
 // All index arithmetic is per block, not per element.
 // A_eff = A (.) edge_importance keeps the skeleton's sparsity (73 of 1875 entries at 25 joints): the forward and dx
 // kernels compact the non-zeros of A in shared memory and touch only those (exact).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace kgan {
@@ -76,7 +74,7 @@ struct MixEntry {
 
 template <int MODE>
 __global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int n,
-                                                       int ct, int v, int w, int k, int chunks_per_block, int64_t total_items) {
+                                                       int ct, int v, int w, int k, int chunks_per_block, int64_t total_items, int rnd) {
     extern __shared__ __align__(16) float sm[];
     const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;           // output blocks per sample / outputs per row
     const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;           // inputs per row / input blocks per sample
@@ -124,7 +122,7 @@ __global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ 
                 const int c = cnt[o];
                 for (int j = 0; j < c; ++j) acc = fmaf(el[j].coef, __ldg(xq + el[j].off), acc);
             }
-            r[u] = acc;
+            r[u] = tf32_out(acc, rnd);
             if (++ww == (unsigned)wo) {
                 ww = 0;
                 ++q;
@@ -247,7 +245,7 @@ struct Mix2Plan {
 // rows q, q + rs, ... of one output column: LT = (padded) length of the column's non-zero list, held in registers
 template <int LT>
 __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const MixEntry* __restrict__ el, float* __restrict__ ob, int q, int rs, int rows,
-                                         int vi, int wo) {
+                                         int vi, int wo, int rnd) {
     float cf[LT > 0 ? LT : 1];
     int of[LT > 0 ? LT : 1];
 #pragma unroll
@@ -268,30 +266,30 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
             a2 = fmaf(cf[j], xp[2 * xstep + of[j]], a2);
             a3 = fmaf(cf[j], xp[3 * xstep + of[j]], a3);
         }
-        op[0] = a0;
-        op[ostep] = a1;
-        op[2 * ostep] = a2;
-        op[3 * ostep] = a3;
+        op[0] = tf32_out(a0, rnd);
+        op[ostep] = tf32_out(a1, rnd);
+        op[2 * ostep] = tf32_out(a2, rnd);
+        op[3 * ostep] = tf32_out(a3, rnd);
     }
     for (; q < rows; q += rs, xp += xstep, op += ostep) {
         float a0 = 0.f;
 #pragma unroll
         for (int j = 0; j < LT; ++j) a0 = fmaf(cf[j], xp[of[j]], a0);
-        op[0] = a0;
+        op[0] = tf32_out(a0, rnd);
     }
 }
 __device__ __noinline__ void mix_rows_any(const float* __restrict__ xs, const MixEntry* __restrict__ el, int L, float* __restrict__ ob, int q, int rs,
-                                          int rows, int vi, int wo) {
+                                          int rows, int vi, int wo, int rnd) {
     for (; q < rows; q += rs) {
         float a0 = 0.f;
         for (int j = 0; j < L; ++j) a0 = fmaf(el[j].coef, xs[q * vi + el[j].off], a0);
-        ob[(size_t)q * wo] = a0;
+        ob[(size_t)q * wo] = tf32_out(a0, rnd);
     }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
-                                                        int w, int k, const __grid_constant__ Mix2Plan pl) {
+                                                        int w, int k, const __grid_constant__ Mix2Plan pl, int rnd) {
     extern __shared__ __align__(128) float sm[];
     const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;
     const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
@@ -378,16 +376,16 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
                 const MixEntry* el = ent + ((size_t)kb * wo + my_w) * lc;          // this thread's list: same output column for every row
                 float* ob = out + ((nn * ko + kb) * (int64_t)ct + q0) * wo + my_w;
                 switch (L) {
-                    case 0: mix_rows<0>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 1: mix_rows<1>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 2: mix_rows<2>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 3: mix_rows<3>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 4: mix_rows<4>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 5: mix_rows<5>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 6: mix_rows<6>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 7: mix_rows<7>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    case 8: mix_rows<8>(xs, el, ob, my_q, rs, rows, vi, wo); break;
-                    default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo); break;
+                    case 0: mix_rows<0>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 1: mix_rows<1>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 2: mix_rows<2>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 3: mix_rows<3>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 4: mix_rows<4>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 5: mix_rows<5>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 6: mix_rows<6>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 7: mix_rows<7>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 8: mix_rows<8>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, rnd); break;
                 }
             }
         }
@@ -537,22 +535,12 @@ static int check_shape(const char* what, int n, int c, int t, int v, int w, int 
     return 0;
 }
 
-template <typename Kern>
-static int set_smem(Kern kern, size_t bytes, bool& done) {
-    if (!done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return check_launch("adjmix attribute");
-        done = true;
-    }
-    (void)bytes;
-    return 0;
-}
-
 }  // namespace kgan
 
 using namespace kgan;
 
 template <int MODE>
-static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
+static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, int rnd, void* stream) {
     KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "%s: empty dimension", what);
     const int64_t ct64 = (int64_t)c * t;
     KGAN_REQUIRE(ct64 * (MODE == 0 ? w : v) < (1ll << 31) && ct64 * k * w < (1ll << 31), "%s: plane too large", what);
@@ -560,18 +548,13 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
     const int nlists = ko * wo;
     const size_t smem = (size_t)((nlists + 3) & ~3) * 4 + (size_t)k * v * w * sizeof(MixEntry);
     KGAN_REQUIRE(smem <= 200 * 1024, "%s: V=%d, W=%d, K=%d do not fit in shared memory", what, v, w, k);
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(adjmix_rowmix_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return check_launch("adjmix attribute");
-        attr = true;
-    }
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(adjmix_rowmix_k<MODE>, 200 * 1024, attr, "adjmix attribute")) return e;
     // bulk-copy pipelined kernel whenever every row block is 16-byte addressable
     {
         const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
         const int maxj = MODE == 0 ? v : k * w;
-        static const bool force_old = getenv("KGAN_ADJMIX_V1") != nullptr;
-        if (!force_old && k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        if (k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             Mix2Plan pl;
             int R = (24 * 1024) / (ki * vi * 4);                 // <= 24 KB per stage: 4 CTAs (2 stages each) per SM
             R = R / 8 * 8;
@@ -588,17 +571,13 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
                 const size_t smem2 = (size_t)2 * pl.in_floats * 4 + 16 + 16 + (size_t)((nlists + 3) & ~3) * 4 + (size_t)nlists * pl.lc_max * sizeof(MixEntry);
                 pl.smem_bytes = (int)smem2;
                 if (smem2 <= 100 * 1024) {
-                    static bool attr2 = false;
-                    if (!attr2) {
-                        if (cudaFuncSetAttribute(adjmix_rowmix2_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-                            return check_launch("adjmix attribute");
-                        attr2 = true;
-                    }
+                    static SmemAttrOnce attr2;
+                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE>, 100 * 1024, attr2, "adjmix attribute")) return e;
                     const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
                     const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
                     const int64_t waves = ceil_div64(pl.tiles, cap);
                     const int64_t grid2 = ceil_div64(pl.tiles, waves);   // every CTA gets `waves` tiles (+-1), all CTAs co-resident
-                    adjmix_rowmix2_k<MODE><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl);
+                    adjmix_rowmix2_k<MODE><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, rnd);
                     return check_launch(what);
                 }
             }
@@ -607,18 +586,18 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
     const int chunks = (int)ceil_div64((int64_t)ct * wo, AT * 4);
     const int64_t items = (int64_t)n * ko * chunks;
     const int64_t grid = items < 8 * kNumSMs ? items : 8 * kNumSMs;
-    adjmix_rowmix_k<MODE><<<(unsigned)grid, AT, smem, (cudaStream_t)stream>>>(in, A, out, n, ct, v, w, k, chunks, items);
+    adjmix_rowmix_k<MODE><<<(unsigned)grid, AT, smem, (cudaStream_t)stream>>>(in, A, out, n, ct, v, w, k, chunks, items, rnd);
     return check_launch(what);
 }
 
-extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, void* stream) {
+extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
-    return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, stream);
+    return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, out_tf32, stream);
 }
 
-extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, void* stream) {
+extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
-    return launch_rowmix<1>("adjmix_bwd_x", g, A, gx, n, c, t, v, w, k, stream);
+    return launch_rowmix<1>("adjmix_bwd_x", g, A, gx, n, c, t, v, w, k, out_tf32, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {
@@ -629,9 +608,8 @@ extern "C" int kgan_adjmix_bwd_a_masked(const float* x, const float* g, const fl
                                         void* stream) {
     KGAN_REQUIRE(x && g && gA, "adjmix_bwd_a: null pointer");
     KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "adjmix_bwd_a: empty dimension");
-    static const bool force_old = getenv("KGAN_ADJMIX_V1") != nullptr;
     const int64_t ct64 = (int64_t)c * t;
-    if (mask && !force_old && (ct64 * v) % 4 == 0 && (ct64 * w) % 4 == 0 && ct64 < (1ll << 30) &&
+    if (mask && (ct64 * v) % 4 == 0 && (ct64 * w) % 4 == 0 && ct64 < (1ll << 30) &&
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g)) & 15) == 0) {
         // sparse path: lane = non-zero of the mask (any number of non-zeros up to k*v*w <= DA_EPT * AT)
         const int per_row = (v + k * w) * 4;
@@ -651,12 +629,8 @@ extern "C" int kgan_adjmix_bwd_a_masked(const float* x, const float* g, const fl
             pl.cap = k * v * w;
             const size_t smem2 = (size_t)2 * (pl.x_floats + pl.g_floats) * 4 + 16 + 16 + (sizeof(DAEntry) + 4) * (size_t)pl.cap;
             pl.smem_bytes = (int)smem2;
-            static bool attr2 = false;
-            if (!attr2) {
-                if (cudaFuncSetAttribute(adjmix_bwd_a2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-                    return check_launch("adjmix attribute");
-                attr2 = true;
-            }
+            static SmemAttrOnce attr2;
+            if (int e = ensure_smem(adjmix_bwd_a2_k, 160 * 1024, attr2, "adjmix attribute")) return e;
             cudaStream_t s2 = (cudaStream_t)stream;
             if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s2) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
             const int64_t cap = 2 * kNumSMs;
@@ -668,8 +642,8 @@ extern "C" int kgan_adjmix_bwd_a_masked(const float* x, const float* g, const fl
     KGAN_REQUIRE(k * ((v + 3) / 4) * ((w + 3) / 4) <= AT, "adjmix_bwd_a: k*v*w too large");
     const size_t fl = carve_floats(k, v, w, 0, 0);
     if (int e = check_shape("adjmix_bwd_a", n, c, t, v, w, k, fl)) return e;
-    static bool attr = false;
-    if (int e = set_smem(adjmix_bwd_a_k, fl * 4, attr)) return e;
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(adjmix_bwd_a_k, 200 * 1024, attr, "adjmix attribute")) return e;
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(gA, 0, sizeof(float) * k * v * w, s) != cudaSuccess) return check_launch("adjmix_bwd_a memset");
     const int ct = c * t, bps = ceil_div(ct, RB);

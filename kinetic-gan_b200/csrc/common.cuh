@@ -1,6 +1,8 @@
 // Shared helpers for libkgan.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -20,6 +22,23 @@ inline int check_launch(const char* what) {
     return 0;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remembered per (kernel, device ordinal), so a process
+// that drives several GPUs sets it on each of them (a process-wide `static bool` left the second device at the 48 KB default).
+struct SmemAttrOnce {
+    std::atomic<uint64_t> done{0};
+};
+template <typename Kern>
+inline int ensure_smem(Kern kern, int bytes, SmemAttrOnce& once, const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return check_launch(what);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(once.done.load(std::memory_order_acquire) & bit)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return check_launch(what);
+        once.done.fetch_or(bit, std::memory_order_release);
+    }
+    return 0;
+}
+
 #define KGAN_REQUIRE(cond, ...)          \
     do {                                 \
         if (!(cond)) {                   \
@@ -35,6 +54,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == KGAN_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
     if (act == KGAN_ACT_TANH) return tanhf(v);
     return v;
+}
+
+// tf32 mode (KGAN_PREC_TF32 / out_tf32 = 1): every kernel that PRODUCES an activation stores it rounded to tf32 (round to nearest,
+// ties away from zero == cvt.rna.tf32.f32 for finite values; fp32 container, low 13 mantissa bits zero).  The tensor-core kernels feed
+// raw fp32 words to tcgen05.mma kind::tf32, which reads the upper 19 bits only: on such values that read is exact, so the product is
+// RN(x) * RN(w) with no bias and tf32-representable data (0/1 masks, all-ones cotangents, small integers) go through exactly.
+__device__ __forceinline__ float tf32_out(float v, int rnd) {
+    return rnd ? __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u) : v;
 }
 
 __device__ __forceinline__ int64_t w_oc_offset(const kgan_tapconv_desc& d, int oc) {
@@ -65,6 +92,6 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d);
 int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);   // TMA-fed variant (tapconv_wgrad_tma.cu)
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
-                       cudaStream_t stream);   // -1: not eligible
+                       int accumulate, cudaStream_t stream);   // -1: not eligible
 
 }  // namespace kgan

@@ -39,7 +39,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // one warp per (n, c) plane: per-plane constants, 16-byte accesses when the plane allows, no per-element index arithmetic
 __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                                                       const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
-                                                      int n, int c, int p, int act, int vec) {
+                                                      int n, int c, int p, int act, int vec, int rnd) {
     const int lane = threadIdx.x & 31;
     const int64_t planes = (int64_t)n * c, tw = (int64_t)gridDim.x * (PT / 32);
     for (int64_t pl = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5); pl < planes; pl += tw) {
@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
                     const float4 z = __ldg(zp + i);
                     v.x = fmaf(wn, z.x, v.x), v.y = fmaf(wn, z.y, v.y), v.z = fmaf(wn, z.z, v.z), v.w = fmaf(wn, z.w, v.w);
                 }
-                op[i] = make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
+                op[i] = make_float4(tf32_out(apply_act(v.x, act), rnd), tf32_out(apply_act(v.y, act), rnd), tf32_out(apply_act(v.z, act), rnd),
+                                    tf32_out(apply_act(v.w, act), rnd));
             }
         } else {
             for (int i = lane; i < p; i += 32) {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
                 if (b) v += b[o + i];
                 v += bs;
                 if (nw) v = fmaf(wn, __ldg(noise + on + i), v);
-                out[o + i] = apply_act(v, act);
+                out[o + i] = tf32_out(apply_act(v, act), rnd);
             }
         }
     }
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
 // element, consecutive threads on consecutive addresses; the warp-per-plane kernel above would leave 31 / 28 / 12 lanes idle
 __global__ void __launch_bounds__(PT) epilogue_fwd_small_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                                                             const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
-                                                            unsigned total, unsigned c, unsigned p, int act) {
+                                                            unsigned total, unsigned c, unsigned p, int act, int rnd) {
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const unsigned pl = e / p, pp = e - pl * p;
         const unsigned nn = pl / c, cc = pl - nn * c;
@@ -89,13 +90,13 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_small_k(const float* __restri
         if (b) v += b[e];
         if (bias) v += __ldg(bias + cc);
         if (nw) v = fmaf(__ldg(nw + cc), __ldg(noise + nn * p + pp), v);
-        out[e] = apply_act(v, act);
+        out[e] = tf32_out(apply_act(v, act), rnd);
     }
 }
 
 // 16-byte vector variant (numel % 4 == 0, 16-byte aligned pointers)
 __global__ void __launch_bounds__(PT) act_bwd4_k(const float4* __restrict__ go, const float4* __restrict__ o, float4* __restrict__ gz, int64_t n4,
-                                                  int act) {
+                                                  int act, int rnd) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 y = o[i], g = go[i];
         float4 r;
@@ -112,18 +113,18 @@ __global__ void __launch_bounds__(PT) act_bwd4_k(const float4* __restrict__ go, 
         } else {
             r = g;
         }
-        gz[i] = r;
+        gz[i] = make_float4(tf32_out(r.x, rnd), tf32_out(r.y, rnd), tf32_out(r.z, rnd), tf32_out(r.w, rnd));
     }
 }
 
 __global__ void __launch_bounds__(PT) act_bwd_k(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ gz, int64_t numel,
-                                                 int act) {
+                                                 int act, int rnd) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
         const float y = o[i];
         float m = 1.f;
         if (act == KGAN_ACT_LRELU) m = y > 0.f ? 1.f : 0.2f;
         else if (act == KGAN_ACT_TANH) m = 1.f - y * y;
-        gz[i] = go[i] * m;
+        gz[i] = tf32_out(go[i] * m, rnd);
     }
 }
 
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(PT) chan_reduce4_k(const float* __restrict__ g
 // its table entries in registers and walks over the (n, c) planes - no index arithmetic and no table loads per element.
 template <int J>
 __global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
-                                                         float* __restrict__ out, int64_t rows, int p_in, int p_out) {
+                                                         float* __restrict__ out, int64_t rows, int p_in, int p_out, int rnd) {
     const int q = blockIdx.y * blockDim.x + threadIdx.x;
     if (q >= p_out) return;
     int id[J];
@@ -204,14 +205,14 @@ __global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict_
             for (int j = 0; j < J; ++j) acc[u] = fmaf(w[j], __ldg(xr + id[j]), acc[u]);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) out[(r + u * (int64_t)gridDim.x) * p_out + q] = acc[u];
+        for (int u = 0; u < U; ++u) out[(r + u * (int64_t)gridDim.x) * p_out + q] = tf32_out(acc[u], rnd);
     }
     for (; r < rows; r += gridDim.x) {
         const float* xr = x + r * p_in;
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < J; ++j) acc = fmaf(w[j], __ldg(xr + id[j]), acc);
-        out[r * p_out + q] = acc;
+        out[r * p_out + q] = tf32_out(acc, rnd);
     }
 }
 
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(PT) plane_spmm_rows_k(const float* __restrict_
 // consecutive addresses.  (The generic kernel below pays a 64-bit division and J table loads per element.)
 template <int J>
 __global__ void __launch_bounds__(PT) plane_spmm_small_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
-                                                          float* __restrict__ out, int64_t rows, int p_in, int p_out, int tpp) {
+                                                          float* __restrict__ out, int64_t rows, int p_in, int p_out, int tpp, int rnd) {
     const int q = threadIdx.x & (tpp - 1);
     if (q >= p_out) return;
     const int ppb = PT / tpp;
@@ -245,20 +246,20 @@ __global__ void __launch_bounds__(PT) plane_spmm_small_k(const float* __restrict
             for (int j = 0; j < J; ++j) acc[u] = fmaf(w[j], __ldg(xr + id[j]), acc[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) out[(r + u * stride) * p_out + q] = acc[u];
+        for (int u = 0; u < 4; ++u) out[(r + u * stride) * p_out + q] = tf32_out(acc[u], rnd);
     }
     for (; r < rows; r += stride) {
         const float* xr = x + r * p_in;
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < J; ++j) acc = fmaf(w[j], __ldg(xr + id[j]), acc);
-        out[r * p_out + q] = acc;
+        out[r * p_out + q] = tf32_out(acc, rnd);
     }
 }
 
 // generic tables (long lists: frame sums, pooling): one thread per output element, four independent partial sums
 __global__ void __launch_bounds__(PT) plane_spmm_k(const float* __restrict__ x, const int32_t* __restrict__ idx, const float* __restrict__ wgt,
-                                                    float* __restrict__ out, int64_t rows, int p_in, int p_out, int jn) {
+                                                    float* __restrict__ out, int64_t rows, int p_in, int p_out, int jn, int rnd) {
     const int64_t total = rows * p_out;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / p_out;
@@ -281,12 +282,12 @@ __global__ void __launch_bounds__(PT) plane_spmm_k(const float* __restrict__ x, 
             const int s0 = __ldg(iq + j);
             if (s0 >= 0) a0 = fmaf(__ldg(wq + j), __ldg(xr + s0), a0);
         }
-        out[i] = (a0 + a1) + (a2 + a3);
+        out[i] = tf32_out((a0 + a1) + (a2 + a3), rnd);
     }
 }
 
 __global__ void __launch_bounds__(PT) label_concat_k(const float* __restrict__ e, const float* __restrict__ x, float* __restrict__ out, int n,
-                                                      int ncls, int c, int p) {
+                                                      int ncls, int c, int p, int rnd) {
     const int ct = ncls + c;
     const int64_t total = (int64_t)n * ct * p;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -294,13 +295,13 @@ __global__ void __launch_bounds__(PT) label_concat_k(const float* __restrict__ e
         const int64_t nc = i / p;
         const int cc = (int)(nc % ct);
         const int64_t nn = nc / ct;
-        out[i] = cc < ncls ? __ldg(e + nn * ncls + cc) : __ldg(x + (nn * c + (cc - ncls)) * p + pp);
+        out[i] = tf32_out(cc < ncls ? __ldg(e + nn * ncls + cc) : __ldg(x + (nn * c + (cc - ncls)) * p + pp), rnd);
     }
 }
 
 // one warp per (n, channel) plane of the label part; remaining threads copy the data part
 __global__ void __launch_bounds__(PT) label_split_k(const float* __restrict__ g, float* __restrict__ ge, float* __restrict__ gx, int n, int ncls,
-                                                     int c, int p) {
+                                                     int c, int p, int rnd) {
     const int ct = ncls + c;
     if (ge) {
         const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(PT) label_split_k(const float* __restrict__ g,
             const int64_t nc = i / p;
             const int cc = (int)(nc % c);
             const int64_t nn = nc / c;
-            gx[i] = __ldg(g + (nn * ct + ncls + cc) * p + pp);
+            gx[i] = tf32_out(__ldg(g + (nn * ct + ncls + cc) * p + pp), rnd);
         }
     }
 }
@@ -414,7 +415,7 @@ template <int MODE>
 __global__ void __launch_bounds__(PT) bn_elem_k(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ mean,
                                                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  const float* __restrict__ s1, const float* __restrict__ s2, float* __restrict__ out, int n, int c, int p,
-                                                 int vec) {
+                                                 int vec, int rnd) {
     const int lane = threadIdx.x & 31;
     const int64_t planes = (int64_t)n * c, tw = (int64_t)gridDim.x * BNW;
     const float inv_cnt = 1.f / (float)((int64_t)n * p);
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(PT) bn_elem_k(const float* __restrict__ x, con
         const float b0 = MODE == 0 ? __ldg(beta + cc) : 0.f;
         const float m1 = MODE == 1 ? __ldg(s1 + cc) * inv_cnt : 0.f, m2 = MODE == 1 ? __ldg(s2 + cc) * inv_cnt : 0.f;
         const int64_t o = pl * p;
-        auto f = [&](float xv, float gv) { return MODE == 0 ? fmaf(xv - mu, sc, b0) : sc * (gv - m1 - (xv - mu) * rs * m2); };
+        auto f = [&](float xv, float gv) { return tf32_out(MODE == 0 ? fmaf(xv - mu, sc, b0) : sc * (gv - m1 - (xv - mu) * rs * m2), rnd); };
         if (vec) {
             const float4* xp = reinterpret_cast<const float4*>(x + o);
             const float4* gp = reinterpret_cast<const float4*>(gy + o);
@@ -465,39 +466,49 @@ __global__ void __launch_bounds__(PT) adam_k(float* __restrict__ p, const float*
 }
 
 __global__ void __launch_bounds__(PT) interpolate_k(const float* __restrict__ alpha, const float* __restrict__ x, const float* __restrict__ y,
-                                                     float* __restrict__ out, int n, int64_t per) {
+                                                     float* __restrict__ out, int n, int64_t per, int rnd) {
     const int64_t total = (int64_t)n * per;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const float a = __ldg(alpha + i / per);
-        out[i] = a * x[i] + (1.f - a) * y[i];
+        out[i] = tf32_out(a * x[i] + (1.f - a) * y[i], rnd);
     }
+}
+
+__global__ void __launch_bounds__(PT) round_tf32_k(const float* __restrict__ x, float* __restrict__ out, int64_t numel) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) out[i] = tf32_out(x[i], 1);
 }
 
 }  // namespace kgan
 
 using namespace kgan;
 
+extern "C" int kgan_round_tf32(const float* x, float* out, int64_t numel, void* stream) {
+    KGAN_REQUIRE(x && out && numel > 0, "round_tf32: bad argument");
+    round_tf32_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(x, out, numel);
+    return check_launch("round_tf32");
+}
+
 extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bias, const float* nw, const float* noise, float* out,
-                                 int n, int c, int p, int act, void* stream) {
+                                 int n, int c, int p, int act, int out_tf32, void* stream) {
     KGAN_REQUIRE(a && out && n > 0 && c > 0 && p > 0, "epilogue_fwd: bad argument");
     KGAN_REQUIRE((nw == nullptr) == (noise == nullptr), "epilogue_fwd: nw and noise go together");
     const int vec = (p & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(noise) |
                                       reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (p < 32 && (int64_t)n * c * p < (1ll << 31))
         epilogue_fwd_small_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, (unsigned)((int64_t)n * c * p),
-                                                                                          (unsigned)c, (unsigned)p, act);
+                                                                                          (unsigned)c, (unsigned)p, act, out_tf32);
     else
-        epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec);
+        epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec, out_tf32);
     return check_launch("epilogue_fwd");
 }
 
-extern "C" int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, void* stream) {
+extern "C" int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, int out_tf32, void* stream) {
     KGAN_REQUIRE(gout && out && gz && numel > 0, "act_bwd: bad argument");
     if ((numel & 3) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gz)) & 15) == 0)
         act_bwd4_k<<<grid_for(numel / 4), PT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(gout), reinterpret_cast<const float4*>(out),
-                                                                        reinterpret_cast<float4*>(gz), numel / 4, act);
+                                                                        reinterpret_cast<float4*>(gz), numel / 4, act, out_tf32);
     else
-        act_bwd_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(gout, out, gz, numel, act);
+        act_bwd_k<<<grid_for(numel), PT, 0, (cudaStream_t)stream>>>(gout, out, gz, numel, act, out_tf32);
     return check_launch("act_bwd");
 }
 
@@ -518,7 +529,7 @@ extern "C" int kgan_chan_reduce(const float* g, const float* mul, float* out, in
 }
 
 extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out, int j,
-                               void* stream) {
+                               int out_tf32, void* stream) {
     KGAN_REQUIRE(x && idx && wgt && out && rows > 0 && p_in > 0 && p_out > 0 && j > 0, "plane_spmm: bad argument");
     if (j <= 4 && p_out >= 64 && rows >= 64) {
         const int chunks = ceil_div(p_out, PT);
@@ -527,10 +538,10 @@ extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* 
         if (gx < 1) gx = 1;
         const dim3 grid((unsigned)gx, (unsigned)chunks);
         cudaStream_t s = (cudaStream_t)stream;
-        if (j == 1) plane_spmm_rows_k<1><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
-        else if (j == 2) plane_spmm_rows_k<2><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
-        else if (j == 3) plane_spmm_rows_k<3><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
-        else plane_spmm_rows_k<4><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out);
+        if (j == 1) plane_spmm_rows_k<1><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, out_tf32);
+        else if (j == 2) plane_spmm_rows_k<2><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, out_tf32);
+        else if (j == 3) plane_spmm_rows_k<3><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, out_tf32);
+        else plane_spmm_rows_k<4><<<grid, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, out_tf32);
         return check_launch("plane_spmm");
     }
     if (j <= 4 && p_out <= 64) {
@@ -540,26 +551,26 @@ extern "C" int kgan_plane_spmm(const float* x, const int32_t* idx, const float* 
         int64_t gx = ceil_div64(rows, ppb);
         if (gx > (int64_t)kNumSMs * 8) gx = (int64_t)kNumSMs * 8;
         cudaStream_t s = (cudaStream_t)stream;
-        if (j == 1) plane_spmm_small_k<1><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
-        else if (j == 2) plane_spmm_small_k<2><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
-        else if (j == 3) plane_spmm_small_k<3><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
-        else plane_spmm_small_k<4><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp);
+        if (j == 1) plane_spmm_small_k<1><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp, out_tf32);
+        else if (j == 2) plane_spmm_small_k<2><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp, out_tf32);
+        else if (j == 3) plane_spmm_small_k<3><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp, out_tf32);
+        else plane_spmm_small_k<4><<<(unsigned)gx, PT, 0, s>>>(x, idx, wgt, out, rows, p_in, p_out, tpp, out_tf32);
         return check_launch("plane_spmm");
     }
-    plane_spmm_k<<<grid_for(rows * p_out), PT, 0, (cudaStream_t)stream>>>(x, idx, wgt, out, rows, p_in, p_out, j);
+    plane_spmm_k<<<grid_for(rows * p_out), PT, 0, (cudaStream_t)stream>>>(x, idx, wgt, out, rows, p_in, p_out, j, out_tf32);
     return check_launch("plane_spmm");
 }
 
-extern "C" int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, void* stream) {
+extern "C" int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, int out_tf32, void* stream) {
     KGAN_REQUIRE(e && x && out && n > 0 && n_cls > 0 && c > 0 && p > 0, "label_concat: bad argument");
-    label_concat_k<<<grid_for((int64_t)n * (n_cls + c) * p), PT, 0, (cudaStream_t)stream>>>(e, x, out, n, n_cls, c, p);
+    label_concat_k<<<grid_for((int64_t)n * (n_cls + c) * p), PT, 0, (cudaStream_t)stream>>>(e, x, out, n, n_cls, c, p, out_tf32);
     return check_launch("label_concat");
 }
 
-extern "C" int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, void* stream) {
+extern "C" int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int c, int p, int out_tf32, void* stream) {
     KGAN_REQUIRE(g && (ge || gx) && n > 0 && n_cls > 0 && c > 0 && p > 0, "label_split: bad argument");
     const int64_t work = (int64_t)n * (n_cls * 32 > c * p ? n_cls * 32 : c * p);
-    label_split_k<<<grid_for(work), PT, 0, (cudaStream_t)stream>>>(g, ge, gx, n, n_cls, c, p);
+    label_split_k<<<grid_for(work), PT, 0, (cudaStream_t)stream>>>(g, ge, gx, n, n_cls, c, p, out_tf32);
     return check_launch("label_split");
 }
 
@@ -576,15 +587,15 @@ extern "C" int kgan_bn_stats(const float* x, float* mean, float* rstd, float* ru
 }
 
 extern "C" int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int n, int c,
-                             int p, void* stream) {
+                             int p, int out_tf32, void* stream) {
     KGAN_REQUIRE(x && mean && rstd && gamma && beta && y && n > 0 && c > 0 && p > 0, "bn_apply: bad argument");
     bn_elem_k<0><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, (cudaStream_t)stream>>>(x, nullptr, mean, rstd, gamma, beta, nullptr, nullptr, y, n, c, p,
-                                                                                  bn_vec_ok(p, x, y, nullptr));
+                                                                                  bn_vec_ok(p, x, y, nullptr), out_tf32);
     return check_launch("bn_apply");
 }
 
 extern "C" int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx, float* ggamma,
-                           float* gbeta, int n, int c, int p, void* stream) {
+                           float* gbeta, int n, int c, int p, int out_tf32, void* stream) {
     KGAN_REQUIRE(gy && x && mean && rstd && gamma && gx && ggamma && gbeta && n > 0 && c > 0 && p > 0, "bn_bwd: bad argument");
     KGAN_REQUIRE(c <= 65535, "bn_bwd: too many channels");
     cudaStream_t s = (cudaStream_t)stream;
@@ -592,7 +603,7 @@ extern "C" int kgan_bn_bwd(const float* gy, const float* x, const float* mean, c
         return check_launch("bn_bwd memset");
     const int vec = bn_vec_ok(p, x, gy, gx);
     bn_partial_k<true><<<bn_partial_grid(n, c), PT, 0, s>>>(x, gy, mean, rstd, gbeta, ggamma, n, c, p, vec);
-    bn_elem_k<1><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, s>>>(x, gy, mean, rstd, gamma, nullptr, gbeta, ggamma, gx, n, c, p, vec);
+    bn_elem_k<1><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, s>>>(x, gy, mean, rstd, gamma, nullptr, gbeta, ggamma, gx, n, c, p, vec, out_tf32);
     return check_launch("bn_bwd");
 }
 
@@ -605,8 +616,9 @@ extern "C" int kgan_adam_step(float* p, const float* g, float* m, float* v, int6
     return check_launch("adam_step");
 }
 
-extern "C" int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, void* stream) {
+extern "C" int kgan_interpolate(const float* alpha, const float* x, const float* y, float* out, int n, int64_t per_sample, int out_tf32,
+                                void* stream) {
     KGAN_REQUIRE(alpha && x && y && out && n > 0 && per_sample > 0, "interpolate: bad argument");
-    interpolate_k<<<grid_for((int64_t)n * per_sample), PT, 0, (cudaStream_t)stream>>>(alpha, x, y, out, n, per_sample);
+    interpolate_k<<<grid_for((int64_t)n * per_sample), PT, 0, (cudaStream_t)stream>>>(alpha, x, y, out, n, per_sample, out_tf32);
     return check_launch("interpolate");
 }

@@ -5,8 +5,6 @@
 // GEMM view: rows = flattened output positions (n, p), columns = output channels,
 // contraction = (tap, input channel).  Positions are contiguous in memory for a fixed channel (NCHW), so
 // lanes run along positions for every global load/store (coalesced 128 B segments).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace kgan {
@@ -109,7 +107,7 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_simt(const __grid_constant__ k
             float v = acc[i][j];
             if (bias) v += __ldg(bias + out_ch0 + oc);
             if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + out_ch0 + oc) * d.add_period + pg % d.add_period : o));
-            out[o] = apply_act(v, d.act);
+            out[o] = tf32_out(apply_act(v, d.act), d.precision == KGAN_PREC_TF32);
         }
     }
 }
@@ -249,16 +247,15 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
                 float v = acc[j];
                 if (bias) v += __ldg(bias + c);
                 if (add) v += __ldg(add + (d.add_period ? ((int64_t)nn * d.c_out_total + c) * d.add_period + pa : o));
-                out[o] = apply_act(v, d.act);
+                out[o] = tf32_out(apply_act(v, d.act), d.precision == KGAN_PREC_TF32);
             }
         }
     }
 }
 
 bool tapconv_is_thin(const kgan_tapconv_desc& d) {
-    static const bool off = getenv("KGAN_NO_THIN") != nullptr;
     const int na = thin_merge(d) * d.co;
-    if (off || na > 16 || d.w_oc_blk != 0 || (int64_t)d.n * d.p_out < 4096) return false;
+    if (na > 16 || d.w_oc_blk != 0 || (int64_t)d.n * d.p_out < 4096) return false;
     const int CO = na <= 4 ? 4 : na <= 8 ? 8 : 16;
     return (int64_t)d.ck * d.ntap * na <= THIN_MAX_W && (int64_t)d.ck * d.ntap * CO <= 4096;
 }
@@ -324,12 +321,12 @@ extern "C" int kgan_tapconv_fwd(const kgan_tapconv_desc* d, const float* in, con
 }
 
 extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
-                                  float* dw, int64_t dw_numel, void* stream) {
+                                  float* dw, int64_t dw_numel, int accumulate, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad: null pointer");
     KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad: position-block groups are a forward / data-gradient feature");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
+    if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
     const int64_t total = (int64_t)d->n * d->p_out;
     const int tiles = d->ntap * ceil_div(d->ck, WB) * ceil_div(d->co, WB) * d->groups;
     int64_t nchunks = ceil_div64(4 * kNumSMs, tiles);
@@ -349,8 +346,7 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
 // (w_oc_blk): the activation tile is fetched once instead of once per group.  Applied to every descriptor entering the tensor-core
 // forward path (workspace size, packing, launch), so the packed image and the kernel always agree.
 static kgan_tapconv_desc merge_groups(const kgan_tapconv_desc& d) {
-    static const bool off = getenv("KGAN_NO_GROUP_MERGE") != nullptr;
-    if (off || d.groups <= 1 || d.g_in != 0 || d.g_out != d.co || d.w_oc_blk != 0 || d.g_pout != 0) return d;
+    if (d.groups <= 1 || d.g_in != 0 || d.g_out != d.co || d.w_oc_blk != 0 || d.g_pout != 0) return d;
     kgan_tapconv_desc m = d;
     m.w_oc_blk = d.co;
     m.w_ocblk = d.g_w;
@@ -390,9 +386,8 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
                                      const float* bias, const float* add, float* out, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
-    static const bool no_tma = getenv("KGAN_NO_TMA") != nullptr;      // A/B switch for benchmarks: force the gather kernel
     const kgan_tapconv_desc m = merge_groups(*d);
-    if (m.tma_mode != 0 && !no_tma) {
+    if (m.tma_mode != 0) {
         const int rt = tapconv_fwd_tma(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
         if (rt != -1) return rt;
     }
@@ -421,11 +416,11 @@ extern "C" int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d) {
 }
 
 extern "C" int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* in, const float* gout, const int32_t* pmap,
-                                       float* dw, int64_t dw_numel, void* stream) {
+                                       float* dw, int64_t dw_numel, int accumulate, void* stream) {
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad_tf32: null pointer");
     KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad_tf32: position-block groups are a forward / data-gradient feature");
-    int r = tapconv_wgrad_tf32(*d, in, gout, pmap, dw, dw_numel, (cudaStream_t)stream);
+    int r = tapconv_wgrad_tf32(*d, in, gout, pmap, dw, dw_numel, accumulate, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_wgrad_tf32: shape not eligible for the tensor-core path (kgan_tapconv_wgrad_tf32_ok() == 0)");
         return 1;

@@ -13,10 +13,11 @@
 // With 4-6 stages of 16 KB in flight per SM the kernel is bandwidth- instead of latency-bound (the SIMT-gather kernel
 // holds at most 32 KB of loads in registers, and measured 8-20 % of HBM peak with long-scoreboard stalls dominating).
 //
-// Raw fp32 activations reach the tensor core, which reads the upper 19 bits (truncation); the weights are pre-rounded
-// (round-to-nearest) by tapconv_pack_k.  Truncating one operand biases every product by -3.53e-4 (half of the two-operand
-// figure measured for the weight-gradient kernel); the epilogue removes that bias, leaving the zero-mean rounding noise
-// (~3e-4 rel-L2, same as round-to-nearest operands).
+// Raw fp32 activation words reach the tensor core, which reads the upper 19 bits; the weights are pre-rounded (round to
+// nearest) by tapconv_pack_k.  In tf32 mode every libkgan kernel stores its activations tf32-rounded (common.cuh tf32_out -
+// this kernel's own epilogue included), so the 19-bit read is exact: products are RN(x) * RN(w), unbiased, and exact for
+// tf32-representable data.  (Round 1 multiplied the accumulator by 1.000353 to undo the mean truncation bias of raw
+// operands: a statistical fix that put a deterministic +3.5e-4 on exactly representable inputs.)
 //
 // The TMA unit requires the innermost (position) coordinate of a box to be a multiple of 16 bytes - an unaligned shift
 // raises an illegal-instruction fault - so only descriptors whose shifts are multiples of 4 positions are eligible.  The host
@@ -27,7 +28,6 @@
 // TMEM owner (accumulators double-buffered), warps 2-9 = epilogue (TMEM -> bias/add/act -> coalesced NCHW stores),
 // warps 10-13 = cp.async activation producers (only launched when p_box < 32).
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "umma.cuh"
@@ -41,7 +41,6 @@ constexpr int TM_PROD_WARPS = 3;                                       // TMA mo
 constexpr int TM_THREADS_TMA = TM_THREADS + 32 * (TM_PROD_WARPS - 1);
 constexpr int TM_CP_WARPS = 4;
 constexpr int TM_THREADS_CP = TM_THREADS + 32 * TM_CP_WARPS;          // cp.async mode
-constexpr float TM_TRUNC_FIX = 1.000353f;      // 1 / (1 - 3.53e-4)
 constexpr int TM_GROUP_BYTES = 32 * 32 * 4;    // one box: 32 channel rows of 128 bytes
 
 struct TmaPlan {
@@ -65,8 +64,7 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     // One-position planes (nn.Linear: the mapping network, the generator's first block at T = V = 1): the activations are an
     // (N, C) row-major matrix, i.e. a plain K-major operand - one [128 samples] x [32 channels] box per stage in the standard
     // SWIZZLE_128B layout.  (As an "MN-major" operand they would need a box along the sample axis, which is strided.)
-    static const bool no_kmajor = getenv("KGAN_TMA_NO_KMAJOR") != nullptr;
-    p.kmajor = (d.p_in == 1 && d.p_out == 1 && out_plane(d) == 1 && !no_kmajor) ? 1 : 0;
+    p.kmajor = (d.p_in == 1 && d.p_out == 1 && out_plane(d) == 1) ? 1 : 0;
     if (p.kmajor) {
         if (d.c_in_total & 3) return false;                        // row stride of the (N, C) matrix must be a multiple of 16 bytes
         for (int t = 0; t < d.ntap; ++t)
@@ -95,13 +93,12 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     // Resident weights: a CTA re-fetches the same packed weight stages for every one of its tiles - a third of the bytes an SM
     // ingests at N = 64 (the marginal cost of a K stage measured ~700 cycles for 16 KB of activations + 8 KB of weights).  When
     // the whole image (all groups, all K stages) fits beside a ring of >= 5 activation stages it is loaded once per CTA.
-    static const bool no_wres = getenv("KGAN_TMA_NO_WRES") != nullptr;
     p.w_res = 0;
     p.w_res_bytes = 0;
     {
         const int64_t img = (int64_t)d.groups * p.nkt * d.ntap * p.n_cta * UK * 4;
         const int64_t tiles_per_cta = ceil_div64(p.num_tiles, kNumSMs);
-        if (!no_wres && p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
+        if (p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
             int st = (int)((200 * 1024 - img) / A_STAGE_BYTES);
             if (st > 8) st = 8;
             if (st >= 5) {
@@ -115,7 +112,7 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     p.a_lbo = TM_GROUP_BYTES;
     p.a_sbo = 512;
     // L2 prefetch (TMA mode only): ~256 KB of unique activation bytes ahead of the shared-memory ring
-    static const int pf_env = getenv("KGAN_TMA_PREFETCH") ? atoi(getenv("KGAN_TMA_PREFETCH")) : -1;
+    constexpr int pf_env = -1;         // compile-time switch (measured slower, see below)
     p.pf_taps = 0;
     int uniq = 0;
     for (int t = 0; t < d.ntap; ++t) {
@@ -174,7 +171,7 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
 template <int ACT>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                   const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
-                                                  uint32_t tfull_bar, uint32_t tfull_parity) {
+                                                  uint32_t tfull_bar, uint32_t tfull_parity, int rnd) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -194,11 +191,11 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
         float* o = op + (int64_t)col0 * p_out;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float val = fmaf(__uint_as_float(r[j]), TM_TRUNC_FIX, __shfl_sync(0xffffffffu, bl, j));
+            float val = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
-            if (valid && j < nc) *o = val;
+            if (valid && j < nc) *o = tf32_out(val, rnd);
             o += p_out;
         }
     }
@@ -438,6 +435,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     } else {
         // ===== epilogue warps: TMEM lane = row of the tile = (M group, element of the box) =====
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may read == M group of the tile
+        const int rnd = d.precision == KGAN_PREC_TF32;                // activations are stored tf32-rounded in tf32 mode
         const int colpar = (warp - TM_EPI_WARP0) >> 2;
         int ti = 0;
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
@@ -462,9 +460,9 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
-            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
-            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar);
+            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
+            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
+            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);
         }
@@ -551,18 +549,8 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return 1;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tapconv_fwd_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return check_launch("tapconv_fwd_tma attribute");
-        attr_set = true;
-    }
-    if (const char* v = getenv("KGAN_TMA_DESC_SWAP")) {            // bring-up switch: exchange the two descriptor strides
-        if (v[0] == '1') {
-            p.a_lbo = 512;
-            p.a_sbo = TM_GROUP_BYTES;
-        }
-    }
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(tapconv_fwd_tma_k, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
     (void)pmap;                                                    // the shift form replaces the position map
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);

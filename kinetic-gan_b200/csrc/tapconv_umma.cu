@@ -146,7 +146,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const UmmaPlan& pl) {
 // and broadcast by shuffle, the activation is a template parameter, addresses advance by one plane per channel.
 template <int ACT>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
-                                              const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane) {
+                                              const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane, int rnd) {
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (FW_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
         float av[16];
@@ -164,7 +164,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int ncols, int col
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
-            if (valid && j < nc) *o = val;
+            if (valid && j < nc) *o = tf32_out(val, rnd);
             o += p_out;
         }
     }
@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);          // columns of this tile that exist
-            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
-            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
-            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane);
+            if (d.act == KGAN_ACT_LRELU) epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, d.precision == KGAN_PREC_TF32);
+            else if (d.act == KGAN_ACT_TANH) epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, d.precision == KGAN_PREC_TF32);
+            else epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, d.precision == KGAN_PREC_TF32);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);                           // accumulator may be overwritten
         }
@@ -459,12 +459,8 @@ int tapconv_fwd_tf32(const kgan_tapconv_desc& d, const float* in, const float* w
                      const float* add, float* out, cudaStream_t stream) {
     UmmaPlan p;
     if (!make_plan(d, p)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tapconv_fwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return check_launch("tapconv_fwd_tf32 attribute");
-        attr_set = true;
-    }
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(tapconv_fwd_umma, 227 * 1024, attr, "tapconv_fwd_tf32 attribute")) return e;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;         // persistent: one CTA per SM
     tapconv_fwd_umma<<<grid, FW_THREADS, p.smem_bytes, stream>>>(d, p, in, wp, pmap, bias, add, out);
     return check_launch("tapconv_fwd_tf32");

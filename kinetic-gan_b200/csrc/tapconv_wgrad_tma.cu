@@ -11,13 +11,12 @@
 // unit zero-fills what falls outside the plane.  (The cp.async producers of tapconv_wgrad_umma.cu issue ~1000 16-byte copies
 // per stage and reached 25-35 % of HBM peak.)
 //
-// Both operands reach the tensor core as raw fp32 (truncation to tf32); the epilogue removes the truncation bias exactly as
-// tapconv_wgrad_umma.cu does.  Rows of a box beyond the channel tile read neighbouring channels (or zeros beyond the tensor);
+// Both operands reach the tensor core as raw fp32 words; in tf32 mode they were stored tf32-rounded by their producers
+// (common.cuh tf32_out), so the tensor core's 19-bit read is exact (see tapconv_wgrad_umma.cu).  Rows of a box beyond the channel tile read neighbouring channels (or zeros beyond the tensor);
 // they only feed accumulator rows / columns the epilogue never stores.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-9 = epilogue.
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "umma.cuh"
@@ -26,7 +25,6 @@ namespace kgan {
 
 constexpr int WT_EPI_WARPS = 8;
 constexpr int WT_THREADS = 32 * (2 + WT_EPI_WARPS);
-constexpr float WT_TRUNC_FIX = 1.000706f;        // 1 / (1 - 7.06e-4), see tapconv_wgrad_umma.cu
 constexpr int WT_KT = 32;                        // positions per K tile: one 128-byte swizzled row per channel
 
 struct WgradTmaPlan {
@@ -57,7 +55,6 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     // with tools/probe_wgrad_tma.py for 16 x 2, 8 x 4 and 4 x 8.)
     if ((d.p_out & 7) || (d.p_in & 3)) return false;
     p.p_box = (d.p_out % 32) == 0 ? 32 : (d.p_out % 16) == 0 ? 16 : 8;
-    if (getenv("KGAN_WGRAD_TMA_BOX32") && p.p_box != 32) return false;            // A/B switch: whole 128-byte rows only
     p.nsub = WT_KT / p.p_box;
     p.row_bytes = 4 * p.p_box;
     p.desc_hi = (uint32_t)((8 * p.row_bytes) >> 4) | (1u << 14) | ((p.p_box == 32 ? 2u : p.p_box == 16 ? 4u : 6u) << 29);
@@ -98,7 +95,7 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     if ((int64_t)p.nchunks * d.groups > 65535) return false;
     p.smem_bytes = p.stages * stage + tail_pad + 1024 + 512;    // + alignment slack + barriers
     // L2 prefetch: ~256 KB of unique operand bytes ahead of the ring
-    static const int pf_env = getenv("KGAN_TMA_PREFETCH") ? atoi(getenv("KGAN_TMA_PREFETCH")) : -1;
+    constexpr int pf_env = -1;         // compile-time switch (measured slower, see below)
     p.pf_taps = 0;
     int uniq = 0;
     for (int t = 0; t < d.ntap; ++t) {
@@ -270,7 +267,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
         float* wb = dw + (int64_t)g * d.g_w + (int64_t)oc * d.w_oc;
         bool taps_inner = d.ntap == 3 && d.w_ic == 3;
         for (int tp = 0; tp < d.ntap; ++tp) taps_inner = taps_inner && d.tap_w_off[tp] == d.tap_w_off[0] + tp;
-        auto fix = [](uint32_t bits) { return __uint_as_float(bits) * WT_TRUNC_FIX; };
+        auto fix = [](uint32_t bits) { return __uint_as_float(bits); };
         if (iters > 0) {
             if (taps_inner) {
                 for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
@@ -340,7 +337,7 @@ int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d) {
 }
 
 // -1: not eligible (the caller falls back to the cp.async kernel)
-int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, cudaStream_t stream) {
+int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, int accumulate, cudaStream_t stream) {
     WgradTmaPlan p;
     if (!make_wgrad_tma_plan(d, p)) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(gout)) & 15) return -1;
@@ -357,13 +354,9 @@ int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* 
         const uint32_t box[3] = {(uint32_t)p.p_box, 1u, (uint32_t)p.n_ic};
         if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, p.p_box == 32 ? 1 : p.p_box == 16 ? 2 : 3)) return e;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tapconv_wgrad_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return check_launch("tapconv_wgrad_tma attribute");
-        attr_set = true;
-    }
-    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tma memset");
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(tapconv_wgrad_tma_k, 227 * 1024, attr, "tapconv_wgrad_tma attribute")) return e;
+    if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tma memset");
     dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
     tapconv_wgrad_tma_k<<<grid, WT_THREADS, p.smem_bytes, stream>>>(d, p, map_g, map_x, dw);
     return check_launch("tapconv_wgrad_tma");

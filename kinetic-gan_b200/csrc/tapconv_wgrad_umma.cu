@@ -10,12 +10,12 @@
 //   selection, odd temporal shifts) fall back to four 4-byte copies per chunk.  gout (A operand) is staged once per K
 //   tile and reused by all taps.  Split-K over one wave of CTAs; the epilogue adds into dW with 16-byte vector
 //   reductions (REDG.ADD.F32x4) where the weight layout allows.
-//   Operands reach the tensor core as raw fp32: kind::tf32 reads the upper 19 bits (truncation).  Truncating both
-//   operands biases every product by -7.06e-4 (measured; 2 x the mean truncation error of a 10-bit mantissa); the
-//   epilogue removes that bias, leaving the zero-mean part (~3e-4 rel-L2, same as round-to-nearest operands).
+//   Operands reach the tensor core as raw fp32 words: kind::tf32 reads the upper 19 bits.  In tf32 mode every kernel of the
+//   library stores its activations already rounded to tf32 (round to nearest, common.cuh tf32_out), so that read is exact:
+//   no bias, and tf32-representable data (masks, all-ones cotangents) give exact products.  A tensor that did not come
+//   from a libkgan kernel is truncated instead (one-sided error < 2^-10 per element); callers that care pass it through
+//   kgan_round_tf32 first.
 // Warp roles: warps 0-7 cp.async producers, then epilogue; warp 8 MMA issuer / TMEM owner.
-#include <stdlib.h>
-
 #include "umma.cuh"
 
 namespace kgan {
@@ -23,7 +23,6 @@ namespace kgan {
 constexpr int WG_PRODUCER_WARPS = 8;
 constexpr int WG_PRODUCERS = 32 * WG_PRODUCER_WARPS;
 constexpr int WG_THREADS = WG_PRODUCERS + 32;
-constexpr float WG_TRUNC_FIX = 1.000706f;        // 1 / (1 - 7.06e-4): undoes the truncation bias of the two operands
 
 struct WgradPlan {
     int n_ic;         // input channels (UMMA N) per CTA, multiple of 16, <= 256
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
         //   taps innermost     (temporal conv weights (C_out, C_in, 3, 1)): the 3 taps x 16 channels interleave to 48 floats
         bool taps_inner = d.ntap == 3 && d.w_ic == 3;
         for (int tp = 0; tp < d.ntap; ++tp) taps_inner = taps_inner && d.tap_w_off[tp] == d.tap_w_off[0] + tp;
-        auto fix = [](uint32_t bits) { return __uint_as_float(bits) * WG_TRUNC_FIX; };
+        auto fix = [](uint32_t bits) { return __uint_as_float(bits); };
         if (taps_inner) {
             for (int col0 = colhalf * 16; col0 < pl.n_ic; col0 += 32) {
                 if (ic0 + col0 >= d.ck) break;                       // warp-uniform
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tapconv_wgrad_umma(const __grid
 }
 
 int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);
-int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, cudaStream_t stream);
+int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* gout, float* dw, int64_t dw_numel, int accumulate, cudaStream_t stream);
 
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
     WgradPlan p;
@@ -276,10 +275,9 @@ int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
 }
 
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
-                       cudaStream_t stream) {
-    static const bool no_tma = getenv("KGAN_NO_WGRAD_TMA") != nullptr;     // A/B switch: force the cp.async producers
-    if (!no_tma) {
-        const int rt = tapconv_wgrad_tma(d, in, gout, dw, dw_numel, stream);
+                       int accumulate, cudaStream_t stream) {
+    {
+        const int rt = tapconv_wgrad_tma(d, in, gout, dw, dw_numel, accumulate, stream);
         if (rt != -1) return rt;
     }
     WgradPlan p;
@@ -288,13 +286,9 @@ int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float*
         set_error("tapconv_wgrad_tf32: in / gout must be 16-byte aligned");
         return 1;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tapconv_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return check_launch("tapconv_wgrad_tf32 attribute");
-        attr_set = true;
-    }
-    if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tf32 memset");
+    static SmemAttrOnce attr;
+    if (int e = ensure_smem(tapconv_wgrad_umma, 227 * 1024, attr, "tapconv_wgrad_tf32 attribute")) return e;
+    if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tf32 memset");
     dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
     tapconv_wgrad_umma<<<grid, WG_THREADS, p.smem_bytes, stream>>>(d, p, in, gout, pmap, dw);
     return check_launch("tapconv_wgrad_tf32");

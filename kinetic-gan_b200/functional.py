@@ -300,6 +300,21 @@ class NoiseAct(Function):
         return ga, gb, None, gnw, None
 
 
+class RoundTF32(Function):
+    """Entry point of the tf32 path for a tensor that no libkgan kernel produced (latent / label-embedding rows, a truncated
+    W): stored tf32-rounded like every activation the kernels write (include/kgan.h `out_tf32`), so that the tensor cores read
+    it exactly.  Identity in fp32 mode; straight-through gradient (the rounding is piecewise constant + identity on its grid)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.set_materialize_grads(False)
+        return ops.round_tf32(_c(x))
+
+    @staticmethod
+    def backward(ctx, go):
+        return go
+
+
 # ------------------------------------------------------------------------------------------------
 # plane gather / scatter, label planes
 # ------------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ class Discriminator(nn.Module):
 
     def forward(self, x, labels):
         N, C, T, V = x.size()
-        c = self.label_emb(labels)                       # (N, n_cls); the (N, n_cls, T, V) planes are never built
+        c = KF.RoundTF32.apply(self.label_emb(labels))   # (N, n_cls); the (N, n_cls, T, V) planes are never built (identity in fp32 mode)
         A = self.A
         last = len(self.st_gcn_networks) - 1
         for i, (gcn, importance) in enumerate(zip(self.st_gcn_networks, self.edge_importance)):

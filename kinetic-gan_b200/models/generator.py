@@ -83,9 +83,9 @@ class Generator(nn.Module):
         """`noises` (optional, not in the reference): the 7 per-block noise tensors, for reproducible parity runs;
         by default each block draws torch.randn(N,1,T,V) on x.device in block order, as generator.py:179 does."""
         c = self.label_emb(labels)
-        x = torch.cat((c, x), -1)
+        x = KF.RoundTF32.apply(torch.cat((c, x), -1))                   # identity in fp32 mode
         w = self.mlp(x)
-        w = self.truncate(w, 1000, trunc) if trunc is not None else w   # Truncation trick on W
+        w = KF.RoundTF32.apply(self.truncate(w, 1000, trunc)) if trunc is not None else w   # Truncation trick on W
         x = w.view((*w.shape, 1, 1))
         A = self.A
         for i, (gcn, importance) in enumerate(zip(self.st_gcn_networks, self.edge_importance)):
@@ -112,7 +112,7 @@ class Generator(nn.Module):
         m = getattr(self, "_w_mean", None)          # generate.GeneratorRunner(cache_mean=True): one estimate for all calls
         if m is None:
             t = torch.as_tensor(np.random.normal(0, 1, (mean, *w.shape[1:])), dtype=w.dtype, device=w.device)
-            m = self.mlp(t).mean(0, keepdim=True)
+            m = self.mlp(KF.RoundTF32.apply(t)).mean(0, keepdim=True)
         return m + truncation * (w - m)
 
     def estimate_w_mean(self, mean=1000):
@@ -120,7 +120,7 @@ class Generator(nn.Module):
         dev, dt = self.label_emb.weight.device, self.label_emb.weight.dtype
         with torch.no_grad():
             t = torch.as_tensor(np.random.normal(0, 1, (mean, self.mlp.mlp[0].in_features)), dtype=dt, device=dev)
-            return self.mlp(t).mean(0, keepdim=True)
+            return self.mlp(KF.RoundTF32.apply(t)).mean(0, keepdim=True)
 
 
 class st_gcn(nn.Module):

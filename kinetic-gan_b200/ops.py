@@ -25,6 +25,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _rnd():
+    """`out_tf32` of include/kgan.h: in tf32 mode every kernel stores the activations it produces tf32-rounded, so the tensor
+    core's 19-bit operand read is exact (no truncation bias, exact on tf32-representable data)."""
+    return 1 if _precision == PREC_TF32 else 0
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -218,10 +224,14 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     return out
 
 
-def tapconv_wgrad(x, gout, desc, w_shape):
-    _chk(x, gout)
+def tapconv_wgrad(x, gout, desc, w_shape, out=None):
+    """`out` (optional): a contiguous fp32 tensor of the weight's shape that the result is ADDED to (the flat gradient view of
+    the parameter) instead of being returned in a fresh tensor - the kernels accumulate with atomics anyway."""
+    _chk(x, gout, out)
     n = x.shape[0]
-    dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+    acc = 0 if out is None else 1
+    dw = torch.empty(w_shape, device=x.device, dtype=torch.float32) if out is None else out
+    assert tuple(dw.shape) == tuple(w_shape)
     l = _lib.lib()
     cs = desc.cstruct(n, ACT_NONE, _precision)
     _io(x, gout, dw)
@@ -232,10 +242,10 @@ def tapconv_wgrad(x, gout, desc, w_shape):
         if ok[n]:
             _io(x, gout, dw)
             _run('tapconv_wgrad_tf32', _tap_flops(desc, n), l.kgan_tapconv_wgrad_tf32, cs, x.data_ptr(), gout.data_ptr(),
-                 desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
+                 desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), acc, _stream())
             return dw
     _run('tapconv_wgrad', _tap_flops(desc, n), l.kgan_tapconv_wgrad, cs, x.data_ptr(), gout.data_ptr(),
-         desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), _stream())
+         desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), acc, _stream())
     return dw
 
 
@@ -247,7 +257,7 @@ def adjmix_fwd(x, A):
     out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
     _shape_sig(x, A)
     _io(x, A, out)
-    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _stream())
+    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
     return out
 
 
@@ -260,7 +270,7 @@ def adjmix_bwd_x(g, A):
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
     _shape_sig(g, A)
     _io(g, A, gx)
-    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _stream())
+    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
     return gx
 
 
@@ -284,7 +294,7 @@ def epilogue_fwd(a, b=None, bias=None, nw=None, noise=None, act=ACT_NONE):
     out = torch.empty_like(a)
     _io(a, b, noise, out)
     _run('pointwise', 0.0, _lib.lib().kgan_epilogue_fwd, a.data_ptr(), _ptr(b), _ptr(bias), _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act,
-                                            _stream())
+                                            _rnd(), _stream())
     return out
 
 
@@ -293,7 +303,7 @@ def act_bwd(gout, out, act):
     gz = torch.empty_like(out)
     _shape_sig(out)
     _io(gout, out, gz)
-    _run('pointwise', 0.0, _lib.lib().kgan_act_bwd, gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _stream())
+    _run('pointwise', 0.0, _lib.lib().kgan_act_bwd, gout.data_ptr(), out.data_ptr(), gz.data_ptr(), out.numel(), act, _rnd(), _stream())
     return gz
 
 
@@ -316,7 +326,7 @@ def plane_spmm(x, table):
     _shape_sig(x, out)
     _io(x, out)
     _run('plane_spmm', 0.0, _lib.lib().kgan_plane_spmm, x.data_ptr(), idx.data_ptr(), wgt.data_ptr(), out.data_ptr(), n * c, table.p_in, table.p_out,
-                                          table.J, _stream())
+                                          table.J, _rnd(), _stream())
     return out
 
 
@@ -325,7 +335,7 @@ def label_concat(e, x):
     n, c, t, v = x.shape
     ncls = e.shape[1]
     out = torch.empty((n, ncls + c, t, v), device=x.device, dtype=torch.float32)
-    _run('label', 0.0, _lib.lib().kgan_label_concat, e.data_ptr(), x.data_ptr(), out.data_ptr(), n, ncls, c, t * v, _stream())
+    _run('label', 0.0, _lib.lib().kgan_label_concat, e.data_ptr(), x.data_ptr(), out.data_ptr(), n, ncls, c, t * v, _rnd(), _stream())
     return out
 
 
@@ -335,7 +345,7 @@ def label_split(g, ncls, need_e=True, need_x=True):
     c = ct - ncls
     ge = torch.empty((n, ncls), device=g.device, dtype=torch.float32) if need_e else None
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32) if need_x else None
-    _run('label', 0.0, _lib.lib().kgan_label_split, g.data_ptr(), _ptr(ge), _ptr(gx), n, ncls, c, t * v, _stream())
+    _run('label', 0.0, _lib.lib().kgan_label_split, g.data_ptr(), _ptr(ge), _ptr(gx), n, ncls, c, t * v, _rnd(), _stream())
     return ge, gx
 
 
@@ -356,7 +366,7 @@ def bn_apply(x, mean, rstd, gamma, beta):
     y = torch.empty_like(x)
     _io(x, y)
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_apply, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), n, c,
-                                        t * v, _stream())
+                                        t * v, _rnd(), _stream())
     return y
 
 
@@ -368,7 +378,7 @@ def bn_bwd(gy, x, mean, rstd, gamma):
     gb = torch.empty((c,), device=x.device, dtype=torch.float32)
     _io(gy, x, gy, x, gx)          # two passes over (gy, x): sums, then the elementwise pass
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_bwd, gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
-                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _stream())
+                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _rnd(), _stream())
     return gx, gg, gb
 
 
@@ -383,5 +393,16 @@ def interpolate(alpha, x, y):
     _chk(alpha, x, y)
     n = x.shape[0]
     out = torch.empty_like(x)
-    _run('pointwise', 0.0, _lib.lib().kgan_interpolate, alpha.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, _stream())
+    _run('pointwise', 0.0, _lib.lib().kgan_interpolate, alpha.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(), n, x.numel() // n, _rnd(), _stream())
+    return out
+
+
+def round_tf32(x):
+    """x rounded to tf32 (no-op copy-free pass-through in fp32 mode): for tensors entering the tf32 path from outside the library."""
+    if _precision != PREC_TF32:
+        return x
+    _chk(x)
+    out = torch.empty_like(x)
+    _io(x, out)
+    _run('pointwise', 0.0, _lib.lib().kgan_round_tf32, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
