@@ -194,15 +194,18 @@ int kgan_label_split(const float* g, float* ge, float* gx, int n, int n_cls, int
 
 /* ---- BatchNorm2d, training mode (generator.py:142,160) ---------------------------------------------
  * stats: mean[c], rstd[c] from biased variance over (n, p); running stats updated in place with `momentum`
- * (unbiased variance), exactly nn.BatchNorm2d defaults.  running_* may be NULL. */
+ * (unbiased variance), exactly nn.BatchNorm2d defaults.  running_* may be NULL.
+ * `workspace`: kgan_bn_workspace(n, c) floats owned by the caller (per-chunk partial sums; they are added in a fixed order,
+ * so statistics and gradients are bit-reproducible - no atomics). */
+int64_t kgan_bn_workspace(int n, int c);
 int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean, float* running_var, int n, int c, int p,
-                  float eps, float momentum, void* stream);
+                  float eps, float momentum, float* workspace, void* stream);
 /* y = (x - mean[c]) * rstd[c] * gamma[c] + beta[c]  (also eval mode with running stats folded by the caller) */
 int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
                   int n, int c, int p, int out_tf32, void* stream);
 /* gx, ggamma[c], gbeta[c] of training-mode BN */
 int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx,
-                float* ggamma, float* gbeta, int n, int c, int p, int out_tf32, void* stream);
+                float* ggamma, float* gbeta, int n, int c, int p, int out_tf32, float* workspace, void* stream);
 
 /* ---- fused Adam over a flat parameter buffer (torch.optim.Adam, kinetic-gan.py:77-78,155,174) ----
  * g is multiplied by grad_scale first (1/world_size after the DDP sum all-reduce). `step` is 1-based. */

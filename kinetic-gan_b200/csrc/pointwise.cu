@@ -330,7 +330,10 @@ __global__ void __launch_bounds__(PT) label_split_k(const float* __restrict__ g,
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm2d (training).  Statistics: grid (sample chunks, channels) - every warp walks whole (n, c) planes of its channel with
-// 16-byte loads, the CTA's partial sums go to the per-channel accumulators with one atomic each, a one-CTA kernel finalises.
+// 16-byte loads, the CTA's partial sums go to a (chunk, channel) workspace and a small kernel adds the chunks IN ORDER (double):
+// the statistics - and with them everything downstream of the generator - are bit-reproducible from run to run.  (Round 1 merged
+// the CTAs with fp32 atomics: the summation order varied, and a 1e-7 wobble of a channel mean, amplified by |mean| / std and by
+// the tf32 rounding of the normalised activations, made two identical generator passes differ by 3e-4.)
 // Sums are taken around a per-channel shift (the channel's first element), so E[d^2] - E[d]^2 does not cancel.  (The first
 // version used ONE CTA per channel with a 64-bit division per element: 3 CTAs for the generator's 3-channel layers.)
 // Elementwise passes: one warp per (n, c) plane, per-plane constants, no per-element index arithmetic.
@@ -339,7 +342,7 @@ constexpr int BNW = PT / 32;      // warps per CTA
 
 template <bool BWD>
 __global__ void __launch_bounds__(PT) bn_partial_k(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ mean,
-                                                    const float* __restrict__ rstd, float* __restrict__ acc1, float* __restrict__ acc2, int n, int c,
+                                                    const float* __restrict__ rstd, float* __restrict__ part, int n, int c,
                                                     int p, int vec) {
     __shared__ float red[32];
     const int cc = blockIdx.y, lane = threadIdx.x & 31;
@@ -387,21 +390,42 @@ __global__ void __launch_bounds__(PT) bn_partial_k(const float* __restrict__ x, 
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) {
-        atomicAdd(acc1 + cc, s1);
-        atomicAdd(acc2 + cc, s2);
+    if (threadIdx.x == 0) {              // part[chunk][channel][2]
+        float* dst = part + ((int64_t)blockIdx.x * c + cc) * 2;
+        dst[0] = s1;
+        dst[1] = s2;
     }
 }
 
-// mean / rstd hold sum(d), sum(d^2) on entry (d = x - first element of the channel)
-__global__ void bn_finalize_k(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rm,
-                              float* __restrict__ rv, int n, int c, int p, float eps, float mom) {
+// out1[c] = sum_chunks part[chunk][c][0], out2[c] likewise: fixed order, double accumulation
+__global__ void bn_reduce_k(const float* __restrict__ part, int chunks, int c, float* __restrict__ out1, float* __restrict__ out2) {
     const int cc = blockIdx.x * blockDim.x + threadIdx.x;
     if (cc >= c) return;
-    const float cnt = (float)((int64_t)n * p);
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < chunks; ++s) {
+        a += (double)part[((int64_t)s * c + cc) * 2];
+        b += (double)part[((int64_t)s * c + cc) * 2 + 1];
+    }
+    out1[cc] = (float)a;
+    out2[cc] = (float)b;
+}
+
+// part holds per-chunk sum(d), sum(d^2) (d = x - first element of the channel): added in chunk order in double
+__global__ void bn_finalize_k(const float* __restrict__ x, const float* __restrict__ part, int chunks, float* __restrict__ mean,
+                              float* __restrict__ rstd, float* __restrict__ rm, float* __restrict__ rv, int n, int c, int p, float eps, float mom) {
+    const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= c) return;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < chunks; ++s) {
+        a += (double)part[((int64_t)s * c + cc) * 2];
+        b += (double)part[((int64_t)s * c + cc) * 2 + 1];
+    }
+    const double cntd = (double)((int64_t)n * p);
+    const float cnt = (float)cntd;
     const float sh = __ldg(x + (int64_t)cc * p);
-    const float m = mean[cc] / cnt;
-    const float var = fmaxf(rstd[cc] / cnt - m * m, 0.f);
+    const double md = a / cntd;
+    const float m = (float)md;
+    const float var = fmaxf((float)(b / cntd - md * md), 0.f);
     const float mu = sh + m;
     mean[cc] = mu;
     rstd[cc] = rsqrtf(var + eps);
@@ -574,15 +598,19 @@ extern "C" int kgan_label_split(const float* g, float* ge, float* gx, int n, int
     return check_launch("label_split");
 }
 
+extern "C" int64_t kgan_bn_workspace(int n, int c) {
+    if (n <= 0 || c <= 0 || c > 65535) return 0;
+    return (int64_t)bn_partial_grid(n, c).x * c * 2;
+}
+
 extern "C" int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean, float* running_var, int n, int c, int p, float eps,
-                             float momentum, void* stream) {
-    KGAN_REQUIRE(x && mean && rstd && n > 0 && c > 0 && p > 0, "bn_stats: bad argument");
+                             float momentum, float* workspace, void* stream) {
+    KGAN_REQUIRE(x && mean && rstd && workspace && n > 0 && c > 0 && p > 0, "bn_stats: bad argument");
     KGAN_REQUIRE(c <= 65535, "bn_stats: too many channels");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(mean, 0, sizeof(float) * c, s) != cudaSuccess || cudaMemsetAsync(rstd, 0, sizeof(float) * c, s) != cudaSuccess)
-        return check_launch("bn_stats memset");
-    bn_partial_k<false><<<bn_partial_grid(n, c), PT, 0, s>>>(x, nullptr, nullptr, nullptr, mean, rstd, n, c, p, bn_vec_ok(p, x, nullptr, nullptr));
-    bn_finalize_k<<<ceil_div(c, 128), 128, 0, s>>>(x, mean, rstd, running_mean, running_var, n, c, p, eps, momentum);
+    const dim3 grid = bn_partial_grid(n, c);
+    bn_partial_k<false><<<grid, PT, 0, s>>>(x, nullptr, nullptr, nullptr, workspace, n, c, p, bn_vec_ok(p, x, nullptr, nullptr));
+    bn_finalize_k<<<ceil_div(c, 128), 128, 0, s>>>(x, workspace, (int)grid.x, mean, rstd, running_mean, running_var, n, c, p, eps, momentum);
     return check_launch("bn_stats");
 }
 
@@ -595,14 +623,14 @@ extern "C" int kgan_bn_apply(const float* x, const float* mean, const float* rst
 }
 
 extern "C" int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx, float* ggamma,
-                           float* gbeta, int n, int c, int p, int out_tf32, void* stream) {
-    KGAN_REQUIRE(gy && x && mean && rstd && gamma && gx && ggamma && gbeta && n > 0 && c > 0 && p > 0, "bn_bwd: bad argument");
+                           float* gbeta, int n, int c, int p, int out_tf32, float* workspace, void* stream) {
+    KGAN_REQUIRE(gy && x && mean && rstd && gamma && gx && ggamma && gbeta && workspace && n > 0 && c > 0 && p > 0, "bn_bwd: bad argument");
     KGAN_REQUIRE(c <= 65535, "bn_bwd: too many channels");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(ggamma, 0, sizeof(float) * c, s) != cudaSuccess || cudaMemsetAsync(gbeta, 0, sizeof(float) * c, s) != cudaSuccess)
-        return check_launch("bn_bwd memset");
     const int vec = bn_vec_ok(p, x, gy, gx);
-    bn_partial_k<true><<<bn_partial_grid(n, c), PT, 0, s>>>(x, gy, mean, rstd, gbeta, ggamma, n, c, p, vec);
+    const dim3 grid = bn_partial_grid(n, c);
+    bn_partial_k<true><<<grid, PT, 0, s>>>(x, gy, mean, rstd, workspace, n, c, p, vec);
+    bn_reduce_k<<<ceil_div(c, 128), 128, 0, s>>>(workspace, (int)grid.x, c, gbeta, ggamma);
     bn_elem_k<1><<<grid_for((int64_t)n * c, BNW, 8), PT, 0, s>>>(x, gy, mean, rstd, gamma, nullptr, gbeta, ggamma, gx, n, c, p, vec, out_tf32);
     return check_launch("bn_bwd");
 }

@@ -354,9 +354,10 @@ def bn_stats(x, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
     n, c, t, v = x.shape
     mean = torch.empty((c,), device=x.device, dtype=torch.float32)
     rstd = torch.empty((c,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((int(_lib.lib().kgan_bn_workspace(n, c)),), device=x.device, dtype=torch.float32)
     _io(x)
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_stats, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), n, c, t * v,
-                                        eps, momentum, _stream())
+                                        eps, momentum, ws.data_ptr(), _stream())
     return mean, rstd
 
 
@@ -376,9 +377,10 @@ def bn_bwd(gy, x, mean, rstd, gamma):
     gx = torch.empty_like(x)
     gg = torch.empty((c,), device=x.device, dtype=torch.float32)
     gb = torch.empty((c,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((int(_lib.lib().kgan_bn_workspace(n, c)),), device=x.device, dtype=torch.float32)
     _io(gy, x, gy, x, gx)          # two passes over (gy, x): sums, then the elementwise pass
     _run('batchnorm', 0.0, _lib.lib().kgan_bn_bwd, gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), gx.data_ptr(),
-                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _rnd(), _stream())
+                                      gg.data_ptr(), gb.data_ptr(), n, c, t * v, _rnd(), ws.data_ptr(), _stream())
     return gx, gg, gb
 
 

@@ -273,8 +273,9 @@ def generator_forward(p, z, labels, cfg, tables, noises, training=True, state_ou
     return x
 
 
-def d_block(x, A_eff, p, prefix, spec, tables):
-    """discriminator.py:125-142."""
+def d_block(x, A_eff, p, prefix, spec, tables, mask=None):
+    """discriminator.py:125-142.  `mask` (checker-only, never set by the reference path): the LeakyReLU slopes (1 / 0.2 per
+    element) to apply INSTEAD of deriving them from the sign of this block's own pre-activation - see discriminator_forward."""
     ci, co, lvl, res, dw_s, dw_t = spec
     if not res:
         r = 0
@@ -288,28 +289,32 @@ def d_block(x, A_eff, p, prefix, spec, tables):
         keep = torch.as_tensor(tables.map[lvl + 1][:, 1], dtype=torch.long)
         y = y[:, :, :, keep]
     y = nearest_t(y, dw_t)
-    return F.leaky_relu(y, 0.2)
+    return F.leaky_relu(y, 0.2) if mask is None else y * mask
 
 
-def discriminator_forward(p, x, labels, cfg, tables, collect=None):
-    """discriminator.py:52-74."""
+def discriminator_forward(p, x, labels, cfg, tables, collect=None, masks=None):
+    """discriminator.py:52-74.
+    `masks` (checker-only): one tensor of LeakyReLU slopes per block, taken from ANOTHER evaluation of the same network (the CUDA
+    path's).  The critic is piecewise linear; with the activation pattern pinned, its gradients are compared arithmetic against
+    arithmetic - otherwise every pre-activation within the forward error of zero flips its slope between 1 and 0.2 and the gradient
+    rel-L2 is ~0.8 * sqrt(fraction flipped), which measures the conditioning of LeakyReLU at zero, not the kernels."""
     N, C, T, V = x.size()
     c = p["label_emb.weight"][labels]
     c = c.view(N, -1, 1, 1).repeat(1, 1, T, V)
     x = torch.cat((c, x), 1)
     for i, spec in enumerate(d_block_table(cfg)):
         A_eff = torch.as_tensor(tables.As[spec[2]], dtype=x.dtype) * p["edge_importance.%d" % i]
-        x = d_block(x, A_eff, p, "st_gcn_networks.%d." % i, spec, tables)
+        x = d_block(x, A_eff, p, "st_gcn_networks.%d." % i, spec, tables, None if masks is None else masks[i])
         if collect is not None:
             collect.append(x)
     x = F.avg_pool2d(x, x.size()[2:]).view(N, -1)
     return F.linear(x, p["fcn.weight"], p["fcn.bias"])
 
 
-def gradient_penalty(pd, real, fake, labels, alpha, cfg, tables, return_grad=False):
-    """kinetic-gan.py:94-114 with alpha (N,1,1,1) supplied by the caller (host RNG at :97)."""
+def gradient_penalty(pd, real, fake, labels, alpha, cfg, tables, return_grad=False, masks=None):
+    """kinetic-gan.py:94-114 with alpha (N,1,1,1) supplied by the caller (host RNG at :97).  `masks`: see discriminator_forward."""
     inter = (alpha * real + (1 - alpha) * fake).requires_grad_(True)
-    d_inter = discriminator_forward(pd, inter, labels, cfg, tables)
+    d_inter = discriminator_forward(pd, inter, labels, cfg, tables, masks=masks)
     ones = torch.ones_like(d_inter)
     (grads,) = torch.autograd.grad(d_inter, inter, ones, create_graph=True, retain_graph=True, only_inputs=True)
     flat = grads.reshape(grads.size(0), -1)

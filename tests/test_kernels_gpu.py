@@ -161,7 +161,7 @@ def test_adam():
 def test_errors_are_reported_not_thrown():
     _lib = __import__("importlib").import_module("kinetic-gan_b200._lib")
     lib = _lib.lib()
-    assert lib.kgan_adjmix_fwd(0, 0, 0, 1, 1, 1, 1, 1, 1, 0) != 0
+    assert lib.kgan_adjmix_fwd(0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0) != 0
     assert b"null" in lib.kgan_last_error()
 
 
