@@ -83,7 +83,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="kgan", choices=["kgan", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "generate"],
+    ap.add_argument("--workload", default="train", choices=["train", "generate", "tf32-deviation"],
                     help="train: WGAN-GP training samples/s (headline); generate: inference-only generated sequences/s (BASELINE.json configs[4])")
     ap.add_argument("--shape", default="ntu120", choices=list(SHAPES), help="network / data shape (BASELINE.json configs); headline: ntu120")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 1024 for train, 4096 for generate)")
@@ -94,6 +94,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-secondary", action="store_true", help="train workload: skip the generate-workload measurement attached as `secondary`")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the `gpu_reference` leg (unmodified reference, torch eager, same GPU)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: where the unmodified reference runs (the arm the "
+                    "driver launches is the default, cpu; cuda is what the `gpu_reference` leg calls)")
+    ap.add_argument("--ref-tf32", type=int, default=0, help="--impl reference --ref-device cuda: torch.backends.*.allow_tf32")
+    ap.add_argument("--first-index", type=int, default=0, help="--impl reference: batch index of the first timed iteration (n_critic phase)")
     return ap.parse_args()
 
 
@@ -192,24 +198,86 @@ def time_oracle(batch, steps, warmup, first_index):
     return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def reference_kind():
+    from oracle import ref_runner
+
+    return "reference" if ref_runner.available() else "port"
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path (oracle port: same torch CPU operators in the reference's order,
-    including its per-sample mapping loop) on the host cores; each step = one iteration on a bounded batch."""
+    """`--impl reference`: the reference's own implementation of the path on the box's host cores - the UNMODIFIED reference
+    modules from baseline/_ref (oracle/ref_runner.py: `kind: "reference"`), all host threads, each step one iteration of the
+    loop body kinetic-gan.py:137-174 on a bounded batch (`--cpu-batch`, the reference's default 32).  Falls back to the oracle
+    port (`kind: "port"`) only if the install is absent.  `--ref-device cuda` runs the same unmodified code in torch eager on the
+    GPU (the `gpu_reference` leg of the kgan arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = args.cpu_batch
-    sps, ms, cores = time_oracle(b, args.steps, args.warmup, first_index=0)
+    from oracle import ref_runner
+
+    kind = reference_kind()
+    on_gpu = args.ref_device == "cuda"
+    b = args.batch if (on_gpu and args.batch) else args.cpu_batch
+    if kind == "reference":
+        sps, ms, who = ref_runner.time_training(SHAPE, b, args.steps, args.warmup, device=args.ref_device, tf32=bool(args.ref_tf32),
+                                                first_index=args.first_index)
+    else:
+        assert not on_gpu, "the GPU leg needs the installed reference (baseline/_ref)"
+        sps, ms, who = time_oracle(b, args.steps, args.warmup, first_index=args.first_index)
+    what = ("unmodified reference modules (baseline/_ref), torch %s" % ("eager on " + str(who) if on_gpu else "CPU operators") if kind == "reference"
+            else "CPU port of the reference step (oracle/networks.py)")
     line = {
         "impl": "reference", "metric": "wgan_gp_train_samples_per_s", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": b, "note": "CPU port of the reference step (oracle/networks.py), host cores only"},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+        "vs_baseline": None, "dtype": ("tf32" if args.ref_tf32 else "fp32") if on_gpu else "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": b, "device": args.ref_device, "note": what + (", host cores only" if not on_gpu else "")},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": who if not on_gpu else 0, "kind": kind,
                          "sample": "%d iterations of batch %d (%s) after %d warm-up" % (args.steps, b, SHAPE["name"], args.warmup)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
+
+
+def sub_bench(extra, timeout=900):
+    """Runs `bench.py <extra>` in a fresh process (own CUDA context / torch thread pool, global monkey-patches of the import shim
+    stay out of this process) and returns its JSON line, or {"error": ...}."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "KGAN_NCU_RANGE", "KGAN_SITES_OUT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + extra, capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr.strip().splitlines() or ["rc=%d" % r.returncode])[-1][:300]}
+        return json.loads(lines[-1])
+    except Exception as e:          # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def cpu_baseline_leg(workload, shape_key, cpu_batch, trunc=None):
+    """`cpu_baseline`: the reference arm on the host cores, bounded sample (training: one n_critic cycle i = 5..9 after i = 4 at
+    batch 32; generate: 2 calls of batch 256)."""
+    if workload == "train":
+        j = sub_bench(["--impl", "reference", "--shape", shape_key, "--steps", "5", "--warmup", "1", "--first-index", "4", "--cpu-batch", str(cpu_batch)])
+    else:
+        j = sub_bench(["--impl", "reference", "--workload", "generate", "--shape", shape_key, "--steps", "2", "--warmup", "1", "--cpu-batch", str(cpu_batch)]
+                      + (["--trunc", str(trunc)] if trunc is not None else []))
+    return j.get("cpu_baseline", j)
+
+
+def gpu_reference_leg(workload, shape_key, batch):
+    """`gpu_reference`: the UNMODIFIED reference in torch eager (cuDNN / cuBLAS) on the same B200, same per-GPU batch, exact fp32 and
+    with TF32 tensor cores allowed; for training also what TF32 does to the reference's own critic gradients."""
+    out = {"what": "unmodified reference modules (baseline/_ref) driven by oracle/ref_runner.py, torch eager, 1 GPU, batch %d" % batch}
+    for name, tf32 in (("fp32", 0), ("tf32", 1)):
+        extra = ["--impl", "reference", "--ref-device", "cuda", "--ref-tf32", str(tf32), "--shape", shape_key, "--batch", str(batch),
+                 "--workload", workload, "--steps", "5" if workload == "train" else "3", "--warmup", "1", "--first-index", "4"]
+        j = sub_bench(extra)
+        out[name] = {k: j[k] for k in ("value", "unit", "ms_per_step", "error") if k in j}
+    if workload == "train":
+        j = sub_bench(["--impl", "reference", "--ref-device", "cuda", "--workload", "tf32-deviation", "--shape", shape_key])
+        out["tf32_deviation"] = j
+    return out
 
 
 def make_roofline(fam, sites, passes, step_tflops):
@@ -249,6 +317,11 @@ def make_roofline(fam, sites, passes, step_tflops):
                         "us_per_launch": round(v["ms"] / v["n"] * 1e3, 1),
                         "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] else None}
                        for k, v in sorted(sites.items(), key=lambda kv: -kv[1]["ms"])[:40]]}
+    if os.environ.get("KGAN_SITES_OUT"):          # full per-site table (diagnostics; not part of the JSON line)
+        with open(os.environ["KGAN_SITES_OUT"] + (".generate" if "generate" in TRAFFIC_FILE else ".train"), "w") as f:
+            json.dump({k: {"ms_per_step": v["ms"] / passes, "n_per_step": v["n"] / passes, "us": v["ms"] / v["n"] * 1e3,
+                           "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else None,
+                           "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else None} for k, v in sites.items()}, f, indent=0)
     if ai < ridge:
         r.update(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak)
     else:
@@ -365,11 +438,26 @@ def run_kgan(args):
     it += 5
     roofline = make_roofline(fam, sites, 5, FLOP_PER_SAMPLE * value / 1e12 / comm.world_size)
 
-    cpu = None
-    if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
-        sps, ms, cores = time_oracle(args.cpu_batch, 5, 1, first_index=4)     # one n_critic cycle: i = 5..9 after i = 4
-        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "one n_critic cycle (5 iterations, 1 G step) of batch %d, %s, after 1 warm-up" % (args.cpu_batch, SHAPE["name"])}
+    # release the training state before the other legs (the generate measurement and the reference on the same GPU need the memory)
+    del tr, G, D, resident
+    kgan.ops._persist.clear()
+    kgan.ops._batches.clear()
+    kgan.ops.clear_temporary_packs()
+    torch.cuda.empty_cache()
+
+    secondary = None
+    if not args.no_secondary:                   # the metric's second half (BASELINE.json configs[4]): generated sequences / s, batch 4096 per GPU
+        ga = argparse.Namespace(**vars(args))
+        ga.batch, ga.trunc, ga.trunc_cached = 4096, None, False
+        secondary = measure_generate(ga, comm, dev)
+        torch.cuda.empty_cache()
+
+    cpu = gpu_ref = None
+    if comm.rank == 0 and comm.world_size == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_leg("train", args.shape, args.cpu_batch)
+        if not args.no_gpu_reference and reference_kind() == "reference":
+            gpu_ref = gpu_reference_leg("train", args.shape, B)
 
     if comm.rank == 0:
         line = {
@@ -382,6 +470,7 @@ def run_kgan(args):
                        "l2_policy": "per-step working set (activations of 4 critic passes at batch %d, >1 GB) exceeds the 126 MB L2; "
                                     "inputs rotate over a pool of %d batches" % (B, POOL)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_reference": gpu_ref, "secondary": secondary,
         }
         emit(json.dumps(line))
     comm.close()
@@ -422,35 +511,70 @@ def time_oracle_generate(batch, steps, warmup, trunc=None):
 
 
 def run_reference_generate(args):
+    """`--impl reference --workload generate`: generate.py:93 `generator(z, labels)` of the UNMODIFIED reference (eval mode, its
+    per-sample mapping loop, no no_grad - as generate.py runs it), host cores by default."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    b = args.cpu_batch * 8
-    sps, ms, cores = time_oracle_generate(b, args.steps, args.warmup, args.trunc)
+    from oracle import ref_runner
+
+    kind = reference_kind()
+    on_gpu = args.ref_device == "cuda"
+    b = args.batch if on_gpu else args.cpu_batch * 8
+    if kind == "reference" and args.trunc is None:
+        sps, ms, who = ref_runner.time_generate(SHAPE, b, args.steps, args.warmup, device=args.ref_device, tf32=bool(args.ref_tf32))
+    else:                                       # W-space truncation draws on torch.cuda.FloatTensor in the reference (generator.py:98): port
+        kind = "port"
+        sps, ms, who = time_oracle_generate(b, args.steps, args.warmup, args.trunc)
     emit(json.dumps({
         "impl": "reference", "metric": "generated_sequences_per_s", "value": sps, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-        "data": "synthetic", "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": b, "trunc": args.trunc,
-                                        "note": "CPU port of the reference generator call (oracle/networks.py), host cores only"},
-        "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ("tf32" if args.ref_tf32 else "fp32") if on_gpu else "fp32",
+        "data": "synthetic", "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": b, "trunc": args.trunc, "device": args.ref_device,
+                                        "note": ("unmodified reference generator (baseline/_ref)" if kind == "reference" else
+                                                 "CPU port of the reference generator call (oracle/networks.py)") + ("" if on_gpu else ", host cores only")},
+        "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": who if not on_gpu else 0, "kind": kind,
                          "sample": "%d generator calls of batch %d after %d warm-up" % (args.steps, b, args.warmup)},
         "e2e": {"value": sps, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_tf32_deviation(args):
+    from oracle import ref_runner
+
+    emit(json.dumps(ref_runner.tf32_gradient_deviation(SHAPE)))
+
+
 def run_generate(args):
+    import torch
+
+    import kgan_b200 as kgan
+    from importlib import import_module
+
+    ddp = import_module("kinetic-gan_b200.ddp")
+    comm = ddp.Comm()
+    dev = torch.device("cuda", comm.local_rank)
+    torch.cuda.set_device(dev)
+    kgan.set_precision(args.precision)
+    line = measure_generate(args, comm, dev)
+    if comm.rank == 0 and comm.world_size == 1:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg("generate", args.shape, args.cpu_batch, args.trunc)
+        if not args.no_gpu_reference and reference_kind() == "reference" and args.trunc is None:
+            line["gpu_reference"] = gpu_reference_leg("generate", args.shape, args.batch)
+    if comm.rank == 0:
+        emit(json.dumps(line))
+    comm.close()
+
+
+def measure_generate(args, comm, dev):
     """BASELINE.json configs[4]: inference-only generator throughput, NTU 25x64x3, batch 4096 per GPU; independent replicas
-    (no collective)."""
+    (no collective).  -> the JSON line as a dict (every rank measures; the times are max-reduced)."""
     import torch
 
     import kgan_b200 as kgan
     from importlib import import_module
 
     gen = import_module("kinetic-gan_b200.generate")
-    ddp = import_module("kinetic-gan_b200.ddp")
     ops = kgan.ops
-    comm = ddp.Comm()
-    dev = torch.device("cuda", comm.local_rank)
-    torch.cuda.set_device(dev)
-    kgan.set_precision(args.precision)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
     G = kgan.Generator(512, SHAPE["channels"], SHAPE["n_classes"], SHAPE["t_size"], mlp_dim=SHAPE["mlp_dim"], dataset=SHAPE["dataset"]).to(dev)
@@ -528,20 +652,18 @@ def run_generate(args):
     # lower bound of the whole pass: z + output (+ noise) = ~21 KB of compulsory HBM traffic per sequence
     roofline["pass_hbm_floor_frac"] = (value / comm.world_size) * 21.2e3 / (peaks()[1] * 1e9)
 
-    cpu = None
-    if comm.rank == 0 and comm.world_size == 1 and not args.no_cpu_baseline:
-        sps, ms, cores = time_oracle_generate(args.cpu_batch * 8, 2, 1, args.trunc)
-        cpu = {"value": sps, "unit": "seq/s", "cores": cores, "kind": "port",
-               "sample": "2 generator calls of batch %d (%s, per-sample mapping loop as generator.py:84-85) after 1 warm-up" % (args.cpu_batch * 8, SHAPE["name"])}
-    if comm.rank == 0:
-        emit(json.dumps({
+    del runner, G
+    ops._persist.clear()
+    ops._batches.clear()
+    ops.clear_temporary_packs()
+    if True:
+        return ({
             "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size, "parallelism": "replicas%d" % comm.world_size,
                        "trunc": args.trunc, "trunc_mean_cached": bool(args.trunc_cached), "flop_per_sequence": F_G, "cuda_graphs": not args.no_graphs,
                        "l2_policy": "inputs rotate over a pool of %d batches; the activations of one pass at batch %d exceed the 126 MB L2" % (POOL, B)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
-    comm.close()
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None})
 
 
 if __name__ == "__main__":
@@ -551,7 +673,9 @@ if __name__ == "__main__":
     if a.batch is None:
         a.batch = 1024 if a.workload == "train" else 4096
     TRAFFIC_BATCH, TRAFFIC_SHAPE = a.batch, a.shape
-    if a.workload == "generate":
+    if a.workload == "tf32-deviation":
+        run_tf32_deviation(a)
+    elif a.workload == "generate":
         run_reference_generate(a) if a.impl == "reference" else run_generate(a)
     elif a.impl == "reference":
         run_reference(a)

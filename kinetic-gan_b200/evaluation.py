@@ -14,7 +14,10 @@ What the reference computes, including its quirks, is kept (published numbers co
 
 `MMD` keeps the reference's class surface (mode, rkhs_mmd, compute_sequence_mmd) on top of the same batched kernel;
 `first_per_class` is the selection loop of mmd-actions.py:136-164; `main` the script (same options).
-FID (evaluation/fid-actions.py) needs the third-party pretrained Inception network of `pytorch_fid` and stays out of scope.
+FID (evaluation/fid-actions.py): the feature extractor is the third-party pretrained Inception network of `pytorch_fid` (no
+weights in this image, no network) and stays out of scope; what the reference itself computes on top of the features - mean /
+covariance (:160-183) and the Frechet distance between the two Gaussians (:106-157) - is here as `activation_statistics` and
+`frechet_distance`, on the device.
 """
 import argparse
 import os
@@ -96,17 +99,54 @@ def calculate_mmd(gen, real, label, mode='avg', device=None, bandwidths=BANDWIDT
 
 def first_per_class(dataset, classes, per_class=100, t_size=64):
     """The selection loops of mmd-actions.py:136-164: walking the dataset from the start, class after class, the first
-    `per_class` items of each class, cropped to `t_size` frames.  -> (actions (n, C, t, V), labels (n,))."""
+    `per_class` items of each class, cropped to `t_size` frames.  -> (actions (n, C, t, V), labels (n,)).
+    Quirk kept: when a class is complete the reference resets `i = 0` and then still executes the loop's `i += 1` (:147-149), so
+    every class after the first is scanned from dataset item 1 - item 0 can only ever be selected for the first class."""
     labels = np.asarray(dataset.label)
     actions, out_labels = [], []
-    for c in classes:
-        idx = np.nonzero(labels == c)[0][:per_class]
+    for k, c in enumerate(classes):
+        idx = np.nonzero(labels == c)[0]
+        if k > 0:
+            idx = idx[idx >= 1]
+        idx = idx[:per_class]
         if len(idx) < per_class:
             raise IndexError("class %d has only %d of the %d samples asked for" % (c, len(idx), per_class))
         for i in idx:
             actions.append(dataset[int(i)][0][:, :t_size, :])
             out_labels.append(int(c))
     return np.asarray(actions), np.asarray(out_labels)
+
+
+def activation_statistics(features, device=None):
+    """fid-actions.py:160-183 after the feature extraction: mu = mean over samples, sigma = np.cov(features, rowvar=False)
+    (unbiased), as float64 tensors on the device; the covariance is one GEMM."""
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    f = torch.as_tensor(np.asarray(features) if not torch.is_tensor(features) else features, dtype=torch.float64, device=dev)
+    mu = f.mean(0)
+    d = f - mu
+    return mu, d.t() @ d / (f.shape[0] - 1)
+
+
+def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """fid-actions.py:106-157: d^2 = |mu1 - mu2|^2 + Tr(S1) + Tr(S2) - 2 Tr(sqrt(S1 S2)), evaluated on the device in float64.
+    The reference takes scipy's Schur-based `sqrtm` of the (non-symmetric) product on the host.  Here Tr(sqrt(S1 S2)) is the sum
+    of the square roots of the eigenvalues of S1 S2, which are those of the SYMMETRIC matrix S1^(1/2) S2 S1^(1/2): two `eigh`
+    calls and two GEMMs, no complex arithmetic, and rank-deficient covariances (fewer samples than the 2048 feature dimensions -
+    the case in which the reference falls back to adding `eps` to the diagonals, :139-144) need no special path: eigenvalues that
+    come out slightly negative from rounding are clamped to zero.  Accepts numpy arrays or tensors; returns a Python float."""
+    dev = sigma1.device if torch.is_tensor(sigma1) else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    t = lambda a: torch.atleast_1d(torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, dtype=torch.float64, device=dev))
+    mu1, mu2 = t(mu1), t(mu2)
+    s1, s2 = torch.atleast_2d(t(sigma1)), torch.atleast_2d(t(sigma2))
+    assert mu1.shape == mu2.shape, 'Training and test mean vectors have different lengths'
+    assert s1.shape == s2.shape, 'Training and test covariances have different dimensions'
+    w, q = torch.linalg.eigh((s1 + s1.t()) / 2)
+    root1 = (q * w.clamp_min(0).sqrt()) @ q.t()                       # S1^(1/2)
+    m = root1 @ s2 @ root1
+    tr_covmean = torch.linalg.eigvalsh((m + m.t()) / 2).clamp_min(0).sqrt().sum()
+    diff = mu1 - mu2
+    (_,) = (eps,)                                                      # kept in the signature for drop-in calls; not needed by this evaluation
+    return float(diff.dot(diff) + torch.trace(s1) + torch.trace(s2) - 2 * tr_covmean)
 
 
 def build_parser():

@@ -157,45 +157,52 @@ class TapConvEp(Function):
 # adjacency product family
 # ------------------------------------------------------------------------------------------------
 class AdjMix(Function):
+    """`support` (optional constant (K, V, W) tensor, not differentiated): the entries of A that can be non-zero for EVERY value
+    of the parameters behind A - the st_gcn blocks pass the skeleton's base adjacency (`A_eff = A_base * edge_importance`:
+    d loss / d edge_importance = gA * A_base, so gA is only ever read where A_base != 0).  The adjacency gradient is then
+    evaluated on that support only (a few dozen dot products instead of K*V*W).  None (the default of a standalone
+    ConvTemporalGraphical call with an arbitrary, possibly dense and learnable A): every entry of gA is computed."""
+
     @staticmethod
-    def forward(ctx, x, A):
+    def forward(ctx, x, A, support=None):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, A)
+        ctx.support = support
         return ops.adjmix_fwd(_c(x), _c(A))
 
     @staticmethod
     def backward(ctx, go):
         if go is None:
-            return None, None
+            return None, None, None
         x, A = ctx.saved_tensors
         go = _c(go)
-        gx = AdjMixDx.apply(go, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(x, go, A.shape[0], A) if _want(ctx, 1) else None
-        return gx, gA
+        gx = AdjMixDx.apply(go, A, ctx.support) if ctx.needs_input_grad[0] else None
+        gA = AdjMixDA.apply(x, go, A.shape[0], ctx.support) if _want(ctx, 1) else None
+        return gx, gA, None
 
 
 class AdjMixDx(Function):
     @staticmethod
-    def forward(ctx, g, A):
+    def forward(ctx, g, A, support=None):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, A)
+        ctx.support = support
         return ops.adjmix_bwd_x(_c(g), _c(A))
 
     @staticmethod
     def backward(ctx, h):
         if h is None:
-            return None, None
+            return None, None, None
         g, A = ctx.saved_tensors
         h = _c(h)
-        gg = AdjMix.apply(h, A) if ctx.needs_input_grad[0] else None
-        gA = AdjMixDA.apply(h, g, A.shape[0], A) if _want(ctx, 1) else None
-        return gg, gA
+        gg = AdjMix.apply(h, A, ctx.support) if ctx.needs_input_grad[0] else None
+        gA = AdjMixDA.apply(h, g, A.shape[0], ctx.support) if _want(ctx, 1) else None
+        return gg, gA, None
 
 
 class AdjMixDA(Function):
-    """gA = dM/dA^T g, evaluated on the support of `support` only (the adjacency the product was taken with: its gradient
-    reaches edge_importance through `A * importance`, i.e. multiplied by A, so entries where A == 0 are never used - and a
-    cotangent hA of this output is zero there for the same reason).  `support` is used as a mask, not differentiated."""
+    """gA = dM/dA^T g, evaluated on the non-zeros of the constant mask `support` only (see AdjMix; entries outside it are
+    returned as 0 and a cotangent hA of this output is never read there); support None: all entries."""
 
     @staticmethod
     def forward(ctx, x, g, k, support=None):

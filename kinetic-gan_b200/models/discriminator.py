@@ -142,7 +142,12 @@ class st_gcn(nn.Module):
             cols = torch.tensor(v_keep + [V] * (Wp - W), dtype=torch.long, device=device)
             rows = torch.tensor(list(range(V)) + [V] * (Vx - V), dtype=torch.long, device=device)
             amap = None if (W == V and Wp == V and Vx == V) else (rows, cols)
-            p = self._plans[key] = (tcn, res, sel, amap)
+            # constant support of the adjacency this block multiplies with (base skeleton adjacency, same row / column selection):
+            # d loss / d edge_importance = gA * A_base, so the adjacency gradient is only evaluated where A_base != 0
+            base = torch.tensor(self.graph.As[self.lvl] != 0, dtype=torch.float32, device=device)
+            if amap is not None:
+                base = torch.nn.functional.pad(base, (0, 1, 0, 1)).index_select(1, rows).index_select(2, cols)
+            p = self._plans[key] = (tcn, res, sel, amap, base.contiguous())
         return p
 
     def forward(self, x, A, label_emb=None, pad_joints=False):
@@ -153,15 +158,15 @@ class st_gcn(nn.Module):
         graph's V and the output may be padded likewise - see PAD_JOINTS above."""
         V = A.size(1)
         assert x.size(3) >= V and (pad_joints or x.size(3) == V)
-        tcn, res, sel, amap = self._plan(x.size(2), V, x.size(3), pad_joints, x.device)
+        tcn, res, sel, amap, support = self._plan(x.size(2), V, x.size(3), pad_joints, x.device)
         A_in = A
         if amap is not None:
             A = torch.nn.functional.pad(A, (0, 1, 0, 1)).index_select(1, amap[0]).index_select(2, amap[1])
         if label_emb is not None:
             assert self._res == "none"
-            g, _ = self.gcn.forward_with_labels(x, A, label_emb)
+            g, _ = self.gcn.forward_with_labels(x, A, label_emb, support)
         else:
-            g, _ = self.gcn(x, A)
+            g, _ = self.gcn(x, A, support)
         if self._res == "none":
             r = None
         elif self._res == "identity":

@@ -186,6 +186,13 @@ class st_gcn(nn.Module):
             p = self._plans[(T, V)] = (up, tcn, res)
         return p
 
+    def _support(self, device):
+        """Constant support of this block's adjacency (functional.AdjMix): the base skeleton adjacency of its level."""
+        s = self._plans.get(("support", str(device)))
+        if s is None:
+            s = self._plans[("support", str(device))] = torch.tensor(self.graph.As[self.lvl] != 0, dtype=torch.float32, device=device)
+        return s
+
     def _batch_norm(self, bn, x):
         if bn.training:
             if bn.num_batches_tracked is not None:
@@ -206,7 +213,7 @@ class st_gcn(nn.Module):
         else:
             r = KF.TapConvEp.apply(x, self.residual[0].weight, self.residual[0].bias, None, res, KF.ACT_NONE)
             r = self._batch_norm(self.residual[1], r)
-        g, A = self.gcn(x, A)
+        g, A = self.gcn(x, A, self._support(x.device))
         if "tcn" in fold:
             z = KF.TapConvEp.apply(g, fold["tcn"][0], fold["tcn"][1], None, tcn, KF.ACT_NONE)
         else:

@@ -43,7 +43,7 @@ class ConvTemporalGraphical(nn.Module):
             self._geoms[key] = g
         return g
 
-    def forward_with_labels(self, x, A, label_emb):
+    def forward_with_labels(self, x, A, label_emb, support=None):
         """The critic's first layer (discriminator.py:57-64) without the label planes: the input of the reference is
         cat(label_emb tiled over (T, V), x).  The tiled channels are constant over (t, v), so their share of the output is
             L[n, c, w] = sum_k (W[kC+c, :n_cls] . e[n]) * sum_v A[k, v, w]
@@ -54,8 +54,8 @@ class ConvTemporalGraphical(nn.Module):
         g_lab, g_dat = self._label_geoms(n_lab, x.size(1), x.size(2), A.size(2))
         b = KF.TapConv.apply(label_emb.reshape(n, n_lab, 1, 1), self.conv.weight, g_lab)      # (N, K*C_out, 1, 1)
         b = b.view(n, K, -1).transpose(1, 2).reshape(n, -1, 1, K)                             # (N, C_out, 1, K)
-        L = KF.AdjMix.apply(b, A.sum(1).unsqueeze(0))                                         # (N, C_out, 1, W)
-        xa = KF.AdjMix.apply(x, A)
+        L = KF.AdjMix.apply(b, A.sum(1).unsqueeze(0))                                         # (N, C_out, 1, W); dense adjacency gradient (K*W entries)
+        xa = KF.AdjMix.apply(x, A, support)
         out = KF.TapConvEp.apply(xa, self.conv.weight, None, L, g_dat, KF.ACT_NONE)
         return out, A
 
@@ -67,7 +67,10 @@ class ConvTemporalGraphical(nn.Module):
             g = self._geoms[key] = TapConvGeom(self.conv.in_channels, self.conv.out_channels, t, v, kt=kt, pad=pad, stride=st, dil=dil)
         return g
 
-    def forward(self, x, A):
+    def forward(self, x, A, support=None):
+        """`support` (optional, not in the reference): constant mask of the entries of A that can ever be non-zero (the base
+        adjacency behind `A_base * edge_importance`); the adjacency gradient is then evaluated there only.  Without it - the
+        reference's signature, any dense / learnable A - every entry of dA is computed (functional.AdjMix)."""
         assert A.size(0) == self.kernel_size
         c_in, c_out = self.conv.in_channels, self.conv.out_channels // self.kernel_size
         # Both evaluation orders of tgcn.py:61-66 are the same bilinear map; they differ in the intermediate that crosses HBM:
@@ -76,9 +79,9 @@ class ConvTemporalGraphical(nn.Module):
         if c_out * A.size(1) < c_in * A.size(2) and self._t == (1, 1, 0, 1):
             y = KF.TapConv.apply(x, self.conv.weight, self._conv_first_geom(x.size(2), x.size(3)))      # (N, K*C_out, T, V)
             # out[c, t, w] = sum_k sum_v y[k*C + c, t, v] A[k, v, w]: the adjoint-product member of the adjacency family
-            out = KF.AdjMixDx.apply(y, A.transpose(1, 2))
+            out = KF.AdjMixDx.apply(y, A.transpose(1, 2), None if support is None else support.transpose(1, 2))
             return self._with_bias(out, A), A
-        xa = KF.AdjMix.apply(x, A)                                  # (N, K*C_in, T, W)
+        xa = KF.AdjMix.apply(x, A, support)                         # (N, K*C_in, T, W)
         out = KF.TapConv.apply(xa, self.conv.weight, self._geom(x.size(2), A.size(2)))
         return self._with_bias(out, A), A
 

@@ -131,3 +131,78 @@ def test_first_per_class_and_script(tmp_path):
     onehot = np.eye(n_cls)[labels[sel]]
     want, _ = ref_calculate(fake[sel][:, :, :16].transpose(0, 3, 2, 1).astype(np.float64), realn[sel][:, :, :16].transpose(0, 3, 2, 1).astype(np.float64), onehot, "avg")
     assert abs(res - want) < 5e-4
+
+
+# ---- against the reference's OWN code (tests/golden/mmd_ref.npz: class MMD, calcualte_mmd and the selection loops of the unmodified
+# evaluation/mmd-actions.py, exec'd by tests/golden/make_mmd_golden.py) -------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mmd_ref.npz")
+
+
+@pytest.mark.parametrize("mode", ["avg", "joint"])
+def test_mmd_class_matches_reference_class(mode):
+    g = np.load(GOLD)
+    m = ev.MMD(mode)
+    mine = np.array([m.compute_sequence_mmd(g["seq_1"], g["seq_2"], bw) for bw in g["bandwidths"]])
+    grid = m.sequence_mmd_grid(g["seq_1"], g["seq_2"], tuple(float(b) for b in g["bandwidths"])).numpy()
+    for ref in (g["seq_mmd_torch_" + mode], g["seq_mmd_numpy_" + mode]):
+        ok = np.isfinite(ref)                      # bandwidths where MMD^2 rounds below zero give NaN in the reference too
+        assert np.array_equal(np.isfinite(mine), ok)
+        # fp32 evaluation of sqrt(difference of near-equal sums): absolute agreement at the 1e-4 level for tiny values
+        assert np.allclose(mine[ok], ref[ok], rtol=2e-4, atol=2e-4), (mine, ref)
+        assert np.allclose(grid[ok], ref[ok], rtol=2e-4, atol=2e-4)
+    if mode == "avg":
+        r = np.array([ev.MMD("avg").rkhs_mmd(g["seq_1"][:, 0], g["seq_2"][:, 0], bw) for bw in g["bandwidths"][3:8]])
+        assert np.allclose(r, g["rkhs_numpy"], rtol=2e-4, atol=2e-4, equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", ["avg", "joint"])
+def test_calculate_mmd_matches_reference_function(mode):
+    g = np.load(GOLD)
+    mine = ev.calculate_mmd(g["calc_gen"], g["calc_real"], g["calc_label"], mode, device="cpu")
+    assert abs(mine - float(g["calc_result_" + mode])) < 2e-4 * max(1.0, abs(float(g["calc_result_" + mode]))), (mine, g["calc_result_" + mode])
+
+
+def test_selection_matches_reference_loops_item0_quirk():
+    """Dataset item 0 belongs to class 3: the reference's scan of every class after the first starts at item 1, so item 0 is never
+    selected; the ids and labels below come from the reference's own loops."""
+    g = np.load(GOLD)
+    labels = g["select_labels"]
+    n = len(labels)
+    data = np.zeros((n, 2, 6, 3), np.float32)
+    data[:, 0, 0, 0] = np.arange(n)
+
+    class DS:
+        label = labels
+
+        def __getitem__(self, i):
+            return data[i], int(labels[i])
+
+    acts, lab = ev.first_per_class(DS(), np.arange(10), 100, int(g["select_t_size"]))
+    assert tuple(acts.shape) == tuple(g["select_shape"])
+    assert np.array_equal(acts[:, 0, 0, 0].astype(int), g["select_ids_real"])
+    assert np.array_equal(lab, g["select_label_batch"])
+    assert 0 not in g["select_ids_real"] and labels[0] == 3
+
+
+def test_frechet_distance_matches_scipy_statement():
+    """fid-actions.py:106-157 (scipy.linalg.sqrtm of the product, real part) against the symmetric-eigenvalue evaluation, for
+    full-rank and rank-deficient covariances (fewer samples than dimensions: the reference's eps fallback case)."""
+    from scipy import linalg
+
+    rng = np.random.RandomState(3)
+    for n, d in ((400, 24), (16, 24)):
+        f1 = rng.randn(n, d) @ rng.randn(d, d) * 0.3 + rng.randn(d)
+        f2 = rng.randn(n, d) @ rng.randn(d, d) * 0.3
+        mu1, s1 = np.mean(f1, 0), np.cov(f1, rowvar=False)
+        mu2, s2 = np.mean(f2, 0), np.cov(f2, rowvar=False)
+        covmean = linalg.sqrtm(s1.dot(s2))          # (reference: `sqrtm(..., disp=False)[0]`; scipy >= 1.16 dropped `disp`)
+        if not np.isfinite(covmean).all():
+            off = np.eye(d) * 1e-6
+            covmean = linalg.sqrtm((s1 + off).dot(s2 + off))
+        ref = (mu1 - mu2).dot(mu1 - mu2) + np.trace(s1) + np.trace(s2) - 2 * np.trace(np.real(covmean))
+        m1, c1 = ev.activation_statistics(f1, device="cpu")
+        m2, c2 = ev.activation_statistics(f2, device="cpu")
+        assert np.allclose(c1.numpy(), s1) and np.allclose(m2.numpy(), mu2)
+        mine = ev.frechet_distance(m1, c1, m2, c2)
+        assert abs(mine - ref) < 1e-6 * max(1.0, abs(ref)) + (1e-3 if n < d else 0.0), (n, d, mine, ref)
+        assert abs(ev.frechet_distance(mu1, s1, mu1, s1)) < 1e-8 * np.trace(s1)

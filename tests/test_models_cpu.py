@@ -158,3 +158,42 @@ def test_generator_eval_batchnorm_folding(emu):
     G.eval().fold_batchnorm()
     G.load_state_dict(G.state_dict())
     assert all(blk._fold is None for blk in G.st_gcn_networks)
+
+
+def test_edge_importance_gradient_where_importance_is_zero(emu):
+    """the adjacency gradient is evaluated on the support of the constant BASE adjacency, not of the current
+    A * edge_importance - an importance entry that is exactly 0 (or a cancelling column sum) still gets its gradient; and a
+    standalone ConvTemporalGraphical with a dense learnable A gets a dense gradient.  Checked against the fp64 oracle."""
+    cfg = CASES["ntu_small"]["cfg"]
+    tables = SkeletonTables(cfg.dataset)
+    _, D = build(cfg, torch.float64)
+    pd = {k: v.double() for k, v in onet.synth_params(onet.d_param_shapes(cfg), 2).items()}
+    for i in (0, 1, 3):                                   # zero one importance entry that sits ON the skeleton's support, per partition
+        base = tables.As[onet.d_block_table(cfg)[i][2]]
+        for k in range(base.shape[0]):
+            v, w = [int(t[0]) for t in np.nonzero(base[k])]
+            pd["edge_importance.%d" % i][k, v, w] = 0.0
+    D.load_state_dict(pd)
+    x = inputs(cfg, 3, 7, torch.float64)
+    (D(x["real"], x["labels"]) * x["cot_d"]).sum().backward()
+    pr = {k: v.clone().requires_grad_(True) for k, v in pd.items()}
+    ref = (onet.discriminator_forward(pr, x["real"], x["labels"], cfg, tables) * x["cot_d"]).sum()
+    gref = torch.autograd.grad(ref, [pr["edge_importance.%d" % i] for i in range(6)])
+    for i in range(6):
+        g = D.edge_importance[i].grad
+        assert rel_l2(g, gref[i]) < 1e-9, i
+    base = tables.As[onet.d_block_table(cfg)[1][2]]
+    v, w = [int(t[0]) for t in np.nonzero(base[0])]
+    assert pd["edge_importance.1"][0, v, w] == 0 and D.edge_importance[1].grad[0, v, w].abs() > 0
+    # standalone operator, dense learnable A: every entry of dA
+    m = kgan.ConvTemporalGraphical(4, 6, 3).double()
+    xs = torch.randn(2, 4, 5, 7, dtype=torch.float64)
+    A = torch.randn(3, 7, 7, dtype=torch.float64)
+    A[0, 2, 3] = 0.0
+    A.requires_grad_(True)
+    out, _ = m(xs, A)
+    out.sum().backward()
+    y = torch.nn.functional.conv2d(xs, m.conv.weight.detach()).view(2, 3, 6, 5, 7)
+    Ar = A.detach().clone().requires_grad_(True)
+    torch.einsum("nkctv,kvw->nctw", y, Ar).sum().backward()
+    assert rel_l2(A.grad, Ar.grad) < 1e-12 and A.grad[0, 2, 3].abs() > 0
