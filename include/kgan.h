@@ -158,6 +158,13 @@ int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float*
 int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
 /* gx[r, v] = sum_k sum_w gout[r, k, w] * A[k, v, w] */
 int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
+/* Same with a fused epilogue - the join of a critic block's backward (discriminator.py:128-136 differentiated):
+ *   gx[r, v] = ( sum_k sum_w gout[r, k, w] * A[k, v, w]  +  add[r, v] ) * slope(ysrc[r, v]),   slope(y) = y > 0 ? 1 : 0.2
+ * `add` (the residual branch's input gradient) and `ysrc` (the block input = the previous block's LeakyReLU output, whose
+ * activation gradient is applied here) are optional, shaped like gx.  Replaces an elementwise add (autograd's accumulation of the
+ * two branches) and leaky_relu_backward over the same tensor. */
+int kgan_adjmix_bwd_x_fused(const float* gout, const float* A, const float* add, const float* ysrc, float* gx, int n, int c, int t, int v,
+                            int w, int k, int out_tf32, void* stream);
 /* gA[k, v, w] = sum_r x[r, v] * gout[r, k, w]  (gA overwritten) */
 int kgan_adjmix_bwd_a(const float* x, const float* gout, float* gA, int n, int c, int t, int v, int w, int k, void* stream);
 /* Same, restricted to the support of `mask` (K, V, W): gA[k, v, w] = 0 where mask[k, v, w] == 0.  The callers pass the

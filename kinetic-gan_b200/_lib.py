@@ -44,6 +44,7 @@ _SIGS = {
     "kgan_tapconv_wgrad": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _I, _V], C.c_int),
     "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_adjmix_bwd_x_fused": ([_F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a_masked": ([_F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_epilogue_fwd": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),

@@ -72,9 +72,34 @@ struct MixEntry {
     float coef;
 };
 
+// Fused epilogue of the data-adjoint product (kgan_adjmix_bwd_x_fused): out = (mix + add) * act'(ysrc), both optional and laid out
+// like `out`.  It is the join of a critic block's backward: the gradient of the residual branch (`add`) and the LeakyReLU slope of
+// the block INPUT (`ysrc` = the previous block's activated output, slope 0.2 where it is <= 0) are applied where the graph-conv
+// branch's input gradient is produced, instead of by an elementwise add and a mask kernel over the same tensor.
+struct MixEpi {
+    const float* add;
+    const float* ysrc;
+    int rnd;
+};
+__device__ __forceinline__ float mix_fin(float v, const MixEpi& e, int64_t idx) {
+    if (e.add) v += __ldg(e.add + idx);
+    if (e.ysrc) v *= (__ldg(e.ysrc + idx) > 0.f ? 1.f : 0.2f);
+    return tf32_out(v, e.rnd);
+}
+// the same for the pipelined kernel: EPI = false compiles the epilogue operands (and their address arithmetic) away; with EPI the two
+// operand pointers advance like the output pointer
+template <bool EPI>
+__device__ __forceinline__ float mix_fin2(float v, const float* ap, const float* yp, int off, int rnd) {
+    if (EPI) {
+        if (ap) v += __ldg(ap + off);
+        if (yp) v *= (__ldg(yp + off) > 0.f ? 1.f : 0.2f);
+    }
+    return tf32_out(v, rnd);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int n,
-                                                       int ct, int v, int w, int k, int chunks_per_block, int64_t total_items, int rnd) {
+                                                       int ct, int v, int w, int k, int chunks_per_block, int64_t total_items, MixEpi epi) {
     extern __shared__ __align__(16) float sm[];
     const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;           // output blocks per sample / outputs per row
     const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;           // inputs per row / input blocks per sample
@@ -122,7 +147,7 @@ __global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ 
                 const int c = cnt[o];
                 for (int j = 0; j < c; ++j) acc = fmaf(el[j].coef, __ldg(xq + el[j].off), acc);
             }
-            r[u] = tf32_out(acc, rnd);
+            r[u] = (e0 + u < plane) ? mix_fin(acc, epi, nb * (int64_t)plane + e0 + u) : 0.f;
             if (++ww == (unsigned)wo) {
                 ww = 0;
                 ++q;
@@ -243,9 +268,9 @@ struct Mix2Plan {
 };
 
 // rows q, q + rs, ... of one output column: LT = (padded) length of the column's non-zero list, held in registers
-template <int LT>
+template <int LT, bool EPI>
 __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const MixEntry* __restrict__ el, float* __restrict__ ob, int q, int rs, int rows,
-                                         int vi, int wo, int rnd) {
+                                         int vi, int wo, const MixEpi& epi, int64_t obase) {
     float cf[LT > 0 ? LT : 1];
     int of[LT > 0 ? LT : 1];
 #pragma unroll
@@ -256,6 +281,9 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
     }
     const float* xp = xs + q * vi;
     float* op = ob + (size_t)q * wo;
+    const float* ap = (EPI && epi.add) ? epi.add + obase + (int64_t)q * wo : nullptr;
+    const float* yp = (EPI && epi.ysrc) ? epi.ysrc + obase + (int64_t)q * wo : nullptr;
+    const int rnd = epi.rnd;
     const int xstep = rs * vi, ostep = rs * wo;
     for (; q + 3 * rs < rows; q += 4 * rs, xp += 4 * xstep, op += 4 * ostep) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -266,30 +294,38 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
             a2 = fmaf(cf[j], xp[2 * xstep + of[j]], a2);
             a3 = fmaf(cf[j], xp[3 * xstep + of[j]], a3);
         }
-        op[0] = tf32_out(a0, rnd);
-        op[ostep] = tf32_out(a1, rnd);
-        op[2 * ostep] = tf32_out(a2, rnd);
-        op[3 * ostep] = tf32_out(a3, rnd);
+        op[0] = mix_fin2<EPI>(a0, ap, yp, 0, rnd);
+        op[ostep] = mix_fin2<EPI>(a1, ap, yp, ostep, rnd);
+        op[2 * ostep] = mix_fin2<EPI>(a2, ap, yp, 2 * ostep, rnd);
+        op[3 * ostep] = mix_fin2<EPI>(a3, ap, yp, 3 * ostep, rnd);
+        if (EPI) {
+            if (ap) ap += 4 * ostep;
+            if (yp) yp += 4 * ostep;
+        }
     }
     for (; q < rows; q += rs, xp += xstep, op += ostep) {
         float a0 = 0.f;
 #pragma unroll
         for (int j = 0; j < LT; ++j) a0 = fmaf(cf[j], xp[of[j]], a0);
-        op[0] = tf32_out(a0, rnd);
+        op[0] = mix_fin2<EPI>(a0, ap, yp, 0, rnd);
+        if (EPI) {
+            if (ap) ap += ostep;
+            if (yp) yp += ostep;
+        }
     }
 }
 __device__ __noinline__ void mix_rows_any(const float* __restrict__ xs, const MixEntry* __restrict__ el, int L, float* __restrict__ ob, int q, int rs,
-                                          int rows, int vi, int wo, int rnd) {
+                                          int rows, int vi, int wo, const MixEpi& epi, int64_t obase) {
     for (; q < rows; q += rs) {
         float a0 = 0.f;
         for (int j = 0; j < L; ++j) a0 = fmaf(el[j].coef, xs[q * vi + el[j].off], a0);
-        ob[(size_t)q * wo] = tf32_out(a0, rnd);
+        ob[(size_t)q * wo] = mix_fin(a0, epi, obase + (int64_t)q * wo);
     }
 }
 
-template <int MODE>
+template <int MODE, bool EPI>
 __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
-                                                        int w, int k, const __grid_constant__ Mix2Plan pl, int rnd) {
+                                                        int w, int k, const __grid_constant__ Mix2Plan pl, MixEpi epi) {
     extern __shared__ __align__(128) float sm[];
     const int ko = MODE == 0 ? k : 1, wo = MODE == 0 ? w : v;
     const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
@@ -374,18 +410,19 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
             for (int kb = 0; kb < ko; ++kb) {
                 const int L = Lk[kb];
                 const MixEntry* el = ent + ((size_t)kb * wo + my_w) * lc;          // this thread's list: same output column for every row
-                float* ob = out + ((nn * ko + kb) * (int64_t)ct + q0) * wo + my_w;
+                const int64_t obase = ((nn * ko + kb) * (int64_t)ct + q0) * wo + my_w;       // element index of ob[0] in out / add / ysrc
+                float* ob = out + obase;
                 switch (L) {
-                    case 0: mix_rows<0>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 1: mix_rows<1>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 2: mix_rows<2>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 3: mix_rows<3>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 4: mix_rows<4>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 5: mix_rows<5>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 6: mix_rows<6>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 7: mix_rows<7>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    case 8: mix_rows<8>(xs, el, ob, my_q, rs, rows, vi, wo, rnd); break;
-                    default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, rnd); break;
+                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, epi, obase); break;
                 }
             }
         }
@@ -540,7 +577,7 @@ static int check_shape(const char* what, int n, int c, int t, int v, int w, int 
 using namespace kgan;
 
 template <int MODE>
-static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, int rnd, void* stream) {
+static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, MixEpi epi, void* stream) {
     KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "%s: empty dimension", what);
     const int64_t ct64 = (int64_t)c * t;
     KGAN_REQUIRE(ct64 * (MODE == 0 ? w : v) < (1ll << 31) && ct64 * k * w < (1ll << 31), "%s: plane too large", what);
@@ -571,13 +608,15 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
                 const size_t smem2 = (size_t)2 * pl.in_floats * 4 + 16 + 16 + (size_t)((nlists + 3) & ~3) * 4 + (size_t)nlists * pl.lc_max * sizeof(MixEntry);
                 pl.smem_bytes = (int)smem2;
                 if (smem2 <= 100 * 1024) {
-                    static SmemAttrOnce attr2;
-                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE>, 100 * 1024, attr2, "adjmix attribute")) return e;
+                    static SmemAttrOnce attr2, attr3;
+                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, false>, 100 * 1024, attr2, "adjmix attribute")) return e;
+                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, true>, 100 * 1024, attr3, "adjmix attribute")) return e;
                     const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
                     const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
                     const int64_t waves = ceil_div64(pl.tiles, cap);
                     const int64_t grid2 = ceil_div64(pl.tiles, waves);   // every CTA gets `waves` tiles (+-1), all CTAs co-resident
-                    adjmix_rowmix2_k<MODE><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, rnd);
+                    if (epi.add || epi.ysrc) adjmix_rowmix2_k<MODE, true><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
+                    else adjmix_rowmix2_k<MODE, false><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
                     return check_launch(what);
                 }
             }
@@ -586,18 +625,24 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
     const int chunks = (int)ceil_div64((int64_t)ct * wo, AT * 4);
     const int64_t items = (int64_t)n * ko * chunks;
     const int64_t grid = items < 8 * kNumSMs ? items : 8 * kNumSMs;
-    adjmix_rowmix_k<MODE><<<(unsigned)grid, AT, smem, (cudaStream_t)stream>>>(in, A, out, n, ct, v, w, k, chunks, items, rnd);
+    adjmix_rowmix_k<MODE><<<(unsigned)grid, AT, smem, (cudaStream_t)stream>>>(in, A, out, n, ct, v, w, k, chunks, items, epi);
     return check_launch(what);
 }
 
 extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
-    return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, out_tf32, stream);
+    return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, MixEpi{nullptr, nullptr, out_tf32}, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x: null pointer");
-    return launch_rowmix<1>("adjmix_bwd_x", g, A, gx, n, c, t, v, w, k, out_tf32, stream);
+    return launch_rowmix<1>("adjmix_bwd_x", g, A, gx, n, c, t, v, w, k, MixEpi{nullptr, nullptr, out_tf32}, stream);
+}
+
+extern "C" int kgan_adjmix_bwd_x_fused(const float* g, const float* A, const float* add, const float* ysrc, float* gx, int n, int c, int t, int v,
+                                       int w, int k, int out_tf32, void* stream) {
+    KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x_fused: null pointer");
+    return launch_rowmix<1>("adjmix_bwd_x_fused", g, A, gx, n, c, t, v, w, k, MixEpi{add, ysrc, out_tf32}, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {

@@ -54,6 +54,34 @@ def _want(ctx, i):
     return ctx.needs_input_grad[i] and not _data_only
 
 
+# Weight gradients straight into `p.grad`.  The weight-gradient kernels accumulate with atomics anyway; when the trainer has seated
+# every parameter's .grad as a view of its flat gradient buffer (wgan_gp.FlatParams) a backward sweep can let them add into that
+# view (kgan_tapconv_wgrad `accumulate`) and hand autograd nothing - instead of a fresh dW tensor per convolution, a memset, and an
+# `at::add_` launch by AccumulateGrad (10 % of the step's launches in round 1).  Opt-in (`param_grads_in_place()` around
+# `loss.backward()`): torch.autograd.grad(..., inputs=[w]) callers want the tensor back.
+_in_place = False
+
+
+class param_grads_in_place:
+    def __enter__(self):
+        global _in_place
+        self.prev, _in_place = _in_place, True
+
+    def __exit__(self, *exc):
+        global _in_place
+        _in_place = self.prev
+
+
+def _wgrad(x, go, geom, w):
+    """dW of a tap convolution as a differentiable Function - or, inside param_grads_in_place() during a first-order sweep, added
+    in place to w.grad (returns None: autograd has nothing left to accumulate)."""
+    if (_in_place and not torch.is_grad_enabled() and isinstance(w, torch.nn.Parameter) and w.grad is not None and w.grad.is_contiguous()
+            and w.grad.shape == w.shape):
+        ops.tapconv_wgrad(_c(x), _c(go), geom.fwd, tuple(w.shape), out=w.grad)
+        return None
+    return TapConvWgrad.apply(x, go, geom, w.shape)
+
+
 _SUM_T = {}
 
 
@@ -83,7 +111,7 @@ class TapConv(Function):
         x, w = ctx.saved_tensors
         go = _c(go)
         gx = TapConvDgrad.apply(go, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(x, go, ctx.geom, w.shape) if _want(ctx, 1) else None
+        gw = _wgrad(x, go, ctx.geom, w) if _want(ctx, 1) else None
         return gx, gw, None
 
 
@@ -102,7 +130,7 @@ class TapConvDgrad(Function):
         go, w = ctx.saved_tensors
         h = _c(h)
         ggo = TapConv.apply(h, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(h, go, ctx.geom, w.shape) if _want(ctx, 1) else None
+        gw = _wgrad(h, go, ctx.geom, w) if _want(ctx, 1) else None
         return ggo, gw, None
 
 
@@ -126,11 +154,14 @@ class TapConvWgrad(Function):
 
 
 class TapConvEp(Function):
-    """out = act(F(x, w) + bias[c] + add): the convolution with its fused epilogue (one kernel)."""
+    """out = act(F(x, w) + bias[c] + add): the convolution with its fused epilogue (one kernel).
+    `act_bwd=False` (critic blocks chained by Discriminator.forward): the incoming gradient has ALREADY been multiplied by act'(out)
+    - the consumer of `out` (GcnRes with mask_input=True) applies the slope where it produces that gradient - so this node's
+    backward starts from it as is.  Only valid when that consumer is the sole user of `out`."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, add, geom, act):
-        ctx.geom, ctx.act = geom, act
+    def forward(ctx, x, w, bias, add, geom, act, act_bwd=True):
+        ctx.geom, ctx.act = geom, (act if act_bwd else ACT_NONE)
         ctx.add_bcast = add is not None and add.shape[2] == 1 and geom.t_out > 1
         ctx.set_materialize_grads(False)
         out = ops.tapconv_fwd(_c(x), _c(w), geom.fwd, bias, None if add is None else _c(add), act)
@@ -140,17 +171,17 @@ class TapConvEp(Function):
     @staticmethod
     def backward(ctx, go):
         if go is None:
-            return None, None, None, None, None, None
+            return (None,) * len(ctx.needs_input_grad)
         x, w, out = ctx.saved_tensors
         go = _c(go)
         gz = ActGrad.apply(go, out, ctx.act) if ctx.act != ACT_NONE else go
         gx = TapConvDgrad.apply(gz, w, ctx.geom) if ctx.needs_input_grad[0] else None
-        gw = TapConvWgrad.apply(x, gz, ctx.geom, w.shape) if _want(ctx, 1) else None
+        gw = _wgrad(x, gz, ctx.geom, w) if _want(ctx, 1) else None
         gb = ChanSum.apply(gz) if _want(ctx, 2) else None
         ga = None
         if ctx.needs_input_grad[3]:
             ga = PlaneSpmm.apply(gz, sum_t_table(ctx.geom.t_out, ctx.geom.v_out)) if ctx.add_bcast else gz
-        return gx, gw, gb, ga, None, None
+        return (gx, gw, gb, ga, None, None, None)[:len(ctx.needs_input_grad)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,31 +204,38 @@ class AdjMix(Function):
     @staticmethod
     def backward(ctx, go):
         if go is None:
-            return None, None, None
+            return (None,) * len(ctx.needs_input_grad)
         x, A = ctx.saved_tensors
         go = _c(go)
         gx = AdjMixDx.apply(go, A, ctx.support) if ctx.needs_input_grad[0] else None
         gA = AdjMixDA.apply(x, go, A.shape[0], ctx.support) if _want(ctx, 1) else None
-        return gx, gA, None
+        return (gx, gA, None)[:len(ctx.needs_input_grad)]
 
 
 class AdjMixDx(Function):
+    """gx = Dx(g, A) [+ add] [* leaky_relu'(mask_src)] - the optional terms are the fused epilogue of kgan_adjmix_bwd_x_fused
+    (see GcnRes); `mask_src` is a constant here (the slope is piecewise constant in it)."""
+
     @staticmethod
-    def forward(ctx, g, A, support=None):
+    def forward(ctx, g, A, support=None, add=None, mask_src=None):
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(g, A)
+        ctx.save_for_backward(g, A, mask_src)
         ctx.support = support
-        return ops.adjmix_bwd_x(_c(g), _c(A))
+        return ops.adjmix_bwd_x(_c(g), _c(A), None if add is None else _c(add), None if mask_src is None else _c(mask_src.detach()))
 
     @staticmethod
     def backward(ctx, h):
         if h is None:
-            return None, None, None
-        g, A = ctx.saved_tensors
+            return (None,) * len(ctx.needs_input_grad)
+        g, A, mask_src = ctx.saved_tensors
         h = _c(h)
+        if mask_src is not None:
+            h = ActGrad.apply(h, mask_src, ACT_LRELU)
         gg = AdjMix.apply(h, A, ctx.support) if ctx.needs_input_grad[0] else None
         gA = AdjMixDA.apply(h, g, A.shape[0], ctx.support) if _want(ctx, 1) else None
-        return gg, gA, None
+        nig = ctx.needs_input_grad                                  # as long as the argument list of this apply() call
+        gadd = h if (len(nig) > 3 and nig[3]) else None
+        return (gg, gA, None, gadd, None)[:len(nig)]
 
 
 class AdjMixDA(Function):
@@ -220,6 +258,71 @@ class AdjMixDA(Function):
         gx = AdjMixDx.apply(g, hA) if ctx.needs_input_grad[0] else None
         gg = AdjMix.apply(x, hA) if ctx.needs_input_grad[1] else None
         return gx, gg, None, None
+
+
+class GcnRes(Function):
+    """The two consumers of a critic block's input as ONE node (discriminator.py:128-130: `self.gcn(x, A)` and `self.residual(x)`):
+
+        g = TapConv(AdjMix(x, A), w_gcn)                                   graph conv, adjacency first (tgcn.py:61-66 refolded)
+        r = TapConvEp(select(x), w_res, b_res)   |   select(x)   |   x     residual: 1x1 conv / identity, at the kept frames / joints
+
+    Why one node: with two, autograd adds their input gradients with an elementwise kernel and the producer of x then applies its
+    LeakyReLU slope with another - three passes over the largest tensors of the step.  Here the backward hands the residual branch's
+    gradient to the kernel that finishes the graph-conv branch (kgan_adjmix_bwd_x_fused: product + add), and with `mask_input` also the
+    slope of x itself: x is the previous block's LeakyReLU output, sign(x) = sign(pre-activation), so what this node returns IS the
+    gradient w.r.t. that pre-activation and the producer (TapConvEp(act_bwd=False)) skips its own mask kernel.
+    The backward is composed of the differentiable members of the two operator families, so the node is as closed under
+    differentiation as they are (gradient penalty); intermediates (AdjMix(x, A), select(x)) are kept from the forward pass for a
+    first-order sweep and recomputed as graph nodes when the sweep itself is recorded (create_graph)."""
+
+    @staticmethod
+    def forward(ctx, x, A, w_gcn, w_res, b_res, gcn_geom, res_geom, sel, support, mask_input):
+        ctx.set_materialize_grads(False)
+        ctx.gcn_geom, ctx.res_geom, ctx.sel, ctx.support, ctx.mask_input = gcn_geom, res_geom, sel, support, mask_input
+        x, A = _c(x), _c(A)
+        xa = ops.adjmix_fwd(x, A)
+        g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
+        xs = x if sel is None else ops.plane_spmm(x, sel)
+        r = ops.tapconv_fwd(xs, _c(w_res), res_geom.fwd, b_res) if w_res is not None else xs
+        ctx.save_for_backward(x, A, w_gcn, w_res)
+        ctx.xa, ctx.xs = xa, (xs if w_res is not None else None)
+        if w_res is None and sel is None:
+            r = x.view_as(x)              # a distinct output object (autograd marks outputs, not inputs)
+        return g, r
+
+    @staticmethod
+    def backward(ctx, gg, gr):
+        x, A, w_gcn, w_res = ctx.saved_tensors
+        nig = ctx.needs_input_grad
+        gx = gA = gw_gcn = gw_res = gb = None
+        recorded = torch.is_grad_enabled()                       # create_graph: intermediates must be graph nodes of (x, A)
+        # residual branch first: its input gradient is an operand of the kernel that closes the graph-conv branch
+        gx_r = None
+        if gr is not None:
+            gr = _c(gr)
+            if w_res is not None:
+                if _want(ctx, 3) or _want(ctx, 4):
+                    xs = ctx.xs if not recorded else (x if ctx.sel is None else PlaneSpmm.apply(x, ctx.sel))
+                    gw_res = _wgrad(xs, gr, ctx.res_geom, w_res) if _want(ctx, 3) else None
+                    gb = ChanSum.apply(gr) if _want(ctx, 4) else None
+                gxs = TapConvDgrad.apply(gr, w_res, ctx.res_geom) if nig[0] else None
+            else:
+                gxs = gr if nig[0] else None
+            if gxs is not None:
+                gx_r = gxs if ctx.sel is None else PlaneSpmm.apply(gxs, ctx.sel.T)
+        mask = x if ctx.mask_input else None
+        if gg is not None:
+            gg = _c(gg)
+            if _want(ctx, 2):
+                xa = ctx.xa if not recorded else AdjMix.apply(x, A, ctx.support)
+                gw_gcn = _wgrad(xa, gg, ctx.gcn_geom, w_gcn)
+            if nig[0] or _want(ctx, 1):
+                g_xa = TapConvDgrad.apply(gg, w_gcn, ctx.gcn_geom)
+                gA = AdjMixDA.apply(x, g_xa, A.shape[0], ctx.support) if _want(ctx, 1) else None
+                gx = AdjMixDx.apply(g_xa, A, ctx.support, gx_r, mask) if nig[0] else None
+        elif gx_r is not None:
+            gx = ActGrad.apply(gx_r, x, ACT_LRELU) if ctx.mask_input else gx_r
+        return gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

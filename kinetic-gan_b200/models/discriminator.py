@@ -45,6 +45,22 @@ class Discriminator(nn.Module):
         self.label_emb = nn.Embedding(n_classes, n_classes)
         self.fcn = nn.Linear(latent, 1)
         self._head = {}
+        self._shared_adj = None          # see share_adjacency()
+
+    def share_adjacency(self):
+        """Context manager for a training step that calls the critic several times on UNCHANGED parameters and differentiates the
+        calls in one backward sweep (kinetic-gan.py:146-154: D(real), D(fake), D(x_hat), then d_loss.backward()): the effective
+        adjacencies `A[lvl] * edge_importance[i]` and their per-block joint selections are computed by the first call and shared by
+        the others, instead of ~10 tiny elementwise / index launches per block and call (forward and backward)."""
+        return _SharedAdjacency(self)
+
+    def _effective_adjacency(self, i, A, importance):
+        sh = self._shared_adj
+        if sh is None:
+            return A * importance
+        if i not in sh:
+            sh[i] = A * importance
+        return sh[i]
 
     @property
     def A(self):
@@ -55,12 +71,17 @@ class Discriminator(nn.Module):
         c = KF.RoundTF32.apply(self.label_emb(labels))   # (N, n_cls); the (N, n_cls, T, V) planes are never built (identity in fp32 mode)
         A = self.A
         last = len(self.st_gcn_networks) - 1
+        # Blocks chained here hand the LeakyReLU slope of a block's output to the NEXT block's backward (functional.GcnRes /
+        # TapConvEp(act_bwd=False)): possible when every later block has a residual branch (all of the reference's do) and each
+        # block output has exactly one consumer - the next block.  The last block's output goes to the pooling: it keeps its own.
+        chain = all(b._res != "none" for b in list(self.st_gcn_networks)[1:])
         for i, (gcn, importance) in enumerate(zip(self.st_gcn_networks, self.edge_importance)):
+            kw = dict(pad_joints=i < last, mask_input=chain and i > 0, act_bwd=not (chain and i < last))
             if i == 0 and gcn._res == "none":
-                x, _ = gcn(x, A[gcn.lvl] * importance, label_emb=c, pad_joints=i < last)      # label channels folded analytically (I3)
+                x, _ = gcn(x, self._effective_adjacency(i, A[gcn.lvl], importance), label_emb=c, **kw)   # label channels folded analytically (I3)
             else:
                 x = KF.LabelConcat.apply(c, x) if i == 0 else x
-                x, _ = gcn(x, A[gcn.lvl] * importance, pad_joints=i < last)
+                x, _ = gcn(x, self._effective_adjacency(i, A[gcn.lvl], importance), **kw)
         # global pooling + prediction (discriminator.py:68-72)
         key = (x.size(1), x.size(2), x.size(3))
         if key not in self._head:
@@ -69,6 +90,22 @@ class Discriminator(nn.Module):
         x = KF.PlaneSpmm.apply(x, pool)
         validity = KF.TapConvEp.apply(x, self.fcn.weight, self.fcn.bias, None, geom, KF.ACT_NONE)
         return validity.view(N, -1)
+
+
+class _SharedAdjacency:
+    def __init__(self, D):
+        self.D = D
+
+    def __enter__(self):
+        self.prev, self.D._shared_adj = self.D._shared_adj, {}
+        for b in self.D.st_gcn_networks:
+            b._sel_cache = None
+        return self
+
+    def __exit__(self, *exc):
+        self.D._shared_adj = self.prev
+        for b in self.D.st_gcn_networks:
+            b._sel_cache = None
 
 
 # Layout policy of the tensor-core path (module-level switches so that benchmarks can A/B them).  The TMA-fed tap
@@ -104,6 +141,7 @@ class st_gcn(nn.Module):
             self.residual = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=(stride, 1))       # parameter container
         self.l_relu = nn.LeakyReLU(0.2, inplace=True)
         self._plans = {}
+        self._sel_cache = None           # (A object, plan key, selected A): reused while Discriminator.share_adjacency() hands in the same A
 
     def _plan(self, T, V, Vx, pad_out, device):
         """Geometry of one call: T frames, V graph joints, Vx >= V joints carried by the input tensor (the extra ones are
@@ -150,33 +188,44 @@ class st_gcn(nn.Module):
             p = self._plans[key] = (tcn, res, sel, amap, base.contiguous())
         return p
 
-    def forward(self, x, A, label_emb=None, pad_joints=False):
+    def forward(self, x, A, label_emb=None, pad_joints=False, mask_input=False, act_bwd=True):
         """`label_emb` (optional, not in the reference): (N, n_cls) label embedding standing for the first n_cls input
         channels, which the reference materialises as constant planes (discriminator.py:57-60); x then holds only the
         data channels.  Only valid for a block without residual branch (the critic's first block).
         `pad_joints` (optional, not in the reference; used by Discriminator.forward): x may carry dummy joints beyond the
-        graph's V and the output may be padded likewise - see PAD_JOINTS above."""
+        graph's V and the output may be padded likewise - see PAD_JOINTS above.
+        `mask_input`, `act_bwd` (optional, not in the reference; set by Discriminator.forward when it chains the blocks): this
+        block's backward also applies the LeakyReLU slope of its INPUT (the previous block's output) / leaves the slope of its own
+        OUTPUT to the next block - see functional.GcnRes.  Defaults: plain autograd semantics."""
         V = A.size(1)
         assert x.size(3) >= V and (pad_joints or x.size(3) == V)
         tcn, res, sel, amap, support = self._plan(x.size(2), V, x.size(3), pad_joints, x.device)
         A_in = A
         if amap is not None:
-            A = torch.nn.functional.pad(A, (0, 1, 0, 1)).index_select(1, amap[0]).index_select(2, amap[1])
+            c = self._sel_cache
+            if c is not None and c[0] is A and c[1] is amap:
+                A = c[2]
+            else:
+                A = torch.nn.functional.pad(A, (0, 1, 0, 1)).index_select(1, amap[0]).index_select(2, amap[1])
+                self._sel_cache = (A_in, amap, A)
         if label_emb is not None:
-            assert self._res == "none"
+            assert self._res == "none" and not mask_input
             g, _ = self.gcn.forward_with_labels(x, A, label_emb, support)
-        else:
-            g, _ = self.gcn(x, A, support)
-        if self._res == "none":
             r = None
-        elif self._res == "identity":
-            r = x if sel is None else KF.PlaneSpmm.apply(x, sel)
+        elif self._res == "none":
+            assert not mask_input, "mask_input needs a residual branch (functional.GcnRes)"
+            g, _ = self.gcn(x, A, support)
+            r = None
         else:
-            xs = x if sel is None else KF.PlaneSpmm.apply(x, sel)
-            r = KF.TapConvEp.apply(xs, self.residual.weight, self.residual.bias, None, res, KF.ACT_NONE)
+            # graph conv and residual branch as one autograd node: their input gradients are joined (and, with mask_input, multiplied
+            # by the LeakyReLU slope of x) inside the kernel that finishes the graph-conv branch (functional.GcnRes)
+            assert self.gcn.conv.bias is None and self.gcn._t == (1, 1, 0, 1)
+            conv = self._res == "conv"
+            g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, self.residual.weight if conv else None, self.residual.bias if conv else None,
+                                   self.gcn._geom(x.size(2), A.size(2)), res, sel, support, mask_input)
         if isinstance(tcn, UnfoldedTcnGeom):
             g = KF.PlaneSpmm.apply(g, tcn.unfold)
-        x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU)
+        x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU, act_bwd)
         return x, A_in
 
     def downsample_s(self, tensor):

@@ -261,16 +261,23 @@ def adjmix_fwd(x, A):
     return out
 
 
-def adjmix_bwd_x(g, A):
-    _chk(g, A)
+def adjmix_bwd_x(g, A, add=None, mask_src=None):
+    """`add`, `mask_src` (optional, shaped like the result): gx = (product + add) * leaky_relu'(mask_src) in the same kernel."""
+    _chk(g, A, add, mask_src)
     k, v, w = A.shape
     n, kc, t, w2 = g.shape
     assert w2 == w and kc % k == 0
     c = kc // k
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
+    assert add is None or add.shape == gx.shape
+    assert mask_src is None or mask_src.shape == gx.shape
     _shape_sig(g, A)
-    _io(g, A, gx)
-    _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
+    _io(g, A, add, mask_src, gx)
+    if add is None and mask_src is None:
+        _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
+    else:
+        _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x_fused, g.data_ptr(), A.data_ptr(), _ptr(add), _ptr(mask_src), gx.data_ptr(), n, c, t, v, w,
+             k, _rnd(), _stream())
     return gx
 
 

@@ -8,6 +8,8 @@
     (SURVEY.md §7 I6);
   * no per-iteration host synchronisation: losses stay on the device unless asked for.
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -101,11 +103,14 @@ class WGANGPTrainer:
         # the critic has no BatchNorm: every sample is processed independently, so the real and the fake pass
         # (kinetic-gan.py:146,148) run as ONE pass over the concatenated batch - same values, half the launches
         n = real.size(0)
-        validity = self.D(torch.cat((real, fake), 0), torch.cat((labels, labels), 0))
-        real_validity, fake_validity = validity[:n], validity[n:]
-        gp = compute_gradient_penalty(self.D, real, fake, labels, alpha)
+        share = self.D.share_adjacency() if hasattr(self.D, "share_adjacency") else contextlib.nullcontext()
+        with share:                                  # both critic calls use the same A * edge_importance tensors (one backward sweep)
+            validity = self.D(torch.cat((real, fake), 0), torch.cat((labels, labels), 0))
+            real_validity, fake_validity = validity[:n], validity[n:]
+            gp = compute_gradient_penalty(self.D, real, fake, labels, alpha)
         d_loss = -torch.mean(real_validity) + torch.mean(fake_validity) + self.lambda_gp * gp
-        d_loss.backward()
+        with functional.param_grads_in_place():      # weight-gradient kernels add straight into the flat gradient views
+            d_loss.backward()
         return d_loss.detach(), gp.detach()
 
     def _g_grads(self, labels, z, noises=None):
@@ -116,7 +121,8 @@ class WGANGPTrainer:
         try:
             fake = self.G(z, labels, noises=noises)
             g_loss = -torch.mean(self.D(fake, labels))
-            g_loss.backward()
+            with functional.param_grads_in_place():
+                g_loss.backward()
         finally:
             for p in self.fd.params:
                 p.requires_grad_(True)

@@ -58,7 +58,11 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=0):
     return out.view(n, desc.c_out_total, desc.t_out, desc.v_out)
 
 
-def tapconv_wgrad(x, gout, desc, w_shape):
+def tapconv_wgrad(x, gout, desc, w_shape, out=None):
+    if out is not None:                       # accumulate into the caller's buffer (kgan_tapconv_wgrad `accumulate`)
+        with torch.no_grad():
+            out.add_(tapconv_wgrad(x, gout, desc, w_shape))
+        return out
     n = x.shape[0]
     xin = x.reshape(n, desc.c_in_total, desc.p_in)
     go = gout.reshape(n, desc.c_out_total, desc.p_out)
@@ -78,10 +82,15 @@ def adjmix_fwd(x, A):
     return torch.einsum("nctv,kvw->nkctw", x, A).reshape(n, k * c, t, w)
 
 
-def adjmix_bwd_x(g, A):
+def adjmix_bwd_x(g, A, add=None, mask_src=None):
     k, v, w = A.shape
     n, kc, t, _ = g.shape
-    return torch.einsum("nkctw,kvw->nctv", g.reshape(n, k, kc // k, t, w), A)
+    out = torch.einsum("nkctw,kvw->nctv", g.reshape(n, k, kc // k, t, w), A)
+    if add is not None:
+        out = out + add
+    if mask_src is not None:
+        out = out * torch.where(mask_src > 0, torch.ones_like(mask_src), torch.full_like(mask_src, 0.2))
+    return out
 
 
 def adjmix_bwd_a(x, g, k, mask=None):

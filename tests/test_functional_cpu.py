@@ -125,3 +125,64 @@ def test_geometry_tables():
     g = G.TapConvGeom(2, 2, 4, 3, kt=3, pad=1)
     assert g.fwd.pmap[0, 0] == -1 and g.fwd.pmap[1, 0] == 0 and g.fwd.pmap[2, 0] == 3   # zero padding at t = -1
     assert (g.dgrad.pmap[0] == np.array([3, 4, 5, 6, 7, 8, 9, 10, 11, -1, -1, -1])).all()
+
+
+@pytest.mark.parametrize("res", ["conv", "identity"])
+def test_gcn_res_joint_node_second_order(emu, res):
+    """functional.GcnRes (graph conv + residual branch of a critic block as one node, with the previous block's LeakyReLU slope
+    applied in its backward): equals the composition of the separate Functions to first and second order, in both recording
+    modes of its backward (plain sweep: stored intermediates; create_graph: recomputed as graph nodes)."""
+    c_in, c_out, T, V, W = 3, (4 if res == "conv" else 3), 6, 5, 4
+    keep = [0, 2, 3, 4]
+    t_sel = [0, 2, 4]
+    gcn_geom = G.TapConvGeom(c_in, c_out, T, W, K=3)
+    res_geom = G.TapConvGeom(c_in, c_out, len(t_sel), W, kt=1) if res == "conv" else None
+    sel = G.select_table(T, V, t_sel, keep)
+    z = rnd(2, c_in, T, V, seed=1)                       # pre-activation of the "previous block"
+    A, wg = rnd(3, V, W, seed=2), rnd(3 * c_out, c_in, 1, 1, seed=3)
+    wr, br = (rnd(c_out, c_in, 1, 1, seed=4), rnd(c_out, seed=5)) if res == "conv" else (None, None)
+    cg, cr = rnd(2, c_out, T, W, seed=6).detach(), rnd(2, c_out, len(t_sel), W, seed=7).detach()
+    lrelu = lambda t: torch.where(t > 0, t, 0.2 * t)
+
+    def fused(z, A, wg, wr=None, br=None):
+        x = _StraightThrough.apply(z)
+        g, r = KF.GcnRes.apply(x, A, wg, wr, br, gcn_geom, res_geom, sel, None, True)
+        return (g * cg).sum() + (r * cr).sum()
+
+    def plain(z, A, wg, wr=None, br=None):
+        x = lrelu(z)
+        g = KF.TapConv.apply(KF.AdjMix.apply(x, A), wg, gcn_geom)
+        xs = KF.PlaneSpmm.apply(x, sel)
+        r = KF.TapConvEp.apply(xs, wr, br, None, res_geom, KF.ACT_NONE) if res == "conv" else xs
+        return (g * cg).sum() + (r * cr).sum()
+
+    args = (z, A, wg) + ((wr, br) if res == "conv" else ())
+    g1 = torch.autograd.grad(fused(*args), args, create_graph=True)
+    g2 = torch.autograd.grad(plain(*args), args, create_graph=True)
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, atol=1e-11)
+    # second order: gradient of a function of the first-order input gradient (what the penalty does), w.r.t. everything
+    h1 = torch.autograd.grad((g1[0] ** 2).sum(), args, allow_unused=True)
+    h2 = torch.autograd.grad((g2[0] ** 2).sum(), args, allow_unused=True)
+    for a, b in zip(h1, h2):
+        if a is None or b is None:                      # no dependence on one side: the other must be (numerically) absent too
+            assert (a is None or a.abs().max() == 0) and (b is None or b.abs().max() == 0)
+        else:
+            assert torch.allclose(a, b, atol=1e-10)
+    # a plain (unrecorded) sweep uses the stored intermediates
+    p1 = torch.autograd.grad(fused(*args), args)
+    for a, b in zip(p1, g2):
+        assert torch.allclose(a, b, atol=1e-11)
+
+
+class _StraightThrough(torch.autograd.Function):
+    """lrelu(z) in value, identity in gradient: stands for `TapConvEp(..., act_bwd=False)`, whose LeakyReLU slope is applied by
+    the consumer (GcnRes with mask_input=True)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        return torch.where(z > 0, z, 0.2 * z)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
