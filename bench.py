@@ -342,6 +342,8 @@ def run_kgan(args):
     dev = torch.device("cuda", comm.local_rank)
     torch.cuda.set_device(dev)
     kgan.set_precision(args.precision)
+    if os.environ.get("KGAN_STAGED_POLICY"):          # A/B switch of this harness (the library itself reads no environment)
+        kgan.geometry.STAGED_POLICY = os.environ["KGAN_STAGED_POLICY"]
     B, K, W = args.batch, args.steps, args.warmup
 
     torch.manual_seed(0)

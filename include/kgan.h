@@ -83,6 +83,14 @@ typedef struct kgan_tapconv_desc {
      * (geometry.UnfoldedTcnGeom) is kt such groups with ONE tap each instead of kt taps of which kt - 1 read nothing. */
     int32_t p_out_plane;
     int32_t g_pout;
+    /* Staged form, used by the operand-building tensor-core kernel (kgan_tapconv_fwd_tf32, csrc/tapconv_build.cu): the number of
+     * input positions one 128-row output tile can touch through the taps of one channel block (taps with equal tap_in_ch), counted
+     * from a 4-aligned first position and rounded up to 4; for planes of at most 128 output positions: p_in (whole planes are staged).
+     * 0 = not available (p_in not a multiple of 4, or more than 512).  Computed from pmap by the caller (geometry.py).
+     * prefer_staged != 0: take that kernel even where the TMA-fed one is eligible (same-channel multi-tap convolutions: one staged
+     * tile serves all taps). */
+    int32_t stage_span;
+    int32_t prefer_staged;
 } kgan_tapconv_desc;
 
 /* Version / diagnostics. */
@@ -131,6 +139,10 @@ int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, co
  *   - one-position planes (p_in == p_out == 1: nn.Linear) with all shifts 0 and c_in_total a multiple of 4 (the (N, C)
  *     activation matrix as a K-major operand: boxes of 128 samples x 32 channels). */
 int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d);
+/* 1 if kgan_tapconv_fwd_tf32 will run the operand-building kernel for this descriptor (stage_span > 0, tensor-core eligible, and
+ * either prefer_staged or not eligible for the TMA-fed kernel): raw tiles by cp.async.bulk.tensor, tap operands gathered in shared
+ * memory through pmap - any injective map, no alignment rule on shifts. */
+int kgan_tapconv_staged_ok(const kgan_tapconv_desc* d);
 
 /* Tensor-core path of kgan_tapconv_wgrad (tcgen05.mma kind::tf32, split-K over CTAs, fp32 atomics into dw).
  * kgan_tapconv_wgrad_tf32_ok(d) -> 1 if the shape is eligible (else use kgan_tapconv_wgrad). */

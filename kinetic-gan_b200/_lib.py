@@ -22,7 +22,7 @@ class TapConvDesc(C.Structure):
         ("tap_in_ch", C.c_int32 * MAX_TAPS), ("tap_w_off", C.c_int64 * MAX_TAPS), ("tap_row", C.c_int32 * MAX_TAPS),
         ("pmap_vec_mask", C.c_int32), ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
         ("tma_mode", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
-        ("p_out_plane", C.c_int32), ("g_pout", C.c_int32),
+        ("p_out_plane", C.c_int32), ("g_pout", C.c_int32), ("stage_span", C.c_int32), ("prefer_staged", C.c_int32),
     ]
 
 
@@ -38,6 +38,7 @@ _SIGS = {
     "kgan_tapconv_pack_tf32_batched": ([_I, C.POINTER(TapConvDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _F, _I, _V], C.c_int),
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_staged_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_wgrad_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, C.c_int64, _I, _V], C.c_int),

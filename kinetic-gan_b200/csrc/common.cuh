@@ -89,6 +89,11 @@ int tapconv_tma_eligible(const kgan_tapconv_desc& d);
 int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
                     float* out, cudaStream_t stream);
 
+// operand-building variant (tapconv_build.cu): raw activations staged by TMA, tap operands gathered in shared memory through the position map
+int tapconv_build_eligible(const kgan_tapconv_desc& d);
+int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                      float* out, cudaStream_t stream);
+
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d);
 int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);   // TMA-fed variant (tapconv_wgrad_tma.cu)
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,

@@ -387,9 +387,17 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
     const kgan_tapconv_desc m = merge_groups(*d);
+    if (m.prefer_staged) {
+        const int rb = tapconv_fwd_build(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+        if (rb != -1) return rb;
+    }
     if (m.tma_mode != 0) {
         const int rt = tapconv_fwd_tma(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
         if (rt != -1) return rt;
+    }
+    if (!m.prefer_staged) {
+        const int rb = tapconv_fwd_build(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
+        if (rb != -1) return rb;
     }
     int r = tapconv_fwd_tf32(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
     if (r == -1) {
@@ -403,6 +411,13 @@ extern "C" int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d) {
     if (validate(d) || tapconv_is_thin(*d)) return 0;
     const kgan_tapconv_desc m = merge_groups(*d);
     return tapconv_tf32_packed_numel(m) > 0 && tapconv_tma_eligible(m);
+}
+
+extern "C" int kgan_tapconv_staged_ok(const kgan_tapconv_desc* d) {
+    if (validate(d) || tapconv_is_thin(*d)) return 0;
+    const kgan_tapconv_desc m = merge_groups(*d);
+    if (tapconv_tf32_packed_numel(m) <= 0 || !tapconv_build_eligible(m)) return 0;
+    return m.prefer_staged || !(m.tma_mode != 0 && tapconv_tma_eligible(m));
 }
 
 extern "C" int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d) {

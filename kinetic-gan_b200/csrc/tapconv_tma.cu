@@ -490,7 +490,7 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // shared with tapconv_wgrad_tma.cu: 3-D fp32 tiled tensor map (dims innermost first); swizzle 0 = 128B with 32-byte atoms, 1 = 128B,
-// 2 = 64B, 3 = 32B
+// 2 = 64B, 3 = 32B, 4 = none
 int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
@@ -503,7 +503,7 @@ int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3
     const cuuint32_t bx[3] = {box[0], box[1], box[2]};
     const cuuint32_t es[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 4 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);

@@ -13,6 +13,12 @@ import torch
 
 from ._lib import MAX_TAPS
 
+# Which tap convolutions take the operand-building tensor-core kernel (csrc/tapconv_build.cu) in tf32 mode:
+#   "fallback": only those the TMA-fed kernel cannot serve (unaligned shifts, stride / selection maps);
+#   "tcn":      also every multi-tap convolution whose taps read the same channels (one staged tile serves all taps);
+#   "all":      every eligible one.
+STAGED_POLICY = "fallback"
+
 
 def nearest_src(t_in, t_out):
     """Index rule of F.interpolate(mode='nearest'): src = floor(dst * in / out)."""
@@ -41,6 +47,9 @@ class TapDesc:
         self._structs = {}
         self.pmap_vec_mask = self._vec_mask()
         self.tma_mode, self.tap_shift = self._shift_form()
+        self.stage_span = self._stage_span()
+        self.prefer_staged = int(self.stage_span > 0 and STAGED_POLICY != "fallback" and
+                                 (STAGED_POLICY == "all" or (self.ntap > 1 and len(set(self.tap_in_ch)) == 1)))
 
     def _vec_mask(self):
         """Rows of pmap whose aligned groups of 4 output positions map to 4 consecutive, aligned inputs (or all to -1)."""
@@ -72,6 +81,27 @@ class TapDesc:
             shifts.append(sh)
         return 1, shifts
 
+    def _stage_span(self):
+        """include/kgan.h `stage_span`: input positions a 128-row output tile can touch through the taps of one channel block, from a
+        4-aligned first position (planes of at most 128 output positions: the whole input plane)."""
+        if self.p_in % 4:
+            return 0
+        if self.p_out <= 128:
+            return self.p_in if self.p_in <= 512 else 0
+        blocks = {}
+        for t in range(self.ntap):
+            blocks.setdefault(self.tap_in_ch[t], []).append(self.tap_row[t])
+        span = 4
+        for rows in blocks.values():
+            m = self.pmap[sorted(set(rows))].astype(np.int64)
+            for r0 in range(0, self.p_out, 128):
+                v = m[:, r0:r0 + 128]
+                v = v[v >= 0]
+                if v.size:
+                    span = max(span, int(v.max()) + 1 - (int(v.min()) & ~3))
+        span = (span + 3) // 4 * 4
+        return span if span <= 512 else 0
+
     def pmap_on(self, device):
         return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
 
@@ -93,6 +123,7 @@ class TapDesc:
             for i in range(self.ntap):
                 s.tap_shift[i] = self.tap_shift[i]
             s.p_out_plane, s.g_pout = getattr(self, "p_out_plane", 0), getattr(self, "g_pout", 0)
+            s.stage_span, s.prefer_staged = (0, 0) if s.p_out_plane else (self.stage_span, self.prefer_staged)
             self._structs[key] = s
         return s
 

@@ -1,0 +1,96 @@
+"""Operand-building tensor-core tap convolution (csrc/tapconv_build.cu): raw tiles staged by TMA, tap operands gathered in shared
+memory through the position map.  Every shape class of the two networks - aligned and unaligned shifts, stride-2 frame selection,
+joint selection, small planes with several samples per tile, ragged channel counts, two staged boxes per tile - against the fp64
+statement of the descriptor semantics (tests/emu_backend.py), forward and data gradient, tf32 tolerance 1e-3; and exactly on
+tf32-representable data."""
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+
+import emu_backend as emu
+import kgan_b200 as kgan
+
+pytestmark = pytest.mark.gpu
+ops, G = kgan.ops, kgan.geometry
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def staged_everywhere():
+    kgan.set_precision("tf32")
+    old = G.STAGED_POLICY
+    G.STAGED_POLICY = "all"
+    yield
+    G.STAGED_POLICY = old
+    kgan.set_precision("fp32")
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def rel(a, b):
+    b = b.double()
+    return ((a.detach().cpu().double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# name: (geometry kwargs, batch, forward staged?, data gradient staged?)
+GEOMS = {
+    "d0_tcn_v12": (dict(c_in=32, c_out=32, t_in=64, v_in=12, kt=3, pad=1), 5, 1, 1),                           # aligned shifts, 6 tiles per plane
+    "d1_tcn_v11": (dict(c_in=64, c_out=64, t_in=64, v_in=11, kt=3, pad=1), 4, 1, 1),                           # unaligned shifts (+-11), ragged last tile
+    "d1_gcn_v11": (dict(c_in=32, c_out=64, t_in=64, v_in=11, K=3), 4, 1, 1),                                   # three channel blocks
+    "d2_tcn_stride2_v5": (dict(c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, t_sel=list(range(0, 64, 2))), 5, 1, 1),      # 2 boxes per tile
+    "d2_tcn_select": (dict(c_in=128, c_out=128, t_in=64, v_in=11, kt=3, pad=1, t_sel=list(range(0, 64, 2)), v_keep=[2, 4, 6, 8, 10]), 5, 0, 1),
+    "d3_tcn_v5": (dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 6, 1, 1),              # p_out = 80: one sample per tile
+    "d4_tcn_512": (dict(c_in=512, c_out=512, t_in=16, v_in=5, kt=3, pad=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 160, 1, 1),   # p_out = 8: 16 samples per tile
+    "d5_tcn_p4": (dict(c_in=512, c_out=512, t_in=8, v_in=1, kt=3, pad=1, t_sel=[0, 2, 4, 6]), 130, 1, 1),                        # p_out = 4: 32 samples per tile
+    "d4_res_select": (dict(c_in=256, c_out=512, t_in=16, v_in=5, kt=1, t_sel=list(range(0, 16, 2)), v_keep=[4]), 40, 1, 1),
+    "d1_res_select": (dict(c_in=64, c_out=128, t_in=64, v_in=12, kt=1, t_sel=list(range(0, 64, 2)), v_keep=[1, 3, 5, 7, 9]), 6, 0, 1),
+    "ragged_k": (dict(c_in=50, c_out=24, t_in=12, v_in=7, kt=3, pad=1), 21, 1, 1),
+    "g2_gcn": (dict(c_in=256, c_out=128, t_in=4, v_in=5, K=3), 64, 1, 1),
+    "d1_tcn_v25": (dict(c_in=32, c_out=48, t_in=64, v_in=25, kt=3, pad=1), 3, 1, 1),                           # 1600 positions: 12.5 tiles per plane
+}
+
+
+@pytest.mark.parametrize("name", list(GEOMS))
+def test_tapconv_staged(name):
+    kw, n, fwd_ok, dg_ok = GEOMS[name]
+    geom = G.TapConvGeom(**kw)
+    lib = import_module("kinetic-gan_b200._lib").lib()
+    assert lib.kgan_tapconv_staged_ok(geom.fwd.cstruct(n, 0, 1)) == fwd_ok, geom.fwd.stage_span
+    assert lib.kgan_tapconv_staged_ok(geom.dgrad.cstruct(n, 0, 1)) == dg_ok, geom.dgrad.stage_span
+    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    w = rnd(geom.K * geom.c_out, geom.c_in, geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
+    bias = rnd(geom.c_out, seed=3)
+    add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)
+    go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
+    xc, wc = x.cuda(), w.cuda()
+    got = ops.tapconv_fwd(xc, wc, geom.fwd)
+    assert rel(got, emu.tapconv_fwd(x.double(), w.double(), geom.fwd)) < TOL
+    got = ops.tapconv_fwd(xc, wc, geom.fwd, bias.cuda(), add.cuda(), ops.ACT_LRELU)
+    assert rel(got, emu.tapconv_fwd(x.double(), w.double(), geom.fwd, bias.double(), add.double(), ops.ACT_LRELU)) < TOL
+    got = ops.tapconv_fwd(go.cuda(), wc, geom.dgrad)
+    assert rel(got, emu.tapconv_fwd(go.double(), w.double(), geom.dgrad)) < TOL
+    # exact on tf32-representable data (small integers; the builder rounds to nearest, which is the identity there)
+    gen = torch.Generator().manual_seed(7)
+    xi = torch.randint(-3, 4, x.shape, generator=gen).float()
+    wi = torch.randint(-2, 3, w.shape, generator=gen).float()
+    assert torch.equal(ops.tapconv_fwd(xi.cuda(), wi.cuda(), geom.fwd).cpu().double(), emu.tapconv_fwd(xi.double(), wi.double(), geom.fwd))
+    gi = torch.randint(-3, 4, go.shape, generator=gen).float()
+    assert torch.equal(ops.tapconv_fwd(gi.cuda(), wi.cuda(), geom.dgrad).cpu().double(), emu.tapconv_fwd(gi.double(), wi.double(), geom.dgrad))
+
+
+def test_staged_rounds_unrounded_inputs_to_nearest():
+    """The builder rounds what it gathers (round to nearest): on inputs that did NOT come from a libkgan kernel the result equals the
+    fp64 product of the tf32-rounded operands - the TMA-fed kernel would truncate such inputs."""
+    geom = G.TapConvGeom(64, 64, 64, 12, kt=3, pad=1)
+    n = 8
+    x = rnd(n, 64, 64, 12, seed=11) * 1.37
+    w = rnd(64, 64, 3, 1, seed=12) / 14
+    rn = lambda t: ((t.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    got = ops.tapconv_fwd(x.cuda(), w.cuda(), geom.fwd)
+    want = emu.tapconv_fwd(rn(x).double(), rn(w).double(), geom.fwd)
+    assert rel(got, want) < 2.5e-4      # only the rounding of the stored output (2^-11 / sqrt(3)) is left
