@@ -35,12 +35,12 @@ class GeneratorRunner:
         every call as generator.py:97-108 does (statistically the same estimator; the per-call draw costs ~10 ms of host RNG
         and forces eager launches) - the truncated pass then replays as a CUDA graph like the plain one."""
         self.G = generator.eval()
-        self.G.fold_batchnorm()             # eval-mode BatchNorm becomes part of the convolution weights: no BN launches
         self.device = device or next(generator.parameters()).device
         # W-space truncation draws its 1000 latents from the HOST RNG on every call (generator.py:98): a captured graph would freeze
         # them (and a pageable H2D copy cannot be captured), so that mode launches eagerly
         self.batch, self.trunc, self.graphs = batch, trunc, graphs and (trunc is None or cache_mean)
-        self.G._w_mean = self.G.estimate_w_mean() if (trunc is not None and cache_mean) else None
+        self.cache_mean = cache_mean
+        self._version = None                # Generator.weights_version the derived state below was built from
         self.z = torch.zeros(batch, latent_dim, device=self.device)
         self.labels = torch.zeros(batch, dtype=torch.long, device=self.device)
         self.out = None
@@ -49,6 +49,17 @@ class GeneratorRunner:
         self._ring = None               # to_host(): two (device staging, pinned host, D2H-done event) slots + the copy stream
         self._ring_k = 0
         self.host_ready = None          # event of the last to_host() copy
+
+    def _refresh(self):
+        """(Re)builds what is derived from the generator's weights: BatchNorm folds, the cached W-space mean, and - by dropping
+        it - the captured graph.  Runs at the first call and whenever Generator.weights_version moved (load_state_dict, .to(), ...)."""
+        if self._version == getattr(self.G, "weights_version", 0) and self._version is not None:
+            return
+        self.G.eval()
+        self.G.fold_batchnorm()             # eval-mode BatchNorm becomes part of the convolution weights: no BN launches
+        self.G._w_mean = self.G.estimate_w_mean() if (self.trunc is not None and self.cache_mean) else None
+        self._graph = None
+        self._version = getattr(self.G, "weights_version", 0)
 
     def _forward(self):
         with torch.no_grad():
@@ -75,6 +86,7 @@ class GeneratorRunner:
 
     def __call__(self, z, labels):
         assert z.shape == self.z.shape and labels.shape == self.labels.shape
+        self._refresh()
         if z is not self.z:
             self.z.copy_(z, non_blocking=True)
         if labels is not self.labels:

@@ -102,9 +102,28 @@ class Generator(nn.Module):
         return self
 
     def load_state_dict(self, *args, **kwargs):
+        self.invalidate_derived()
+        return super().load_state_dict(*args, **kwargs)
+
+    def invalidate_derived(self):
+        """Everything computed FROM the weights - eval-mode BatchNorm folds, the cached W-space mean of truncate() - is dropped, and
+        `weights_version` moves on so that holders of derived state (generate.GeneratorRunner: folds, mean, captured CUDA graph)
+        rebuild it.  Called by load_state_dict(), .to() / .float() (`_apply`) and .train()."""
         for blk in self.st_gcn_networks:
             blk._fold = None
-        return super().load_state_dict(*args, **kwargs)
+        self._w_mean = None
+        self.weights_version = getattr(self, "weights_version", 0) + 1
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "st_gcn_networks"):
+            self.invalidate_derived()
+        return out
+
+    def train(self, mode=True):
+        if mode and hasattr(self, "st_gcn_networks"):
+            self.invalidate_derived()
+        return super().train(mode)
 
     def truncate(self, w, mean, truncation):
         """generator.py:97-108: W-space truncation towards the mean of `mean` mapped N(0,1) latents (host RNG, as the

@@ -112,27 +112,62 @@ def _shape_sig(*ts):
 
 
 # ---- tf32 tensor-core path: packed weight images ----------------------------------------------------------------------
-# Parameters keep a persistent packed image per (storage, geometry): it is refreshed by ONE batched launch after the
-# optimizer step (repack_weights) - inside a captured CUDA graph the tap convolutions then simply read it.  Any other tensor
-# used as a "weight" (the second-order terms of the gradient penalty) is packed on the spot, cached only until the next
+# Parameters keep a persistent packed image per (storage, geometry, batch class): it is refreshed by ONE batched launch after the
+# optimizer step of ITS network (repack_weights) - inside a captured CUDA graph the tap convolutions then simply read it.  Any other
+# tensor used as a "weight" (the second-order terms of the gradient penalty) is packed on the spot, cached only until the next
 # optimizer step.
-weights_epoch = 0          # bumped by the fused Adam (it rewrites weights behind autograd's version counter)
+#   * freshness is tracked per flat parameter buffer (`_epochs`): the critic's Adam step does not make the generator's images stale;
+#   * an image is re-packed by the batched launch only if it was used since the previous one, or was touched while a CUDA graph was
+#     being captured (a replay reads it without coming through here); the others are marked stale and re-packed lazily;
+#   * entries hold their parameter weakly: images of a model that is gone are dropped (no leak across models / tests).
+import weakref
+
+weights_epoch = 0          # bumped by every fused Adam step (kept for callers that key caches on "the weights changed")
+_epochs = {}               # flat-buffer pointer -> epoch; None: parameters outside any registered flat buffer
+_flats = []                # registered flat parameter buffers: (lo, hi) address ranges
 _packed = {}               # temporaries: key -> (wp, desc, w)
 _persist = {}              # parameters:  key -> _PackedParam
 _batches = {}              # flat-buffer id -> _PackBatch
 
 
 class _PackedParam:
-    __slots__ = ("w", "desc", "cs", "wp", "epoch", "version")
+    __slots__ = ("wref", "ptr", "desc", "cs", "wp", "epoch", "version", "flat", "used", "pinned")
+
+    @property
+    def w(self):
+        return self.wref()
 
 
 class _PackBatch:
     __slots__ = ("entries", "table", "uploaded", "arrays")
 
 
-def invalidate_packed_weights():
+def register_flat(flat):
+    """A trainer's flat parameter buffer (wgan_gp.FlatParams): its parameters' packed images follow this buffer's optimizer steps."""
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+    if (lo, hi) not in _flats:
+        _flats.append((lo, hi))
+    _epochs.setdefault(lo, 0)
+
+
+def _flat_of(ptr):
+    for lo, hi in _flats:
+        if lo <= ptr < hi:
+            return lo
+    return None
+
+
+def invalidate_packed_weights(flat=None):
+    """The weights in `flat` (a registered flat buffer; None: all weights) were rewritten behind autograd's version counter."""
     global weights_epoch
     weights_epoch += 1
+    if flat is None:
+        for k in list(_epochs):
+            _epochs[k] += 1
+        _epochs[None] = _epochs.get(None, 0) + 1
+    else:
+        lo = flat.data_ptr()
+        _epochs[lo] = _epochs.get(lo, 0) + 1
     _packed.clear()
 
 
@@ -140,11 +175,24 @@ def clear_temporary_packs():
     _packed.clear()
 
 
+def _drop_dead():
+    dead = [k for k, e in _persist.items() if e.wref() is None]
+    for k in dead:
+        del _persist[k]
+    if dead:
+        _batches.clear()
+
+
 def repack_weights(flat):
-    """Refresh, with one launch, every persistent packed image whose weight lives in the flat parameter buffer `flat`
-    (called by FlatParams.adam right after the optimizer kernel)."""
+    """Refresh, with one launch, the persistent packed images of the weights that live in the flat parameter buffer `flat` and were
+    used since the last refresh (or are read by a captured CUDA graph); called by FlatParams.adam right after the optimizer kernel."""
+    _drop_dead()
     lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
-    ents = [e for e in _persist.values() if lo <= e.w.data_ptr() < hi]
+    mine = [e for e in _persist.values() if lo <= e.ptr < hi]
+    ents = [e for e in mine if e.used or e.pinned]
+    for e in mine:
+        if not (e.used or e.pinned):
+            e.epoch = -1                       # stale: re-packed on its next use
     if not ents:
         return
     b = _batches.get(lo)
@@ -156,7 +204,7 @@ def repack_weights(flat):
 
         n = len(ents)
         descs = (_lib.TapConvDesc * n)(*[e.cs for e in ents])
-        wv = (C.c_void_p * n)(*[e.w.data_ptr() for e in ents])
+        wv = (C.c_void_p * n)(*[e.ptr for e in ents])
         wpv = (C.c_void_p * n)(*[e.wp.data_ptr() for e in ents])
         b.entries, b.arrays, b.uploaded = ents, (descs, wv, wpv), False
         b.table = torch.empty(n * int(_lib.lib().kgan_tapconv_pack_item_bytes()), device=flat.device, dtype=torch.uint8)
@@ -164,8 +212,10 @@ def repack_weights(flat):
     _run('tapconv_pack', 0.0, _lib.lib().kgan_tapconv_pack_tf32_batched, len(ents), descs, wv, wpv, b.table.data_ptr(), 0 if b.uploaded else 1,
          _stream())
     b.uploaded = True
+    ep = _epochs.get(lo, 0)
     for e in ents:
-        e.epoch, e.version = weights_epoch, e.w._version
+        w = e.wref()
+        e.epoch, e.version, e.used = ep, (w._version if w is not None else -1), False
 
 
 def _packed_weights(w, desc, cs, l):
@@ -178,14 +228,18 @@ def _packed_weights(w, desc, cs, l):
     if isinstance(w, torch.nn.Parameter):
         key = (w.data_ptr(), id(desc), numel)
         e = _persist.get(key)
-        if e is None or e.desc is not desc or e.w is not w:
+        if e is None or e.desc is not desc or e.wref() is not w:
             e = _PackedParam()
-            e.w, e.desc, e.cs, e.epoch, e.version = w, desc, cs, -1, -1
+            e.wref, e.ptr, e.desc, e.cs, e.epoch, e.version = weakref.ref(w), w.data_ptr(), desc, cs, -1, -1
+            e.flat, e.used, e.pinned = _flat_of(w.data_ptr()), False, False
             e.wp = torch.empty(numel, device=w.device, dtype=torch.float32)
             _persist[key] = e
-        if e.epoch != weights_epoch or e.version != w._version:
+        e.used = True
+        if torch.cuda.is_current_stream_capturing():
+            e.pinned = True                    # a graph replay reads this image without passing through here: always refresh it
+        if e.epoch != _epochs.get(e.flat, 0) or e.version != w._version:
             _run('tapconv_pack', 0.0, l.kgan_tapconv_pack_tf32, cs, w.data_ptr(), e.wp.data_ptr(), _stream())
-            e.epoch, e.version = weights_epoch, w._version
+            e.epoch, e.version = _epochs.get(e.flat, 0), w._version
         return e.wp
     key = (w.data_ptr(), w._version, id(desc), numel)
     hit = _packed.get(key)

@@ -74,12 +74,18 @@ def build_parser():
     return p
 
 
-def sample_action(generator, n_row, latent_dim, path, device):
-    """kinetic-gan.py:84-91: 10 actions per class through the TRAINING-mode generator, saved as one (10*n_row, C, T, V) .npy."""
+def sample_action(generator, n_row, latent_dim, path, device, keep_buffers=False):
+    """kinetic-gan.py:84-91: 10 actions per class through the TRAINING-mode generator, saved as one (10*n_row, C, T, V) .npy.
+    The pass updates the BatchNorm running statistics (as in the reference).  `keep_buffers`: restore them afterwards - used under
+    DDP, where only rank 0 samples: its replica's buffers (and with them the checkpoint) would otherwise drift from the other
+    ranks' by one extra momentum update per sample interval."""
     z = torch.as_tensor(np.random.normal(0, 1, (10 * n_row, latent_dim)), dtype=torch.float32, device=device)
     labels = torch.as_tensor(np.array([num for _ in range(10) for num in range(n_row)]), dtype=torch.long, device=device)
+    saved = [(b, b.detach().clone()) for b in generator.buffers()] if keep_buffers else []
     with torch.no_grad():
         gen = generator(z, labels)
+        for b, s in saved:
+            b.copy_(s)
     with open(path, 'wb') as f:
         np.save(f, gen.cpu().numpy())
 
@@ -179,7 +185,13 @@ def train(opt, comm=None):
                     print("[Epoch %d/%d] [Batch %d/%d] [D loss: %f] [G loss: %f]" % (epoch, opt.n_epochs, i, len(stream), vals[-1, 0], vals[-1, 1]),
                           flush=True)
             if comm.rank == 0 and batches_done % opt.sample_interval == 0:
-                sample_action(generator, opt.n_classes, opt.latent_dim, os.path.join(actions_out, str(batches_done) + '.npy'), device)
+                sample_action(generator, opt.n_classes, opt.latent_dim, os.path.join(actions_out, str(batches_done) + '.npy'), device,
+                              keep_buffers=comm.world_size > 1)
+                if pending:                         # the history written now includes this iteration (kinetic-gan.py:184-188)
+                    vals = torch.stack(pending).cpu().numpy()
+                    pending = []
+                    loss_d.extend(vals[:, 0].tolist())
+                    loss_g.extend(vals[:, 1].tolist())
                 save_losses(out, loss_d, loss_g)
             if comm.rank == 0 and opt.checkpoint_interval != -1 and batches_done % opt.checkpoint_interval == 0:
                 # parameters are views of one flat buffer (wgan_gp.FlatParams): clone so that each entry owns its storage

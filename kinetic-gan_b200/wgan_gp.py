@@ -60,6 +60,7 @@ class FlatParams:
             p.data = self.flat[o:o + n].view_as(p)
             p.grad = self.grad[o:o + n].view_as(p)
         self.step = 0
+        ops.register_flat(self.flat)             # packed tf32 weight images follow THIS buffer's optimizer steps
 
     def zero_grad(self):
         self.grad.zero_()
@@ -70,8 +71,8 @@ class FlatParams:
     def adam(self, lr, b1, b2, eps=1e-8, grad_scale=1.0):
         self.step += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, lr, b1, b2, eps, self.step, grad_scale)
-        ops.invalidate_packed_weights()          # tf32 path: packed weight images are stale now ...
-        ops.repack_weights(self.flat)            # ... and refreshed for this network's parameters by one batched launch
+        ops.invalidate_packed_weights(self.flat)   # tf32 path: this network's packed weight images are stale now ...
+        ops.repack_weights(self.flat)              # ... and those in use are refreshed by one batched launch
 
 
 class WGANGPTrainer:

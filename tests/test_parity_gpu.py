@@ -2,7 +2,9 @@
  (a) the golden fixtures dumped from the unmodified reference (fp64 ground truth), small shapes;
  (b) the fp64 CPU oracle at the full NTU shape (25 joints x 64 frames, 60 classes) for a small batch;
  (c) size-independent properties at BASELINE batch sizes.
-Tolerance (fp32 path): rel-L2 <= 1e-5 on outputs, 5e-4 on gradients (reference's own fp32 noise floor allowed)."""
+Tolerance (fp32 path): rel-L2 <= 1e-5 on outputs; gradients <= 2e-5 with the LeakyReLU activation pattern pinned to the CUDA pass's
+(test_full_ntu_shape_gradients_with_pinned_activation_pattern: arithmetic against arithmetic) and 5e-4 / 2e-3 against the oracle's
+own pattern (slope flips of pre-activations within 1e-6 of zero; the reference's own fp32-vs-fp64 distance is of that size)."""
 from importlib import import_module
 
 import numpy as np
@@ -121,7 +123,44 @@ def test_full_ntu_shape_vs_oracle():
     keys = list(pd64)
     gref = dict(zip(keys, torch.autograd.grad(loss_ref, [pd64[k] for k in keys], allow_unused=True)))
     for k, p in D.named_parameters():
-        assert rel_l2(p.grad, gref[k]) < 5e-4, k
+        assert rel_l2(p.grad, gref[k]) < 5e-4, k          # the oracle's OWN LeakyReLU pattern: slopes flip within the forward error of zero
+
+
+def test_full_ntu_shape_gradients_with_pinned_activation_pattern():
+    """The fp32 path's gradients at the measured floor.  Against the oracle's own activation pattern the parameter gradients agree
+    to ~1e-4 .. 5e-4 although every forward quantity agrees to 1e-6: a pre-activation within the forward error of zero has slope
+    0.2 in one evaluation and 1 in the other, and a fraction f of flipped slopes costs ~0.8 sqrt(f) in rel-L2 (f ~ 1e-7 here).
+    With the pattern PINNED to the CUDA pass's (oracle `masks=`) arithmetic is compared with arithmetic: <= 2e-5 on every
+    parameter gradient of loss = -mean(D(x)) + 10 * GP, first-order and double-backward terms together (achieved: printed)."""
+    cfg = onet.Config()
+    n = 6
+    tables = SkeletonTables("ntu")
+    _, D, _, pd = build(cfg)
+    x = inputs(cfg, n, 3)
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    fake = torch.tanh(torch.randn(n, 3, 64, 25, generator=torch.Generator().manual_seed(9)))
+    blocks = []
+    hooks = [m.register_forward_hook(lambda m, i, o: blocks.append(o[0].detach())) for m in D.st_gcn_networks]
+    dv = D(x["real"].cuda(), x["labels"].cuda())
+    gp = wg.compute_gradient_penalty(D, x["real"].cuda(), fake.cuda(), x["labels"].cuda(), alpha=x["alpha"].cuda())
+    for h in hooks:
+        h.remove()
+    (-dv.mean() + 10 * gp).backward()
+    pd64 = {k: v.double().requires_grad_(True) for k, v in pd.items()}
+    ref_blocks = []
+    onet.discriminator_forward(pd64, x["real"].double(), x["labels"], cfg, tables, collect=ref_blocks)
+    slopes = lambda bs: [torch.where(b[..., :r.shape[-1]].cpu() > 0, 1.0, 0.2).double() for b, r in zip(bs, ref_blocks)]
+    dv_ref = onet.discriminator_forward(pd64, x["real"].double(), x["labels"], cfg, tables, masks=slopes(blocks[:6]))
+    gp_ref = onet.gradient_penalty(pd64, x["real"].double(), fake.double(), x["labels"], x["alpha"].double(), cfg, tables, masks=slopes(blocks[6:]))
+    keys = list(pd64)
+    gref = dict(zip(keys, torch.autograd.grad(-dv_ref.mean() + 10 * gp_ref, [pd64[k] for k in keys], allow_unused=True)))
+    worst = 0.0
+    for k, p in D.named_parameters():
+        e = rel_l2(p.grad, gref[k])
+        print("fp32 path, pinned pattern: %-45s rel-L2 %.2e" % (k, e))
+        worst = max(worst, e)
+    assert abs(gp.item() - gp_ref.item()) < 1e-5 * max(1.0, abs(gp_ref.item()))
+    assert worst < 2e-5, worst
 
 
 def test_properties_at_baseline_batch():
