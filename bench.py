@@ -384,6 +384,7 @@ def run_kgan(args):
         e0.record()
         for i in range(first, first + K):
             fn(i)
+        tr.synchronize_updates()                  # the last iteration's all-reduce / Adam (side stream) belong to the timed region
         e1.record()
         comm.barrier()
         torch.cuda.synchronize()

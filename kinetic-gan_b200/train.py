@@ -184,6 +184,8 @@ def train(opt, comm=None):
                 if comm.rank == 0:
                     print("[Epoch %d/%d] [Batch %d/%d] [D loss: %f] [G loss: %f]" % (epoch, opt.n_epochs, i, len(stream), vals[-1, 0], vals[-1, 1]),
                           flush=True)
+            if batches_done % opt.sample_interval == 0 or (opt.checkpoint_interval != -1 and batches_done % opt.checkpoint_interval == 0):
+                trainer.synchronize_updates()       # the optimizer updates run on a side stream: land them before the weights are read
             if comm.rank == 0 and batches_done % opt.sample_interval == 0:
                 sample_action(generator, opt.n_classes, opt.latent_dim, os.path.join(actions_out, str(batches_done) + '.npy'), device,
                               keep_buffers=comm.world_size > 1)

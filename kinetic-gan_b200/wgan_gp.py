@@ -96,11 +96,17 @@ class WGANGPTrainer:
             self.comm.all_reduce_sum_(flat.grad)
 
     # ---- forward + backward halves (everything that can be captured into a CUDA graph) ----------------------------
-    def _d_grads(self, real, labels, z, alpha=None, noises=None):
-        """kinetic-gan.py:137-154: fills the critic's flat gradient buffer, returns (d_loss, gp)."""
+    def _fake(self, labels, z, noises=None):
+        """kinetic-gan.py:143 for the critic update: G's autograd graph is never used there (its grads are zeroed at :157)."""
+        with torch.no_grad():
+            return self.G(z, labels, noises=noises)
+
+    def _d_grads(self, real, labels, z, alpha=None, noises=None, fake=None):
+        """kinetic-gan.py:137-154: fills the critic's flat gradient buffer, returns (d_loss, gp).  `fake`: the generator's output
+        for (z, labels) when it has been computed already (the CUDA-graph path runs that pass as a graph of its own)."""
         self.fd.zero_grad()
-        with torch.no_grad():           # G's graph is never used by the critic update (its grads are zeroed at :157)
-            fake = self.G(z, labels, noises=noises)
+        if fake is None:
+            fake = self._fake(labels, z, noises)
         # the critic has no BatchNorm: every sample is processed independently, so the real and the fake pass
         # (kinetic-gan.py:146,148) run as ONE pass over the concatenated batch - same values, half the launches
         n = real.size(0)
@@ -131,9 +137,13 @@ class WGANGPTrainer:
 
     # ---- CUDA graphs: at the reference batch size the step is launch-bound ------------------
     def capture_graphs(self, real, labels, z, alpha):
-        """Captures forward+backward of the critic step and of the generator step into two CUDA graphs fed from static
-        input buffers (shapes taken from the arguments).  The optimizer update and the DDP all-reduce stay outside the
-        graphs.  Afterwards `iteration()` copies its inputs into the static buffers and replays."""
+        """Captures the step into THREE CUDA graphs fed from static input buffers (shapes taken from the arguments): the
+        generator pass of the critic update (kinetic-gan.py:143), the critic's forward + backward (:146-154), and the generator
+        update's forward + backward (:167-173).  The gradient all-reduce, the fused Adam step and the refresh of the packed weight
+        images run on a SIDE stream after the graph that filled the gradients; the next critic update's generator pass - which
+        depends on none of them - is already running on the main stream meanwhile (`d_step`), so the collective is off the
+        critical path (overlap the exchange; round 1 ran it serially between graph replay and Adam).
+        Afterwards `iteration()` copies its inputs into the static buffers and replays."""
         if self._graphs is not None:
             return
         st = {k: torch.empty_like(v) for k, v in dict(real=real, labels=labels, z=z, alpha=alpha).items()}
@@ -153,20 +163,47 @@ class WGANGPTrainer:
         # so the graphs only read them.  Images of temporaries (second-order terms) must be packed INSIDE the graphs: drop
         # whatever the eager warm-up cached so that no capture-time lookup hits a buffer no replay would refresh.
         ops.clear_temporary_packs()
-        gd, gg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        gf, gd, gg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         l0 = ops.launches
-        with torch.cuda.graph(gd):
-            d_out = self._d_grads(st["real"], st["labels"], st["z"], st["alpha"])
+        with torch.cuda.graph(gf):
+            fake = self._fake(st["labels"], st["z"])                 # stays allocated in the shared pool: the critic graph reads it
+        lf = ops.launches
+        ops.clear_temporary_packs()
+        with torch.cuda.graph(gd, pool=gf.pool()):
+            d_out = self._d_grads(st["real"], st["labels"], st["z"], st["alpha"], fake=fake)
         l1 = ops.launches
         ops.clear_temporary_packs()
-        with torch.cuda.graph(gg, pool=gd.pool()):
+        with torch.cuda.graph(gg, pool=gf.pool()):
             g_out = self._g_grads(st["labels"], st["z"])
         l2 = ops.launches
         ops.clear_temporary_packs()
         with torch.no_grad():
             for b, saved in buffers:
                 b.copy_(saved)
-        self._graphs = dict(static=st, d=gd, g=gg, d_out=d_out, g_out=g_out, d_launches=l1 - l0, g_launches=l2 - l1)
+        self._graphs = dict(static=st, f=gf, d=gd, g=gg, fake=fake, d_out=d_out, g_out=g_out, f_launches=lf - l0, d_launches=l1 - lf,
+                            g_launches=l2 - l1, side=torch.cuda.Stream(), d_done=None, g_done=None)
+
+    def _update_on_side_stream(self, flat, key):
+        """all-reduce + fused Adam + packed-image refresh of one network on the side stream, after everything queued on the main
+        stream so far; `key` ('d_done' / 'g_done') names the event later consumers of those weights wait for."""
+        g = self._graphs
+        main, side = torch.cuda.current_stream(), g["side"]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._reduce(flat)
+            flat.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        g[key] = ev
+
+    def synchronize_updates(self):
+        """Makes the main stream wait for the optimizer updates still running on the side stream (call before reading parameters
+        outside `iteration()`: checkpoints, evaluation, eager passes)."""
+        g = self._graphs
+        if g is not None:
+            for key in ("d_done", "g_done"):
+                if g[key] is not None:
+                    torch.cuda.current_stream().wait_event(g[key])
 
     def d_step(self, real, labels, z, alpha=None, noises=None):
         """kinetic-gan.py:137-155."""
@@ -175,14 +212,23 @@ class WGANGPTrainer:
             st = g["static"]
             if alpha is None:
                 alpha = torch.as_tensor(np.random.random(tuple(st["alpha"].shape)), dtype=torch.float32)
+            main = torch.cuda.current_stream()
             for k, v in (("real", real), ("labels", labels), ("z", z), ("alpha", alpha)):
                 if v is not st[k]:
                     st[k].copy_(v, non_blocking=True)
+            if g["g_done"] is not None:                # the generator pass reads G's weights: its last update must have landed
+                main.wait_event(g["g_done"])
+            g["f"].replay()                            # overlaps the critic's all-reduce / Adam of the previous iteration
+            if g["d_done"] is not None:
+                main.wait_event(g["d_done"])
             g["d"].replay()
-            ops.launches += g["d_launches"]
+            ops.launches += g["f_launches"] + g["d_launches"]
             d_loss, gp = g["d_out"]
-        else:
-            d_loss, gp = self._d_grads(real, labels, z, alpha, noises)
+            self._update_on_side_stream(self.fd, "d_done")
+            return d_loss, gp
+        if g is not None:
+            self.synchronize_updates()
+        d_loss, gp = self._d_grads(real, labels, z, alpha, noises)
         self._reduce(self.fd)
         self.fd.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
         return d_loss, gp
@@ -195,13 +241,17 @@ class WGANGPTrainer:
             for k, v in (("labels", labels), ("z", z)):
                 if v is not st[k]:
                     st[k].copy_(v, non_blocking=True)
+            self.synchronize_updates()                 # the generator update differentiates through the UPDATED critic (kinetic-gan.py:155 -> :170)
             g["g"].replay()
             ops.launches += g["g_launches"]
-            # the two graphs share one memory pool: the critic graph's temporaries may occupy the bytes of this output, so
+            # the graphs share one memory pool: the critic graph's temporaries may occupy the bytes of this output, so
             # hand out a copy that survives the next d_step replay
             g_loss = g["g_out"].clone()
-        else:
-            g_loss = self._g_grads(labels, z, noises)
+            self._update_on_side_stream(self.fg, "g_done")
+            return g_loss
+        if g is not None:
+            self.synchronize_updates()
+        g_loss = self._g_grads(labels, z, noises)
         self._reduce(self.fg)
         self.fg.adam(self.lr, self.b1, self.b2, grad_scale=1.0 / self.world)
         return g_loss
