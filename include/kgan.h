@@ -205,6 +205,10 @@ int kgan_chan_reduce(const float* g, const float* mul, float* out, int n, int c,
 int kgan_plane_spmm(const float* x, const int32_t* idx, const float* wgt, float* out, int64_t rows, int p_in, int p_out,
                     int j, int out_tf32, void* stream);
 
+/* out[r, v] = sum_t x[r, t, v] over the N*C planes r (V <= 32): the adjoint of broadcasting a per-joint term along T (the label term of
+ * the critic's first layer, added with add_period in the tap convolution's epilogue). */
+int kgan_plane_sum_t(const float* x, float* out, int64_t rows, int t, int v, int out_tf32, void* stream);
+
 /* ---- label planes (discriminator.py:57-60) -------------------------------------------------------
  * out[n, c, p] = c < n_cls ? e[n, c] : x[n, c - n_cls, p] */
 int kgan_label_concat(const float* e, const float* x, float* out, int n, int n_cls, int c, int p, int out_tf32, void* stream);

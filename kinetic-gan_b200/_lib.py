@@ -52,6 +52,7 @@ _SIGS = {
     "kgan_act_bwd": ([_F, _F, _F, C.c_int64, _I, _I, _V], C.c_int),
     "kgan_chan_reduce": ([_F, _F, _F, _I, _I, _I, _V], C.c_int),
     "kgan_plane_spmm": ([_F, _F, _F, _F, C.c_int64, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_plane_sum_t": ([_F, _F, C.c_int64, _I, _I, _I, _V], C.c_int),
     "kgan_label_concat": ([_F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_label_split": ([_F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_bn_workspace": ([_I, _I], C.c_int64),

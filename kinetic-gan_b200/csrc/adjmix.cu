@@ -591,7 +591,9 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
     {
         const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
         const int maxj = MODE == 0 ? v : k * w;
-        if (k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        // (planes of a few hundred bytes - the label term of the critic's first layer, 32 rows of 3 floats per sample - are latency-bound
+        // in the pipelined kernel: one barrier round trip per 384-byte tile made that launch 123 us at 32 GB/s; the plain kernel serves them)
+        if (k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (int64_t)ct * vi * ki >= 2048) {
             Mix2Plan pl;
             int R = (24 * 1024) / (ki * vi * 4);                 // <= 24 KB per stage: 4 CTAs (2 stages each) per SM
             R = R / 8 * 8;

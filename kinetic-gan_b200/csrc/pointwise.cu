@@ -498,6 +498,30 @@ __global__ void __launch_bounds__(PT) interpolate_k(const float* __restrict__ al
     }
 }
 
+// out[r, v] = sum_t x[r, t, v]: one warp per (T, V) plane, lanes stream the contiguous plane (coalesced), per-warp column bins in shared
+// memory (V <= 32).  The generic gather kernel did this at 1.2 TB/s (one thread per output walking T strided elements).
+__global__ void __launch_bounds__(PT) plane_sum_t_k(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int t, int v, int rnd) {
+    __shared__ float bins[PT / 32][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = t * v;
+    const int64_t tw = (int64_t)gridDim.x * (PT / 32);
+    for (int64_t r = (int64_t)blockIdx.x * (PT / 32) + wid; r < rows; r += tw) {
+        bins[wid][lane] = 0.f;
+        __syncwarp();
+        const float* xr = x + r * p;
+        int col = lane % v;
+        const int step = 32 % v;
+        for (int e = lane; e < p; e += 32) {
+            atomicAdd(&bins[wid][col], __ldg(xr + e));
+            col += step;
+            if (col >= v) col -= v;
+        }
+        __syncwarp();
+        if (lane < v) out[r * v + lane] = tf32_out(bins[wid][lane], rnd);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(PT) round_tf32_k(const float* __restrict__ x, float* __restrict__ out, int64_t numel) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) out[i] = tf32_out(x[i], 1);
 }
@@ -505,6 +529,12 @@ __global__ void __launch_bounds__(PT) round_tf32_k(const float* __restrict__ x, 
 }  // namespace kgan
 
 using namespace kgan;
+
+extern "C" int kgan_plane_sum_t(const float* x, float* out, int64_t rows, int t, int v, int out_tf32, void* stream) {
+    KGAN_REQUIRE(x && out && rows > 0 && t > 0 && v > 0 && v <= 32, "plane_sum_t: bad argument (1 <= V <= 32)");
+    plane_sum_t_k<<<grid_for(rows, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(x, out, rows, t, v, out_tf32);
+    return check_launch("plane_sum_t");
+}
 
 extern "C" int kgan_round_tf32(const float* x, float* out, int64_t numel, void* stream) {
     KGAN_REQUIRE(x && out && numel > 0, "round_tf32: bad argument");

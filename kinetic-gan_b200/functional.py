@@ -180,7 +180,7 @@ class TapConvEp(Function):
         gb = ChanSum.apply(gz) if _want(ctx, 2) else None
         ga = None
         if ctx.needs_input_grad[3]:
-            ga = PlaneSpmm.apply(gz, sum_t_table(ctx.geom.t_out, ctx.geom.v_out)) if ctx.add_bcast else gz
+            ga = SumT.apply(gz) if ctx.add_bcast else gz
         return (gx, gw, gb, ga, None, None, None)[:len(ctx.needs_input_grad)]
 
 
@@ -440,6 +440,21 @@ class PlaneSpmm(Function):
         if go is None:
             return None, None
         return PlaneSpmm.apply(_c(go), ctx.table.T), None
+
+
+class SumT(Function):
+    """(N, C, T, V) -> (N, C, 1, V), sum over frames: the adjoint of a per-joint term broadcast along T (TapConvEp `add` with one
+    frame).  Its own adjoint is the broadcast, a plane gather with the transposed sum table."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.tv = (x.shape[2], x.shape[3])
+        ctx.set_materialize_grads(False)
+        return ops.plane_sum_t(_c(x)) if x.shape[3] <= 32 else ops.plane_spmm(_c(x), sum_t_table(*ctx.tv))
+
+    @staticmethod
+    def backward(ctx, h):
+        return None if h is None else PlaneSpmm.apply(_c(h), sum_t_table(*ctx.tv).T)
 
 
 class LabelConcat(Function):

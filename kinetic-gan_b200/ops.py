@@ -391,6 +391,17 @@ def plane_spmm(x, table):
     return out
 
 
+def plane_sum_t(x):
+    """(N, C, T, V) -> (N, C, 1, V): sum over frames."""
+    _chk(x)
+    n, c, t, v = x.shape
+    out = torch.empty((n, c, 1, v), device=x.device, dtype=torch.float32)
+    _shape_sig(x, out)
+    _io(x, out)
+    _run('plane_spmm', 0.0, _lib.lib().kgan_plane_sum_t, x.data_ptr(), out.data_ptr(), n * c, t, v, _rnd(), _stream())
+    return out
+
+
 def label_concat(e, x):
     _chk(e, x)
     n, c, t, v = x.shape

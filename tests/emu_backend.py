@@ -134,6 +134,10 @@ def plane_spmm(x, table):
     return xs.sum(-1).reshape(n, c, table.t_out, table.v_out)
 
 
+def plane_sum_t(x):
+    return x.sum(2, keepdim=True)
+
+
 def label_concat(e, x):
     n, c, t, v = x.shape
     return torch.cat((e.view(n, -1, 1, 1).expand(n, e.shape[1], t, v), x), 1).contiguous()
@@ -184,7 +188,7 @@ def interpolate(alpha, x, y):
 
 
 NAMES = ["tapconv_fwd", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
-         "chan_reduce", "plane_spmm", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_bwd", "adam_step",
+         "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_bwd", "adam_step",
          "interpolate"]
 
 

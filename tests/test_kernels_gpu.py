@@ -179,3 +179,17 @@ def test_plane_spmm_small_planes_and_long_lists():
              (G.mean_table(4, 1), rnd(50, 512, 4, 1, seed=10)), (G.mean_table(4, 1).T, rnd(50, 512, 1, 1, seed=11))]
     for tb, inp in cases:
         assert rel(ops.plane_spmm(cu(inp), tb), emu.plane_spmm(dbl(inp), tb)) < TOL, (tb.p_in, tb.p_out, tb.J)
+
+
+def test_plane_sum_t_and_tiny_adjmix():
+    """kgan_plane_sum_t (frame sums of (T, V) planes, V <= 32) against the fp64 statement, incl. V that does not divide 32; and the
+    adjacency product on planes of a few floats (the label term of the critic's first layer: 32 rows of 3 floats per sample), which
+    is routed to the non-pipelined kernel."""
+    for shape in ((9, 32, 64, 12), (5, 7, 16, 5), (3, 4, 8, 1), (2, 3, 64, 25), (4, 5, 3, 32)):
+        x = rnd(*shape, seed=sum(shape))
+        assert rel(ops.plane_sum_t(cu(x)), dbl(x).sum(2, keepdim=True)) < TOL, shape
+    b = rnd(300, 32, 1, 3, seed=1)
+    A = rnd(1, 3, 12, seed=2)
+    assert rel(ops.adjmix_fwd(cu(b), cu(A)), emu.adjmix_fwd(dbl(b), dbl(A))) < TOL
+    g = rnd(300, 32, 1, 12, seed=3)
+    assert rel(ops.adjmix_bwd_x(cu(g), cu(A)), emu.adjmix_bwd_x(dbl(g), dbl(A))) < TOL
