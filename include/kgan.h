@@ -132,6 +132,16 @@ int64_t kgan_tapconv_pack_item_bytes(void);
 int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
                                    int upload, void* stream);
 
+/* Tap convolution with a fused residual branch (the critic block's `tcn(gcn(x)) + residual(x)` then LeakyReLU, discriminator.py:128-136):
+ *     out = act( conv_d(in) + bias + conv_d2(in2) + bias2 )
+ * d2 is a 1x1 convolution (one tap, shift 0, groups 1) of a SECOND tensor with the same samples, output channels and plane as d's output;
+ * its K panel is accumulated into the same TMEM accumulator, so the residual never goes to HBM and back.  wp / wp2 are the
+ * packed images of d / d2 (kgan_tapconv_pack_tf32).  kgan_tapconv_res_ok(d, d2) == 1 when the pair is eligible (both TMA-fed plans, same
+ * channel tiling); otherwise run kgan_tapconv_fwd_tf32 twice with the first result as `add`. */
+int kgan_tapconv_res_ok(const kgan_tapconv_desc* d, const kgan_tapconv_desc* d2);
+int kgan_tapconv_fwd_tf32_res(const kgan_tapconv_desc* d, const float* in, const float* wp, const kgan_tapconv_desc* d2, const float* in2,
+                              const float* wp2, const float* bias, const float* bias2, float* out, void* stream);
+
 /* 1 if kgan_tapconv_fwd_tf32 will run the TMA-fed kernel for this descriptor: activations then reach shared memory by
  * cp.async.bulk.tensor instead of per-thread gathers.  Eligible: tma_mode != 0, tensor-core eligible, and either
  *   - planes of a multiple of 4 positions with every tap shift a multiple of 4 positions (activations as an MN-major operand:

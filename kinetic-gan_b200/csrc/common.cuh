@@ -89,6 +89,11 @@ int tapconv_tma_eligible(const kgan_tapconv_desc& d);
 int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
                     float* out, cudaStream_t stream);
 
+// `d` with the 1x1 convolution `d2` of a second tensor accumulated into the same accumulator (fused residual branch); -1: not eligible
+int tapconv_fwd_tma_res(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2, const float* in, const float* wp, const float* in2, const float* wp2,
+                        const float* bias, const float* bias2, float* out, cudaStream_t stream);
+int tapconv_tma_res_eligible(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2);
+
 // operand-building variant (tapconv_build.cu): raw activations staged by TMA, tap operands gathered in shared memory through the position map
 int tapconv_build_eligible(const kgan_tapconv_desc& d);
 int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,

@@ -498,26 +498,38 @@ __global__ void __launch_bounds__(PT) interpolate_k(const float* __restrict__ al
     }
 }
 
-// out[r, v] = sum_t x[r, t, v]: one warp per (T, V) plane, lanes stream the contiguous plane (coalesced), per-warp column bins in shared
-// memory (V <= 32).  The generic gather kernel did this at 1.2 TB/s (one thread per output walking T strided elements).
+// out[r, v] = sum_t x[r, t, v]: one warp per (T, V) plane.  Lane = (frame slot, joint): the first floor(32 / V) * V lanes read that many
+// consecutive frames per step (contiguous addresses), every lane sums ONE joint in a register, four steps in flight; the frame slots are
+// merged through shared memory at the end.  (The generic gather kernel did this at 1.2 TB/s: one thread per output walking T strided
+// elements; a first version with shared-memory atomics per element reached 1.6 TB/s.)
 __global__ void __launch_bounds__(PT) plane_sum_t_k(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int t, int v, int rnd) {
     __shared__ float bins[PT / 32][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int p = t * v;
+    const int fpw = 32 / v;                                   // frames per warp step
+    const int sub = lane / v, col = lane - sub * v;
+    const bool active = sub < fpw;
+    const int p = t * v, stepe = fpw * v;
     const int64_t tw = (int64_t)gridDim.x * (PT / 32);
     for (int64_t r = (int64_t)blockIdx.x * (PT / 32) + wid; r < rows; r += tw) {
-        bins[wid][lane] = 0.f;
-        __syncwarp();
-        const float* xr = x + r * p;
-        int col = lane % v;
-        const int step = 32 % v;
-        for (int e = lane; e < p; e += 32) {
-            atomicAdd(&bins[wid][col], __ldg(xr + e));
-            col += step;
-            if (col >= v) col -= v;
+        const float* xr = x + r * p + lane;                   // element sub * v + col == lane for active lanes
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (active) {
+            int e = lane;
+            for (; e + 3 * stepe < p; e += 4 * stepe, xr += 4 * stepe) {
+                a0 += __ldg(xr);
+                a1 += __ldg(xr + stepe);
+                a2 += __ldg(xr + 2 * stepe);
+                a3 += __ldg(xr + 3 * stepe);
+            }
+            for (; e < p; e += stepe, xr += stepe) a0 += __ldg(xr);
         }
+        bins[wid][lane] = (a0 + a1) + (a2 + a3);
         __syncwarp();
-        if (lane < v) out[r * v + lane] = tf32_out(bins[wid][lane], rnd);
+        if (lane < v) {
+            float acc = 0.f;
+            for (int s2 = 0; s2 < fpw; ++s2) acc += bins[wid][s2 * v + lane];
+            out[r * v + lane] = tf32_out(acc, rnd);
+        }
         __syncwarp();
     }
 }

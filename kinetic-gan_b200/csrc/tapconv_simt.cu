@@ -407,6 +407,25 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     return r;
 }
 
+extern "C" int kgan_tapconv_res_ok(const kgan_tapconv_desc* d, const kgan_tapconv_desc* d2) {
+    if (validate(d) || validate(d2) || tapconv_is_thin(*d) || tapconv_is_thin(*d2)) return 0;
+    if (tapconv_tf32_packed_numel(*d) <= 0 || tapconv_tf32_packed_numel(*d2) <= 0) return 0;
+    return tapconv_tma_res_eligible(*d, *d2);
+}
+
+extern "C" int kgan_tapconv_fwd_tf32_res(const kgan_tapconv_desc* d, const float* in, const float* wp, const kgan_tapconv_desc* d2, const float* in2,
+                                         const float* wp2, const float* bias, const float* bias2, float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    if (int e = validate(d2)) return e;
+    KGAN_REQUIRE(in && wp && in2 && wp2 && out, "tapconv_fwd_tf32_res: null pointer");
+    const int r = tapconv_fwd_tma_res(*d, *d2, in, wp, in2, wp2, bias, bias2, out, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("tapconv_fwd_tf32_res: not eligible (kgan_tapconv_res_ok() == 0): run the two convolutions separately");
+        return 1;
+    }
+    return r;
+}
+
 extern "C" int kgan_tapconv_tma_ok(const kgan_tapconv_desc* d) {
     if (validate(d) || tapconv_is_thin(*d)) return 0;
     const kgan_tapconv_desc m = merge_groups(*d);

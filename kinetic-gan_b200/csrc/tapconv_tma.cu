@@ -53,14 +53,20 @@ struct TmaPlan {
     int w_res;                                    // 1: the whole packed weight image stays resident in shared memory (loaded once per CTA)
     int w_res_bytes;
     int kmajor;                                   // 1: one-position planes (Linear layers): A is a K-major [128 samples] x [32 channels] box
+    int nkt2;                                     // extra K panel (fused residual 1x1 conv, see tapconv_fwd_tma_res): channel tiles of the
+    int c2_total, p_in2;                          //   second input tensor (0: none), its channel count and plane size
+    int img1_bytes;                               // bytes of the main packed weight image (the panel's image follows it when resident)
     int pf_tiles;                                 // L2 prefetch distance in tiles of this CTA (0: off)
     uint32_t pf_taps;                             // taps whose boxes are prefetched (temporal shifts of the same channels are near-duplicates)
 };
 
 bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, int* n_rows, int* tmem_cols, int* nkt);
 
-static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
+static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck = 0) {
     if (d.tma_mode != 1) return false;
+    p.nkt2 = panel_ck > 0 ? ceil_div(panel_ck, UK) : 0;
+    p.c2_total = panel_ck;
+    p.p_in2 = d.p_out;
     // One-position planes (nn.Linear: the mapping network, the generator's first block at T = V = 1): the activations are an
     // (N, C) row-major matrix, i.e. a plain K-major operand - one [128 samples] x [32 channels] box per stage in the standard
     // SWIZZLE_128B layout.  (As an "MN-major" operand they would need a box along the sample axis, which is strided.)
@@ -96,7 +102,9 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p) {
     p.w_res = 0;
     p.w_res_bytes = 0;
     {
-        const int64_t img = (int64_t)d.groups * p.nkt * d.ntap * p.n_cta * UK * 4;
+        const int64_t img1 = (int64_t)d.groups * p.nkt * d.ntap * p.n_cta * UK * 4;
+        const int64_t img = img1 + (int64_t)p.nkt2 * p.n_cta * UK * 4;
+        p.img1_bytes = (int)img1;
         const int64_t tiles_per_cta = ceil_div64(p.num_tiles, kNumSMs);
         if (p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
             int st = (int)((200 * 1024 - img) / A_STAGE_BYTES);
@@ -171,7 +179,7 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
 template <int ACT>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                   const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
-                                                  uint32_t tfull_bar, uint32_t tfull_parity, int rnd) {
+                                                  uint32_t tfull_bar, uint32_t tfull_parity, int rnd, const float* __restrict__ bp2 = nullptr) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -180,7 +188,8 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
 #pragma unroll
             for (int j = 0; j < 16; ++j) av[j] = ldg_pred(ap + (int64_t)(col0 + j) * astride, valid && j < nc);
         }
-        const float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        if (bp2 && lane < nc) bl += __ldg(bp2 + col0 + lane);        // the fused residual conv's bias
         if (!waited) {
             mbar_wait(tfull_bar, tfull_parity);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -208,7 +217,9 @@ __device__ __forceinline__ void tm_cp_async16(uint32_t dst, const void* src, uin
 __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
                                                                     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
                                                                     const float* __restrict__ in, const float* __restrict__ bias,
-                                                                    const float* __restrict__ add, float* __restrict__ out) {
+                                                                    const float* __restrict__ add, float* __restrict__ out,
+                                                                    const __grid_constant__ CUtensorMap tmap2, const float* __restrict__ wp2,
+                                                                    const float* __restrict__ in2, const float* __restrict__ bias2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
@@ -222,7 +233,8 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
     const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
     const uint32_t wfull = smem_u32(bars + 2 * S + 4);
-    const int kiters = pl.nkt * d.ntap;
+    const int kmain = pl.nkt * d.ntap;                               // K steps of the convolution itself ...
+    const int kiters = kmain + pl.nkt2;                              // ... + the extra panel: a 1x1 conv of a second tensor into the same accumulator
     const bool use_tma = pl.p_box == 32 || pl.kmajor;                // else: cp.async producers (warps 10-13)
 
     if (threadIdx.x == 0) {
@@ -239,6 +251,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
         mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (use_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        if (use_tma && pl.nkt2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap2)) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols)
@@ -267,9 +280,13 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + (pl.w_res ? 0u : chunk_bytes * 8);
             if (pl.w_res && leader && prod_idx == 0) {               // the whole packed image (contiguous for n_split == 1), once
                 mbar_arrive_expect_tx(wfull, (uint32_t)pl.w_res_bytes);
-                for (int off = 0; off < pl.w_res_bytes; off += 16384) {
-                    const int nb = min(16384, pl.w_res_bytes - off);
+                for (int off = 0; off < pl.img1_bytes; off += 16384) {
+                    const int nb = min(16384, pl.img1_bytes - off);
                     bulk_g2s(smem_u32(b_base + off), reinterpret_cast<const uint8_t*>(wp) + off, (uint32_t)nb, wfull);
+                }
+                for (int off = pl.img1_bytes; off < pl.w_res_bytes; off += 16384) {      // the panel's image behind it
+                    const int nb = min(16384, pl.w_res_bytes - off);
+                    bulk_g2s(smem_u32(b_base + off), reinterpret_cast<const uint8_t*>(wp2) + (off - pl.img1_bytes), (uint32_t)nb, wfull);
                 }
             }
             // activation boxes of a later tile of this CTA -> L2 (off by default: measured slower); tiles that share an activation tile
@@ -314,14 +331,17 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                     if (leader) {
                         mbar_arrive_expect_tx(full0 + 8 * s, stage_tx);
                         const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                        const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+                        const bool panel = it >= kmain;                                 // extra K panel: second tensor, no shift
+                        const int ch0 = panel ? (it - kmain) * UK : ch_g + d.tap_in_ch[tap] + ict * UK, sh = panel ? 0 : d.tap_shift[tap];
+                        const CUtensorMap* tm = panel ? &tmap2 : &tmap;
                         if (pl.kmajor) {
-                            tma_load_3d(a_dst, &tmap, ch0, tc.mt * UM, 0, full0 + 8 * s);      // (channel, sample, -): rows past n / channels past C read zero
+                            tma_load_3d(a_dst, tm, ch0, tc.mt * UM, 0, full0 + 8 * s);         // (channel, sample, -): rows past n / channels past C read zero
                         } else if (use_tma) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, &tmap, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
+                            for (int i = 0; i < 4; ++i) tma_load_3d(a_dst + i * TM_GROUP_BYTES, tm, cp[i] + sh, cn[i], ch0, full0 + 8 * s);
                         }
-                        const float* src = wg + (int64_t)it * pl.n_rows * UK;          // loop order == packing order (ic tile, tap)
+                        const float* src = panel ? wp2 + (int64_t)(it - kmain) * pl.n_rows * UK
+                                                 : wg + (int64_t)it * pl.n_rows * UK;    // loop order == packing order (ic tile, tap)
                         const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
                         if (pl.w_res) {
                             // nothing: the weights are resident
@@ -359,7 +379,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             if (pl.w_res) mbar_wait(wfull, 0);
             for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
                 const int buf = ti & 1;
-                const uint32_t b_res = smem_u32(b_base) + (uint32_t)(tma_tile(tile, pl).g * kiters) * (uint32_t)b_stage_bytes;
+                const uint32_t b_res = smem_u32(b_base) + (uint32_t)(tma_tile(tile, pl).g * kmain) * (uint32_t)b_stage_bytes;
                 mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + buf * pl.n_cta;
@@ -371,7 +391,9 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (leader) {
                         const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                        const uint32_t b_addr = pl.w_res ? b_res + (uint32_t)it * (uint32_t)b_stage_bytes : smem_u32(b_base + (size_t)s * b_stage_bytes);
+                        const uint32_t b_addr = !pl.w_res ? smem_u32(b_base + (size_t)s * b_stage_bytes)
+                                                : it < kmain ? b_res + (uint32_t)it * (uint32_t)b_stage_bytes
+                                                             : smem_u32(b_base) + (uint32_t)pl.img1_bytes + (uint32_t)(it - kmain) * (uint32_t)b_stage_bytes;
 #pragma unroll
                         for (int j = 0; j < UK / 8; ++j)
                             umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
@@ -398,6 +420,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
             const TmaTile tc = tma_tile(tile, pl);
             const float* base[4];
+            const float* base2[4];                                     // the extra K panel's tensor (same samples, plane = the output plane)
             int pq[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -407,25 +430,29 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                 const bool ok = G < pl.groups32 && nn < d.n;
                 pq[i] = ok ? ((int)(G - (int64_t)nb * pl.cps) << pl.p_shift) + pl0 : -(1 << 30);
                 base[i] = in + (int64_t)(ok ? nn : 0) * d.c_in_total * d.p_in;
+                base2[i] = pl.nkt2 ? in2 + (int64_t)(ok ? nn : 0) * pl.c2_total * pl.p_in2 : in;
             }
             const int ch_g = tc.g * d.g_in;
             for (int it = 0; it < kiters; ++it) {
                 const int k = kit + it, s = k % S;
                 const uint32_t ph = (uint32_t)(k / S) & 1u;
-                const int ict = it / d.ntap, tap = it - ict * d.ntap;
+                const bool panel = it >= kmain;
+                const int ict = it / d.ntap, tap = panel ? 0 : it - ict * d.ntap;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t a_dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                const int ch0 = ch_g + d.tap_in_ch[tap] + ict * UK, sh = d.tap_shift[tap];
+                const int ch0 = panel ? (it - kmain) * UK : ch_g + d.tap_in_ch[tap] + ict * UK, sh = panel ? 0 : d.tap_shift[tap];
+                const int c_lim = panel ? pl.c2_total : d.c_in_total, p_lim = panel ? pl.p_in2 : d.p_in;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int pos = pq[i] + sh;                       // 4-aligned: the chunk lies entirely inside or outside the plane
-                    const bool pok = pos >= 0 && pos < d.p_in;
+                    const bool pok = pos >= 0 && pos < p_lim;
+                    const float* bs = panel ? base2[i] : base[i];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c = rr + 16 * h;
-                        const bool ok = pok && ch0 + c < d.c_in_total;
+                        const bool ok = pok && ch0 + c < c_lim;
                         const uint32_t dst = a_dst + i * TM_GROUP_BYTES + c * 128 + ((chunk * 16) ^ ((c & 3) << 5));
-                        tm_cp_async16(dst, ok ? base[i] + (int64_t)(ch0 + c) * d.p_in + pos : in, ok ? 16u : 0u);
+                        tm_cp_async16(dst, ok ? bs + (int64_t)(ch0 + c) * p_lim + pos : in, ok ? 16u : 0u);
                     }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8 * s) : "memory");
@@ -454,15 +481,16 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? pg % d.add_period : pg)
                                   : nullptr;
             const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
+            const float* bp2 = (pl.nkt2 && bias2) ? bias2 + out_ch0 + oc_base : nullptr;
             const uint32_t tbar = tfull0 + 8 * buf, tpar = (uint32_t)(ti >> 1) & 1u;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);
             if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
-            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
-            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
+            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+            else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+            else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty0 + 8 * buf);
         }
@@ -517,19 +545,16 @@ int tapconv_tma_eligible(const kgan_tapconv_desc& d) {
     return make_tma_plan(d, p) ? 1 : 0;
 }
 
-// -1: not eligible (caller falls back to the gather kernel)
-int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
-                    float* out, cudaStream_t stream) {
-    TmaPlan p;
-    if (!make_tma_plan(d, p)) return -1;
-    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+static int launch_tma(const kgan_tapconv_desc& d, TmaPlan& p, const float* in, const float* wp, const float* bias, const float* add, float* out,
+                      const float* in2, const float* wp2, const float* bias2, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled not available");
         return 1;
     }
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap2, 0, sizeof(tmap2));
     const cuuint64_t gdim[3] = {(cuuint64_t)d.p_in, (cuuint64_t)d.n, (cuuint64_t)d.c_in_total};
     const cuuint64_t gstr[2] = {(cuuint64_t)d.c_in_total * d.p_in * 4, (cuuint64_t)d.p_in * 4};
     const cuuint32_t box[3] = {(cuuint32_t)p.p_box, (cuuint32_t)p.n_box, 32u};
@@ -544,6 +569,12 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     } else if (p.p_box == 32) {
         r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS && p.nkt2) {                          // the extra K panel's tensor: (position, sample, channel) of in2
+            const cuuint64_t g2[3] = {(cuuint64_t)p.p_in2, (cuuint64_t)d.n, (cuuint64_t)p.c2_total};
+            const cuuint64_t s2[2] = {(cuuint64_t)p.c2_total * p.p_in2 * 4, (cuuint64_t)p.p_in2 * 4};
+            r = enc(&tmap2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in2), g2, s2, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
     }
     if (r != CUDA_SUCCESS) {
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -551,10 +582,46 @@ int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp
     }
     static SmemAttrOnce attr;
     if (int e = ensure_smem(tapconv_fwd_tma_k, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
-    (void)pmap;                                                    // the shift form replaces the position map
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out);
+    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
+                                                                                                                    tmap2, wp2, in2, bias2);
     return check_launch("tapconv_fwd_tma");
+}
+
+// -1: not eligible (caller falls back to the gather kernel)
+int tapconv_fwd_tma(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                    float* out, cudaStream_t stream) {
+    TmaPlan p;
+    if (!make_tma_plan(d, p)) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    (void)pmap;                                                    // the shift form replaces the position map
+    return launch_tma(d, p, in, wp, bias, add, out, nullptr, nullptr, nullptr, stream);
+}
+
+static bool res_plans(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2, TmaPlan& p) {
+    if (d.groups != 1 || d2.groups != 1 || d2.ntap != 1 || d2.tma_mode != 1 || d2.tap_shift[0] != 0 || d2.tap_in_ch[0] != 0) return false;
+    if (d2.n != d.n || d2.co != d.co || d2.c_out_total != d.c_out_total || d2.p_in != d.p_out || d2.p_out != d.p_out || d2.ck != d2.c_in_total) return false;
+    if (d.p_out_plane != 0 || d2.p_out_plane != 0 || d.w_oc_blk != 0 || d2.w_oc_blk != 0) return false;
+    TmaPlan p2;
+    if (!make_tma_plan(d, p, d2.ck) || p.kmajor) return false;
+    return make_tma_plan(d2, p2) && !p2.kmajor && p2.n_cta == p.n_cta && p2.n_split == p.n_split && p2.n_rows == p.n_rows;       // same image tiling
+}
+
+int tapconv_tma_res_eligible(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2) {
+    TmaPlan p;
+    return res_plans(d, d2, p) ? 1 : 0;
+}
+
+// The tap convolution `d` with an extra K panel: out = act(conv_d(in) + bias + conv_d2(in2) + bias2), d2 a 1x1 convolution (one tap, no
+// shift) of a second tensor with the SAME samples, output channels and plane as d's output - the residual branch of a critic block
+// (discriminator.py:115-130) accumulated into the temporal conv's TMEM accumulator instead of being written to HBM by one GEMM and read
+// back as `add` by the next.  -1: not eligible (the caller runs the two convolutions separately).
+int tapconv_fwd_tma_res(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2, const float* in, const float* wp, const float* in2, const float* wp2,
+                        const float* bias, const float* bias2, float* out, cudaStream_t stream) {
+    TmaPlan p;
+    if (!res_plans(d, d2, p)) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(in2)) & 15) return -1;
+    return launch_tma(d, p, in, wp, bias, nullptr, out, in2, wp2, bias2, stream);
 }
 
 }  // namespace kgan

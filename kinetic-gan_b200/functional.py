@@ -184,6 +184,40 @@ class TapConvEp(Function):
         return (gx, gw, gb, ga, None, None, None)[:len(ctx.needs_input_grad)]
 
 
+class TcnRes(Function):
+    """out = act(F_tcn(g, w) + b + F_res(xs, w_res) + b_res): the temporal conv of a critic block with its residual 1x1 conv as an extra
+    K panel of the same accumulator (discriminator.py:128-136; kgan_tapconv_fwd_tf32_res) - where the pair is not eligible the two
+    convolutions run separately, the first as the `add` operand of the second.  The backward is the sum of the two TapConvEp backwards
+    (one activation mask, one bias reduction for both biases).  `act_bwd`: see TapConvEp."""
+
+    @staticmethod
+    def forward(ctx, g, w, b, xs, w_res, b_res, geom, res_geom, act, act_bwd=True):
+        ctx.geom, ctx.res_geom, ctx.act = geom, res_geom, (act if act_bwd else ACT_NONE)
+        ctx.set_materialize_grads(False)
+        g, xs, w, w_res = _c(g), _c(xs), _c(w), _c(w_res)
+        out = ops.tapconv_fwd_res(g, w, geom.fwd, xs, w_res, res_geom.fwd, b, b_res, act)
+        if out is None:
+            r = ops.tapconv_fwd(xs, w_res, res_geom.fwd, b_res)
+            out = ops.tapconv_fwd(g, w, geom.fwd, b, r, act)
+        ctx.save_for_backward(g, w, xs, w_res, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        nig = ctx.needs_input_grad
+        if go is None:
+            return (None,) * len(nig)
+        g, w, xs, w_res, out = ctx.saved_tensors
+        go = _c(go)
+        gz = ActGrad.apply(go, out, ctx.act) if ctx.act != ACT_NONE else go
+        gg = TapConvDgrad.apply(gz, w, ctx.geom) if nig[0] else None
+        gw = _wgrad(g, gz, ctx.geom, w) if _want(ctx, 1) else None
+        gb = ChanSum.apply(gz) if (_want(ctx, 2) or _want(ctx, 5)) else None
+        gxs = TapConvDgrad.apply(gz, w_res, ctx.res_geom) if nig[3] else None
+        gwr = _wgrad(xs, gz, ctx.res_geom, w_res) if _want(ctx, 4) else None
+        return (gg, gw, gb if _want(ctx, 2) else None, gxs, gwr, gb if _want(ctx, 5) else None, None, None, None, None)[:len(nig)]
+
+
 # ------------------------------------------------------------------------------------------------
 # adjacency product family
 # ------------------------------------------------------------------------------------------------

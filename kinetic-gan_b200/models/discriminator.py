@@ -220,12 +220,15 @@ class st_gcn(nn.Module):
             # graph conv and residual branch as one autograd node: their input gradients are joined (and, with mask_input, multiplied
             # by the LeakyReLU slope of x) inside the kernel that finishes the graph-conv branch (functional.GcnRes)
             assert self.gcn.conv.bias is None and self.gcn._t == (1, 1, 0, 1)
-            conv = self._res == "conv"
-            g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, self.residual.weight if conv else None, self.residual.bias if conv else None,
-                                   self.gcn._geom(x.size(2), A.size(2)), res, sel, support, mask_input)
+            # (the joint node hands on the - selected - block input `r`; a residual CONV runs inside the temporal conv's kernel below)
+            g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, None, None, self.gcn._geom(x.size(2), A.size(2)), None, sel, support, mask_input)
         if isinstance(tcn, UnfoldedTcnGeom):
             g = KF.PlaneSpmm.apply(g, tcn.unfold)
-        x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU, act_bwd)
+        if self._res == "conv":
+            # temporal conv + residual 1x1 conv + both biases + LeakyReLU in one launch: the residual is an extra K panel of the accumulator
+            x = KF.TcnRes.apply(g, self.tcn.weight, self.tcn.bias, r, self.residual.weight, self.residual.bias, tcn, res, KF.ACT_LRELU, act_bwd)
+        else:
+            x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU, act_bwd)
         return x, A_in
 
     def downsample_s(self, tensor):

@@ -278,6 +278,33 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     return out
 
 
+def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=ACT_NONE):
+    """act(conv_desc(x, w) + bias + conv_desc2(x2, w2) + bias2) - a tap convolution with a fused residual 1x1 convolution of a second
+    tensor (kgan_tapconv_fwd_tf32_res: one accumulator, the residual never visits HBM).  Returns None when the pair is not eligible
+    (fp32 mode, shapes outside the TMA-fed plans): the caller then runs the two convolutions separately."""
+    if _precision != PREC_TF32:
+        return None
+    _chk(x, w, x2, w2, bias, bias2)
+    n = x.shape[0]
+    l = _lib.lib()
+    cs, cs2 = desc.cstruct(n, act, _precision), desc2.cstruct(n, ACT_NONE, _precision)
+    ok = desc.__dict__.setdefault("_res_ok", {})
+    key = (n, id(desc2))
+    if key not in ok:
+        ok[key] = bool(l.kgan_tapconv_res_ok(cs, cs2))
+    if not ok[key]:
+        return None
+    wp, wp2 = _packed_weights(w, desc, cs, l), _packed_weights(w2, desc2, cs2, l)
+    if wp is None or wp2 is None:
+        return None
+    out = torch.empty((n, desc.c_out_total, desc.t_out, desc.v_out), device=x.device, dtype=torch.float32)
+    _io(x, w, x2, w2, bias, bias2, out)
+    flops = _tap_flops(desc, n) + 2.0 * n * desc2.p_out * desc2.co * desc2.ck
+    _run('tapconv_fwd_tf32', flops, l.kgan_tapconv_fwd_tf32_res, cs, x.data_ptr(), wp.data_ptr(), cs2, x2.data_ptr(), wp2.data_ptr(), _ptr(bias),
+         _ptr(bias2), out.data_ptr(), _stream())
+    return out
+
+
 def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     """`out` (optional): a contiguous fp32 tensor of the weight's shape that the result is ADDED to (the flat gradient view of
     the parameter) instead of being returned in a fresh tensor - the kernels accumulate with atomics anyway."""

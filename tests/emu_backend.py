@@ -58,6 +58,10 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=0):
     return out.view(n, desc.c_out_total, desc.t_out, desc.v_out)
 
 
+def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=0):
+    return tapconv_fwd(x, w, desc, bias, tapconv_fwd(x2, w2, desc2, bias2), act)
+
+
 def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     if out is not None:                       # accumulate into the caller's buffer (kgan_tapconv_wgrad `accumulate`)
         with torch.no_grad():
@@ -187,7 +191,7 @@ def interpolate(alpha, x, y):
     return a * x + (1 - a) * y
 
 
-NAMES = ["tapconv_fwd", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
+NAMES = ["tapconv_fwd", "tapconv_fwd_res", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
          "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_bwd", "adam_step",
          "interpolate"]
 

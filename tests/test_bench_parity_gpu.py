@@ -212,7 +212,7 @@ def test_critic_bench_config_vs_oracle():
     dv = D(xr, x["labels"].cuda())
     tc, simt = tensor_core_share(prof)
     print("critic forward: %d tensor-core launches, %d exact-SIMT tap convolutions" % (tc, simt))
-    assert tc >= 14                          # D1..D5: gcn + tcn (+ residual) on the tensor cores; D0 (3 channels) and the head are SIMT
+    assert tc >= 10                          # D1..D5: gcn + tcn (the residual convs ride in the tcn launches) on the tensor cores; D0 / head: SIMT
     ref_blocks = []
     xr64 = x["real"].double().requires_grad_(True)
     dv_ref = onet.discriminator_forward(pd64, xr64, x["labels"], CFG, tables, collect=ref_blocks)

@@ -149,3 +149,39 @@ def test_critic_tf32_vs_oracle():
     # per-layer error <= 1e-3 (test above) compounds to ~1e-2 at the first block; stated tolerance 2e-2
     for k, p in D.named_parameters():
         assert rel(p.grad, gref[k]) < 2e-2, k
+
+
+RES_CASES = {
+    # name: (tcn geometry, unfolded?, residual in-channels, batch, fused expected)
+    "d1": (dict(c_in=64, c_out=64, t_in=64, v_in=12, kt=3, pad=1), False, 32, 5, 1),                                # TMA boxes (768 positions)
+    "d2_unfolded": (dict(c_in=128, c_out=128, t_in=64, v_in=5, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 64, 2))), True, 64, 5, 1),
+    "d3_unfolded": (dict(c_in=256, c_out=256, t_in=32, v_in=5, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 32, 2))), True, 128, 7, 1),   # 80 positions: cp.async producers
+    "d4_unfolded": (dict(c_in=512, c_out=512, t_in=16, v_in=1, kt=3, pad=1, stride=1, dil=1, t_sel=list(range(0, 16, 2))), True, 256, 70, 1),  # 8 positions, N split
+    "unaligned": (dict(c_in=64, c_out=64, t_in=64, v_in=11, kt=3, pad=1), False, 32, 4, 0),                         # no TMA-fed plan: separate launches
+}
+
+
+@pytest.mark.parametrize("name", list(RES_CASES))
+def test_tapconv_with_fused_residual(name):
+    """kgan_tapconv_fwd_tf32_res: act(tcn(g) + b + res(xs) + b_res) in one accumulator, against the fp64 statement of the two
+    convolutions; where the pair is not eligible ops.tapconv_fwd_res returns None (the Function then launches them separately)."""
+    kw, unfolded, c_res, n, fused = RES_CASES[name]
+    geom = G.UnfoldedTcnGeom(**kw) if unfolded else G.TapConvGeom(**kw)
+    res = G.TapConvGeom(c_res, geom.c_out, geom.t_out, geom.v_out, kt=1)
+    g = rnd(n, geom.c_in, (geom.kt * geom.t_out) if unfolded else geom.t_in, geom.v_in, seed=1)
+    xs = rnd(n, c_res, geom.t_out, geom.v_out, seed=2)
+    w = rnd(geom.c_out, geom.c_in, geom.kt, 1, seed=3) / np.sqrt(geom.c_in * geom.kt)
+    wr = rnd(geom.c_out, c_res, 1, 1, seed=4) / np.sqrt(c_res)
+    b, br = rnd(geom.c_out, seed=5), rnd(geom.c_out, seed=6)
+    got = ops.tapconv_fwd_res(g.cuda(), w.cuda(), geom.fwd, xs.cuda(), wr.cuda(), res.fwd, b.cuda(), br.cuda(), ops.ACT_LRELU)
+    assert (got is not None) == bool(fused)
+    want = emu.tapconv_fwd_res(g.double(), w.double(), geom.fwd, xs.double(), wr.double(), res.fwd, b.double(), br.double(), ops.ACT_LRELU)
+    if got is not None:
+        assert rel(got, want) < TOL
+        # and it equals the two separate launches up to fp32 accumulation order + one output rounding
+        r = ops.tapconv_fwd(xs.cuda(), wr.cuda(), res.fwd, br.cuda())
+        sep = ops.tapconv_fwd(g.cuda(), w.cuda(), geom.fwd, b.cuda(), r, ops.ACT_LRELU)
+        assert rel(got, sep.cpu()) < 5e-4
+    # the Function covers both cases
+    out = kgan.functional.TcnRes.apply(g.cuda(), w.cuda(), b.cuda(), xs.cuda(), wr.cuda(), br.cuda(), geom, res, ops.ACT_LRELU)
+    assert rel(out, want) < TOL
