@@ -132,6 +132,16 @@ int64_t kgan_tapconv_pack_item_bytes(void);
 int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
                                    int upload, void* stream);
 
+/* Tap convolution stored through a scatter table: the p_out computed positions of a plane go to an output plane of d->p_out_plane
+ * positions - position p to omap[3p] and (if >= 0) also to omap[3p + 1]; omap[3p + 2] (if >= 0) is a slot that position keeps ZERO.
+ * Every slot of the output plane must be covered by exactly one of the three roles.  Replaces "graph conv, then gather its output into the
+ * time-unfolded layout of the strided temporal conv" (geometry.UnfoldedTcnGeom.unfold via kgan_plane_spmm): the unfolded tensor is written
+ * by the convolution's epilogue, the intermediate and the copy kernel disappear.  d->groups == 1, no `add`.
+ * kgan_tapconv_scatter_ok(d) == 1 when eligible (TMA-fed plan). */
+int kgan_tapconv_scatter_ok(const kgan_tapconv_desc* d);
+int kgan_tapconv_fwd_tf32_scatter(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* omap, const float* bias,
+                                  float* out, void* stream);
+
 /* Tap convolution with a fused residual branch (the critic block's `tcn(gcn(x)) + residual(x)` then LeakyReLU, discriminator.py:128-136):
  *     out = act( conv_d(in) + bias + conv_d2(in2) + bias2 )
  * d2 is a 1x1 convolution (one tap, shift 0, groups 1) of a SECOND tensor with the same samples, output channels and plane as d's output;

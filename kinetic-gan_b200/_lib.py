@@ -37,6 +37,8 @@ _SIGS = {
     "kgan_tapconv_pack_item_bytes": ([], C.c_int64),
     "kgan_tapconv_pack_tf32_batched": ([_I, C.POINTER(TapConvDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _F, _I, _V], C.c_int),
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
+    "kgan_tapconv_scatter_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_fwd_tf32_scatter": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_res_ok": ([C.POINTER(TapConvDesc), C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_fwd_tf32_res": ([C.POINTER(TapConvDesc), _F, _F, C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),

@@ -94,6 +94,11 @@ int tapconv_fwd_tma_res(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2,
                         const float* bias, const float* bias2, float* out, cudaStream_t stream);
 int tapconv_tma_res_eligible(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2);
 
+// `d` stored through a scatter table (graph conv output written in the unfolded layout of the next temporal conv); -1: not eligible
+int tapconv_fwd_tma_scatter(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* omap, const float* bias, float* out,
+                            cudaStream_t stream);
+int tapconv_tma_scatter_eligible(const kgan_tapconv_desc& d);
+
 // operand-building variant (tapconv_build.cu): raw activations staged by TMA, tap operands gathered in shared memory through the position map
 int tapconv_build_eligible(const kgan_tapconv_desc& d);
 int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,

@@ -282,7 +282,7 @@ static int validate(const kgan_tapconv_desc* d) {
         KGAN_REQUIRE(d->tap_in_ch[t] >= 0 && d->tap_in_ch[t] + d->ck + (d->groups - 1) * d->g_in <= d->c_in_total,
                      "tapconv: tap %d reads channels beyond c_in_total", t);
     KGAN_REQUIRE(d->co + (d->groups - 1) * d->g_out <= d->c_out_total, "tapconv: writes channels beyond c_out_total");
-    KGAN_REQUIRE(d->p_out_plane >= 0 && d->g_pout >= 0 && (d->p_out_plane == 0 ? d->g_pout == 0 : d->p_out + (d->groups - 1) * d->g_pout <= d->p_out_plane),
+    KGAN_REQUIRE(d->p_out_plane >= 0 && d->g_pout >= 0 && (d->p_out_plane == 0 ? d->g_pout == 0 : (d->g_pout == 0 || d->p_out + (d->groups - 1) * d->g_pout <= d->p_out_plane)),
                  "tapconv: position-block groups write beyond the output plane");
     KGAN_REQUIRE(d->p_out_plane == 0 || d->add_period == 0 || d->g_pout % d->add_period == 0, "tapconv: add_period does not divide g_pout");
     return 0;
@@ -402,6 +402,23 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     int r = tapconv_fwd_tf32(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_fwd_tf32: shape not eligible for the tensor-core path (kgan_tapconv_tf32_workspace() == 0)");
+        return 1;
+    }
+    return r;
+}
+
+extern "C" int kgan_tapconv_scatter_ok(const kgan_tapconv_desc* d) {
+    if (validate(d) || tapconv_is_thin(*d) || tapconv_tf32_packed_numel(*d) <= 0) return 0;
+    return tapconv_tma_scatter_eligible(*d);
+}
+
+extern "C" int kgan_tapconv_fwd_tf32_scatter(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* omap, const float* bias,
+                                             float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && wp && omap && out, "tapconv_fwd_tf32_scatter: null pointer");
+    const int r = tapconv_fwd_tma_scatter(*d, in, wp, omap, bias, out, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("tapconv_fwd_tf32_scatter: not eligible (kgan_tapconv_scatter_ok() == 0)");
         return 1;
     }
     return r;

@@ -176,10 +176,11 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
 
 // The residual / label term `add` and the bias do not depend on the accumulator: their loads for the first column chunk are issued
 // BEFORE the wait on the accumulator barrier, so their latency hides behind the tile's main loop instead of following it.
-template <int ACT>
+template <int ACT, bool SCAT = false>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                   const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
-                                                  uint32_t tfull_bar, uint32_t tfull_parity, int rnd, const float* __restrict__ bp2 = nullptr) {
+                                                  uint32_t tfull_bar, uint32_t tfull_parity, int rnd, const float* __restrict__ bp2 = nullptr,
+                                                  int d1 = 0, int dz = 0) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -204,7 +205,14 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
-            if (valid && j < nc) *o = tf32_out(val, rnd);
+            if (valid && j < nc) {
+                const float q = tf32_out(val, rnd);
+                *o = q;
+                if (SCAT) {                                        // scatter store (kgan_tapconv_fwd_tf32_scatter): second copy of this position
+                    if (d1 != 0) o[d1] = q;                        // and a slot of the output plane this position keeps zero (offsets relative to *o,
+                    if (dz != 0) o[dz] = 0.f;                      // 0 = none); compiled out of the ordinary launches (two predicated stores per element cost
+                }                                                  // 5-25 % on the small-channel layers, whose epilogue is on the critical path)
+            }
             o += p_out;
         }
     }
@@ -219,7 +227,8 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                                                                     const float* __restrict__ in, const float* __restrict__ bias,
                                                                     const float* __restrict__ add, float* __restrict__ out,
                                                                     const __grid_constant__ CUtensorMap tmap2, const float* __restrict__ wp2,
-                                                                    const float* __restrict__ in2, const float* __restrict__ bias2) {
+                                                                    const float* __restrict__ in2, const float* __restrict__ bias2,
+                                                                    const int32_t* __restrict__ omap) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
@@ -475,7 +484,15 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const bool valid = G < pl.groups32 && nn < d.n;
             const int po = valid ? pv : 0, nv = valid ? nn : 0;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
-            const int pst = out_plane(d), pg = po + tc.g * d.g_pout;      // plane stride, position inside the output plane
+            int d1 = 0, dz = 0;                                       // offsets relative to the first destination; 0: none
+            int pg0 = po + tc.g * d.g_pout;
+            if (omap) {                                               // scatter store: destinations of source position po inside the output plane
+                const int q0 = __ldg(omap + 3 * po), q1 = __ldg(omap + 3 * po + 1), q2 = __ldg(omap + 3 * po + 2);
+                pg0 = q0;
+                d1 = q1 >= 0 ? q1 - q0 : 0;
+                dz = q2 >= 0 ? q2 - q0 : 0;
+            }
+            const int pst = out_plane(d), pg = pg0;                       // plane stride, position inside the output plane
             float* op = out + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * pst + pg;
             const int64_t astride = d.add_period ? d.add_period : pst;
             const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? pg % d.add_period : pg)
@@ -488,7 +505,8 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+            } else if (omap) tma_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, nullptr, d1, dz);
+            else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -546,7 +564,7 @@ int tapconv_tma_eligible(const kgan_tapconv_desc& d) {
 }
 
 static int launch_tma(const kgan_tapconv_desc& d, TmaPlan& p, const float* in, const float* wp, const float* bias, const float* add, float* out,
-                      const float* in2, const float* wp2, const float* bias2, cudaStream_t stream) {
+                      const float* in2, const float* wp2, const float* bias2, cudaStream_t stream, const int32_t* omap = nullptr) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled not available");
@@ -584,7 +602,7 @@ static int launch_tma(const kgan_tapconv_desc& d, TmaPlan& p, const float* in, c
     if (int e = ensure_smem(tapconv_fwd_tma_k, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
-                                                                                                                    tmap2, wp2, in2, bias2);
+                                                                                                                    tmap2, wp2, in2, bias2, omap);
     return check_launch("tapconv_fwd_tma");
 }
 
@@ -610,6 +628,24 @@ static bool res_plans(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2, T
 int tapconv_tma_res_eligible(const kgan_tapconv_desc& d, const kgan_tapconv_desc& d2) {
     TmaPlan p;
     return res_plans(d, d2, p) ? 1 : 0;
+}
+
+// The tap convolution `d` whose result is STORED through a scatter table: source position p of the p_out computed positions goes to
+// omap[3p] and (if >= 0) omap[3p + 1] of the output plane of d.p_out_plane positions, and keeps omap[3p + 2] (if >= 0) zero.  Used to
+// write a graph conv's output directly in the time-unfolded layout the following strided temporal conv reads (geometry.UnfoldedTcnGeom):
+// no intermediate tensor, no copy kernel.  -1: not eligible.
+int tapconv_fwd_tma_scatter(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* omap, const float* bias, float* out,
+                            cudaStream_t stream) {
+    if (d.groups != 1 || d.g_pout != 0 || d.p_out_plane < d.p_out || d.add_period != 0) return -1;
+    TmaPlan p;
+    if (!make_tma_plan(d, p) || p.kmajor) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    return launch_tma(d, p, in, wp, bias, nullptr, out, nullptr, nullptr, nullptr, stream, omap);
+}
+
+int tapconv_tma_scatter_eligible(const kgan_tapconv_desc& d) {
+    TmaPlan p;
+    return d.groups == 1 && d.g_pout == 0 && d.p_out_plane >= d.p_out && d.add_period == 0 && make_tma_plan(d, p) && !p.kmajor;
 }
 
 // The tap convolution `d` with an extra K panel: out = act(conv_d(in) + bias + conv_d2(in2) + bias2), d2 a 1x1 convolution (one tap, no

@@ -310,12 +310,22 @@ class GcnRes(Function):
     first-order sweep and recomputed as graph nodes when the sweep itself is recorded (create_graph)."""
 
     @staticmethod
-    def forward(ctx, x, A, w_gcn, w_res, b_res, gcn_geom, res_geom, sel, support, mask_input):
+    def forward(ctx, x, A, w_gcn, w_res, b_res, gcn_geom, res_geom, sel, support, mask_input, out_table=None):
+        """`out_table` (optional PlaneTable): g is returned gathered through it - the time-unfolded layout a strided temporal conv
+        reads (geometry.UnfoldedTcnGeom.unfold); where the table is a pure gather the graph conv's epilogue stores that layout
+        directly (ops.tapconv_fwd_scatter), otherwise a gather kernel follows."""
         ctx.set_materialize_grads(False)
         ctx.gcn_geom, ctx.res_geom, ctx.sel, ctx.support, ctx.mask_input = gcn_geom, res_geom, sel, support, mask_input
+        ctx.out_table = out_table
         x, A = _c(x), _c(A)
         xa = ops.adjmix_fwd(x, A)
-        g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
+        g = None
+        if out_table is not None:
+            g = ops.tapconv_fwd_scatter(xa, _c(w_gcn), gcn_geom.fwd, out_table)
+        if g is None:
+            g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
+            if out_table is not None:
+                g = ops.plane_spmm(g, out_table)
         xs = x if sel is None else ops.plane_spmm(x, sel)
         r = ops.tapconv_fwd(xs, _c(w_res), res_geom.fwd, b_res) if w_res is not None else xs
         ctx.save_for_backward(x, A, w_gcn, w_res)
@@ -347,6 +357,8 @@ class GcnRes(Function):
         mask = x if ctx.mask_input else None
         if gg is not None:
             gg = _c(gg)
+            if ctx.out_table is not None:
+                gg = PlaneSpmm.apply(gg, ctx.out_table.T)        # fold the gathered layout back (sum of the copies)
             if _want(ctx, 2):
                 xa = ctx.xa if not recorded else AdjMix.apply(x, A, ctx.support)
                 gw_gcn = _wgrad(xa, gg, ctx.gcn_geom, w_gcn)
@@ -356,7 +368,7 @@ class GcnRes(Function):
                 gx = AdjMixDx.apply(g_xa, A, ctx.support, gx_r, mask) if nig[0] else None
         elif gx_r is not None:
             gx = ActGrad.apply(gx_r, x, ACT_LRELU) if ctx.mask_input else gx_r
-        return gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None
+        return (gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None, None)[:len(nig)]
 
 
 # ------------------------------------------------------------------------------------------------

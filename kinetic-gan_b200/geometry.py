@@ -105,10 +105,11 @@ class TapDesc:
     def pmap_on(self, device):
         return self._dev.get("pmap", device, lambda: torch.from_numpy(self.pmap))
 
-    def cstruct(self, n, act, precision, add_period=0):
+    def cstruct(self, n, act, precision, add_period=0, out_plane=0):
+        """`out_plane` > 0: the result is stored through a scatter table into planes of that many positions (ops.tapconv_fwd_scatter)."""
         from ._lib import TapConvDesc
 
-        key = (n, act, precision, add_period)
+        key = (n, act, precision, add_period, out_plane)
         s = self._structs.get(key)
         if s is None:
             s = TapConvDesc()
@@ -122,7 +123,7 @@ class TapDesc:
             s.tma_mode = self.tma_mode
             for i in range(self.ntap):
                 s.tap_shift[i] = self.tap_shift[i]
-            s.p_out_plane, s.g_pout = getattr(self, "p_out_plane", 0), getattr(self, "g_pout", 0)
+            s.p_out_plane, s.g_pout = (out_plane, 0) if out_plane else (getattr(self, "p_out_plane", 0), getattr(self, "g_pout", 0))
             s.stage_span, s.prefer_staged = (0, 0) if s.p_out_plane else (self.stage_span, self.prefer_staged)
             self._structs[key] = s
         return s
@@ -253,6 +254,38 @@ class PlaneTable:
     def on(self, device):
         return (self._dev.get("idx", device, lambda: torch.from_numpy(self.idx)),
                 self._dev.get("wgt", device, lambda: torch.from_numpy(self.wgt)))
+
+    def scatter_map(self):
+        """The table as a STORE pattern (include/kgan.h kgan_tapconv_fwd_tf32_scatter): for a pure gather table (every output
+        position copies one input position with weight 1, or is zero) in which an input position is copied at most twice, an int32
+        (p_in, 3) array - the two destinations of every source position (-1: none) and one zero slot it is responsible for.
+        None if the table is not of that form."""
+        if hasattr(self, "_scatter"):
+            return self._scatter
+        self._scatter = None
+        if self.J != 1 or not np.all((self.wgt[:, 0] == 1.0) | (self.idx[:, 0] < 0)):
+            return None
+        m = np.full((self.p_in, 3), -1, np.int32)
+        zeros = []
+        for q in range(self.p_out):
+            p = int(self.idx[q, 0])
+            if p < 0:
+                zeros.append(q)
+            elif m[p, 0] < 0:
+                m[p, 0] = q
+            elif m[p, 1] < 0:
+                m[p, 1] = q
+            else:
+                return None
+        if (m[:, 0] < 0).any() or len(zeros) > self.p_in:        # every source must have a destination; one zero slot per source at most
+            return None
+        for i, q in enumerate(zeros):
+            m[i, 2] = q
+        self._scatter = m
+        return m
+
+    def scatter_on(self, device):
+        return self._dev.get("scatter", device, lambda: torch.from_numpy(self.scatter_map()))
 
 
 def upsample_matrix(hoods, v_coarse, halve):

@@ -221,8 +221,10 @@ class st_gcn(nn.Module):
             # by the LeakyReLU slope of x) inside the kernel that finishes the graph-conv branch (functional.GcnRes)
             assert self.gcn.conv.bias is None and self.gcn._t == (1, 1, 0, 1)
             # (the joint node hands on the - selected - block input `r`; a residual CONV runs inside the temporal conv's kernel below)
-            g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, None, None, self.gcn._geom(x.size(2), A.size(2)), None, sel, support, mask_input)
-        if isinstance(tcn, UnfoldedTcnGeom):
+            # ... and, in front of a strided temporal conv, stores the graph conv's result directly in the time-unfolded layout that conv reads
+            g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, None, None, self.gcn._geom(x.size(2), A.size(2)), None, sel, support, mask_input,
+                                   tcn.unfold if isinstance(tcn, UnfoldedTcnGeom) else None)
+        if self._res == "none" and isinstance(tcn, UnfoldedTcnGeom):
             g = KF.PlaneSpmm.apply(g, tcn.unfold)
         if self._res == "conv":
             # temporal conv + residual 1x1 conv + both biases + LeakyReLU in one launch: the residual is an extra K panel of the accumulator

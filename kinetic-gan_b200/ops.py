@@ -278,6 +278,33 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     return out
 
 
+def tapconv_fwd_scatter(x, w, desc, table):
+    """plane_spmm(tapconv_fwd(x, w, desc), table) for a pure-gather `table` (geometry.PlaneTable.scatter_map) in ONE launch: the
+    convolution's epilogue stores every result at its (one or two) positions of the gathered layout and zero-fills the empty slots
+    (kgan_tapconv_fwd_tf32_scatter).  Returns None when not eligible (fp32 mode, no TMA-fed plan, table not a gather)."""
+    if _precision != PREC_TF32 or table.scatter_map() is None:
+        return None
+    _chk(x, w)
+    n = x.shape[0]
+    assert table.p_in == desc.p_out
+    l = _lib.lib()
+    cs = desc.cstruct(n, ACT_NONE, _precision, 0, table.p_out)
+    ok = desc.__dict__.setdefault("_scatter_ok", {})
+    key = (n, table.p_out)
+    if key not in ok:
+        ok[key] = bool(l.kgan_tapconv_scatter_ok(cs))
+    if not ok[key]:
+        return None
+    wp = _packed_weights(w, desc, desc.cstruct(n, ACT_NONE, _precision), l)      # the packed image does not depend on the output layout
+    if wp is None:
+        return None
+    out = torch.empty((n, desc.c_out_total, table.t_out, table.v_out), device=x.device, dtype=torch.float32)
+    _io(x, w, out)
+    _run('tapconv_fwd_tf32', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32_scatter, cs, x.data_ptr(), wp.data_ptr(), table.scatter_on(x.device).data_ptr(),
+         0, out.data_ptr(), _stream())
+    return out
+
+
 def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=ACT_NONE):
     """act(conv_desc(x, w) + bias + conv_desc2(x2, w2) + bias2) - a tap convolution with a fused residual 1x1 convolution of a second
     tensor (kgan_tapconv_fwd_tf32_res: one accumulator, the residual never visits HBM).  Returns None when the pair is not eligible

@@ -185,3 +185,23 @@ def test_tapconv_with_fused_residual(name):
     # the Function covers both cases
     out = kgan.functional.TcnRes.apply(g.cuda(), w.cuda(), b.cuda(), xs.cuda(), wr.cuda(), br.cuda(), geom, res, ops.ACT_LRELU)
     assert rel(out, want) < TOL
+
+
+@pytest.mark.parametrize("c_in,c_out,t,v,n", [(64, 128, 64, 5, 6), (128, 256, 32, 5, 9), (256, 512, 16, 1, 70), (512, 512, 8, 1, 130)])
+def test_tapconv_scatter_store(c_in, c_out, t, v, n):
+    """kgan_tapconv_fwd_tf32_scatter: a graph conv whose epilogue stores its result directly in the time-unfolded layout of the following
+    stride-2 temporal conv (two copies of the odd frames, zero padding slots) == tap convolution followed by the gather kernel, bit for
+    bit (same accumulators, same rounding), and both against the fp64 statement."""
+    geom = G.TapConvGeom(c_in, c_out, t, v, K=3)
+    unf = G.UnfoldedTcnGeom(c_out, c_out, t, v, 3, 1, 1, 1, list(range(0, t, 2))).unfold
+    m = unf.scatter_map()
+    assert m is not None and sorted(int(q) for q in m.reshape(-1) if q >= 0) == list(range(unf.p_out))      # every slot has exactly one role
+    x = rnd(n, 3 * c_in, t, v, seed=1)
+    w = rnd(3 * c_out, c_in, 1, 1, seed=2) / np.sqrt(3 * c_in)
+    poison = torch.full((n, c_out, unf.t_out, unf.v_out), float('nan'), device='cuda')       # the result must not depend on what the allocator hands out
+    del poison
+    got = ops.tapconv_fwd_scatter(x.cuda(), w.cuda(), geom.fwd, unf)
+    assert got is not None
+    two = ops.plane_spmm(ops.tapconv_fwd(x.cuda(), w.cuda(), geom.fwd), unf)
+    assert torch.equal(got, two)
+    assert rel(got, emu.plane_spmm(emu.tapconv_fwd(x.double(), w.double(), geom.fwd), unf)) < TOL
