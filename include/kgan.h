@@ -91,6 +91,11 @@ typedef struct kgan_tapconv_desc {
      * tile serves all taps). */
     int32_t stage_span;
     int32_t prefer_staged;
+    /* Fused graph convolution (kgan_gcn_fwd_tf32 only; 0, 0, 0 elsewhere): the adjacency product is taken inside the kernel.  `in` is the
+     * block input x (c_in_total = ck channels, planes of T * mix_v positions), the output planes hold T * mix_w positions, the ntap taps
+     * are the K partitions (tap_in_ch all 0; tap_w_off = the partitions' weight blocks) and tap k contracts the channels of
+     * x * A[k] (A: (ntap, mix_v, mix_w)).  mix_l >= the largest number of non-zeros in a column of any A[k] (<= 8). */
+    int32_t mix_v, mix_w, mix_l;
 } kgan_tapconv_desc;
 
 /* Version / diagnostics. */
@@ -131,6 +136,18 @@ int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in, const flo
 int64_t kgan_tapconv_pack_item_bytes(void);
 int kgan_tapconv_pack_tf32_batched(int count, const kgan_tapconv_desc* descs, const float* const* w, float* const* wp, void* items,
                                    int upload, void* stream);
+
+/* Graph convolution as ONE kernel (tgcn.py:61-66: conv1x1 to K*C_out channels, then einsum('nkctv,kvw->nctw'), refolded):
+ *     out[n, oc, t, w] = act( bias[oc] + add[...] + sum_k sum_ic W[k*C_out + oc, ic] * sum_v x[n, ic, t, v] * A[k, v, w] )
+ * The x tile is staged by TMA, the (A (.) edge_importance) product is taken over the non-zeros of A's columns by the operand-building
+ * warps, written tf32-rounded into the swizzled shared-memory operand image, and the K partitions are K taps of one tcgen05 GEMM - the
+ * K*C-channel mixed tensor of kgan_adjmix_fwd + kgan_tapconv_fwd_tf32 never exists.  `d`: see mix_v / mix_w / mix_l; wp: the packed
+ * image of d.  The callers use it where nothing else reads the mixed tensor (no weight gradient will be taken: inference, the critic
+ * pass of the generator update, the interpolate pass of the gradient penalty); kgan_gcn_fused_ok(d) == 1 when eligible.
+ * `omap` (optional): scatter store of the result as in kgan_tapconv_fwd_tf32_scatter (d->p_out_plane = positions of the output plane; `add` NULL). */
+int kgan_gcn_fused_ok(const kgan_tapconv_desc* d);
+int kgan_gcn_fwd_tf32(const kgan_tapconv_desc* d, const float* x, const float* wp, const float* A, const float* bias, const float* add,
+                      const int32_t* omap, float* out, void* stream);
 
 /* Tap convolution stored through a scatter table: the p_out computed positions of a plane go to an output plane of d->p_out_plane
  * positions - position p to omap[3p] and (if >= 0) also to omap[3p + 1]; omap[3p + 2] (if >= 0) is a slot that position keeps ZERO.

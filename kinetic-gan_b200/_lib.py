@@ -23,6 +23,7 @@ class TapConvDesc(C.Structure):
         ("pmap_vec_mask", C.c_int32), ("add_period", C.c_int32), ("act", C.c_int32), ("precision", C.c_int32),
         ("tma_mode", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
         ("p_out_plane", C.c_int32), ("g_pout", C.c_int32), ("stage_span", C.c_int32), ("prefer_staged", C.c_int32),
+        ("mix_v", C.c_int32), ("mix_w", C.c_int32), ("mix_l", C.c_int32),
     ]
 
 
@@ -37,6 +38,8 @@ _SIGS = {
     "kgan_tapconv_pack_item_bytes": ([], C.c_int64),
     "kgan_tapconv_pack_tf32_batched": ([_I, C.POINTER(TapConvDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _F, _I, _V], C.c_int),
     "kgan_tapconv_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _V], C.c_int),
+    "kgan_gcn_fused_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_gcn_fwd_tf32": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_scatter_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_fwd_tf32_scatter": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_res_ok": ([C.POINTER(TapConvDesc), C.POINTER(TapConvDesc)], C.c_int),

@@ -104,6 +104,9 @@ int tapconv_build_eligible(const kgan_tapconv_desc& d);
 int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
                       float* out, cudaStream_t stream);
 
+int gcn_fwd_fused(const kgan_tapconv_desc& d, const float* x, const float* wp, const float* adj, const float* bias, const float* add, float* out,
+                  const int32_t* omap, cudaStream_t stream);   // adjacency product in the operand builder; -1: not eligible
+
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d);
 int tapconv_wgrad_tma_eligible(const kgan_tapconv_desc& d);   // TMA-fed variant (tapconv_wgrad_tma.cu)
 int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,

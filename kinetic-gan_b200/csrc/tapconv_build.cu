@@ -28,6 +28,12 @@
 // stages their whole input planes.  `span` (a launch constant: it is the box extent of the tensor map) comes with the descriptor
 // (kgan_tapconv_desc.stage_span, computed from the position map on the host side).
 //
+// Graph convolution with the adjacency product IN the operand builder (kgan_gcn_fwd_tf32, template MIX): the staged tile holds the
+// block input x itself; for partition k the builders write  xa_k[row (t, w)][c] = sum_j coef_j * x[c][t, v_j]  - the (A (.) edge_importance)
+// product of tgcn.py:66, taken over the few non-zeros of column w of A_k (compacted into shared memory once per CTA) - rounded to tf32,
+// straight into the K-major operand image, and the K partitions are K taps of ONE tcgen05 GEMM: conv1x1 + einsum('nkctv,kvw->nctw') as a
+// single kernel, the K*C-channel mixed tensor never exists in HBM.
+//
 // Warp roles: 0 = raw-tile producer, 1 = MMA issuer / TMEM owner, 2-9 = epilogue, 10-13 = operand builders, 14 = weight loader.
 #include <cuda.h>
 #include <string.h>
@@ -65,6 +71,11 @@ struct BuildPlan {
     int map_row[KGAN_MAX_TAPS];
     int tap_map[KGAN_MAX_TAPS];
     int pm_bytes;                                 // shared-memory copy of the used position-map rows (nmaps x p_out ints), 0: read from global
+    int mix;                                      // 1: adjacency product in the builders (d.mix_v joints -> d.mix_w joints, d.mix_l list entries)
+};
+struct MixItem {
+    int v;                                        // input joint
+    float coef;                                   // A[k, v, w]
 };
 constexpr int BD_MAX_TPP = 32;                    // tiles per plane (planes of up to 4096 positions)
 
@@ -72,8 +83,15 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
 int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle);
 
 static bool make_build_plan(const kgan_tapconv_desc& d, BuildPlan& p) {
+    p.mix = d.mix_v > 0 ? 1 : 0;
+    if (p.mix) {
+        if (d.mix_w <= 0 || d.mix_l <= 0 || d.mix_l > 8 || d.groups != 1 || d.ntap > 4) return false;
+        if (d.p_in % d.mix_v || d.p_out % d.mix_w || d.p_in / d.mix_v != d.p_out / d.mix_w) return false;          // same frames in and out
+        for (int t = 0; t < d.ntap; ++t)
+            if (d.tap_in_ch[t] != 0) return false;                                                                  // every partition reads x itself
+    }
     if (d.stage_span <= 0 || (d.stage_span & 3) || (d.p_in & 3)) return false;      // global strides / box extents: multiples of 16 bytes
-    if (d.p_out_plane != 0 || d.w_oc_blk < 0) return false;
+    if ((d.p_out_plane != 0 && (d.mix_v <= 0 || d.g_pout != 0)) || d.w_oc_blk < 0) return false;      // enlarged output planes: fused gcn + scatter store only
     if (!tapconv_umma_nsplit(d, &p.n_cta, &p.n_split, &p.n_rows, &p.tmem_cols, &p.nkt)) return false;
     p.small = d.p_out <= UM ? 1 : 0;
     if (p.small) {
@@ -139,6 +157,7 @@ static bool make_build_plan(const kgan_tapconv_desc& d, BuildPlan& p) {
     const int b_stage = p.n_cta * UK * 4;
     p.pm_bytes = round_up(p.nmaps * d.p_out * 4, 128);
     if (p.pm_bytes > 32 * 1024) p.pm_bytes = 0;
+    if (p.mix) p.pm_bytes = round_up(d.ntap * d.mix_w * d.mix_l * (int)sizeof(MixItem), 128);      // the region holds the compacted adjacency instead
     int budget = 224 * 1024 - 2048 - p.pm_bytes;
     p.w_res = 0;
     p.w_res_bytes = 0;
@@ -204,10 +223,10 @@ __device__ __forceinline__ BdTile bd_tile(int tile, const BuildPlan& pl) {
     return c;
 }
 
-template <int ACT>
+template <int ACT, bool SCAT = false>
 __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                  const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
-                                                 uint32_t tfull_bar, uint32_t tfull_parity, int rnd) {
+                                                 uint32_t tfull_bar, uint32_t tfull_parity, int rnd, int d1 = 0, int dz = 0) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (BD_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -231,16 +250,25 @@ __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int 
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
-            if (valid && j < nc) *o = tf32_out(val, rnd);
+            if (valid && j < nc) {
+                const float q = tf32_out(val, rnd);
+                *o = q;
+                if (SCAT) {                                        // scatter store (see tapconv_tma.cu): second copy / zero slot, relative to *o
+                    if (d1 != 0) o[d1] = q;
+                    if (dz != 0) o[dz] = 0.f;
+                }
+            }
             o += p_out;
         }
     }
 }
 
+template <bool MIX>
 __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ BuildPlan pl,
                                                                      const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
                                                                      const int32_t* __restrict__ pmap, const float* __restrict__ bias,
-                                                                     const float* __restrict__ add, float* __restrict__ out) {
+                                                                     const float* __restrict__ add, float* __restrict__ out,
+                                                                     const float* __restrict__ adj, const int32_t* __restrict__ omap) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
@@ -285,13 +313,27 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
     }
     // once per CTA: the used position-map rows -> shared memory, and from them the first staged position of every (channel block,
     // tile of the plane): min over the tile's rows and the block's taps, rounded down to a 16-byte boundary
-    if (pl.pm_bytes) {
+    if (MIX) {
+        // compacted adjacency: for (partition k, output joint w) the non-zeros of column w of A_k, padded with zero coefficients to mix_l
+        MixItem* mt = reinterpret_cast<MixItem*>(pm_s);
+        for (int e = threadIdx.x; e < d.ntap * d.mix_w; e += blockDim.x) {
+            const int k = e / d.mix_w, w = e - k * d.mix_w;
+            int cnt = 0;
+            for (int v = 0; v < d.mix_v && cnt < d.mix_l; ++v) {
+                const float a = __ldg(adj + ((int64_t)k * d.mix_v + v) * d.mix_w + w);
+                if (a != 0.f) mt[e * d.mix_l + cnt++] = MixItem{v, a};
+            }
+            for (; cnt < d.mix_l; ++cnt) mt[e * d.mix_l + cnt] = MixItem{0, 0.f};
+        }
+        if (!pl.small)                                                // first staged position of tile tp: its first frame, 16-byte aligned
+            for (int tp = threadIdx.x; tp < pl.tpp; tp += blockDim.x) lo_tab[tp] = ((tp * UM) / d.mix_w * d.mix_v) & ~3;
+    } else if (pl.pm_bytes) {
         for (int i = threadIdx.x; i < pl.nmaps * d.p_out; i += blockDim.x) {
             const int m = i / d.p_out;
             pm_s[i] = __ldg(pmap + (int64_t)pl.map_row[m] * d.p_out + (i - m * d.p_out));
         }
     }
-    if (!pl.small) {
+    if (!MIX && !pl.small) {
         for (int e = warp; e < pl.ncb * pl.tpp; e += BD_THREADS / 32) {
             const int cb = e / pl.tpp, tp = e - cb * pl.tpp;
             const int row0 = tp * UM, nrows = min(UM, d.p_out - row0);
@@ -459,7 +501,12 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
             int srcs[BD_ROW_CACHE];
 #pragma unroll
             for (int m = 0; m < BD_ROW_CACHE; ++m)
-                srcs[m] = (valid && m < pl.nmaps) ? (pl.pm_bytes ? pm_s[m * d.p_out + p] : __ldg(pmap + (int64_t)pl.map_row[m] * d.p_out + p)) : -1;
+                srcs[m] = (!MIX && valid && m < pl.nmaps) ? (pl.pm_bytes ? pm_s[m * d.p_out + p] : __ldg(pmap + (int64_t)pl.map_row[m] * d.p_out + p)) : -1;
+            int mix_t = 0, mix_w = 0;                                 // MIX: this row's frame and output joint
+            if (MIX) {
+                mix_t = p / d.mix_w;
+                mix_w = p - mix_t * d.mix_w;
+            }
             for (int ict = 0; ict < pl.nkt; ++ict) {
                 const int kvalid = min(UK, d.ck - ict * UK);          // channels of this tile that belong to the contraction
                 for (int cb = 0; cb < pl.ncb; ++cb) {
@@ -468,6 +515,47 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
                     const int lo = raw_lo[r];
                     for (int k = pl.cb_beg[cb]; k < pl.cb_beg[cb + 1]; ++k) {
                         const int tap = pl.order[k];
+                        if (MIX) {
+                            // xa_k[row][c] = sum_j coef_j * x[c][frame, v_j]: the adjacency product of partition `tap`, built into the operand image
+                            const MixItem* mt = reinterpret_cast<const MixItem*>(pm_s) + (tap * d.mix_w + mix_w) * d.mix_l;
+                            const uint32_t cs4 = 4u * (uint32_t)pl.chan_stride;
+                            const int fbase = mix_t * d.mix_v - lo;       // offset of this row's frame inside the staged range
+                            float acc[UK];
+#pragma unroll
+                            for (int c = 0; c < UK; ++c) acc[c] = 0.f;
+                            for (int j = 0; j < d.mix_l; ++j) {
+                                const MixItem it = mt[j];
+                                const int off = fbase + it.v;
+                                const bool ok = valid && it.coef != 0.f && off >= 0 && off < pl.nbox * pl.bspan;
+                                const int bx = (pl.nbox == 2 && off >= pl.bspan) ? 1 : 0;
+                                const uint32_t rp = raw + 4u * (uint32_t)(ok ? bx * pl.box_floats + seg * pl.bspan + (off - bx * pl.bspan) : 0);
+                                const float cf = ok ? it.coef : 0.f;
+                                float xv[UK];
+#pragma unroll
+                                for (int c = 0; c < UK; ++c) xv[c] = bd_lds(rp + (uint32_t)c * cs4);
+#pragma unroll
+                                for (int c = 0; c < UK; ++c) acc[c] = fmaf(cf, xv[c], acc[c]);
+                            }
+                            mbar_wait(empty0 + 8 * s, sph);
+                            const uint32_t dst = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + row_off;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                uint32_t v[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[e] = (4 * q + e) < kvalid ? to_tf32_fast(acc[4 * q + e]) : 0u;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)q ^ row_x) << 4)), "r"(v[0]), "r"(v[1]),
+                                             "r"(v[2]), "r"(v[3])
+                                             : "memory");
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(full0 + 8 * s);
+                            if (++s == S) {
+                                s = 0;
+                                sph ^= 1u;
+                            }
+                            continue;
+                        }
                         const int m = pl.tap_map[tap];
                         int src = -1;
                         if (m < BD_ROW_CACHE) {
@@ -544,9 +632,17 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
                 pv = (tc.mt - nn * pl.tpp) * UM + row;
                 valid = pv < d.p_out;
             }
-            const int po = valid ? pv : 0, nv = valid ? nn : 0;
+            int po = valid ? pv : 0;
+            const int nv = valid ? nn : 0;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
-            const int pst = d.p_out;
+            const int pst = omap ? d.p_out_plane : d.p_out;
+            int d1 = 0, dz = 0;
+            if (omap) {                                               // scatter store: destinations of source position po inside the output plane
+                const int q0 = __ldg(omap + 3 * po), q1 = __ldg(omap + 3 * po + 1), q2 = __ldg(omap + 3 * po + 2);
+                d1 = q1 >= 0 ? q1 - q0 : 0;
+                dz = q2 >= 0 ? q2 - q0 : 0;
+                po = q0;
+            }
             float* op = out + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * pst + po;
             const int64_t astride = d.add_period ? d.add_period : pst;
             const float* ap = add ? add + ((int64_t)nv * d.c_out_total + out_ch0 + oc_base) * astride + (d.add_period ? po % d.add_period : po)
@@ -558,7 +654,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
             if (16 * colpar >= ncols) {                               // no columns for this warp: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            } else if (d.act == KGAN_ACT_LRELU) bd_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
+            } else if (omap) bd_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, d1, dz);
+            else if (d.act == KGAN_ACT_LRELU) bd_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
             else if (d.act == KGAN_ACT_TANH) bd_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
             else bd_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -578,22 +675,42 @@ int tapconv_build_eligible(const kgan_tapconv_desc& d) {
     return make_build_plan(d, p) ? 1 : 0;
 }
 
-// -1: not eligible (the caller goes on to the TMA-fed / gather kernels)
-int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
-                      float* out, cudaStream_t stream) {
-    BuildPlan p;
-    if (!make_build_plan(d, p)) return -1;
-    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+static int launch_build(const kgan_tapconv_desc& d, BuildPlan& p, const float* in, const float* wp, const int32_t* pmap, const float* bias,
+                        const float* add, float* out, const float* adj, cudaStream_t stream, const int32_t* omap = nullptr) {
     CUtensorMap tmap;
     const uint64_t gdim[3] = {(uint64_t)d.p_in, (uint64_t)d.n, (uint64_t)d.c_in_total};
     const uint64_t gstr[2] = {(uint64_t)d.c_in_total * d.p_in * 4, (uint64_t)d.p_in * 4};
     const uint32_t box[3] = {(uint32_t)p.bspan, (uint32_t)p.nseg, 32u};
     if (int e = tma_encode_3d_f32(&tmap, in, gdim, gstr, box, 4)) return e;
-    static SmemAttrOnce attr;
-    if (int e = ensure_smem(tapconv_fwd_build_k, 227 * 1024, attr, "tapconv_fwd_build attribute")) return e;
+    static SmemAttrOnce attr0, attr1;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_build_k<<<grid, BD_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, pmap, bias, add, out);
+    if (p.mix) {
+        if (int e = ensure_smem(tapconv_fwd_build_k<true>, 227 * 1024, attr1, "gcn_fwd attribute")) return e;
+        tapconv_fwd_build_k<true><<<grid, BD_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, pmap, bias, add, out, adj, omap);
+    } else {
+        if (int e = ensure_smem(tapconv_fwd_build_k<false>, 227 * 1024, attr0, "tapconv_fwd_build attribute")) return e;
+        tapconv_fwd_build_k<false><<<grid, BD_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, pmap, bias, add, out, adj, omap);
+    }
     return check_launch("tapconv_fwd_build");
+}
+
+// Graph convolution with the adjacency product inside the GEMM's operand builder (see the head of this file); -1: not eligible
+int gcn_fwd_fused(const kgan_tapconv_desc& d, const float* x, const float* wp, const float* adj, const float* bias, const float* add, float* out,
+                  const int32_t* omap, cudaStream_t stream) {
+    BuildPlan p;
+    if (d.mix_v <= 0 || !make_build_plan(d, p)) return -1;
+    if ((d.p_out_plane != 0) != (omap != nullptr) || (omap && add)) return -1;      // enlarged output planes <=> scatter store (no `add` then)
+    if (reinterpret_cast<uintptr_t>(x) & 15) return -1;
+    return launch_build(d, p, x, wp, nullptr, bias, add, out, adj, stream, omap);
+}
+
+// -1: not eligible (the caller goes on to the TMA-fed / gather kernels)
+int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                      float* out, cudaStream_t stream) {
+    BuildPlan p;
+    if (d.mix_v > 0 || !make_build_plan(d, p)) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    return launch_build(d, p, in, wp, pmap, bias, add, out, nullptr, stream);
 }
 
 }  // namespace kgan

@@ -407,6 +407,23 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     return r;
 }
 
+extern "C" int kgan_gcn_fused_ok(const kgan_tapconv_desc* d) {
+    if (validate(d) || d->mix_v <= 0) return 0;
+    return tapconv_tf32_packed_numel(*d) > 0 && tapconv_build_eligible(*d);
+}
+
+extern "C" int kgan_gcn_fwd_tf32(const kgan_tapconv_desc* d, const float* x, const float* wp, const float* A, const float* bias, const float* add,
+                                 const int32_t* omap, float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(x && wp && A && out, "gcn_fwd_tf32: null pointer");
+    const int r = gcn_fwd_fused(*d, x, wp, A, bias, add, out, omap, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("gcn_fwd_tf32: not eligible (kgan_gcn_fused_ok() == 0)");
+        return 1;
+    }
+    return r;
+}
+
 extern "C" int kgan_tapconv_scatter_ok(const kgan_tapconv_desc* d) {
     if (validate(d) || tapconv_is_thin(*d) || tapconv_tf32_packed_numel(*d) <= 0) return 0;
     return tapconv_tma_scatter_eligible(*d);

@@ -82,6 +82,29 @@ def _wgrad(x, go, geom, w):
     return TapConvWgrad.apply(x, go, geom, w.shape)
 
 
+# Forward passes whose weight gradients will never be asked for (inference, a frozen critic, the interpolate pass of the gradient penalty -
+# its forward nodes hang off the second-order graph only through LeakyReLU slopes): the graph conv may then run as ONE kernel with the
+# adjacency product inside the GEMM (ops.gcn_fused_fwd) instead of materialising the mixed tensor that only a weight gradient would read.
+# If a weight gradient is asked for after all, the backward recomputes the mixed tensor: correct, merely slower.
+_no_wgrad_hint = False
+
+
+class no_weight_grads_expected:
+    def __enter__(self):
+        global _no_wgrad_hint
+        self.prev, _no_wgrad_hint = _no_wgrad_hint, True
+
+    def __exit__(self, *exc):
+        global _no_wgrad_hint
+        _no_wgrad_hint = self.prev
+
+
+def wants_fused_gcn(weight):
+    """True where a graph conv's mixed tensor would have no reader: no autograd graph is being recorded, the weight is frozen, or the
+    caller declared the pass free of weight gradients (no_weight_grads_expected)."""
+    return _no_wgrad_hint or not torch.is_grad_enabled() or not weight.requires_grad
+
+
 _SUM_T = {}
 
 
@@ -310,7 +333,7 @@ class GcnRes(Function):
     first-order sweep and recomputed as graph nodes when the sweep itself is recorded (create_graph)."""
 
     @staticmethod
-    def forward(ctx, x, A, w_gcn, w_res, b_res, gcn_geom, res_geom, sel, support, mask_input, out_table=None):
+    def forward(ctx, x, A, w_gcn, w_res, b_res, gcn_geom, res_geom, sel, support, mask_input, out_table=None, fused_geom=None):
         """`out_table` (optional PlaneTable): g is returned gathered through it - the time-unfolded layout a strided temporal conv
         reads (geometry.UnfoldedTcnGeom.unfold); where the table is a pure gather the graph conv's epilogue stores that layout
         directly (ops.tapconv_fwd_scatter), otherwise a gather kernel follows."""
@@ -318,14 +341,20 @@ class GcnRes(Function):
         ctx.gcn_geom, ctx.res_geom, ctx.sel, ctx.support, ctx.mask_input = gcn_geom, res_geom, sel, support, mask_input
         ctx.out_table = out_table
         x, A = _c(x), _c(A)
-        xa = ops.adjmix_fwd(x, A)
-        g = None
-        if out_table is not None:
-            g = ops.tapconv_fwd_scatter(xa, _c(w_gcn), gcn_geom.fwd, out_table)
+        g = xa = None
+        # `fused_geom` (optional geometry.GcnFusedGeom): where no weight gradient is expected (frozen / no_grad / hinted pass) the whole
+        # graph conv is one kernel with the adjacency product inside the GEMM, and the mixed tensor is not materialised
+        # (the caller decides - grad mode is always off INSIDE a Function's forward - and passes fused_geom only then: wants_fused_gcn())
+        if fused_geom is not None:
+            g = ops.gcn_fused_fwd(x, A, _c(w_gcn), fused_geom, out_table)
         if g is None:
-            g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
+            xa = ops.adjmix_fwd(x, A)
             if out_table is not None:
-                g = ops.plane_spmm(g, out_table)
+                g = ops.tapconv_fwd_scatter(xa, _c(w_gcn), gcn_geom.fwd, out_table)
+            if g is None:
+                g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
+                if out_table is not None:
+                    g = ops.plane_spmm(g, out_table)
         xs = x if sel is None else ops.plane_spmm(x, sel)
         r = ops.tapconv_fwd(xs, _c(w_res), res_geom.fwd, b_res) if w_res is not None else xs
         ctx.save_for_backward(x, A, w_gcn, w_res)
@@ -360,7 +389,7 @@ class GcnRes(Function):
             if ctx.out_table is not None:
                 gg = PlaneSpmm.apply(gg, ctx.out_table.T)        # fold the gathered layout back (sum of the copies)
             if _want(ctx, 2):
-                xa = ctx.xa if not recorded else AdjMix.apply(x, A, ctx.support)
+                xa = AdjMix.apply(x, A, ctx.support) if (recorded or ctx.xa is None) else ctx.xa     # (fused forward: recomputed on demand)
                 gw_gcn = _wgrad(xa, gg, ctx.gcn_geom, w_gcn)
             if nig[0] or _want(ctx, 1):
                 g_xa = TapConvDgrad.apply(gg, w_gcn, ctx.gcn_geom)
@@ -368,7 +397,7 @@ class GcnRes(Function):
                 gx = AdjMixDx.apply(g_xa, A, ctx.support, gx_r, mask) if nig[0] else None
         elif gx_r is not None:
             gx = ActGrad.apply(gx_r, x, ACT_LRELU) if ctx.mask_input else gx_r
-        return (gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None, None)[:len(nig)]
+        return (gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None, None, None)[:len(nig)]
 
 
 # ------------------------------------------------------------------------------------------------

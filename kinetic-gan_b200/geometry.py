@@ -124,7 +124,8 @@ class TapDesc:
             for i in range(self.ntap):
                 s.tap_shift[i] = self.tap_shift[i]
             s.p_out_plane, s.g_pout = (out_plane, 0) if out_plane else (getattr(self, "p_out_plane", 0), getattr(self, "g_pout", 0))
-            s.stage_span, s.prefer_staged = (0, 0) if s.p_out_plane else (self.stage_span, self.prefer_staged)
+            s.mix_v, s.mix_w, s.mix_l = getattr(self, "mix", (0, 0, 0))
+            s.stage_span, s.prefer_staged = (0, 0) if (s.p_out_plane and not s.mix_v) else (self.stage_span, self.prefer_staged)
             self._structs[key] = s
         return s
 
@@ -183,6 +184,32 @@ class TapConvGeom:
             groups=K, g_in=0, g_out=c_in, g_w=c_out * w_cin * kt, w_oc=kt, w_ic=w_cin * kt,
             tap_in_ch=[0] * len(live), tap_w_off=[w_ic0 * kt + dt for dt in live], tap_row=list(live), pmap=inv, t_out=t_in,
             v_out=v_in)
+
+
+class GcnFusedGeom:
+    """The graph convolution of tgcn.py:61-66 as ONE kernel (include/kgan.h kgan_gcn_fwd_tf32): x (N, C_in, T, V) and the effective adjacency
+    A (K, V, W) in, (N, C_out, T, W) out; the adjacency product is taken inside the GEMM's operand builder.  `nnz_max`: the largest number
+    of non-zeros in a column of any partition of the (constant) base adjacency."""
+
+    def __init__(self, c_in, c_out, t, v, w, K, nnz_max):
+        self.c_in, self.c_out, self.t, self.v, self.w, self.K = c_in, c_out, t, v, w, K
+        p_in, p_out = t * v, t * w
+        if p_out <= 128:
+            span = p_in
+        else:
+            span = 4
+            for r0 in range(0, p_out, 128):
+                t0, t1 = r0 // w, (min(r0 + 128, p_out) - 1) // w
+                span = max(span, (t1 + 1) * v - ((t0 * v) & ~3))
+        span = (span + 3) // 4 * 4
+        ok = p_in % 4 == 0 and span <= 512 and 1 <= nnz_max <= 8
+        self.fwd = TapDesc(
+            c_in_total=c_in, p_in=p_in, c_out_total=c_out, p_out=p_out, ntap=K, ck=c_in, co=c_out, groups=1, g_in=0, g_out=0, g_w=0,
+            w_oc=c_in, w_ic=1, tap_in_ch=[0] * K, tap_w_off=[k * c_out * c_in for k in range(K)], tap_row=[0] * K,
+            pmap=np.zeros((1, p_out), np.int32), t_out=t, v_out=w)
+        self.fwd.tma_mode, self.fwd.stage_span, self.fwd.prefer_staged = 0, (span if ok else 0), 0
+        self.fwd.mix = (v, w, int(nnz_max)) if ok else (0, 0, 0)
+        self.fwd._structs.clear()
 
 
 class UnfoldedTcnGeom:

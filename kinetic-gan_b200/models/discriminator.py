@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as KF
-from ..geometry import TapConvGeom, UnfoldedTcnGeom, mean_table, nearest_src, select_table
+from ..geometry import GcnFusedGeom, TapConvGeom, UnfoldedTcnGeom, mean_table, nearest_src, select_table
 from .init_gan.graph_h36m import Graph_h36m
 from .init_gan.graph_ntu import graph_ntu
 from .init_gan.tgcn import ConvTemporalGraphical
@@ -223,7 +223,8 @@ class st_gcn(nn.Module):
             # (the joint node hands on the - selected - block input `r`; a residual CONV runs inside the temporal conv's kernel below)
             # ... and, in front of a strided temporal conv, stores the graph conv's result directly in the time-unfolded layout that conv reads
             g, r = KF.GcnRes.apply(x, A, self.gcn.conv.weight, None, None, self.gcn._geom(x.size(2), A.size(2)), None, sel, support, mask_input,
-                                   tcn.unfold if isinstance(tcn, UnfoldedTcnGeom) else None)
+                                   tcn.unfold if isinstance(tcn, UnfoldedTcnGeom) else None,
+                                   self._fused_geom(x.size(2), x.size(3), A.size(2), support) if KF.wants_fused_gcn(self.gcn.conv.weight) else None)
         if self._res == "none" and isinstance(tcn, UnfoldedTcnGeom):
             g = KF.PlaneSpmm.apply(g, tcn.unfold)
         if self._res == "conv":
@@ -232,6 +233,15 @@ class st_gcn(nn.Module):
         else:
             x = KF.TapConvEp.apply(g, self.tcn.weight, self.tcn.bias, r, tcn, KF.ACT_LRELU, act_bwd)
         return x, A_in
+
+    def _fused_geom(self, T, Vx, W, support):
+        """One-kernel graph conv (adjacency product inside the GEMM, geometry.GcnFusedGeom) for passes without weight gradients."""
+        key = ("fused", T, Vx, W)
+        g = self._plans.get(key)
+        if g is None:
+            nnz = int((support != 0).sum(1).max().item())
+            g = self._plans[key] = GcnFusedGeom(self.gcn.conv.in_channels, self.tcn.out_channels, T, Vx, W, self.gcn.kernel_size, max(nnz, 1))
+        return g
 
     def downsample_s(self, tensor):
         """Kept for API parity (discriminator.py:139-142); the forward pass folds it into the adjacency."""

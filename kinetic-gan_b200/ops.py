@@ -278,6 +278,36 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
     return out
 
 
+def gcn_fused_fwd(x, A, w, fused, table=None):
+    """tapconv_fwd(adjmix_fwd(x, A), w) - the refolded graph convolution of tgcn.py:61-66 - as ONE kernel (kgan_gcn_fwd_tf32): the adjacency
+    product is taken in shared memory by the GEMM's operand builders, the K*C-channel mixed tensor is never written.  `fused`: a
+    geometry.GcnFusedGeom; `table` (optional pure-gather PlaneTable): the result is stored through it (see tapconv_fwd_scatter).
+    Returns None when not eligible (fp32 mode, shapes outside the staged plan)."""
+    if _precision != PREC_TF32 or fused.fwd.mix[0] == 0 or (table is not None and table.scatter_map() is None):
+        return None
+    _chk(x, A, w)
+    desc = fused.fwd
+    n = x.shape[0]
+    assert x.shape[1] == desc.c_in_total and x.shape[2] * x.shape[3] == desc.p_in and tuple(A.shape) == (desc.ntap, desc.mix[0], desc.mix[1])
+    l = _lib.lib()
+    cs = desc.cstruct(n, ACT_NONE, _precision, 0, 0 if table is None else table.p_out)
+    ok = desc.__dict__.setdefault("_fused_ok", {})
+    key = (n, 0 if table is None else table.p_out)
+    if key not in ok:
+        ok[key] = bool(l.kgan_gcn_fused_ok(cs))
+    if not ok[key]:
+        return None
+    wp = _packed_weights(w, desc, desc.cstruct(n, ACT_NONE, _precision), l)
+    if wp is None:
+        return None
+    shape = (n, desc.c_out_total, desc.t_out, desc.v_out) if table is None else (n, desc.c_out_total, table.t_out, table.v_out)
+    out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    _io(x, A, w, out)
+    _run('gcn_fused_tf32', _tap_flops(desc, n), l.kgan_gcn_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(), A.data_ptr(), 0, 0,
+         0 if table is None else table.scatter_on(x.device).data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def tapconv_fwd_scatter(x, w, desc, table):
     """plane_spmm(tapconv_fwd(x, w, desc), table) for a pure-gather `table` (geometry.PlaneTable.scatter_map) in ONE launch: the
     convolution's epilogue stores every result at its (one or two) positions of the gathered layout and zero-fills the empty slots

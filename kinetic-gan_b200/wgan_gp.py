@@ -24,7 +24,10 @@ def compute_gradient_penalty(D, real_samples, fake_samples, labels, alpha=None, 
         alpha = torch.as_tensor(np.random.random((n, 1, 1, 1)), dtype=real_samples.dtype, device=real_samples.device)
     interpolates = ops.interpolate(alpha.reshape(n).contiguous(), real_samples.contiguous(),
                                    fake_samples.contiguous()).requires_grad_(True)
-    d_interpolates = D(interpolates, labels)
+    # the forward nodes of this pass receive no weight gradients from the step (they hang off the second-order graph only through LeakyReLU
+    # slopes): its graph convs may run as single kernels with the adjacency product inside the GEMM (functional.no_weight_grads_expected)
+    with functional.no_weight_grads_expected():
+        d_interpolates = D(interpolates, labels)
     fake = torch.ones(n, 1, dtype=real_samples.dtype, device=real_samples.device)
     # only d/d(interpolates) is asked for: skip the weight / bias / adjacency gradients every node would otherwise compute
     # for the engine to drop (functional.data_grads_only); the graph built here still depends on all parameters

@@ -62,6 +62,14 @@ def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=0):
     return tapconv_fwd(x, w, desc, bias, tapconv_fwd(x2, w2, desc2, bias2), act)
 
 
+def gcn_fused_fwd(x, A, w, fused, table=None):
+    return None          # the emulation always takes the two-kernel formulation (same arithmetic)
+
+
+def tapconv_fwd_scatter(x, w, desc, table):
+    return None
+
+
 def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     if out is not None:                       # accumulate into the caller's buffer (kgan_tapconv_wgrad `accumulate`)
         with torch.no_grad():
@@ -191,7 +199,7 @@ def interpolate(alpha, x, y):
     return a * x + (1 - a) * y
 
 
-NAMES = ["tapconv_fwd", "tapconv_fwd_res", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
+NAMES = ["tapconv_fwd", "tapconv_fwd_res", "gcn_fused_fwd", "tapconv_fwd_scatter", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
          "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_bwd", "adam_step",
          "interpolate"]
 

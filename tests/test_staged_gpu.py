@@ -94,3 +94,55 @@ def test_staged_rounds_unrounded_inputs_to_nearest():
     got = ops.tapconv_fwd(x.cuda(), w.cuda(), geom.fwd)
     want = emu.tapconv_fwd(rn(x).double(), rn(w).double(), geom.fwd)
     assert rel(got, want) < 2.5e-4      # only the rounding of the stored output (2^-11 / sqrt(3)) is left
+
+
+@pytest.mark.parametrize("c_in,c_out,t,v,w,n", [(32, 64, 64, 12, 12, 5), (64, 128, 64, 12, 5, 5), (128, 256, 32, 5, 5, 7), (256, 512, 16, 5, 1, 40),
+                                                (512, 512, 8, 1, 1, 70), (32, 64, 64, 11, 11, 4), (24, 40, 16, 25, 11, 9)])
+def test_gcn_with_adjacency_product_inside_the_gemm(c_in, c_out, t, v, w, n):
+    """kgan_gcn_fwd_tf32 (conv1x1 + einsum('nkctv,kvw->nctw') of tgcn.py:61-66 as ONE kernel, the A (.) importance product taken in shared
+    memory by the operand builders) against the fp64 statement and against the two-kernel formulation it replaces."""
+    gen = torch.Generator().manual_seed(3)
+    K = 3
+    A = torch.zeros(K, v, w)
+    for k in range(K):                                        # skeleton-like sparsity: 1-3 non-zeros per column
+        for col in range(w):
+            for _ in range(1 + (k + col) % 3):
+                A[k, int(torch.randint(0, v, (1,), generator=gen)), col] = float(torch.rand(1, generator=gen)) + 0.1
+    nnz = int((A != 0).sum(1).max())
+    fused = G.GcnFusedGeom(c_in, c_out, t, v, w, K, nnz)
+    two = G.TapConvGeom(c_in, c_out, t, w, K=K)
+    x = rnd(n, c_in, t, v, seed=1)
+    wt = rnd(K * c_out, c_in, 1, 1, seed=2) / np.sqrt(K * c_in)
+    got = ops.gcn_fused_fwd(x.cuda(), A.cuda(), wt.cuda(), fused)
+    assert got is not None
+    want = emu.tapconv_fwd(emu.adjmix_fwd(x.double(), A.double()), wt.double(), two.fwd)
+    assert rel(got, want) < TOL
+    sep = ops.tapconv_fwd(ops.adjmix_fwd(x.cuda(), A.cuda()), wt.cuda(), two.fwd)
+    assert rel(got, sep.cpu()) < 5e-4
+    # exact on tf32-representable data
+    xi = torch.randint(-3, 4, x.shape, generator=gen).float()
+    Ai = (A != 0).float() * 2
+    wi = torch.randint(-2, 3, wt.shape, generator=gen).float()
+    assert torch.equal(ops.gcn_fused_fwd(xi.cuda(), Ai.cuda(), wi.cuda(), fused).cpu().double(),
+                       emu.tapconv_fwd(emu.adjmix_fwd(xi.double(), Ai.double()), wi.double(), two.fwd))
+
+
+@pytest.mark.parametrize("c_in,c_out,t,v,w,n", [(64, 128, 64, 12, 5, 5), (128, 256, 32, 5, 5, 7), (256, 512, 16, 5, 1, 40)])
+def test_fused_gcn_with_scatter_store(c_in, c_out, t, v, w, n):
+    """The one-kernel graph conv writing its result directly in the time-unfolded layout of the following stride-2 temporal conv
+    == adjacency kernel + tap convolution + gather kernel."""
+    gen = torch.Generator().manual_seed(4)
+    A = (torch.rand(3, v, w, generator=gen) < 0.25).float() * torch.rand(3, v, w, generator=gen)
+    A[:, 0, :] += 0.5
+    nnz = int((A != 0).sum(1).max())
+    fused = G.GcnFusedGeom(c_in, c_out, t, v, w, 3, nnz)
+    two = G.TapConvGeom(c_in, c_out, t, w, K=3)
+    unf = G.UnfoldedTcnGeom(c_out, c_out, t, w, 3, 1, 1, 1, list(range(0, t, 2))).unfold
+    x = rnd(n, c_in, t, v, seed=1)
+    wt = rnd(3 * c_out, c_in, 1, 1, seed=2) / np.sqrt(3 * c_in)
+    poison = torch.full((n, c_out, unf.t_out, unf.v_out), float("nan"), device="cuda")
+    del poison
+    got = ops.gcn_fused_fwd(x.cuda(), A.cuda(), wt.cuda(), fused, unf)
+    assert got is not None
+    want = emu.plane_spmm(emu.tapconv_fwd(emu.adjmix_fwd(x.double(), A.double()), wt.double(), two.fwd), unf)
+    assert rel(got, want) < TOL
