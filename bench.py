@@ -39,7 +39,7 @@ FLOP_PER_SAMPLE = 1.6 * F_G + 10.4 * F_D
 WORKLOAD = SHAPE["name"] + ", WGAN-GP training, n_critic=5"
 GEN_WORKLOAD = "generate.py generator pass, " + SHAPE["name"] + ", eval mode, no_grad"
 TRAFFIC_BATCH, TRAFFIC_SHAPE = None, None      # configuration of THIS run (set in __main__): a capture of another one is not attached
-TRAFFIC_FILE = "r1_traffic_b1024.json"        # ncu DRAM-traffic capture of the training step (generate: r1_traffic_generate.json)
+TRAFFIC_FILE = "r2_traffic_b4096.json"        # ncu DRAM-traffic capture of the training step (generate: r2_traffic_generate.json)
 NCU_RANGE = os.environ.get("KGAN_NCU_RANGE") == "1"   # bracket the eager roofline pass with cudaProfilerStart/Stop (ncu --profile-from-start off)
 
 
@@ -86,7 +86,7 @@ def parse():
     ap.add_argument("--workload", default="train", choices=["train", "generate", "tf32-deviation"],
                     help="train: WGAN-GP training samples/s (headline); generate: inference-only generated sequences/s (BASELINE.json configs[4])")
     ap.add_argument("--shape", default="ntu120", choices=list(SHAPES), help="network / data shape (BASELINE.json configs); headline: ntu120")
-    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 1024 for train, 4096 for generate)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 for train and for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--trunc-cached", action="store_true", help="generate: estimate the W-space mean once (GeneratorRunner cache_mean) instead of per call")
     ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
@@ -441,6 +441,7 @@ def run_kgan(args):
     it += 5
     roofline = make_roofline(fam, sites, 5, FLOP_PER_SAMPLE * value / 1e12 / comm.world_size)
 
+    hbm_peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9      # activations of one step + graphs' pools + parameters
     # release the training state before the other legs (the generate measurement and the reference on the same GPU need the memory)
     del tr, G, D, resident
     kgan.ops._persist.clear()
@@ -460,7 +461,7 @@ def run_kgan(args):
         if not args.no_cpu_baseline:
             cpu = cpu_baseline_leg("train", args.shape, args.cpu_batch)
         if not args.no_gpu_reference and reference_kind() == "reference":
-            gpu_ref = gpu_reference_leg("train", args.shape, B)
+            gpu_ref = gpu_reference_leg("train", args.shape, min(B, 1024))     # (its per-sample mapping loop is O(N^2): 1024 keeps the leg short)
 
     if comm.rank == 0:
         line = {
@@ -470,10 +471,12 @@ def run_kgan(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size,
                        "parallelism": "dp%d" % comm.world_size, "n_critic": 5, "flop_per_sample": FLOP_PER_SAMPLE,
                        "cuda_graphs": graphs,
+                       "batch_note": "throughput vs per-GPU batch on this GPU (profiles/r2_batch_sweep.txt): 1024: 55.9k, 2048: 61.4k, 4096: 65.7k, "
+                                     "6144: 66.6k samples/s; 38 GB of HBM at 4096",
                        "l2_policy": "per-step working set (activations of 4 critic passes at batch %d, >1 GB) exceeds the 126 MB L2; "
                                     "inputs rotate over a pool of %d batches" % (B, POOL)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "gpu_reference": gpu_ref, "secondary": secondary,
+            "gpu_reference": gpu_ref, "secondary": secondary, "hbm_peak_gb": hbm_peak_gb,
         }
         emit(json.dumps(line))
     comm.close()
@@ -637,7 +640,7 @@ def measure_generate(args, comm, dev):
         e2e = {"value": B * comm.world_size * K / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": out.numel() * out.element_size()}
     global TRAFFIC_FILE
-    TRAFFIC_FILE = "r1_traffic_generate.json"
+    TRAFFIC_FILE = "r2_traffic_generate.json"
     runner.graphs = False
     if NCU_RANGE:
         torch.cuda.synchronize()
@@ -674,7 +677,7 @@ if __name__ == "__main__":
     quiet_stdout()
     set_shape(a.shape)
     if a.batch is None:
-        a.batch = 1024 if a.workload == "train" else 4096
+        a.batch = 4096
     TRAFFIC_BATCH, TRAFFIC_SHAPE = a.batch, a.shape
     if a.workload == "tf32-deviation":
         run_tf32_deviation(a)
