@@ -235,13 +235,19 @@ class st_gcn(nn.Module):
         return x, A_in
 
     def _fused_geom(self, T, Vx, W, support):
-        """One-kernel graph conv (adjacency product inside the GEMM, geometry.GcnFusedGeom) for passes without weight gradients."""
+        """One-kernel graph conv (adjacency product inside the GEMM, geometry.GcnFusedGeom) for passes without weight gradients.
+        Used where its 128-row tiles are full - output planes that are a multiple of 128 positions, or small planes tiled by whole
+        samples; on planes like 160 or 320 positions the last tile of every plane is mostly padding and the two-kernel formulation
+        measured faster (profiles/r2_gcn_fused_ab.txt): None there."""
         key = ("fused", T, Vx, W)
-        g = self._plans.get(key)
-        if g is None:
-            nnz = int((support != 0).sum(1).max().item())
-            g = self._plans[key] = GcnFusedGeom(self.gcn.conv.in_channels, self.tcn.out_channels, T, Vx, W, self.gcn.kernel_size, max(nnz, 1))
-        return g
+        if key not in self._plans:
+            p_out = T * W
+            g = None
+            if p_out % 128 == 0 or p_out <= 128:
+                nnz = int((support != 0).sum(1).max().item())
+                g = GcnFusedGeom(self.gcn.conv.in_channels, self.tcn.out_channels, T, Vx, W, self.gcn.kernel_size, max(nnz, 1))
+            self._plans[key] = g
+        return self._plans[key]
 
     def downsample_s(self, tensor):
         """Kept for API parity (discriminator.py:139-142); the forward pass folds it into the adjacency."""
