@@ -89,7 +89,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 for train and for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--trunc-cached", action="store_true", help="generate: estimate the W-space mean once (GeneratorRunner cache_mean) instead of per call")
-    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "fp32x3", "tf32"],
+                    help="tf32: headline mode; fp32x3: fp32-accurate tensor-core mode (3xTF32 split in the TMA-fed kernels); fp32: FMA kernels only")
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

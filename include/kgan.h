@@ -32,7 +32,15 @@ extern "C" {
 #define KGAN_MAX_TAPS 16
 
 enum { KGAN_ACT_NONE = 0, KGAN_ACT_LRELU = 1 /* slope 0.2 */, KGAN_ACT_TANH = 2 };
-enum { KGAN_PREC_FP32 = 0 /* SIMT fp32 FMA */, KGAN_PREC_TF32 = 1 /* tcgen05 kind::tf32, fp32 accumulate */ };
+enum {
+    KGAN_PREC_FP32 = 0,   /* SIMT fp32 FMA */
+    KGAN_PREC_TF32 = 1,   /* tcgen05 kind::tf32, fp32 accumulate, operands rounded to tf32 */
+    KGAN_PREC_TF32X3 = 2  /* fp32-accurate tensor-core mode: every operand is split x = hi + lo inside the kernel (hi = the 19 bits the
+                             tensor core reads, lo = x - hi, exact) and the product is taken as hi*hi + lo*hi + hi*lo on
+                             tcgen05 kind::tf32 with fp32 accumulation (the dropped lo*lo term is ~2^-22 relative).  Activations stay
+                             full fp32 in HBM.  Entry points: the *_tf32 ones; eligible shapes: the TMA-fed plans (forward / data
+                             gradient / weight gradient), everything else reports "not eligible" and runs on the fp32 FMA kernels. */
+};
 
 /* Geometry of one "tap convolution": the single GEMM-shaped primitive that the graph conv, the
  * temporal conv, the residual 1x1 conv, the mapping MLP and the critic head all reduce to, in

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libkgan.so")
 MAX_TAPS = 16
 
 ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_X3 = 0, 1, 2
 
 
 class TapConvDesc(C.Structure):

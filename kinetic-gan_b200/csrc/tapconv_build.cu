@@ -83,6 +83,7 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
 int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle);
 
 static bool make_build_plan(const kgan_tapconv_desc& d, BuildPlan& p) {
+    if (d.precision == KGAN_PREC_TF32X3) return false;              // the fp32-accurate split lives in the TMA-fed kernels only
     p.mix = d.mix_v > 0 ? 1 : 0;
     if (p.mix) {
         if (d.mix_w <= 0 || d.mix_l <= 0 || d.mix_l > 8 || d.groups != 1 || d.ntap > 4) return false;

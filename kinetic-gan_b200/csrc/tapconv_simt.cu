@@ -360,7 +360,9 @@ static kgan_tapconv_desc merge_groups(const kgan_tapconv_desc& d) {
 extern "C" int64_t kgan_tapconv_tf32_workspace(const kgan_tapconv_desc* d) {
     if (validate(d)) return -1;
     if (tapconv_is_thin(*d)) return 0;         // small contractions run on the exact streaming kernel in both precision modes
-    return tapconv_tf32_packed_numel(merge_groups(*d));
+    const kgan_tapconv_desc m = merge_groups(*d);
+    if (m.precision == KGAN_PREC_TF32X3 && !(m.tma_mode != 0 && tapconv_tma_eligible(m))) return 0;      // x3: the TMA-fed kernel only
+    return tapconv_tf32_packed_numel(m);
 }
 
 extern "C" int kgan_tapconv_pack_tf32(const kgan_tapconv_desc* d, const float* w, float* wp, void* stream) {
@@ -387,6 +389,14 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && wp && pmap && out, "tapconv_fwd_tf32: null pointer");
     const kgan_tapconv_desc m = merge_groups(*d);
+    if (m.precision == KGAN_PREC_TF32X3) {
+        const int rt = m.tma_mode != 0 ? tapconv_fwd_tma(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream) : -1;
+        if (rt == -1) {
+            set_error("tapconv_fwd_tf32: shape not eligible for the 3xTF32 path (kgan_tapconv_tf32_workspace() == 0)");
+            return 1;
+        }
+        return rt;
+    }
     if (m.prefer_staged) {
         const int rb = tapconv_fwd_build(m, in, wp, pmap, bias, add, out, (cudaStream_t)stream);
         if (rb != -1) return rb;

@@ -42,6 +42,16 @@ constexpr int TM_THREADS_TMA = TM_THREADS + 32 * (TM_PROD_WARPS - 1);
 constexpr int TM_CP_WARPS = 4;
 constexpr int TM_THREADS_CP = TM_THREADS + 32 * TM_CP_WARPS;          // cp.async mode
 constexpr int TM_GROUP_BYTES = 32 * 32 * 4;    // one box: 32 channel rows of 128 bytes
+// KGAN_PREC_TF32X3 (fp32-accurate mode): four more warps - the splitters - follow the copy engine through the ring; for every stage that
+// has landed they write  lo = x - (x & 0xFFFFE000)  (what the tensor core's 19-bit read of x drops; exact in fp32) into a second operand
+// image of the same layout, and the MMA warp issues three MMAs per K step: lo * W_hi + x * W_lo + x * W_hi (W_hi / W_lo: the two halves of
+// the packed weight image).  The split is elementwise, so it is the same code for every operand layout (MN-major boxes, cp.async image,
+// K-major Linear plan).  The two small terms go to an accumulator of their own, added by the epilogue: the tensor core's fp32 accumulation
+// truncates (measured: the error of a K-step chain grows linearly, ~2e-8 per MMA - tools/x3_accuracy.py), so the main accumulator takes
+// one MMA per K step instead of three, and the small accumulator's truncation is 2^-11 smaller.
+constexpr int TM_SPLIT_WARPS = 4;
+constexpr int TM_SPLIT_WARP0 = TM_EPI_WARP0 + TM_EPI_WARPS + TM_CP_WARPS;      // 14 (warps 12, 13 idle in TMA mode)
+constexpr int TM_THREADS_X3 = 32 * (TM_SPLIT_WARP0 + TM_SPLIT_WARPS);
 
 struct TmaPlan {
     int n_cta, n_split, n_rows, tmem_cols, nkt;   // identical to UmmaPlan (the packed weight image is shared)
@@ -56,6 +66,8 @@ struct TmaPlan {
     int nkt2;                                     // extra K panel (fused residual 1x1 conv, see tapconv_fwd_tma_res): channel tiles of the
     int c2_total, p_in2;                          //   second input tensor (0: none), its channel count and plane size
     int img1_bytes;                               // bytes of the main packed weight image (the panel's image follows it when resident)
+    int x3;                                       // KGAN_PREC_TF32X3: lo image per activation stage, hi + lo weight images
+    int64_t w_lo_off;                             //   floats between the hi and the lo half of the packed weight image
     int pf_tiles;                                 // L2 prefetch distance in tiles of this CTA (0: off)
     uint32_t pf_taps;                             // taps whose boxes are prefetched (temporal shifts of the same channels are near-duplicates)
 };
@@ -64,6 +76,8 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
 
 static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck = 0) {
     if (d.tma_mode != 1) return false;
+    p.x3 = d.precision == KGAN_PREC_TF32X3 ? 1 : 0;
+    if (p.x3 && panel_ck > 0) return false;                        // the fused residual panel is a tf32-mode feature
     p.nkt2 = panel_ck > 0 ? ceil_div(panel_ck, UK) : 0;
     p.c2_total = panel_ck;
     p.p_in2 = d.p_out;
@@ -92,10 +106,13 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck =
     p.m_tiles = (int)ceil_div64(p.groups32, 4);
     if ((int64_t)p.m_tiles * d.groups * p.n_split > (1 << 28)) return false;
     p.num_tiles = p.m_tiles * p.n_split * d.groups;
-    const int stage = A_STAGE_BYTES + p.n_cta * UK * 4;
+    const int xm = p.x3 ? 2 : 1;                                   // x3: every stage holds a lo image next to each operand image
+    const int stage = xm * (A_STAGE_BYTES + p.n_cta * UK * 4);
     p.stages = (200 * 1024) / stage;
     if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return false;
     p.smem_bytes = p.stages * stage + 1024 + 512;                  // + alignment slack + barriers
+    p.w_lo_off = (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;
     // Resident weights: a CTA re-fetches the same packed weight stages for every one of its tiles - a third of the bytes an SM
     // ingests at N = 64 (the marginal cost of a K stage measured ~700 cycles for 16 KB of activations + 8 KB of weights).  When
     // the whole image (all groups, all K stages) fits beside a ring of >= 5 activation stages it is loaded once per CTA.
@@ -103,17 +120,17 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck =
     p.w_res_bytes = 0;
     {
         const int64_t img1 = (int64_t)d.groups * p.nkt * d.ntap * p.n_cta * UK * 4;
-        const int64_t img = img1 + (int64_t)p.nkt2 * p.n_cta * UK * 4;
+        const int64_t img = xm * img1 + (int64_t)p.nkt2 * p.n_cta * UK * 4;      // (x3: hi image, then the lo image - contiguous in the packed buffer too)
         p.img1_bytes = (int)img1;
         const int64_t tiles_per_cta = ceil_div64(p.num_tiles, kNumSMs);
         if (p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
-            int st = (int)((200 * 1024 - img) / A_STAGE_BYTES);
+            int st = (int)((200 * 1024 - img) / (xm * A_STAGE_BYTES));
             if (st > 8) st = 8;
-            if (st >= 5) {
+            if (st >= (p.x3 ? 3 : 5)) {
                 p.w_res = 1;
                 p.w_res_bytes = (int)img;
                 p.stages = st;
-                p.smem_bytes = st * A_STAGE_BYTES + (int)img + 1024 + 512;
+                p.smem_bytes = st * xm * A_STAGE_BYTES + (int)img + 1024 + 512;
             }
         }
     }
@@ -176,11 +193,11 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
 
 // The residual / label term `add` and the bias do not depend on the accumulator: their loads for the first column chunk are issued
 // BEFORE the wait on the accumulator barrier, so their latency hides behind the tile's main loop instead of following it.
-template <int ACT, bool SCAT = false>
+template <int ACT, bool SCAT = false, bool X3 = false>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                   const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
                                                   uint32_t tfull_bar, uint32_t tfull_parity, int rnd, const float* __restrict__ bp2 = nullptr,
-                                                  int d1 = 0, int dz = 0) {
+                                                  int d1 = 0, int dz = 0, int small_off = 0) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (TM_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -198,6 +215,12 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
         }
         uint32_t r[16];
         tmem_ld16(taddr + col0, r);
+        if (X3) {                                                  // + the accumulator of the small terms (small_off columns further)
+            uint32_t r2[16];
+            tmem_ld16(taddr + small_off + col0, r2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         float* o = op + (int64_t)col0 * p_out;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -222,7 +245,8 @@ __device__ __forceinline__ void tm_cp_async16(uint32_t dst, const void* src, uin
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
                                                                     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
                                                                     const float* __restrict__ in, const float* __restrict__ bias,
                                                                     const float* __restrict__ add, float* __restrict__ out,
@@ -234,11 +258,14 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
     const int b_stage_bytes = pl.n_cta * UK * 4;
+    constexpr int XM = X3 ? 2 : 1;
     uint8_t* a_base = smem;
-    uint8_t* b_base = smem + (size_t)S * A_STAGE_BYTES;             // ring of S weight stages, or the resident image (pl.w_res)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (pl.w_res ? (size_t)pl.w_res_bytes : (size_t)S * b_stage_bytes));
-    // full[S], empty[S], tfull[2], tempty[2], wfull
+    uint8_t* alo_base = smem + (size_t)S * A_STAGE_BYTES;           // X3: the lo images of the S activation stages
+    uint8_t* b_base = smem + (size_t)XM * S * A_STAGE_BYTES;        // ring of S weight stages (X3: hi, lo per stage), or the resident image (pl.w_res)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (pl.w_res ? (size_t)pl.w_res_bytes : (size_t)S * XM * b_stage_bytes));
+    // full[S], empty[S], tfull[2], tempty[2], wfull, (tmem slot), lofull[S]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+    const uint32_t lofull0 = smem_u32(bars + 2 * S + 6);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
     const uint32_t tfull0 = smem_u32(bars + 2 * S), tempty0 = smem_u32(bars + 2 * S + 2);
     const uint32_t wfull = smem_u32(bars + 2 * S + 4);
@@ -252,6 +279,7 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             // arrival per producer thread
             mbar_init(full0 + 8 * s, use_tma ? 1 : 1 + 32 * TM_CP_WARPS);
             mbar_init(empty0 + 8 * s, 1);                            // tcgen05.commit
+            if (X3) mbar_init(lofull0 + 8 * s, TM_SPLIT_WARPS);      // one arrival per splitter warp
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8 * b, 1);
@@ -276,8 +304,8 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
     // it never waited on an empty stage, the MMA warp waited on full ones a third of its time, and a stage cost ~780 cycles of
     // mostly dependent uniform-datapath instructions (coordinates, descriptors, 4 UTMALDG).  In TMA mode the stages are
     // therefore dealt round-robin to TM_PROD_WARPS warps (each stage still has exactly one producer and its own barrier pair).
-    const int n_prod = use_tma ? TM_PROD_WARPS : 1;
-    const int prod_idx = warp == 0 ? 0 : (use_tma && warp >= TM_EPI_WARP0 + TM_EPI_WARPS && warp < TM_EPI_WARP0 + TM_EPI_WARPS + TM_PROD_WARPS - 1)
+    const int n_prod = (use_tma && S >= TM_PROD_WARPS) ? TM_PROD_WARPS : 1;      // (a producer's first stage slot is its index: needs S >= n_prod)
+    const int prod_idx = warp == 0 ? 0 : (n_prod > 1 && warp >= TM_EPI_WARP0 + TM_EPI_WARPS && warp < TM_EPI_WARP0 + TM_EPI_WARPS + TM_PROD_WARPS - 1)
                                              ? warp - (TM_EPI_WARP0 + TM_EPI_WARPS) + 1
                                              : -1;
     if (prod_idx >= 0) {
@@ -286,16 +314,17 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
         {
             const bool leader = elect_one();
             const uint32_t chunk_bytes = pl.n_cta * 16;
-            const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + (pl.w_res ? 0u : chunk_bytes * 8);
+            const uint32_t stage_tx = (use_tma ? A_STAGE_BYTES : 0) + (pl.w_res ? 0u : chunk_bytes * 8 * XM);
             if (pl.w_res && leader && prod_idx == 0) {               // the whole packed image (contiguous for n_split == 1), once
                 mbar_arrive_expect_tx(wfull, (uint32_t)pl.w_res_bytes);
                 for (int off = 0; off < pl.img1_bytes; off += 16384) {
                     const int nb = min(16384, pl.img1_bytes - off);
                     bulk_g2s(smem_u32(b_base + off), reinterpret_cast<const uint8_t*>(wp) + off, (uint32_t)nb, wfull);
                 }
-                for (int off = pl.img1_bytes; off < pl.w_res_bytes; off += 16384) {      // the panel's image behind it
+                for (int off = pl.img1_bytes; off < pl.w_res_bytes; off += 16384) {      // the panel's image (X3: the lo image) behind it
                     const int nb = min(16384, pl.w_res_bytes - off);
-                    bulk_g2s(smem_u32(b_base + off), reinterpret_cast<const uint8_t*>(wp2) + (off - pl.img1_bytes), (uint32_t)nb, wfull);
+                    const uint8_t* src2 = X3 ? reinterpret_cast<const uint8_t*>(wp + pl.w_lo_off) : reinterpret_cast<const uint8_t*>(wp2);
+                    bulk_g2s(smem_u32(b_base + off), src2 + (off - pl.img1_bytes), (uint32_t)nb, wfull);
                 }
             }
             // activation boxes of a later tile of this CTA -> L2 (off by default: measured slower); tiles that share an activation tile
@@ -351,15 +380,20 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                         }
                         const float* src = panel ? wp2 + (int64_t)(it - kmain) * pl.n_rows * UK
                                                  : wg + (int64_t)it * pl.n_rows * UK;    // loop order == packing order (ic tile, tap)
-                        const uint32_t b_dst = smem_u32(b_base + (size_t)s * b_stage_bytes);
-                        if (pl.w_res) {
-                            // nothing: the weights are resident
-                        } else if (pl.n_split == 1) {
-                            bulk_g2s(b_dst, src, chunk_bytes * 8, full0 + 8 * s);       // the whole stage is contiguous in the image
-                        } else {
+                        const uint32_t b_dst = smem_u32(b_base + (size_t)s * XM * b_stage_bytes);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                bulk_g2s(b_dst + c * chunk_bytes, src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                        for (int half = 0; half < XM; ++half) {                         // X3: the lo stage behind the hi stage
+                            const float* sh_src = src + half * pl.w_lo_off;
+                            const uint32_t bd = b_dst + half * b_stage_bytes;
+                            if (pl.w_res) {
+                                // nothing: the weights are resident
+                            } else if (pl.n_split == 1) {
+                                bulk_g2s(bd, sh_src, chunk_bytes * 8, full0 + 8 * s);   // the whole stage is contiguous in the image
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    bulk_g2s(bd + c * chunk_bytes, sh_src + ((int64_t)c * pl.n_rows + oc_base) * 4, chunk_bytes, full0 + 8 * s);
+                            }
                         }
                     }
                     __syncwarp();
@@ -391,22 +425,38 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                 const uint32_t b_res = smem_u32(b_base) + (uint32_t)(tma_tile(tile, pl).g * kmain) * (uint32_t)b_stage_bytes;
                 mbar_wait(tempty0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_base + buf * pl.n_cta;
+                const uint32_t acc = tmem_base + buf * XM * pl.n_cta;      // X3: [main | small terms] per buffer
                 for (int it = 0; it < kiters; ++it) {
                     mbar_wait(full0 + 8 * s, ph);
+                    if (X3) mbar_wait(lofull0 + 8 * s, ph);          // the splitters' lo image of this stage (they ran the proxy fence)
                     // TMA mode: both operands were written by the async proxy.  cp.async mode: the activations went through the
                     // generic proxy and must be made visible to the tensor core's async-proxy reads
                     if (!use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (leader) {
                         const uint32_t a_addr = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
-                        const uint32_t b_addr = !pl.w_res ? smem_u32(b_base + (size_t)s * b_stage_bytes)
+                        const uint32_t b_addr = !pl.w_res ? smem_u32(b_base + (size_t)s * XM * b_stage_bytes)
                                                 : it < kmain ? b_res + (uint32_t)it * (uint32_t)b_stage_bytes
                                                              : smem_u32(b_base) + (uint32_t)pl.img1_bytes + (uint32_t)(it - kmain) * (uint32_t)b_stage_bytes;
+                        if (X3) {
+                            // lo * W_hi + x * W_lo -> the small accumulator, x * W_hi -> the main one (the tensor core reads x as its upper 19 bits = hi)
+                            const uint32_t alo_addr = smem_u32(alo_base + (size_t)s * A_STAGE_BYTES);
+                            const uint32_t blo_addr = b_addr + (pl.w_res ? (uint32_t)pl.img1_bytes : (uint32_t)b_stage_bytes);
 #pragma unroll
-                        for (int j = 0; j < UK / 8; ++j)
-                            umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
-                                      smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                            for (int j = 0; j < UK / 8; ++j) {
+                                const uint64_t ad = pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo);
+                                const uint64_t ald = pl.kmajor ? smem_desc_k_sw128(alo_addr + j * 32) : smem_desc_mn_sw128(alo_addr + j * 1024, pl.a_lbo, pl.a_sbo);
+                                const uint64_t bd = smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), bld = smem_desc(blo_addr + j * 2 * b_lbo, b_lbo, CORE_SBO);
+                                umma_tf32(acc + pl.n_cta, ald, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                                umma_tf32(acc + pl.n_cta, ad, bld, idesc, 1u);
+                                umma_tf32(acc, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < UK / 8; ++j)
+                                umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
+                                          smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                        }
                         umma_commit(empty0 + 8 * s);
                     }
                     __syncwarp();
@@ -419,14 +469,42 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
                 __syncwarp();
             }
         }
+    } else if (X3 && warp >= TM_SPLIT_WARP0) {
+        // ===== splitters (X3): lo image of every landed activation stage; thread = 16-byte column of the 2 KB rows of the stage =====
+        const uint32_t t16 = (uint32_t)(threadIdx.x - 32 * TM_SPLIT_WARP0) * 16u;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x)
+            for (int it = 0; it < kiters; ++it) {
+                mbar_wait(full0 + 8 * s, ph);
+                const uint32_t src = smem_u32(a_base + (size_t)s * A_STAGE_BYTES) + t16, dst = smem_u32(alo_base + (size_t)s * A_STAGE_BYTES) + t16;
+                uint32_t v[8][4];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q][0]), "=r"(v[q][1]), "=r"(v[q][2]), "=r"(v[q][3]) : "r"(src + q * 2048));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[q][e] = __float_as_uint(__uint_as_float(v[q][e]) - __uint_as_float(v[q][e] & 0xFFFFE000u));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 2048), "r"(v[q][0]), "r"(v[q][1]), "r"(v[q][2]), "r"(v[q][3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(lofull0 + 8 * s);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
     } else if (warp >= TM_EPI_WARP0 + TM_EPI_WARPS) {
         // ===== cp.async activation producers (p_box < 32): thread = (16-byte chunk of the 128-byte row, channel rows rr, rr + 16) =====
+        // (warps 12, 13 of an X3 launch in TMA mode have no role)
         const int t = threadIdx.x - 32 * (TM_EPI_WARP0 + TM_EPI_WARPS);
         const int chunk = t & 7, rr = t >> 3;
         const int m0 = chunk * 4;                                     // first of this chunk's 4 M elements within the group
         const int nl = m0 >> pl.p_shift, pl0 = m0 & (pl.p_box - 1);   // sample within the box, position within the chunk row
         int kit = 0;
-        for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < (use_tma ? 0 : pl.num_tiles); tile += gridDim.x) {
             const TmaTile tc = tma_tile(tile, pl);
             const float* base[4];
             const float* base2[4];                                     // the extra K panel's tensor (same samples, plane = the output plane)
@@ -500,11 +578,16 @@ __global__ void __launch_bounds__(TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __gr
             const float* bp = bias ? bias + out_ch0 + oc_base : nullptr;
             const float* bp2 = (pl.nkt2 && bias2) ? bias2 + out_ch0 + oc_base : nullptr;
             const uint32_t tbar = tfull0 + 8 * buf, tpar = (uint32_t)(ti >> 1) & 1u;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * pl.n_cta;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * XM * pl.n_cta;
             const int ncols = min(pl.n_cta, d.co - oc_base);
             if (16 * colpar >= ncols) {                               // this warp has no columns in the tile: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            } else if (X3) {
+                if (omap) tma_epilogue_tile<KGAN_ACT_NONE, true, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, nullptr, d1, dz, pl.n_cta);
+                else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
+                else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
+                else tma_epilogue_tile<KGAN_ACT_NONE, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
             } else if (omap) tma_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, nullptr, d1, dz);
             else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
@@ -598,11 +681,16 @@ static int launch_tma(const kgan_tapconv_desc& d, TmaPlan& p, const float* in, c
         set_error("tapconv_fwd_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return 1;
     }
-    static SmemAttrOnce attr;
-    if (int e = ensure_smem(tapconv_fwd_tma_k, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
+    static SmemAttrOnce attr, attr3;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    tapconv_fwd_tma_k<<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
-                                                                                                                    tmap2, wp2, in2, bias2, omap);
+    if (p.x3) {
+        if (int e = ensure_smem(tapconv_fwd_tma_k<true>, 227 * 1024, attr3, "tapconv_fwd_tma (x3) attribute")) return e;
+        tapconv_fwd_tma_k<true><<<grid, TM_THREADS_X3, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out, tmap2, wp2, in2, bias2, omap);
+        return check_launch("tapconv_fwd_tma (x3)");
+    }
+    if (int e = ensure_smem(tapconv_fwd_tma_k<false>, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
+    tapconv_fwd_tma_k<false><<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
+                                                                                                                           tmap2, wp2, in2, bias2, omap);
     return check_launch("tapconv_fwd_tma");
 }
 

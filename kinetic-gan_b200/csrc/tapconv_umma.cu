@@ -48,13 +48,16 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
     const int64_t m_tiles = ceil_div64(total, UM);
     if (m_tiles * d.groups > (1 << 24)) return false;
     const int n16 = round_up(d.co, 16);
-    int split = ceil_div(n16, 256);
+    // KGAN_PREC_TF32X3: tiles of at most 128 channels - a stage holds hi + lo images of both operands, and the accumulator of the
+    // small terms (lo * W_hi + x * W_lo) sits beside the main one in TMEM, both double-buffered: 4 * n_cta <= 512 columns
+    const bool x3 = d.precision == KGAN_PREC_TF32X3;
+    int split = ceil_div(n16, x3 ? 128 : 256);
     while (m_tiles * d.groups * split < kNumSMs && ceil_div(n16, split * 2) >= 64) split *= 2;
     *n_cta = round_up(ceil_div(n16, split), 16);
     *n_split = ceil_div(n16, *n_cta);
     *n_rows = *n_cta * *n_split;
     *tmem_cols = 32;
-    while (*tmem_cols < 2 * *n_cta) *tmem_cols *= 2;
+    while (*tmem_cols < (x3 ? 4 : 2) * *n_cta) *tmem_cols *= 2;
     *nkt = ceil_div(d.ck, UK);
     return true;
 }
@@ -74,11 +77,19 @@ static bool make_plan(const kgan_tapconv_desc& d, UmmaPlan& p) {
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: natural (strided) fp32 weights -> tf32 shared-memory image
 //   wp[group][ic tile][tap][k-chunk c (8)][row r (n_rows)][4]     (zero for r >= co or ic >= ck)
+// KGAN_PREC_TF32X3: a second image of the same layout follows the first - hi = RN_tf32(w) in the first, RN_tf32(w - hi) in the second.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pack_value(float v, bool lo_half) {
+    const float hi = __uint_as_float(to_tf32(v));
+    return lo_half ? __uint_as_float(to_tf32(v - hi)) : hi;
+}
 __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ w,
                                                        float* __restrict__ wp, int n_rows, int nkt) {
-    const int64_t total = (int64_t)d.groups * nkt * d.ntap * 8 * n_rows * 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t total1 = (int64_t)d.groups * nkt * d.ntap * 8 * n_rows * 4;
+    const int64_t total = d.precision == KGAN_PREC_TF32X3 ? 2 * total1 : total1;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const bool lo_half = i0 >= total1;
+        const int64_t i = lo_half ? i0 - total1 : i0;
         const int e = (int)(i & 3);
         int64_t r = i >> 2;
         const int row = (int)(r % n_rows);
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(256) tapconv_pack_k(const __grid_constant__ kg
         const int ic = ict * UK + c * 4 + e;
         float v = 0.f;
         if (row < d.co && ic < d.ck) v = __ldg(w + (int64_t)g * d.g_w + d.tap_w_off[tap] + w_oc_offset(d, row) + (int64_t)ic * d.w_ic);
-        wp[i] = __uint_as_float(to_tf32(v));
+        wp[i0] = pack_value(v, lo_half);
     }
 }
 
@@ -102,13 +113,16 @@ struct PackItem {
     const float* w;
     float* wp;
     int32_t n_rows, nkt;
-    int64_t total;
+    int64_t total;                             // elements of ONE image (KGAN_PREC_TF32X3 writes two)
 };
 __global__ void __launch_bounds__(256) tapconv_pack_batched_k(const PackItem* __restrict__ items) {
     const PackItem& it = items[blockIdx.y];
     const kgan_tapconv_desc& d = it.d;
     const int n_rows = it.n_rows, nkt = it.nkt;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t total = d.precision == KGAN_PREC_TF32X3 ? 2 * it.total : it.total;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const bool lo_half = i0 >= it.total;
+        const int64_t i = lo_half ? i0 - it.total : i0;
         const int e = (int)(i & 3);
         int64_t r = i >> 2;
         const int row = (int)(r % n_rows);
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(256) tapconv_pack_batched_k(const PackItem* __
         const int ic = ict * UK + c * 4 + e;
         float v = 0.f;
         if (row < d.co && ic < d.ck) v = __ldg(it.w + (int64_t)g * d.g_w + d.tap_w_off[tap] + w_oc_offset(d, row) + (int64_t)ic * d.w_ic);
-        it.wp[i] = __uint_as_float(to_tf32(v));
+        it.wp[i0] = pack_value(v, lo_half);
     }
 }
 
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) tapconv_fwd_umma(const __grid_c
 int64_t tapconv_tf32_packed_numel(const kgan_tapconv_desc& d) {
     UmmaPlan p;
     if (!make_plan(d, p)) return 0;
-    return (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;
+    return (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK * (d.precision == KGAN_PREC_TF32X3 ? 2 : 1);
 }
 
 int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cudaStream_t stream) {
@@ -419,7 +433,7 @@ int tapconv_pack_tf32(const kgan_tapconv_desc& d, const float* w, float* wp, cud
         set_error("tapconv_pack: shape not eligible for the tf32 path");
         return 1;
     }
-    const int64_t total = (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;
+    const int64_t total = (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK * (d.precision == KGAN_PREC_TF32X3 ? 2 : 1);
     int64_t blocks = ceil_div64(total, 256);
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     tapconv_pack_k<<<(unsigned)blocks, 256, 0, stream>>>(d, w, wp, p.n_rows, p.nkt);

@@ -26,6 +26,13 @@ namespace kgan {
 constexpr int WT_EPI_WARPS = 8;
 constexpr int WT_THREADS = 32 * (2 + WT_EPI_WARPS);
 constexpr int WT_KT = 32;                        // positions per K tile: one 128-byte swizzled row per channel
+// KGAN_PREC_TF32X3: four splitter warps write, for every landed stage, the lo image (x - its upper 19 bits) of BOTH operands behind the
+// stage, and the MMA warp issues g_lo * x + g * x_lo + g * x per K step (see tapconv_tma.cu): the small terms into an accumulator of their
+// own (2 * ntap * n_ic <= 512 TMEM columns), and split-K chunks of at most WT_X3_CHUNK K tiles - the tensor core's fp32 accumulation
+// truncates, so the error of a chain grows linearly with its length (tools/x3_accuracy.py); the chunks are summed by fp32 atomics
+constexpr int WT_X3_CHUNK = 32;
+constexpr int WT_SPLIT_WARPS = 4;
+constexpr int WT_THREADS_X3 = WT_THREADS + 32 * WT_SPLIT_WARPS;
 
 struct WgradTmaPlan {
     int n_ic, ic_tiles, oc_tiles, tmem_cols, stages;
@@ -43,6 +50,7 @@ struct WgradTmaPlan {
     int nchunks;
     int64_t chunk;           // K tiles per split-K chunk
     int smem_bytes;
+    int x3;                  // KGAN_PREC_TF32X3: a stage is followed by its lo image (stage_stride = 2 * stage bytes)
 };
 
 int tma_encode_3d_f32(CUtensorMap* map, const float* base, const uint64_t gdim[3], const uint64_t gstr_bytes[2], const uint32_t box[3], int swizzle);
@@ -62,14 +70,16 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
         if (d.tap_shift[t] & 3) return false;                    // box origins must be 16-byte aligned
     const int64_t total = (int64_t)d.n * d.p_out;
     if (total < 1024 || total >= (1ll << 31) - WT_KT) return false;
-    int n_max = (512 / d.ntap) / 16 * 16;
+    p.x3 = d.precision == KGAN_PREC_TF32X3 ? 1 : 0;
+    int n_max = ((p.x3 ? 256 : 512) / d.ntap) / 16 * 16;
     if (n_max > 256) n_max = 256;
-    if (d.ntap >= 3 && n_max > 128) n_max = 128;
+    if ((d.ntap >= 3 || p.x3) && n_max > 128) n_max = 128;
+    if (n_max < 16) return false;
     p.n_ic = round_up(d.ck, 16) < n_max ? round_up(d.ck, 16) : n_max;
     p.ic_tiles = ceil_div(d.ck, p.n_ic);
     p.oc_tiles = ceil_div(d.co, UM);
     p.tmem_cols = 32;
-    while (p.tmem_cols < d.ntap * p.n_ic) p.tmem_cols *= 2;
+    while (p.tmem_cols < (p.x3 ? 2 : 1) * d.ntap * p.n_ic) p.tmem_cols *= 2;
     if (p.tmem_cols > 512) return false;
     p.a_rows = d.co >= UM ? UM : round_up(d.co, 8);
     // The A tile only holds the a_rows rows the box writes; the M = 128 MMA reads on into the B tiles behind it (rows that feed
@@ -78,7 +88,7 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     p.a_bytes = p.a_rows * p.row_bytes;
     p.b_bytes = p.n_ic * p.row_bytes;
     p.sub_bytes = p.a_bytes + d.ntap * p.b_bytes;
-    const int stage = p.nsub * p.sub_bytes;
+    const int stage = p.nsub * p.sub_bytes * (p.x3 ? 2 : 1);
     const int tail_pad = p.sub_bytes < UM * p.row_bytes ? UM * p.row_bytes - p.sub_bytes : 0;
     p.tail_pad = tail_pad;
     p.stages = (212 * 1024 - tail_pad) / stage;
@@ -90,6 +100,7 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     int64_t nchunks = kNumSMs / tiles;                           // one wave
     if (nchunks > p.ktiles / 4) nchunks = p.ktiles / 4;
     if (nchunks < 1) nchunks = 1;
+    if (p.x3 && nchunks < ceil_div64(p.ktiles, WT_X3_CHUNK)) nchunks = ceil_div64(p.ktiles, WT_X3_CHUNK);
     p.chunk = ceil_div64(p.ktiles, nchunks);
     p.nchunks = (int)ceil_div64(p.ktiles, p.chunk);
     if ((int64_t)p.nchunks * d.groups > 65535) return false;
@@ -127,17 +138,20 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw(uint32_t addr, uint32_t hi) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)hi << 32);
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradTmaPlan pl,
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? WT_THREADS_X3 : WT_THREADS, 1) tapconv_wgrad_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ WgradTmaPlan pl,
                                                                      const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                                                                      float* __restrict__ dw) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int S = pl.stages;
-    const int stage_bytes = pl.nsub * pl.sub_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + pl.tail_pad);   // full[S], empty[S], accfull
+    const int half_bytes = pl.nsub * pl.sub_bytes;                    // the operand boxes of a stage
+    const int stage_bytes = X3 ? 2 * half_bytes : half_bytes;         // X3: + their lo images behind them
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes + pl.tail_pad);   // full[S], empty[S], accfull, (tmem slot), lofull[S]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+    const uint32_t lofull0 = smem_u32(bars + 2 * S + 2);
 
     const int ic0 = blockIdx.x * pl.n_ic, oc0 = blockIdx.y * UM;
     const int g = blockIdx.z / pl.nchunks, ch = blockIdx.z % pl.nchunks;
@@ -148,6 +162,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
         for (int s = 0; s < S; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
+            if (X3) mbar_init(lofull0 + 8 * s, WT_SPLIT_WARPS);
         }
         mbar_init(accfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
         {
             const bool leader = elect_one();
             const int in_ch0 = g * d.g_in + ic0, out_ch0 = g * d.g_out + oc0;
-            const uint32_t stage_tx = (uint32_t)stage_bytes;
+            const uint32_t stage_tx = (uint32_t)half_bytes;
             // first K tile of this producer: stage k covers K tiles k * nsub ... + nsub - 1, K tile t = (sample t / kt_per_plane, box t % ...)
             const int64_t t0 = (kbeg + prod_idx) * pl.nsub;
             int nn = (int)(t0 / pl.kt_per_plane), pt = (int)(t0 - (int64_t)nn * pl.kt_per_plane);
@@ -222,6 +237,38 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
     }
     if (warp == 0) {
         // producer only
+    } else if (X3 && warp >= 2 + WT_EPI_WARPS) {
+        // ===== splitters (X3): lo image of both operands of every landed stage (elementwise: any box layout) =====
+        const uint32_t t16 = (uint32_t)(threadIdx.x - 32 * (2 + WT_EPI_WARPS)) * 16u;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(full0 + 8 * s, ph);
+            const uint32_t src = smem_u32(smem + (size_t)s * stage_bytes);
+            for (uint32_t off = t16; off < (uint32_t)half_bytes; off += 4 * 2048) {
+                uint32_t v[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (off + q * 2048 < (uint32_t)half_bytes)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q][0]), "=r"(v[q][1]), "=r"(v[q][2]), "=r"(v[q][3]) : "r"(src + off + q * 2048));
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (off + q * 2048 < (uint32_t)half_bytes) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[q][e] = __float_as_uint(__uint_as_float(v[q][e]) - __uint_as_float(v[q][e] & 0xFFFFE000u));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(src + half_bytes + off + q * 2048), "r"(v[q][0]), "r"(v[q][1]), "r"(v[q][2]),
+                                     "r"(v[q][3])
+                                     : "memory");
+                    }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lofull0 + 8 * s);
+            if (++s == S) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp waits, one lane issues) =====
         {
@@ -234,6 +281,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
             uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(full0 + 8 * s, ph);
+                if (X3) mbar_wait(lofull0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
@@ -241,9 +289,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                         const uint32_t a_addr = st + sub * pl.sub_bytes;
                         for (int tap = 0; tap < nmma; ++tap) {
                             const uint32_t b_addr = a_addr + pl.a_bytes + tap * pl.b_bytes;
-                            for (int j = 0; j < pl.p_box / 8; ++j)          // 32 bytes of K per MMA inside the swizzled row
-                                umma_tf32(tmem_base + tap * pl.n_ic, smem_desc_k_sw(a_addr + j * 32, pl.desc_hi), smem_desc_k_sw(b_addr + j * 32, pl.desc_hi),
-                                          idesc, (it > 0 || sub > 0 || j > 0) ? 1u : 0u);
+                            for (int j = 0; j < pl.p_box / 8; ++j) {        // 32 bytes of K per MMA inside the swizzled row
+                                const uint64_t ad = smem_desc_k_sw(a_addr + j * 32, pl.desc_hi), bd = smem_desc_k_sw(b_addr + j * 32, pl.desc_hi);
+                                const uint32_t first = (it > 0 || sub > 0 || j > 0) ? 1u : 0u;
+                                if (X3) {
+                                    const uint64_t ald = smem_desc_k_sw(a_addr + half_bytes + j * 32, pl.desc_hi);
+                                    const uint64_t bld = smem_desc_k_sw(b_addr + half_bytes + j * 32, pl.desc_hi);
+                                    const uint32_t small = tmem_base + (d.ntap + tap) * pl.n_ic;      // the small terms' accumulator
+                                    umma_tf32(small, ald, bd, idesc, first);
+                                    umma_tf32(small, ad, bld, idesc, 1u);
+                                    umma_tf32(tmem_base + tap * pl.n_ic, ad, bd, idesc, first);
+                                } else {
+                                    umma_tf32(tmem_base + tap * pl.n_ic, ad, bd, idesc, first);
+                                }
+                            }
                         }
                     }
                     umma_commit(empty0 + 8 * s);
@@ -277,6 +336,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                     tmem_ld16_nowait(taddr + pl.n_ic + col0, r[1]);
                     tmem_ld16_nowait(taddr + 2 * pl.n_ic + col0, r[2]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (X3) {
+#pragma unroll
+                        for (int tp = 0; tp < 3; ++tp) {
+                            uint32_t r2[16];
+                            tmem_ld16(taddr + (3 + tp) * pl.n_ic + col0, r2);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[tp][j] = __float_as_uint(__uint_as_float(r[tp][j]) + __uint_as_float(r2[j]));
+                        }
+                    }
                     if (oc < d.co) {
                         float* dst = wb + d.tap_w_off[0] + (int64_t)(ic0 + col0) * 3;
                         if (ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -305,6 +373,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tapconv_wgrad_tma_k(const __gri
                         if (ic0 + col0 >= d.ck) break;                   // warp-uniform
                         uint32_t r[16];
                         tmem_ld16(taddr + tap * pl.n_ic + col0, r);
+                        if (X3) {
+                            uint32_t r2[16];
+                            tmem_ld16(taddr + (d.ntap + tap) * pl.n_ic + col0, r2);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                        }
                         if (oc < d.co) {
                             float* dst = wb + d.tap_w_off[tap] + (int64_t)(ic0 + col0) * d.w_ic;
                             if (d.w_ic == 1 && ic0 + col0 + 16 <= d.ck && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -354,11 +428,14 @@ int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* 
         const uint32_t box[3] = {(uint32_t)p.p_box, 1u, (uint32_t)p.n_ic};
         if (int e = tma_encode_3d_f32(&map_x, in, gdim, gstr, box, p.p_box == 32 ? 1 : p.p_box == 16 ? 2 : 3)) return e;
     }
-    static SmemAttrOnce attr;
-    if (int e = ensure_smem(tapconv_wgrad_tma_k, 227 * 1024, attr, "tapconv_wgrad_tma attribute")) return e;
+    static SmemAttrOnce attr, attr3;
+    if (int e = p.x3 ? ensure_smem(tapconv_wgrad_tma_k<true>, 227 * 1024, attr3, "tapconv_wgrad_tma (x3) attribute")
+                     : ensure_smem(tapconv_wgrad_tma_k<false>, 227 * 1024, attr, "tapconv_wgrad_tma attribute"))
+        return e;
     if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, stream) != cudaSuccess) return check_launch("tapconv_wgrad_tma memset");
     dim3 grid(p.ic_tiles, p.oc_tiles, (unsigned)(d.groups * p.nchunks));
-    tapconv_wgrad_tma_k<<<grid, WT_THREADS, p.smem_bytes, stream>>>(d, p, map_g, map_x, dw);
+    if (p.x3) tapconv_wgrad_tma_k<true><<<grid, WT_THREADS_X3, p.smem_bytes, stream>>>(d, p, map_g, map_x, dw);
+    else tapconv_wgrad_tma_k<false><<<grid, WT_THREADS, p.smem_bytes, stream>>>(d, p, map_g, map_x, dw);
     return check_launch("tapconv_wgrad_tma");
 }
 

@@ -271,6 +271,7 @@ int tapconv_wgrad_tma(const kgan_tapconv_desc& d, const float* in, const float* 
 
 int tapconv_wgrad_tf32_eligible(const kgan_tapconv_desc& d) {
     WgradPlan p;
+    if (d.precision == KGAN_PREC_TF32X3) return tapconv_wgrad_tma_eligible(d);      // the fp32-accurate split lives in the TMA-fed kernel only
     return (make_wgrad_plan(d, p) || tapconv_wgrad_tma_eligible(d)) ? 1 : 0;
 }
 
@@ -280,6 +281,7 @@ int tapconv_wgrad_tf32(const kgan_tapconv_desc& d, const float* in, const float*
         const int rt = tapconv_wgrad_tma(d, in, gout, dw, dw_numel, accumulate, stream);
         if (rt != -1) return rt;
     }
+    if (d.precision == KGAN_PREC_TF32X3) return -1;
     WgradPlan p;
     if (!make_wgrad_plan(d, p)) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(gout)) & 15) {

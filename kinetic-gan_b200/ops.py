@@ -4,7 +4,7 @@ function ends in a libkgan.so kernel launch."""
 import torch
 
 from . import _lib
-from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, PREC_FP32, PREC_TF32  # noqa: F401
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH, PREC_FP32, PREC_TF32, PREC_X3  # noqa: F401
 
 _precision = PREC_FP32
 launches = 0       # number of libkgan kernels launched by this process (bench.py reports it)
@@ -12,13 +12,18 @@ launches = 0       # number of libkgan kernels launched by this process (bench.p
 
 def set_precision(name):
     """'fp32' = exact SIMT FMA path (rel-L2 <= 1e-5 vs the fp32 reference);
+    'fp32x3' = the same accuracy class on the tensor cores: operands split hi + lo inside the TMA-fed kernels, three tcgen05
+    kind::tf32 MMAs per product (KGAN_PREC_TF32X3), fp32 activations in HBM; shapes without a TMA-fed plan run the FMA kernels;
     'tf32' = tcgen05 kind::tf32 tensor-core path with fp32 accumulation (<= 1e-3)."""
     global _precision
-    _precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}[name]
+    _precision = _PRECISIONS[name]
+
+
+_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32x3": PREC_X3}
 
 
 def get_precision():
-    return "tf32" if _precision == PREC_TF32 else "fp32"
+    return {v: k for k, v in _PRECISIONS.items()}[_precision]
 
 
 def _stream():
@@ -220,9 +225,9 @@ def repack_weights(flat):
 
 def _packed_weights(w, desc, cs, l):
     cache = desc.__dict__.setdefault("_tf32_numel", {})       # eligibility / image size depend on the batch size too
-    numel = cache.get(cs.n)
+    numel = cache.get((cs.n, cs.precision))
     if numel is None:
-        numel = cache[cs.n] = int(l.kgan_tapconv_tf32_workspace(cs))
+        numel = cache[(cs.n, cs.precision)] = int(l.kgan_tapconv_tf32_workspace(cs))
     if numel <= 0:
         return None
     if isinstance(w, torch.nn.Parameter):
@@ -265,11 +270,11 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=ACT_NONE):
         add_period = desc.v_out
     l = _lib.lib()
     cs = desc.cstruct(n, act, _precision, add_period)
-    if _precision == PREC_TF32:
+    if _precision != PREC_FP32:
         wp = _packed_weights(w, desc, cs, l)
-        _io(x, w, bias, add, out)
         if wp is not None:
-            _run('tapconv_fwd_tf32', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(),
+            _io(x, w, bias, add, out)
+            _run('tapconv_fwd_tf32' if _precision == PREC_TF32 else 'tapconv_fwd_x3', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(),
                  desc.pmap_on(x.device).data_ptr(), _ptr(bias), _ptr(add), out.data_ptr(), _stream())
             return out
     _io(x, w, bias, add, out)
@@ -373,13 +378,12 @@ def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     l = _lib.lib()
     cs = desc.cstruct(n, ACT_NONE, _precision)
     _io(x, gout, dw)
-    if _precision == PREC_TF32:
+    if _precision != PREC_FP32:
         ok = desc.__dict__.setdefault("_tf32_wgrad_ok", {})
-        if n not in ok:
-            ok[n] = bool(l.kgan_tapconv_wgrad_tf32_ok(cs))
-        if ok[n]:
-            _io(x, gout, dw)
-            _run('tapconv_wgrad_tf32', _tap_flops(desc, n), l.kgan_tapconv_wgrad_tf32, cs, x.data_ptr(), gout.data_ptr(),
+        if (n, _precision) not in ok:
+            ok[(n, _precision)] = bool(l.kgan_tapconv_wgrad_tf32_ok(cs))
+        if ok[(n, _precision)]:
+            _run('tapconv_wgrad_tf32' if _precision == PREC_TF32 else 'tapconv_wgrad_x3', _tap_flops(desc, n), l.kgan_tapconv_wgrad_tf32, cs, x.data_ptr(), gout.data_ptr(),
                  desc.pmap_on(x.device).data_ptr(), dw.data_ptr(), dw.numel(), acc, _stream())
             return dw
     _run('tapconv_wgrad', _tap_flops(desc, n), l.kgan_tapconv_wgrad, cs, x.data_ptr(), gout.data_ptr(),
