@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: WGAN-GP training throughput (samples/s) of Kinetic-GAN at the NTU 25x64x3 shape.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kgan|reference] [--batch B] [--precision fp32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kgan|reference] [--batch B] [--precision tf32|fp32|fp32_fma]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one iteration of the training loop body kinetic-gan.py:137-174 on one synthetic batch per GPU: the critic
@@ -77,6 +77,10 @@ def oracle_cfg():
                        channels=SHAPE["channels"])
 
 
+LIB_MODE = {"tf32": "tf32", "fp32": "fp32x3", "fp32_fma": "fp32"}                     # --precision -> kgan.set_precision
+DTYPE_NAME = {"tf32": "tf32", "fp32": "fp32 (3xTF32 split on the tensor cores + FMA kernels)", "fp32_fma": "fp32"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -89,8 +93,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096 for train and for generate)")
     ap.add_argument("--trunc", type=float, default=None, help="generate: W-space truncation factor (generate.py --trunc_mode w); default off")
     ap.add_argument("--trunc-cached", action="store_true", help="generate: estimate the W-space mean once (GeneratorRunner cache_mean) instead of per call")
-    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "fp32x3", "tf32"],
-                    help="tf32: headline mode; fp32x3: fp32-accurate tensor-core mode (3xTF32 split in the TMA-fed kernels); fp32: FMA kernels only")
+    ap.add_argument("--precision", default=os.environ.get("KGAN_PRECISION", "tf32"), choices=["fp32", "fp32_fma", "tf32"],
+                    help="tf32: headline mode; fp32: fp32-accurate mode - 3xTF32 operand split on the tensor cores wherever a TMA-fed plan exists, "
+                         "FMA kernels elsewhere (library mode 'fp32x3'); fp32_fma: FMA kernels only (library mode 'fp32')")
     ap.add_argument("--cpu-batch", type=int, default=32, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -342,7 +347,7 @@ def run_kgan(args):
     comm = ddp.Comm()
     dev = torch.device("cuda", comm.local_rank)
     torch.cuda.set_device(dev)
-    kgan.set_precision(args.precision)
+    kgan.set_precision(LIB_MODE[args.precision])
     if os.environ.get("KGAN_STAGED_POLICY"):          # A/B switch of this harness (the library itself reads no environment)
         kgan.geometry.STAGED_POLICY = os.environ["KGAN_STAGED_POLICY"]
     B, K, W = args.batch, args.steps, args.warmup
@@ -468,7 +473,7 @@ def run_kgan(args):
         line = {
             "metric": "wgan_gp_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": comm.world_size, "steps": K,
             "warmup": max(W, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
+            "dtype": DTYPE_NAME[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size,
                        "parallelism": "dp%d" % comm.world_size, "n_critic": 5, "flop_per_sample": FLOP_PER_SAMPLE,
                        "cuda_graphs": graphs,
@@ -560,7 +565,7 @@ def run_generate(args):
     comm = ddp.Comm()
     dev = torch.device("cuda", comm.local_rank)
     torch.cuda.set_device(dev)
-    kgan.set_precision(args.precision)
+    kgan.set_precision(LIB_MODE[args.precision])
     line = measure_generate(args, comm, dev)
     if comm.rank == 0 and comm.world_size == 1:
         if not args.no_cpu_baseline:
@@ -666,7 +671,7 @@ def measure_generate(args, comm, dev):
     if True:
         return ({
             "metric": "generated_sequences_per_s", "value": value, "unit": "seq/s", "n_gpus": comm.world_size, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[args.precision], "data": "synthetic",
             "config": {"workload": GEN_WORKLOAD, "per_gpu_batch": B, "global_batch": B * comm.world_size, "parallelism": "replicas%d" % comm.world_size,
                        "trunc": args.trunc, "trunc_mean_cached": bool(args.trunc_cached), "flop_per_sequence": F_G, "cuda_graphs": not args.no_graphs,
                        "l2_policy": "inputs rotate over a pool of %d batches; the activations of one pass at batch %d exceed the 126 MB L2" % (POOL, B)},

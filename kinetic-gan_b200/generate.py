@@ -164,7 +164,7 @@ def build_parser():
     p.add_argument("--trunc_mode", type=str, default='w', choices=['z', 'w', '-'], help="truncate in Z space, in W space, or not at all")
     p.add_argument("--mean_size", type=int, default=1000, help="latents used to estimate the truncation mean")
     # not in the reference
-    p.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4)")
+    p.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4): tf32 tensor cores / fp32 FMA kernels / fp32x3 = fp32-accurate tensor-core split")
     p.add_argument("--out", type=str, default=None, help="output directory (default: actions/ of the latest run, generate.py:24-26)")
     return p
 

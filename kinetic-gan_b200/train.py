@@ -65,7 +65,7 @@ def build_parser():
     p.add_argument("--data_path", type=str, required=True, help=".npy with the training sequences")
     p.add_argument("--label_path", type=str, required=True, help=".pkl with (names, labels)")
     # not in the reference
-    p.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4)")
+    p.add_argument("--precision", default="tf32", choices=["fp32", "fp32x3", "tf32"], help="libkgan arithmetic mode (DESIGN.md §4): tf32 tensor cores / fp32 FMA kernels / fp32x3 = fp32-accurate tensor-core split")
     p.add_argument("--log_interval", type=int, default=100, help="iterations between loss read-backs / prints")
     p.add_argument("--max_iters", type=int, default=-1, help="stop after this many iterations (-1: n_epochs decides)")
     p.add_argument("--no_graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
