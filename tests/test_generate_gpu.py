@@ -73,6 +73,38 @@ def test_runner_w_truncation():
     assert (a - c).abs().max().item() > 1e-4                           # the truncation really moved the latents
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_w_truncation_vs_oracle(precision):
+    """generator.py:97-108 on the GPU against the fp64 oracle fed the SAME 1000 host-RNG latents (not against the module itself):
+    runner and module output vs oracle `generator_forward(..., trunc=0.7, trunc_latents=...)`, eval mode, noise weights zero."""
+    gen = import_module("kinetic-gan_b200.generate")
+    cfg = CASES["ntu_small"]["cfg"]
+    kgan.set_precision(precision)
+    try:
+        G, pg = build(cfg)
+        z, labels = gen.class_conditioned_batch(cfg.n_classes, 8, cfg.latent_dim, seed=7)
+        n = z.shape[0]
+        runner = gen.GeneratorRunner(G, n, cfg.latent_dim, trunc=0.7, graphs=False)
+        np.random.seed(21)
+        out = runner(z.cuda(), labels.cuda()).clone()
+        np.random.seed(21)
+        t_lat = torch.as_tensor(np.random.normal(0, 1, (1000, G.mlp.mlp[0].in_features)))          # the draw of generator.py:98
+        tables = SkeletonTables(cfg.dataset)
+        pg64 = {k: (v.double() if v.is_floating_point() else v) for k, v in pg.items()}
+        nz = [torch.zeros(*s, dtype=torch.float64) for s in onet.noise_shapes(cfg, n, tables)]
+        ref = onet.generator_forward(pg64, z.double(), labels, cfg, tables, nz, training=False, trunc=0.7, trunc_latents=t_lat.double())
+        plain = onet.generator_forward(pg64, z.double(), labels, cfg, tables, nz, training=False)
+        rel = ((out.cpu().double() - ref).norm() / ref.norm()).item()
+        moved = ((plain - ref).norm() / ref.norm()).item()
+        print("W-space truncation vs fp64 oracle (%s): rel-L2 %.2e (truncation moves the output by %.2e)" % (precision, rel, moved))
+        assert rel < (2e-5 if precision == "fp32" else 5e-3), rel
+        assert moved > 100 * rel
+    finally:
+        kgan.set_precision("fp32")
+        kgan.ops._persist.clear()
+        kgan.ops._batches.clear()
+
+
 def test_runner_cached_w_mean_replays_as_graph():
     """cache_mean=True: the W-space mean is estimated once, the truncated pass is a CUDA-graph replay and equals the module's
     own truncated forward with that mean; the default keeps the reference's per-call estimate (test above)."""
