@@ -193,7 +193,7 @@ __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
 
 // The residual / label term `add` and the bias do not depend on the accumulator: their loads for the first column chunk are issued
 // BEFORE the wait on the accumulator barrier, so their latency hides behind the tile's main loop instead of following it.
-template <int ACT, bool SCAT = false, bool X3 = false>
+template <int ACT, bool SCAT = false, bool X3 = false, bool KM = false>
 __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                   const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
                                                   uint32_t tfull_bar, uint32_t tfull_parity, int rnd, const float* __restrict__ bp2 = nullptr,
@@ -222,13 +222,21 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
             for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
         float* o = op + (int64_t)col0 * p_out;
+        // one-position planes (Linear layers): a thread's 16 columns are 64 contiguous bytes of its sample's row - four 16-byte stores
+        // instead of 16 scalar ones that each touch their own 32-byte sector (lanes are samples, c_out_total floats apart)
+        // (KM: instantiated for the K-major plan only - the hot epilogues of the small-channel layers stay as they were)
+        const bool rowvec = KM && !SCAT && p_out == 1 && nc == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             float val = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
-            if (valid && j < nc) {
+            if (rowvec) {
+                r[j] = __float_as_uint(tf32_out(val, rnd));
+                if ((j & 3) == 3 && valid)
+                    *reinterpret_cast<float4*>(o + j - 3) = make_float4(__uint_as_float(r[j - 3]), __uint_as_float(r[j - 2]), __uint_as_float(r[j - 1]), __uint_as_float(r[j]));
+            } else if (valid && j < nc) {
                 const float q = tf32_out(val, rnd);
                 *o = q;
                 if (SCAT) {                                        // scatter store (kgan_tapconv_fwd_tf32_scatter): second copy of this position
@@ -236,7 +244,7 @@ __device__ __forceinline__ void tma_epilogue_tile(uint32_t taddr, int ncols, int
                     if (dz != 0) o[dz] = 0.f;                      // 0 = none); compiled out of the ordinary launches (two predicated stores per element cost
                 }                                                  // 5-25 % on the small-channel layers, whose epilogue is on the critical path)
             }
-            o += p_out;
+            if (!rowvec) o += p_out;
         }
     }
 }
@@ -589,7 +597,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                 else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
                 else tma_epilogue_tile<KGAN_ACT_NONE, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
             } else if (omap) tma_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, nullptr, d1, dz);
-            else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+            else if (pl.kmajor) {
+                if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU, false, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+                else tma_epilogue_tile<KGAN_ACT_NONE, false, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
+            } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             else tma_epilogue_tile<KGAN_ACT_NONE>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
