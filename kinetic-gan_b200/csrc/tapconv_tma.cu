@@ -253,7 +253,9 @@ __device__ __forceinline__ void tm_cp_async16(uint32_t dst, const void* src, uin
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-template <bool X3>
+// KM: the instantiation launched for the K-major (Linear-layer) plan - its epilogue stores row segments (tma_epilogue_tile<.., KM>).  A
+// separate kernel because the extra epilogue variants cost the main instantiation 8 % (100 -> 128 registers, measured on the whole step).
+template <bool X3, bool KM>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv_fwd_tma_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ TmaPlan pl,
                                                                     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
                                                                     const float* __restrict__ in, const float* __restrict__ bias,
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
     const uint32_t wfull = smem_u32(bars + 2 * S + 4);
     const int kmain = pl.nkt * d.ntap;                               // K steps of the convolution itself ...
     const int kiters = kmain + pl.nkt2;                              // ... + the extra panel: a 1x1 conv of a second tensor into the same accumulator
-    const bool use_tma = pl.p_box == 32 || pl.kmajor;                // else: cp.async producers (warps 10-13)
+    const bool kmajor = X3 ? pl.kmajor != 0 : KM;                    // (a compile-time constant in the two tf32-mode instantiations)
+    const bool use_tma = pl.p_box == 32 || kmajor;                   // else: cp.async producers (warps 10-13)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                         const bool panel = it >= kmain;                                 // extra K panel: second tensor, no shift
                         const int ch0 = panel ? (it - kmain) * UK : ch_g + d.tap_in_ch[tap] + ict * UK, sh = panel ? 0 : d.tap_shift[tap];
                         const CUtensorMap* tm = panel ? &tmap2 : &tmap;
-                        if (pl.kmajor) {
+                        if (kmajor) {
                             tma_load_3d(a_dst, tm, ch0, tc.mt * UM, 0, full0 + 8 * s);         // (channel, sample, -): rows past n / channels past C read zero
                         } else if (use_tma) {
 #pragma unroll
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
         // ===== MMA issuer (whole warp waits, one elected lane issues) =====
         {
             const bool leader = elect_one();
-            const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (pl.kmajor ? 0u : (1u << 15));      // A operand MN-major unless kmajor
+            const uint32_t idesc = instr_desc_tf32(pl.n_cta) | (kmajor ? 0u : (1u << 15));      // A operand MN-major unless kmajor
             const uint32_t b_lbo = pl.n_cta * 16;
             int s = 0, ti = 0;
             uint32_t ph = 0;
@@ -452,8 +455,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                             const uint32_t blo_addr = b_addr + (pl.w_res ? (uint32_t)pl.img1_bytes : (uint32_t)b_stage_bytes);
 #pragma unroll
                             for (int j = 0; j < UK / 8; ++j) {
-                                const uint64_t ad = pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo);
-                                const uint64_t ald = pl.kmajor ? smem_desc_k_sw128(alo_addr + j * 32) : smem_desc_mn_sw128(alo_addr + j * 1024, pl.a_lbo, pl.a_sbo);
+                                const uint64_t ad = kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo);
+                                const uint64_t ald = kmajor ? smem_desc_k_sw128(alo_addr + j * 32) : smem_desc_mn_sw128(alo_addr + j * 1024, pl.a_lbo, pl.a_sbo);
                                 const uint64_t bd = smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), bld = smem_desc(blo_addr + j * 2 * b_lbo, b_lbo, CORE_SBO);
                                 umma_tf32(acc + pl.n_cta, ald, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
                                 umma_tf32(acc + pl.n_cta, ad, bld, idesc, 1u);
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                         } else {
 #pragma unroll
                             for (int j = 0; j < UK / 8; ++j)
-                                umma_tf32(acc, pl.kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
+                                umma_tf32(acc, kmajor ? smem_desc_k_sw128(a_addr + j * 32) : smem_desc_mn_sw128(a_addr + j * 1024, pl.a_lbo, pl.a_sbo),
                                           smem_desc(b_addr + j * 2 * b_lbo, b_lbo, CORE_SBO), idesc, (it > 0 || j > 0) ? 1u : 0u);
                         }
                         umma_commit(empty0 + 8 * s);
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                 else if (d.act == KGAN_ACT_TANH) tma_epilogue_tile<KGAN_ACT_TANH, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
                 else tma_epilogue_tile<KGAN_ACT_NONE, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2, 0, 0, pl.n_cta);
             } else if (omap) tma_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, nullptr, d1, dz);
-            else if (pl.kmajor) {
+            else if (KM) {
                 if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU, false, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
                 else tma_epilogue_tile<KGAN_ACT_NONE, false, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
             } else if (d.act == KGAN_ACT_LRELU) tma_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, bp2);
@@ -695,13 +698,19 @@ static int launch_tma(const kgan_tapconv_desc& d, TmaPlan& p, const float* in, c
     static SmemAttrOnce attr, attr3;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
     if (p.x3) {
-        if (int e = ensure_smem(tapconv_fwd_tma_k<true>, 227 * 1024, attr3, "tapconv_fwd_tma (x3) attribute")) return e;
-        tapconv_fwd_tma_k<true><<<grid, TM_THREADS_X3, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out, tmap2, wp2, in2, bias2, omap);
+        if (int e = ensure_smem(tapconv_fwd_tma_k<true, false>, 227 * 1024, attr3, "tapconv_fwd_tma (x3) attribute")) return e;
+        tapconv_fwd_tma_k<true, false><<<grid, TM_THREADS_X3, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out, tmap2, wp2, in2, bias2, omap);
         return check_launch("tapconv_fwd_tma (x3)");
     }
-    if (int e = ensure_smem(tapconv_fwd_tma_k<false>, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
-    tapconv_fwd_tma_k<false><<<grid, (p.p_box == 32 || p.kmajor) ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
-                                                                                                                           tmap2, wp2, in2, bias2, omap);
+    if (p.kmajor) {
+        static SmemAttrOnce attrk;
+        if (int e = ensure_smem(tapconv_fwd_tma_k<false, true>, 227 * 1024, attrk, "tapconv_fwd_tma (K-major) attribute")) return e;
+        tapconv_fwd_tma_k<false, true><<<grid, TM_THREADS_TMA, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out, tmap2, wp2, in2, bias2, omap);
+        return check_launch("tapconv_fwd_tma (K-major)");
+    }
+    if (int e = ensure_smem(tapconv_fwd_tma_k<false, false>, 227 * 1024, attr, "tapconv_fwd_tma attribute")) return e;
+    tapconv_fwd_tma_k<false, false><<<grid, p.p_box == 32 ? TM_THREADS_TMA : TM_THREADS_CP, p.smem_bytes, stream>>>(d, p, tmap, wp, in, bias, add, out,
+                                                                                                                   tmap2, wp2, in2, bias2, omap);
     return check_launch("tapconv_fwd_tma");
 }
 
