@@ -53,6 +53,11 @@ constexpr int TM_SPLIT_WARPS = 4;
 constexpr int TM_SPLIT_WARP0 = TM_EPI_WARP0 + TM_EPI_WARPS + TM_CP_WARPS;      // 14 (warps 12, 13 idle in TMA mode)
 constexpr int TM_THREADS_X3 = 32 * (TM_SPLIT_WARP0 + TM_SPLIT_WARPS);
 
+// Ring size.  A deeper ring does not help: with 10 stages (216 KB) the 3-tap D1 layer measured 337 us against 327 us with 8 - the kernel is
+// not bound by its own bytes in flight but by what the L2 delivers for the taps' re-reads (profiles/r2_ncu_full_d1tcn_b4096.txt)
+constexpr int TM_SMEM_BUDGET = 200 * 1024;
+constexpr int TM_MAX_STAGES = 8;
+
 struct TmaPlan {
     int n_cta, n_split, n_rows, tmem_cols, nkt;   // identical to UmmaPlan (the packed weight image is shared)
     int p_box, n_box, p_shift;                    // box = p_box positions x n_box samples; p_box = 1 << p_shift
@@ -108,8 +113,8 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck =
     p.num_tiles = p.m_tiles * p.n_split * d.groups;
     const int xm = p.x3 ? 2 : 1;                                   // x3: every stage holds a lo image next to each operand image
     const int stage = xm * (A_STAGE_BYTES + p.n_cta * UK * 4);
-    p.stages = (200 * 1024) / stage;
-    if (p.stages > 8) p.stages = 8;
+    p.stages = TM_SMEM_BUDGET / stage;
+    if (p.stages > TM_MAX_STAGES) p.stages = TM_MAX_STAGES;
     if (p.stages < 2) return false;
     p.smem_bytes = p.stages * stage + 1024 + 512;                  // + alignment slack + barriers
     p.w_lo_off = (int64_t)d.groups * p.nkt * d.ntap * p.n_rows * UK;
@@ -124,8 +129,8 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck =
         p.img1_bytes = (int)img1;
         const int64_t tiles_per_cta = ceil_div64(p.num_tiles, kNumSMs);
         if (p.n_split == 1 && img <= 112 * 1024 && tiles_per_cta >= 2) {
-            int st = (int)((200 * 1024 - img) / (xm * A_STAGE_BYTES));
-            if (st > 8) st = 8;
+            int st = (int)((TM_SMEM_BUDGET - img) / (xm * A_STAGE_BYTES));
+            if (st > TM_MAX_STAGES) st = TM_MAX_STAGES;
             if (st >= (p.x3 ? 3 : 5)) {
                 p.w_res = 1;
                 p.w_res_bytes = (int)img;
