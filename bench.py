@@ -374,13 +374,14 @@ def run_kgan(args):
         x = resident[i % POOL]
         return tr.iteration(i, x["real"], x["labels"], x["z"], x["alpha"])
 
+    nxt = [None]
+
     def step_e2e(i):
-        h = host[i % POOL]
-        if graphs:                                # pinned host buffers are copied straight into the graphs' static inputs
-            x = h
-        else:
-            x = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        d_loss, _, _ = tr.iteration(i, x["real"], x["labels"], x["z"], x["alpha"])
+        # every step: ONE host -> device copy of a batch from pinned memory - the NEXT step's, started on the trainer's copy stream so that
+        # it overlaps this step (WGANGPTrainer.prefetch, what train.py's BatchStream does) - and the read-back of this step's loss
+        x = nxt[0] if nxt[0] is not None else tr.prefetch(**host[i % POOL])
+        nxt[0] = tr.prefetch(**host[(i + 1) % POOL])
+        d_loss, _, _ = tr.iteration(i, *x)
         return d_loss.item()                      # device -> host read of the step's result
 
     def timed(fn, first):

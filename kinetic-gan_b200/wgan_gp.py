@@ -92,6 +92,7 @@ class WGANGPTrainer:
         self.fg, self.fd = FlatParams(self.G), FlatParams(self.D)
         self.world = 1 if comm is None else comm.world_size
         self._graphs = None
+        self._copy = None                         # prefetch(): copy stream, two staging slots, the event of the copy in flight
         self.use_graphs = True      # set False to run eagerly even after capture_graphs() (per-kernel profiling)
 
     def _reduce(self, flat):
@@ -201,12 +202,43 @@ class WGANGPTrainer:
 
     def synchronize_updates(self):
         """Makes the main stream wait for the optimizer updates still running on the side stream (call before reading parameters
-        outside `iteration()`: checkpoints, evaluation, eager passes)."""
+        outside `iteration()`: checkpoints, evaluation, eager passes) and for a prefetch() still in flight."""
         g = self._graphs
         if g is not None:
             for key in ("d_done", "g_done"):
                 if g[key] is not None:
                     torch.cuda.current_stream().wait_event(g[key])
+        if self._copy is not None and self._copy["event"] is not None:
+            torch.cuda.current_stream().wait_event(self._copy["event"])
+
+    def prefetch(self, real, labels, z, alpha=None):
+        """Starts the host -> device copy of the NEXT iteration's inputs (pinned host tensors) on a copy stream, so that it overlaps the
+        iteration in flight, and returns the device tensors to hand to `iteration()` / `d_step()` (which wait for the copy).  Two staging
+        slots: a slot is rewritten only after the iteration that read it has been enqueued."""
+        c = self._copy
+        if c is None:
+            c = self._copy = {"stream": torch.cuda.Stream(), "slots": [None, None], "i": 0, "event": None, "ids": ()}
+        c["i"] ^= 1
+        src = {"real": real, "labels": labels, "z": z, "alpha": alpha}
+        dev = self.fd.flat.device
+        slot = c["slots"][c["i"]]
+        if slot is None or any(v is not None and (k not in slot or slot[k].shape != v.shape or slot[k].dtype != v.dtype) for k, v in src.items()):
+            slot = c["slots"][c["i"]] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items() if v is not None}
+        cs = c["stream"]
+        cs.wait_stream(torch.cuda.current_stream())        # the slot's previous reader (two iterations back) is on the main stream
+        with torch.cuda.stream(cs):
+            for k, v in src.items():
+                if v is not None:
+                    slot[k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        c["event"], c["ids"] = ev, tuple(id(t) for t in slot.values())
+        return slot["real"], slot["labels"], slot["z"], slot.get("alpha")
+
+    def _await_prefetch(self, *tensors):
+        c = self._copy
+        if c is not None and c["event"] is not None and any(id(t) in c["ids"] for t in tensors if t is not None):
+            torch.cuda.current_stream().wait_event(c["event"])
 
     def d_step(self, real, labels, z, alpha=None, noises=None):
         """kinetic-gan.py:137-155."""
@@ -260,6 +292,7 @@ class WGANGPTrainer:
         return g_loss
 
     def iteration(self, i, real, labels, z, alpha=None, noises_d=None, noises_g=None):
+        self._await_prefetch(real, labels, z, alpha)
         d_loss, gp = self.d_step(real, labels, z, alpha, noises_d)
         g_loss = self.g_step(labels, z, noises_g) if i % self.n_critic == 0 else None
         return d_loss, g_loss, gp

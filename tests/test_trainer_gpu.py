@@ -101,3 +101,44 @@ def test_graph_replay_matches_eager(precision):
         kgan.set_precision("fp32")
         ops._persist.clear()
         ops._batches.clear()
+
+
+def test_prefetch_overlapped_inputs_match_direct_inputs():
+    """WGANGPTrainer.prefetch (the next iteration's host -> device copy on a copy stream, two staging slots) feeds the captured graphs
+    the same numbers as handing pinned host tensors to iteration() directly: first critic loss bit-equal (the forward pass has no
+    atomics), parameters after three critic updates equal up to atomics-order noise."""
+    cfg, n = CASES["ntu_small"]["cfg"], 8
+    wg = import_module("kinetic-gan_b200.wgan_gp")
+    kgan.set_precision("fp32")
+    try:
+        res = []
+        for use_prefetch in (False, True):
+            G, D = build(cfg)
+            with torch.no_grad():
+                for blk in G.st_gcn_networks:
+                    blk.noise.weight.zero_()
+            tr = wg.WGANGPTrainer(G, D, cfg.lr, cfg.b1, cfg.b2, cfg.n_critic, cfg.lambda_gp)
+            x0 = {k: v.cuda() for k, v in inputs(cfg, n, 20, torch.float32).items()}
+            tr.capture_graphs(x0["real"], x0["labels"], x0["z"], x0["alpha"])
+            host = [{k: v.pin_memory() for k, v in inputs(cfg, n, 20 + i, torch.float32).items() if k in ("real", "labels", "z", "alpha")}
+                    for i in range(1, 5)]
+            losses = []
+            nxt = tr.prefetch(**host[0]) if use_prefetch else None
+            for i in range(1, 4):
+                if use_prefetch:
+                    x, nxt = nxt, tr.prefetch(**host[i])          # the copy of iteration i + 1 overlaps iteration i
+                    d_loss, _, _ = tr.iteration(i, *x)
+                else:
+                    h = host[i - 1]
+                    d_loss, _, _ = tr.iteration(i, h["real"], h["labels"], h["z"], h["alpha"])
+                losses.append(d_loss.item())
+            tr.synchronize_updates()
+            torch.cuda.synchronize()
+            res.append((losses, tr.fd.flat.clone()))
+        (l0, f0), (l1, f1) = res
+        assert l0[0] == l1[0], (l0, l1)
+        assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-3 * max(1.0, abs(l0[-1]))
+        assert (f0 - f1).abs().max().item() < 3 * cfg.lr
+    finally:
+        ops._persist.clear()
+        ops._batches.clear()
