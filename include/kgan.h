@@ -222,6 +222,13 @@ int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c
  * two branches) and leaky_relu_backward over the same tensor. */
 int kgan_adjmix_bwd_x_fused(const float* gout, const float* A, const float* add, const float* ysrc, float* gx, int n, int c, int t, int v,
                             int w, int k, int out_tf32, void* stream);
+/* Same, with the residual branch's gradient given where that branch lives: `add_c` is COMPACT, shaped (n, c, pc) - the frames / joints
+ * the residual branch kept (discriminator.py:132-134: x[..., keep] at every other frame) - and inv[p] (int32, t * v entries) is the
+ * compact position of plane position p, -1 where the branch did not read x:
+ *   gx[r, p] = ( mix[r, p] + (inv[p] >= 0 ? add_c[r, inv[p]] : 0) ) * slope(ysrc[r, p])
+ * The adjoint of the selection is taken here instead of by a scatter kernel writing a mostly-zero full-size tensor. */
+int kgan_adjmix_bwd_x_fused_sel(const float* gout, const float* A, const float* add_c, const int32_t* inv, int pc, const float* ysrc, float* gx,
+                                int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
 /* gA[k, v, w] = sum_r x[r, v] * gout[r, k, w]  (gA overwritten) */
 int kgan_adjmix_bwd_a(const float* x, const float* gout, float* gA, int n, int c, int t, int v, int w, int k, void* stream);
 /* Same, restricted to the support of `mask` (K, V, W): gA[k, v, w] = 0 where mask[k, v, w] == 0.  The callers pass the

@@ -76,25 +76,56 @@ struct MixEntry {
 // like `out`.  It is the join of a critic block's backward: the gradient of the residual branch (`add`) and the LeakyReLU slope of
 // the block INPUT (`ysrc` = the previous block's activated output, slope 0.2 where it is <= 0) are applied where the graph-conv
 // branch's input gradient is produced, instead of by an elementwise add and a mask kernel over the same tensor.
+// `inv` (kgan_adjmix_bwd_x_fused_sel): `add` is a COMPACT tensor (n, c, pc) - the residual branch's gradient at the frames / joints that
+// branch kept - and inv[p] is the compact position of plane position p = t * V + v (-1: not kept): the adjoint of the selection is taken
+// here instead of by a scatter kernel that writes a mostly-zero full-size tensor for this kernel to read back.
 struct MixEpi {
     const float* add;
     const float* ysrc;
     int rnd;
+    const int32_t* inv = nullptr;
+    int pc = 0, frames = 0;      // compact plane size; frames per channel (rows of the output are (channel, frame) pairs)
 };
-__device__ __forceinline__ float mix_fin(float v, const MixEpi& e, int64_t idx) {
-    if (e.add) v += __ldg(e.add + idx);
+__device__ __forceinline__ float mix_fin(float v, const MixEpi& e, int64_t idx, int wo = 0) {
+    if (e.add) {
+        if (e.inv) {             // idx = (row r = (n * C + c) * T + t) * wo + joint  (MODE 1: one output block per sample)
+            const int64_t r = idx / wo;
+            const int j = (int)(idx - r * wo);
+            const int64_t nc = r / e.frames;
+            const int ci = __ldg(e.inv + (int)(r - nc * e.frames) * wo + j);
+            if (ci >= 0) v += __ldg(e.add + nc * e.pc + ci);
+        } else {
+            v += __ldg(e.add + idx);
+        }
+    }
     if (e.ysrc) v *= (__ldg(e.ysrc + idx) > 0.f ? 1.f : 0.2f);
     return tf32_out(v, e.rnd);
 }
 // the same for the pipelined kernel: EPI = false compiles the epilogue operands (and their address arithmetic) away; with EPI the two
 // operand pointers advance like the output pointer
-template <bool EPI>
+template <int EPI>
 __device__ __forceinline__ float mix_fin2(float v, const float* ap, const float* yp, int off, int rnd) {
     if (EPI) {
-        if (ap) v += __ldg(ap + off);
+        if (EPI == 1 && ap) v += __ldg(ap + off);
         if (yp) v *= (__ldg(yp + off) > 0.f ? 1.f : 0.2f);
     }
     return tf32_out(v, rnd);
+}
+// EPI == 2: the compact `add` through the inverse selection map.  (c, t) = channel / frame of the thread's current row, advanced with the row
+struct SelPos {
+    int c, t;
+};
+__device__ __forceinline__ float sel_add(const MixEpi& e, int64_t nc0, SelPos ps, int wo, int col) {
+    const int ci = __ldg(e.inv + ps.t * wo + col);
+    return ci >= 0 ? __ldg(e.add + (nc0 + ps.c) * e.pc + ci) : 0.f;
+}
+__device__ __forceinline__ SelPos sel_next(SelPos ps, int step, int frames) {
+    ps.t += step;
+    while (ps.t >= frames) {
+        ps.t -= frames;
+        ++ps.c;
+    }
+    return ps;
 }
 
 template <int MODE>
@@ -147,7 +178,7 @@ __global__ void __launch_bounds__(AT) adjmix_rowmix_k(const float* __restrict__ 
                 const int c = cnt[o];
                 for (int j = 0; j < c; ++j) acc = fmaf(el[j].coef, __ldg(xq + el[j].off), acc);
             }
-            r[u] = (e0 + u < plane) ? mix_fin(acc, epi, nb * (int64_t)plane + e0 + u) : 0.f;
+            r[u] = (e0 + u < plane) ? mix_fin(acc, epi, nb * (int64_t)plane + e0 + u, wo) : 0.f;
             if (++ww == (unsigned)wo) {
                 ww = 0;
                 ++q;
@@ -268,9 +299,9 @@ struct Mix2Plan {
 };
 
 // rows q, q + rs, ... of one output column: LT = (padded) length of the column's non-zero list, held in registers
-template <int LT, bool EPI>
+template <int LT, int EPI>
 __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const MixEntry* __restrict__ el, float* __restrict__ ob, int q, int rs, int rows,
-                                         int vi, int wo, const MixEpi& epi, int64_t obase) {
+                                         int vi, int wo, const MixEpi& epi, int64_t obase, int64_t nc0 = 0, int row0 = 0, int col = 0) {
     float cf[LT > 0 ? LT : 1];
     int of[LT > 0 ? LT : 1];
 #pragma unroll
@@ -281,12 +312,27 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
     }
     const float* xp = xs + q * vi;
     float* op = ob + (size_t)q * wo;
-    const float* ap = (EPI && epi.add) ? epi.add + obase + (int64_t)q * wo : nullptr;
+    const float* ap = (EPI == 1 && epi.add) ? epi.add + obase + (int64_t)q * wo : nullptr;
     const float* yp = (EPI && epi.ysrc) ? epi.ysrc + obase + (int64_t)q * wo : nullptr;
     const int rnd = epi.rnd;
     const int xstep = rs * vi, ostep = rs * wo;
+    SelPos ps{0, 0};
+    if (EPI == 2) {
+        ps.c = (row0 + q) / epi.frames;
+        ps.t = (row0 + q) - ps.c * epi.frames;
+    }
     for (; q + 3 * rs < rows; q += 4 * rs, xp += 4 * xstep, op += 4 * ostep) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (EPI == 2) {          // the residual branch's gradient at this thread's four rows (issued before the shared-memory sums)
+            a0 = sel_add(epi, nc0, ps, wo, col);
+            ps = sel_next(ps, rs, epi.frames);
+            a1 = sel_add(epi, nc0, ps, wo, col);
+            ps = sel_next(ps, rs, epi.frames);
+            a2 = sel_add(epi, nc0, ps, wo, col);
+            ps = sel_next(ps, rs, epi.frames);
+            a3 = sel_add(epi, nc0, ps, wo, col);
+            ps = sel_next(ps, rs, epi.frames);
+        }
 #pragma unroll
         for (int j = 0; j < LT; ++j) {
             a0 = fmaf(cf[j], xp[of[j]], a0);
@@ -305,6 +351,10 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
     }
     for (; q < rows; q += rs, xp += xstep, op += ostep) {
         float a0 = 0.f;
+        if (EPI == 2) {
+            a0 = sel_add(epi, nc0, ps, wo, col);
+            ps = sel_next(ps, rs, epi.frames);
+        }
 #pragma unroll
         for (int j = 0; j < LT; ++j) a0 = fmaf(cf[j], xp[of[j]], a0);
         op[0] = mix_fin2<EPI>(a0, ap, yp, 0, rnd);
@@ -319,11 +369,11 @@ __device__ __noinline__ void mix_rows_any(const float* __restrict__ xs, const Mi
     for (; q < rows; q += rs) {
         float a0 = 0.f;
         for (int j = 0; j < L; ++j) a0 = fmaf(el[j].coef, xs[q * vi + el[j].off], a0);
-        ob[(size_t)q * wo] = mix_fin(a0, epi, obase + (int64_t)q * wo);
+        ob[(size_t)q * wo] = mix_fin(a0, epi, obase + (int64_t)q * wo, wo);
     }
 }
 
-template <int MODE, bool EPI>
+template <int MODE, int EPI>
 __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restrict__ in, const float* __restrict__ A, float* __restrict__ out, int ct, int v,
                                                         int w, int k, const __grid_constant__ Mix2Plan pl, MixEpi epi) {
     extern __shared__ __align__(128) float sm[];
@@ -412,16 +462,17 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
                 const MixEntry* el = ent + ((size_t)kb * wo + my_w) * lc;          // this thread's list: same output column for every row
                 const int64_t obase = ((nn * ko + kb) * (int64_t)ct + q0) * wo + my_w;       // element index of ob[0] in out / add / ysrc
                 float* ob = out + obase;
+                const int64_t nc0 = EPI == 2 ? nn * (ct / epi.frames) : 0;           // (sample, channel 0) row of the compact `add`
                 switch (L) {
-                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
-                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase); break;
+                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
                     default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, epi, obase); break;
                 }
             }
@@ -611,14 +662,18 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
                 pl.smem_bytes = (int)smem2;
                 if (smem2 <= 100 * 1024) {
                     static SmemAttrOnce attr2, attr3;
-                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, false>, 100 * 1024, attr2, "adjmix attribute")) return e;
-                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, true>, 100 * 1024, attr3, "adjmix attribute")) return e;
+                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 0>, 100 * 1024, attr2, "adjmix attribute")) return e;
+                    if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 1>, 100 * 1024, attr3, "adjmix attribute")) return e;
                     const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
                     const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
                     const int64_t waves = ceil_div64(pl.tiles, cap);
                     const int64_t grid2 = ceil_div64(pl.tiles, waves);   // every CTA gets `waves` tiles (+-1), all CTAs co-resident
-                    if (epi.add || epi.ysrc) adjmix_rowmix2_k<MODE, true><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
-                    else adjmix_rowmix2_k<MODE, false><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
+                    if (epi.add && epi.inv) {
+                        static SmemAttrOnce attr4;
+                        if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 2>, 100 * 1024, attr4, "adjmix attribute")) return e;
+                        adjmix_rowmix2_k<MODE, 2><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
+                    } else if (epi.add || epi.ysrc) adjmix_rowmix2_k<MODE, 1><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
+                    else adjmix_rowmix2_k<MODE, 0><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
                     return check_launch(what);
                 }
             }
@@ -645,6 +700,16 @@ extern "C" int kgan_adjmix_bwd_x_fused(const float* g, const float* A, const flo
                                        int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(g && A && gx, "adjmix_bwd_x_fused: null pointer");
     return launch_rowmix<1>("adjmix_bwd_x_fused", g, A, gx, n, c, t, v, w, k, MixEpi{add, ysrc, out_tf32}, stream);
+}
+
+extern "C" int kgan_adjmix_bwd_x_fused_sel(const float* g, const float* A, const float* add_c, const int32_t* inv, int pc, const float* ysrc, float* gx,
+                                           int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
+    KGAN_REQUIRE(g && A && gx && add_c && inv && pc > 0, "adjmix_bwd_x_fused_sel: null pointer");
+    MixEpi epi{add_c, ysrc, out_tf32};
+    epi.inv = inv;
+    epi.pc = pc;
+    epi.frames = t;
+    return launch_rowmix<1>("adjmix_bwd_x_fused_sel", g, A, gx, n, c, t, v, w, k, epi, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_a(const float* x, const float* g, float* gA, int n, int c, int t, int v, int w, int k, void* stream) {

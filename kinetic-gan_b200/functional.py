@@ -271,14 +271,15 @@ class AdjMix(Function):
 
 class AdjMixDx(Function):
     """gx = Dx(g, A) [+ add] [* leaky_relu'(mask_src)] - the optional terms are the fused epilogue of kgan_adjmix_bwd_x_fused
-    (see GcnRes); `mask_src` is a constant here (the slope is piecewise constant in it)."""
+    (see GcnRes); `mask_src` is a constant here (the slope is piecewise constant in it).  `add_sel` (a selection PlaneTable): `add` is
+    given in the selection's compact layout and enters through the selection's adjoint (kgan_adjmix_bwd_x_fused_sel)."""
 
     @staticmethod
-    def forward(ctx, g, A, support=None, add=None, mask_src=None):
+    def forward(ctx, g, A, support=None, add=None, mask_src=None, add_sel=None):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, A, mask_src)
-        ctx.support = support
-        return ops.adjmix_bwd_x(_c(g), _c(A), None if add is None else _c(add), None if mask_src is None else _c(mask_src.detach()))
+        ctx.support, ctx.add_sel = support, add_sel
+        return ops.adjmix_bwd_x(_c(g), _c(A), None if add is None else _c(add), None if mask_src is None else _c(mask_src.detach()), add_sel)
 
     @staticmethod
     def backward(ctx, h):
@@ -291,8 +292,10 @@ class AdjMixDx(Function):
         gg = AdjMix.apply(h, A, ctx.support) if ctx.needs_input_grad[0] else None
         gA = AdjMixDA.apply(h, g, A.shape[0], ctx.support) if _want(ctx, 1) else None
         nig = ctx.needs_input_grad                                  # as long as the argument list of this apply() call
-        gadd = h if (len(nig) > 3 and nig[3]) else None
-        return (gg, gA, None, gadd, None)[:len(nig)]
+        gadd = None
+        if len(nig) > 3 and nig[3]:
+            gadd = h if ctx.add_sel is None else PlaneSpmm.apply(h, ctx.add_sel)
+        return (gg, gA, None, gadd, None, None)[:len(nig)]
 
 
 class AdjMixDA(Function):
@@ -370,7 +373,7 @@ class GcnRes(Function):
         gx = gA = gw_gcn = gw_res = gb = None
         recorded = torch.is_grad_enabled()                       # create_graph: intermediates must be graph nodes of (x, A)
         # residual branch first: its input gradient is an operand of the kernel that closes the graph-conv branch
-        gx_r = None
+        gx_r = add_sel = None
         if gr is not None:
             gr = _c(gr)
             if w_res is not None:
@@ -382,7 +385,10 @@ class GcnRes(Function):
             else:
                 gxs = gr if nig[0] else None
             if gxs is not None:
-                gx_r = gxs if ctx.sel is None else PlaneSpmm.apply(gxs, ctx.sel.T)
+                if ctx.sel is not None and gg is not None and nig[0] and ctx.sel.inverse_gather() is not None:
+                    gx_r, add_sel = gxs, ctx.sel       # stays compact: the selection's adjoint is taken by the kernel that joins the branches
+                else:
+                    gx_r = gxs if ctx.sel is None else PlaneSpmm.apply(gxs, ctx.sel.T)
         mask = x if ctx.mask_input else None
         if gg is not None:
             gg = _c(gg)
@@ -394,7 +400,7 @@ class GcnRes(Function):
             if nig[0] or _want(ctx, 1):
                 g_xa = TapConvDgrad.apply(gg, w_gcn, ctx.gcn_geom)
                 gA = AdjMixDA.apply(x, g_xa, A.shape[0], ctx.support) if _want(ctx, 1) else None
-                gx = AdjMixDx.apply(g_xa, A, ctx.support, gx_r, mask) if nig[0] else None
+                gx = AdjMixDx.apply(g_xa, A, ctx.support, gx_r, mask, add_sel) if nig[0] else None
         elif gx_r is not None:
             gx = ActGrad.apply(gx_r, x, ACT_LRELU) if ctx.mask_input else gx_r
         return (gx, gA, gw_gcn, gw_res, gb, None, None, None, None, None, None, None)[:len(nig)]

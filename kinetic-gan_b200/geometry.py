@@ -311,6 +311,21 @@ class PlaneTable:
         self._scatter = m
         return m
 
+    def inverse_gather(self):
+        """For a selection table (every output position copies ONE input position with weight 1, no input position copied twice): the
+        int32 array inv[p_in] = output position that copies p, -1 if none - the form kgan_adjmix_bwd_x_fused_sel takes the adjoint of
+        the selection in.  None if the table is not of that form."""
+        if not hasattr(self, "_inv"):
+            self._inv = None
+            if self.J == 1 and np.all(self.idx[:, 0] >= 0) and np.all(self.wgt[:, 0] == 1.0) and len(np.unique(self.idx[:, 0])) == self.p_out:
+                inv = np.full(self.p_in, -1, np.int32)
+                inv[self.idx[:, 0]] = np.arange(self.p_out, dtype=np.int32)
+                self._inv = inv
+        return self._inv
+
+    def inverse_on(self, device):
+        return self._dev.get("inv", device, lambda: torch.from_numpy(self.inverse_gather()))
+
     def scatter_on(self, device):
         return self._dev.get("scatter", device, lambda: torch.from_numpy(self.scatter_map()))
 

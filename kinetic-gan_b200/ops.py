@@ -403,18 +403,25 @@ def adjmix_fwd(x, A):
     return out
 
 
-def adjmix_bwd_x(g, A, add=None, mask_src=None):
-    """`add`, `mask_src` (optional, shaped like the result): gx = (product + add) * leaky_relu'(mask_src) in the same kernel."""
+def adjmix_bwd_x(g, A, add=None, mask_src=None, add_sel=None):
+    """`add`, `mask_src` (optional, shaped like the result): gx = (product + add) * leaky_relu'(mask_src) in the same kernel.
+    `add_sel` (a selection PlaneTable with inverse_gather()): `add` is COMPACT - shaped like the selection's output - and enters at the
+    positions the selection reads (the adjoint of the selection, taken inside the kernel: kgan_adjmix_bwd_x_fused_sel)."""
     _chk(g, A, add, mask_src)
     k, v, w = A.shape
     n, kc, t, w2 = g.shape
     assert w2 == w and kc % k == 0
     c = kc // k
     gx = torch.empty((n, c, t, v), device=g.device, dtype=torch.float32)
-    assert add is None or add.shape == gx.shape
     assert mask_src is None or mask_src.shape == gx.shape
     _shape_sig(g, A)
     _io(g, A, add, mask_src, gx)
+    if add_sel is not None:
+        assert add is not None and add_sel.p_in == t * v and tuple(add.shape) == (n, c, add_sel.t_out, add_sel.v_out), (tuple(add.shape), t, v)
+        _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x_fused_sel, g.data_ptr(), A.data_ptr(), add.data_ptr(), add_sel.inverse_on(g.device).data_ptr(),
+             add_sel.p_out, _ptr(mask_src), gx.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
+        return gx
+    assert add is None or add.shape == gx.shape
     if add is None and mask_src is None:
         _run('adjmix', 0.0, _lib.lib().kgan_adjmix_bwd_x, g.data_ptr(), A.data_ptr(), gx.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
     else:

@@ -94,10 +94,13 @@ def adjmix_fwd(x, A):
     return torch.einsum("nctv,kvw->nkctw", x, A).reshape(n, k * c, t, w)
 
 
-def adjmix_bwd_x(g, A, add=None, mask_src=None):
+def adjmix_bwd_x(g, A, add=None, mask_src=None, add_sel=None):
     k, v, w = A.shape
     n, kc, t, _ = g.shape
     out = torch.einsum("nkctw,kvw->nctv", g.reshape(n, k, kc // k, t, w), A)
+    if add is not None and add_sel is not None:                 # compact residual gradient through the selection's adjoint
+        assert add_sel.inverse_gather() is not None
+        add = plane_spmm(add, add_sel.T)
     if add is not None:
         out = out + add
     if mask_src is not None:

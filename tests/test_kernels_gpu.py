@@ -193,3 +193,34 @@ def test_plane_sum_t_and_tiny_adjmix():
     assert rel(ops.adjmix_fwd(cu(b), cu(A)), emu.adjmix_fwd(dbl(b), dbl(A))) < TOL
     g = rnd(300, 32, 1, 12, seed=3)
     assert rel(ops.adjmix_bwd_x(cu(g), cu(A)), emu.adjmix_bwd_x(dbl(g), dbl(A))) < TOL
+
+
+@pytest.mark.parametrize("case", [
+    # (n, c, t, v, w, k, dense adjacency, t_sel step, kept joints)
+    (5, 64, 64, 12, 5, 3, False, 2, [1, 4, 6, 9, 11]),      # D2-like: pipelined kernel, short non-zero lists
+    (3, 128, 32, 5, 5, 3, True, 2, [4]),                     # dense A (lists of 15 entries: the generic row loop), one kept joint
+    (2, 2, 4, 12, 5, 3, False, 2, [0, 2, 3]),                # tiny plane: the plain kernel
+    (4, 32, 16, 11, 11, 3, False, 1, [0, 5, 10]),            # joints selected, every frame kept
+])
+def test_adjmix_bwd_x_fused_epilogues(case):
+    """kgan_adjmix_bwd_x_fused (add + LeakyReLU slope of the block input) and kgan_adjmix_bwd_x_fused_sel (the residual branch's gradient
+    given in the selection's compact layout, its adjoint taken inside the kernel) against the float64 statement."""
+    n, c, t, v, w, k, dense, step, keep = case
+    G = kgan.geometry
+    g = rnd(n, k * c, t, w, seed=1)
+    A = rnd(k, v, w, seed=2) if dense else sparse_adjacency(k, v, w, 3)
+    add = rnd(n, c, t, v, seed=4)
+    src = rnd(n, c, t, v, seed=5)
+    ref = emu.adjmix_bwd_x(dbl(g), dbl(A), dbl(add), dbl(src))
+    assert rel(ops.adjmix_bwd_x(cu(g), cu(A), cu(add), cu(src)), ref) < TOL
+    assert rel(ops.adjmix_bwd_x(cu(g), cu(A), cu(add), None), emu.adjmix_bwd_x(dbl(g), dbl(A), dbl(add), None)) < TOL
+    sel = G.select_table(t, v, list(range(0, t, step)), keep)
+    assert sel.inverse_gather() is not None
+    addc = rnd(n, c, sel.t_out, sel.v_out, seed=6)
+    for m in (src, None):
+        got = ops.adjmix_bwd_x(cu(g), cu(A), cu(addc), None if m is None else cu(m), sel)
+        want = emu.adjmix_bwd_x(dbl(g), dbl(A), emu.plane_spmm(dbl(addc), sel.T), None if m is None else dbl(m))
+        assert rel(got, want) < TOL
+    # the same result as the two-kernel formulation it replaces (scatter, then fused add) up to the order of the fp32 additions
+    full = ops.plane_spmm(cu(addc), sel.T)
+    assert rel(ops.adjmix_bwd_x(cu(g), cu(A), cu(addc), cu(src), sel), ops.adjmix_bwd_x(cu(g), cu(A), full, cu(src)).cpu()) < 1e-6
