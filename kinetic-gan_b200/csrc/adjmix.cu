@@ -116,12 +116,15 @@ struct SelPos {
     int c, t;
 };
 __device__ __forceinline__ float sel_add(const MixEpi& e, int64_t nc0, SelPos ps, int wo, int col) {
+    if (col < 0) return 0.f;                      // this thread's joint is not kept by the selection at any frame
     const int ci = __ldg(e.inv + ps.t * wo + col);
     return ci >= 0 ? __ldg(e.add + (nc0 + ps.c) * e.pc + ci) : 0.f;
 }
-__device__ __forceinline__ SelPos sel_next(SelPos ps, int step, int frames) {
-    ps.t += step;
-    while (ps.t >= frames) {
+// rows advance by a constant stride: (dc, dt) = (stride / frames, stride % frames), one carry at most
+__device__ __forceinline__ SelPos sel_next(SelPos ps, int dc, int dt, int frames) {
+    ps.c += dc;
+    ps.t += dt;
+    if (ps.t >= frames) {
         ps.t -= frames;
         ++ps.c;
     }
@@ -317,21 +320,24 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
     const int rnd = epi.rnd;
     const int xstep = rs * vi, ostep = rs * wo;
     SelPos ps{0, 0};
+    int sdc = 0, sdt = 0;
     if (EPI == 2) {
         ps.c = (row0 + q) / epi.frames;
         ps.t = (row0 + q) - ps.c * epi.frames;
+        sdc = rs / epi.frames;
+        sdt = rs - sdc * epi.frames;
     }
     for (; q + 3 * rs < rows; q += 4 * rs, xp += 4 * xstep, op += 4 * ostep) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (EPI == 2) {          // the residual branch's gradient at this thread's four rows (issued before the shared-memory sums)
             a0 = sel_add(epi, nc0, ps, wo, col);
-            ps = sel_next(ps, rs, epi.frames);
+            ps = sel_next(ps, sdc, sdt, epi.frames);
             a1 = sel_add(epi, nc0, ps, wo, col);
-            ps = sel_next(ps, rs, epi.frames);
+            ps = sel_next(ps, sdc, sdt, epi.frames);
             a2 = sel_add(epi, nc0, ps, wo, col);
-            ps = sel_next(ps, rs, epi.frames);
+            ps = sel_next(ps, sdc, sdt, epi.frames);
             a3 = sel_add(epi, nc0, ps, wo, col);
-            ps = sel_next(ps, rs, epi.frames);
+            ps = sel_next(ps, sdc, sdt, epi.frames);
         }
 #pragma unroll
         for (int j = 0; j < LT; ++j) {
@@ -353,7 +359,7 @@ __device__ __forceinline__ void mix_rows(const float* __restrict__ xs, const Mix
         float a0 = 0.f;
         if (EPI == 2) {
             a0 = sel_add(epi, nc0, ps, wo, col);
-            ps = sel_next(ps, rs, epi.frames);
+            ps = sel_next(ps, sdc, sdt, epi.frames);
         }
 #pragma unroll
         for (int j = 0; j < LT; ++j) a0 = fmaf(cf[j], xp[of[j]], a0);
@@ -445,6 +451,12 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
     const int rs = wo <= AT ? AT / wo : 0;
     const bool t_active = (int)threadIdx.x < rs * wo;
     const int my_q = t_active ? (int)threadIdx.x / wo : 0, my_w = t_active ? (int)threadIdx.x - my_q * wo : 0;
+    int sel_col = my_w;                            // EPI == 2: -1 if the selection keeps this thread's joint at no frame (most joints of a coarsened graph)
+    if (EPI == 2) {
+        bool any = false;
+        for (int tt = 0; tt < epi.frames; ++tt) any = any || __ldg(epi.inv + tt * wo + my_w) >= 0;
+        if (!any) sel_col = -1;
+    }
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x, ++it) {
@@ -464,15 +476,15 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
                 float* ob = out + obase;
                 const int64_t nc0 = EPI == 2 ? nn * (ct / epi.frames) : 0;           // (sample, channel 0) row of the compact `add`
                 switch (L) {
-                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
-                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, my_w); break;
+                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
                     default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, epi, obase); break;
                 }
             }

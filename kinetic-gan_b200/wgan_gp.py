@@ -208,22 +208,25 @@ class WGANGPTrainer:
             for key in ("d_done", "g_done"):
                 if g[key] is not None:
                     torch.cuda.current_stream().wait_event(g[key])
-        if self._copy is not None and self._copy["event"] is not None:
-            torch.cuda.current_stream().wait_event(self._copy["event"])
+        if self._copy is not None:
+            for ev in self._copy["events"]:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
 
     def prefetch(self, real, labels, z, alpha=None):
         """Starts the host -> device copy of the NEXT iteration's inputs (pinned host tensors) on a copy stream, so that it overlaps the
-        iteration in flight, and returns the device tensors to hand to `iteration()` / `d_step()` (which wait for the copy).  Two staging
-        slots: a slot is rewritten only after the iteration that read it has been enqueued."""
+        iteration in flight, and returns the device tensors to hand to `iteration()` / `d_step()` (which wait for that copy).  Two staging
+        slots, each with its own completion event: a slot is rewritten only after the iteration that read it has been enqueued."""
         c = self._copy
         if c is None:
-            c = self._copy = {"stream": torch.cuda.Stream(), "slots": [None, None], "i": 0, "event": None, "ids": ()}
+            c = self._copy = {"stream": torch.cuda.Stream(), "slots": [None, None], "events": [None, None], "ids": [(), ()], "i": 0}
         c["i"] ^= 1
+        i = c["i"]
         src = {"real": real, "labels": labels, "z": z, "alpha": alpha}
         dev = self.fd.flat.device
-        slot = c["slots"][c["i"]]
+        slot = c["slots"][i]
         if slot is None or any(v is not None and (k not in slot or slot[k].shape != v.shape or slot[k].dtype != v.dtype) for k, v in src.items()):
-            slot = c["slots"][c["i"]] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items() if v is not None}
+            slot = c["slots"][i] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items() if v is not None}
         cs = c["stream"]
         cs.wait_stream(torch.cuda.current_stream())        # the slot's previous reader (two iterations back) is on the main stream
         with torch.cuda.stream(cs):
@@ -232,16 +235,22 @@ class WGANGPTrainer:
                     slot[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
-        c["event"], c["ids"] = ev, tuple(id(t) for t in slot.values())
+        c["events"][i], c["ids"][i] = ev, tuple(id(t) for t in slot.values())
         return slot["real"], slot["labels"], slot["z"], slot.get("alpha")
 
     def _await_prefetch(self, *tensors):
+        """Main stream waits for the copy that filled the staging slot these tensors belong to (no-op for other tensors)."""
         c = self._copy
-        if c is not None and c["event"] is not None and any(id(t) in c["ids"] for t in tensors if t is not None):
-            torch.cuda.current_stream().wait_event(c["event"])
+        if c is None:
+            return
+        mine = {id(t) for t in tensors if t is not None}
+        for ev, ids in zip(c["events"], c["ids"]):
+            if ev is not None and mine.intersection(ids):
+                torch.cuda.current_stream().wait_event(ev)
 
     def d_step(self, real, labels, z, alpha=None, noises=None):
         """kinetic-gan.py:137-155."""
+        self._await_prefetch(real, labels, z, alpha)
         g = self._graphs
         if g is not None and self.use_graphs and noises is None:
             st = g["static"]
@@ -270,6 +279,7 @@ class WGANGPTrainer:
 
     def g_step(self, labels, z, noises=None):
         """kinetic-gan.py:167-174.  With CUDA graphs the (labels, z) of the preceding d_step are reused, as in the reference loop."""
+        self._await_prefetch(labels, z)
         g = self._graphs
         if g is not None and self.use_graphs and noises is None:
             st = g["static"]
@@ -292,7 +302,6 @@ class WGANGPTrainer:
         return g_loss
 
     def iteration(self, i, real, labels, z, alpha=None, noises_d=None, noises_g=None):
-        self._await_prefetch(real, labels, z, alpha)
         d_loss, gp = self.d_step(real, labels, z, alpha, noises_d)
         g_loss = self.g_step(labels, z, noises_g) if i % self.n_critic == 0 else None
         return d_loss, g_loss, gp
