@@ -224,3 +224,34 @@ def test_adjmix_bwd_x_fused_epilogues(case):
     # the same result as the two-kernel formulation it replaces (scatter, then fused add) up to the order of the fp32 additions
     full = ops.plane_spmm(cu(addc), sel.T)
     assert rel(ops.adjmix_bwd_x(cu(g), cu(A), cu(addc), cu(src), sel), ops.adjmix_bwd_x(cu(g), cu(A), full, cu(src)).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 5),         # generator tail: taps shifted by an odd number of joints (scalar source loads)
+    (dict(c_in=32, c_out=3, t_in=32, v_in=11, kt=1), 13),               # 32 -> 3 channels, 352 positions: contiguous sources (16-byte loads)
+    (dict(c_in=8, c_out=6, t_in=16, v_in=12, kt=3, pad=1), 30),         # aligned shifts, 8 accumulators
+    (dict(c_in=4, c_out=2, t_in=32, v_in=12, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 30),      # strided: non-contiguous sources
+    (dict(c_in=3, c_out=3, t_in=64, v_in=25, K=3), 5),                  # channel-block taps
+    (dict(c_in=32, c_out=9, t_in=32, v_in=11, kt=1), 13),               # the generator's convolution-first graph conv (K * 3 = 9 outputs): 16 accumulators
+    (dict(c_in=6, c_out=14, t_in=16, v_in=12, kt=3, pad=1), 30),        # 14 outputs, 16 accumulators
+])
+def test_thin_four_positions_per_thread(kw, n):
+    """The small-contraction streaming kernel in its four-positions-per-thread form (planes that are multiples of 4 positions):
+    forward with every epilogue variant - bias, full and per-joint-periodic `add`, the three activations - and the data
+    gradient, against the float64 statement; fp32 FMA arithmetic (<= 1e-6)."""
+    geom = G.TapConvGeom(**kw)
+    assert (geom.t_out * geom.v_out) % 4 == 0 and n * geom.t_out * geom.v_out >= 4096
+    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    w = rnd(geom.K * geom.c_out, geom.c_in, geom.kt, 1, seed=2) / np.sqrt(geom.c_in * geom.kt * geom.K)
+    bias = rnd(geom.c_out, seed=3)
+    add = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=4)
+    addp = rnd(n, geom.c_out, 1, geom.v_out, seed=6)
+    go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
+    assert rel(ops.tapconv_fwd(cu(x), cu(w), geom.fwd), emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd)) < 1e-6
+    for act in (ops.ACT_NONE, ops.ACT_LRELU, ops.ACT_TANH):
+        got = ops.tapconv_fwd(cu(x), cu(w), geom.fwd, cu(bias), cu(add), act)
+        assert rel(got, emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd, dbl(bias), dbl(add), act)) < 1e-6, act
+    got = ops.tapconv_fwd(cu(x), cu(w), geom.fwd, cu(bias), cu(addp), ops.ACT_LRELU)
+    assert rel(got, emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd, dbl(bias), dbl(addp), ops.ACT_LRELU)) < 1e-6
+    if geom.c_in * geom.K <= 16:                                        # the data gradient is thin as well
+        assert rel(ops.tapconv_fwd(cu(go), cu(w), geom.dgrad), emu.tapconv_fwd(dbl(go), dbl(w), geom.dgrad)) < 1e-6
