@@ -370,6 +370,88 @@ static void launch_thin(const kgan_tapconv_desc& d, const float* in, const float
     tapconv_fwd_thin<CO><<<dim3((unsigned)gx, gy), NT, 0, s>>>(d, in, w, pmap, bias, add, out, ng);
 }
 
+// Weight gradient of the thinnest layers (ntap * ck * co <= 32: the 3 -> 3 channel tail of the generator).  As a GEMM the tensor-core
+// kernel pads M = 3 output channels to 128 and ran this layer at 0.2 TB/s; here a thread walks positions (lanes along positions:
+// coalesced), keeps all ntap * co * ck partial sums in registers, and the block reduces them once at the end (shuffles, shared memory,
+// one atomic per weight and block).  Exact fp32 FMA arithmetic in every precision mode.
+constexpr int TW_MAX = 32;
+static bool wgrad_is_thin(const kgan_tapconv_desc& d) {
+    return d.groups == 1 && d.w_oc_blk == 0 && d.ntap * d.ck * d.co <= TW_MAX && (int64_t)d.n * d.p_out >= 4096 &&
+           (int64_t)d.n * d.c_in_total * d.p_in < (1ll << 31) && (int64_t)d.n * d.c_out_total * d.p_out < (1ll << 31);
+}
+// TAPS / CO / CK > 0: the shape as compile-time constants (loops fully unrolled, accumulators indexed by constants); 0: any shape within
+// TW_MAX, accumulators addressed by a select chain
+template <int TAPS, int CO, int CK>
+__global__ void __launch_bounds__(NT) tapconv_wgrad_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
+                                                         const float* __restrict__ gout, const int32_t* __restrict__ pmap, float* __restrict__ dw) {
+    __shared__ float red[TW_MAX];
+    if (threadIdx.x < TW_MAX) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    float acc[TW_MAX];
+#pragma unroll
+    for (int i = 0; i < TW_MAX; ++i) acc[i] = 0.f;
+    const int total = d.n * d.p_out, cc = d.co * d.ck;
+    for (int pos = blockIdx.x * NT + threadIdx.x; pos < total; pos += gridDim.x * NT) {
+        const int nn = pos / d.p_out, p = pos - nn * d.p_out;
+        const float* gp = gout + nn * d.c_out_total * d.p_out + p;
+        const float* xn = in + nn * d.c_in_total * d.p_in;
+        if (TAPS > 0) {
+            float g[CO > 0 ? CO : 1];
+#pragma unroll
+            for (int oc = 0; oc < CO; ++oc) g[oc] = __ldg(gp + oc * d.p_out);
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int src = __ldg(pmap + d.tap_row[tap] * d.p_out + p);
+                const float* xb = xn + d.tap_in_ch[tap] * d.p_in + (src < 0 ? 0 : src);
+#pragma unroll
+                for (int ic = 0; ic < CK; ++ic) {
+                    const float x = src < 0 ? 0.f : __ldg(xb + ic * d.p_in);
+#pragma unroll
+                    for (int oc = 0; oc < CO; ++oc) acc[(tap * CO + oc) * CK + ic] = fmaf(g[oc], x, acc[(tap * CO + oc) * CK + ic]);
+                }
+            }
+            continue;
+        }
+        for (int tap = 0; tap < d.ntap; ++tap) {
+            const int src = __ldg(pmap + d.tap_row[tap] * d.p_out + p);
+            if (src < 0) continue;
+            const float* xb = xn + d.tap_in_ch[tap] * d.p_in + src;
+            for (int oc = 0; oc < d.co; ++oc) {
+                const float g = __ldg(gp + oc * d.p_out);
+                for (int ic = 0; ic < d.ck; ++ic) {
+                    const float v = g * __ldg(xb + ic * d.p_in);
+                    const int a = tap * cc + oc * d.ck + ic;
+                    // (registers are indexed by constants only after full unrolling: a select chain over the <= 32 accumulators)
+#pragma unroll
+                    for (int i = 0; i < TW_MAX; ++i) acc[i] += (i == a) ? v : 0.f;
+                }
+            }
+        }
+    }
+    const int na = d.ntap * cc;
+#pragma unroll
+    for (int i = 0; i < TW_MAX; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && i < na) atomicAdd(red + i, v);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < na) {
+        const int a = threadIdx.x, tap = a / cc, oc = (a - tap * cc) / d.ck, ic = a - tap * cc - oc * d.ck;
+        atomicAdd(dw + d.tap_w_off[tap] + w_oc_offset(d, oc) + (int64_t)ic * d.w_ic, red[a]);
+    }
+}
+static int launch_wgrad_thin(const kgan_tapconv_desc& d, const float* in, const float* gout, const int32_t* pmap, float* dw, int64_t dw_numel,
+                             int accumulate, cudaStream_t s) {
+    if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
+    int64_t gx = ceil_div64((int64_t)d.n * d.p_out, NT);
+    if (gx > 4 * kNumSMs) gx = 4 * kNumSMs;
+    if (d.ntap == 3 && d.co == 3 && d.ck == 3) tapconv_wgrad_thin<3, 3, 3><<<(unsigned)gx, NT, 0, s>>>(d, in, gout, pmap, dw);
+    else tapconv_wgrad_thin<0, 0, 0><<<(unsigned)gx, NT, 0, s>>>(d, in, gout, pmap, dw);
+    return check_launch("tapconv_wgrad (thin)");
+}
+
 static int validate(const kgan_tapconv_desc* d) {
     KGAN_REQUIRE(d != nullptr, "tapconv: null descriptor");
     KGAN_REQUIRE(d->n > 0 && d->p_in > 0 && d->p_out > 0 && d->ck > 0 && d->co > 0, "tapconv: empty dimension");
@@ -425,6 +507,7 @@ extern "C" int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, c
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad: null pointer");
     KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad: position-block groups are a forward / data-gradient feature");
     cudaStream_t s = (cudaStream_t)stream;
+    if (wgrad_is_thin(*d)) return launch_wgrad_thin(*d, in, gout, pmap, dw, dw_numel, accumulate, s);
     if (!accumulate && cudaMemsetAsync(dw, 0, sizeof(float) * dw_numel, s) != cudaSuccess) return check_launch("tapconv_wgrad memset");
     const int64_t total = (int64_t)d->n * d->p_out;
     const int tiles = d->ntap * ceil_div(d->ck, WB) * ceil_div(d->co, WB) * d->groups;
@@ -589,6 +672,7 @@ extern "C" int kgan_tapconv_wgrad_tma_ok(const kgan_tapconv_desc* d) {
 
 extern "C" int kgan_tapconv_wgrad_tf32_ok(const kgan_tapconv_desc* d) {
     if (validate(d)) return 0;
+    if (wgrad_is_thin(*d)) return 1;
     return tapconv_wgrad_tf32_eligible(*d);
 }
 
@@ -597,6 +681,7 @@ extern "C" int kgan_tapconv_wgrad_tf32(const kgan_tapconv_desc* d, const float* 
     if (int e = validate(d)) return e;
     KGAN_REQUIRE(in && gout && pmap && dw && dw_numel > 0, "tapconv_wgrad_tf32: null pointer");
     KGAN_REQUIRE(d->p_out_plane == 0, "tapconv_wgrad_tf32: position-block groups are a forward / data-gradient feature");
+    if (wgrad_is_thin(*d)) return launch_wgrad_thin(*d, in, gout, pmap, dw, dw_numel, accumulate, (cudaStream_t)stream);      // exact, and far faster than M = 128 tiles
     int r = tapconv_wgrad_tf32(*d, in, gout, pmap, dw, dw_numel, accumulate, (cudaStream_t)stream);
     if (r == -1) {
         set_error("tapconv_wgrad_tf32: shape not eligible for the tensor-core path (kgan_tapconv_wgrad_tf32_ok() == 0)");

@@ -255,3 +255,28 @@ def test_thin_four_positions_per_thread(kw, n):
     assert rel(got, emu.tapconv_fwd(dbl(x), dbl(w), geom.fwd, dbl(bias), dbl(addp), ops.ACT_LRELU)) < 1e-6
     if geom.c_in * geom.K <= 16:                                        # the data gradient is thin as well
         assert rel(ops.tapconv_fwd(cu(go), cu(w), geom.dgrad), emu.tapconv_fwd(dbl(go), dbl(w), geom.dgrad)) < 1e-6
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(c_in=3, c_out=3, t_in=64, v_in=25, kt=3, pad=1), 5),          # the generator's last temporal conv: the unrolled 3 x 3 x 3 instance
+    (dict(c_in=2, c_out=4, t_in=32, v_in=12, kt=3, pad=1), 20),         # generic instance (24 sums)
+    (dict(c_in=3, c_out=3, t_in=32, v_in=11, K=3), 13),                 # channel-block taps
+    (dict(c_in=4, c_out=2, t_in=32, v_in=12, kt=3, pad=1, t_sel=list(range(0, 32, 2))), 30),      # strided
+])
+def test_thin_weight_gradient(kw, n):
+    """Weight gradient of layers with at most 32 weights per group (register-resident partial sums, one block-level reduction), also with
+    `accumulate`, against the float64 statement - in fp32 and in tf32 mode (the kernel is exact fp32 in both)."""
+    geom = G.TapConvGeom(**kw)
+    x = rnd(n, geom.K * geom.c_in, geom.t_in, geom.v_in, seed=1)
+    go = rnd(n, geom.c_out, geom.t_out, geom.v_out, seed=5)
+    wshape = (geom.K * geom.c_out, geom.c_in, geom.kt, 1)
+    ref = emu.tapconv_wgrad(dbl(x), dbl(go), geom.fwd, wshape)
+    for mode in ("fp32", "tf32"):
+        kgan.set_precision(mode)
+        try:
+            assert rel(ops.tapconv_wgrad(cu(x), cu(go), geom.fwd, wshape), ref) < 2e-6, mode
+            acc = torch.full(wshape, 2.0, device="cuda")
+            ops.tapconv_wgrad(cu(x), cu(go), geom.fwd, wshape, out=acc)
+            assert rel(acc - 2.0, ref) < 2e-5, mode
+        finally:
+            kgan.set_precision("fp32")
