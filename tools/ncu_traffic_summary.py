@@ -16,7 +16,7 @@ from collections import defaultdict
 FAMILY = [
     (r"tapconv_fwd_build_k<(\(bool\))?(1|true)>", "gcn_fused_tf32"),
     (r"tapconv_fwd_tma_k|tapconv_fwd_umma|tapconv_fwd_build_k", "tapconv_fwd_tf32"),
-    (r"tapconv_wgrad_tma_k|tapconv_wgrad_umma", "tapconv_wgrad_tf32"),
+    (r"tapconv_wgrad_tma_k|tapconv_wgrad_umma|tapconv_wgrad_thin", "tapconv_wgrad_tf32"),
     (r"tapconv_fwd_thin|tapconv_fwd_simt", "tapconv_fwd"),
     (r"tapconv_wgrad_simt", "tapconv_wgrad"),
     (r"tapconv_pack", "tapconv_pack"),
