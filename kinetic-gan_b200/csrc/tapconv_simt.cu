@@ -196,7 +196,7 @@ constexpr int THIN_MAX_W = 1024;
 static inline int thin_merge(const kgan_tapconv_desc& d) { return (d.groups > 1 && d.g_in == 0 && d.g_pout == 0 && d.groups * d.co <= 16) ? d.groups : 1; }
 
 template <int CO>   // accumulators per thread (ng * co <= CO), CO in {4, 8, 16}
-__global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
+__global__ void __launch_bounds__(NT, 4) tapconv_fwd_thin(const __grid_constant__ kgan_tapconv_desc d, const float* __restrict__ in,
                                                        const float* __restrict__ w, const int32_t* __restrict__ pmap,
                                                        const float* __restrict__ bias, const float* __restrict__ add, float* __restrict__ out,
                                                        int ng) {
@@ -224,8 +224,27 @@ __global__ void __launch_bounds__(NT) tapconv_fwd_thin(const __grid_constant__ k
             if (src < 0) continue;
             const float* xb = xn + (int64_t)d.tap_in_ch[tap] * d.p_in + src;
             const float* wt = ws + tap * d.ck * CO;
-#pragma unroll 4
-            for (int ic = 0; ic < d.ck; ++ic) {
+            // eight channel loads in flight per thread before their FMAs, four blocks per SM (<= 64 registers): with four loads in flight and
+            // three resident blocks the kernel was bound by its bytes in flight - 465 -> 367 us on the 32-channel data gradient of the critic's
+            // first graph conv (same-box A/B, tools/thin_bench.py)
+            int ic = 0;
+            for (; ic + 8 <= d.ck; ic += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + (int64_t)(ic + u) * d.p_in);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int j4 = 0; j4 < CO / 4; ++j4) {
+                        const float4 q = *reinterpret_cast<const float4*>(wt + (ic + u) * CO + 4 * j4);
+                        acc[4 * j4 + 0] = fmaf(v[u], q.x, acc[4 * j4 + 0]);
+                        acc[4 * j4 + 1] = fmaf(v[u], q.y, acc[4 * j4 + 1]);
+                        acc[4 * j4 + 2] = fmaf(v[u], q.z, acc[4 * j4 + 2]);
+                        acc[4 * j4 + 3] = fmaf(v[u], q.w, acc[4 * j4 + 3]);
+                    }
+                }
+            }
+            for (; ic < d.ck; ++ic) {
                 const float v = __ldg(xb + (int64_t)ic * d.p_in);
 #pragma unroll
                 for (int j4 = 0; j4 < CO / 4; ++j4) {
