@@ -64,6 +64,7 @@ struct TmaPlan {
     int cps;                                      // position chunks per output plane: p_out / p_box
     int64_t groups32;                             // 32-row M groups: ceil(n / n_box) * cps
     int m_tiles, num_tiles, stages, smem_bytes;
+    int per_mt;                                   // num_tiles / m_tiles = groups * n_split
     int a_lbo, a_sbo;                             // A descriptor strides (bytes): between 32-position M groups / between 8-channel K groups
     int w_res;                                    // 1: the whole packed weight image stays resident in shared memory (loaded once per CTA)
     int w_res_bytes;
@@ -111,6 +112,7 @@ static bool make_tma_plan(const kgan_tapconv_desc& d, TmaPlan& p, int panel_ck =
     p.m_tiles = (int)ceil_div64(p.groups32, 4);
     if ((int64_t)p.m_tiles * d.groups * p.n_split > (1 << 28)) return false;
     p.num_tiles = p.m_tiles * p.n_split * d.groups;
+    p.per_mt = p.n_split * d.groups;
     const int xm = p.x3 ? 2 : 1;                                   // x3: every stage holds a lo image next to each operand image
     const int stage = xm * (A_STAGE_BYTES + p.n_cta * UK * 4);
     p.stages = TM_SMEM_BUDGET / stage;
@@ -187,10 +189,16 @@ struct TmaTile {
     int g, mt, ns;
 };
 __device__ __forceinline__ TmaTile tma_tile(int tile, const TmaPlan& pl) {
+    // (index arithmetic per tile is on the critical path of the small-channel layers - three K stages per tile: 32-bit, and none
+    // at all in the common case of one tile per position tile)
     TmaTile c;
-    const int per_mt = pl.num_tiles / pl.m_tiles;      // groups * n_split: consecutive tiles re-use the activation tile in L2
-    c.mt = tile / per_mt;
-    const int r = tile - c.mt * per_mt;
+    if (pl.per_mt == 1) {
+        c.mt = tile;
+        c.g = c.ns = 0;
+        return c;
+    }
+    c.mt = tile / pl.per_mt;                           // groups * n_split consecutive tiles re-use the activation tile in L2
+    const int r = tile - c.mt * pl.per_mt;
     c.g = r / pl.n_split;
     c.ns = r - c.g * pl.n_split;
     return c;
@@ -350,10 +358,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                 const TmaTile pc = tma_tile(t2, pl);
                 if (pc.ns != 0 || (pc.g != 0 && d.g_in == 0)) return;
                 for (int i = 0; i < 4; ++i) {
-                    const int64_t G = (int64_t)pc.mt * 4 + i;
+                    const int G = pc.mt * 4 + i;                 // (< 2^30: make_tma_plan)
                     if (G >= pl.groups32) break;
-                    const int nb = (int)(G / pl.cps);
-                    const int pp = (int)(G - (int64_t)nb * pl.cps) << pl.p_shift;
+                    const int nb = G / pl.cps;
+                    const int pp = (G - nb * pl.cps) << pl.p_shift;
                     for (int ict = 0; ict < pl.nkt; ++ict)
                         for (int tap = 0; tap < d.ntap; ++tap)
                             if ((pl.pf_taps >> tap) & 1)
@@ -369,12 +377,17 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
                 if (use_tma && pl.pf_tiles > 0 && leader && prod_idx == 0) prefetch_tile(tile + pl.pf_tiles * gridDim.x);
                 const TmaTile tc = tma_tile(tile, pl);
                 int cp[4], cn[4];                                     // box origin (position, sample) of the 4 M groups
+                {                                                     // the four groups are consecutive: one division per tile
+                    int nb = (tc.mt * 4) / pl.cps, rem = tc.mt * 4 - nb * pl.cps;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t G = (int64_t)tc.mt * 4 + i;
-                    const int nb = (int)(G / pl.cps);
-                    cp[i] = (int)(G - (int64_t)nb * pl.cps) << pl.p_shift;
-                    cn[i] = nb * pl.n_box;                            // >= n for the groups past the end: zero-filled
+                    for (int i = 0; i < 4; ++i) {
+                        cp[i] = rem << pl.p_shift;
+                        cn[i] = nb * pl.n_box;                        // >= n for the groups past the end: zero-filled
+                        if (++rem == pl.cps) {
+                            rem = 0;
+                            ++nb;
+                        }
+                    }
                 }
                 const float* wg = wp + (int64_t)tc.g * pl.nkt * d.ntap * pl.n_rows * UK;
                 const int oc_base = tc.ns * pl.n_cta;
@@ -527,11 +540,11 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
             int pq[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t G = (int64_t)tc.mt * 4 + i;
-                const int nb = (int)(G / pl.cps);
+                const int G = tc.mt * 4 + i;
+                const int nb = G / pl.cps;
                 const int nn = nb * pl.n_box + nl;
                 const bool ok = G < pl.groups32 && nn < d.n;
-                pq[i] = ok ? ((int)(G - (int64_t)nb * pl.cps) << pl.p_shift) + pl0 : -(1 << 30);
+                pq[i] = ok ? ((G - nb * pl.cps) << pl.p_shift) + pl0 : -(1 << 30);
                 base[i] = in + (int64_t)(ok ? nn : 0) * d.c_in_total * d.p_in;
                 base2[i] = pl.nkt2 ? in2 + (int64_t)(ok ? nn : 0) * pl.c2_total * pl.p_in2 : in;
             }
@@ -571,10 +584,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS_CP, 1) tapconv
         for (int tile = blockIdx.x; tile < pl.num_tiles; tile += gridDim.x, ++ti) {
             const TmaTile tc = tma_tile(tile, pl);
             const int buf = ti & 1;
-            const int64_t G = (int64_t)tc.mt * 4 + quarter;
-            const int nb = (int)(G / pl.cps);
+            const int G = tc.mt * 4 + quarter;
+            const int nb = G / pl.cps;
             const int nn = nb * pl.n_box + (lane >> pl.p_shift);
-            const int pv = ((int)(G - (int64_t)nb * pl.cps) << pl.p_shift) + (lane & (pl.p_box - 1));
+            const int pv = ((G - nb * pl.cps) << pl.p_shift) + (lane & (pl.p_box - 1));
             const bool valid = G < pl.groups32 && nn < d.n;
             const int po = valid ? pv : 0, nv = valid ? nn : 0;
             const int out_ch0 = tc.g * d.g_out, oc_base = tc.ns * pl.n_cta;
