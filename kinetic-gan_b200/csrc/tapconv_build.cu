@@ -57,6 +57,7 @@ struct BuildPlan {
     int small;                                    // 1: tile = spt whole planes, 0: tpp tiles of 128 rows per plane
     int spt, tpp;
     int m_tiles, num_tiles;
+    int per_mt;                                   // num_tiles / m_tiles = groups * n_split
     int bspan, nbox, nseg;                        // box extent (positions), boxes per staged tile (1 / 2), samples per staged tile
     int chan_stride;                              // floats between channels inside one box image: nseg * bspan
     int box_floats;                               // 32 * chan_stride
@@ -117,6 +118,7 @@ static bool make_build_plan(const kgan_tapconv_desc& d, BuildPlan& p) {
     }
     if ((int64_t)p.m_tiles * d.groups * p.n_split > (1 << 28)) return false;
     p.num_tiles = p.m_tiles * p.n_split * d.groups;
+    p.per_mt = p.n_split * d.groups;
     p.nbox = d.stage_span <= 256 ? 1 : 2;
     p.bspan = p.nbox == 1 ? d.stage_span : round_up(ceil_div(d.stage_span, 2), 4);
     if (p.bspan > 256 || p.nseg > 256) return false;
@@ -216,9 +218,13 @@ struct BdTile {
 };
 __device__ __forceinline__ BdTile bd_tile(int tile, const BuildPlan& pl) {
     BdTile c;
-    const int per_mt = pl.num_tiles / pl.m_tiles;      // groups * n_split: consecutive tiles re-use the staged activations in L2
-    c.mt = tile / per_mt;
-    const int r = tile - c.mt * per_mt;
+    if (pl.per_mt == 1) {                              // (per-tile index arithmetic is on the critical path of small tiles: see tapconv_tma.cu)
+        c.mt = tile;
+        c.g = c.ns = 0;
+        return c;
+    }
+    c.mt = tile / pl.per_mt;                           // groups * n_split consecutive tiles re-use the staged activations in L2
+    const int r = tile - c.mt * pl.per_mt;
     c.g = r / pl.n_split;
     c.ns = r - c.g * pl.n_split;
     return c;
