@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
     __syncthreads();
 
     auto issue = [&](int64_t tile, int buf) {      // one thread: ki contiguous ranges of this tile -> shared memory
-        const int64_t nn = tile / pl.tiles_per_n;
+        const int64_t nn = (int)tile / pl.tiles_per_n;       // (tiles < 2^31: checked by the launcher; a 64-bit division per tile and thread is ~150 instructions)
         const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
         const int rows = min(R, ct - q0);
         const uint32_t bytes = (uint32_t)rows * vi * 4u;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
         const int buf = it & 1;
         const int64_t next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < pl.tiles) issue(next, buf ^ 1);                  // buffer buf^1 was released by the barrier below
-        const int64_t nn = tile / pl.tiles_per_n;
+        const int64_t nn = (int)tile / pl.tiles_per_n;       // (tiles < 2^31: checked by the launcher; a 64-bit division per tile and thread is ~150 instructions)
         const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
         const int rows = min(R, ct - q0);
         am_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(AT) adjmix_bwd_a2_k(const float* __restrict__ 
     }
     __syncthreads();
     auto issue = [&](int64_t tile, int buf) {
-        const int64_t nn = tile / pl.tiles_per_n;
+        const int64_t nn = (int)tile / pl.tiles_per_n;       // (tiles < 2^31: checked by the launcher; a 64-bit division per tile and thread is ~150 instructions)
         const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
         const int rows = min(R, ct - q0);
         const uint32_t bar = bar0 + 8 * buf;
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(AT) adjmix_bwd_a2_k(const float* __restrict__ 
         const int buf = it & 1;
         const int64_t next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < pl.tiles) issue(next, buf ^ 1);
-        const int64_t nn = tile / pl.tiles_per_n;
+        const int64_t nn = (int)tile / pl.tiles_per_n;       // (tiles < 2^31: checked by the launcher; a 64-bit division per tile and thread is ~150 instructions)
         const int q0 = (int)(tile - nn * pl.tiles_per_n) * R;
         const int rows = min(R, ct - q0);
         am_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
@@ -663,7 +663,7 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
             if (R > 1024) R = 1024;
             if (R >= ct) R = (ct + 3) / 4 * 4;
             else R = (ceil_div(ct, ceil_div(ct, R)) + 7) / 8 * 8;   // equal tiles: no sliver at the end of a sample
-            if (R >= 8 && (int64_t)R * wo < (1 << 20) && (int64_t)R * vi * ki < (1 << 20)) {
+            if (R >= 8 && (int64_t)R * wo < (1 << 20) && (int64_t)R * vi * ki < (1 << 20) && (int64_t)n * ceil_div(ct, R) < (1ll << 31)) {
                 pl.R = R;
                 pl.tiles_per_n = ceil_div(ct, R);
                 pl.tiles = (int64_t)n * pl.tiles_per_n;
@@ -742,7 +742,7 @@ extern "C" int kgan_adjmix_bwd_a_masked(const float* x, const float* g, const fl
         if (R > 1024) R = 1024;
         if (R >= ct64) R = (int)((ct64 + 3) / 4 * 4);
         else R = (int)((ceil_div64(ct64, ceil_div64(ct64, R)) + 7) / 8 * 8);
-        if (R >= 8 && k * v * w <= DA_EPT * AT) {
+        if (R >= 8 && k * v * w <= DA_EPT * AT && (int64_t)n * ceil_div64(ct64, R) < (1ll << 31)) {
             DA2Plan pl;
             pl.R = R;
             pl.tiles_per_n = (int)ceil_div64(ct64, R);

@@ -25,7 +25,7 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-def adjacency(k, v, w, nnz_per_col=3, seed=0):
+def adjacency(k, v, w, nnz_per_col=1, seed=0):
     rng = np.random.default_rng(seed)
     A = np.zeros((k, v, w), np.float32)
     for kk in range(k):
