@@ -658,7 +658,11 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
         // in the pipelined kernel: one barrier round trip per 384-byte tile made that launch 123 us at 32 GB/s; the plain kernel serves them)
         if (k <= 4 && wo <= AT && ((int64_t)ct * vi) % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (int64_t)ct * vi * ki >= 2048) {
             Mix2Plan pl;
-            int R = (24 * 1024) / (ki * vi * 4);                 // <= 24 KB per stage: 4 CTAs (2 stages each) per SM
+            // <= 24 KB per stage: 4 CTAs (2 stages each) per SM; the forward product where it writes more than it reads (K partitions out
+            // of one input) runs 9-12 % faster with 12 KB stages and 6 CTAs per SM, everything else slower (same-box sweep of 12 / 16 / 24 / 32 KB,
+            // tools/adjmix_bench.py)
+            const int stage_bytes = (MODE == 0 && ko * wo > vi) ? 12 * 1024 : 24 * 1024;
+            int R = stage_bytes / (ki * vi * 4);
             R = R / 8 * 8;
             if (R > 1024) R = 1024;
             if (R >= ct) R = (ct + 3) / 4 * 4;
