@@ -213,6 +213,13 @@ int kgan_tapconv_wgrad(const kgan_tapconv_desc* d, const float* in, const float*
  * because gcn.conv has bias=False, tgcn.py:44,55).  A is (K, V, W) - rectangular so that upsample_s
  * (generator.py:185-200) can be folded into it. */
 int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
+/* The same product with a by-product: out2[n, c, q] = x[n, c, sidx[q]], q < pc - x gathered at the plane positions sidx (int32, t * v
+ * indexed) - the input of the critic block's residual branch (x[..., keep] at every other frame, discriminator.py:132-134), written from
+ * the tile the product has staged in shared memory instead of by a gather kernel that reads x from HBM again.
+ * kgan_adjmix_fwd_sel_ok(...) == 1 when the pipelined plan takes the shape with whole channel planes per tile. */
+int kgan_adjmix_fwd_sel_ok(const float* x, int n, int c, int t, int v, int w, int k);
+int kgan_adjmix_fwd_sel(const float* x, const float* A, const int32_t* sidx, int pc, float* out, float* out2, int n, int c, int t, int v, int w,
+                        int k, int out_tf32, void* stream);
 /* gx[r, v] = sum_k sum_w gout[r, k, w] * A[k, v, w] */
 int kgan_adjmix_bwd_x(const float* gout, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream);
 /* Same with a fused epilogue - the join of a critic block's backward (discriminator.py:128-136 differentiated):

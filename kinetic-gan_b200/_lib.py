@@ -53,6 +53,8 @@ _SIGS = {
     "kgan_adjmix_fwd": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x_fused": ([_F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_adjmix_fwd_sel_ok": ([_F, _I, _I, _I, _I, _I, _I], C.c_int),
+    "kgan_adjmix_fwd_sel": ([_F, _F, _F, _I, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_x_fused_sel": ([_F, _F, _F, _F, _I, _F, _F, _I, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a": ([_F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_adjmix_bwd_a_masked": ([_F, _F, _F, _F, _I, _I, _I, _I, _I, _I, _V], C.c_int),

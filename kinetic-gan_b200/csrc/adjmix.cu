@@ -85,6 +85,11 @@ struct MixEpi {
     int rnd;
     const int32_t* inv = nullptr;
     int pc = 0, frames = 0;      // compact plane size; frames per channel (rows of the output are (channel, frame) pairs)
+    // forward product with a selection by-product (kgan_adjmix_fwd_sel, EPI == 3): out2[n, c, q] = x[n, c, sidx[q]], q < pc - the input of the
+    // block's residual branch (x at every other frame / the kept joints), written from the staged tile instead of by a gather kernel
+    // that reads x from HBM a second time.  Tiles hold whole channel planes (R % frames == 0).
+    const int32_t* sidx = nullptr;
+    float* out2 = nullptr;
 };
 __device__ __forceinline__ float mix_fin(float v, const MixEpi& e, int64_t idx, int wo = 0) {
     if (e.add) {
@@ -458,6 +463,7 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
         if (!any) sel_col = -1;
     }
 
+    constexpr int ME = EPI == 3 ? 0 : EPI;          // the selection by-product (EPI 3) is a loop of its own: the product itself has no epilogue
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -476,17 +482,25 @@ __global__ void __launch_bounds__(AT, 4) adjmix_rowmix2_k(const float* __restric
                 float* ob = out + obase;
                 const int64_t nc0 = EPI == 2 ? nn * (ct / epi.frames) : 0;           // (sample, channel 0) row of the compact `add`
                 switch (L) {
-                    case 0: mix_rows<0, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 1: mix_rows<1, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 2: mix_rows<2, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 3: mix_rows<3, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 4: mix_rows<4, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 5: mix_rows<5, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 6: mix_rows<6, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 7: mix_rows<7, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
-                    case 8: mix_rows<8, EPI>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 0: mix_rows<0, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 1: mix_rows<1, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 2: mix_rows<2, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 3: mix_rows<3, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 4: mix_rows<4, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 5: mix_rows<5, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 6: mix_rows<6, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 7: mix_rows<7, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
+                    case 8: mix_rows<8, ME>(xs, el, ob, my_q, rs, rows, vi, wo, epi, obase, nc0, q0, sel_col); break;
                     default: mix_rows_any(xs, el, L, ob, my_q, rs, rows, vi, wo, epi, obase); break;
                 }
+            }
+        }
+        if (EPI == 3) {
+            const int c0 = q0 / epi.frames, total = (rows / epi.frames) * epi.pc;       // whole channel planes: rows % frames == 0
+            float* o2 = epi.out2 + (nn * (ct / epi.frames) + c0) * (int64_t)epi.pc;
+            for (int i = threadIdx.x; i < total; i += AT) {
+                const int cl = i / epi.pc, qc = i - cl * epi.pc;
+                o2[i] = xs[cl * epi.frames * vi + __ldg(epi.sidx + qc)];
             }
         }
         __syncthreads();                                                                // every read of xs[buf] is done
@@ -640,7 +654,8 @@ static int check_shape(const char* what, int n, int c, int t, int v, int w, int 
 using namespace kgan;
 
 template <int MODE>
-static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, MixEpi epi, void* stream) {
+static int launch_rowmix(const char* what, const float* in, const float* A, float* out, int n, int c, int t, int v, int w, int k, MixEpi epi, void* stream,
+                         bool dry = false) {      // dry: no launch - 0 if the selection by-product (epi.out2) has a plan, 1 if not
     KGAN_REQUIRE(n > 0 && c > 0 && t > 0 && v > 0 && w > 0 && k > 0, "%s: empty dimension", what);
     const int64_t ct64 = (int64_t)c * t;
     KGAN_REQUIRE(ct64 * (MODE == 0 ? w : v) < (1ll << 31) && ct64 * k * w < (1ll << 31), "%s: plane too large", what);
@@ -649,7 +664,9 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
     const size_t smem = (size_t)((nlists + 3) & ~3) * 4 + (size_t)k * v * w * sizeof(MixEntry);
     KGAN_REQUIRE(smem <= 200 * 1024, "%s: V=%d, W=%d, K=%d do not fit in shared memory", what, v, w, k);
     static SmemAttrOnce attr;
-    if (int e = ensure_smem(adjmix_rowmix_k<MODE>, 200 * 1024, attr, "adjmix attribute")) return e;
+    if (!dry)
+        if (int e = ensure_smem(adjmix_rowmix_k<MODE>, 200 * 1024, attr, "adjmix attribute")) return e;
+    const bool want_sel = MODE == 0 && (epi.out2 != nullptr || dry);
     // bulk-copy pipelined kernel whenever every row block is 16-byte addressable
     {
         const int vi = MODE == 0 ? v : w, ki = MODE == 0 ? 1 : k;
@@ -667,6 +684,10 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
             if (R > 1024) R = 1024;
             if (R >= ct) R = (ct + 3) / 4 * 4;
             else R = (ceil_div(ct, ceil_div(ct, R)) + 7) / 8 * 8;   // equal tiles: no sliver at the end of a sample
+            if (want_sel) {                                         // whole channel planes per tile
+                R = R >= t ? R / t * t : t;
+                if ((R & 3) || (int64_t)R * vi * 4 > 32 * 1024) R = 0;
+            }
             if (R >= 8 && (int64_t)R * wo < (1 << 20) && (int64_t)R * vi * ki < (1 << 20) && (int64_t)n * ceil_div(ct, R) < (1ll << 31)) {
                 pl.R = R;
                 pl.tiles_per_n = ceil_div(ct, R);
@@ -677,6 +698,7 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
                 const size_t smem2 = (size_t)2 * pl.in_floats * 4 + 16 + 16 + (size_t)((nlists + 3) & ~3) * 4 + (size_t)nlists * pl.lc_max * sizeof(MixEntry);
                 pl.smem_bytes = (int)smem2;
                 if (smem2 <= 100 * 1024) {
+                    if (dry) return 0;
                     static SmemAttrOnce attr2, attr3;
                     if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 0>, 100 * 1024, attr2, "adjmix attribute")) return e;
                     if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 1>, 100 * 1024, attr3, "adjmix attribute")) return e;
@@ -684,7 +706,11 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
                     const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm);
                     const int64_t waves = ceil_div64(pl.tiles, cap);
                     const int64_t grid2 = ceil_div64(pl.tiles, waves);   // every CTA gets `waves` tiles (+-1), all CTAs co-resident
-                    if (epi.add && epi.inv) {
+                    if (want_sel) {
+                        static SmemAttrOnce attr5;
+                        if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 3>, 100 * 1024, attr5, "adjmix attribute")) return e;
+                        adjmix_rowmix2_k<MODE, 3><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
+                    } else if (epi.add && epi.inv) {
                         static SmemAttrOnce attr4;
                         if (int e = ensure_smem(adjmix_rowmix2_k<MODE, 2>, 100 * 1024, attr4, "adjmix attribute")) return e;
                         adjmix_rowmix2_k<MODE, 2><<<(unsigned)grid2, AT, smem2, (cudaStream_t)stream>>>(in, A, out, ct, v, w, k, pl, epi);
@@ -695,6 +721,8 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
             }
         }
     }
+    if (dry) return 1;
+    KGAN_REQUIRE(!want_sel, "%s: no plan for the selection by-product (kgan_adjmix_fwd_sel_ok() == 0)", what);
     const int chunks = (int)ceil_div64((int64_t)ct * wo, AT * 4);
     const int64_t items = (int64_t)n * ko * chunks;
     const int64_t grid = items < 8 * kNumSMs ? items : 8 * kNumSMs;
@@ -705,6 +733,22 @@ static int launch_rowmix(const char* what, const float* in, const float* A, floa
 extern "C" int kgan_adjmix_fwd(const float* x, const float* A, float* out, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {
     KGAN_REQUIRE(x && A && out, "adjmix_fwd: null pointer");
     return launch_rowmix<0>("adjmix_fwd", x, A, out, n, c, t, v, w, k, MixEpi{nullptr, nullptr, out_tf32}, stream);
+}
+
+extern "C" int kgan_adjmix_fwd_sel_ok(const float* x, int n, int c, int t, int v, int w, int k) {
+    if (!x || n <= 0 || c <= 0 || t <= 0 || v <= 0 || w <= 0 || k <= 0 || (int64_t)c * t * v >= (1ll << 31) || (int64_t)c * t * k * w >= (1ll << 31)) return 0;
+    return launch_rowmix<0>("adjmix_fwd_sel", x, nullptr, nullptr, n, c, t, v, w, k, MixEpi{nullptr, nullptr, 0}, nullptr, true) == 0 ? 1 : 0;
+}
+
+extern "C" int kgan_adjmix_fwd_sel(const float* x, const float* A, const int32_t* sidx, int pc, float* out, float* out2, int n, int c, int t, int v, int w,
+                                   int k, int out_tf32, void* stream) {
+    KGAN_REQUIRE(x && A && out && out2 && sidx && pc > 0, "adjmix_fwd_sel: null pointer");
+    MixEpi epi{nullptr, nullptr, out_tf32};
+    epi.sidx = sidx;
+    epi.out2 = out2;
+    epi.pc = pc;
+    epi.frames = t;
+    return launch_rowmix<0>("adjmix_fwd_sel", x, A, out, n, c, t, v, w, k, epi, stream);
 }
 
 extern "C" int kgan_adjmix_bwd_x(const float* g, const float* A, float* gx, int n, int c, int t, int v, int w, int k, int out_tf32, void* stream) {

@@ -350,15 +350,20 @@ class GcnRes(Function):
         # (the caller decides - grad mode is always off INSIDE a Function's forward - and passes fused_geom only then: wants_fused_gcn())
         if fused_geom is not None:
             g = ops.gcn_fused_fwd(x, A, _c(w_gcn), fused_geom, out_table)
+        xs = None
         if g is None:
-            xa = ops.adjmix_fwd(x, A)
+            if sel is not None:
+                xa, xs = ops.adjmix_fwd(x, A, sel)             # the residual branch's input as a by-product of the same kernel
+            else:
+                xa = ops.adjmix_fwd(x, A)
             if out_table is not None:
                 g = ops.tapconv_fwd_scatter(xa, _c(w_gcn), gcn_geom.fwd, out_table)
             if g is None:
                 g = ops.tapconv_fwd(xa, _c(w_gcn), gcn_geom.fwd)
                 if out_table is not None:
                     g = ops.plane_spmm(g, out_table)
-        xs = x if sel is None else ops.plane_spmm(x, sel)
+        if xs is None:
+            xs = x if sel is None else ops.plane_spmm(x, sel)
         r = ops.tapconv_fwd(xs, _c(w_res), res_geom.fwd, b_res) if w_res is not None else xs
         ctx.save_for_backward(x, A, w_gcn, w_res)
         ctx.xa, ctx.xs = xa, (xs if w_res is not None else None)

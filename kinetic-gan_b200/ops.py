@@ -391,13 +391,28 @@ def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     return dw
 
 
-def adjmix_fwd(x, A):
+def adjmix_fwd(x, A, sel=None):
+    """`sel` (optional selection PlaneTable with inverse_gather()): also returns plane_spmm(x, sel) - written by the same kernel from the
+    tile it has staged (kgan_adjmix_fwd_sel) - as a second result; (out, None) when that by-product has no plan for the shape."""
     _chk(x, A)
     n, c, t, v = x.shape
     k, v2, w = A.shape
     assert v2 == v
     out = torch.empty((n, k * c, t, w), device=x.device, dtype=torch.float32)
     _shape_sig(x, A)
+    if sel is not None:
+        l = _lib.lib()
+        ok = sel.__dict__.setdefault("_fwd_sel_ok", {})
+        key = (n, c, t, v, w, k, x.data_ptr() & 15)
+        if key not in ok:
+            ok[key] = sel.inverse_gather() is not None and sel.p_in == t * v and bool(l.kgan_adjmix_fwd_sel_ok(x.data_ptr(), n, c, t, v, w, k))
+        if not ok[key]:
+            return adjmix_fwd(x, A), None
+        xs = torch.empty((n, c, sel.t_out, sel.v_out), device=x.device, dtype=torch.float32)
+        _io(x, A, out, xs)
+        _run('adjmix', 0.0, l.kgan_adjmix_fwd_sel, x.data_ptr(), A.data_ptr(), sel.on(x.device)[0].data_ptr(), sel.p_out, out.data_ptr(), xs.data_ptr(),
+             n, c, t, v, w, k, _rnd(), _stream())
+        return out, xs
     _io(x, A, out)
     _run('adjmix', 0.0, _lib.lib().kgan_adjmix_fwd, x.data_ptr(), A.data_ptr(), out.data_ptr(), n, c, t, v, w, k, _rnd(), _stream())
     return out

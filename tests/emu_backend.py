@@ -88,10 +88,11 @@ def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     return dw.view(w_shape)
 
 
-def adjmix_fwd(x, A):
+def adjmix_fwd(x, A, sel=None):
     n, c, t, v = x.shape
     k, _, w = A.shape
-    return torch.einsum("nctv,kvw->nkctw", x, A).reshape(n, k * c, t, w)
+    out = torch.einsum("nctv,kvw->nkctw", x, A).reshape(n, k * c, t, w)
+    return out if sel is None else (out, plane_spmm(x, sel))
 
 
 def adjmix_bwd_x(g, A, add=None, mask_src=None, add_sel=None):

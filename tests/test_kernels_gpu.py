@@ -280,3 +280,24 @@ def test_thin_weight_gradient(kw, n):
             assert rel(acc - 2.0, ref) < 2e-5, mode
         finally:
             kgan.set_precision("fp32")
+
+
+@pytest.mark.parametrize("case", [
+    # (n, c, t, v, w, k, frame step, kept joints)
+    (5, 64, 64, 12, 5, 3, 2, [1, 4, 6, 9, 11]),       # D2: several whole channel planes per tile
+    (6, 128, 32, 5, 5, 3, 2, [0, 1, 2, 3, 4]),        # D3: ragged last tile (still whole planes)
+    (9, 256, 16, 5, 1, 3, 2, [2]),                    # D4: one kept joint
+    (3, 8, 64, 12, 12, 3, 1, [0, 3, 7]),              # joints only
+])
+def test_adjmix_fwd_with_selection_byproduct(case):
+    """kgan_adjmix_fwd_sel: the adjacency product and, from the same staged tile, the residual branch's input x[:, :, t_sel][..., keep] ==
+    the product kernel and the gather kernel run one after the other (bit for bit: both are copies / the same sums)."""
+    n, c, t, v, w, k, step, keep = case
+    x = rnd(n, c, t, v, seed=1)
+    A = sparse_adjacency(k, v, w, 2)
+    sel = kgan.geometry.select_table(t, v, list(range(0, t, step)), keep)
+    out, xs = ops.adjmix_fwd(cu(x), cu(A), sel)
+    assert xs is not None, "no plan for the by-product at a shape of the critic"
+    assert torch.equal(out, ops.adjmix_fwd(cu(x), cu(A)))
+    assert torch.equal(xs, ops.plane_spmm(cu(x), sel))
+    assert rel(out, emu.adjmix_fwd(dbl(x), dbl(A))) < TOL
