@@ -88,6 +88,10 @@ static bool make_wgrad_tma_plan(const kgan_tapconv_desc& d, WgradTmaPlan& p) {
     p.a_bytes = p.a_rows * p.row_bytes;
     p.b_bytes = p.n_ic * p.row_bytes;
     p.sub_bytes = p.a_bytes + d.ntap * p.b_bytes;
+    // thin layers (few channels: a 32-position K tile is only 10-16 KB): 2 or 4 K tiles per stage, up to 32 KB - the per-stage work
+    // (barrier round trips, expect_tx, commit) is per stage, not per byte
+    if (!p.x3)
+        while (p.nsub * p.p_box < 128 && 2 * p.nsub * p.sub_bytes <= 32 * 1024) p.nsub *= 2;
     const int stage = p.nsub * p.sub_bytes * (p.x3 ? 2 : 1);
     const int tail_pad = p.sub_bytes < UM * p.row_bytes ? UM * p.row_bytes - p.sub_bytes : 0;
     p.tail_pad = tail_pad;
