@@ -2,7 +2,7 @@
 
     KGAN_NCU_RANGE=1 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
         --profile-from-start off --csv --log-file gpurun_out/traffic.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline
-    python tools/ncu_traffic_summary.py gpurun_out/traffic.csv 1024 [iterations in the range: KGAN_NCU_STEPS, default 5] > profiles/rN_traffic_b1024.json
+    python tools/ncu_traffic_summary.py gpurun_out/traffic.csv 1024 [shape, default ntu120] [iterations in the range: KGAN_NCU_STEPS, default 5] > profiles/rN_traffic_b1024.json
 
 KGAN_NCU_RANGE=1 makes bench.py bracket the eager roofline pass (one n_critic cycle: 5 iterations) with cudaProfilerStart/Stop,
 so the capture holds exactly the launches that `roofline.algorithmic_bytes_per_launch` averages over.  Families are the ones
@@ -70,7 +70,7 @@ def main():
         a["us"] += d.get("us", 0.0)
     total_us = sum(a["us"] for a in fam.values())
     out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over the eager "
-                     "roofline pass of bench.py (%s iterations)" % (sys.argv[3] if len(sys.argv) > 3 else "5") + "; per-launch times are cold-cache and serialised",
+                     "roofline pass of bench.py (%s iterations)" % (sys.argv[4] if len(sys.argv) > 4 else "5") + "; per-launch times are cold-cache and serialised",
            "per_gpu_batch": int(sys.argv[2]) if len(sys.argv) > 2 else None, "shape": sys.argv[3] if len(sys.argv) > 3 else "ntu120", "launches": len(per_id), "total_us": total_us, "families": {}}
     for k, a in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
         n = a["launches"]
