@@ -1,5 +1,8 @@
+"""Adjacency product + selection gather as two kernels vs the fused by-product (kgan_adjmix_fwd_sel): python tools/sel_bench.py"""
 import sys
-sys.path.insert(0, "/root/repo")
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 import kgan_b200 as kgan
 ops, G = kgan.ops, kgan.geometry
