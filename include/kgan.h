@@ -285,6 +285,11 @@ int kgan_bn_stats(const float* x, float* mean, float* rstd, float* running_mean,
 /* y = (x - mean[c]) * rstd[c] * gamma[c] + beta[c]  (also eval mode with running stats folded by the caller) */
 int kgan_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
                   int n, int c, int p, int out_tf32, void* stream);
+/* Training-mode BatchNorm, residual add, NoiseInjection and activation of a generator block in ONE pass (generator.py:160,176-182):
+ *   out = act( (a - mean[c]) * rstd[c] * gamma[c] + beta[c]  +  b  +  nw[c] * noise[n, 0, p] ),   mean / rstd from kgan_bn_stats;
+ * b, (nw, noise) optional.  Replaces kgan_bn_apply followed by kgan_epilogue_fwd (one read and one write of the tensor less). */
+int kgan_bn_epilogue_fwd(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* b,
+                         const float* nw, const float* noise, float* out, int n, int c, int p, int act, int out_tf32, void* stream);
 /* gx, ggamma[c], gbeta[c] of training-mode BN */
 int kgan_bn_bwd(const float* gy, const float* x, const float* mean, const float* rstd, const float* gamma, float* gx,
                 float* ggamma, float* gbeta, int n, int c, int p, int out_tf32, float* workspace, void* stream);

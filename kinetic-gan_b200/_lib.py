@@ -68,6 +68,7 @@ _SIGS = {
     "kgan_bn_workspace": ([_I, _I], C.c_int64),
     "kgan_bn_stats": ([_F, _F, _F, _F, _F, _I, _I, _I, C.c_float, C.c_float, _F, _V], C.c_int),
     "kgan_bn_apply": ([_F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _V], C.c_int),
+    "kgan_bn_epilogue_fwd": ([_F, _F, _F, _F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _V], C.c_int),
     "kgan_bn_bwd": ([_F, _F, _F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _F, _V], C.c_int),
     "kgan_adam_step": ([_F, _F, _F, _F, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _V], C.c_int),
     "kgan_interpolate": ([_F, _F, _F, _F, _I, C.c_int64, _I, _V], C.c_int),

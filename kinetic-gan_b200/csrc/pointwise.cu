@@ -37,15 +37,28 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // pointwise epilogues
 // ------------------------------------------------------------------------------------------------
 // one warp per (n, c) plane: per-plane constants, 16-byte accesses when the plane allows, no per-element index arithmetic
+// `bn` (kgan_bn_epilogue_fwd): a is normalised first - a' = (a - mean[c]) * rstd[c] * gamma[c] + beta[c], training-mode BatchNorm with the
+// batch statistics of kgan_bn_stats - so that BatchNorm, residual add, noise injection and activation of a generator block
+// (generator.py:160,176-182) are ONE pass over the tensor
+struct BnArgs {
+    const float *mean, *rstd, *gamma, *beta;
+};
 __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                                                       const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
-                                                      int n, int c, int p, int act, int vec, int rnd) {
+                                                      int n, int c, int p, int act, int vec, int rnd, BnArgs bn = BnArgs{nullptr, nullptr, nullptr, nullptr}) {
     const int lane = threadIdx.x & 31;
     const int64_t planes = (int64_t)n * c, tw = (int64_t)gridDim.x * (PT / 32);
     for (int64_t pl = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5); pl < planes; pl += tw) {
         const int64_t nn = pl / c;
         const int cc = (int)(pl - nn * c);
-        const float bs = bias ? __ldg(bias + cc) : 0.f, wn = nw ? __ldg(nw + cc) : 0.f;
+        float bs = bias ? __ldg(bias + cc) : 0.f;
+        const float wn = nw ? __ldg(nw + cc) : 0.f;
+        float sc = 1.f, mu = 0.f;
+        if (bn.mean) {                           // same expression as kgan_bn_apply: (a - mean) * (rstd * gamma) + beta
+            mu = __ldg(bn.mean + cc);
+            sc = __ldg(bn.rstd + cc) * __ldg(bn.gamma + cc);
+            bs += __ldg(bn.beta + cc);
+        }
         const int64_t o = pl * p, on = nn * p;
         if (vec) {
             const float4* ap = reinterpret_cast<const float4*>(a + o);
@@ -54,11 +67,11 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
             float4* op = reinterpret_cast<float4*>(out + o);
             for (int i = lane; i < (p >> 2); i += 32) {
                 float4 v = ap[i];
+                v.x = fmaf(v.x - mu, sc, bs), v.y = fmaf(v.y - mu, sc, bs), v.z = fmaf(v.z - mu, sc, bs), v.w = fmaf(v.w - mu, sc, bs);
                 if (b) {
                     const float4 t = bp[i];
                     v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
                 }
-                v.x += bs, v.y += bs, v.z += bs, v.w += bs;
                 if (nw) {
                     const float4 z = __ldg(zp + i);
                     v.x = fmaf(wn, z.x, v.x), v.y = fmaf(wn, z.y, v.y), v.z = fmaf(wn, z.z, v.z), v.w = fmaf(wn, z.w, v.w);
@@ -68,9 +81,8 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
             }
         } else {
             for (int i = lane; i < p; i += 32) {
-                float v = a[o + i];
+                float v = fmaf(a[o + i] - mu, sc, bs);
                 if (b) v += b[o + i];
-                v += bs;
                 if (nw) v = fmaf(wn, __ldg(noise + on + i), v);
                 out[o + i] = tf32_out(apply_act(v, act), rnd);
             }
@@ -82,11 +94,13 @@ __global__ void __launch_bounds__(PT) epilogue_fwd_k(const float* __restrict__ a
 // element, consecutive threads on consecutive addresses; the warp-per-plane kernel above would leave 31 / 28 / 12 lanes idle
 __global__ void __launch_bounds__(PT) epilogue_fwd_small_k(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                                                             const float* __restrict__ nw, const float* __restrict__ noise, float* __restrict__ out,
-                                                            unsigned total, unsigned c, unsigned p, int act, int rnd) {
+                                                            unsigned total, unsigned c, unsigned p, int act, int rnd,
+                                                            BnArgs bn = BnArgs{nullptr, nullptr, nullptr, nullptr}) {
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const unsigned pl = e / p, pp = e - pl * p;
         const unsigned nn = pl / c, cc = pl - nn * c;
         float v = a[e];
+        if (bn.mean) v = fmaf(v - __ldg(bn.mean + cc), __ldg(bn.rstd + cc) * __ldg(bn.gamma + cc), __ldg(bn.beta + cc));
         if (b) v += b[e];
         if (bias) v += __ldg(bias + cc);
         if (nw) v = fmaf(__ldg(nw + cc), __ldg(noise + nn * p + pp), v);
@@ -566,6 +580,21 @@ extern "C" int kgan_epilogue_fwd(const float* a, const float* b, const float* bi
     else
         epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, bias, nw, noise, out, n, c, p, act, vec, out_tf32);
     return check_launch("epilogue_fwd");
+}
+
+extern "C" int kgan_bn_epilogue_fwd(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* b,
+                                    const float* nw, const float* noise, float* out, int n, int c, int p, int act, int out_tf32, void* stream) {
+    KGAN_REQUIRE(a && mean && rstd && gamma && beta && out && n > 0 && c > 0 && p > 0, "bn_epilogue_fwd: bad argument");
+    KGAN_REQUIRE((nw == nullptr) == (noise == nullptr), "bn_epilogue_fwd: nw and noise go together");
+    const BnArgs bn{mean, rstd, gamma, beta};
+    const int vec = (p & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(noise) |
+                                      reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (p < 32 && (int64_t)n * c * p < (1ll << 31))
+        epilogue_fwd_small_k<<<grid_for((int64_t)n * c * p), PT, 0, (cudaStream_t)stream>>>(a, b, nullptr, nw, noise, out, (unsigned)((int64_t)n * c * p),
+                                                                                          (unsigned)c, (unsigned)p, act, out_tf32, bn);
+    else
+        epilogue_fwd_k<<<grid_for((int64_t)n * c, PT / 32, 8), PT, 0, (cudaStream_t)stream>>>(a, b, nullptr, nw, noise, out, n, c, p, act, vec, out_tf32, bn);
+    return check_launch("bn_epilogue_fwd");
 }
 
 extern "C" int kgan_act_bwd(const float* gout, const float* out, float* gz, int64_t numel, int act, int out_tf32, void* stream) {

@@ -593,6 +593,33 @@ class BatchNormTrain(Function):
         return gx, gg, gb, None, None, None, None
 
 
+class BnNoiseAct(Function):
+    """act(BatchNorm_train(z) + r + nw[c] * noise): normalisation with the batch statistics, residual add, NoiseInjection and the
+    activation of a generator block (generator.py:160,176-182) as the statistics kernel + ONE pass over the tensor
+    (kgan_bn_epilogue_fwd) instead of a normalise pass and a noise / activation pass.  First-order backward (as BatchNormTrain)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, eps, momentum, r, noise, nw, act):
+        z = _c(z)
+        mean, rstd = ops.bn_stats(z, running_mean, running_var, eps, momentum)
+        out = ops.bn_epilogue_fwd(z, mean, rstd, gamma, beta, None if r is None else _c(r), _c(nw.reshape(-1)), _c(noise), act)
+        ctx.save_for_backward(z, mean, rstd, gamma, out, noise)
+        ctx.act, ctx.nw_shape = act, nw.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        z, mean, rstd, gamma, out, noise = ctx.saved_tensors
+        g = ops.act_bwd(_c(go), out, ctx.act) if ctx.act != ACT_NONE else _c(go)
+        nig = ctx.needs_input_grad
+        gz = gg = gb = None
+        if nig[0] or nig[1] or nig[2]:
+            gz, gg, gb = ops.bn_bwd(g, z, mean, rstd, gamma)
+        gnw = ops.chan_reduce(g, noise).view(ctx.nw_shape) if nig[9] else None
+        return gz, gg, gb, None, None, None, None, (g if nig[7] else None), None, gnw, None
+
+
 class BatchNormEval(Function):
     """nn.BatchNorm2d in eval mode (generate.py:67): affine map with the running statistics."""
 

@@ -237,8 +237,18 @@ class st_gcn(nn.Module):
             z = KF.TapConvEp.apply(g, fold["tcn"][0], fold["tcn"][1], None, tcn, KF.ACT_NONE)
         else:
             z = KF.TapConvEp.apply(g, self.tcn[0].weight, self.tcn[0].bias, None, tcn, KF.ACT_NONE)
-            if self._bn:
-                z = self._batch_norm(self.tcn[1], z)
+            bn = self.tcn[1] if self._bn else None
+            if bn is not None and bn.training:
+                # batch statistics, then normalise + residual + noise + activation in one pass (functional.BnNoiseAct)
+                if noise is None:
+                    noise = torch.randn(z.size(0), 1, z.size(2), z.size(3), device=z.device)
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                out = KF.BnNoiseAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, r, noise, self.noise.weight,
+                                          KF.ACT_TANH if self.tan else KF.ACT_LRELU)
+                return out, A
+            if bn is not None:
+                z = self._batch_norm(bn, z)
         if noise is None:
             noise = torch.randn(z.size(0), 1, z.size(2), z.size(3), device=z.device)
         out = KF.NoiseAct.apply(z, r, noise, self.noise.weight, KF.ACT_TANH if self.tan else KF.ACT_LRELU)

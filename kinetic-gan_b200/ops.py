@@ -553,6 +553,17 @@ def bn_apply(x, mean, rstd, gamma, beta):
     return y
 
 
+def bn_epilogue_fwd(x, mean, rstd, gamma, beta, b=None, nw=None, noise=None, act=ACT_NONE):
+    """act(bn_apply(x, ...) + b + nw[c] * noise) in one pass (kgan_bn_epilogue_fwd)."""
+    _chk(x, mean, rstd, gamma, beta, b, nw, noise)
+    n, c, t, v = x.shape
+    out = torch.empty_like(x)
+    _io(x, b, noise, out)
+    _run('batchnorm', 0.0, _lib.lib().kgan_bn_epilogue_fwd, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(b),
+         _ptr(nw), _ptr(noise), out.data_ptr(), n, c, t * v, act, _rnd(), _stream())
+    return out
+
+
 def bn_bwd(gy, x, mean, rstd, gamma):
     _chk(gy, x, mean, rstd, gamma)
     n, c, t, v = x.shape

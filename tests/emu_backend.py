@@ -180,6 +180,10 @@ def bn_apply(x, mean, rstd, gamma, beta):
     return (x - v(mean)) * v(rstd) * v(gamma) + v(beta)
 
 
+def bn_epilogue_fwd(x, mean, rstd, gamma, beta, b=None, nw=None, noise=None, act=0):
+    return epilogue_fwd(bn_apply(x, mean, rstd, gamma, beta), b, None, nw, noise, act)
+
+
 def bn_bwd(gy, x, mean, rstd, gamma):
     v = lambda t: t.view(1, -1, 1, 1)
     xh = (x - v(mean)) * v(rstd)
@@ -204,7 +208,7 @@ def interpolate(alpha, x, y):
 
 
 NAMES = ["tapconv_fwd", "tapconv_fwd_res", "gcn_fused_fwd", "tapconv_fwd_scatter", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
-         "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_bwd", "adam_step",
+         "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_epilogue_fwd", "bn_bwd", "adam_step",
          "interpolate"]
 
 
