@@ -163,6 +163,14 @@ int kgan_gcn_fwd_tf32(const kgan_tapconv_desc* d, const float* x, const float* w
  * time-unfolded layout of the strided temporal conv" (geometry.UnfoldedTcnGeom.unfold via kgan_plane_spmm): the unfolded tensor is written
  * by the convolution's epilogue, the intermediate and the copy kernel disappear.  d->groups == 1, no `add`.
  * kgan_tapconv_scatter_ok(d) == 1 when eligible (TMA-fed plan). */
+/* The tap convolution with the generator's NoiseInjection in its epilogue - the eval-mode generator block (generator.py:168-182 with the
+ * BatchNorm folded into the weights) as ONE kernel:
+ *     out = act( conv_d(in) + bias + add + nw[oc] * noise[n, 0, p] )        noise: (n, 1, T, V), nw: (C_out)
+ * Runs on the operand-building kernel (the generator's planes of 5 / 11 / 25 joints); kgan_tapconv_noise_ok(d) == 1 when eligible
+ * (tf32 mode, groups == 1, no TMA-fed plan for d). */
+int kgan_tapconv_noise_ok(const kgan_tapconv_desc* d);
+int kgan_tapconv_fwd_tf32_noise(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                                const float* noise, const float* nw, float* out, void* stream);
 int kgan_tapconv_scatter_ok(const kgan_tapconv_desc* d);
 int kgan_tapconv_fwd_tf32_scatter(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* omap, const float* bias,
                                   float* out, void* stream);

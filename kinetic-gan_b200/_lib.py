@@ -43,6 +43,8 @@ _SIGS = {
     "kgan_tapconv_scatter_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_fwd_tf32_scatter": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_res_ok": ([C.POINTER(TapConvDesc), C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_noise_ok": ([C.POINTER(TapConvDesc)], C.c_int),
+    "kgan_tapconv_fwd_tf32_noise": ([C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_fwd_tf32_res": ([C.POINTER(TapConvDesc), _F, _F, C.POINTER(TapConvDesc), _F, _F, _F, _F, _F, _V], C.c_int),
     "kgan_tapconv_tma_ok": ([C.POINTER(TapConvDesc)], C.c_int),
     "kgan_tapconv_staged_ok": ([C.POINTER(TapConvDesc)], C.c_int),

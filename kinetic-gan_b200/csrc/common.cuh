@@ -101,6 +101,8 @@ int tapconv_tma_scatter_eligible(const kgan_tapconv_desc& d);
 
 // operand-building variant (tapconv_build.cu): raw activations staged by TMA, tap operands gathered in shared memory through the position map
 int tapconv_build_eligible(const kgan_tapconv_desc& d);
+int tapconv_fwd_build_noise(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                            const float* noise, const float* nw, float* out, cudaStream_t stream);
 int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
                       float* out, cudaStream_t stream);
 

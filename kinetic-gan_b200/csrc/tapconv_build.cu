@@ -230,10 +230,12 @@ __device__ __forceinline__ BdTile bd_tile(int tile, const BuildPlan& pl) {
     return c;
 }
 
-template <int ACT, bool SCAT = false>
+// NZ: + nw[column] * nz, nz = this row's element of a one-channel noise tensor (the generator's NoiseInjection, generator.py:12-19)
+template <int ACT, bool SCAT = false, bool NZ = false>
 __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int colpar, bool valid, float* __restrict__ op, int p_out,
                                                  const float* __restrict__ ap, int64_t astride, const float* __restrict__ bp, int lane,
-                                                 uint32_t tfull_bar, uint32_t tfull_parity, int rnd, int d1 = 0, int dz = 0) {
+                                                 uint32_t tfull_bar, uint32_t tfull_parity, int rnd, int d1 = 0, int dz = 0, float nz = 0.f,
+                                                 const float* __restrict__ nwp = nullptr) {
     bool waited = false;
     for (int col0 = 16 * colpar; col0 < ncols; col0 += 16 * (BD_EPI_WARPS / 4)) {
         const int nc = min(16, ncols - col0);                         // warp-uniform
@@ -243,6 +245,7 @@ __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int 
             for (int j = 0; j < 16; ++j) av[j] = ldg_pred(ap + (int64_t)(col0 + j) * astride, valid && j < nc);
         }
         const float bl = (bp && lane < nc) ? __ldg(bp + col0 + lane) : 0.f;
+        const float nl = (NZ && lane < nc) ? __ldg(nwp + col0 + lane) : 0.f;
         if (!waited) {
             mbar_wait(tfull_bar, tfull_parity);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -254,6 +257,7 @@ __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             float val = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+            if (NZ) val = fmaf(__shfl_sync(0xffffffffu, nl, j), nz, val);
             if (ap) val += av[j];
             if (ACT == KGAN_ACT_LRELU) val = val > 0.f ? val : 0.2f * val;
             if (ACT == KGAN_ACT_TANH) val = tanhf(val);
@@ -270,12 +274,15 @@ __device__ __forceinline__ void bd_epilogue_tile(uint32_t taddr, int ncols, int 
     }
 }
 
-template <bool MIX>
+// NZ: the instantiation with the noise term in the epilogue (kgan_tapconv_fwd_tf32_noise); `adj` then points to the noise tensor (n, 1, plane)
+// and `nw` to the per-channel noise weights.  A separate instantiation: extra epilogue variants cost the main ones registers (tapconv_tma.cu).
+template <bool MIX, bool NZ = false>
 __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __grid_constant__ kgan_tapconv_desc d, const __grid_constant__ BuildPlan pl,
                                                                      const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wp,
                                                                      const int32_t* __restrict__ pmap, const float* __restrict__ bias,
                                                                      const float* __restrict__ add, float* __restrict__ out,
-                                                                     const float* __restrict__ adj, const int32_t* __restrict__ omap) {
+                                                                     const float* __restrict__ adj, const int32_t* __restrict__ omap,
+                                                                     const float* __restrict__ nw = nullptr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
@@ -661,6 +668,12 @@ __global__ void __launch_bounds__(BD_THREADS, 1) tapconv_fwd_build_k(const __gri
             if (16 * colpar >= ncols) {                               // no columns for this warp: it still has to observe the barrier
                 mbar_wait(tbar, tpar);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            } else if (NZ) {
+                const float nz = valid ? __ldg(adj + (int64_t)nv * d.p_out + pv) : 0.f;       // noise[n, 0, position]
+                const float* nwp = nw + out_ch0 + oc_base;
+                if (d.act == KGAN_ACT_LRELU) bd_epilogue_tile<KGAN_ACT_LRELU, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, 0, 0, nz, nwp);
+                else if (d.act == KGAN_ACT_TANH) bd_epilogue_tile<KGAN_ACT_TANH, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, 0, 0, nz, nwp);
+                else bd_epilogue_tile<KGAN_ACT_NONE, false, true>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd, 0, 0, nz, nwp);
             } else if (omap) bd_epilogue_tile<KGAN_ACT_NONE, true>(taddr, ncols, colpar, valid, op, pst, nullptr, astride, bp, lane, tbar, tpar, rnd, d1, dz);
             else if (d.act == KGAN_ACT_LRELU) bd_epilogue_tile<KGAN_ACT_LRELU>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
             else if (d.act == KGAN_ACT_TANH) bd_epilogue_tile<KGAN_ACT_TANH>(taddr, ncols, colpar, valid, op, pst, ap, astride, bp, lane, tbar, tpar, rnd);
@@ -683,7 +696,7 @@ int tapconv_build_eligible(const kgan_tapconv_desc& d) {
 }
 
 static int launch_build(const kgan_tapconv_desc& d, BuildPlan& p, const float* in, const float* wp, const int32_t* pmap, const float* bias,
-                        const float* add, float* out, const float* adj, cudaStream_t stream, const int32_t* omap = nullptr) {
+                        const float* add, float* out, const float* adj, cudaStream_t stream, const int32_t* omap = nullptr, const float* nw = nullptr) {
     CUtensorMap tmap;
     const uint64_t gdim[3] = {(uint64_t)d.p_in, (uint64_t)d.n, (uint64_t)d.c_in_total};
     const uint64_t gstr[2] = {(uint64_t)d.c_in_total * d.p_in * 4, (uint64_t)d.p_in * 4};
@@ -691,6 +704,12 @@ static int launch_build(const kgan_tapconv_desc& d, BuildPlan& p, const float* i
     if (int e = tma_encode_3d_f32(&tmap, in, gdim, gstr, box, 4)) return e;
     static SmemAttrOnce attr0, attr1;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    if (nw) {                                                       // noise term in the epilogue: `adj` carries the noise tensor
+        static SmemAttrOnce attr2;
+        if (int e = ensure_smem(tapconv_fwd_build_k<false, true>, 227 * 1024, attr2, "tapconv_fwd_build (noise) attribute")) return e;
+        tapconv_fwd_build_k<false, true><<<grid, BD_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, pmap, bias, add, out, adj, omap, nw);
+        return check_launch("tapconv_fwd_build (noise)");
+    }
     if (p.mix) {
         if (int e = ensure_smem(tapconv_fwd_build_k<true>, 227 * 1024, attr1, "gcn_fwd attribute")) return e;
         tapconv_fwd_build_k<true><<<grid, BD_THREADS, p.smem_bytes, stream>>>(d, p, tmap, wp, pmap, bias, add, out, adj, omap);
@@ -718,6 +737,16 @@ int tapconv_fwd_build(const kgan_tapconv_desc& d, const float* in, const float* 
     if (d.mix_v > 0 || !make_build_plan(d, p)) return -1;
     if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
     return launch_build(d, p, in, wp, pmap, bias, add, out, nullptr, stream);
+}
+
+// The tap convolution with the generator's noise term in its epilogue: out = act(conv(in) + bias + add + nw[oc] * noise[n, 0, p]) - the
+// eval-mode generator block (BatchNorm folded into the weights) as one kernel.  -1: not eligible (no operand-building plan)
+int tapconv_fwd_build_noise(const kgan_tapconv_desc& d, const float* in, const float* wp, const int32_t* pmap, const float* bias, const float* add,
+                            const float* noise, const float* nw, float* out, cudaStream_t stream) {
+    BuildPlan p;
+    if (d.mix_v > 0 || d.p_out_plane != 0 || d.add_period != 0 || !make_build_plan(d, p)) return -1;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return -1;
+    return launch_build(d, p, in, wp, pmap, bias, add, out, noise, stream, nullptr, nw);
 }
 
 }  // namespace kgan

@@ -619,6 +619,25 @@ extern "C" int kgan_tapconv_fwd_tf32(const kgan_tapconv_desc* d, const float* in
     return r;
 }
 
+extern "C" int kgan_tapconv_noise_ok(const kgan_tapconv_desc* d) {
+    if (validate(d) || tapconv_is_thin(*d) || d->precision != KGAN_PREC_TF32 || d->groups != 1 || d->add_period != 0 || d->p_out_plane != 0) return 0;
+    if (d->tma_mode != 0 && tapconv_tma_eligible(*d)) return 0;      // the TMA-fed kernel + a separate noise pass is the faster pair there
+    return tapconv_tf32_packed_numel(*d) > 0 && tapconv_build_eligible(*d);
+}
+
+extern "C" int kgan_tapconv_fwd_tf32_noise(const kgan_tapconv_desc* d, const float* in, const float* wp, const int32_t* pmap, const float* bias,
+                                           const float* add, const float* noise, const float* nw, float* out, void* stream) {
+    if (int e = validate(d)) return e;
+    KGAN_REQUIRE(in && wp && pmap && noise && nw && out, "tapconv_fwd_tf32_noise: null pointer");
+    KGAN_REQUIRE(d->groups == 1, "tapconv_fwd_tf32_noise: groups");
+    const int r = tapconv_fwd_build_noise(*d, in, wp, pmap, bias, add, noise, nw, out, (cudaStream_t)stream);
+    if (r == -1) {
+        set_error("tapconv_fwd_tf32_noise: not eligible (kgan_tapconv_noise_ok() == 0)");
+        return 1;
+    }
+    return r;
+}
+
 extern "C" int kgan_gcn_fused_ok(const kgan_tapconv_desc* d) {
     if (validate(d) || d->mix_v <= 0) return 0;
     return tapconv_tf32_packed_numel(*d) > 0 && tapconv_build_eligible(*d);

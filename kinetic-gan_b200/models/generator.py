@@ -233,7 +233,17 @@ class st_gcn(nn.Module):
             r = KF.TapConvEp.apply(x, self.residual[0].weight, self.residual[0].bias, None, res, KF.ACT_NONE)
             r = self._batch_norm(self.residual[1], r)
         g, A = self.gcn(x, A, self._support(x.device))
-        if "tcn" in fold:
+        if "tcn" in fold and not torch.is_grad_enabled():
+            # inference (BatchNorm folded, no autograd graph): temporal conv + bias + residual + noise + activation as ONE kernel where the
+            # layer runs on the operand-building kernel (kgan_tapconv_fwd_tf32_noise); None: not eligible, the two passes below
+            if noise is None:
+                noise = torch.randn(g.size(0), 1, self.up_t, g.size(3), device=g.device)
+            out = KF.ops.tapconv_fwd_noise(KF._c(g), fold["tcn"][0], tcn.fwd, KF._c(noise), KF._c(self.noise.weight.reshape(-1)), fold["tcn"][1],
+                                           None if r is None else KF._c(r), KF.ACT_TANH if self.tan else KF.ACT_LRELU)
+            if out is not None:
+                return out, A
+            z = KF.TapConvEp.apply(g, fold["tcn"][0], fold["tcn"][1], None, tcn, KF.ACT_NONE)
+        elif "tcn" in fold:
             z = KF.TapConvEp.apply(g, fold["tcn"][0], fold["tcn"][1], None, tcn, KF.ACT_NONE)
         else:
             z = KF.TapConvEp.apply(g, self.tcn[0].weight, self.tcn[0].bias, None, tcn, KF.ACT_NONE)

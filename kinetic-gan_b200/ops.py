@@ -340,6 +340,31 @@ def tapconv_fwd_scatter(x, w, desc, table):
     return out
 
 
+def tapconv_fwd_noise(x, w, desc, noise, nw, bias=None, add=None, act=ACT_NONE):
+    """act(conv_desc(x, w) + bias + add + nw[c] * noise) as one kernel (kgan_tapconv_fwd_tf32_noise) - the eval-mode generator block.
+    Returns None when not eligible (fp32 modes, layers the TMA-fed kernel takes): the caller then runs convolution and noise pass separately."""
+    if _precision != PREC_TF32:
+        return None
+    _chk(x, w, noise, nw, bias, add)
+    n = x.shape[0]
+    l = _lib.lib()
+    cs = desc.cstruct(n, act, _precision)
+    ok = desc.__dict__.setdefault("_noise_ok", {})
+    if n not in ok:
+        ok[n] = bool(l.kgan_tapconv_noise_ok(cs))
+    if not ok[n]:
+        return None
+    wp = _packed_weights(w, desc, cs, l)
+    if wp is None:
+        return None
+    out = torch.empty((n, desc.c_out_total, desc.t_out, desc.v_out), device=x.device, dtype=torch.float32)
+    assert tuple(noise.shape) == (n, 1, desc.t_out, desc.v_out) and nw.numel() == desc.c_out_total and (add is None or add.shape == out.shape)
+    _io(x, w, bias, add, noise, out)
+    _run('tapconv_fwd_tf32', _tap_flops(desc, n), l.kgan_tapconv_fwd_tf32_noise, cs, x.data_ptr(), wp.data_ptr(), desc.pmap_on(x.device).data_ptr(),
+         _ptr(bias), _ptr(add), noise.data_ptr(), nw.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=ACT_NONE):
     """act(conv_desc(x, w) + bias + conv_desc2(x2, w2) + bias2) - a tap convolution with a fused residual 1x1 convolution of a second
     tensor (kgan_tapconv_fwd_tf32_res: one accumulator, the residual never visits HBM).  Returns None when the pair is not eligible

@@ -58,6 +58,10 @@ def tapconv_fwd(x, w, desc, bias=None, add=None, act=0):
     return out.view(n, desc.c_out_total, desc.t_out, desc.v_out)
 
 
+def tapconv_fwd_noise(x, w, desc, noise, nw, bias=None, add=None, act=0):
+    return None          # the emulation always takes the two-pass formulation (same arithmetic)
+
+
 def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=0):
     return tapconv_fwd(x, w, desc, bias, tapconv_fwd(x2, w2, desc2, bias2), act)
 
@@ -207,7 +211,7 @@ def interpolate(alpha, x, y):
     return a * x + (1 - a) * y
 
 
-NAMES = ["tapconv_fwd", "tapconv_fwd_res", "gcn_fused_fwd", "tapconv_fwd_scatter", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
+NAMES = ["tapconv_fwd", "tapconv_fwd_noise", "tapconv_fwd_res", "gcn_fused_fwd", "tapconv_fwd_scatter", "tapconv_wgrad", "adjmix_fwd", "adjmix_bwd_x", "adjmix_bwd_a", "epilogue_fwd", "act_bwd",
          "chan_reduce", "plane_spmm", "plane_sum_t", "label_concat", "label_split", "bn_stats", "bn_apply", "bn_epilogue_fwd", "bn_bwd", "adam_step",
          "interpolate"]
 

@@ -146,3 +146,25 @@ def test_fused_gcn_with_scatter_store(c_in, c_out, t, v, w, n):
     assert got is not None
     want = emu.plane_spmm(emu.tapconv_fwd(emu.adjmix_fwd(x.double(), A.double()), wt.double(), two.fwd), unf)
     assert rel(got, want) < TOL
+
+
+@pytest.mark.parametrize("c,t,v,n,act", [(32, 32, 11, 24, ops.ACT_LRELU), (64, 16, 11, 40, ops.ACT_LRELU), (128, 8, 5, 60, ops.ACT_LRELU), (32, 64, 25, 6, ops.ACT_TANH)])
+def test_generator_block_with_noise_epilogue(c, t, v, n, act):
+    """kgan_tapconv_fwd_tf32_noise: the eval-mode generator block (generator.py:168-182, BatchNorm folded) - temporal conv + bias + residual +
+    noise_weight * noise + activation - as one launch of the operand-building kernel, against the float64 statement and against the two-pass
+    formulation (convolution, then the noise / activation pass)."""
+    geom = G.TapConvGeom(c, c, t, v, kt=3, pad=1)
+    g, r = rnd(n, c, t, v, seed=1), rnd(n, c, t, v, seed=2)
+    noise = rnd(n, 1, t, v, seed=3)
+    w = rnd(c, c, 3, 1, seed=4) / np.sqrt(3 * c)
+    b, nw = rnd(c, seed=5), rnd(c, seed=6)
+    got = ops.tapconv_fwd_noise(g.cuda(), w.cuda(), geom.fwd, noise.cuda(), nw.cuda(), b.cuda(), r.cuda(), act)
+    assert got is not None, "no plan for a shape of the generator"
+    z = emu.tapconv_fwd(g.double(), w.double(), geom.fwd, b.double())
+    want = emu.epilogue_fwd(z, r.double(), None, nw.double(), noise.double(), act)
+    assert rel(got, want) < TOL
+    two = ops.epilogue_fwd(ops.tapconv_fwd(g.cuda(), w.cuda(), geom.fwd, b.cuda()), r.cuda(), None, nw.cuda(), noise.cuda(), act)
+    assert rel(got, two.cpu()) < 6e-4
+    # without residual
+    got = ops.tapconv_fwd_noise(g.cuda(), w.cuda(), geom.fwd, noise.cuda(), nw.cuda(), b.cuda(), None, act)
+    assert rel(got, emu.epilogue_fwd(z, None, None, nw.double(), noise.double(), act)) < TOL
