@@ -52,7 +52,24 @@ bool tapconv_umma_nsplit(const kgan_tapconv_desc& d, int* n_cta, int* n_split, i
     // small terms (lo * W_hi + x * W_lo) sits beside the main one in TMEM, both double-buffered: 4 * n_cta <= 512 columns
     const bool x3 = d.precision == KGAN_PREC_TF32X3;
     int split = ceil_div(n16, x3 ? 128 : 256);
-    while (m_tiles * d.groups * split < kNumSMs && ceil_div(n16, split * 2) >= 64) split *= 2;
+    if (m_tiles * d.groups * split < kNumSMs) {
+        // fewer tiles than SMs: split the channels further - every tile streams its 128 rows of activations plus its n_cta rows of
+        // weights per K step, and the launch takes ceil(tiles / SMs) waves of them: take the split that minimises waves * (128 + n_cta)
+        // (the mapping network's 4096 x 632 x 632 layers: 4 splits of 160 channels = 128 tiles in one wave, not 6 x 112 = 192 in two)
+        int best = split;
+        int64_t best_cost = INT64_MAX;
+        for (int s2 = split; s2 <= 16 * split; ++s2) {
+            const int nc = round_up(ceil_div(n16, s2), 16);
+            if (nc < 64 && s2 > split) break;
+            const int64_t tiles = m_tiles * d.groups * ceil_div(n16, nc);
+            const int64_t cost = ceil_div64(tiles, kNumSMs) * (UM + nc);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = s2;
+            }
+        }
+        split = best;
+    }
     *n_cta = round_up(ceil_div(n16, split), 16);
     *n_split = ceil_div(n16, *n_cta);
     *n_rows = *n_cta * *n_split;
