@@ -186,7 +186,8 @@ def test_properties_at_baseline_batch():
 
 
 def test_properties_at_bench_size_tf32():
-    """Size-independent properties at the bench's own size (BASELINE configs[2]: NTU-120 mlp8, per-GPU batch 1024, tf32 path):
+    """Size-independent properties at a bench size (BASELINE configs[2]: NTU-120 mlp8, per-GPU batch 1024 - the batch of round 1's bench
+    line; the default is 4096 now, where the same plans run on four times the tiles - tf32 path):
     (1) adjoint identities <F(x, w), g> = <x, Dgrad(g, w)> = <w, Wgrad(x, g)> on the largest layers (the three kernels must be
     transposes of one another whatever the tiling); (2) the critic treats samples independently (a batch equals its slices);
     (3) one full WGAN-GP iteration through the CUDA-graph trainer leaves finite losses, finite parameters and a tanh-bounded
