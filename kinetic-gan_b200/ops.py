@@ -223,13 +223,19 @@ def repack_weights(flat):
         e.epoch, e.version, e.used = ep, (w._version if w is not None else -1), False
 
 
-def _packed_weights(w, desc, cs, l):
+def _packed_weights(w, desc, cs, l, cache_image=True):
+    """`cache_image=False`: `w` is not a weight but a tensor of the step (see _linear_wgrad): always packed afresh - the address of a recycled
+    activation buffer says nothing about its contents."""
     cache = desc.__dict__.setdefault("_tf32_numel", {})       # eligibility / image size depend on the batch size too
     numel = cache.get((cs.n, cs.precision))
     if numel is None:
         numel = cache[(cs.n, cs.precision)] = int(l.kgan_tapconv_tf32_workspace(cs))
     if numel <= 0:
         return None
+    if not cache_image:
+        wp = torch.empty(numel, device=w.device, dtype=torch.float32)
+        _run('tapconv_pack', 0.0, l.kgan_tapconv_pack_tf32, cs, w.data_ptr(), wp.data_ptr(), _stream())
+        return wp
     if isinstance(w, torch.nn.Parameter):
         key = (w.data_ptr(), id(desc), numel)
         e = _persist.get(key)
@@ -392,6 +398,35 @@ def tapconv_fwd_res(x, w, desc, x2, w2, desc2, bias=None, bias2=None, act=ACT_NO
     return out
 
 
+_LINEAR_T = {}
+
+
+def _linear_wgrad(x, gout, desc, dw, acc):
+    """Weight gradient of a Linear layer (one-position planes), dW[oc, ic] = sum_n gout[n, oc] * x[n, ic], on the tensor-core FORWARD kernel:
+    it is the tap convolution of the one-sample tensor x viewed as (1, N channels, C_in positions) with gout as the weight matrix
+    (W[oc][n] = gout[n, oc]: strides (1, C_out)), whose output (1, C_out, C_in positions) IS dW; `acc`: dW is also the `add` operand.
+    (The weight-gradient kernels contract over positions, of which these layers have one: they ran the FMA kernel at 0.1 TB/s.)
+    None: not eligible."""
+    from .geometry import TapDesc
+    import numpy as np
+    n, c_in, c_out = x.shape[0], desc.ck, desc.co
+    key = (n, c_in, c_out, desc.c_out_total)
+    dt = _LINEAR_T.get(key)
+    if dt is None:
+        dt = _LINEAR_T[key] = TapDesc(c_in_total=n, p_in=c_in, c_out_total=c_out, p_out=c_in, ntap=1, ck=n, co=c_out, groups=1, g_in=0, g_out=0, g_w=0,
+                                      w_oc=1, w_ic=desc.c_out_total, tap_in_ch=[0], tap_w_off=[0], tap_row=[0],
+                                      pmap=np.arange(c_in, dtype=np.int32).reshape(1, c_in), t_out=1, v_out=c_in)
+    l = _lib.lib()
+    cs = dt.cstruct(1, ACT_NONE, _precision)
+    wp = _packed_weights(gout, dt, cs, l, cache_image=False)
+    if wp is None:
+        return None
+    _io(x, gout, dw)
+    _run('tapconv_wgrad_tf32', 2.0 * n * c_in * c_out, l.kgan_tapconv_fwd_tf32, cs, x.data_ptr(), wp.data_ptr(), dt.pmap_on(x.device).data_ptr(), 0,
+         dw.data_ptr() if acc else 0, dw.data_ptr(), _stream())
+    return dw
+
+
 def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     """`out` (optional): a contiguous fp32 tensor of the weight's shape that the result is ADDED to (the flat gradient view of
     the parameter) instead of being returned in a fresh tensor - the kernels accumulate with atomics anyway."""
@@ -402,6 +437,12 @@ def tapconv_wgrad(x, gout, desc, w_shape, out=None):
     assert tuple(dw.shape) == tuple(w_shape)
     l = _lib.lib()
     cs = desc.cstruct(n, ACT_NONE, _precision)
+    if (_precision == PREC_TF32 and desc.p_in == 1 and desc.p_out == 1 and desc.ntap == 1 and desc.groups == 1 and desc.tap_in_ch[0] == 0
+            and desc.ck == desc.c_in_total and desc.co == desc.c_out_total and desc.ck % 4 == 0 and desc.w_oc == desc.ck and desc.w_ic == 1
+            and desc.tap_w_off[0] == 0 and n >= 512 and desc.co >= 16):
+        r = _linear_wgrad(x, gout, desc, dw, acc)
+        if r is not None:
+            return r
     _io(x, gout, dw)
     if _precision != PREC_FP32:
         ok = desc.__dict__.setdefault("_tf32_wgrad_ok", {})

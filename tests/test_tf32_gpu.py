@@ -205,3 +205,24 @@ def test_tapconv_scatter_store(c_in, c_out, t, v, n):
     two = ops.plane_spmm(ops.tapconv_fwd(x.cuda(), w.cuda(), geom.fwd), unf)
     assert torch.equal(got, two)
     assert rel(got, emu.plane_spmm(emu.tapconv_fwd(x.double(), w.double(), geom.fwd), unf)) < TOL
+
+
+@pytest.mark.parametrize("c_in,c_out,n", [(632, 632, 4096), (632, 1536, 2048), (512, 512, 1024), (572, 572, 600)])
+def test_linear_weight_gradient_on_the_forward_kernel(c_in, c_out, n):
+    """Weight gradient of a Linear layer in tf32 mode: dW = gout^T x computed by the tensor-core FORWARD kernel on the transposed problem
+    (x as a one-sample tensor of N channels, gout as the weight matrix) - against the float64 statement, with and without `accumulate`,
+    and the launch is a tensor-core one."""
+    geom = G.TapConvGeom(c_in=c_in, c_out=c_out, t_in=1, v_in=1)
+    x, go = rnd(n, c_in, 1, 1, seed=1), rnd(n, c_out, 1, 1, seed=2)
+    ref = emu.tapconv_wgrad(x.double(), go.double(), geom.fwd, (c_out, c_in, 1, 1))
+    prof = ops.profile_start()
+    try:
+        dw = ops.tapconv_wgrad(x.cuda(), go.cuda(), geom.fwd, (c_out, c_in, 1, 1))
+        acc = torch.full((c_out, c_in, 1, 1), 3.0, device="cuda")
+        ops.tapconv_wgrad(x.cuda(), go.cuda(), geom.fwd, (c_out, c_in, 1, 1), out=acc)
+    finally:
+        ops.profile_stop(prof)
+    fams = [p[0] for p in prof]
+    assert fams.count("tapconv_wgrad_tf32") == 2 and "tapconv_wgrad" not in fams, fams
+    assert rel(dw, ref) < TOL
+    assert rel(acc - 3.0, ref) < TOL
